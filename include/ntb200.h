@@ -1,0 +1,161 @@
+/* ntb200.h — C ABI of libntb200.so, the B200 (sm_100a) backend for the training step of
+ * ZouJiu1/numpy_transformer.
+ *
+ * The reference has no FFI: its "plugin API" is the duck-typed Python layer protocol
+ * forward/backward/update/setzero/save_model/restore_model.  Each entry point
+ * below is what the host-side mirror of one reference method binds through ctypes; the
+ * reference method it replaces is cited as file:line (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; nt_last_error() gives the text.
+ *   - all tensor arguments are DEVICE pointers to dense row-major fp32 unless stated otherwise;
+ *     index tensors are int32.  Host pointers appear only in nt_h2d / nt_d2h.
+ *   - work is enqueued on the library's single compute stream; nothing synchronises except
+ *     nt_d2h, nt_sync and nt_event_elapsed_ms.  All ops are CUDA-graph capturable.
+ *   - "accumulates" means += into the destination (the reference's *_delta buffers, which
+ *     live until setzero()).
+ */
+#ifndef NTB200_H
+#define NTB200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- runtime */
+int nt_init(int device);                 /* select device, create the compute stream (idempotent) */
+int nt_shutdown(void);
+const char* nt_last_error(void);
+int nt_device_count(int* n);
+int nt_sm_count(int* n);
+int nt_malloc(void** dptr, size_t bytes);   /* stream-ordered size-class pool over cudaMalloc */
+int nt_free(void* dptr);
+int nt_pool_bytes(size_t* reserved);
+int nt_host_alloc(void** hptr, size_t bytes);   /* pinned host memory for the e2e path */
+int nt_host_free(void* hptr);
+int nt_h2d(void* dst, const void* src, size_t bytes);
+int nt_d2h(void* dst, const void* src, size_t bytes);     /* synchronises the stream */
+int nt_d2h_async(void* dst, const void* src, size_t bytes);
+int nt_d2d(void* dst, const void* src, size_t bytes);
+int nt_memset(void* dst, int value, size_t bytes);
+int nt_sync(void);
+int nt_stream_handle(void** cuda_stream);
+int nt_event_create(void** ev);
+int nt_event_record(void* ev);
+int nt_event_elapsed_ms(void* ev0, void* ev1, float* ms);  /* synchronises on ev1 */
+int nt_event_destroy(void* ev);
+/* CUDA-graph capture of whatever is enqueued between begin and end (one step of the trainer
+ * loop transformer_of_image.py:141-159 / gpt/gpt_train_potry3000.py:256-288). */
+int nt_graph_begin(void);
+int nt_graph_end(void** graph_exec, int* n_kernel_nodes);
+int nt_graph_launch(void* graph_exec);
+int nt_graph_destroy(void* graph_exec);
+/* number of this library's kernels launched so far (graph replays count their kernel nodes) */
+int nt_launch_count(long long* n);
+/* GEMM engine: 0 = fp32 SIMT (exact fp32), 1 = tcgen05 TF32 x3 split (fp32-class accuracy),
+ * 2 = tcgen05 TF32 single pass.  Shapes the tensor-core path cannot take fall back to 0. */
+int nt_set_gemm_mode(int mode);
+int nt_get_gemm_mode(int* mode);
+int nt_flush_l2(void);                   /* writes a 256 MB scratch buffer (bench hygiene) */
+
+/* ---------------------------------------------------------------- Linear  (net/fullconnect.py) */
+#define NT_ACT_NONE 0
+#define NT_ACT_RELU 1
+#define NT_ACT_GELU 2
+/* fclayer.forward, net/fullconnect.py:99-106:  y[M,N] = act(x[M,K] @ w[K,N] + b[N]) + residual[M,N].
+ * b, pre, residual may be NULL.  If pre != NULL the pre-activation is stored there
+ * (GELU.forward net/activation.py:139-142 and ReLU.forward :11-14 fused as epilogues). */
+int nt_linear_fwd(const float* x, const float* w, const float* b, float* y,
+                  int M, int K, int N, int act, float* pre, const float* residual);
+/* fclayer.backward input half, net/fullconnect.py:114:  dx[M,K] = (dy[M,N] @ w[K,N]^T) * act'(pre[M,K]) + addend[M,K].
+ * act' is GELU.backward (net/activation.py:144-148) or ReLU.backward (:16-17) of the layer that
+ * PRODUCED x; pre / addend may be NULL. */
+int nt_linear_bwd_input(const float* dy, const float* w, float* dx,
+                        int M, int K, int N, int act, const float* pre, const float* addend);
+/* fclayer.backward parameter half, net/fullconnect.py:118-125:  dw[K,N] += x^T @ dy ; db[N] += colsum(dy).
+ * db may be NULL. Accumulates. */
+int nt_linear_bwd_params(const float* x, const float* dy, float* dw, float* db, int M, int K, int N);
+
+/* ---------------------------------------------------------------- LayerNorm (net/layernorm.py) */
+/* layer_norm.forward, net/layernorm.py:88-114: rows of width D, biased variance, eps inside sqrt.
+ * mean/rstd (length M) are kept for backward.  post_add (may be NULL) is a [period,D] table added
+ * after the affine (Position_learnable.forward, Position_add.py:20-23, fused). */
+int nt_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
+                     float* mean, float* rstd, int M, int D, float eps,
+                     const float* post_add, int period);
+/* layer_norm.backward, net/layernorm.py:116-135: dx = three-term formula (+ addend if non-NULL);
+ * dgamma[D] += sum xhat*dy ; dbeta[D] += sum dy.  Accumulates into dgamma/dbeta. */
+int nt_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                     const float* gamma, float* dx, float* dgamma, float* dbeta,
+                     int M, int D, const float* addend);
+
+/* ---------------------------------------------------------------- activations (net/activation.py) */
+int nt_gelu_fwd(const float* x, float* y, size_t n);                       /* :139-142 */
+int nt_gelu_bwd(const float* dy, const float* x, float* dx, size_t n);     /* :144-148 */
+int nt_relu_fwd(const float* x, float* y, size_t n);                       /* :11-14  */
+int nt_relu_bwd(const float* dy, const float* x_pre, float* dx, size_t n); /* :16-17  */
+int nt_softmax_fwd(const float* x, float* p, int rows, int cols);          /* :76-84, axis=-1 */
+int nt_softmax_bwd(const float* dp, const float* p, float* dx, int rows, int cols); /* :86-129 closed form */
+int nt_add(const float* a, const float* b, float* out, size_t n);          /* residual adds */
+int nt_add_rows(const float* x, const float* table, float* out, int rows, int period, int D); /* Position_add.py:20-23 */
+int nt_scale(float* x, float alpha, size_t n);
+
+/* ---------------------------------------------------------------- attention core
+ * attention.py:31-46,63-84 and gpt/attdecoderblock.py:52-69,79-99 (the per-sample/per-head loops).
+ * qkv [B,N,3*H*dh], columns ordered [q,k,v][head][dh] (attention.py:24).
+ * mask_kind: 0 none, 1 causal (-inf above the diagonal, gpt_train_potry3000.py:84-91),
+ *            2 dense additive fp32 mask[N,N] (added AFTER the 1/sqrt(dh) scale, attention.py:37-39).
+ * P [B,H,N,N] receives the softmax (the reference's atg__), S (may be NULL) the pre-mask scaled
+ * scores (att_col, attdecoderblock.py:58-59).  out[B,N,H*dh] = concat_h(P V) (+ residual if non-NULL). */
+#define NT_MASK_NONE 0
+#define NT_MASK_CAUSAL 1
+#define NT_MASK_DENSE 2
+int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S,
+                     int B, int N, int H, int dh, const float* residual);
+/* dqkv[B,N,3*H*dh] from dout[B,N,H*dh]; scratch must hold B*H*N*N floats (dS). */
+int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch,
+                     int B, int N, int H, int dh);
+
+/* ---------------------------------------------------------------- embeds */
+/* PatchEmbed_flatten.forward patch loops, PatchEmbed.py:22-36: (B,C,Hi,Wi) -> (B, n_patch^2, C*h*w) */
+int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, int n_patch);
+/* Position_Embedding.forward, PatchEmbed.py:132-138 + Embedding_layer.forward net/Embedding.py:50-55:
+ * out[b,t,:] = etok[idx[b,t],:] + epos[t,:]  (epos may be NULL). */
+int nt_embedding_fwd(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int T, int D);
+/* Position_Embedding.backward, PatchEmbed.py:140-144 + Embedding_layer.backward net/Embedding.py:57-70:
+ * detok[idx[b,t],:] += dy[b,t,:] ; depos[t,:] += sum_b dy[b,t,:]  (either may be NULL). Accumulates. */
+int nt_embedding_bwd(const int32_t* idx, const float* dy, float* detok, float* depos, int B, int T, int D);
+
+/* ---------------------------------------------------------------- loss (net/loss.py:46-51) */
+/* cross_entropy_loss: p = softmax(logits), loss = -sum(label*log(p+1e-10))/n_norm, grad = (p-label)/n_norm.
+ * labels are int32 class indices when onehot == NULL, else the dense label matrix [rows,cols].
+ * argmax (may be NULL) receives np.argmax(p, -1) with first-index tie-break
+ * (transformer_of_image.py:151).  row_loss is a [rows] scratch; loss a device scalar.
+ * n_norm is the GLOBAL row count under data parallelism. */
+int nt_cross_entropy(const float* logits, const int32_t* labels, const float* onehot, float n_norm,
+                     float* loss, float* row_loss, float* grad, float* prob, int32_t* argmax,
+                     int rows, int cols);
+
+/* ---------------------------------------------------------------- optimiser */
+/* fclayer.update SGD branch + setzero, net/fullconnect.py:150-153,129-132: p -= lr*g ; g = 0 if zero_grad.
+ * lr_dev (device float*, may be NULL) overrides lr so a captured graph can follow a schedule. */
+int nt_sgd(float* p, float* g, size_t n, float lr, const float* lr_dev, int zero_grad);
+/* fclayer.update Adam branch, net/fullconnect.py:137-149 (sqrt on both bias corrections, eps 1e-8
+ * outside the sqrt).  t_dev (device int*, may be NULL) overrides t. */
+int nt_adam_star(float* p, float* g, float* m, float* v, size_t n, float lr, const float* lr_dev,
+                 int t, const int32_t* t_dev, int zero_grad);
+int nt_increment(int32_t* counter);      /* t += 1 on device (fullconnect.py:149) */
+
+/* ---------------------------------------------------------------- data parallel */
+/* One NCCL communicator per process (one process per GPU).  uid is the 128-byte ncclUniqueId. */
+int nt_dp_unique_id(void* uid128);
+int nt_dp_init(const void* uid128, int rank, int world);
+int nt_dp_allreduce_sum(float* buf, size_t n);   /* in place, on the comm stream, ordered after compute */
+int nt_dp_join(void);                            /* compute stream waits for outstanding all-reduces */
+int nt_dp_shutdown(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,95 @@
+// Internal helpers shared by the kernels of libntb200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+#include "../../include/ntb200.h"
+
+namespace nt {
+
+extern cudaStream_t g_stream;
+extern int g_sm_count;
+extern int g_gemm_mode;
+extern long long g_launches;
+extern bool g_capturing;
+void set_error(const char* fmt, ...);
+bool ensure_init();
+
+#define NT_CHECK(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      nt::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                     \
+    }                                                                               \
+  } while (0)
+
+#define NT_REQUIRE(cond, ...)                   \
+  do {                                          \
+    if (!(cond)) {                              \
+      nt::set_error(__VA_ARGS__);               \
+      return 2;                                 \
+    }                                           \
+  } while (0)
+
+// every kernel launch goes through this so gpu_launches is counted honestly
+#define NT_LAUNCH_OK()                                                 \
+  do {                                                                 \
+    if (!nt::g_capturing) nt::g_launches++;                            \
+    cudaError_t _e = cudaGetLastError();                               \
+    if (_e != cudaSuccess) {                                           \
+      nt::set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return 1;                                                        \
+    }                                                                  \
+  } while (0)
+
+#define NT_ENTRY() do { if (!nt::ensure_init()) return 3; } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// exact-erf GELU and its derivative (net/activation.py:139-148)
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  float s = x * 0.70710678118654752f;
+  return 0.5f + 0.5f * erff(s) + x * 0.3989422804014327f * expf(-s * s);
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// epilogue description shared by the SIMT and tcgen05 GEMMs
+struct Epilogue {
+  const float* bias = nullptr;      // [N], added first
+  int act = 0;                      // forward activation applied after bias (NT_ACT_*)
+  float* pre_out = nullptr;         // store pre-activation (row stride ldc)
+  int dact = 0;                     // multiply by act'(pre_in) (backward fusion)
+  const float* pre_in = nullptr;    // [M,N] row stride ldc
+  const float* addend = nullptr;    // [M,N] row stride ldc, added last
+  float alpha = 1.0f;               // scale on the accumulator
+  int atomic = 0;                   // 1: atomicAdd into C (split-K / accumulate semantics)
+};
+
+// C(m,n) = alpha * sum_k A(m,k) B(k,n), generic strides, two-level batch (z = z0*nb1 + z1)
+struct GemmDesc {
+  const float* A; const float* B; float* C;
+  int M, N, K;
+  long long sAm, sAk, sBk, sBn, ldc;
+  int nb0 = 1, nb1 = 1;
+  long long bA0 = 0, bA1 = 0, bB0 = 0, bB1 = 0, bC0 = 0, bC1 = 0;
+  int splitk = 1;
+  Epilogue ep;
+};
+int gemm_simt(const GemmDesc& d);
+int gemm_dispatch(const GemmDesc& d);   // picks tcgen05 when the mode and shape allow
+int gemm_tc(const GemmDesc& d, int passes, bool* handled);
+
+}  // namespace nt

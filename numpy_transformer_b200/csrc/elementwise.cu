@@ -1,0 +1,227 @@
+// Bandwidth kernels: activations, adds, patchify, embedding gather/scatter, optimiser updates.
+#include "common.cuh"
+
+namespace nt {
+
+enum { OP_GELU_F, OP_GELU_B, OP_RELU_F, OP_RELU_B, OP_ADD, OP_SCALE };
+
+template <int OP>
+__global__ void __launch_bounds__(256) ew_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                 float* __restrict__ out, size_t n, float alpha) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = n / 4;
+  const bool al = ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)out)) & 15) == 0;
+  auto f = [&](float x, float y) -> float {
+    if (OP == OP_GELU_F) return gelu_f(x);
+    if (OP == OP_GELU_B) return x * gelu_grad_f(y);          // a = dy, b = x
+    if (OP == OP_RELU_F) return x < 0.f ? 0.f : x;
+    if (OP == OP_RELU_B) return y > 0.f ? x : 0.f;           // a = dy, b = pre
+    if (OP == OP_ADD) return x + y;
+    return x * alpha;
+  };
+  if (al) {
+    for (; i < n4; i += stride) {
+      float4 x = reinterpret_cast<const float4*>(a)[i];
+      float4 y = b ? reinterpret_cast<const float4*>(b)[i] : make_float4(0, 0, 0, 0);
+      float4 o = make_float4(f(x.x, y.x), f(x.y, y.y), f(x.z, y.z), f(x.w, y.w));
+      reinterpret_cast<float4*>(out)[i] = o;
+    }
+    for (size_t j = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+      out[j] = f(a[j], b ? b[j] : 0.f);
+  } else {
+    for (; i < n; i += stride) out[i] = f(a[i], b ? b[i] : 0.f);
+  }
+}
+
+template <int OP>
+static int launch_ew(const float* a, const float* b, float* out, size_t n, float alpha = 1.f) {
+  if (n == 0) return 0;
+  long long blocks = (long long)((n / 4 + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  long long cap = (long long)g_sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  ew_kernel<OP><<<(int)blocks, 256, 0, g_stream>>>(a, b, out, n, alpha);
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void add_rows_kernel(const float* __restrict__ x, const float* __restrict__ table, float* __restrict__ out,
+                                long long total, int period, int D) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long pd = (long long)period * D;
+  for (; i < total; i += stride) out[i] = x[i] + table[i % pd];
+}
+
+// (B,C,Hi,Wi) -> (B, P*P, C*hl*wl), (c,h,w) order inside a patch  (PatchEmbed.py:27-36)
+__global__ void patchify_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int C, int Hi, int Wi,
+                                int P, int hl, int wl) {
+  const long long total = (long long)B * P * P * C * hl * wl;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    long long r = i;
+    int w = r % wl; r /= wl;
+    int h = r % hl; r /= hl;
+    int c = r % C; r /= C;
+    int pj = r % P; r /= P;
+    int pi = r % P; r /= P;
+    int b = (int)r;
+    out[i] = img[(((long long)b * C + c) * Hi + pi * hl + h) * Wi + pj * wl + w];
+  }
+}
+
+__global__ void embedding_fwd_kernel(const int32_t* __restrict__ idx, const float* __restrict__ etok,
+                                     const float* __restrict__ epos, float* __restrict__ out, int BT, int T, int D) {
+  const int row = blockIdx.x;
+  if (row >= BT) return;
+  const int tok = idx[row];
+  const int t = row % T;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float v = etok[(long long)tok * D + c];
+    if (epos) v += epos[(long long)t * D + c];
+    out[(long long)row * D + c] = v;
+  }
+}
+
+__global__ void embedding_bwd_tok_kernel(const int32_t* __restrict__ idx, const float* __restrict__ dy,
+                                         float* __restrict__ detok, int BT, int D) {
+  const int row = blockIdx.x;
+  if (row >= BT) return;
+  const int tok = idx[row];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) atomicAdd(detok + (long long)tok * D + c, dy[(long long)row * D + c]);
+}
+
+__global__ void embedding_bwd_pos_kernel(const float* __restrict__ dy, float* __restrict__ depos, int B, int T, int D) {
+  const long long total = (long long)T * D;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float s = 0.f;
+  for (int b = 0; b < B; b++) s += dy[(long long)b * total + i];
+  depos[i] += s;
+}
+
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, float* __restrict__ g, size_t n, float lr,
+                                                  const float* __restrict__ lr_dev, int zero_grad) {
+  if (lr_dev) lr = *lr_dev;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    p[i] -= g[i] * lr;
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+// net/fullconnect.py:137-149: m̂ = m/sqrt(1-b1^t), v̂ = v/sqrt(1-b2^t), p -= m̂*lr/(sqrt(v̂)+1e-8)
+__global__ void __launch_bounds__(256) adam_star_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, size_t n,
+                                                        float lr, const float* __restrict__ lr_dev, int t,
+                                                        const int32_t* __restrict__ t_dev, int zero_grad) {
+  if (lr_dev) lr = *lr_dev;
+  if (t_dev) t = *t_dev;
+  const float b1 = 0.9f, omb1 = 0.1f, b2 = 0.999f, omb2 = 0.001f, eps = 1e-8f;
+  // bias corrections once per thread in fp64: 1-0.999^t loses ~1e-5 relative in fp32 for small t
+  const float c1 = (float)(1.0 / sqrt(1.0 - pow(0.9, (double)t)));
+  const float c2 = (float)(1.0 / sqrt(1.0 - pow(0.999, (double)t)));
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + omb1 * gi;
+    const float vi = b2 * v[i] + omb2 * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= (mi * c1) * lr / (sqrtf(vi * c2) + eps);
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+__global__ void increment_kernel(int32_t* c) { *c += 1; }
+
+static int grid_for(size_t n) {
+  long long blocks = (long long)((n + 255) / 256);
+  long long cap = (long long)g_sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace nt
+using namespace nt;
+
+extern "C" {
+
+int nt_gelu_fwd(const float* x, float* y, size_t n) { NT_ENTRY(); return launch_ew<OP_GELU_F>(x, nullptr, y, n); }
+int nt_gelu_bwd(const float* dy, const float* x, float* dx, size_t n) { NT_ENTRY(); return launch_ew<OP_GELU_B>(dy, x, dx, n); }
+int nt_relu_fwd(const float* x, float* y, size_t n) { NT_ENTRY(); return launch_ew<OP_RELU_F>(x, nullptr, y, n); }
+int nt_relu_bwd(const float* dy, const float* pre, float* dx, size_t n) { NT_ENTRY(); return launch_ew<OP_RELU_B>(dy, pre, dx, n); }
+int nt_add(const float* a, const float* b, float* out, size_t n) { NT_ENTRY(); return launch_ew<OP_ADD>(a, b, out, n); }
+int nt_scale(float* x, float alpha, size_t n) { NT_ENTRY(); return launch_ew<OP_SCALE>(x, nullptr, x, n, alpha); }
+
+int nt_add_rows(const float* x, const float* table, float* out, int rows, int period, int D) {
+  NT_ENTRY();
+  NT_REQUIRE(period > 0 && D > 0, "nt_add_rows: bad period/D");
+  long long total = (long long)rows * D;
+  if (total == 0) return 0;
+  add_rows_kernel<<<grid_for(total), 256, 0, g_stream>>>(x, table, out, total, period, D);
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, int n_patch) {
+  NT_ENTRY();
+  NT_REQUIRE(n_patch > 0 && Hi >= n_patch && Wi >= n_patch, "nt_patchify: bad geometry");
+  int hl = Hi / n_patch, wl = Wi / n_patch;
+  long long total = (long long)B * n_patch * n_patch * C * hl * wl;
+  if (total == 0) return 0;
+  patchify_kernel<<<grid_for(total), 256, 0, g_stream>>>(images, out, B, C, Hi, Wi, n_patch, hl, wl);
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_embedding_fwd(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int T, int D) {
+  NT_ENTRY();
+  if (B * T == 0) return 0;
+  embedding_fwd_kernel<<<B * T, D >= 256 ? 256 : 128, 0, g_stream>>>(idx, etok, epos, out, B * T, T, D);
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_embedding_bwd(const int32_t* idx, const float* dy, float* detok, float* depos, int B, int T, int D) {
+  NT_ENTRY();
+  if (B * T == 0) return 0;
+  if (detok) {
+    embedding_bwd_tok_kernel<<<B * T, D >= 256 ? 256 : 128, 0, g_stream>>>(idx, dy, detok, B * T, D);
+    NT_LAUNCH_OK();
+  }
+  if (depos) {
+    embedding_bwd_pos_kernel<<<ceil_div((long long)T * D, 256), 256, 0, g_stream>>>(dy, depos, B, T, D);
+    NT_LAUNCH_OK();
+  }
+  return 0;
+}
+
+int nt_sgd(float* p, float* g, size_t n, float lr, const float* lr_dev, int zero_grad) {
+  NT_ENTRY();
+  if (n == 0) return 0;
+  sgd_kernel<<<grid_for(n), 256, 0, g_stream>>>(p, g, n, lr, lr_dev, zero_grad);
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_adam_star(float* p, float* g, float* m, float* v, size_t n, float lr, const float* lr_dev, int t,
+                 const int32_t* t_dev, int zero_grad) {
+  NT_ENTRY();
+  if (n == 0) return 0;
+  adam_star_kernel<<<grid_for(n), 256, 0, g_stream>>>(p, g, m, v, n, lr, lr_dev, t, t_dev, zero_grad);
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_increment(int32_t* counter) {
+  NT_ENTRY();
+  increment_kernel<<<1, 1, 0, g_stream>>>(counter);
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

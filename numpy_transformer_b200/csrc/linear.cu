@@ -1,0 +1,92 @@
+// Linear layer entry points (net/fullconnect.py) -> GEMM descriptors.
+#include "common.cuh"
+
+namespace nt {
+
+// db[n] += sum_m dy[m,n]   (net/fullconnect.py:122,125)
+__global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ db, int M, int N, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  if (c < N)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += __ldg(dy + (long long)r * N + c);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += red[i][threadIdx.x];
+    atomicAdd(db + c, t);
+  }
+}
+
+int gemm_dispatch(const GemmDesc& d) {
+  if (g_gemm_mode != 0) {
+    bool handled = false;
+    int rc = gemm_tc(d, g_gemm_mode == 1 ? 3 : 1, &handled);
+    if (rc) return rc;
+    if (handled) return 0;
+  }
+  return gemm_simt(d);
+}
+
+}  // namespace nt
+using namespace nt;
+
+extern "C" {
+
+int nt_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int K, int N, int act,
+                  float* pre, const float* residual) {
+  NT_ENTRY();
+  NT_REQUIRE(M >= 0 && K > 0 && N > 0, "nt_linear_fwd: bad shape M=%d K=%d N=%d", M, K, N);
+  NT_REQUIRE(act >= 0 && act <= 2, "nt_linear_fwd: act %d", act);
+  GemmDesc d{};
+  d.A = x; d.B = w; d.C = y;
+  d.M = M; d.N = N; d.K = K;
+  d.sAm = K; d.sAk = 1; d.sBk = N; d.sBn = 1; d.ldc = N;
+  d.ep.bias = b; d.ep.act = act; d.ep.pre_out = pre; d.ep.addend = residual;
+  return gemm_dispatch(d);
+}
+
+int nt_linear_bwd_input(const float* dy, const float* w, float* dx, int M, int K, int N, int act,
+                        const float* pre, const float* addend) {
+  NT_ENTRY();
+  NT_REQUIRE(M >= 0 && K > 0 && N > 0, "nt_linear_bwd_input: bad shape M=%d K=%d N=%d", M, K, N);
+  NT_REQUIRE(act == 0 || pre != nullptr, "nt_linear_bwd_input: act' needs the saved pre-activation");
+  GemmDesc d{};
+  // dx[M,K] = dy[M,N] . w[K,N]^T : contraction over N
+  d.A = dy; d.B = w; d.C = dx;
+  d.M = M; d.N = K; d.K = N;
+  d.sAm = N; d.sAk = 1; d.sBk = 1; d.sBn = N; d.ldc = K;
+  d.ep.dact = act; d.ep.pre_in = pre; d.ep.addend = addend;
+  return gemm_dispatch(d);
+}
+
+int nt_linear_bwd_params(const float* x, const float* dy, float* dw, float* db, int M, int K, int N) {
+  NT_ENTRY();
+  NT_REQUIRE(M >= 0 && K > 0 && N > 0, "nt_linear_bwd_params: bad shape M=%d K=%d N=%d", M, K, N);
+  if (M == 0) return 0;
+  GemmDesc d{};
+  // dw[K,N] += x[M,K]^T . dy[M,N] : contraction over M (long), split across CTAs, atomic accumulate
+  d.A = x; d.B = dy; d.C = dw;
+  d.M = K; d.N = N; d.K = M;
+  d.sAm = 1; d.sAk = K; d.sBk = N; d.sBn = 1; d.ldc = N;
+  d.ep.atomic = 1;
+  int tiles = ceil_div(K, 64) * ceil_div(N, 64);
+  int want = ceil_div(2 * g_sm_count, tiles);
+  int maxsplit = ceil_div(M, 128);
+  d.splitk = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
+  int rc = gemm_dispatch(d);
+  if (rc) return rc;
+  if (db) {
+    int rows_per_block = 256;
+    dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_block));
+    colsum_kernel<<<grid, dim3(32, 8), 0, g_stream>>>(dy, db, M, N, rows_per_block);
+    NT_LAUNCH_OK();
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+"""attention.attention_layer — the ViT encoder block on the B200 backend (mirrors attention.py:6-114).
+
+  h   = x + MHA(LN(x))                 (no output projection)
+  out = h + FC1(GELU(FC0(LN1(h))))     (MLP ratio 2)
+
+The reference's per-sample / per-head Python loops (attention.py:31-45, 63-83) become one fused
+attention kernel each way; GELU, bias and both residual adds ride in GEMM / attention epilogues."""
+import numpy as np
+from net.layernorm import layer_norm
+from net.fullconnect import fclayer
+from net.activation import Softmax, GELU
+from numpy_transformer_b200.device import as_device
+from numpy_transformer_b200 import ops
+
+
+class attention_layer():
+    def __init__(self, embed_dim, num_h):
+        self.embed_dim = embed_dim
+        self.num_h = num_h
+        self.len_single = embed_dim // num_h
+        self.norm = layer_norm(self.embed_dim)
+        self.norm1 = layer_norm(self.embed_dim)
+        self.qkvfc = fclayer(self.embed_dim, self.len_single * num_h * 3, True)
+        self.fc0 = fclayer(self.embed_dim, self.embed_dim * 2, True)
+        self.fc1 = fclayer(self.embed_dim * 2, self.embed_dim, True)
+        self.softmax = Softmax()
+        self.gelu = GELU()
+
+    def forward(self, inputs, masks=[]):
+        x = as_device(inputs)
+        self.batch, self.block, _ = x.shape
+        kind, dmask = ops.detect_mask(masks, self.block)
+        self.out = self.norm._forward(x)
+        self.qkv = self.qkvfc._forward(self.out)                       # (B,N,3D): [q,k,v][head][dh]
+        input1, self.P, _ = ops.attention_fwd(self.qkv, self.num_h, dmask, kind, residual=x)
+        self.out1 = self.norm1._forward(input1)
+        self.out2, self.pre2 = self.fc0._forward(self.out1, ops.ACT_GELU, want_pre=True)
+        return self.fc1._forward(self.out2, residual=input1)          # out6 + input1
+
+    def backward(self, delta):
+        delta = as_device(delta)
+        d = self.fc1._backward(delta, self.out2, ops.ACT_GELU, self.pre2)   # fc1.backward + gelu.backward
+        d = self.fc0._backward(d, self.out1)
+        delta0 = self.norm1._backward(d, addend=delta)                 # delta0 += delta (attention.py:62)
+        self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h)
+        d = self.qkvfc._backward(self.delta_qkv, self.out)
+        return self.norm._backward(d, addend=delta0)                   # input_delta += delta0 (attention.py:88)
+
+    @property
+    def atg__(self):
+        """[batch][head] -> (N,N) softmax matrices, as the reference keeps them (attention.py:30,41)."""
+        P = np.asarray(self.P)
+        return [[P[n, i] for i in range(self.num_h)] for n in range(self.batch)]
+
+    def _children(self):
+        return [self.norm, self.qkvfc, self.norm1, self.fc0, self.fc1]
+
+    def update(self, lr):
+        for c in (self.norm, self.norm1, self.qkvfc, self.fc0, self.fc1):
+            c.update(lr)
+
+    def setzero(self):
+        for c in self._children():
+            c.setzero()
+
+    def save_model(self):
+        return [c.save_model() for c in self._children()]
+
+    def restore_model(self, models):
+        for c, m in zip(self._children(), models):
+            c.restore_model(m)
+
+    def _slots(self):
+        return [s for c in self._children() for s in c._slots()]

@@ -1,0 +1,95 @@
+"""net.fullconnect.fclayer on the B200 backend (mirrors the reference's net/fullconnect.py:36-164).
+Same constructor, attributes (params, bias_params, params_delta, bias_delta, t) and methods; the
+tensors live on the GPU as DeviceArrays and every method only enqueues CUDA work."""
+import numpy as np
+from numpy_transformer_b200.device import DeviceArray, as_device
+from numpy_transformer_b200 import ops
+
+
+class fclayer(object):
+    def __init__(self, infeature, outfeature, bias=False, params=[], bias_params=[], adam=False, float32=False,
+                 float16=False, name='', init=''):
+        self.infeature, self.outfeature, self.bias = infeature, outfeature, bias
+        self.float32, self.float16 = float32, float16
+        self.host_dtype = np.float32 if float32 else (np.float16 if float16 else np.float64)
+        # same draws, in the same order, as net/fullconnect.py:41-59 (bias is drawn even if unused)
+        if len(params):
+            w = np.asarray(params)
+        else:
+            r = np.sqrt(1 / infeature)
+            w = np.random.uniform(-r, r, (infeature, outfeature))
+        if bias and len(bias_params):
+            b = np.asarray(bias_params)
+        else:
+            r = np.sqrt(1 / infeature)
+            b = np.random.uniform(-r, r, (outfeature))
+        self.params = DeviceArray.from_host(w.reshape(infeature, outfeature), host_dtype=self.host_dtype)
+        self.bias_params = DeviceArray.from_host(b.reshape(outfeature), host_dtype=self.host_dtype)
+        self.params_delta = DeviceArray.zeros((infeature, outfeature), host_dtype=self.host_dtype)
+        self.bias_delta = DeviceArray.zeros((outfeature,), host_dtype=self.host_dtype)
+        self.adam = adam
+        self.beta1, self.beta2, self.epsadam = 0.9, 0.999, 10 ** (2 - 10)
+        self.moment_p = self.rmsprop_p = self.moment_b = self.rmsprop_b = None
+        if adam:
+            self.moment_p = DeviceArray.zeros((infeature, outfeature), host_dtype=self.host_dtype)
+            self.rmsprop_p = DeviceArray.zeros((infeature, outfeature), host_dtype=self.host_dtype)
+            self.moment_b = DeviceArray.zeros((outfeature,), host_dtype=self.host_dtype)
+            self.rmsprop_b = DeviceArray.zeros((outfeature,), host_dtype=self.host_dtype)
+        self.t = 1
+        self.inputs = None
+
+    # --- extended forms used by the fused composite layers
+    def _forward(self, x, act=ops.ACT_NONE, want_pre=False, residual=None):
+        self.inputs = x
+        return ops.linear_fwd(x, self.params, self.bias_params if self.bias else None, act, want_pre, residual)
+
+    def _backward(self, dy, x, act=ops.ACT_NONE, pre=None, addend=None, want_dx=True):
+        ops.linear_bwd_params(x, dy, self.params_delta, self.bias_delta)
+        if not want_dx:
+            return None
+        return ops.linear_bwd_input(dy, self.params, act, pre, addend)
+
+    # --- reference protocol
+    def forward(self, inputs):
+        return self._forward(as_device(inputs, self.host_dtype))
+
+    def backward(self, delta, inputs=[]):
+        dy = as_device(delta, self.host_dtype)
+        x = as_device(inputs, self.host_dtype) if len(inputs) else self.inputs
+        return self._backward(dy, x)
+
+    def setzero(self):
+        self.params_delta.fill_zero()
+        if self.bias:
+            self.bias_delta.fill_zero()
+
+    def update(self, lr=1e-10):
+        if self.adam:
+            ops.adam_star(self.params, self.params_delta, self.moment_p, self.rmsprop_p, lr, self.t)
+            if self.bias:
+                ops.adam_star(self.bias_params, self.bias_delta, self.moment_b, self.rmsprop_b, lr, self.t)
+            self.t += 1
+        else:
+            ops.sgd(self.params, self.params_delta, lr)
+            if self.bias:
+                ops.sgd(self.bias_params, self.bias_delta, lr)
+
+    def save_model(self):
+        if self.bias:
+            return [np.asarray(self.params), np.asarray(self.bias_params)]
+        return [np.asarray(self.params)]
+
+    def restore_model(self, models):
+        self.params.set(np.asarray(models[0]).reshape(self.params.shape))
+        if self.bias:
+            self.bias_params.set(np.asarray(models[1]).reshape(self.bias_params.shape))
+
+    def __name__(self):
+        return "fclayer"
+
+    def _slots(self):
+        """(param, grad, m, v) attribute names for the trainer's flat arenas."""
+        s = [("params", "params_delta", "moment_p", "rmsprop_p")]
+        if self.bias:
+            s.append(("bias_params", "bias_delta", "moment_b", "rmsprop_b"))
+        return [(self, *x) for x in s]

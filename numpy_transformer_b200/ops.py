@@ -1,0 +1,128 @@
+"""Thin functional wrappers: DeviceArray in, DeviceArray out, one C-ABI call each (see include/ntb200.h).
+Nothing here touches the host copy of a tensor, so every function is graph-capturable."""
+import numpy as np
+from ._lib import lib
+from .device import DeviceArray, as_device, ptr_or_null, _prod
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+MASK_NONE, MASK_CAUSAL, MASK_DENSE = 0, 1, 2
+LN_EPS = 1e-5        # net/layernorm.py:86
+
+
+def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None):
+    K, N = w.shape
+    assert x.shape[-1] == K, "linear_fwd: input feature %d != %d" % (x.shape[-1], K)
+    M = x.size // K
+    y = DeviceArray(x.shape[:-1] + (N,), host_dtype=x.host_dtype)
+    pre = y.empty_like() if want_pre else None
+    lib.nt_linear_fwd(x.ptr, w.ptr, ptr_or_null(b), y.ptr, M, K, N, act, ptr_or_null(pre), ptr_or_null(residual))
+    return (y, pre) if want_pre else y
+
+
+def linear_bwd_input(dy, w, act=ACT_NONE, pre=None, addend=None):
+    K, N = w.shape
+    M = dy.size // N
+    dx = DeviceArray(dy.shape[:-1] + (K,), host_dtype=dy.host_dtype)
+    lib.nt_linear_bwd_input(dy.ptr, w.ptr, dx.ptr, M, K, N, act, ptr_or_null(pre), ptr_or_null(addend))
+    return dx
+
+
+def linear_bwd_params(x, dy, dw, db=None):
+    K, N = dw.shape
+    M = dy.size // N
+    assert x.size == M * K, "linear_bwd_params: x %s vs dy %s" % (x.shape, dy.shape)
+    lib.nt_linear_bwd_params(x.ptr, dy.ptr, dw.ptr, ptr_or_null(db), M, K, N)
+
+
+def layernorm_fwd(x, gamma, beta, post_add=None):
+    D = gamma.size
+    M = x.size // D
+    y = x.empty_like()
+    mean = DeviceArray((M,))
+    rstd = DeviceArray((M,))
+    period = 0 if post_add is None else post_add.size // D
+    lib.nt_layernorm_fwd(x.ptr, gamma.ptr, beta.ptr, y.ptr, mean.ptr, rstd.ptr, M, D, LN_EPS,
+                         ptr_or_null(post_add), period)
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, addend=None, want_dx=True):
+    D = gamma.size
+    M = x.size // D
+    dx = x.empty_like() if want_dx else None
+    lib.nt_layernorm_bwd(dy.ptr, x.ptr, mean.ptr, rstd.ptr, gamma.ptr, ptr_or_null(dx), ptr_or_null(dgamma),
+                         ptr_or_null(dbeta), M, D, ptr_or_null(addend))
+    return dx
+
+
+def attention_fwd(qkv, H, mask=None, mask_kind=MASK_NONE, residual=None, want_scores=False):
+    B, N, three_d = qkv.shape
+    D = three_d // 3
+    out = DeviceArray((B, N, D), host_dtype=qkv.host_dtype)
+    P = DeviceArray((B, H, N, N), host_dtype=qkv.host_dtype)
+    S = P.empty_like() if want_scores else None
+    lib.nt_attention_fwd(qkv.ptr, ptr_or_null(mask), mask_kind, out.ptr, P.ptr, ptr_or_null(S), B, N, H, D // H,
+                         ptr_or_null(residual))
+    return out, P, S
+
+
+def attention_bwd(dout, qkv, P, H):
+    B, N, three_d = qkv.shape
+    D = three_d // 3
+    dh = D // H
+    dqkv = qkv.empty_like()
+    scratch = None if (N <= 64 and dh <= 64) else P.empty_like()
+    lib.nt_attention_bwd(dout.ptr, qkv.ptr, P.ptr, dqkv.ptr, ptr_or_null(scratch), B, N, H, dh)
+    return dqkv
+
+
+def cross_entropy(logits, labels=None, onehot=None, n_norm=None, want_prob=True, want_grad=True):
+    rows, cols = logits.shape
+    n_norm = float(rows if n_norm is None else n_norm)
+    loss = DeviceArray((), host_dtype=np.float64)
+    row_loss = DeviceArray((rows,))
+    grad = logits.empty_like() if want_grad else None
+    prob = logits.empty_like() if want_prob else None
+    amax = DeviceArray((rows,), dtype=np.int32)
+    lib.nt_cross_entropy(logits.ptr, ptr_or_null(labels), ptr_or_null(onehot), n_norm, loss.ptr, row_loss.ptr,
+                         ptr_or_null(grad), ptr_or_null(prob), amax.ptr, rows, cols)
+    if prob is not None:
+        prob._argmax = amax
+    return loss, grad, prob, amax
+
+
+def sgd(p, g, lr, zero_grad=False):
+    if isinstance(lr, DeviceArray):
+        lib.nt_sgd(p.ptr, g.ptr, p.size, 0.0, lr.ptr, int(zero_grad))
+    else:
+        lib.nt_sgd(p.ptr, g.ptr, p.size, float(lr), None, int(zero_grad))
+
+
+def adam_star(p, g, m, v, lr, t, zero_grad=False):
+    lr_dev = lr.ptr if isinstance(lr, DeviceArray) else None
+    t_dev = t.ptr if isinstance(t, DeviceArray) else None
+    lib.nt_adam_star(p.ptr, g.ptr, m.ptr, v.ptr, p.size, 0.0 if lr_dev else float(lr), lr_dev,
+                     0 if t_dev else int(t), t_dev, int(zero_grad))
+
+
+def detect_mask(masks, N):
+    """Reference callers pass `masks=[]` or a (T,T) additive ndarray (attention.py:38-39).  Returns
+    (mask_kind, device_mask_or_None).  A 0 / -inf lower-triangular pattern (gpt_train_potry3000.py:84-91)
+    is recognised and handled in-kernel without uploading the matrix."""
+    if masks is None:
+        return MASK_NONE, None
+    if isinstance(masks, str):
+        assert masks == "causal"
+        return MASK_CAUSAL, None
+    if isinstance(masks, DeviceArray):
+        return MASK_DENSE, masks
+    if len(masks) == 0:
+        return MASK_NONE, None
+    m = np.asarray(masks)
+    assert m.shape == (N, N), "mask must be (%d,%d), got %s" % (N, N, m.shape)
+    lower = np.tril(np.ones((N, N), dtype=bool))
+    if np.all(m[lower] == 0) and np.all(np.isneginf(m[~lower])):
+        return MASK_CAUSAL, None
+    if not np.any(m):
+        return MASK_NONE, None
+    return MASK_DENSE, DeviceArray.from_host(m)

@@ -1,0 +1,247 @@
+"""Whole-step driver over a reference-style layer list.
+
+`TrainStep` runs exactly the loop of transformer_of_image.py:141-159 /
+gpt/gpt_train_potry3000.py:256-288 — forward every layer, cross_entropy_loss, then
+backward/update/setzero in reverse — but
+
+  * parameters, gradients and Adam* state are re-homed into flat arenas so update+setzero is ONE
+    kernel over all parameters (and the DP all-reduce is one/few NCCL calls over the grad arena);
+  * the step is captured once into a CUDA graph and replayed (the shapes are tiny and launch-bound);
+  * inputs arrive from pinned host staging buffers, loss/argmax go back the same way, so the public
+    call `step(host_images, host_labels) -> loss` is an honest end-to-end measurement.
+
+The update is applied after the whole backward instead of layer by layer; a layer's backward never
+reads another layer's parameters, so the result is identical to the reference's interleaving.
+"""
+import ctypes
+import numpy as np
+
+from . import install
+from ._lib import lib
+from .device import DeviceArray, PinnedBuffer, as_device, init, keep_allocations
+from . import ops
+
+
+def _import_layers():
+    install()
+    from net.layernorm import layer_norm
+    from net.flatten import flatten_layer
+    from attention import attention_layer
+    from classify import classify_layer
+    from PatchEmbed import PatchEmbed_flatten, Position_Embedding
+    from Position_add import Position_learnable
+    from gpt.attdecoderblock import attdecoderblock_layer
+    return dict(layer_norm=layer_norm, flatten_layer=flatten_layer, attention_layer=attention_layer,
+                classify_layer=classify_layer, PatchEmbed_flatten=PatchEmbed_flatten,
+                Position_Embedding=Position_Embedding, Position_learnable=Position_learnable,
+                attdecoderblock_layer=attdecoderblock_layer)
+
+
+def build_vit_layers(batch=100, channels=1, height=28, width=28, n_patch=7, embed_dim=96, heads=4, blocks=6,
+                     classes=10, seed=None):
+    """Layer list of transformer_of_image.py:56-77 (patch_convolu=0, patchnorm, fixed=1, cls_token=0)."""
+    L = _import_layers()
+    if seed is not None:
+        np.random.seed(seed)
+    layers = [L["PatchEmbed_flatten"](embed_dim, (batch, channels, height, width), n_patch, patchnorm=True),
+              L["Position_learnable"](n_patch, embed_dim, fixed=1)]
+    layers += [L["attention_layer"](embed_dim, heads) for _ in range(blocks)]
+    layers += [L["layer_norm"](embed_dim), L["flatten_layer"](),
+               L["classify_layer"](embed_dim, batch, n_patch, classes, 0)]
+    return layers
+
+
+def build_gpt_layers(batch=64, context=256, embed_dim=384, heads=6, blocks=5, vocab=2350, adam=True, float32=False,
+                     seed=None):
+    """Layer list of gpt/gpt_train_potry3000.py:176-207 (per-token head, relu=False)."""
+    L = _import_layers()
+    if seed is not None:
+        np.random.seed(seed)
+    kw = dict(adam=adam, float32=float32)
+    layers = [L["Position_Embedding"](context, vocab, embed_dim, **kw)]
+    layers += [L["attdecoderblock_layer"](embed_dim, heads, **kw) for _ in range(blocks)]
+    layers += [L["layer_norm"](embed_dim, **kw),
+               L["classify_layer"](embed_dim, batch, 1, vocab, cls_token=False, relu=False, **kw)]
+    return layers
+
+
+def save_walk(layers):
+    """Checkpoint walk of transformer_of_image.py:200-208."""
+    return [l.save_model() for l in layers if 'save_model' in dir(l) and 'restore_model' in dir(l)]
+
+
+def restore_walk(layers, tree):
+    """Restore walk of transformer_of_image.py:84-92."""
+    it = iter(tree)
+    for l in layers:
+        if 'save_model' in dir(l) and 'restore_model' in dir(l):
+            l.restore_model(next(it))
+
+
+class ParamArena:
+    """Flat fp32 arenas for parameters / gradients / Adam* moments; layer attributes become views."""
+
+    def __init__(self, layers, adam):
+        slots = []
+        for l in layers:
+            if hasattr(l, "_slots"):
+                slots.extend(l._slots())
+        self.slots = slots
+        offs, n = [], 0
+        for obj, pn, gn, mn, vn in slots:
+            offs.append(n)
+            n += (getattr(obj, pn).size + 3) // 4 * 4           # 16-byte aligned tensors
+        self.offsets, self.n = offs, n
+        self.params = DeviceArray.zeros((n,))
+        self.grads = DeviceArray.zeros((n,))
+        self.m = DeviceArray.zeros((n,)) if adam else None
+        self.v = DeviceArray.zeros((n,)) if adam else None
+        for (obj, pn, gn, mn, vn), off in zip(slots, offs):
+            p = getattr(obj, pn)
+            g = getattr(obj, gn)
+            pv = self.params.view(off, p.shape)
+            pv.host_dtype = p.host_dtype
+            lib.nt_d2d(pv.ptr, p.ptr, p.nbytes)
+            gv = self.grads.view(off, g.shape)
+            gv.host_dtype = g.host_dtype
+            lib.nt_d2d(gv.ptr, g.ptr, g.nbytes)
+            setattr(obj, pn, pv)
+            setattr(obj, gn, gv)
+            if adam and mn is not None:
+                for arena, name in ((self.m, mn), (self.v, vn)):
+                    old = getattr(obj, name)
+                    nv = arena.view(off, p.shape)
+                    if old is not None:
+                        lib.nt_d2d(nv.ptr, old.ptr, old.nbytes)
+                    setattr(obj, name, nv)
+        self.n_params = sum(getattr(o, pn).size for o, pn, *_ in slots)
+
+
+class TrainStep:
+    """One training step of a reference-style layer list as a replayable CUDA graph.
+
+    kind='vit': inputs (B,C,H,W) float images, labels (B,) int   -> N = B        (loss.py:49-50)
+    kind='gpt': inputs (B,T) int tokens,      labels (B,T) int   -> N = B*T, causal mask in-kernel
+    dp: None or a DataParallel (parallel.py); the local batch is one shard of the global batch and
+        the loss/gradient normaliser is the GLOBAL row count.
+    """
+
+    def __init__(self, layers, kind, input_shape, lr, adam=False, dp=None, use_graph=True, grad_buckets=1):
+        init()
+        self.layers, self.kind, self.adam, self.dp = layers, kind, adam, dp
+        self.use_graph = use_graph
+        self.arena = ParamArena(layers, adam)
+        self.input_shape = tuple(input_shape)
+        in_dtype = np.float32 if kind == "vit" else np.int32
+        self.rows = input_shape[0] if kind == "vit" else input_shape[0] * input_shape[1]
+        world = 1 if dp is None else dp.world
+        self.n_norm = float(self.rows * world)
+        self.h_in = PinnedBuffer(self.input_shape, in_dtype)
+        self.h_lab = PinnedBuffer((self.rows,), np.int32)
+        self.h_out = PinnedBuffer((2,), np.float32)
+        self.h_amax = PinnedBuffer((self.rows,), np.int32)
+        self.d_in = DeviceArray(self.input_shape, in_dtype)
+        self.d_lab = DeviceArray((self.rows,), np.int32)
+        self.d_lr = DeviceArray.from_host(np.array([lr], dtype=np.float32)).reshape(())
+        self.d_t = DeviceArray.from_host(np.array([1], dtype=np.int32)).reshape(())
+        self._lr = float(lr)
+        self.graph = None
+        self.graph_kernels = 0
+        self.steps_done = 0
+        self.grad_buckets = max(1, int(grad_buckets))
+        self.loss = self.logits = self.probs = self.argmax = None
+        L = _import_layers()
+        self._block_t = L["attdecoderblock_layer"]
+
+    # ------------------------------------------------------------------ the step body (enqueue only)
+    def _enqueue(self):
+        x = self.d_in
+        for l in self.layers:
+            if isinstance(l, self._block_t):
+                x = l.forward(x, "causal")
+            else:
+                x = l.forward(x)
+        self.logits = x
+        flat = x.reshape(self.rows, x.shape[-1])
+        self.loss, grad, self.probs, self.argmax = ops.cross_entropy(flat, self.d_lab, None, self.n_norm)
+        delta = grad.reshape(x.shape)
+        first = self.layers[0]
+        for l in reversed(self.layers):
+            if l is first and hasattr(l, "fullconnect"):
+                delta = l.backward(delta, want_dx=False)     # nobody consumes the patch-space gradient
+            else:
+                delta = l.backward(delta)
+        a = self.arena
+        if self.dp is not None and self.dp.world > 1:
+            self.dp.allreduce_buckets(a.grads, self.grad_buckets)
+            lib.nt_dp_join()
+        if self.adam:
+            lib.nt_adam_star(a.params.ptr, a.grads.ptr, a.m.ptr, a.v.ptr, a.n, 0.0, self.d_lr.ptr, 0, self.d_t.ptr, 1)
+            lib.nt_increment(self.d_t.ptr)
+        else:
+            lib.nt_sgd(a.params.ptr, a.grads.ptr, a.n, 0.0, self.d_lr.ptr, 1)
+
+    def set_lr(self, lr):
+        if float(lr) != self._lr:
+            self._lr = float(lr)
+            self.d_lr.set(np.array([lr], dtype=np.float32))
+
+    def run_device(self):
+        """One step on whatever is in the device input buffers (no host traffic).  Call 1 runs
+        eagerly (sizes the pool, loads modules), call 2 captures the graph and launches it, later
+        calls replay it; every call is exactly one training step."""
+        if not self.use_graph or self.steps_done == 0:
+            self._enqueue()
+        elif self.graph is None:
+            lib.nt_sync()
+            with keep_allocations() as keep:
+                lib.nt_graph_begin()
+                try:
+                    self._enqueue()
+                finally:
+                    g = ctypes.c_void_p()
+                    nk = ctypes.c_int(0)
+                    lib.nt_graph_end(ctypes.byref(g), ctypes.byref(nk))
+            self._graph_buffers = keep.buffers
+            self.graph, self.graph_kernels = g, nk.value
+            lib.nt_graph_launch(self.graph)
+        else:
+            lib.nt_graph_launch(self.graph)
+        self.steps_done += 1
+
+    def load(self, inputs, labels):
+        """Host -> pinned staging -> device (async on the compute stream)."""
+        np.copyto(self.h_in.array, np.asarray(inputs).reshape(self.input_shape), casting="unsafe")
+        np.copyto(self.h_lab.array, np.asarray(labels).reshape(-1), casting="unsafe")
+        lib.nt_h2d(self.d_in.ptr, self.h_in.ptr, self.h_in.nbytes)
+        lib.nt_h2d(self.d_lab.ptr, self.h_lab.ptr, self.h_lab.nbytes)
+
+    def step(self, inputs, labels, lr=None, want_argmax=False):
+        """End-to-end public call: host batch in, host loss (and argmax) out."""
+        if lr is not None:
+            self.set_lr(lr)
+        self.load(inputs, labels)
+        self.run_device()
+        lib.nt_d2h_async(self.h_out.ptr, self.loss.ptr, 4)
+        if want_argmax:
+            lib.nt_d2h_async(self.h_amax.ptr, self.argmax.ptr, self.h_amax.nbytes)
+        lib.nt_sync()
+        loss = float(self.h_out.array[0])
+        return (loss, self.h_amax.array.copy()) if want_argmax else loss
+
+    @property
+    def h2d_bytes(self):
+        return self.h_in.nbytes + self.h_lab.nbytes
+
+    def sync_layer_counters(self):
+        """Bring the per-object Adam `t` (fullconnect.py:97,149) in line with the device counter."""
+        t = int(self.d_t)
+        for obj, *_ in self.arena.slots:
+            obj.t = t
+
+    def __del__(self):
+        try:
+            if self.graph is not None:
+                lib.nt_graph_destroy(self.graph)
+        except Exception:
+            pass

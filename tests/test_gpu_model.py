@@ -1,0 +1,182 @@
+"""GPU parity, model level: full training steps through the drop-in layer API and through the
+graph-captured TrainStep, against reference-generated goldens (tiny configs), the oracle on seeded
+inputs (mid-size), and the committed README-size reference trajectory (loss/logits/argmax)."""
+import pickle
+import numpy as np
+import pytest
+from conftest import load_golden, golden_tree, rel_err
+from oracle import models as M
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def nt():
+    import numpy_transformer_b200 as nt
+    nt.init(0)
+    nt.install()
+    return nt
+
+
+def _leaves_close(mine, gold, tol, what=""):
+    a, b = M.tree_leaves(mine), M.tree_leaves(gold)
+    assert len(a) == len(b)
+    for i, (x, y) in enumerate(zip(a, b)):
+        e = rel_err(np.asarray(x).reshape(-1), np.asarray(y).reshape(-1))
+        assert e < tol, "%s leaf %d rel err %.3e" % (what, i, e)
+
+
+def test_vit_tiny_layer_api_matches_reference_golden(nt):
+    """Drive the mirror exactly like transformer_of_image.py:141-159 and compare per layer."""
+    from numpy_transformer_b200 import trainer
+    from net.loss import cross_entropy_loss
+    d = load_golden("vit_tiny.npz")
+    cfg = M.ViTConfig(batch=3, embed_dim=16, heads=2, blocks=2)
+    layers = trainer.build_vit_layers(3, embed_dim=16, heads=2, blocks=2, seed=0)
+    like = M.vit_init(cfg, 0)
+    _leaves_close(trainer.save_walk(layers), golden_tree(d, "p0", like), 1e-7, "init")   # same RNG draws
+    lr = float(d["lr"])
+    for step in range(2):
+        x = d["images"]
+        outs = []
+        for l in layers:
+            x = l.forward(x)
+            outs.append(x)
+        loss, delta, predict = cross_entropy_loss(x, d["onehot"])
+        assert abs(float(loss) - d["loss_%d" % step]) < TOL * abs(d["loss_%d" % step])
+        assert rel_err(x, d["logits_%d" % step]) < TOL
+        if step == 0:
+            for i, o in enumerate(outs):
+                assert rel_err(o, d["out_%02d" % i]) < TOL, "forward layer %d" % i
+            assert np.array_equal(np.argmax(predict, axis=-1), np.argmax(d["probs_0"], axis=-1))
+        deltas = []
+        for l in reversed(layers):
+            delta = l.backward(delta)
+            deltas.append(delta)
+        if step == 0:
+            for i, o in enumerate(deltas):
+                assert rel_err(o, d["delta_%02d" % i]) < TOL, "backward layer %d" % i
+        for l in layers:
+            l.update(lr)
+            l.setzero()
+        _leaves_close(trainer.save_walk(layers), golden_tree(d, "p%d" % (step + 1), like), TOL, "params step %d" % step)
+    # checkpoint format: nested lists of float64 ndarrays, picklable, restorable
+    blob = pickle.dumps(trainer.save_walk(layers))
+    layers2 = trainer.build_vit_layers(3, embed_dim=16, heads=2, blocks=2, seed=5)
+    trainer.restore_walk(layers2, pickle.loads(blob))
+    _leaves_close(trainer.save_walk(layers2), trainer.save_walk(layers), 1e-7, "restore")
+
+
+def test_gpt_tiny_layer_api_adam_three_steps(nt):
+    from numpy_transformer_b200 import trainer
+    from net.loss import cross_entropy_loss
+    from gpt.attdecoderblock import attdecoderblock_layer
+    d = load_golden("gpt_tiny.npz")
+    cfg = M.GPTConfig(batch=2, context=8, embed_dim=16, heads=2, blocks=2, vocab=11)
+    layers = trainer.build_gpt_layers(2, 8, 16, 2, 2, 11, adam=True, seed=0)
+    like = M.gpt_init(cfg, 0)
+    mask = M.causal_mask(8)
+    lr = float(d["lr"])
+    for step in range(3):
+        x = d["tokens"]
+        for l in layers:
+            x = l.forward(x, mask) if isinstance(l, attdecoderblock_layer) else l.forward(x)
+        ishape = x.shape
+        flat = np.reshape(x, (-1, cfg.vocab))
+        labels = np.zeros(flat.shape)
+        labels[np.arange(flat.shape[0]), d["labels"].reshape(-1)] = 1
+        loss, delta, predict = cross_entropy_loss(flat, labels)
+        assert abs(float(loss) - d["loss_%d" % step]) < TOL * abs(d["loss_%d" % step]), step
+        assert rel_err(x, d["logits_%d" % step]) < 2e-4
+        delta = np.reshape(delta, ishape)
+        for l in reversed(layers):
+            delta = l.backward(delta)
+        if step == 0:
+            grads = []
+            pe = layers[0]
+            grads += [pe.text_embedding.delta, pe.pos_embedding.delta]
+            for blk in layers[1:3]:
+                for c in blk._children():
+                    grads += [c.gamma_delta, c.beta_delta] if hasattr(c, "gamma") else [c.params_delta, c.bias_delta]
+            grads += [layers[3].gamma_delta, layers[3].beta_delta]
+            grads += [layers[4].fc0.params_delta, layers[4].fc0.bias_delta, layers[4].fc1.params_delta, layers[4].fc1.bias_delta]
+            _leaves_close(grads, golden_tree(d, "g0", like), TOL, "grads")
+        for l in layers:
+            l.update(lr)
+            l.setzero()
+        mine = trainer.save_walk(layers)
+        # Adam* divides by sqrt(v)+1e-8: fp32 rounding of tiny gradients moves the update by ~1e-4 of lr
+        _leaves_close(mine, golden_tree(d, "p%d" % (step + 1), like), 2e-4, "params step %d" % step)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_trainstep_vit_matches_oracle_three_steps(nt, use_graph):
+    from numpy_transformer_b200 import trainer
+    cfg = M.ViTConfig(batch=8, embed_dim=48, heads=4, blocks=3)
+    params = M.vit_init(cfg, 0)
+    images, labels, onehot = M.synthetic_vit_batch(cfg, 1)
+    layers = trainer.build_vit_layers(8, embed_dim=48, heads=4, blocks=3, seed=0)
+    ts = trainer.TrainStep(layers, "vit", images.shape, lr=0.02, use_graph=use_graph)
+    for step in range(4):
+        ref = M.vit_step(params, images, onehot, 0.02, cfg)
+        loss, amax = ts.step(images, labels, want_argmax=True)
+        assert abs(loss - ref["loss"]) < TOL * abs(ref["loss"]), step
+        assert np.array_equal(amax, ref["argmax"])
+        params = ref["params"]
+        _leaves_close(trainer.save_walk(layers), params, TOL, "step %d" % step)
+    if use_graph:
+        assert ts.graph is not None and ts.graph_kernels > 10
+
+
+def test_trainstep_gpt_adam_matches_oracle(nt):
+    from numpy_transformer_b200 import trainer
+    cfg = M.GPTConfig(batch=3, context=40, embed_dim=64, heads=2, blocks=2, vocab=97)
+    params = M.gpt_init(cfg, 0)
+    opt = M.adam_state(params)
+    tokens, labels = M.synthetic_gpt_batch(cfg, 1)
+    layers = trainer.build_gpt_layers(3, 40, 64, 2, 2, 97, adam=True, seed=0)
+    ts = trainer.TrainStep(layers, "gpt", tokens.shape, lr=1e-3, adam=True)
+    for step in range(4):
+        ref = M.gpt_step(params, opt, tokens, labels, 1e-3, cfg)
+        loss, amax = ts.step(tokens, labels, want_argmax=True)
+        assert abs(loss - ref["loss"]) < TOL * abs(ref["loss"]), step
+        assert np.mean(amax == ref["argmax"]) > 0.99
+        params, opt = ref["params"], ref["opt"]
+        mine = trainer.save_walk(layers)
+        mine[0] = [[np.asarray(layers[0].text_embedding.params)], [np.asarray(layers[0].pos_embedding.params)]]
+        _leaves_close(mine, params, 3e-4, "step %d" % step)
+    ts.sync_layer_counters()
+    assert layers[1].fc0.t == 5
+
+
+def test_vit_readme_trajectory_vs_reference(nt):
+    """Full README-size ViT (B=100, D=96, 6x4 heads): two steps against numbers produced by the
+    unmodified reference (tests/golden/vit_readme_traj.npz)."""
+    from numpy_transformer_b200 import trainer
+    d = load_golden("vit_readme_traj.npz")
+    cfg = M.VIT_README
+    images, labels, onehot = M.synthetic_vit_batch(cfg, 1)
+    layers = trainer.build_vit_layers(seed=0)
+    ts = trainer.TrainStep(layers, "vit", images.shape, lr=float(d["lr"]))
+    for step in range(2):
+        loss, amax = ts.step(images, labels, want_argmax=True)
+        assert abs(loss - d["loss_%d" % step]) < TOL * d["loss_%d" % step]
+        assert rel_err(ts.logits, d["logits_%d" % step]) < TOL
+        assert np.array_equal(amax, d["argmax_%d" % step])
+
+
+def test_full_size_properties(nt):
+    """Size-independent checks at the README shape: softmax rows sum to 1, gradients are zeroed by
+    the fused update, accumulate-until-setzero holds, and a repeated batch lowers the loss."""
+    from numpy_transformer_b200 import trainer
+    cfg = M.VIT_README
+    images, labels, _ = M.synthetic_vit_batch(cfg, 3)
+    layers = trainer.build_vit_layers(seed=2)
+    ts = trainer.TrainStep(layers, "vit", images.shape, lr=1e-2)
+    losses = [ts.step(images, labels) for _ in range(6)]
+    assert losses[-1] < losses[0]
+    assert np.allclose(np.asarray(ts.probs).sum(-1), 1.0, atol=1e-5)
+    P = np.asarray(layers[2].P)
+    assert P.shape == (100, 4, 49, 49) and np.allclose(P.sum(-1), 1.0, atol=1e-5)
+    assert not np.any(ts.arena.grads.numpy())

@@ -1,0 +1,105 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/ntb200.h declares,
+the product path fails loudly without a GPU (no CPU fallback), and host-side helpers."""
+import os
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def nt():
+    import numpy_transformer_b200 as nt
+    if not os.path.exists(nt.LIBPATH):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "numpy_transformer_b200", "csrc"), "-j8"])
+    return nt
+
+
+def test_header_parses_and_library_exports_every_symbol(nt):
+    protos = nt.lib.protos
+    assert len(protos) >= 50
+    for must in ("nt_linear_fwd", "nt_linear_bwd_input", "nt_linear_bwd_params", "nt_layernorm_fwd",
+                 "nt_attention_fwd", "nt_attention_bwd", "nt_cross_entropy", "nt_adam_star", "nt_dp_allreduce_sum"):
+        assert must in protos
+    dll = nt.lib.load()
+    for name in protos:
+        assert hasattr(dll, name), name
+    out = subprocess.check_output(["nm", "-D", "--defined-only", nt.LIBPATH]).decode()
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(protos) <= exported
+
+
+def test_library_is_sm100a_only_and_carries_tcgen05_tma(nt):
+    sass = subprocess.run(["cuobjdump", "-lelf", nt.LIBPATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "sm_90" not in sass and "sm_80" not in sass
+
+
+def test_no_cpu_fallback(nt):
+    if nt.available():
+        pytest.skip("a GPU is visible")
+    nt.install()
+    from net.fullconnect import fclayer
+    with pytest.raises(nt.NtError):
+        fclayer(3, 4, True)
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "numpy_transformer_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src, os.path.join(dp, f)
+
+
+def test_mask_detection_and_onehot_conversion(nt):
+    from numpy_transformer_b200 import ops
+    nt.install()
+    from net.loss import _labels_from_onehot
+    assert ops.detect_mask([], 4) == (ops.MASK_NONE, None)
+    m = np.tril(np.ones((4, 4)))
+    c = np.where(m == 0, -np.inf, 0.0)
+    assert ops.detect_mask(c, 4) == (ops.MASK_CAUSAL, None)
+    assert ops.detect_mask(np.zeros((4, 4)), 4) == (ops.MASK_NONE, None)
+    assert ops.detect_mask("causal", 4) == (ops.MASK_CAUSAL, None)
+    oh = np.zeros((5, 7))
+    oh[np.arange(5), [1, 0, 6, 3, 3]] = 1
+    assert _labels_from_onehot(oh).tolist() == [1, 0, 6, 3, 3]
+    assert _labels_from_onehot(oh * 0.5) is None
+    oh[0, 2] = 1
+    assert _labels_from_onehot(oh) is None
+
+
+def test_dropin_module_surface(nt):
+    """Every import the reference's trainers perform resolves to the mirror."""
+    nt.install()
+    import importlib
+    for mod, names in [("net.fullconnect", ["fclayer"]), ("net.layernorm", ["layer_norm"]),
+                       ("net.activation", ["ReLU", "Softmax", "GELU"]), ("net.loss", ["cross_entropy_loss", "mean_square_loss"]),
+                       ("net.flatten", ["flatten_layer"]), ("net.Embedding", ["Embedding_layer"]),
+                       ("net.Convolution", ["convolution_layer"]), ("attention", ["attention_layer"]),
+                       ("classify", ["classify_layer"]),
+                       ("PatchEmbed", ["PatchEmbed_flatten", "PatchEmbed_convolution", "Position_Embedding"]),
+                       ("Position_add", ["Position_learnable"]), ("attdecoderblock", ["attdecoderblock_layer"]),
+                       ("gpt.attdecoderblock", ["attdecoderblock_layer"]), ("gpt.classify_gpt", ["classify_layer"]),
+                       ("gpt.gpt_linear", ["gpt_linear_layer"]), ("gpt.FixedEmbed", ["Position_Fixed"])]:
+        m = importlib.import_module(mod)
+        assert m.__file__.startswith(nt.DROPIN), mod
+        for n in names:
+            assert hasattr(m, n), (mod, n)
+    from net.flatten import flatten_layer
+    from net.activation import ReLU
+    for cls in (flatten_layer, ReLU):
+        assert "save_model" not in dir(cls) and "restore_model" not in dir(cls)
+    from gpt.attdecoderblock import attdecoderblock_layer
+    assert "attdecoderblock" in attdecoderblock_layer.__module__          # gpt_train_potry3000.py:220-221
+
+
+def test_sincos_table_matches_oracle(nt):
+    nt.install()
+    from gpt.FixedEmbed import sincos_table
+    from oracle.numpy_ref import posk_table
+    assert np.array_equal(sincos_table(49, 96)[None], posk_table(49, 96))
