@@ -19,11 +19,18 @@ def nt():
     return nt
 
 
-def _leaves_close(mine, gold, tol, what=""):
+def _leaves_close(mine, gold, tol, what="", skip_kbias_of=None):
+    """skip_kbias_of=D: ignore the key-bias third of every (3D,) qkv bias.  Its gradient is exactly 0
+    in real arithmetic (softmax is invariant to a per-row shift of the scores), so the reference holds
+    ~1e-17 round-off there and fp32 holds ~1e-9; Adam* divides by sqrt(v)+1e-8 and turns that noise into
+    an O(lr) step in both implementations — there is no reference value to agree with."""
     a, b = M.tree_leaves(mine), M.tree_leaves(gold)
     assert len(a) == len(b)
     for i, (x, y) in enumerate(zip(a, b)):
-        e = rel_err(np.asarray(x).reshape(-1), np.asarray(y).reshape(-1))
+        x, y = np.asarray(x).reshape(-1).copy(), np.asarray(y).reshape(-1).copy()
+        if skip_kbias_of and x.size == 3 * skip_kbias_of:
+            x[skip_kbias_of:2 * skip_kbias_of] = y[skip_kbias_of:2 * skip_kbias_of] = 0
+        e = rel_err(x, y)
         assert e < tol, "%s leaf %d rel err %.3e" % (what, i, e)
 
 
@@ -107,7 +114,7 @@ def test_gpt_tiny_layer_api_adam_three_steps(nt):
             l.setzero()
         mine = trainer.save_walk(layers)
         # Adam* divides by sqrt(v)+1e-8: fp32 rounding of tiny gradients moves the update by ~1e-4 of lr
-        _leaves_close(mine, golden_tree(d, "p%d" % (step + 1), like), 2e-4, "params step %d" % step)
+        _leaves_close(mine, golden_tree(d, "p%d" % (step + 1), like), 2e-4, "params step %d" % step, skip_kbias_of=16)
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
@@ -145,7 +152,7 @@ def test_trainstep_gpt_adam_matches_oracle(nt):
         params, opt = ref["params"], ref["opt"]
         mine = trainer.save_walk(layers)
         mine[0] = [[np.asarray(layers[0].text_embedding.params)], [np.asarray(layers[0].pos_embedding.params)]]
-        _leaves_close(mine, params, 3e-4, "step %d" % step)
+        _leaves_close(mine, params, 3e-4, "step %d" % step, skip_kbias_of=64)
     ts.sync_layer_counters()
     assert layers[1].fc0.t == 5
 
