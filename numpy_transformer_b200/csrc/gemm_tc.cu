@@ -1,5 +1,384 @@
-// placeholder until the tcgen05 GEMM lands: reports "not handled" so callers fall back to SIMT.
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = alpha * op(A) op(B)  (+ shared epilogue)
+//
+//   * operands are the fp32 tensors as they sit in HBM; TMA (cp.async.bulk.tensor) lands 128-byte
+//     swizzled tiles in shared memory in exactly the canonical UMMA layout, tcgen05.mma kind::tf32
+//     consumes them straight from smem, the fp32 accumulator lives in TMEM.
+//   * K-major operands (contraction dim contiguous: X in X@W, dY and W in dY@W^T) use SWIZZLE_128B;
+//     MN-major operands (W in X@W, X and dY in X^T@dY) use SWIZZLE_128B_BASE32B, the only MN-major
+//     layout UMMA accepts for 32-bit elements.  No operand is ever transposed or converted in HBM.
+//   * passes == 3 (gemm mode 1): error-compensated 3xTF32.  Four converter warps split every landed
+//     tile into hi = tf32(x) and lo = x - hi in shared memory (element-wise, so layout-agnostic) and
+//     the issuer accumulates hi*hi + hi*lo + lo*hi  ->  ~2^-21 relative error, fp32-class results
+//     (rel <= 1e-4 bar of the spec; single-pass TF32 measures ~3e-3 on gradients and fails it).
+//   * warp roles: w0 = TMA producer, w1 = TMEM allocator + single-thread MMA issuer,
+//     w2..w5 = converters during the main loop, then the epilogue (tcgen05.ld -> bias / GELU / ReLU /
+//     act' / residual -> global, or red.add for the split-K weight-gradient GEMM).
+//   * one 128 x BN output tile per CTA, BN in {32,64,96,128}; blockIdx.z splits K (dW: K = rows of
+//     the batch, thousands long) so the grid fills the 148 SMs; ragged M/N/K edges come from TMA
+//     zero fill + guarded stores.
 #include "common.cuh"
+#include <cuda.h>
+
 namespace nt {
-int gemm_tc(const GemmDesc&, int, bool* handled) { *handled = false; return 0; }
+
+static constexpr int BM = 128;      // UMMA M (cta_group::1)
+static constexpr int BK = 32;       // fp32 elements per k-block = one 128-byte swizzle row
+static constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  int M, N, K;            // problem (C is M x N, contraction K)
+  int BN;                 // N tile
+  int a_mn, b_mn;         // 1 = MN-major operand
+  int passes;             // 1 or 3
+  int stages;
+  int kblocks_per_split;  // k-blocks handled by one blockIdx.z
+  long long ldc;
+  float* C;
+  Epilogue ep;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  // bounded spin: a protocol bug traps (process error) instead of hanging the GPU
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout & 7) << 61;
+  return d;
+}
+static constexpr uint32_t LAYOUT_SW128 = 2;          // K-major tiles
+static constexpr uint32_t LAYOUT_SW128_BASE32B = 1;  // MN-major 32-bit tiles
+
+// ---------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages] x { A hi | B hi | (A lo | B lo) }, then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = BM * BK * 4;            // 16 KB
+  const uint32_t b_bytes = p.BN * BK * 4;
+  const uint32_t stage_bytes = (a_bytes + b_bytes) * (p.passes == 3 ? 2 : 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.stages;
+  uint64_t* conv = bars + 2 * p.stages;
+  uint64_t* tmem_full = bars + 3 * p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * p.BN;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kblocks_per_split;
+  const int kb_end = min(total_kb, kb_begin + p.kblocks_per_split);
+  const int nkb = kb_end - kb_begin;       // >= 1 by construction of the grid
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.BN) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&conv[s], 4);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0) {
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const uint32_t sa = smem_u32(st), sb = sa + a_bytes;
+        const int k0 = (kb_begin + i) * BK;
+        mbar_expect_tx(&full[s], a_bytes + b_bytes);
+        if (!p.a_mn) {
+          tma_load_2d(sa, &tmA, &full[s], k0, m0);                       // box {32 k, 128 m}
+        } else {
+          for (int j = 0; j < BM / 32; j++) tma_load_2d(sa + j * (BK * 128), &tmA, &full[s], m0 + 32 * j, k0);  // box {32 m, 32 k}
+        }
+        if (!p.b_mn) {
+          tma_load_2d(sb, &tmB, &full[s], k0, n0);                       // box {32 k, BN n}
+        } else {
+          for (int j = 0; j < p.BN / 32; j++) tma_load_2d(sb + j * (BK * 128), &tmB, &full[s], n0 + 32 * j, k0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one lane) =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // per-MMA (K = 8 fp32) start-address advance and descriptor strides
+      const uint32_t a_adv = p.a_mn ? 8 * 128 : 32, b_adv = p.b_mn ? 8 * 128 : 32;
+      const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, a_sbo = p.a_mn ? 512 : 1024;
+      const uint32_t b_lbo = p.b_mn ? BK * 128 : 16, b_sbo = p.b_mn ? 512 : 1024;
+      const uint32_t a_lay = p.a_mn ? LAYOUT_SW128_BASE32B : LAYOUT_SW128;
+      const uint32_t b_lay = p.b_mn ? LAYOUT_SW128_BASE32B : LAYOUT_SW128;
+      uint32_t accum = 0;
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        mbar_wait(p.passes == 3 ? &conv[s] : &full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
+        const uint32_t sal = sb + b_bytes, sbl = sal + a_bytes;
+#pragma unroll
+        for (int k = 0; k < BK / 8; k++) {
+          const uint64_t ah = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo, a_lay);
+          const uint64_t bh = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo, b_lay);
+          if (p.passes == 3) {
+            const uint64_t al = make_smem_desc(sal + k * a_adv, a_lbo, a_sbo, a_lay);
+            const uint64_t bl = make_smem_desc(sbl + k * b_adv, b_lbo, b_sbo, b_lay);
+            umma_tf32(tmem_base, al, bh, idesc, accum);      // small terms first
+            umma_tf32(tmem_base, ah, bl, idesc, 1);
+            umma_tf32(tmem_base, ah, bh, idesc, 1);
+          } else {
+            umma_tf32(tmem_base, ah, bh, idesc, accum);
+          }
+          accum = 1;
+        }
+        umma_commit(&empty[s]);          // frees the smem slot when these MMAs retire
+      }
+      umma_commit(tmem_full);            // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===================== converters (3xTF32 split), then epilogue =====================
+    const int ct = threadIdx.x - 64;     // 0..127
+    if (p.passes == 3) {
+      const uint32_t hi_bytes = a_bytes + b_bytes;
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        mbar_wait(&full[s], ph);
+        float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+        float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + hi_bytes);
+        const int n4 = hi_bytes / 16;
+        for (int e = ct; e < n4; e += 128) {
+          float4 x = hi[e];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+          hi[e] = h;
+          lo[e] = l;
+        }
+        fence_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[s]);
+      }
+    }
+    // ---- epilogue: this warp owns TMEM lanes 32*(warp%4) .. +31  == output rows
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const Epilogue& ep = p.ep;
+    const bool first = (blockIdx.z == 0);
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (row < p.M) {
+        const long long rbase = (long long)row * p.ldc;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int col = n0 + c0 + j;
+          if (col < p.N) {
+            float v = ep.alpha * __uint_as_float(r[j]);
+            if (ep.bias && first) v += __ldg(ep.bias + col);
+            if (ep.pre_out) ep.pre_out[rbase + col] = v;
+            if (ep.act == NT_ACT_RELU) v = v < 0.f ? 0.f : v;
+            else if (ep.act == NT_ACT_GELU) v = gelu_f(v);
+            if (ep.dact == NT_ACT_RELU) v = (__ldg(ep.pre_in + rbase + col) > 0.f) ? v : 0.f;
+            else if (ep.dact == NT_ACT_GELU) v *= gelu_grad_f(__ldg(ep.pre_in + rbase + col));
+            if (ep.addend && first) v += __ldg(ep.addend + rbase + col);
+            if (ep.atomic) atomicAdd(p.C + rbase + col, v);
+            else p.C[rbase + col] = v;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  NT_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  NT_REQUIRE(qres == cudaDriverEntryPointSuccess && fn, "cuTensorMapEncodeTiled is not available from the driver");
+  g_encode = (EncodeTiledFn)fn;
+  return 0;
+}
+
+// 2-D fp32 tensor map: inner dim `inner` contiguous, `outer` rows of `ld` elements; box {32, box_outer}
+static int make_tmap(CUtensorMap* tm, const float* base, long long inner, long long outer, long long ld, int box_outer,
+                     bool mn_major) {
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box=%d", (int)r, inner,
+             outer, ld, box_outer);
+  return 0;
+}
+
+static int pick_bn(int N) {
+  if (N % 128 == 0) return 128;
+  if (N % 96 == 0) return 96;
+  if (N >= 112) return 128;
+  if (N > 64) return 96;
+  if (N > 32) return 64;
+  return 32;
+}
+
+int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
+  *handled = false;
+  if (d.nb0 * d.nb1 != 1) return 0;                       // batched (attention) shapes stay on the SIMT path
+  if (d.M < 1 || d.N < 8 || d.K < 1) return 0;
+  const bool a_k = (d.sAk == 1), a_mn = (d.sAm == 1 && !a_k);
+  const bool b_k = (d.sBk == 1), b_mn = (d.sBn == 1 && !b_k);
+  if (!(a_k || a_mn) || !(b_k || b_mn)) return 0;
+  const long long lda = a_k ? d.sAm : d.sAk, ldb = b_k ? d.sBn : d.sBk;
+  // TMA needs 16-byte aligned bases and row pitches
+  if ((lda & 3) || (ldb & 3) || ((uintptr_t)d.A & 15) || ((uintptr_t)d.B & 15)) return 0;
+  if (d.splitk > 1 && !d.ep.atomic) return 0;
+  if (load_encode()) return 1;
+
+  TcParams p{};
+  p.M = d.M; p.N = d.N; p.K = d.K;
+  p.BN = pick_bn(d.N);
+  p.a_mn = a_mn; p.b_mn = b_mn;
+  p.passes = passes;
+  p.ldc = d.ldc;
+  p.C = d.C;
+  p.ep = d.ep;
+  const int total_kb = ceil_div(d.K, BK);
+  int splits = 1;
+  if (d.splitk > 1) {
+    // split the long contraction (dW: K = batch rows) so the grid covers the SMs; >= 4 k-blocks per split
+    const int tiles = ceil_div(d.N, p.BN) * ceil_div(d.M, BM);
+    splits = ceil_div(g_sm_count, tiles);
+    const int maxs = total_kb / 4 < 1 ? 1 : total_kb / 4;
+    if (splits > maxs) splits = maxs;
+  }
+  p.kblocks_per_split = ceil_div(total_kb, splits);
+  splits = ceil_div(total_kb, p.kblocks_per_split);
+  const size_t stage = (size_t)(BM * BK * 4 + p.BN * BK * 4) * (passes == 3 ? 2 : 1);
+  int stages = (int)((200 * 1024) / stage);
+  if (stages > 6) stages = 6;
+  if (stages > p.kblocks_per_split) stages = p.kblocks_per_split < 2 ? 2 : p.kblocks_per_split;
+  p.stages = stages;
+  const size_t smem = stages * stage + (3 * stages + 2) * 8 + 1024;
+
+  CUtensorMap tmA, tmB;
+  if (a_k) { if (make_tmap(&tmA, d.A, d.K, d.M, lda, BM, false)) return 1; }
+  else     { if (make_tmap(&tmA, d.A, d.M, d.K, lda, BK, true)) return 1; }
+  if (b_k) { if (make_tmap(&tmB, d.B, d.K, d.N, ldb, p.BN, false)) return 1; }
+  else     { if (make_tmap(&tmB, d.B, d.N, d.K, ldb, BK, true)) return 1; }
+
+  static size_t configured = 0;
+  if (smem > configured) {
+    NT_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    configured = 227 * 1024;
+  }
+  dim3 grid(ceil_div(d.N, p.BN), ceil_div(d.M, BM), splits);
+  gemm_tc_kernel<<<grid, TC_THREADS, smem, g_stream>>>(tmA, tmB, p);
+  NT_LAUNCH_OK();
+  *handled = true;
+  return 0;
+}
+
+}  // namespace nt

@@ -9,7 +9,7 @@
 namespace nt {
 cudaStream_t g_stream = nullptr;
 int g_sm_count = 148;
-int g_gemm_mode = 0;
+int g_gemm_mode = 1;   // default: tcgen05 3xTF32 (fp32-class accuracy)
 long long g_launches = 0;
 bool g_capturing = false;
 static int g_device = -1;
