@@ -23,7 +23,8 @@ namespace nt {
 
 static constexpr int BM = 128;      // UMMA M (cta_group::1)
 static constexpr int BK = 32;       // fp32 elements per k-block = one 128-byte swizzle row
-static constexpr int TC_THREADS = 192;
+static constexpr int TC_WORKERS = 8;                    // converter / epilogue warps
+static constexpr int TC_THREADS = 64 + 32 * TC_WORKERS;
 
 struct TcParams {
   int M, N, K;            // problem (C is M x N, contraction K)
@@ -53,6 +54,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
   // bounded spin: a protocol bug traps (process error) instead of hanging the GPU
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 24); ++it) {
     asm volatile(
         "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
@@ -110,12 +112,30 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 static constexpr uint32_t LAYOUT_SW128 = 2;          // K-major tiles
 static constexpr uint32_t LAYOUT_SW128_BASE32B = 1;  // MN-major 32-bit tiles
 
+#ifdef NT_TC_TIMING
+__device__ unsigned long long g_tc_times[4096 * 8];
+#define TC_STAMP(ev)                                                                         \
+  do {                                                                                       \
+    unsigned long long _t;                                                                   \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                   \
+    int _cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);               \
+    if (_cta < 4096) g_tc_times[_cta * 8 + (ev)] = _t;                                       \
+  } while (0)
+#else
+#define TC_STAMP(ev) do {} while (0)
+#endif
+
 // ---------------------------------------------------------------- kernel
+// Epilogue flags are template parameters: a runtime-configured epilogue costs ~8 uniform branches per
+// 4-row store group, which measured ~250 cycles per group on a path that runs once per CTA.
+template <int ACT, int DACT, bool PRE_OUT, bool ATOMIC, bool ADDEND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages] x { A hi | B hi | (A lo | B lo) }, then barriers
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // offset arithmetic on the __shared__ array (not on a generic uintptr_t) keeps the address space known,
+  // so the converter / epilogue staging compile to LDS/STS instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t a_bytes = BM * BK * 4;            // 16 KB
   const uint32_t b_bytes = p.BN * BK * 4;
   const uint32_t stage_bytes = (a_bytes + b_bytes) * (p.passes == 3 ? 2 : 1);
@@ -127,6 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TC_STAMP(0);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * p.BN;
   const int total_kb = (p.K + BK - 1) / BK;
   const int kb_begin = blockIdx.z * p.kblocks_per_split;
@@ -139,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < p.stages; s++) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
-      mbar_init(&conv[s], 4);
+      mbar_init(&conv[s], TC_WORKERS);
     }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -152,6 +173,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     // ===================== TMA producer (one lane) =====================
@@ -215,11 +237,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(&empty[s]);          // frees the smem slot when these MMAs retire
       }
       umma_commit(tmem_full);            // accumulator complete
+      TC_STAMP(5);
     }
     __syncwarp();
   } else {
     // ===================== converters (3xTF32 split), then epilogue =====================
-    const int ct = threadIdx.x - 64;     // 0..127
+    const int ct = threadIdx.x - 64;     // 0 .. 32*TC_WORKERS-1
     if (p.passes == 3) {
       const uint32_t hi_bytes = a_bytes + b_bytes;
       for (int i = 0; i < nkb; i++) {
@@ -229,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + hi_bytes);
         const int n4 = hi_bytes / 16;
-        for (int e = ct; e < n4; e += 128) {
+        for (int e = ct; e < n4; e += 32 * TC_WORKERS) {
           float4 x = hi[e];
           float4 h, l;
           h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
@@ -244,37 +267,120 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) mbar_arrive(&conv[s]);
       }
     }
-    // ---- epilogue: this warp owns TMEM lanes 32*(warp%4) .. +31  == output rows
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
+    if (ct == 0) TC_STAMP(4);
+    // ---- epilogue: this warp owns TMEM lanes 32*(warp%4) .. +31  == output rows.
+    // tcgen05.ld gives one row per thread; a per-warp smem transpose (the pipeline's stage-0 region
+    // is idle once tmem_full fires) turns that into row-contiguous 128-byte global accesses.
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;             // two warps per quarter split the column chunks
     const Epilogue& ep = p.ep;
     const bool first = (blockIdx.z == 0);
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (row < p.M) {
-        const long long rbase = (long long)row * p.ldc;
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const int col = n0 + c0 + j;
-          if (col < p.N) {
-            float v = ep.alpha * __uint_as_float(r[j]);
-            if (ep.bias && first) v += __ldg(ep.bias + col);
-            if (ep.pre_out) ep.pre_out[rbase + col] = v;
-            if (ep.act == NT_ACT_RELU) v = v < 0.f ? 0.f : v;
-            else if (ep.act == NT_ACT_GELU) v = gelu_f(v);
-            if (ep.dact == NT_ACT_RELU) v = (__ldg(ep.pre_in + rbase + col) > 0.f) ? v : 0.f;
-            else if (ep.dact == NT_ACT_GELU) v *= gelu_grad_f(__ldg(ep.pre_in + rbase + col));
-            if (ep.addend && first) v += __ldg(ep.addend + rbase + col);
-            if (ep.atomic) atomicAdd(p.C + rbase + col, v);
-            else p.C[rbase + col] = v;
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36);
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(ep.pre_out) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(ep.pre_in) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(ep.addend) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
+    const int rsub = lane >> 3, csub = (lane & 7) * 4;
+    const bool has_bias = (ep.bias != nullptr) && first;
+    const bool add_on = ADDEND && first;
+    for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+      const int colv = n0 + c0 + csub;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vec_ok && colv < p.N) {
+        // pull this chunk's global operands towards L1 before blocking on the accumulator
+        if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + colv));
+        if (DACT != 0 || add_on) {
+#pragma unroll 1
+          for (int it = 0; it < 8; it++) {
+            const int gm = m0 + q * 32 + it * 4 + rsub;
+            if (gm < p.M) {
+              const long long idx = (long long)gm * p.ldc + colv;
+              if (DACT != 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(ep.pre_in + idx));
+              if (add_on) asm volatile("prefetch.global.L1 [%0];" ::"l"(ep.addend + idx));
+            }
           }
         }
       }
+      if (c0 == half * 32) {
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        if (ct == 0) TC_STAMP(6);
+      }
+      {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        if (ct == 0 && c0 == 0) TC_STAMP(2);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+      }
+      __syncwarp();
+      if (vec_ok) {
+        if (colv < p.N) {
+          const int gm0 = m0 + q * 32 + rsub;
+          long long idx = (long long)gm0 * p.ldc + colv;
+          const long long istep = 4 * p.ldc;
+          const float* sp = stg + rsub * 36 + csub;
+          const float alpha = ep.alpha;
+#pragma unroll 4
+          for (int it = 0; it < 8; it++, idx += istep, sp += 4 * 36) {
+            if (gm0 + it * 4 < p.M) {
+              float4 v = *reinterpret_cast<const float4*>(sp);
+              v.x = alpha * v.x + b4.x; v.y = alpha * v.y + b4.y;
+              v.z = alpha * v.z + b4.z; v.w = alpha * v.w + b4.w;
+              if (PRE_OUT) *reinterpret_cast<float4*>(ep.pre_out + idx) = v;
+              if (ACT == NT_ACT_RELU) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              } else if (ACT == NT_ACT_GELU) {
+                v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w);
+              }
+              if (DACT != 0) {
+                const float4 pz = __ldg(reinterpret_cast<const float4*>(ep.pre_in + idx));
+                if (DACT == NT_ACT_RELU) {
+                  v.x = pz.x > 0.f ? v.x : 0.f; v.y = pz.y > 0.f ? v.y : 0.f;
+                  v.z = pz.z > 0.f ? v.z : 0.f; v.w = pz.w > 0.f ? v.w : 0.f;
+                } else {
+                  v.x *= gelu_grad_f(pz.x); v.y *= gelu_grad_f(pz.y); v.z *= gelu_grad_f(pz.z); v.w *= gelu_grad_f(pz.w);
+                }
+              }
+              if (add_on) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(ep.addend + idx));
+                v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+              }
+              if (ATOMIC) atomicAdd(reinterpret_cast<float4*>(p.C + idx), v);
+              else *reinterpret_cast<float4*>(p.C + idx) = v;
+            }
+          }
+        }
+      } else {
+        const int col = n0 + c0 + lane;
+        if (col < p.N) {
+          const float b1 = has_bias ? __ldg(ep.bias + col) : 0.f;
+#pragma unroll 1
+          for (int rr = 0; rr < 32; rr++) {
+            const int gm = m0 + q * 32 + rr;
+            if (gm >= p.M) break;
+            const long long idx = (long long)gm * p.ldc + col;
+            float v = ep.alpha * stg[rr * 36 + lane] + b1;
+            if (PRE_OUT) ep.pre_out[idx] = v;
+            if (ACT == NT_ACT_RELU) v = fmaxf(v, 0.f);
+            else if (ACT == NT_ACT_GELU) v = gelu_f(v);
+            if (DACT == NT_ACT_RELU) v = (__ldg(ep.pre_in + idx) > 0.f) ? v : 0.f;
+            else if (DACT == NT_ACT_GELU) v *= gelu_grad_f(__ldg(ep.pre_in + idx));
+            if (add_on) v += __ldg(ep.addend + idx);
+            if (ATOMIC) atomicAdd(p.C + idx, v);
+            else p.C[idx] = v;
+          }
+        }
+      }
+      __syncwarp();
+      if (ct == 0 && c0 == 0) TC_STAMP(3);
     }
     tc_fence_before();
+    if (ct == 0) TC_STAMP(7);
   }
   __syncthreads();
   if (warp == 1) {
@@ -315,13 +421,36 @@ static int make_tmap(CUtensorMap* tm, const float* base, long long inner, long l
   return 0;
 }
 
-static int pick_bn(int N) {
-  if (N % 128 == 0) return 128;
-  if (N % 96 == 0) return 96;
-  if (N >= 112) return 128;
-  if (N > 64) return 96;
-  if (N > 32) return 64;
-  return 32;
+template <int ACT, int DACT, bool PRE_OUT, bool ATOMIC, bool ADDEND>
+static int launch_tc(dim3 grid, size_t smem, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
+  static bool configured = false;
+  if (!configured) {
+    NT_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT, DACT, PRE_OUT, ATOMIC, ADDEND>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    configured = true;
+  }
+  gemm_tc_kernel<ACT, DACT, PRE_OUT, ATOMIC, ADDEND><<<grid, TC_THREADS, smem, g_stream>>>(tmA, tmB, p);
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+// N-tile: the widest of {128,96,64,32} that still yields about one wave of CTAs (small problems are
+// latency-bound, so more, narrower tiles beat fewer wide ones); ties prefer exact divisors of N.
+static int pick_bn(int M, int N, int splits_hint) {
+  const int mt = ceil_div(M, BM) * (splits_hint < 1 ? 1 : splits_hint);
+  const int cand[4] = {128, 96, 64, 32};
+  int best = 32;
+  long long best_score = -1;
+  for (int i = 0; i < 4; i++) {
+    const int bn = cand[i];
+    if (bn > 32 && bn >= 2 * N) continue;
+    const int tiles = mt * ceil_div(N, bn);
+    const long long waste = (long long)ceil_div(N, bn) * bn - N;          // padded columns
+    const int fill = tiles >= (g_sm_count * 3) / 4 ? g_sm_count : tiles;   // >= 3/4 wave counts as full
+    const long long score = (long long)fill * 1000000 - waste * 1000 + bn;
+    if (score > best_score) { best_score = score; best = bn; }
+  }
+  return best;
 }
 
 int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
@@ -339,7 +468,12 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
 
   TcParams p{};
   p.M = d.M; p.N = d.N; p.K = d.K;
-  p.BN = pick_bn(d.N);
+  if (d.splitk > 1) {
+    // split-K fills the machine; take the widest tile without padded columns so A is re-read least
+    p.BN = d.N % 128 == 0 ? 128 : (d.N % 96 == 0 ? 96 : (d.N % 64 == 0 ? 64 : (d.N >= 96 ? 128 : (d.N > 32 ? 64 : 32))));
+  } else {
+    p.BN = pick_bn(d.M, d.N, 1);
+  }
   p.a_mn = a_mn; p.b_mn = b_mn;
   p.passes = passes;
   p.ldc = d.ldc;
@@ -369,14 +503,27 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   if (b_k) { if (make_tmap(&tmB, d.B, d.K, d.N, ldb, p.BN, false)) return 1; }
   else     { if (make_tmap(&tmB, d.B, d.N, d.K, ldb, BK, true)) return 1; }
 
-  static size_t configured = 0;
-  if (smem > configured) {
-    NT_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    configured = 227 * 1024;
-  }
   dim3 grid(ceil_div(d.N, p.BN), ceil_div(d.M, BM), splits);
-  gemm_tc_kernel<<<grid, TC_THREADS, smem, g_stream>>>(tmA, tmB, p);
-  NT_LAUNCH_OK();
+  const Epilogue& e = d.ep;
+  int rc = -1;
+#define NT_TC_CASE(A_, D_, P_, T_, X_)                                                                   \
+  if (rc < 0 && e.act == A_ && e.dact == D_ && (e.pre_out != nullptr) == P_ && (e.atomic != 0) == T_ &&   \
+      (e.addend != nullptr) == X_)                                                                        \
+    rc = launch_tc<A_, D_, P_, T_, X_>(grid, smem, tmA, tmB, p);
+  NT_TC_CASE(0, 0, false, false, false)   // y = xW + b ; dx = dy W^T
+  NT_TC_CASE(0, 0, false, false, true)    // + residual
+  NT_TC_CASE(NT_ACT_GELU, 0, true, false, false)
+  NT_TC_CASE(NT_ACT_RELU, 0, true, false, false)
+  NT_TC_CASE(NT_ACT_GELU, 0, true, false, true)
+  NT_TC_CASE(NT_ACT_RELU, 0, true, false, true)
+  NT_TC_CASE(0, NT_ACT_GELU, false, false, false)
+  NT_TC_CASE(0, NT_ACT_RELU, false, false, false)
+  NT_TC_CASE(0, NT_ACT_GELU, false, false, true)
+  NT_TC_CASE(0, NT_ACT_RELU, false, false, true)
+  NT_TC_CASE(0, 0, false, true, false)    // dW += x^T dy (split-K, red.add)
+#undef NT_TC_CASE
+  if (rc < 0) return 0;                   // epilogue combination without a tensor-core instance -> SIMT
+  if (rc) return rc;
   *handled = true;
   return 0;
 }
