@@ -47,41 +47,71 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* dp, 
 }
 
 // ---------------------------------------------------------------- fused small-N kernels
-__global__ void __launch_bounds__(128) attn_fwd_small_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
-                                                             int mask_kind, float* __restrict__ out,
-                                                             float* __restrict__ P, float* __restrict__ S, int N, int H,
-                                                             int dh, const float* __restrict__ residual) {
-  extern __shared__ float sm[];
-  const int dhp = dh + 1, Np = N + 1;
-  float* sQ = sm;
-  float* sK = sQ + N * dh;
-  float* sV = sK + N * dhp;
-  float* sP = sV + N * dh;
+// One CTA per (sample, head); Q/K/V (and dO, P, dS in backward) live in shared memory.  Every thread
+// owns a 1x4 register tile (4 independent FMA chains, 128-bit LDS), K/V are staged transposed where
+// the contraction runs over dh so that a warp reads consecutive addresses; requires dh % 4 == 0.
+constexpr int ATT_THREADS = 256;
+
+__device__ __forceinline__ int pad4(int n) { return (n + 3) & ~3; }
+
+__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_small_kernel(const float* __restrict__ qkv,
+                                                                      const float* __restrict__ mask, int mask_kind,
+                                                                      float* __restrict__ out, float* __restrict__ P,
+                                                                      float* __restrict__ S, int N, int H, int dh,
+                                                                      const float* __restrict__ residual) {
+  extern __shared__ __align__(16) float sm[];
+  const int Np = pad4(N) + 4;
+  float* sQ = sm;                    // [N][dh]
+  float* sKt = sQ + N * dh;          // [dh][Np]
+  float* sV = sKt + dh * Np;         // [N][dh]
+  float* sP = sV + N * dh;           // [N][Np]
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const int D = H * dh;
-  const int tid = threadIdx.x, nt_ = blockDim.x;
+  const int tid = threadIdx.x;
+  const int dh4 = dh >> 2;
   const float* base = qkv + (long long)b * N * 3 * D + h * dh;
-  for (int e = tid; e < N * dh; e += nt_) {
-    const int i = e / dh, d = e % dh;
-    const float* r = base + (long long)i * 3 * D + d;
-    sQ[i * dh + d] = r[0];
-    sK[i * dhp + d] = r[D];
-    sV[i * dh + d] = r[2 * D];
+  for (int e = tid; e < N * dh4; e += ATT_THREADS) {
+    const int i = e / dh4, d4 = (e % dh4) * 4;
+    const float* r = base + (long long)i * 3 * D + d4;
+    const float4 q = __ldg(reinterpret_cast<const float4*>(r));
+    const float4 k = __ldg(reinterpret_cast<const float4*>(r + D));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(r + 2 * D));
+    *reinterpret_cast<float4*>(sQ + i * dh + d4) = q;
+    *reinterpret_cast<float4*>(sV + i * dh + d4) = v;
+    sKt[(d4 + 0) * Np + i] = k.x; sKt[(d4 + 1) * Np + i] = k.y;
+    sKt[(d4 + 2) * Np + i] = k.z; sKt[(d4 + 3) * Np + i] = k.w;
   }
+  // zero the padded key columns so the 4-wide tiles read defined data
+  for (int e = tid; e < dh * (Np - N); e += ATT_THREADS) sKt[(e / (Np - N)) * Np + N + e % (Np - N)] = 0.f;
   __syncthreads();
   const float scale = 1.0f / sqrtf((float)dh);
-  for (int e = tid; e < N * N; e += nt_) {
-    const int i = e / N, j = e % N;
-    float acc = 0.f;
-    for (int d = 0; d < dh; d++) acc = fmaf(sQ[i * dh + d], sK[j * dhp + d], acc);
-    acc *= scale;                                           // attention.py:37
-    if (S) S[(long long)bh * N * N + e] = acc;              // att_col, attdecoderblock.py:58-59
-    if (mask_kind == NT_MASK_CAUSAL) { if (j > i) acc = -INFINITY; }
-    else if (mask_kind == NT_MASK_DENSE) acc += mask[i * N + j];   // attention.py:38-39
-    sP[i * Np + j] = acc;
+  const int ng = pad4(N) >> 2;                         // column groups of 4
+  for (int e = tid; e < N * ng; e += ATT_THREADS) {
+    const int i = e / ng, j0 = (e % ng) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* qi = sQ + i * dh;
+#pragma unroll 4
+    for (int d = 0; d < dh; d++) {
+      const float qv = qi[d];
+      const float4 kv = *reinterpret_cast<const float4*>(sKt + d * Np + j0);
+      acc.x = fmaf(qv, kv.x, acc.x); acc.y = fmaf(qv, kv.y, acc.y);
+      acc.z = fmaf(qv, kv.z, acc.z); acc.w = fmaf(qv, kv.w, acc.w);
+    }
+    float a[4] = {acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale};   // attention.py:37
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int j = j0 + t;
+      if (j < N) {
+        float v = a[t];
+        if (S) S[(long long)bh * N * N + i * N + j] = v;                          // att_col
+        if (mask_kind == NT_MASK_CAUSAL) { if (j > i) v = -INFINITY; }
+        else if (mask_kind == NT_MASK_DENSE) v += mask[i * N + j];                // attention.py:38-39
+        sP[i * Np + j] = v;
+      }
+    }
   }
   __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31, nw = nt_ >> 5;
+  const int warp = tid >> 5, lane = tid & 31, nw = ATT_THREADS >> 5;
   for (int i = warp; i < N; i += nw) {
     float mx = -INFINITY;
     for (int j = lane; j < N; j += 32) mx = fmaxf(mx, sP[i * Np + j]);
@@ -91,56 +121,83 @@ __global__ void __launch_bounds__(128) attn_fwd_small_kernel(const float* __rest
     s = warp_sum(s);
     const float inv = 1.0f / s;
     for (int j = lane; j < N; j += 32) {
-      float pv = sP[i * Np + j] * inv;
+      const float pv = sP[i * Np + j] * inv;
       sP[i * Np + j] = pv;
-      P[((long long)bh * N + i) * N + j] = pv;              // atg__
+      P[((long long)bh * N + i) * N + j] = pv;                                     // atg__
     }
   }
   __syncthreads();
-  for (int e = tid; e < N * dh; e += nt_) {
-    const int i = e / dh, d = e % dh;
-    float acc = 0.f;
-    for (int j = 0; j < N; j++) acc = fmaf(sP[i * Np + j], sV[j * dh + d], acc);
-    const long long o = ((long long)b * N + i) * D + h * dh + d;
-    out[o] = residual ? acc + residual[o] : acc;
+  for (int e = tid; e < N * dh4; e += ATT_THREADS) {
+    const int i = e / dh4, d4 = (e % dh4) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* pi = sP + i * Np;
+#pragma unroll 4
+    for (int j = 0; j < N; j++) {
+      const float pv = pi[j];
+      const float4 vv = *reinterpret_cast<const float4*>(sV + j * dh + d4);
+      acc.x = fmaf(pv, vv.x, acc.x); acc.y = fmaf(pv, vv.y, acc.y);
+      acc.z = fmaf(pv, vv.z, acc.z); acc.w = fmaf(pv, vv.w, acc.w);
+    }
+    const long long o = ((long long)b * N + i) * D + h * dh + d4;
+    if (residual) {
+      const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + o));
+      acc.x += rr.x; acc.y += rr.y; acc.z += rr.z; acc.w += rr.w;
+    }
+    *reinterpret_cast<float4*>(out + o) = acc;
   }
 }
 
-__global__ void __launch_bounds__(128) attn_bwd_small_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
-                                                             const float* __restrict__ P, float* __restrict__ dqkv,
-                                                             int N, int H, int dh) {
-  extern __shared__ float sm[];
-  const int dhp = dh + 1, Np = N + 1;
-  float* sQ = sm;                  // [N][dh]
-  float* sK = sQ + N * dh;         // [N][dh]
-  float* sV = sK + N * dh;         // [N][dh+1]
-  float* sdO = sV + N * dhp;       // [N][dh]
-  float* sP = sdO + N * dh;        // [N][N+1]
-  float* sdS = sP + N * Np;        // [N][N+1]
+__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_small_kernel(const float* __restrict__ dout,
+                                                                      const float* __restrict__ qkv,
+                                                                      const float* __restrict__ P,
+                                                                      float* __restrict__ dqkv, int N, int H, int dh) {
+  extern __shared__ __align__(16) float sm[];
+  const int Np = pad4(N) + 4;
+  float* sQ = sm;                    // [N][dh]
+  float* sK = sQ + N * dh;           // [N][dh]
+  float* sVt = sK + N * dh;          // [dh][Np]
+  float* sdO = sVt + dh * Np;        // [N][dh]
+  float* sP = sdO + N * dh;          // [N][Np]
+  float* sdS = sP + N * Np;          // [N][Np]
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const int D = H * dh;
-  const int tid = threadIdx.x, nt_ = blockDim.x;
+  const int tid = threadIdx.x;
+  const int dh4 = dh >> 2;
   const float* base = qkv + (long long)b * N * 3 * D + h * dh;
-  for (int e = tid; e < N * dh; e += nt_) {
-    const int i = e / dh, d = e % dh;
-    const float* r = base + (long long)i * 3 * D + d;
-    sQ[i * dh + d] = r[0];
-    sK[i * dh + d] = r[D];
-    sV[i * dhp + d] = r[2 * D];
-    sdO[i * dh + d] = dout[((long long)b * N + i) * D + h * dh + d];
+  for (int e = tid; e < N * dh4; e += ATT_THREADS) {
+    const int i = e / dh4, d4 = (e % dh4) * 4;
+    const float* r = base + (long long)i * 3 * D + d4;
+    const float4 q = __ldg(reinterpret_cast<const float4*>(r));
+    const float4 k = __ldg(reinterpret_cast<const float4*>(r + D));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(r + 2 * D));
+    const float4 g = __ldg(reinterpret_cast<const float4*>(dout + ((long long)b * N + i) * D + h * dh + d4));
+    *reinterpret_cast<float4*>(sQ + i * dh + d4) = q;
+    *reinterpret_cast<float4*>(sK + i * dh + d4) = k;
+    *reinterpret_cast<float4*>(sdO + i * dh + d4) = g;
+    sVt[(d4 + 0) * Np + i] = v.x; sVt[(d4 + 1) * Np + i] = v.y;
+    sVt[(d4 + 2) * Np + i] = v.z; sVt[(d4 + 3) * Np + i] = v.w;
   }
-  for (int e = tid; e < N * N; e += nt_) sP[(e / N) * Np + e % N] = P[(long long)bh * N * N + e];
+  for (int e = tid; e < dh * (Np - N); e += ATT_THREADS) sVt[(e / (Np - N)) * Np + N + e % (Np - N)] = 0.f;
+  for (int e = tid; e < N * N; e += ATT_THREADS) sP[(e / N) * Np + e % N] = __ldg(P + (long long)bh * N * N + e);
   __syncthreads();
   // dP = dO V^T   (attention.py:74)
-  for (int e = tid; e < N * N; e += nt_) {
-    const int i = e / N, j = e % N;
-    float acc = 0.f;
-    for (int d = 0; d < dh; d++) acc = fmaf(sdO[i * dh + d], sV[j * dhp + d], acc);
-    sdS[i * Np + j] = acc;
+  const int ng = pad4(N) >> 2;
+  for (int e = tid; e < N * ng; e += ATT_THREADS) {
+    const int i = e / ng, j0 = (e % ng) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* gi = sdO + i * dh;
+#pragma unroll 4
+    for (int d = 0; d < dh; d++) {
+      const float gv = gi[d];
+      const float4 vv = *reinterpret_cast<const float4*>(sVt + d * Np + j0);
+      acc.x = fmaf(gv, vv.x, acc.x); acc.y = fmaf(gv, vv.y, acc.y);
+      acc.z = fmaf(gv, vv.z, acc.z); acc.w = fmaf(gv, vv.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(sdS + i * Np + j0) = acc;
   }
   __syncthreads();
-  // dS = P o (dP - rowsum(dP o P))   (attention.py:75)
-  const int warp = tid >> 5, lane = tid & 31, nw = nt_ >> 5;
+  // dS = P o (dP - rowsum(dP o P))   (attention.py:75, closed form of the per-row Jacobian)
+  const int warp = tid >> 5, lane = tid & 31, nw = ATT_THREADS >> 5;
   for (int i = warp; i < N; i += nw) {
     float s = 0.f;
     for (int j = lane; j < N; j += 32) s += sdS[i * Np + j] * sP[i * Np + j];
@@ -150,23 +207,50 @@ __global__ void __launch_bounds__(128) attn_bwd_small_kernel(const float* __rest
   __syncthreads();
   const float scale = 1.0f / sqrtf((float)dh);
   float* obase = dqkv + (long long)b * N * 3 * D + h * dh;
-  for (int e = tid; e < N * dh; e += nt_) {
-    const int r = e / dh, d = e % dh;
-    float aq = 0.f, ak = 0.f, av = 0.f;
-    for (int t = 0; t < N; t++) {
-      aq = fmaf(sdS[r * Np + t], sK[t * dh + d], aq);       // dQ = dS K       (attention.py:78)
-      ak = fmaf(sdS[t * Np + r], sQ[t * dh + d], ak);       // dK = dS^T Q     (attention.py:79)
-      av = fmaf(sP[t * Np + r], sdO[t * dh + d], av);       // dV = P^T dO     (attention.py:76)
+  // dQ = dS K / sqrt(dh)   (attention.py:78): item = (row i, 4 features)
+  for (int e = tid; e < N * dh4; e += ATT_THREADS) {
+    const int i = e / dh4, d4 = (e % dh4) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* si = sdS + i * Np;
+#pragma unroll 4
+    for (int j = 0; j < N; j++) {
+      const float sv = si[j];
+      const float4 kv = *reinterpret_cast<const float4*>(sK + j * dh + d4);
+      acc.x = fmaf(sv, kv.x, acc.x); acc.y = fmaf(sv, kv.y, acc.y);
+      acc.z = fmaf(sv, kv.z, acc.z); acc.w = fmaf(sv, kv.w, acc.w);
     }
-    float* o = obase + (long long)r * 3 * D + d;
-    o[0] = aq * scale;
-    o[D] = ak * scale;
-    o[2 * D] = av;
+    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+    *reinterpret_cast<float4*>(obase + (long long)i * 3 * D + d4) = acc;
+  }
+  // dK = dS^T Q / sqrt(dh) (attention.py:79) and dV = P^T dO (attention.py:76): item = (key j, 4 features),
+  // j fastest so a warp walks a row of dS / P
+  for (int e = tid; e < N * dh4; e += ATT_THREADS) {
+    const int j = e % N, d4 = (e / N) * 4;
+    float4 ak = make_float4(0.f, 0.f, 0.f, 0.f), av = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int i = 0; i < N; i++) {
+      const float sv = sdS[i * Np + j], pv = sP[i * Np + j];
+      const float4 qv = *reinterpret_cast<const float4*>(sQ + i * dh + d4);
+      const float4 gv = *reinterpret_cast<const float4*>(sdO + i * dh + d4);
+      ak.x = fmaf(sv, qv.x, ak.x); ak.y = fmaf(sv, qv.y, ak.y); ak.z = fmaf(sv, qv.z, ak.z); ak.w = fmaf(sv, qv.w, ak.w);
+      av.x = fmaf(pv, gv.x, av.x); av.y = fmaf(pv, gv.y, av.y); av.z = fmaf(pv, gv.z, av.z); av.w = fmaf(pv, gv.w, av.w);
+    }
+    ak.x *= scale; ak.y *= scale; ak.z *= scale; ak.w *= scale;
+    float* o = obase + (long long)j * 3 * D + d4;
+    *reinterpret_cast<float4*>(o + D) = ak;
+    *reinterpret_cast<float4*>(o + 2 * D) = av;
   }
 }
 
-static size_t fwd_small_smem(int N, int dh) { return sizeof(float) * ((size_t)N * dh * 2 + (size_t)N * (dh + 1) + (size_t)N * (N + 1)); }
-static size_t bwd_small_smem(int N, int dh) { return sizeof(float) * ((size_t)N * dh * 3 + (size_t)N * (dh + 1) + 2 * (size_t)N * (N + 1)); }
+static size_t fwd_small_smem(int N, int dh) {
+  const int Np = ((N + 3) & ~3) + 4;
+  return sizeof(float) * ((size_t)N * dh * 2 + (size_t)dh * Np + (size_t)N * Np);
+}
+static size_t bwd_small_smem(int N, int dh) {
+  const int Np = ((N + 3) & ~3) + 4;
+  return sizeof(float) * ((size_t)N * dh * 3 + (size_t)dh * Np + 2 * (size_t)N * Np);
+}
+static bool small_ok(int N, int H, int dh) { return N <= 64 && dh <= 64 && (dh & 3) == 0; }
 
 static int softmax_rows(const float* x, float* p, long long rows, int cols, const float* mask, int mask_kind, int N) {
   if (rows == 0) return 0;
@@ -202,14 +286,14 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
   NT_REQUIRE(mask_kind != NT_MASK_DENSE || mask, "nt_attention_fwd: dense mask_kind needs a mask");
   if (B == 0) return 0;
   const int D = H * dh;
-  if (N <= 64 && dh <= 64) {
+  if (small_ok(N, H, dh)) {
     size_t smem = fwd_small_smem(N, dh);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
       NT_CHECK(cudaFuncSetAttribute(attn_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
-    attn_fwd_small_kernel<<<B * H, 128, smem, g_stream>>>(qkv, mask, mask_kind, out, P, S, N, H, dh, residual);
+    attn_fwd_small_kernel<<<B * H, ATT_THREADS, smem, g_stream>>>(qkv, mask, mask_kind, out, P, S, N, H, dh, residual);
     NT_LAUNCH_OK();
     return 0;
   }
@@ -244,14 +328,14 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
   NT_REQUIRE(B >= 0 && N > 0 && H > 0 && dh > 0, "nt_attention_bwd: bad shape");
   if (B == 0) return 0;
   const int D = H * dh;
-  if (N <= 64 && dh <= 64) {
+  if (small_ok(N, H, dh)) {
     size_t smem = bwd_small_smem(N, dh);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
       NT_CHECK(cudaFuncSetAttribute(attn_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
-    attn_bwd_small_kernel<<<B * H, 128, smem, g_stream>>>(dout, qkv, P, dqkv, N, H, dh);
+    attn_bwd_small_kernel<<<B * H, ATT_THREADS, smem, g_stream>>>(dout, qkv, P, dqkv, N, H, dh);
     NT_LAUNCH_OK();
     return 0;
   }

@@ -87,6 +87,86 @@ __global__ void ln_bwd_param_kernel(const float* __restrict__ dy, const float* _
   }
 }
 
+// Fused backward: one pass over x and dy produces dx AND the dgamma/dbeta partials.  A CTA of 8 warps owns
+// LN_ROWS rows; each lane keeps its columns (c = lane + 32k) of x/dy in registers, so the row reductions are
+// warp shuffles and the column reductions are register accumulators -> smem across warps -> one atomicAdd
+// per column per CTA.  NC = columns per lane (D <= 32*NC).
+constexpr int LN_ROWS = 32;
+template <int NC>
+__global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ gamma, float* __restrict__ dx,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
+                                                           int D, const float* __restrict__ addend) {
+  extern __shared__ float red[];                 // [8 warps][2][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * LN_ROWS;
+  float g[NC], ag[NC], ab[NC];
+#pragma unroll
+  for (int k = 0; k < NC; k++) {
+    const int c = lane + 32 * k;
+    g[k] = c < D ? gamma[c] : 0.f;
+    ag[k] = 0.f;
+    ab[k] = 0.f;
+  }
+  const float invD = 1.0f / D;
+  for (int r = r0 + warp; r < min(M, r0 + LN_ROWS); r += 8) {
+    const long long off = (long long)r * D;
+    const float mu = mean[r], rs = rstd[r];
+    float dyv[NC], xh[NC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+      const int c = lane + 32 * k;
+      dyv[k] = c < D ? dy[off + c] : 0.f;
+      xh[k] = c < D ? (x[off + c] - mu) * rs : 0.f;
+      const float gdy = g[k] * dyv[k];
+      s1 += gdy;
+      s2 += gdy * xh[k];
+      ag[k] = fmaf(xh[k], dyv[k], ag[k]);
+      ab[k] += dyv[k];
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    if (dx) {
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        const int c = lane + 32 * k;
+        if (c < D) {
+          float o = rs * (g[k] * dyv[k] - s1 - xh[k] * s2);
+          if (addend) o += addend[off + c];
+          dx[off + c] = o;
+        }
+      }
+    }
+  }
+  if (dgamma) {
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+      const int c = lane + 32 * k;
+      if (c < D) { red[(warp * 2) * D + c] = ag[k]; red[(warp * 2 + 1) * D + c] = ab[k]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += 256) {
+      float tg = 0.f, tb = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; w++) { tg += red[(w * 2) * D + c]; tb += red[(w * 2 + 1) * D + c]; }
+      atomicAdd(dgamma + c, tg);
+      atomicAdd(dbeta + c, tb);
+    }
+  }
+}
+
+template <int NC>
+static int launch_ln_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                               float* dx, float* dgamma, float* dbeta, int M, int D, const float* addend) {
+  const size_t smem = sizeof(float) * 16 * (size_t)D;
+  ln_bwd_fused_kernel<NC><<<ceil_div(M, LN_ROWS), 256, smem, g_stream>>>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D,
+                                                                         addend);
+  NT_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace nt
 using namespace nt;
 
@@ -109,6 +189,12 @@ int nt_layernorm_bwd(const float* dy, const float* x, const float* mean, const f
   NT_ENTRY();
   NT_REQUIRE(M >= 0 && D > 0, "nt_layernorm_bwd: bad shape M=%d D=%d", M, D);
   if (M == 0) return 0;
+  if (D <= 768 && (dgamma != nullptr) == (dbeta != nullptr)) {
+    if (D <= 128) return launch_ln_bwd_fused<4>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
+    if (D <= 256) return launch_ln_bwd_fused<8>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
+    if (D <= 384) return launch_ln_bwd_fused<12>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
+    return launch_ln_bwd_fused<24>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
+  }
   if (dgamma && dbeta) {
     int rows_per_block = M >= 8192 ? 512 : 128;
     dim3 grid(ceil_div(D, 32), ceil_div(M, rows_per_block));

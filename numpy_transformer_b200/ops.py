@@ -71,7 +71,7 @@ def attention_bwd(dout, qkv, P, H):
     D = three_d // 3
     dh = D // H
     dqkv = qkv.empty_like()
-    scratch = None if (N <= 64 and dh <= 64) else P.empty_like()
+    scratch = None if (N <= 64 and dh <= 64 and dh % 4 == 0) else P.empty_like()
     lib.nt_attention_bwd(dout.ptr, qkv.ptr, P.ptr, dqkv.ptr, ptr_or_null(scratch), B, N, H, dh)
     return dqkv
 
