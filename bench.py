@@ -208,17 +208,18 @@ def run_ours(args):
     e2e = dict(value=units * world * K / e2e_s_max, unit=unit, h2d_bytes_per_step=ts.h2d_bytes, d2h_bytes_per_step=4,
                timing="host wall clock around K public step() calls, max over ranks")
 
-    # ---------------- roofline of the dominant kernel: eager pass with CUDA events around every op
+    # ---------------- roofline of the dominant kernel: the same step captured with a CUDA-event pair around every op
+    # (event-record graph nodes), replayed; durations are device times with no host gaps between ops
     pk = peaks()
-    prof_steps = 3
-    ts_prof = ts
-    ts_prof.use_graph = False
-    lib.profile_begin()
+    prof_steps = 5
+    pg, precs = ts.capture_profiled()
+    recs = []
     for _ in range(prof_steps):
         lib.nt_flush_l2()
-        ts_prof.run_device()
-    recs = lib.profile_end()
-    ts_prof.use_graph = True
+        lib.nt_graph_launch(pg)
+        lib.nt_sync()
+        recs += lib.profile_read(precs)
+    ts.steps_done += prof_steps
     agg = {}
     for name, a, ms_ in recs:
         key = (name, a)
@@ -271,6 +272,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
+    lib.nt_graph_destroy(pg)
+    ts.close()
     if dp:
         dp.shutdown()
     return out

@@ -43,6 +43,7 @@ int nt_sync(void);
 int nt_stream_handle(void** cuda_stream);
 int nt_event_create(void** ev);
 int nt_event_record(void* ev);
+int nt_event_record_external(void* ev);                   /* capturable: becomes a graph event-record node */
 int nt_event_elapsed_ms(void* ev0, void* ev1, float* ms);  /* synchronises on ev1 */
 int nt_event_destroy(void* ev);
 /* CUDA-graph capture of whatever is enqueued between begin and end (one step of the trainer

@@ -47,14 +47,32 @@ class _Lib:
         self._dll = None
         self.protos = parse_header()
         self._prof = None
+        self._prof_external = False
 
     # ---- op-level CUDA-event profiler (bench.py roofline leg): every op call is bracketed by a
     # pair of events on the library stream; durations are read back in profile_end().
     _PROFILED = ("nt_linear_", "nt_layernorm_", "nt_attention_", "nt_cross_entropy", "nt_sgd", "nt_adam_star",
                  "nt_patchify", "nt_add", "nt_embedding_", "nt_gelu_", "nt_relu_", "nt_softmax_", "nt_dp_")
 
-    def profile_begin(self):
+    def profile_begin(self, external=False):
+        """external=True records with cudaEventRecordExternal so the pairs survive stream capture as graph
+        nodes (per-op device times of a replayed graph, no host gaps between ops)."""
         self._prof = []
+        self._prof_external = external
+
+    def profile_pause(self):
+        recs, self._prof = self._prof, None
+        return recs
+
+    def profile_read(self, recs):
+        import ctypes as C
+        dll = self.load()
+        out = []
+        for name, args, e0, e1 in recs:
+            ms = C.c_float(0)
+            dll.nt_event_elapsed_ms(e0, e1, C.byref(ms))
+            out.append((name, args, ms.value))
+        return out
 
     def profile_end(self):
         import ctypes as C
@@ -96,9 +114,10 @@ class _Lib:
                     e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
                     self._dll.nt_event_create(ctypes.byref(e0))
                     self._dll.nt_event_create(ctypes.byref(e1))
-                    self._dll.nt_event_record(e0)
+                    rec = self._dll.nt_event_record_external if self._prof_external else self._dll.nt_event_record
+                    rec(e0)
                     rc = fn(*a)
-                    self._dll.nt_event_record(e1)
+                    rec(e1)
                     self._prof.append((name, tuple(x for x in a if isinstance(x, float) or (isinstance(x, int) and x < (1 << 31))), e0, e1))
                 else:
                     rc = fn(*a)

@@ -47,12 +47,22 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* dp, 
 }
 
 // ---------------------------------------------------------------- fused small-N kernels
-// One CTA per (sample, head); Q/K/V (and dO, P, dS in backward) live in shared memory.  Every thread
-// owns a 1x4 register tile (4 independent FMA chains, 128-bit LDS), K/V are staged transposed where
-// the contraction runs over dh so that a warp reads consecutive addresses; requires dh % 4 == 0.
+// One CTA per (sample, head); Q/K/V (and dO, P, dS in backward) live in shared memory.  Every thread owns
+// a 4x4 register tile fed by 128-bit LDS (16 FMA per two loads: a 1x4 tile is 5x shared-memory-bandwidth
+// bound).  Operands whose tile runs along the token axis are staged transposed ([dh][Np]).  dh % 4 == 0.
 constexpr int ATT_THREADS = 256;
 
 __device__ __forceinline__ int pad4(int n) { return (n + 3) & ~3; }
+
+#define NT_FMA4x4(acc, a4, b4)                                                                                   \
+  acc[0][0] = fmaf(a4.x, b4.x, acc[0][0]); acc[0][1] = fmaf(a4.x, b4.y, acc[0][1]);                                \
+  acc[0][2] = fmaf(a4.x, b4.z, acc[0][2]); acc[0][3] = fmaf(a4.x, b4.w, acc[0][3]);                                \
+  acc[1][0] = fmaf(a4.y, b4.x, acc[1][0]); acc[1][1] = fmaf(a4.y, b4.y, acc[1][1]);                                \
+  acc[1][2] = fmaf(a4.y, b4.z, acc[1][2]); acc[1][3] = fmaf(a4.y, b4.w, acc[1][3]);                                \
+  acc[2][0] = fmaf(a4.z, b4.x, acc[2][0]); acc[2][1] = fmaf(a4.z, b4.y, acc[2][1]);                                \
+  acc[2][2] = fmaf(a4.z, b4.z, acc[2][2]); acc[2][3] = fmaf(a4.z, b4.w, acc[2][3]);                                \
+  acc[3][0] = fmaf(a4.w, b4.x, acc[3][0]); acc[3][1] = fmaf(a4.w, b4.y, acc[3][1]);                                \
+  acc[3][2] = fmaf(a4.w, b4.z, acc[3][2]); acc[3][3] = fmaf(a4.w, b4.w, acc[3][3]);
 
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_small_kernel(const float* __restrict__ qkv,
                                                                       const float* __restrict__ mask, int mask_kind,
@@ -60,52 +70,51 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_small_kernel(const float
                                                                       float* __restrict__ S, int N, int H, int dh,
                                                                       const float* __restrict__ residual) {
   extern __shared__ __align__(16) float sm[];
-  const int Np = pad4(N) + 4;
-  float* sQ = sm;                    // [N][dh]
-  float* sKt = sQ + N * dh;          // [dh][Np]
+  const int N4 = pad4(N), Np = N4 + 4;
+  float* sQt = sm;                   // [dh][Np]
+  float* sKt = sQt + dh * Np;        // [dh][Np]
   float* sV = sKt + dh * Np;         // [N][dh]
-  float* sP = sV + N * dh;           // [N][Np]
+  float* sP = sV + N * dh;           // [N4][Np]
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const int D = H * dh;
   const int tid = threadIdx.x;
-  const int dh4 = dh >> 2;
+  const int dh4 = dh >> 2, ng = N4 >> 2;
   const float* base = qkv + (long long)b * N * 3 * D + h * dh;
-  for (int e = tid; e < N * dh4; e += ATT_THREADS) {
+  for (int e = tid; e < N4 * dh4; e += ATT_THREADS) {
     const int i = e / dh4, d4 = (e % dh4) * 4;
-    const float* r = base + (long long)i * 3 * D + d4;
-    const float4 q = __ldg(reinterpret_cast<const float4*>(r));
-    const float4 k = __ldg(reinterpret_cast<const float4*>(r + D));
-    const float4 v = __ldg(reinterpret_cast<const float4*>(r + 2 * D));
-    *reinterpret_cast<float4*>(sQ + i * dh + d4) = q;
-    *reinterpret_cast<float4*>(sV + i * dh + d4) = v;
-    sKt[(d4 + 0) * Np + i] = k.x; sKt[(d4 + 1) * Np + i] = k.y;
-    sKt[(d4 + 2) * Np + i] = k.z; sKt[(d4 + 3) * Np + i] = k.w;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q;
+    if (i < N) {
+      const float* r = base + (long long)i * 3 * D + d4;
+      q = __ldg(reinterpret_cast<const float4*>(r));
+      k = __ldg(reinterpret_cast<const float4*>(r + D));
+      *reinterpret_cast<float4*>(sV + i * dh + d4) = __ldg(reinterpret_cast<const float4*>(r + 2 * D));
+    }
+    sQt[(d4 + 0) * Np + i] = q.x; sQt[(d4 + 1) * Np + i] = q.y; sQt[(d4 + 2) * Np + i] = q.z; sQt[(d4 + 3) * Np + i] = q.w;
+    sKt[(d4 + 0) * Np + i] = k.x; sKt[(d4 + 1) * Np + i] = k.y; sKt[(d4 + 2) * Np + i] = k.z; sKt[(d4 + 3) * Np + i] = k.w;
   }
-  // zero the padded key columns so the 4-wide tiles read defined data
-  for (int e = tid; e < dh * (Np - N); e += ATT_THREADS) sKt[(e / (Np - N)) * Np + N + e % (Np - N)] = 0.f;
   __syncthreads();
   const float scale = 1.0f / sqrtf((float)dh);
-  const int ng = pad4(N) >> 2;                         // column groups of 4
-  for (int e = tid; e < N * ng; e += ATT_THREADS) {
-    const int i = e / ng, j0 = (e % ng) * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* qi = sQ + i * dh;
+  for (int e = tid; e < ng * ng; e += ATT_THREADS) {
+    const int i0 = (e / ng) * 4, j0 = (e % ng) * 4;
+    float acc[4][4] = {};
 #pragma unroll 4
     for (int d = 0; d < dh; d++) {
-      const float qv = qi[d];
-      const float4 kv = *reinterpret_cast<const float4*>(sKt + d * Np + j0);
-      acc.x = fmaf(qv, kv.x, acc.x); acc.y = fmaf(qv, kv.y, acc.y);
-      acc.z = fmaf(qv, kv.z, acc.z); acc.w = fmaf(qv, kv.w, acc.w);
+      const float4 q4 = *reinterpret_cast<const float4*>(sQt + d * Np + i0);
+      const float4 k4 = *reinterpret_cast<const float4*>(sKt + d * Np + j0);
+      NT_FMA4x4(acc, q4, k4)
     }
-    float a[4] = {acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale};   // attention.py:37
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const int j = j0 + t;
-      if (j < N) {
-        float v = a[t];
-        if (S) S[(long long)bh * N * N + i * N + j] = v;                          // att_col
-        if (mask_kind == NT_MASK_CAUSAL) { if (j > i) v = -INFINITY; }
-        else if (mask_kind == NT_MASK_DENSE) v += mask[i * N + j];                // attention.py:38-39
+    for (int r = 0; r < 4; r++) {
+      const int i = i0 + r;
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int j = j0 + t;
+        float v = acc[r][t] * scale;                                               // attention.py:37
+        if (i < N && j < N) {
+          if (S) S[(long long)bh * N * N + i * N + j] = v;                          // att_col
+          if (mask_kind == NT_MASK_CAUSAL) { if (j > i) v = -INFINITY; }
+          else if (mask_kind == NT_MASK_DENSE) v += mask[i * N + j];                // attention.py:38-39
+        }
         sP[i * Np + j] = v;
       }
     }
@@ -127,23 +136,29 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_small_kernel(const float
     }
   }
   __syncthreads();
-  for (int e = tid; e < N * dh4; e += ATT_THREADS) {
-    const int i = e / dh4, d4 = (e % dh4) * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* pi = sP + i * Np;
-#pragma unroll 4
+  for (int e = tid; e < ng * dh4; e += ATT_THREADS) {
+    const int i0 = (e / dh4) * 4, d4 = (e % dh4) * 4;
+    float acc[4][4] = {};
+    const float* p0 = sP + i0 * Np;
+#pragma unroll 2
     for (int j = 0; j < N; j++) {
-      const float pv = pi[j];
-      const float4 vv = *reinterpret_cast<const float4*>(sV + j * dh + d4);
-      acc.x = fmaf(pv, vv.x, acc.x); acc.y = fmaf(pv, vv.y, acc.y);
-      acc.z = fmaf(pv, vv.z, acc.z); acc.w = fmaf(pv, vv.w, acc.w);
+      const float4 p4 = make_float4(p0[j], p0[Np + j], p0[2 * Np + j], p0[3 * Np + j]);
+      const float4 v4 = *reinterpret_cast<const float4*>(sV + j * dh + d4);
+      NT_FMA4x4(acc, p4, v4)
     }
-    const long long o = ((long long)b * N + i) * D + h * dh + d4;
-    if (residual) {
-      const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + o));
-      acc.x += rr.x; acc.y += rr.y; acc.z += rr.z; acc.w += rr.w;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int i = i0 + r;
+      if (i < N) {
+        const long long o = ((long long)b * N + i) * D + h * dh + d4;
+        float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        if (residual) {
+          const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + o));
+          v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+        }
+        *reinterpret_cast<float4*>(out + o) = v;
+      }
     }
-    *reinterpret_cast<float4*>(out + o) = acc;
   }
 }
 
@@ -152,103 +167,114 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_small_kernel(const float
                                                                       const float* __restrict__ P,
                                                                       float* __restrict__ dqkv, int N, int H, int dh) {
   extern __shared__ __align__(16) float sm[];
-  const int Np = pad4(N) + 4;
+  const int N4 = pad4(N), Np = N4 + 4;
   float* sQ = sm;                    // [N][dh]
   float* sK = sQ + N * dh;           // [N][dh]
-  float* sVt = sK + N * dh;          // [dh][Np]
-  float* sdO = sVt + dh * Np;        // [N][dh]
-  float* sP = sdO + N * dh;          // [N][Np]
-  float* sdS = sP + N * Np;          // [N][Np]
+  float* sdO = sK + N * dh;          // [N][dh]
+  float* sVt = sdO + N * dh;         // [dh][Np]
+  float* sdOt = sVt + dh * Np;       // [dh][Np]
+  float* sP = sdOt + dh * Np;        // [N4][Np]
+  float* sdS = sP + N4 * Np;         // [N4][Np]
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const int D = H * dh;
   const int tid = threadIdx.x;
-  const int dh4 = dh >> 2;
+  const int dh4 = dh >> 2, ng = N4 >> 2;
   const float* base = qkv + (long long)b * N * 3 * D + h * dh;
-  for (int e = tid; e < N * dh4; e += ATT_THREADS) {
+  for (int e = tid; e < N4 * dh4; e += ATT_THREADS) {
     const int i = e / dh4, d4 = (e % dh4) * 4;
-    const float* r = base + (long long)i * 3 * D + d4;
-    const float4 q = __ldg(reinterpret_cast<const float4*>(r));
-    const float4 k = __ldg(reinterpret_cast<const float4*>(r + D));
-    const float4 v = __ldg(reinterpret_cast<const float4*>(r + 2 * D));
-    const float4 g = __ldg(reinterpret_cast<const float4*>(dout + ((long long)b * N + i) * D + h * dh + d4));
-    *reinterpret_cast<float4*>(sQ + i * dh + d4) = q;
-    *reinterpret_cast<float4*>(sK + i * dh + d4) = k;
-    *reinterpret_cast<float4*>(sdO + i * dh + d4) = g;
-    sVt[(d4 + 0) * Np + i] = v.x; sVt[(d4 + 1) * Np + i] = v.y;
-    sVt[(d4 + 2) * Np + i] = v.z; sVt[(d4 + 3) * Np + i] = v.w;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), g = v;
+    if (i < N) {
+      const float* r = base + (long long)i * 3 * D + d4;
+      *reinterpret_cast<float4*>(sQ + i * dh + d4) = __ldg(reinterpret_cast<const float4*>(r));
+      *reinterpret_cast<float4*>(sK + i * dh + d4) = __ldg(reinterpret_cast<const float4*>(r + D));
+      v = __ldg(reinterpret_cast<const float4*>(r + 2 * D));
+      g = __ldg(reinterpret_cast<const float4*>(dout + ((long long)b * N + i) * D + h * dh + d4));
+      *reinterpret_cast<float4*>(sdO + i * dh + d4) = g;
+    }
+    sVt[(d4 + 0) * Np + i] = v.x; sVt[(d4 + 1) * Np + i] = v.y; sVt[(d4 + 2) * Np + i] = v.z; sVt[(d4 + 3) * Np + i] = v.w;
+    sdOt[(d4 + 0) * Np + i] = g.x; sdOt[(d4 + 1) * Np + i] = g.y; sdOt[(d4 + 2) * Np + i] = g.z; sdOt[(d4 + 3) * Np + i] = g.w;
   }
-  for (int e = tid; e < dh * (Np - N); e += ATT_THREADS) sVt[(e / (Np - N)) * Np + N + e % (Np - N)] = 0.f;
-  for (int e = tid; e < N * N; e += ATT_THREADS) sP[(e / N) * Np + e % N] = __ldg(P + (long long)bh * N * N + e);
+  for (int e = tid; e < N4 * N4; e += ATT_THREADS) {
+    const int i = e / N4, j = e % N4;
+    sP[i * Np + j] = (i < N && j < N) ? __ldg(P + (long long)bh * N * N + i * N + j) : 0.f;
+  }
   __syncthreads();
   // dP = dO V^T   (attention.py:74)
-  const int ng = pad4(N) >> 2;
-  for (int e = tid; e < N * ng; e += ATT_THREADS) {
-    const int i = e / ng, j0 = (e % ng) * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* gi = sdO + i * dh;
+  for (int e = tid; e < ng * ng; e += ATT_THREADS) {
+    const int i0 = (e / ng) * 4, j0 = (e % ng) * 4;
+    float acc[4][4] = {};
 #pragma unroll 4
     for (int d = 0; d < dh; d++) {
-      const float gv = gi[d];
-      const float4 vv = *reinterpret_cast<const float4*>(sVt + d * Np + j0);
-      acc.x = fmaf(gv, vv.x, acc.x); acc.y = fmaf(gv, vv.y, acc.y);
-      acc.z = fmaf(gv, vv.z, acc.z); acc.w = fmaf(gv, vv.w, acc.w);
+      const float4 g4 = *reinterpret_cast<const float4*>(sdOt + d * Np + i0);
+      const float4 v4 = *reinterpret_cast<const float4*>(sVt + d * Np + j0);
+      NT_FMA4x4(acc, g4, v4)
     }
-    *reinterpret_cast<float4*>(sdS + i * Np + j0) = acc;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      *reinterpret_cast<float4*>(sdS + (i0 + r) * Np + j0) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
   }
   __syncthreads();
-  // dS = P o (dP - rowsum(dP o P))   (attention.py:75, closed form of the per-row Jacobian)
+  // dS = P o (dP - rowsum(dP o P))   (attention.py:75, closed form of the per-row Jacobian); padded entries stay 0
   const int warp = tid >> 5, lane = tid & 31, nw = ATT_THREADS >> 5;
-  for (int i = warp; i < N; i += nw) {
+  for (int i = warp; i < N4; i += nw) {
     float s = 0.f;
-    for (int j = lane; j < N; j += 32) s += sdS[i * Np + j] * sP[i * Np + j];
+    for (int j = lane; j < N4; j += 32) s += sdS[i * Np + j] * sP[i * Np + j];
     s = warp_sum(s);
-    for (int j = lane; j < N; j += 32) sdS[i * Np + j] = sP[i * Np + j] * (sdS[i * Np + j] - s);
+    for (int j = lane; j < N4; j += 32) sdS[i * Np + j] = sP[i * Np + j] * (sdS[i * Np + j] - s);
   }
   __syncthreads();
   const float scale = 1.0f / sqrtf((float)dh);
   float* obase = dqkv + (long long)b * N * 3 * D + h * dh;
-  // dQ = dS K / sqrt(dh)   (attention.py:78): item = (row i, 4 features)
-  for (int e = tid; e < N * dh4; e += ATT_THREADS) {
-    const int i = e / dh4, d4 = (e % dh4) * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* si = sdS + i * Np;
-#pragma unroll 4
-    for (int j = 0; j < N; j++) {
-      const float sv = si[j];
-      const float4 kv = *reinterpret_cast<const float4*>(sK + j * dh + d4);
-      acc.x = fmaf(sv, kv.x, acc.x); acc.y = fmaf(sv, kv.y, acc.y);
-      acc.z = fmaf(sv, kv.z, acc.z); acc.w = fmaf(sv, kv.w, acc.w);
-    }
-    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
-    *reinterpret_cast<float4*>(obase + (long long)i * 3 * D + d4) = acc;
-  }
-  // dK = dS^T Q / sqrt(dh) (attention.py:79) and dV = P^T dO (attention.py:76): item = (key j, 4 features),
-  // j fastest so a warp walks a row of dS / P
-  for (int e = tid; e < N * dh4; e += ATT_THREADS) {
-    const int j = e % N, d4 = (e / N) * 4;
-    float4 ak = make_float4(0.f, 0.f, 0.f, 0.f), av = make_float4(0.f, 0.f, 0.f, 0.f);
+  // phase A: dQ = dS K / sqrt(dh)  (attention.py:78), tile = 4 query rows x 4 features
+  // phase B: dK = dS^T Q / sqrt(dh) (attention.py:79) and dV = P^T dO (attention.py:76), tile = 4 keys x 4 features
+  const int itemsA = ng * dh4;
+  for (int e = tid; e < 2 * itemsA; e += ATT_THREADS) {
+    if (e < itemsA) {
+      const int i0 = (e / dh4) * 4, d4 = (e % dh4) * 4;
+      float acc[4][4] = {};
+      const float* s0 = sdS + i0 * Np;
 #pragma unroll 2
-    for (int i = 0; i < N; i++) {
-      const float sv = sdS[i * Np + j], pv = sP[i * Np + j];
-      const float4 qv = *reinterpret_cast<const float4*>(sQ + i * dh + d4);
-      const float4 gv = *reinterpret_cast<const float4*>(sdO + i * dh + d4);
-      ak.x = fmaf(sv, qv.x, ak.x); ak.y = fmaf(sv, qv.y, ak.y); ak.z = fmaf(sv, qv.z, ak.z); ak.w = fmaf(sv, qv.w, ak.w);
-      av.x = fmaf(pv, gv.x, av.x); av.y = fmaf(pv, gv.y, av.y); av.z = fmaf(pv, gv.z, av.z); av.w = fmaf(pv, gv.w, av.w);
+      for (int j = 0; j < N; j++) {
+        const float4 s4 = make_float4(s0[j], s0[Np + j], s0[2 * Np + j], s0[3 * Np + j]);
+        const float4 k4 = *reinterpret_cast<const float4*>(sK + j * dh + d4);
+        NT_FMA4x4(acc, s4, k4)
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+        if (i0 + r < N)
+          *reinterpret_cast<float4*>(obase + (long long)(i0 + r) * 3 * D + d4) =
+              make_float4(acc[r][0] * scale, acc[r][1] * scale, acc[r][2] * scale, acc[r][3] * scale);
+    } else {
+      const int f = e - itemsA;
+      const int j0 = (f / dh4) * 4, d4 = (f % dh4) * 4;
+      float ak[4][4] = {}, av[4][4] = {};
+#pragma unroll 2
+      for (int i = 0; i < N; i++) {
+        const float4 s4 = *reinterpret_cast<const float4*>(sdS + i * Np + j0);
+        const float4 p4 = *reinterpret_cast<const float4*>(sP + i * Np + j0);
+        const float4 q4 = *reinterpret_cast<const float4*>(sQ + i * dh + d4);
+        const float4 g4 = *reinterpret_cast<const float4*>(sdO + i * dh + d4);
+        NT_FMA4x4(ak, s4, q4)
+        NT_FMA4x4(av, p4, g4)
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+        if (j0 + r < N) {
+          float* o = obase + (long long)(j0 + r) * 3 * D + d4;
+          *reinterpret_cast<float4*>(o + D) = make_float4(ak[r][0] * scale, ak[r][1] * scale, ak[r][2] * scale, ak[r][3] * scale);
+          *reinterpret_cast<float4*>(o + 2 * D) = make_float4(av[r][0], av[r][1], av[r][2], av[r][3]);
+        }
     }
-    ak.x *= scale; ak.y *= scale; ak.z *= scale; ak.w *= scale;
-    float* o = obase + (long long)j * 3 * D + d4;
-    *reinterpret_cast<float4*>(o + D) = ak;
-    *reinterpret_cast<float4*>(o + 2 * D) = av;
   }
 }
 
 static size_t fwd_small_smem(int N, int dh) {
-  const int Np = ((N + 3) & ~3) + 4;
-  return sizeof(float) * ((size_t)N * dh * 2 + (size_t)dh * Np + (size_t)N * Np);
+  const int N4 = (N + 3) & ~3, Np = N4 + 4;
+  return sizeof(float) * (2 * (size_t)dh * Np + (size_t)N * dh + (size_t)N4 * Np);
 }
 static size_t bwd_small_smem(int N, int dh) {
-  const int Np = ((N + 3) & ~3) + 4;
-  return sizeof(float) * ((size_t)N * dh * 3 + (size_t)dh * Np + 2 * (size_t)N * Np);
+  const int N4 = (N + 3) & ~3, Np = N4 + 4;
+  return sizeof(float) * (3 * (size_t)N * dh + 2 * (size_t)dh * Np + 2 * (size_t)N4 * Np);
 }
 static bool small_ok(int N, int H, int dh) { return N <= 64 && dh <= 64 && (dh & 3) == 0; }
 

@@ -63,7 +63,15 @@ int nt_dp_join(void) {
 }
 
 int nt_dp_shutdown(void) {
-  if (g_comm) { ncclCommDestroy(g_comm); g_comm = nullptr; }
+  if (g_comm) {
+    // all collectives have completed once both streams drain; abort tears the communicator down
+    // without the cross-rank handshake of ncclCommDestroy (which blocks while captured graphs that
+    // contain NCCL kernels are still alive in another rank)
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    if (g_comm_stream) cudaStreamSynchronize(g_comm_stream);
+    ncclCommAbort(g_comm);
+    g_comm = nullptr;
+  }
   if (g_comm_stream) { cudaStreamDestroy(g_comm_stream); g_comm_stream = nullptr; }
   if (g_ev_ready) { cudaEventDestroy(g_ev_ready); g_ev_ready = nullptr; }
   if (g_ev_done) { cudaEventDestroy(g_ev_done); g_ev_done = nullptr; }

@@ -46,6 +46,29 @@ int nt_linear_fwd(const float* x, const float* w, const float* b, float* y, int 
   d.A = x; d.B = w; d.C = y;
   d.M = M; d.N = N; d.K = K;
   d.sAm = K; d.sAk = 1; d.sBk = N; d.sBn = 1; d.ldc = N;
+  // Few output tiles but a long contraction (the ViT head: 100 x 4704 -> 96): one CTA per tile would walk
+  // ~150 k-blocks serially.  Split K across CTAs with red.add into a zeroed buffer, then apply the
+  // activation / residual in a second, tiny pass.
+  const int tiles = ceil_div(M, 128) * ceil_div(N, 32);
+  if (g_gemm_mode != 0 && tiles * 4 < g_sm_count && K >= 1024) {
+    float* acc = (act != 0 && pre) ? pre : y;
+    NT_CHECK(cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)M * N, g_stream));
+    d.C = acc;
+    d.ep.bias = b;
+    d.ep.atomic = 1;
+    d.splitk = 2;                       // > 1: gemm_tc sizes the split from the SM count
+    int rc = gemm_dispatch(d);
+    if (rc) return rc;
+    if (act == 0 && !residual) return 0;
+    if (act != 0 && !pre) {             // activation in place on y
+      rc = act == NT_ACT_RELU ? nt_relu_fwd(y, y, (size_t)M * N) : nt_gelu_fwd(y, y, (size_t)M * N);
+    } else if (act != 0) {
+      rc = act == NT_ACT_RELU ? nt_relu_fwd(pre, y, (size_t)M * N) : nt_gelu_fwd(pre, y, (size_t)M * N);
+    }
+    if (rc) return rc;
+    if (residual) return nt_add(y, residual, y, (size_t)M * N);
+    return 0;
+  }
   d.ep.bias = b; d.ep.act = act; d.ep.pre_out = pre; d.ep.addend = residual;
   return gemm_dispatch(d);
 }

@@ -168,6 +168,12 @@ int nt_event_create(void** ev) {
   *ev = (void*)e;
   return 0;
 }
+int nt_event_record_external(void* ev) {
+  // inside stream capture this becomes an event-record NODE whose timestamp can be read after replay
+  NT_ENTRY();
+  NT_CHECK(cudaEventRecordWithFlags((cudaEvent_t)ev, g_stream, cudaEventRecordExternal));
+  return 0;
+}
 int nt_event_record(void* ev) { NT_ENTRY(); NT_CHECK(cudaEventRecord((cudaEvent_t)ev, g_stream)); return 0; }
 int nt_event_elapsed_ms(void* e0, void* e1, float* ms) {
   NT_CHECK(cudaEventSynchronize((cudaEvent_t)e1));

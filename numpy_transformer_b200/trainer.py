@@ -209,6 +209,24 @@ class TrainStep:
             lib.nt_graph_launch(self.graph)
         self.steps_done += 1
 
+    def capture_profiled(self):
+        """Capture the step once more with an (external) CUDA-event pair around every C-ABI op.  Returns
+        (graph, records); after `lib.nt_graph_launch(graph)` + sync, `lib.profile_read(records)` yields the
+        per-op device durations of that replay.  Every replay is a real training step."""
+        lib.nt_sync()
+        with keep_allocations() as keep:
+            lib.profile_begin(external=True)
+            lib.nt_graph_begin()
+            try:
+                self._enqueue()
+            finally:
+                recs = lib.profile_pause()
+                g = ctypes.c_void_p()
+                nk = ctypes.c_int(0)
+                lib.nt_graph_end(ctypes.byref(g), ctypes.byref(nk))
+        self._prof_buffers = keep.buffers
+        return g, recs
+
     def load(self, inputs, labels):
         """Host -> pinned staging -> device (async on the compute stream)."""
         np.copyto(self.h_in.array, np.asarray(inputs).reshape(self.input_shape), casting="unsafe")
@@ -238,6 +256,14 @@ class TrainStep:
         t = int(self.d_t)
         for obj, *_ in self.arena.slots:
             obj.t = t
+
+    def close(self):
+        """Destroy the captured graphs (required before DataParallel.shutdown: they hold NCCL kernels)."""
+        lib.nt_sync()
+        if self.graph is not None:
+            lib.nt_graph_destroy(self.graph)
+            self.graph = None
+        self._graph_buffers = None
 
     def __del__(self):
         try:

@@ -1,0 +1,49 @@
+"""Data-parallel parity on real GPUs (run under torchrun, one rank per GPU):
+each rank takes its shard of ONE global batch, gradients are all-reduced over NCCL by libntb200,
+and the post-update parameters of every rank must match the oracle's single-process step on the
+full batch (SURVEY.md §4 'DP test').  Usage:
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tools/dp_check.py
+"""
+import os
+import sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy_transformer_b200 as nt
+from numpy_transformer_b200 import trainer
+from numpy_transformer_b200.parallel import DataParallel, shard_range
+from oracle import models as M
+
+
+def main():
+    dp = DataParallel()
+    nt.init(int(os.environ.get("LOCAL_RANK", "0")))
+    dp.init_nccl()
+    world, rank = dp.world, dp.rank
+    per = 6
+    cfg = M.ViTConfig(batch=per * world, embed_dim=48, heads=4, blocks=2)
+    params = M.vit_init(cfg, 0)
+    images, labels, onehot = M.synthetic_vit_batch(cfg, 1)
+    lo, hi = shard_range(cfg.batch, rank, world)
+    layers = trainer.build_vit_layers(per, embed_dim=48, heads=4, blocks=2, seed=0)
+    ts = trainer.TrainStep(layers, "vit", (per,) + images.shape[1:], lr=0.02, dp=dp, grad_buckets=3)
+    worst = 0.0
+    for step in range(4):
+        ref = M.vit_step(params, images, onehot, 0.02, cfg)
+        loss_local = ts.step(images[lo:hi], labels[lo:hi])
+        loss = dp.sum_over_ranks(loss_local)          # local losses are already divided by the GLOBAL N
+        params = ref["params"]
+        mine = M.tree_leaves(trainer.save_walk(layers))
+        err = max(float(np.max(np.abs(a.reshape(-1) - b.reshape(-1))) / (np.max(np.abs(b)) + 1e-30))
+                  for a, b in zip(mine, M.tree_leaves(params)))
+        worst = max(worst, err, abs(loss - ref["loss"]) / abs(ref["loss"]))
+        if rank == 0:
+            print("step %d loss %.6f (oracle %.6f) max rel param err %.2e graph=%s" % (step, loss, ref["loss"], err, ts.graph is not None), flush=True)
+    worst = dp.max_over_ranks(worst)
+    if rank == 0:
+        print("DP_CHECK world=%d worst=%.2e %s" % (world, worst, "OK" if worst < 1e-4 else "FAIL"), flush=True)
+    ts.close()
+    dp.shutdown()
+    sys.exit(0 if worst < 1e-4 else 1)
+
+
+main()
