@@ -51,6 +51,11 @@ int nt_event_destroy(void* ev);
 int nt_graph_begin(void);
 int nt_graph_end(void** graph_exec, int* n_kernel_nodes);
 int nt_graph_launch(void* graph_exec);
+/* Fork/join of a side branch inside a captured step (no-ops outside capture): ops enqueued between
+ * begin/end run concurrently with the main chain; join before anything consumes their results. */
+int nt_side_begin(void);
+int nt_side_end(void);
+int nt_side_join(void);
 int nt_graph_destroy(void* graph_exec);
 /* number of this library's kernels launched so far (graph replays count their kernel nodes) */
 int nt_launch_count(long long* n);

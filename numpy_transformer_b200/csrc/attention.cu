@@ -64,11 +64,16 @@ __device__ __forceinline__ int pad4(int n) { return (n + 3) & ~3; }
   acc[3][0] = fmaf(a4.w, b4.x, acc[3][0]); acc[3][1] = fmaf(a4.w, b4.y, acc[3][1]);                                \
   acc[3][2] = fmaf(a4.w, b4.z, acc[3][2]); acc[3][3] = fmaf(a4.w, b4.w, acc[3][3]);
 
+// NC / DHC: compile-time token count / head width (0 = use the runtime arguments).  With constants the
+// index divisions fold to shifts and the contraction loops unroll; the generic instance was
+// instruction-bound on integer div/mod (ncu: 26.6 K warp-instructions per CTA for ~7 K of FMA work).
+template <int NC, int DHC>
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_small_kernel(const float* __restrict__ qkv,
                                                                       const float* __restrict__ mask, int mask_kind,
                                                                       float* __restrict__ out, float* __restrict__ P,
-                                                                      float* __restrict__ S, int N, int H, int dh,
+                                                                      float* __restrict__ S, int N_rt, int H, int dh_rt,
                                                                       const float* __restrict__ residual) {
+  const int N = NC ? NC : N_rt, dh = DHC ? DHC : dh_rt;
   extern __shared__ __align__(16) float sm[];
   const int N4 = pad4(N), Np = N4 + 4;
   float* sQt = sm;                   // [dh][Np]
@@ -162,10 +167,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_small_kernel(const float
   }
 }
 
+template <int NC, int DHC>
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_small_kernel(const float* __restrict__ dout,
                                                                       const float* __restrict__ qkv,
                                                                       const float* __restrict__ P,
-                                                                      float* __restrict__ dqkv, int N, int H, int dh) {
+                                                                      float* __restrict__ dqkv, int N_rt, int H, int dh_rt) {
+  const int N = NC ? NC : N_rt, dh = DHC ? DHC : dh_rt;
   extern __shared__ __align__(16) float sm[];
   const int N4 = pad4(N), Np = N4 + 4;
   float* sQ = sm;                    // [N][dh]
@@ -314,12 +321,21 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
   const int D = H * dh;
   if (small_ok(N, H, dh)) {
     size_t smem = fwd_small_smem(N, dh);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      NT_CHECK(cudaFuncSetAttribute(attn_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
+#define NT_ATT_FWD(NC_, DHC_)                                                                                       \
+    {                                                                                                               \
+      static size_t configured = 0;                                                                                 \
+      if (smem > 48 * 1024 && smem > configured) {                                                                  \
+        NT_CHECK(cudaFuncSetAttribute(attn_fwd_small_kernel<NC_, DHC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                                  \
+        configured = smem;                                                                                          \
+      }                                                                                                             \
+      attn_fwd_small_kernel<NC_, DHC_><<<B * H, ATT_THREADS, smem, g_stream>>>(qkv, mask, mask_kind, out, P, S, N, H, \
+                                                                               dh, residual);                       \
     }
-    attn_fwd_small_kernel<<<B * H, ATT_THREADS, smem, g_stream>>>(qkv, mask, mask_kind, out, P, S, N, H, dh, residual);
+    if (N == 49 && dh == 24) NT_ATT_FWD(49, 24)
+    else if (N == 49 && dh == 64) NT_ATT_FWD(49, 64)
+    else NT_ATT_FWD(0, 0)
+#undef NT_ATT_FWD
     NT_LAUNCH_OK();
     return 0;
   }
@@ -356,12 +372,20 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
   const int D = H * dh;
   if (small_ok(N, H, dh)) {
     size_t smem = bwd_small_smem(N, dh);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      NT_CHECK(cudaFuncSetAttribute(attn_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
+#define NT_ATT_BWD(NC_, DHC_)                                                                                       \
+    {                                                                                                               \
+      static size_t configured = 0;                                                                                 \
+      if (smem > 48 * 1024 && smem > configured) {                                                                  \
+        NT_CHECK(cudaFuncSetAttribute(attn_bwd_small_kernel<NC_, DHC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                                  \
+        configured = smem;                                                                                          \
+      }                                                                                                             \
+      attn_bwd_small_kernel<NC_, DHC_><<<B * H, ATT_THREADS, smem, g_stream>>>(dout, qkv, P, dqkv, N, H, dh);        \
     }
-    attn_bwd_small_kernel<<<B * H, ATT_THREADS, smem, g_stream>>>(dout, qkv, P, dqkv, N, H, dh);
+    if (N == 49 && dh == 24) NT_ATT_BWD(49, 24)
+    else if (N == 49 && dh == 64) NT_ATT_BWD(49, 64)
+    else NT_ATT_BWD(0, 0)
+#undef NT_ATT_BWD
     NT_LAUNCH_OK();
     return 0;
   }

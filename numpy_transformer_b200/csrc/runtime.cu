@@ -20,6 +20,9 @@ static std::map<size_t, std::vector<void*>> g_free;      // size class -> free b
 static std::unordered_map<void*, size_t> g_size;         // live + pooled blocks
 static size_t g_reserved = 0;
 static void* g_flush_buf = nullptr;
+static cudaStream_t g_main_stream = nullptr, g_side_stream = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+static bool g_side_active = false, g_side_dirty = false;
 static const size_t kFlushBytes = 256ull << 20;
 struct GraphRec { cudaGraphExec_t exec; cudaGraph_t graph; int kernels; };
 
@@ -69,6 +72,10 @@ int nt_init(int device) {
              prop.major, prop.minor);
   g_sm_count = prop.multiProcessorCount;
   NT_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  g_main_stream = g_stream;
+  NT_CHECK(cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking));
+  NT_CHECK(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+  NT_CHECK(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
   g_device = device;
   return 0;
 }
@@ -192,6 +199,7 @@ int nt_graph_begin(void) {
 int nt_graph_end(void** graph_exec, int* n_kernel_nodes) {
   NT_ENTRY();
   NT_REQUIRE(g_capturing, "nt_graph_end: not capturing");
+  if (nt_side_join()) return 1;
   g_capturing = false;
   cudaGraph_t graph = nullptr;
   NT_CHECK(cudaStreamEndCapture(g_stream, &graph));
@@ -225,6 +233,38 @@ int nt_graph_destroy(void* graph_exec) {
   cudaGraphExecDestroy(r->exec);
   cudaGraphDestroy(r->graph);
   delete r;
+  return 0;
+}
+
+// Side branch: while a graph is being captured, work enqueued between nt_side_begin/nt_side_end goes to a
+// second stream forked from the current point of the main stream (the weight-gradient GEMMs, which nothing
+// on the backward critical path consumes).  nt_side_join makes the main stream wait for all of it.  Outside
+// capture the calls are no-ops: the pooled allocator's reuse rule assumes a single stream, and only a
+// captured step pins every buffer for the lifetime of the graph.
+int nt_side_begin(void) {
+  NT_ENTRY();
+  if (!g_capturing || g_side_active) return 0;
+  NT_CHECK(cudaEventRecord(g_ev_fork, g_main_stream));
+  NT_CHECK(cudaStreamWaitEvent(g_side_stream, g_ev_fork, 0));
+  g_stream = g_side_stream;
+  g_side_active = true;
+  g_side_dirty = true;
+  return 0;
+}
+int nt_side_end(void) {
+  NT_ENTRY();
+  if (!g_side_active) return 0;
+  g_stream = g_main_stream;
+  g_side_active = false;
+  return 0;
+}
+int nt_side_join(void) {
+  NT_ENTRY();
+  if (g_side_active) nt_side_end();
+  if (!g_side_dirty) return 0;
+  NT_CHECK(cudaEventRecord(g_ev_join, g_side_stream));
+  NT_CHECK(cudaStreamWaitEvent(g_main_stream, g_ev_join, 0));
+  g_side_dirty = false;
   return 0;
 }
 

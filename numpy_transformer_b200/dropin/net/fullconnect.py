@@ -4,6 +4,7 @@ tensors live on the GPU as DeviceArrays and every method only enqueues CUDA work
 import numpy as np
 from numpy_transformer_b200.device import DeviceArray, as_device
 from numpy_transformer_b200 import ops
+from numpy_transformer_b200._lib import lib
 
 
 class fclayer(object):
@@ -44,7 +45,10 @@ class fclayer(object):
         return ops.linear_fwd(x, self.params, self.bias_params if self.bias else None, act, want_pre, residual)
 
     def _backward(self, dy, x, act=ops.ACT_NONE, pre=None, addend=None, want_dx=True):
+        # dW / db feed nothing on the backward critical path: inside a captured step they run on a side branch
+        lib.nt_side_begin()
         ops.linear_bwd_params(x, dy, self.params_delta, self.bias_delta)
+        lib.nt_side_end()
         if not want_dx:
             return None
         return ops.linear_bwd_input(dy, self.params, act, pre, addend)

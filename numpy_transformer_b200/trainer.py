@@ -172,6 +172,7 @@ class TrainStep:
             else:
                 delta = l.backward(delta)
         a = self.arena
+        lib.nt_side_join()                       # weight-gradient branch must land before all-reduce / update
         if self.dp is not None and self.dp.world > 1:
             self.dp.allreduce_buckets(a.grads, self.grad_buckets)
             lib.nt_dp_join()
