@@ -140,20 +140,25 @@ def run_ours(args):
     if dp:
         dp.init_nccl()
     B = c["batch"]
+    chains = args.chains if args.chains is not None else 1
     if kind == "vit":
-        cfg = M.ViTConfig(batch=B, embed_dim=c["embed_dim"], heads=c["heads"], blocks=c["blocks"])
-        layers = trainer.build_vit_layers(B, embed_dim=c["embed_dim"], heads=c["heads"], blocks=c["blocks"], seed=0)
+        reps = [trainer.build_vit_layers(B // chains, embed_dim=c["embed_dim"], heads=c["heads"], blocks=c["blocks"], seed=0)
+                for _ in range(chains)]
+        layers = reps[0]
         rs = np.random.RandomState(1 + rank)
         inputs = rs.rand(B, 1, 28, 28)
         labels = rs.randint(0, 10, B)
         units, unit = B, "images/s"
     else:
-        layers = trainer.build_gpt_layers(B, c["context"], c["embed_dim"], c["heads"], c["blocks"], c["vocab"], adam=True, seed=0)
+        reps = [trainer.build_gpt_layers(B // chains, c["context"], c["embed_dim"], c["heads"], c["blocks"], c["vocab"], adam=True, seed=0)
+                for _ in range(chains)]
+        layers = reps[0]
         rs = np.random.RandomState(1 + rank)
         inputs = rs.randint(0, c["vocab"], (B, c["context"]))
         labels = rs.randint(0, c["vocab"], (B, c["context"]))
         units, unit = B, "sequences/s"
-    ts = trainer.TrainStep(layers, kind, inputs.shape, lr=c["lr"], adam=c["adam"], dp=dp, grad_buckets=args.buckets)
+    ts = trainer.TrainStep(layers, kind, inputs.shape, lr=c["lr"], adam=c["adam"], dp=dp, grad_buckets=args.buckets,
+                           replicas=reps[1:])
 
     W = max(3, args.warmup)
     K = args.steps
@@ -205,7 +210,7 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     e2e_s_max = dp.max_over_ranks(e2e_s) if dp else e2e_s
     clocks = sampler.stop()
-    e2e = dict(value=units * world * K / e2e_s_max, unit=unit, h2d_bytes_per_step=ts.h2d_bytes, d2h_bytes_per_step=4,
+    e2e = dict(value=units * world * K / e2e_s_max, unit=unit, h2d_bytes_per_step=ts.h2d_bytes, d2h_bytes_per_step=4 * chains,
                timing="host wall clock around K public step() calls, max over ranks")
 
     # ---------------- roofline of the dominant kernel: the same step captured with a CUDA-event pair around every op
@@ -261,7 +266,7 @@ def run_ours(args):
             "ms_per_step": dev_s_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": B * world, **{k: v for k, v in c.items() if k not in ("batch",)},
-                       "parallelism": "dp%d" % world, "gemm_mode": nt.get_gemm_mode(),
+                       "parallelism": "dp%d" % world, "micro_batch_chains_per_gpu": chains, "gemm_mode": nt.get_gemm_mode(),
                        "l2": "256 MB memset between timed steps (working set is L2-resident)",
                        "graph_kernels_per_step": ts.graph_kernels, "params": ts.arena.n_params},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
@@ -387,6 +392,7 @@ def main():
     ap.add_argument("--workload", default="vit_readme", choices=sorted(WORKLOADS))
     ap.add_argument("--gemm-mode", type=int, default=None)
     ap.add_argument("--buckets", type=int, default=1)
+    ap.add_argument("--chains", type=int, default=None, help="parallel micro-batch branches per GPU (default 1; measured slower than 1 on B200 for vit_readme, see DESIGN.md)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()

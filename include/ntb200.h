@@ -56,6 +56,10 @@ int nt_graph_launch(void* graph_exec);
 int nt_side_begin(void);
 int nt_side_end(void);
 int nt_side_join(void);
+/* Parallel branches for independent sample groups inside a captured step (intra-GPU data parallelism). */
+int nt_chain_begin(int idx);
+int nt_chain_end(void);
+int nt_chain_join(void);
 int nt_graph_destroy(void* graph_exec);
 /* number of this library's kernels launched so far (graph replays count their kernel nodes) */
 int nt_launch_count(long long* n);

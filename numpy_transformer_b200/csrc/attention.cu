@@ -10,6 +10,7 @@ namespace nt {
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, float* __restrict__ p,
                                                            long long rows, int cols, const float* __restrict__ mask,
                                                            int mask_kind, int N) {
+  pdl_prologue();
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 // dx = p * (dp - sum(dp*p))  (closed form of the per-row Jacobian product, activation.py:86-91)
 __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* dp, const float* __restrict__ p,
                                                                float* dx, long long rows, int cols) {
+  pdl_prologue();
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_small_kernel(const float
                                                                       float* __restrict__ out, float* __restrict__ P,
                                                                       float* __restrict__ S, int N_rt, int H, int dh_rt,
                                                                       const float* __restrict__ residual) {
+  pdl_prologue();
   const int N = NC ? NC : N_rt, dh = DHC ? DHC : dh_rt;
   extern __shared__ __align__(16) float sm[];
   const int N4 = pad4(N), Np = N4 + 4;
@@ -172,6 +175,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_small_kernel(const float
                                                                       const float* __restrict__ qkv,
                                                                       const float* __restrict__ P,
                                                                       float* __restrict__ dqkv, int N_rt, int H, int dh_rt) {
+  pdl_prologue();
   const int N = NC ? NC : N_rt, dh = DHC ? DHC : dh_rt;
   extern __shared__ __align__(16) float sm[];
   const int N4 = pad4(N), Np = N4 + 4;
@@ -287,7 +291,7 @@ static bool small_ok(int N, int H, int dh) { return N <= 64 && dh <= 64 && (dh &
 
 static int softmax_rows(const float* x, float* p, long long rows, int cols, const float* mask, int mask_kind, int N) {
   if (rows == 0) return 0;
-  softmax_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, g_stream>>>(x, p, rows, cols, mask, mask_kind, N);
+  NT_CHECK(nt::launch_k(softmax_rows_kernel, dim3(ceil_div(rows * 32, 256)), dim3(256), 0, x, p, rows, cols, mask, mask_kind, N));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -307,7 +311,7 @@ int nt_softmax_bwd(const float* dp, const float* p, float* dx, int rows, int col
   NT_ENTRY();
   NT_REQUIRE(rows >= 0 && cols > 0, "nt_softmax_bwd: bad shape");
   if (rows == 0) return 0;
-  softmax_bwd_rows_kernel<<<ceil_div((long long)rows * 32, 256), 256, 0, g_stream>>>(dp, p, dx, rows, cols);
+  NT_CHECK(nt::launch_k(softmax_bwd_rows_kernel, dim3(ceil_div((long long)rows * 32, 256)), dim3(256), 0, dp, p, dx, rows, cols));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -329,8 +333,8 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
                                       (int)smem));                                                                  \
         configured = smem;                                                                                          \
       }                                                                                                             \
-      attn_fwd_small_kernel<NC_, DHC_><<<B * H, ATT_THREADS, smem, g_stream>>>(qkv, mask, mask_kind, out, P, S, N, H, \
-                                                                               dh, residual);                       \
+      NT_CHECK(nt::launch_k(attn_fwd_small_kernel<NC_, DHC_>, dim3(B * H), dim3(ATT_THREADS), smem, qkv, mask, mask_kind, out, P, S, N, H, \
+                                                                               dh, residual));                       \
     }
     if (N == 49 && dh == 24) NT_ATT_FWD(49, 24)
     else if (N == 49 && dh == 64) NT_ATT_FWD(49, 64)
@@ -380,7 +384,7 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
                                       (int)smem));                                                                  \
         configured = smem;                                                                                          \
       }                                                                                                             \
-      attn_bwd_small_kernel<NC_, DHC_><<<B * H, ATT_THREADS, smem, g_stream>>>(dout, qkv, P, dqkv, N, H, dh);        \
+      NT_CHECK(nt::launch_k(attn_bwd_small_kernel<NC_, DHC_>, dim3(B * H), dim3(ATT_THREADS), smem, dout, qkv, P, dqkv, N, H, dh));        \
     }
     if (N == 49 && dh == 24) NT_ATT_BWD(49, 24)
     else if (N == 49 && dh == 64) NT_ATT_BWD(49, 64)
@@ -403,8 +407,8 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
   int rc = gemm_simt(g);
   if (rc) return rc;
   // dS in place
-  softmax_bwd_rows_kernel<<<ceil_div((long long)B * H * N * 32, 256), 256, 0, g_stream>>>(scratch, P, scratch,
-                                                                                         (long long)B * H * N, N);
+  NT_CHECK(nt::launch_k(softmax_bwd_rows_kernel, dim3(ceil_div((long long)B * H * N * 32, 256)), dim3(256), 0, scratch, P, scratch,
+                                                                                         (long long)B * H * N, N));
   NT_LAUNCH_OK();
   // dV = P^T dO
   GemmDesc v{};

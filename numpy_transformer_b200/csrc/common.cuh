@@ -13,6 +13,7 @@ extern int g_sm_count;
 extern int g_gemm_mode;
 extern long long g_launches;
 extern bool g_capturing;
+extern bool g_use_pdl;
 void set_error(const char* fmt, ...);
 bool ensure_init();
 
@@ -62,6 +63,28 @@ __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erf
 __device__ __forceinline__ float gelu_grad_f(float x) {
   float s = x * 0.70710678118654752f;
   return 0.5f + 0.5f * erff(s) + x * 0.3989422804014327f * expf(-s * s);
+}
+
+// Programmatic dependent launch: every kernel of this library starts with pdl_prologue(), so it can be
+// launched while its predecessor in the stream is still draining (the ~2 us dependent-launch gap of a
+// 130-kernel latency-bound step is then hidden) and only blocks where it first touches global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = g_stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

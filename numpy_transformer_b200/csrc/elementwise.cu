@@ -8,6 +8,7 @@ enum { OP_GELU_F, OP_GELU_B, OP_RELU_F, OP_RELU_B, OP_ADD, OP_SCALE };
 template <int OP>
 __global__ void __launch_bounds__(256) ew_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                  float* __restrict__ out, size_t n, float alpha) {
+  pdl_prologue();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n4 = n / 4;
@@ -41,13 +42,14 @@ static int launch_ew(const float* a, const float* b, float* out, size_t n, float
   if (blocks < 1) blocks = 1;
   long long cap = (long long)g_sm_count * 8;
   if (blocks > cap) blocks = cap;
-  ew_kernel<OP><<<(int)blocks, 256, 0, g_stream>>>(a, b, out, n, alpha);
+  NT_CHECK(nt::launch_k(ew_kernel<OP>, dim3((int)blocks), dim3(256), 0, a, b, out, n, alpha));
   NT_LAUNCH_OK();
   return 0;
 }
 
 __global__ void add_rows_kernel(const float* __restrict__ x, const float* __restrict__ table, float* __restrict__ out,
                                 long long total, int period, int D) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long pd = (long long)period * D;
@@ -57,6 +59,7 @@ __global__ void add_rows_kernel(const float* __restrict__ x, const float* __rest
 // (B,C,Hi,Wi) -> (B, P*P, C*hl*wl), (c,h,w) order inside a patch  (PatchEmbed.py:27-36)
 __global__ void patchify_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int C, int Hi, int Wi,
                                 int P, int hl, int wl) {
+  pdl_prologue();
   const long long total = (long long)B * P * P * C * hl * wl;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -74,6 +77,7 @@ __global__ void patchify_kernel(const float* __restrict__ img, float* __restrict
 
 __global__ void embedding_fwd_kernel(const int32_t* __restrict__ idx, const float* __restrict__ etok,
                                      const float* __restrict__ epos, float* __restrict__ out, int BT, int T, int D) {
+  pdl_prologue();
   const int row = blockIdx.x;
   if (row >= BT) return;
   const int tok = idx[row];
@@ -87,6 +91,7 @@ __global__ void embedding_fwd_kernel(const int32_t* __restrict__ idx, const floa
 
 __global__ void embedding_bwd_tok_kernel(const int32_t* __restrict__ idx, const float* __restrict__ dy,
                                          float* __restrict__ detok, int BT, int D) {
+  pdl_prologue();
   const int row = blockIdx.x;
   if (row >= BT) return;
   const int tok = idx[row];
@@ -94,16 +99,18 @@ __global__ void embedding_bwd_tok_kernel(const int32_t* __restrict__ idx, const 
 }
 
 __global__ void embedding_bwd_pos_kernel(const float* __restrict__ dy, float* __restrict__ depos, int B, int T, int D) {
+  pdl_prologue();
   const long long total = (long long)T * D;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   float s = 0.f;
   for (int b = 0; b < B; b++) s += dy[(long long)b * total + i];
-  depos[i] += s;
+  atomicAdd(depos + i, s);     // several micro-batch chains may accumulate concurrently
 }
 
 __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, float* __restrict__ g, size_t n, float lr,
                                                   const float* __restrict__ lr_dev, int zero_grad) {
+  pdl_prologue();
   if (lr_dev) lr = *lr_dev;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -117,6 +124,7 @@ __global__ void __launch_bounds__(256) adam_star_kernel(float* __restrict__ p, f
                                                         float* __restrict__ m, float* __restrict__ v, size_t n,
                                                         float lr, const float* __restrict__ lr_dev, int t,
                                                         const int32_t* __restrict__ t_dev, int zero_grad) {
+  pdl_prologue();
   if (lr_dev) lr = *lr_dev;
   if (t_dev) t = *t_dev;
   const float b1 = 0.9f, omb1 = 0.1f, b2 = 0.999f, omb2 = 0.001f, eps = 1e-8f;
@@ -135,7 +143,8 @@ __global__ void __launch_bounds__(256) adam_star_kernel(float* __restrict__ p, f
   }
 }
 
-__global__ void increment_kernel(int32_t* c) { *c += 1; }
+__global__ void increment_kernel(int32_t* c) {
+  pdl_prologue(); *c += 1; }
 
 static int grid_for(size_t n) {
   long long blocks = (long long)((n + 255) / 256);
@@ -162,7 +171,7 @@ int nt_add_rows(const float* x, const float* table, float* out, int rows, int pe
   NT_REQUIRE(period > 0 && D > 0, "nt_add_rows: bad period/D");
   long long total = (long long)rows * D;
   if (total == 0) return 0;
-  add_rows_kernel<<<grid_for(total), 256, 0, g_stream>>>(x, table, out, total, period, D);
+  NT_CHECK(nt::launch_k(add_rows_kernel, dim3(grid_for(total)), dim3(256), 0, x, table, out, total, period, D));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -173,7 +182,7 @@ int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, i
   int hl = Hi / n_patch, wl = Wi / n_patch;
   long long total = (long long)B * n_patch * n_patch * C * hl * wl;
   if (total == 0) return 0;
-  patchify_kernel<<<grid_for(total), 256, 0, g_stream>>>(images, out, B, C, Hi, Wi, n_patch, hl, wl);
+  NT_CHECK(nt::launch_k(patchify_kernel, dim3(grid_for(total)), dim3(256), 0, images, out, B, C, Hi, Wi, n_patch, hl, wl));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -181,7 +190,7 @@ int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, i
 int nt_embedding_fwd(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int T, int D) {
   NT_ENTRY();
   if (B * T == 0) return 0;
-  embedding_fwd_kernel<<<B * T, D >= 256 ? 256 : 128, 0, g_stream>>>(idx, etok, epos, out, B * T, T, D);
+  NT_CHECK(nt::launch_k(embedding_fwd_kernel, dim3(B * T), dim3(D >= 256 ? 256 : 128), 0, idx, etok, epos, out, B * T, T, D));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -190,11 +199,11 @@ int nt_embedding_bwd(const int32_t* idx, const float* dy, float* detok, float* d
   NT_ENTRY();
   if (B * T == 0) return 0;
   if (detok) {
-    embedding_bwd_tok_kernel<<<B * T, D >= 256 ? 256 : 128, 0, g_stream>>>(idx, dy, detok, B * T, D);
+    NT_CHECK(nt::launch_k(embedding_bwd_tok_kernel, dim3(B * T), dim3(D >= 256 ? 256 : 128), 0, idx, dy, detok, B * T, D));
     NT_LAUNCH_OK();
   }
   if (depos) {
-    embedding_bwd_pos_kernel<<<ceil_div((long long)T * D, 256), 256, 0, g_stream>>>(dy, depos, B, T, D);
+    NT_CHECK(nt::launch_k(embedding_bwd_pos_kernel, dim3(ceil_div((long long)T * D, 256)), dim3(256), 0, dy, depos, B, T, D));
     NT_LAUNCH_OK();
   }
   return 0;
@@ -203,7 +212,7 @@ int nt_embedding_bwd(const int32_t* idx, const float* dy, float* detok, float* d
 int nt_sgd(float* p, float* g, size_t n, float lr, const float* lr_dev, int zero_grad) {
   NT_ENTRY();
   if (n == 0) return 0;
-  sgd_kernel<<<grid_for(n), 256, 0, g_stream>>>(p, g, n, lr, lr_dev, zero_grad);
+  NT_CHECK(nt::launch_k(sgd_kernel, dim3(grid_for(n)), dim3(256), 0, p, g, n, lr, lr_dev, zero_grad));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -212,14 +221,14 @@ int nt_adam_star(float* p, float* g, float* m, float* v, size_t n, float lr, con
                  const int32_t* t_dev, int zero_grad) {
   NT_ENTRY();
   if (n == 0) return 0;
-  adam_star_kernel<<<grid_for(n), 256, 0, g_stream>>>(p, g, m, v, n, lr, lr_dev, t, t_dev, zero_grad);
+  NT_CHECK(nt::launch_k(adam_star_kernel, dim3(grid_for(n)), dim3(256), 0, p, g, m, v, n, lr, lr_dev, t, t_dev, zero_grad));
   NT_LAUNCH_OK();
   return 0;
 }
 
 int nt_increment(int32_t* counter) {
   NT_ENTRY();
-  increment_kernel<<<1, 1, 0, g_stream>>>(counter);
+  NT_CHECK(nt::launch_k(increment_kernel, dim3(1), dim3(1), 0, counter));
   NT_LAUNCH_OK();
   return 0;
 }

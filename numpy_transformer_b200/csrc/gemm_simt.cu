@@ -7,6 +7,7 @@ namespace nt {
 
 template <int BM, int BN, int BK>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmDesc d) {
+  pdl_prologue();
   constexpr int TM = BM / 16, TN = BN / 16;
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
@@ -120,10 +121,10 @@ int gemm_simt(const GemmDesc& d) {
   const int nb = d.nb0 * d.nb1;
   if (d.N <= 32 && d.M >= 64) {
     dim3 grid(ceil_div(d.N, 32), ceil_div(d.M, 128), nb * d.splitk);
-    gemm_simt_kernel<128, 32, 16><<<grid, 256, 0, g_stream>>>(d);
+    NT_CHECK(nt::launch_k(gemm_simt_kernel<128, 32, 16>, dim3(grid), dim3(256), 0, d));
   } else {
     dim3 grid(ceil_div(d.N, 64), ceil_div(d.M, 64), nb * d.splitk);
-    gemm_simt_kernel<64, 64, 16><<<grid, 256, 0, g_stream>>>(d);
+    NT_CHECK(nt::launch_k(gemm_simt_kernel<64, 64, 16>, dim3(grid), dim3(256), 0, d));
   }
   NT_LAUNCH_OK();
   return 0;

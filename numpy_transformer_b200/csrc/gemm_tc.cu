@@ -146,6 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = bars + 3 * p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
 
+  pdl_launch_dependents();            // the next kernel may start its own prologue now
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TC_STAMP(0);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * p.BN;
@@ -186,6 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    pdl_wait();                        // operands are outputs of the preceding kernels
     // first ring of loads goes out before the CTA-wide sync: the DRAM/L2 latency of the first tiles
     // overlaps the TMEM allocation and barrier hand-shake (all slots are trivially empty)
     for (int i = 0; i < prologue; i++) issue_stage(i);
@@ -194,6 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -442,7 +445,7 @@ static int launch_tc(dim3 grid, size_t smem, const CUtensorMap& tmA, const CUten
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     configured = true;
   }
-  gemm_tc_kernel<ACT, DACT, PRE_OUT, ATOMIC, ADDEND><<<grid, TC_THREADS, smem, g_stream>>>(tmA, tmB, p);
+  NT_CHECK(nt::launch_k(gemm_tc_kernel<ACT, DACT, PRE_OUT, ATOMIC, ADDEND>, dim3(grid), dim3(TC_THREADS), smem, tmA, tmB, p));
   NT_LAUNCH_OK();
   return 0;
 }

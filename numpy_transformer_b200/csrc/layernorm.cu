@@ -9,6 +9,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      int M, int D, float eps, const float* __restrict__ post_add,
                                                      int period) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const float* __restrict_
                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                                         const float* __restrict__ gamma, float* __restrict__ dx,
                                                         int M, int D, const float* __restrict__ addend) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -63,6 +65,7 @@ __global__ void ln_bwd_param_kernel(const float* __restrict__ dy, const float* _
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int D,
                                     int rows_per_block) {
+  pdl_prologue();
   __shared__ float rg[8][33], rb[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_block;
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* __restri
                                                            const float* __restrict__ gamma, float* __restrict__ dx,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
                                                            int D, const float* __restrict__ addend) {
+  pdl_prologue();
   extern __shared__ float red[];                 // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * LN_ROWS;
@@ -161,8 +165,8 @@ template <int NC>
 static int launch_ln_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                                float* dx, float* dgamma, float* dbeta, int M, int D, const float* addend) {
   const size_t smem = sizeof(float) * 16 * (size_t)D;
-  ln_bwd_fused_kernel<NC><<<ceil_div(M, LN_ROWS), 256, smem, g_stream>>>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D,
-                                                                         addend);
+  NT_CHECK(nt::launch_k(ln_bwd_fused_kernel<NC>, dim3(ceil_div(M, LN_ROWS)), dim3(256), smem, dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D,
+                                                                         addend));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -178,8 +182,8 @@ int nt_layernorm_fwd(const float* x, const float* gamma, const float* beta, floa
   NT_REQUIRE(M >= 0 && D > 0, "nt_layernorm_fwd: bad shape M=%d D=%d", M, D);
   NT_REQUIRE(!post_add || period > 0, "nt_layernorm_fwd: post_add needs period > 0");
   if (M == 0) return 0;
-  ln_fwd_kernel<<<ceil_div((long long)M * 32, 256), 256, 0, g_stream>>>(x, gamma, beta, y, mean, rstd, M, D, eps,
-                                                                        post_add, period);
+  NT_CHECK(nt::launch_k(ln_fwd_kernel, dim3(ceil_div((long long)M * 32, 256)), dim3(256), 0, x, gamma, beta, y, mean, rstd, M, D, eps,
+                                                                        post_add, period));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -198,11 +202,11 @@ int nt_layernorm_bwd(const float* dy, const float* x, const float* mean, const f
   if (dgamma && dbeta) {
     int rows_per_block = M >= 8192 ? 512 : 128;
     dim3 grid(ceil_div(D, 32), ceil_div(M, rows_per_block));
-    ln_bwd_param_kernel<<<grid, dim3(32, 8), 0, g_stream>>>(dy, x, mean, rstd, dgamma, dbeta, M, D, rows_per_block);
+    NT_CHECK(nt::launch_k(ln_bwd_param_kernel, dim3(grid), dim3(dim3(32, 8)), 0, dy, x, mean, rstd, dgamma, dbeta, M, D, rows_per_block));
     NT_LAUNCH_OK();
   }
   if (dx) {
-    ln_bwd_dx_kernel<<<ceil_div((long long)M * 32, 256), 256, 0, g_stream>>>(dy, x, mean, rstd, gamma, dx, M, D, addend);
+    NT_CHECK(nt::launch_k(ln_bwd_dx_kernel, dim3(ceil_div((long long)M * 32, 256)), dim3(256), 0, dy, x, mean, rstd, gamma, dx, M, D, addend));
     NT_LAUNCH_OK();
   }
   return 0;

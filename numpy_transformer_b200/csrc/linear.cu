@@ -5,6 +5,7 @@ namespace nt {
 
 // db[n] += sum_m dy[m,n]   (net/fullconnect.py:122,125)
 __global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ db, int M, int N, int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_block;
@@ -106,7 +107,7 @@ int nt_linear_bwd_params(const float* x, const float* dy, float* dw, float* db, 
   if (db) {
     int rows_per_block = 256;
     dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_block));
-    colsum_kernel<<<grid, dim3(32, 8), 0, g_stream>>>(dy, db, M, N, rows_per_block);
+    NT_CHECK(nt::launch_k(colsum_kernel, dim3(grid), dim3(dim3(32, 8)), 0, dy, db, M, N, rows_per_block));
     NT_LAUNCH_OK();
   }
   return 0;

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(128) ce_row_kernel(const float* __restrict__ l
                                                      float* __restrict__ row_loss, float* __restrict__ grad,
                                                      float* __restrict__ prob, int32_t* __restrict__ argmax_out,
                                                      int cols) {
+  pdl_prologue();
   __shared__ float sv[4];
   __shared__ int si[4];
   const long long row = blockIdx.x;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(128) ce_row_kernel(const float* __restrict__ l
 // deterministic single-block reduction of the per-row losses
 __global__ void __launch_bounds__(256) ce_reduce_kernel(const float* __restrict__ row_loss, float* __restrict__ loss,
                                                         int rows, float inv_n) {
+  pdl_prologue();
   __shared__ float sv[8];
   float s = 0.f;
   for (int i = threadIdx.x; i < rows; i += blockDim.x) s += row_loss[i];
@@ -110,9 +112,9 @@ extern "C" int nt_cross_entropy(const float* logits, const int32_t* labels, cons
   NT_REQUIRE((labels != nullptr) != (onehot != nullptr), "nt_cross_entropy: pass exactly one of labels / onehot");
   NT_REQUIRE(n_norm > 0.f && row_loss && loss, "nt_cross_entropy: n_norm, row_loss and loss are required");
   const float inv_n = 1.0f / n_norm;
-  ce_row_kernel<<<rows, 128, 0, g_stream>>>(logits, labels, onehot, inv_n, row_loss, grad, prob, argmax, cols);
+  NT_CHECK(nt::launch_k(ce_row_kernel, dim3(rows), dim3(128), 0, logits, labels, onehot, inv_n, row_loss, grad, prob, argmax, cols));
   NT_LAUNCH_OK();
-  ce_reduce_kernel<<<1, 256, 0, g_stream>>>(row_loss, loss, rows, inv_n);
+  NT_CHECK(nt::launch_k(ce_reduce_kernel, dim3(1), dim3(256), 0, row_loss, loss, rows, inv_n));
   NT_LAUNCH_OK();
   return 0;
 }

@@ -1,6 +1,7 @@
 // Runtime plumbing of libntb200.so: device/stream, pooled allocator, copies, events, graphs.
 #include "common.cuh"
 #include <cstdarg>
+#include <cstdlib>
 #include <map>
 #include <vector>
 #include <mutex>
@@ -12,6 +13,7 @@ int g_sm_count = 148;
 int g_gemm_mode = 1;   // default: tcgen05 3xTF32 (fp32-class accuracy)
 long long g_launches = 0;
 bool g_capturing = false;
+bool g_use_pdl = true;
 static int g_device = -1;
 static thread_local char g_err[1024] = "";
 static char g_err_global[1024] = "";
@@ -23,6 +25,11 @@ static void* g_flush_buf = nullptr;
 static cudaStream_t g_main_stream = nullptr, g_side_stream = nullptr;
 static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
 static bool g_side_active = false, g_side_dirty = false;
+static const int kMaxChains = 8;
+static cudaStream_t g_chain_stream[kMaxChains] = {};
+static cudaEvent_t g_chain_done[kMaxChains] = {};
+static bool g_chain_dirty[kMaxChains] = {};
+static int g_chain_active = -1;
 static const size_t kFlushBytes = 256ull << 20;
 struct GraphRec { cudaGraphExec_t exec; cudaGraph_t graph; int kernels; };
 
@@ -71,6 +78,7 @@ int nt_init(int device) {
   NT_REQUIRE(prop.major == 10, "nt_init: device is sm_%d%d; this library is built for sm_100a only",
              prop.major, prop.minor);
   g_sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("NTB200_PDL")) g_use_pdl = (e[0] != '0');
   NT_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   g_main_stream = g_stream;
   NT_CHECK(cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking));
@@ -200,6 +208,7 @@ int nt_graph_end(void** graph_exec, int* n_kernel_nodes) {
   NT_ENTRY();
   NT_REQUIRE(g_capturing, "nt_graph_end: not capturing");
   if (nt_side_join()) return 1;
+  if (nt_chain_join()) return 1;
   g_capturing = false;
   cudaGraph_t graph = nullptr;
   NT_CHECK(cudaStreamEndCapture(g_stream, &graph));
@@ -243,7 +252,7 @@ int nt_graph_destroy(void* graph_exec) {
 // captured step pins every buffer for the lifetime of the graph.
 int nt_side_begin(void) {
   NT_ENTRY();
-  if (!g_capturing || g_side_active) return 0;
+  if (!g_capturing || g_side_active || g_chain_active >= 0) return 0;
   NT_CHECK(cudaEventRecord(g_ev_fork, g_main_stream));
   NT_CHECK(cudaStreamWaitEvent(g_side_stream, g_ev_fork, 0));
   g_stream = g_side_stream;
@@ -265,6 +274,45 @@ int nt_side_join(void) {
   NT_CHECK(cudaEventRecord(g_ev_join, g_side_stream));
   NT_CHECK(cudaStreamWaitEvent(g_main_stream, g_ev_join, 0));
   g_side_dirty = false;
+  return 0;
+}
+
+// Micro-batch chains: inside a captured step, work enqueued between nt_chain_begin(i)/nt_chain_end goes to
+// stream i, forked from the main stream.  Independent sample groups (data parallelism inside one GPU) then
+// run as parallel graph branches: the per-kernel latencies of the tiny ViT shapes overlap instead of adding
+// up.  nt_chain_join makes the main stream wait for every branch.  No-ops outside capture.
+int nt_chain_begin(int idx) {
+  NT_ENTRY();
+  NT_REQUIRE(idx >= 0 && idx < kMaxChains, "nt_chain_begin: idx %d out of range", idx);
+  if (!g_capturing) return 0;
+  NT_REQUIRE(g_chain_active < 0 && !g_side_active, "nt_chain_begin: a branch is already open");
+  if (!g_chain_stream[idx]) {
+    NT_CHECK(cudaStreamCreateWithFlags(&g_chain_stream[idx], cudaStreamNonBlocking));
+    NT_CHECK(cudaEventCreateWithFlags(&g_chain_done[idx], cudaEventDisableTiming));
+  }
+  NT_CHECK(cudaEventRecord(g_ev_fork, g_main_stream));
+  NT_CHECK(cudaStreamWaitEvent(g_chain_stream[idx], g_ev_fork, 0));
+  g_stream = g_chain_stream[idx];
+  g_chain_active = idx;
+  g_chain_dirty[idx] = true;
+  return 0;
+}
+int nt_chain_end(void) {
+  NT_ENTRY();
+  if (g_chain_active < 0) return 0;
+  NT_CHECK(cudaEventRecord(g_chain_done[g_chain_active], g_stream));
+  g_stream = g_main_stream;
+  g_chain_active = -1;
+  return 0;
+}
+int nt_chain_join(void) {
+  NT_ENTRY();
+  if (g_chain_active >= 0) nt_chain_end();
+  for (int i = 0; i < kMaxChains; i++)
+    if (g_chain_dirty[i]) {
+      NT_CHECK(cudaStreamWaitEvent(g_main_stream, g_chain_done[i], 0));
+      g_chain_dirty[i] = false;
+    }
   return 0;
 }
 

@@ -78,15 +78,51 @@ class fclayer(object):
             if self.bias:
                 ops.sgd(self.bias_params, self.bias_delta, lr)
 
+    def _pad_out(self, mult=4):
+        """Fast-path only (TrainStep, for the layer that feeds cross_entropy): pad the output width to a
+        multiple of `mult` with dummy classes whose weights are 0 and whose bias is -1e30.  Their softmax
+        probability is exactly 0, so loss, gradients, argmax and every real parameter are unchanged, while
+        the padded pitch (e.g. vocab 2350 -> 2352, 10 -> 12) satisfies TMA's 16-byte stride rule and the
+        three GEMMs of the layer run on the tensor cores instead of the SIMT fallback."""
+        N = self.outfeature
+        Np = (N + mult - 1) // mult * mult
+        if Np == N or not self.bias:
+            return
+        w = np.zeros((self.infeature, Np), dtype=np.float32)
+        w[:, :N] = self.params.numpy()
+        b = np.full((Np,), -1e30, dtype=np.float32)
+        b[:N] = self.bias_params.numpy()
+        hd = self.host_dtype
+        self.params = DeviceArray.from_host(w, host_dtype=hd)
+        self.bias_params = DeviceArray.from_host(b, host_dtype=hd)
+        self.params_delta = DeviceArray.zeros((self.infeature, Np), host_dtype=hd)
+        self.bias_delta = DeviceArray.zeros((Np,), host_dtype=hd)
+        if self.adam:
+            self.moment_p, self.rmsprop_p = DeviceArray.zeros((self.infeature, Np)), DeviceArray.zeros((self.infeature, Np))
+            self.moment_b, self.rmsprop_b = DeviceArray.zeros((Np,)), DeviceArray.zeros((Np,))
+        self._logical_out, self.outfeature = N, Np
+
     def save_model(self):
+        n = getattr(self, "_logical_out", self.outfeature)
         if self.bias:
-            return [np.asarray(self.params), np.asarray(self.bias_params)]
-        return [np.asarray(self.params)]
+            return [np.asarray(self.params)[:, :n], np.asarray(self.bias_params)[:n]]
+        return [np.asarray(self.params)[:, :n]]
 
     def restore_model(self, models):
-        self.params.set(np.asarray(models[0]).reshape(self.params.shape))
+        n = getattr(self, "_logical_out", self.outfeature)
+        w = np.asarray(models[0]).reshape(self.infeature, n)
+        if n != self.outfeature:
+            full = np.zeros(self.params.shape)
+            full[:, :n] = w
+            w = full
+        self.params.set(w)
         if self.bias:
-            self.bias_params.set(np.asarray(models[1]).reshape(self.bias_params.shape))
+            b = np.asarray(models[1]).reshape(n)
+            if n != self.outfeature:
+                fb = np.full(self.bias_params.shape, -1e30)
+                fb[:n] = b
+                b = fb
+            self.bias_params.set(b)
 
     def __name__(self):
         return "fclayer"

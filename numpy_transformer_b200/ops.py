@@ -76,14 +76,15 @@ def attention_bwd(dout, qkv, P, H):
     return dqkv
 
 
-def cross_entropy(logits, labels=None, onehot=None, n_norm=None, want_prob=True, want_grad=True):
+def cross_entropy(logits, labels=None, onehot=None, n_norm=None, want_prob=True, want_grad=True, loss_out=None,
+                  argmax_out=None):
     rows, cols = logits.shape
     n_norm = float(rows if n_norm is None else n_norm)
-    loss = DeviceArray((), host_dtype=np.float64)
+    loss = loss_out if loss_out is not None else DeviceArray((), host_dtype=np.float64)
     row_loss = DeviceArray((rows,))
     grad = logits.empty_like() if want_grad else None
     prob = logits.empty_like() if want_prob else None
-    amax = DeviceArray((rows,), dtype=np.int32)
+    amax = argmax_out if argmax_out is not None else DeviceArray((rows,), dtype=np.int32)
     lib.nt_cross_entropy(logits.ptr, ptr_or_null(labels), ptr_or_null(onehot), n_norm, loss.ptr, row_loss.ptr,
                          ptr_or_null(grad), ptr_or_null(prob), amax.ptr, rows, cols)
     if prob is not None:

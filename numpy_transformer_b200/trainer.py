@@ -116,6 +116,20 @@ class ParamArena:
                     setattr(obj, name, nv)
         self.n_params = sum(getattr(o, pn).size for o, pn, *_ in slots)
 
+    def share_with(self, layers):
+        """Point another replica of the same layer list (same constructor order) at these arenas: the
+        replica keeps its own activations but reads / accumulates the same parameters and gradients."""
+        other = []
+        for l in layers:
+            if hasattr(l, "_slots"):
+                other.extend(l._slots())
+        assert len(other) == len(self.slots), "replica has a different parameter structure"
+        for (o0, pn, gn, mn, vn), (o1, pn1, gn1, mn1, vn1) in zip(self.slots, other):
+            assert getattr(o0, pn).shape == getattr(o1, pn1).shape
+            for a in (pn, gn, mn, vn):
+                if a is not None and getattr(o0, a, None) is not None:
+                    setattr(o1, a, getattr(o0, a))
+
 
 class TrainStep:
     """One training step of a reference-style layer list as a replayable CUDA graph.
@@ -126,11 +140,24 @@ class TrainStep:
         the loss/gradient normaliser is the GLOBAL row count.
     """
 
-    def __init__(self, layers, kind, input_shape, lr, adam=False, dp=None, use_graph=True, grad_buckets=1):
+    def __init__(self, layers, kind, input_shape, lr, adam=False, dp=None, use_graph=True, grad_buckets=1,
+                 replicas=()):
+        """replicas: extra copies of the layer list (same constructors).  With r replicas the local batch is
+        cut into r+1 micro-batches that run as parallel branches of the captured step (intra-GPU data
+        parallelism: same parameters, gradients accumulate atomically into the same arena, loss normalised
+        by the full row count) — the tiny ViT kernels are latency-bound, so their latencies overlap."""
         init()
         self.layers, self.kind, self.adam, self.dp = layers, kind, adam, dp
         self.use_graph = use_graph
+        self.chains = [layers] + [list(r) for r in replicas]
+        for ch in self.chains:                  # the head feeds cross_entropy directly: pad its class axis
+            head = ch[-1]
+            if hasattr(head, "fc1") and hasattr(head.fc1, "_pad_out"):
+                head.fc1._pad_out(4)
         self.arena = ParamArena(layers, adam)
+        for r in self.chains[1:]:
+            self.arena.share_with(r)
+        assert input_shape[0] % len(self.chains) == 0, "batch must divide evenly into micro-batch chains"
         self.input_shape = tuple(input_shape)
         in_dtype = np.float32 if kind == "vit" else np.int32
         self.rows = input_shape[0] if kind == "vit" else input_shape[0] * input_shape[1]
@@ -138,10 +165,12 @@ class TrainStep:
         self.n_norm = float(self.rows * world)
         self.h_in = PinnedBuffer(self.input_shape, in_dtype)
         self.h_lab = PinnedBuffer((self.rows,), np.int32)
-        self.h_out = PinnedBuffer((2,), np.float32)
+        self.h_out = PinnedBuffer((8,), np.float32)
         self.h_amax = PinnedBuffer((self.rows,), np.int32)
         self.d_in = DeviceArray(self.input_shape, in_dtype)
         self.d_lab = DeviceArray((self.rows,), np.int32)
+        self.d_loss = DeviceArray.zeros((len(self.chains),))
+        self.d_amax = DeviceArray.zeros((self.rows,), dtype=np.int32)
         self.d_lr = DeviceArray.from_host(np.array([lr], dtype=np.float32)).reshape(())
         self.d_t = DeviceArray.from_host(np.array([1], dtype=np.int32)).reshape(())
         self._lr = float(lr)
@@ -154,23 +183,43 @@ class TrainStep:
         self._block_t = L["attdecoderblock_layer"]
 
     # ------------------------------------------------------------------ the step body (enqueue only)
-    def _enqueue(self):
-        x = self.d_in
-        for l in self.layers:
+    def _enqueue_chain(self, c, layers):
+        nc = len(self.chains)
+        bs = self.input_shape[0] // nc
+        rows = self.rows // nc
+        in_elems = self.d_in.size // nc
+        x = self.d_in.view(c * in_elems, (bs,) + self.input_shape[1:])
+        lab = self.d_lab.view(c * rows, (rows,))
+        for l in layers:
             if isinstance(l, self._block_t):
                 x = l.forward(x, "causal")
             else:
                 x = l.forward(x)
-        self.logits = x
-        flat = x.reshape(self.rows, x.shape[-1])
-        self.loss, grad, self.probs, self.argmax = ops.cross_entropy(flat, self.d_lab, None, self.n_norm)
+        flat = x.reshape(rows, x.shape[-1])
+        loss, grad, probs, amax = ops.cross_entropy(flat, lab, None, self.n_norm, loss_out=self.d_loss.view(c, ()),
+                                                    argmax_out=self.d_amax.view(c * rows, (rows,)))
         delta = grad.reshape(x.shape)
-        first = self.layers[0]
-        for l in reversed(self.layers):
+        first = layers[0]
+        for l in reversed(layers):
             if l is first and hasattr(l, "fullconnect"):
                 delta = l.backward(delta, want_dx=False)     # nobody consumes the patch-space gradient
             else:
                 delta = l.backward(delta)
+        return x, probs
+
+    def _enqueue(self):
+        nc = len(self.chains)
+        outs = []
+        for c, layers in enumerate(self.chains):
+            if nc > 1:
+                lib.nt_chain_begin(c)
+            outs.append(self._enqueue_chain(c, layers))
+            if nc > 1:
+                lib.nt_chain_end()
+        if nc > 1:
+            lib.nt_chain_join()
+        self.logits, self.probs = outs[0] if nc == 1 else ([o[0] for o in outs], [o[1] for o in outs])
+        self.loss, self.argmax = self.d_loss, self.d_amax
         a = self.arena
         lib.nt_side_join()                       # weight-gradient branch must land before all-reduce / update
         if self.dp is not None and self.dp.world > 1:
@@ -241,11 +290,12 @@ class TrainStep:
             self.set_lr(lr)
         self.load(inputs, labels)
         self.run_device()
-        lib.nt_d2h_async(self.h_out.ptr, self.loss.ptr, 4)
+        nc = len(self.chains)
+        lib.nt_d2h_async(self.h_out.ptr, self.d_loss.ptr, 4 * nc)
         if want_argmax:
-            lib.nt_d2h_async(self.h_amax.ptr, self.argmax.ptr, self.h_amax.nbytes)
+            lib.nt_d2h_async(self.h_amax.ptr, self.d_amax.ptr, self.h_amax.nbytes)
         lib.nt_sync()
-        loss = float(self.h_out.array[0])
+        loss = float(self.h_out.array[:nc].sum())      # each chain's partial is already divided by the global N
         return (loss, self.h_amax.array.copy()) if want_argmax else loss
 
     @property
