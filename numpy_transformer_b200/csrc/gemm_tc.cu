@@ -18,6 +18,7 @@
 //     zero fill + guarded stores.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace nt {
 
@@ -33,6 +34,9 @@ struct TcParams {
   int passes;             // 1 or 3
   int stages;
   int kblocks_per_split;  // k-blocks handled by one blockIdx.z
+  int dbg_skip_a;         // experiment: do not load A (results are garbage)
+  int dbg_mma;            // experiment: MMAs issued per k-block (default 4)
+  int a_3d, b_3d;         // MN-major operand described by a 3-D map {32, k, chunk}: one TMA per k-block
   long long ldc;
   float* C;
   Epilogue ep;
@@ -69,6 +73,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -113,13 +123,13 @@ static constexpr uint32_t LAYOUT_SW128 = 2;          // K-major tiles
 static constexpr uint32_t LAYOUT_SW128_BASE32B = 1;  // MN-major 32-bit tiles
 
 #ifdef NT_TC_TIMING
-__device__ unsigned long long g_tc_times[4096 * 8];
+__device__ unsigned long long g_tc_times[16384 * 8];
 #define TC_STAMP(ev)                                                                         \
   do {                                                                                       \
     unsigned long long _t;                                                                   \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                   \
     int _cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);               \
-    if (_cta < 4096) g_tc_times[_cta * 8 + (ev)] = _t;                                       \
+    if (_cta < 16384) g_tc_times[_cta * 8 + (ev)] = _t;                                       \
   } while (0)
 #else
 #define TC_STAMP(ev) do {} while (0)
@@ -164,14 +174,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* st = smem + (size_t)s * stage_bytes;
     const uint32_t sa = smem_u32(st), sb = sa + a_bytes_;
     const int k0 = (kb_begin + i) * BK;
-    mbar_expect_tx(&full[s], a_bytes_ + b_bytes);
-    if (!p.a_mn) {
+    mbar_expect_tx(&full[s], (p.dbg_skip_a ? 0 : a_bytes_) + b_bytes);
+    if (p.dbg_skip_a) {
+    } else if (!p.a_mn) {
       tma_load_2d(sa, &tmA, &full[s], k0, m0);                       // box {32 k, 128 m}
+    } else if (p.a_3d) {
+      tma_load_3d(sa, &tmA, &full[s], 0, k0, m0 >> 5);               // box {32 m, 32 k, 4 chunks} in one instruction
     } else {
       for (int j = 0; j < BM / 32; j++) tma_load_2d(sa + j * (BK * 128), &tmA, &full[s], m0 + 32 * j, k0);  // box {32 m, 32 k}
     }
     if (!p.b_mn) {
       tma_load_2d(sb, &tmB, &full[s], k0, n0);                       // box {32 k, BN n}
+    } else if (p.b_3d) {
+      tma_load_3d(sb, &tmB, &full[s], 0, k0, n0 >> 5);
     } else {
       for (int j = 0; j < p.BN / 32; j++) tma_load_2d(sb + j * (BK * 128), &tmB, &full[s], n0 + 32 * j, k0);
     }
@@ -236,6 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sal = sb + b_bytes, sbl = sal + a_bytes;
 #pragma unroll
         for (int k = 0; k < BK / 8; k++) {
+          if (k >= p.dbg_mma && p.dbg_mma < 4) break;
           const uint64_t ah = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo, a_lay);
           const uint64_t bh = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo, b_lay);
           if (p.passes == 3) {
@@ -264,23 +280,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = i % p.stages;
         const uint32_t ph = (i / p.stages) & 1;
         mbar_wait(&full[s], ph);
-        float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+        if (ct == 0 && i == 0) TC_STAMP(2);
+        const float4* hi = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + hi_bytes);
         const int n4 = hi_bytes / 16;
 #pragma unroll 4
         for (int e = ct; e < n4; e += 32 * TC_WORKERS) {
-          float4 x = hi[e];
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-          hi[e] = h;
+          // kind::tf32 ignores the low 13 mantissa bits of its operands (measured: matches a truncated
+          // reference to 2.6e-7, a rounded one only to 1e-3), so the landed tile IS hi; only lo is written.
+          const float4 x = hi[e];
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
           lo[e] = l;
         }
-        fence_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
+        if (p.dbg_mma != 5) fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv[s]);
+        if (ct == 0 && i == 0) TC_STAMP(3);
       }
     }
     if (ct == 0) TC_STAMP(4);
@@ -326,7 +345,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        if (ct == 0 && c0 == 0) TC_STAMP(2);
 #pragma unroll
         for (int j = 0; j < 8; j++)
           *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) =
@@ -393,7 +411,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       __syncwarp();
-      if (ct == 0 && c0 == 0) TC_STAMP(3);
     }
     tc_fence_before();
     if (ct == 0) TC_STAMP(7);
@@ -452,6 +469,23 @@ static int launch_tc(dim3 grid, size_t smem, const CUtensorMap& tmA, const CUten
 
 // N-tile: the widest of {128,96,64,32} that still yields about one wave of CTAs (small problems are
 // latency-bound, so more, narrower tiles beat fewer wide ones); ties prefer exact divisors of N.
+// MN-major operand whose contiguous extent is a multiple of 32: view [K][MN] as {32, K, MN/32} so one
+// TMA instruction lands all 32-wide chunks of a k-block (each cp.async.bulk.tensor has a fixed cost of a few
+// hundred ns in the TMA unit; four 4 KB boxes per k-block made the main loop issue-latency bound).
+static int make_tmap_mn3d(CUtensorMap* tm, const float* base, long long mn, long long k, long long ld, int chunks) {
+  cuuint64_t dims[3] = {32, (cuuint64_t)k, (cuuint64_t)(mn / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)BK, (cuuint32_t)chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed (%d) mn=%lld k=%lld ld=%lld", (int)r, mn, k, ld);
+  return 0;
+}
+
+static inline bool ld_ok3(long long ld) { return (ld % 4) == 0; }
+
 static int pick_bn(int M, int N, int splits_hint) {
   const int mt = ceil_div(M, BM) * (splits_hint < 1 ? 1 : splits_hint);
   const int cand[4] = {128, 96, 64, 32};
@@ -495,6 +529,9 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   p.ldc = d.ldc;
   p.C = d.C;
   p.ep = d.ep;
+  { const char* e = getenv("NTB200_DBG_MMA"); p.dbg_mma = e ? atoi(e) : 4; }
+  { const char* e = getenv("NTB200_DBG_SKIP_A"); p.dbg_skip_a = (e && e[0] == '1') ? 1 : 0; }
+  if (const char* e = getenv("NTB200_BN")) { int v = atoi(e); if (v == 32 || v == 64 || v == 96 || v == 128) p.BN = v; }
   const int total_kb = ceil_div(d.K, BK);
   int splits = 1;
   if (d.splitk > 1) {
@@ -510,13 +547,22 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   int stages = (int)((200 * 1024) / stage);
   if (stages > 6) stages = 6;
   if (stages > p.kblocks_per_split) stages = p.kblocks_per_split < 2 ? 2 : p.kblocks_per_split;
+  // single-pass tiles are small (32 KB/stage): with two stages three CTAs share an SM and one CTA's
+  // prologue / epilogue hides behind another's main loop (measured 218 -> 115 us on 50176x384x1152)
+  if (passes == 1 && (long long)ceil_div(d.N, p.BN) * ceil_div(d.M, BM) * splits >= 2LL * g_sm_count && stages > 2) stages = 2;
+  if (const char* e = getenv("NTB200_STAGES")) { int v = atoi(e); if (v >= 1 && v <= stages) stages = v; }
   p.stages = stages;
   const size_t smem = stages * stage + (3 * stages + 2) * 8 + 1024;
 
   CUtensorMap tmA, tmB;
+  const bool use3d = getenv("NTB200_TMA_2D") == nullptr;
+  p.a_3d = (a_mn && use3d && d.M % 32 == 0 && ld_ok3(lda)) ? 1 : 0;
+  p.b_3d = (b_mn && use3d && d.N % 32 == 0 && ld_ok3(ldb)) ? 1 : 0;
   if (a_k) { if (make_tmap(&tmA, d.A, d.K, d.M, lda, BM, false)) return 1; }
+  else if (p.a_3d) { if (make_tmap_mn3d(&tmA, d.A, d.M, d.K, lda, BM / 32)) return 1; }
   else     { if (make_tmap(&tmA, d.A, d.M, d.K, lda, BK, true)) return 1; }
   if (b_k) { if (make_tmap(&tmB, d.B, d.K, d.N, ldb, p.BN, false)) return 1; }
+  else if (p.b_3d) { if (make_tmap_mn3d(&tmB, d.B, d.N, d.K, ldb, p.BN / 32)) return 1; }
   else     { if (make_tmap(&tmB, d.B, d.N, d.K, ldb, BK, true)) return 1; }
 
   dim3 grid(ceil_div(d.N, p.BN), ceil_div(d.M, BM), splits);

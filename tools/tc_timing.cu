@@ -34,19 +34,19 @@ static void run(const char* name, int M, int K, int N, int which, int passes, in
     float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms);
   }
   cudaError_t err = cudaGetLastError();
-  std::vector<unsigned long long> t(4096 * 8);
-  cudaMemcpyFromSymbol(t.data(), g_tc_times, sizeof(unsigned long long) * 4096 * 8);
+  std::vector<unsigned long long> t(16384 * 8);
+  cudaMemcpyFromSymbol(t.data(), g_tc_times, sizeof(unsigned long long) * 16384 * 8);
   // averages relative to the earliest CTA start
   unsigned long long base = ~0ull;
   int ncta = 0;
-  for (int c = 0; c < 4096; c++) if (t[c * 8]) { base = std::min(base, t[c * 8]); ncta++; }
+  for (int c = 0; c < 16384; c++) if (t[c * 8]) { base = std::min(base, t[c * 8]); ncta++; }
   double avg[8] = {0};
   unsigned long long last = 0;
-  for (int c = 0; c < 4096; c++) if (t[c * 8]) { for (int e = 0; e < 8; e++) avg[e] += (double)(t[c * 8 + e] - (e == 0 ? base : t[c * 8])) / ncta; last = std::max(last, t[c*8+7]); }
-  printf("%-28s passes=%d handled=%d err=%d event=%.1fus ctas=%d span=%.1fus | start+%.1f setup %.1f tmem_ld0 %.1f chunk0_done %.1f conv_done %.1f mma_issued %.1f tmem_full %.1f epi_done %.1f (us after CTA start)\n",
+  for (int c = 0; c < 16384; c++) if (t[c * 8]) { for (int e = 0; e < 8; e++) avg[e] += (double)(t[c * 8 + e] - (e == 0 ? base : t[c * 8])) / ncta; last = std::max(last, t[c*8+7]); }
+  printf("%-28s passes=%d handled=%d err=%d event=%.1fus ctas=%d span=%.1fus | start+%.1f setup %.1f full0 %.1f conv0_done %.1f conv_done %.1f mma_issued %.1f tmem_full %.1f epi_done %.1f (us after CTA start)\n",
          name, passes, (int)handled, (int)err, best * 1e3, ncta, (last - base) / 1e3, avg[0] / 1e3, avg[1] / 1e3, avg[2] / 1e3, avg[3] / 1e3, avg[4] / 1e3, avg[5] / 1e3, avg[6] / 1e3, avg[7] / 1e3);
   cudaMemset(x, 0, 4);
-  void* sym; cudaGetSymbolAddress(&sym, g_tc_times); cudaMemset(sym, 0, sizeof(unsigned long long) * 4096 * 8);
+  void* sym; cudaGetSymbolAddress(&sym, g_tc_times); cudaMemset(sym, 0, sizeof(unsigned long long) * 16384 * 8);
   cudaFree(x); cudaFree(w); cudaFree(y); cudaFree(b); cudaFree(pre); cudaFree(res);
 }
 
