@@ -3,6 +3,7 @@
 // dh<=64 (the ViT shapes), otherwise batched GEMMs + masked row softmax (the T=256 GPT shapes).
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace nt {
 
@@ -287,6 +288,371 @@ static size_t bwd_small_smem(int N, int dh) {
   const int N4 = (N + 3) & ~3, Np = N4 + 4;
   return sizeof(float) * (3 * (size_t)N * dh + 2 * (size_t)dh * Np + 2 * (size_t)N4 * Np);
 }
+// ---------------------------------------------------------------- mma.sync (TF32 x3) small-N kernels
+// N <= 64, dh in {24, 64}.  One CTA (4 warps) per (sample, head); warp w owns query rows 16w..16w+15 for
+// S = QK^T, the softmax (on the accumulator fragments, in registers) and O = PV, so only the initial load
+// needs a CTA barrier in forward.  Every operand is split hi/lo in registers (hi = top 19 bits, lo = x - hi)
+// and each product is three m16n8k8 MMAs (lo*hi + hi*lo + hi*hi): fp32-class accuracy at ~1/10 of the
+// FFMA instruction count.  Shared-memory row strides are chosen per access pattern: stride = 4 (mod 32) is
+// conflict-free for (row=groupID, col=tig) fragment reads, stride = 8 (mod 32) for (row=tig, col=groupID).
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xFFFFE000u;
+}
+template <int NA>
+__device__ __forceinline__ void split_frag(const float (&x)[NA], uint32_t (&hi)[NA], uint32_t (&lo)[NA]) {
+#pragma unroll
+  for (int i = 0; i < NA; i++) split_tf32(x[i], hi[i], lo[i]);
+}
+__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                     const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  mma_tf32(d, al, bh);
+  mma_tf32(d, ah, bl);
+  mma_tf32(d, ah, bh);
+}
+// A fragment (16x8) of a row-major matrix M[row][col] with leading dimension ld, tile origin (r0, c0)
+__device__ __forceinline__ void load_a(const float* M, int ld, int r0, int c0, int g, int t, float (&a)[4]) {
+  a[0] = M[(r0 + g) * ld + c0 + t];
+  a[1] = M[(r0 + g + 8) * ld + c0 + t];
+  a[2] = M[(r0 + g) * ld + c0 + t + 4];
+  a[3] = M[(r0 + g + 8) * ld + c0 + t + 4];
+}
+// A fragment of the TRANSPOSE of M: A(row, col) = M[col][row]
+__device__ __forceinline__ void load_at(const float* M, int ld, int r0, int c0, int g, int t, float (&a)[4]) {
+  a[0] = M[(c0 + t) * ld + r0 + g];
+  a[1] = M[(c0 + t) * ld + r0 + g + 8];
+  a[2] = M[(c0 + t + 4) * ld + r0 + g];
+  a[3] = M[(c0 + t + 4) * ld + r0 + g + 8];
+}
+// B fragment (8x8, "col" layout) where B(k, n) = M[n][k]   (e.g. K in Q K^T)
+__device__ __forceinline__ void load_b_nk(const float* M, int ld, int n0, int k0, int g, int t, float (&b)[2]) {
+  b[0] = M[(n0 + g) * ld + k0 + t];
+  b[1] = M[(n0 + g) * ld + k0 + t + 4];
+}
+// B fragment where B(k, n) = M[k][n]   (e.g. V in P V)
+__device__ __forceinline__ void load_b_kn(const float* M, int ld, int k0, int n0, int g, int t, float (&b)[2]) {
+  b[0] = M[(k0 + t) * ld + n0 + g];
+  b[1] = M[(k0 + t + 4) * ld + n0 + g];
+}
+
+template <int DH>
+struct AttMma {
+  static constexpr int LDA = DH + 4;                       // = 4 (mod 32) for DH in {24, 64}... (28 / 68)
+  static constexpr int LDB = (DH % 32 == 0) ? DH + 8 : DH + 16;   // = 8 (mod 32): 72 / 40
+  static constexpr int LDP = 68;                           // [64][68] score tiles
+  static constexpr int KD = DH / 8;                        // k-steps over the head dimension
+};
+
+template <int DH>
+__global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
+                                                           int mask_kind, float* __restrict__ out, float* __restrict__ P,
+                                                           float* __restrict__ S, int N, int H,
+                                                           const float* __restrict__ residual) {
+  pdl_prologue();
+  using C = AttMma<DH>;
+  extern __shared__ __align__(16) float sm[];
+  float* sQ = sm;                          // [64][LDA]
+  float* sK = sQ + 64 * C::LDA;            // [64][LDA]   B(k=d, n=j) = K[j][d]
+  float* sV = sK + 64 * C::LDA;            // [64][LDB]   B(k=j, n=d) = V[j][d]
+  float* sP = sV + 64 * C::LDB;            // [64][LDP]
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int D = H * DH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const float* base = qkv + (long long)b * N * 3 * D + h * DH;
+  for (int e = tid; e < 64 * (DH / 4); e += 128) {
+    const int i = e / (DH / 4), d4 = (e % (DH / 4)) * 4;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q;
+    if (i < N) {
+      const float* r = base + (long long)i * 3 * D + d4;
+      q = __ldg(reinterpret_cast<const float4*>(r));
+      k = __ldg(reinterpret_cast<const float4*>(r + D));
+      v = __ldg(reinterpret_cast<const float4*>(r + 2 * D));
+    }
+    *reinterpret_cast<float4*>(sQ + i * C::LDA + d4) = q;
+    *reinterpret_cast<float4*>(sK + i * C::LDA + d4) = k;
+    *reinterpret_cast<float4*>(sV + i * C::LDB + d4) = v;
+  }
+  __syncthreads();
+  const int i0 = warp * 16;
+  if (i0 >= N) return;                     // no further CTA-wide barriers below
+  const int NT = (N + 7) >> 3;             // key tiles of 8
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < C::KD; ks++) {
+    float a[4];
+    uint32_t ah[4], al[4];
+    load_a(sQ, C::LDA, i0, ks * 8, g, t, a);
+    split_frag<4>(a, ah, al);
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      if (nt < NT) {
+        float bb[2];
+        uint32_t bh_[2], bl_[2];
+        load_b_nk(sK, C::LDA, nt * 8, ks * 8, g, t, bb);
+        split_frag<2>(bb, bh_, bl_);
+        mma3(acc[nt], ah, al, bh_, bl_);
+      }
+    }
+  }
+  // scale, optional score dump, mask, softmax over the accumulator fragments (rows r0 = i0+g, r1 = r0+8)
+  const float scale = 1.0f / sqrtf((float)DH);
+  const int r0 = i0 + g, r1 = r0 + 8;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int row = (c < 2) ? r0 : r1, col = nt * 8 + 2 * t + (c & 1);
+      float v = acc[nt][c] * scale;                                           // attention.py:37
+      if (nt < NT && col < N && row < N) {
+        if (S) S[(long long)bh * N * N + row * N + col] = v;                   // att_col
+        if (mask_kind == NT_MASK_CAUSAL) { if (col > row) v = -INFINITY; }
+        else if (mask_kind == NT_MASK_DENSE) v += mask[row * N + col];         // attention.py:38-39
+      } else {
+        v = -INFINITY;                                                         // padded keys never win
+      }
+      acc[nt][c] = v;
+      if (c < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  if (r0 >= N) mx0 = 0.f;                  // fully padded rows: keep the arithmetic finite
+  if (r1 >= N) mx1 = 0.f;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++) {
+    acc[nt][0] = expf(acc[nt][0] - mx0); acc[nt][1] = expf(acc[nt][1] - mx0);
+    acc[nt][2] = expf(acc[nt][2] - mx1); acc[nt][3] = expf(acc[nt][3] - mx1);
+    s0 += acc[nt][0] + acc[nt][1];
+    s1 += acc[nt][2] + acc[nt][3];
+  }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float inv0 = r0 < N ? 1.0f / s0 : 0.f, inv1 = r1 < N ? 1.0f / s1 : 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++) {
+    const int col = nt * 8 + 2 * t;
+    const float p00 = acc[nt][0] * inv0, p01 = acc[nt][1] * inv0, p10 = acc[nt][2] * inv1, p11 = acc[nt][3] * inv1;
+    *reinterpret_cast<float2*>(sP + r0 * C::LDP + col) = make_float2(p00, p01);
+    *reinterpret_cast<float2*>(sP + r1 * C::LDP + col) = make_float2(p10, p11);
+    if (nt < NT) {
+      float* pg0 = P + ((long long)bh * N + r0) * N + col;                     // atg__
+      float* pg1 = P + ((long long)bh * N + r1) * N + col;
+      if (r0 < N) { if (col < N) pg0[0] = p00; if (col + 1 < N) pg0[1] = p01; }
+      if (r1 < N) { if (col < N) pg1[0] = p10; if (col + 1 < N) pg1[1] = p11; }
+    }
+  }
+  __syncwarp();
+  // O = P V : this warp's 16 rows x DH
+  float o[C::KD][4];
+#pragma unroll
+  for (int nd = 0; nd < C::KD; nd++) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+  for (int kt = 0; kt < NT; kt++) {
+    float a[4];
+    uint32_t ah[4], al[4];
+    load_a(sP, C::LDP, i0, kt * 8, g, t, a);
+    split_frag<4>(a, ah, al);
+#pragma unroll
+    for (int nd = 0; nd < C::KD; nd++) {
+      float bb[2];
+      uint32_t bh_[2], bl_[2];
+      load_b_kn(sV, C::LDB, kt * 8, nd * 8, g, t, bb);
+      split_frag<2>(bb, bh_, bl_);
+      mma3(o[nd], ah, al, bh_, bl_);
+    }
+  }
+#pragma unroll
+  for (int nd = 0; nd < C::KD; nd++) {
+    const int col = h * DH + nd * 8 + 2 * t;
+    if (r0 < N) {
+      const long long oi = ((long long)b * N + r0) * D + col;
+      float2 v = make_float2(o[nd][0], o[nd][1]);
+      if (residual) { const float2 rr = __ldg(reinterpret_cast<const float2*>(residual + oi)); v.x += rr.x; v.y += rr.y; }
+      *reinterpret_cast<float2*>(out + oi) = v;
+    }
+    if (r1 < N) {
+      const long long oi = ((long long)b * N + r1) * D + col;
+      float2 v = make_float2(o[nd][2], o[nd][3]);
+      if (residual) { const float2 rr = __ldg(reinterpret_cast<const float2*>(residual + oi)); v.x += rr.x; v.y += rr.y; }
+      *reinterpret_cast<float2*>(out + oi) = v;
+    }
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
+                                                           const float* __restrict__ P, float* __restrict__ dqkv, int N,
+                                                           int H) {
+  pdl_prologue();
+  using C = AttMma<DH>;
+  extern __shared__ __align__(16) float sm[];
+  float* sQ = sm;                          // [64][LDB]  B(k=i, n=d) = Q[i][d]       (dK)
+  float* sK = sQ + 64 * C::LDB;            // [64][LDB]  B(k=j, n=d) = K[j][d]       (dQ)
+  float* sV = sK + 64 * C::LDB;            // [64][LDA]  B(k=d, n=j) = V[j][d]       (dP)
+  float* sdO = sV + 64 * C::LDA;           // [64][LDA]  A in dP, B(k=i, n=d) in dV
+  float* sP = sdO + 64 * C::LDA;           // [64][LDP]
+  float* sdS = sP + 64 * C::LDP;           // [64][LDP]
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int D = H * DH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const float* base = qkv + (long long)b * N * 3 * D + h * DH;
+  for (int e = tid; e < 64 * (DH / 4); e += 128) {
+    const int i = e / (DH / 4), d4 = (e % (DH / 4)) * 4;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q, go = q;
+    if (i < N) {
+      const float* r = base + (long long)i * 3 * D + d4;
+      q = __ldg(reinterpret_cast<const float4*>(r));
+      k = __ldg(reinterpret_cast<const float4*>(r + D));
+      v = __ldg(reinterpret_cast<const float4*>(r + 2 * D));
+      go = __ldg(reinterpret_cast<const float4*>(dout + ((long long)b * N + i) * D + h * DH + d4));
+    }
+    *reinterpret_cast<float4*>(sQ + i * C::LDB + d4) = q;
+    *reinterpret_cast<float4*>(sK + i * C::LDB + d4) = k;
+    *reinterpret_cast<float4*>(sV + i * C::LDA + d4) = v;
+    *reinterpret_cast<float4*>(sdO + i * C::LDA + d4) = go;
+  }
+  for (int e = tid; e < 64 * 64; e += 128) {
+    const int i = e >> 6, j = e & 63;
+    sP[i * C::LDP + j] = (i < N && j < N) ? __ldg(P + (long long)bh * N * N + i * N + j) : 0.f;
+  }
+  __syncthreads();
+  const int NT = (N + 7) >> 3;
+  const int i0 = warp * 16;
+  const float scale = 1.0f / sqrtf((float)DH);
+  float* obase = dqkv + (long long)b * N * 3 * D + h * DH;
+  const int r0 = i0 + g, r1 = r0 + 8;
+  {
+    // dP = dO V^T  (attention.py:74) for this warp's 16 query rows; rows >= N are all-zero and harmless
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < C::KD; ks++) {
+      float a[4];
+      uint32_t ah[4], al[4];
+      load_a(sdO, C::LDA, i0, ks * 8, g, t, a);
+      split_frag<4>(a, ah, al);
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) {
+        if (nt < NT) {
+          float bb[2];
+          uint32_t bh_[2], bl_[2];
+          load_b_nk(sV, C::LDA, nt * 8, ks * 8, g, t, bb);
+          split_frag<2>(bb, bh_, bl_);
+          mma3(acc[nt], ah, al, bh_, bl_);
+        }
+      }
+    }
+    // dS = P o (dP - rowsum(dP o P))  (attention.py:75), on the fragments
+    float s0 = 0.f, s1 = 0.f;
+    float2 p0[8], p1[8];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      p0[nt] = *reinterpret_cast<const float2*>(sP + r0 * C::LDP + nt * 8 + 2 * t);
+      p1[nt] = *reinterpret_cast<const float2*>(sP + r1 * C::LDP + nt * 8 + 2 * t);
+      s0 += acc[nt][0] * p0[nt].x + acc[nt][1] * p0[nt].y;
+      s1 += acc[nt][2] * p1[nt].x + acc[nt][3] * p1[nt].y;
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      *reinterpret_cast<float2*>(sdS + r0 * C::LDP + nt * 8 + 2 * t) =
+          make_float2(p0[nt].x * (acc[nt][0] - s0), p0[nt].y * (acc[nt][1] - s0));
+      *reinterpret_cast<float2*>(sdS + r1 * C::LDP + nt * 8 + 2 * t) =
+          make_float2(p1[nt].x * (acc[nt][2] - s1), p1[nt].y * (acc[nt][3] - s1));
+    }
+  }
+  __syncwarp();
+  if (i0 < N) {
+    // dQ = dS K / sqrt(dh)  (attention.py:78)
+    float o[C::KD][4];
+#pragma unroll
+    for (int nd = 0; nd < C::KD; nd++) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+    for (int kt = 0; kt < NT; kt++) {
+      float a[4];
+      uint32_t ah[4], al[4];
+      load_a(sdS, C::LDP, i0, kt * 8, g, t, a);
+      split_frag<4>(a, ah, al);
+#pragma unroll
+      for (int nd = 0; nd < C::KD; nd++) {
+        float bb[2];
+        uint32_t bh_[2], bl_[2];
+        load_b_kn(sK, C::LDB, kt * 8, nd * 8, g, t, bb);
+        split_frag<2>(bb, bh_, bl_);
+        mma3(o[nd], ah, al, bh_, bl_);
+      }
+    }
+#pragma unroll
+    for (int nd = 0; nd < C::KD; nd++) {
+      const int col = nd * 8 + 2 * t;
+      if (r0 < N) *reinterpret_cast<float2*>(obase + (long long)r0 * 3 * D + col) = make_float2(o[nd][0] * scale, o[nd][1] * scale);
+      if (r1 < N) *reinterpret_cast<float2*>(obase + (long long)r1 * 3 * D + col) = make_float2(o[nd][2] * scale, o[nd][3] * scale);
+    }
+  }
+  __syncthreads();                         // every warp's rows of dS are in shared memory
+  if (i0 < N) {
+    // this warp now owns KEYS j0 = 16w..: dK = dS^T Q / sqrt(dh) (attention.py:79), dV = P^T dO (attention.py:76)
+    const int j0 = i0;
+    float ok[C::KD][4], ov[C::KD][4];
+#pragma unroll
+    for (int nd = 0; nd < C::KD; nd++) {
+      ok[nd][0] = ok[nd][1] = ok[nd][2] = ok[nd][3] = 0.f;
+      ov[nd][0] = ov[nd][1] = ov[nd][2] = ov[nd][3] = 0.f;
+    }
+    for (int kt = 0; kt < NT; kt++) {       // contraction over query rows i
+      float a[4];
+      uint32_t sh[4], sl[4], ph[4], pl[4];
+      load_at(sdS, C::LDP, j0, kt * 8, g, t, a);
+      split_frag<4>(a, sh, sl);
+      load_at(sP, C::LDP, j0, kt * 8, g, t, a);
+      split_frag<4>(a, ph, pl);
+#pragma unroll
+      for (int nd = 0; nd < C::KD; nd++) {
+        float bb[2];
+        uint32_t bh_[2], bl_[2];
+        load_b_kn(sQ, C::LDB, kt * 8, nd * 8, g, t, bb);
+        split_frag<2>(bb, bh_, bl_);
+        mma3(ok[nd], sh, sl, bh_, bl_);
+        load_b_kn(sdO, C::LDA, kt * 8, nd * 8, g, t, bb);
+        split_frag<2>(bb, bh_, bl_);
+        mma3(ov[nd], ph, pl, bh_, bl_);
+      }
+    }
+    const int k0r = j0 + g, k1r = k0r + 8;
+#pragma unroll
+    for (int nd = 0; nd < C::KD; nd++) {
+      const int col = nd * 8 + 2 * t;
+      if (k0r < N) {
+        float* o = obase + (long long)k0r * 3 * D + col;
+        *reinterpret_cast<float2*>(o + D) = make_float2(ok[nd][0] * scale, ok[nd][1] * scale);
+        *reinterpret_cast<float2*>(o + 2 * D) = make_float2(ov[nd][0], ov[nd][1]);
+      }
+      if (k1r < N) {
+        float* o = obase + (long long)k1r * 3 * D + col;
+        *reinterpret_cast<float2*>(o + D) = make_float2(ok[nd][2] * scale, ok[nd][3] * scale);
+        *reinterpret_cast<float2*>(o + 2 * D) = make_float2(ov[nd][2], ov[nd][3]);
+      }
+    }
+  }
+}
+
+template <int DH>
+static size_t fwd_mma_smem() { using C = AttMma<DH>; return sizeof(float) * (64 * C::LDA * 2 + 64 * C::LDB + 64 * C::LDP); }
+template <int DH>
+static size_t bwd_mma_smem() { using C = AttMma<DH>; return sizeof(float) * (64 * C::LDB * 2 + 64 * C::LDA * 2 + 2 * 64 * C::LDP); }
+static bool g_att_mma = true;               // NTB200_ATT_MMA=0 falls back to the FFMA kernels
+static bool mma_ok(int N, int dh) { return g_att_mma && N <= 64 && (dh == 24 || dh == 64); }
+
 static bool small_ok(int N, int H, int dh) { return N <= 64 && dh <= 64 && (dh & 3) == 0; }
 
 static int softmax_rows(const float* x, float* p, long long rows, int cols, const float* mask, int mask_kind, int N) {
@@ -323,6 +689,22 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
   NT_REQUIRE(mask_kind != NT_MASK_DENSE || mask, "nt_attention_fwd: dense mask_kind needs a mask");
   if (B == 0) return 0;
   const int D = H * dh;
+  if (const char* e = getenv("NTB200_ATT_MMA")) g_att_mma = (e[0] != '0');
+  if (mma_ok(N, dh)) {
+    if (dh == 24) {
+      const size_t smem = fwd_mma_smem<24>();
+      static bool cfg = false;
+      if (!cfg) { NT_CHECK(cudaFuncSetAttribute(attn_fwd_mma_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+      NT_CHECK(nt::launch_k(attn_fwd_mma_kernel<24>, dim3(B * H), dim3(128), smem, qkv, mask, mask_kind, out, P, S, N, H, residual));
+    } else {
+      const size_t smem = fwd_mma_smem<64>();
+      static bool cfg = false;
+      if (!cfg) { NT_CHECK(cudaFuncSetAttribute(attn_fwd_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+      NT_CHECK(nt::launch_k(attn_fwd_mma_kernel<64>, dim3(B * H), dim3(128), smem, qkv, mask, mask_kind, out, P, S, N, H, residual));
+    }
+    NT_LAUNCH_OK();
+    return 0;
+  }
   if (small_ok(N, H, dh)) {
     size_t smem = fwd_small_smem(N, dh);
 #define NT_ATT_FWD(NC_, DHC_)                                                                                       \
@@ -374,6 +756,21 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
   NT_REQUIRE(B >= 0 && N > 0 && H > 0 && dh > 0, "nt_attention_bwd: bad shape");
   if (B == 0) return 0;
   const int D = H * dh;
+  if (mma_ok(N, dh)) {
+    if (dh == 24) {
+      const size_t smem = bwd_mma_smem<24>();
+      static bool cfg = false;
+      if (!cfg) { NT_CHECK(cudaFuncSetAttribute(attn_bwd_mma_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+      NT_CHECK(nt::launch_k(attn_bwd_mma_kernel<24>, dim3(B * H), dim3(128), smem, dout, qkv, P, dqkv, N, H));
+    } else {
+      const size_t smem = bwd_mma_smem<64>();
+      static bool cfg = false;
+      if (!cfg) { NT_CHECK(cudaFuncSetAttribute(attn_bwd_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+      NT_CHECK(nt::launch_k(attn_bwd_mma_kernel<64>, dim3(B * H), dim3(128), smem, dout, qkv, P, dqkv, N, H));
+    }
+    NT_LAUNCH_OK();
+    return 0;
+  }
   if (small_ok(N, H, dh)) {
     size_t smem = bwd_small_smem(N, dh);
 #define NT_ATT_BWD(NC_, DHC_)                                                                                       \
