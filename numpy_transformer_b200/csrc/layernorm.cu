@@ -1,5 +1,6 @@
 // LayerNorm forward/backward (net/layernorm.py:88-135): one warp per row, shuffle reductions.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace nt {
 
@@ -91,64 +92,83 @@ __global__ void ln_bwd_param_kernel(const float* __restrict__ dy, const float* _
 }
 
 // Fused backward: one pass over x and dy produces dx AND the dgamma/dbeta partials.  A CTA of 8 warps owns
-// LN_ROWS rows; each lane keeps its columns (c = lane + 32k) of x/dy in registers, so the row reductions are
-// warp shuffles and the column reductions are register accumulators -> smem across warps -> one atomicAdd
-// per column per CTA.  NC = columns per lane (D <= 32*NC).
-constexpr int LN_ROWS = 32;
-template <int NC>
+// `rows` rows; each lane keeps NV float4 column groups (c = 4*(lane + 32k)) of x / dy / addend in registers,
+// loaded with 128-bit accesses issued together, so the row reductions are warp shuffles and the column
+// reductions are register accumulators -> smem across warps -> one atomicAdd per column per CTA.  D % 4 == 0.
+template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma, float* __restrict__ dx,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
-                                                           int D, const float* __restrict__ addend) {
+                                                           int D, const float* __restrict__ addend, int LN_ROWS) {
   pdl_prologue();
   extern __shared__ float red[];                 // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * LN_ROWS;
-  float g[NC], ag[NC], ab[NC];
+  const int D4 = D >> 2;
+  float4 g[NV], ag[NV], ab[NV];
 #pragma unroll
-  for (int k = 0; k < NC; k++) {
-    const int c = lane + 32 * k;
-    g[k] = c < D ? gamma[c] : 0.f;
-    ag[k] = 0.f;
-    ab[k] = 0.f;
+  for (int k = 0; k < NV; k++) {
+    const int c4 = lane + 32 * k;
+    g[k] = c4 < D4 ? reinterpret_cast<const float4*>(gamma)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float invD = 1.0f / D;
-  for (int r = r0 + warp; r < min(M, r0 + LN_ROWS); r += 8) {
-    const long long off = (long long)r * D;
+  const int rend = min(M, r0 + LN_ROWS);
+  for (int r = r0 + warp; r < rend; r += 8) {
+    const long long off4 = (long long)r * D4;
+    float4 dyv[NV], xv[NV], av[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      const int c4 = lane + 32 * k;
+      const bool ok = c4 < D4;
+      dyv[k] = ok ? reinterpret_cast<const float4*>(dy)[off4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      xv[k] = ok ? reinterpret_cast<const float4*>(x)[off4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      av[k] = (ok && addend) ? reinterpret_cast<const float4*>(addend)[off4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const float mu = mean[r], rs = rstd[r];
-    float dyv[NC], xh[NC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < NC; k++) {
-      const int c = lane + 32 * k;
-      dyv[k] = c < D ? dy[off + c] : 0.f;
-      xh[k] = c < D ? (x[off + c] - mu) * rs : 0.f;
-      const float gdy = g[k] * dyv[k];
-      s1 += gdy;
-      s2 += gdy * xh[k];
-      ag[k] = fmaf(xh[k], dyv[k], ag[k]);
-      ab[k] += dyv[k];
+    for (int k = 0; k < NV; k++) {
+      const bool ok = (lane + 32 * k) < D4;
+      float4& xh = xv[k];
+      xh.x = ok ? (xh.x - mu) * rs : 0.f; xh.y = ok ? (xh.y - mu) * rs : 0.f;
+      xh.z = ok ? (xh.z - mu) * rs : 0.f; xh.w = ok ? (xh.w - mu) * rs : 0.f;
+      const float4 d = dyv[k];
+      const float gx = g[k].x * d.x, gy = g[k].y * d.y, gz = g[k].z * d.z, gw = g[k].w * d.w;
+      s1 += gx + gy + gz + gw;
+      s2 += gx * xh.x + gy * xh.y + gz * xh.z + gw * xh.w;
+      ag[k].x = fmaf(xh.x, d.x, ag[k].x); ag[k].y = fmaf(xh.y, d.y, ag[k].y);
+      ag[k].z = fmaf(xh.z, d.z, ag[k].z); ag[k].w = fmaf(xh.w, d.w, ag[k].w);
+      ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
     }
     s1 = warp_sum(s1) * invD;
     s2 = warp_sum(s2) * invD;
     if (dx) {
 #pragma unroll
-      for (int k = 0; k < NC; k++) {
-        const int c = lane + 32 * k;
-        if (c < D) {
-          float o = rs * (g[k] * dyv[k] - s1 - xh[k] * s2);
-          if (addend) o += addend[off + c];
-          dx[off + c] = o;
+      for (int k = 0; k < NV; k++) {
+        const int c4 = lane + 32 * k;
+        if (c4 < D4) {
+          const float4 d = dyv[k], xh = xv[k];
+          float4 o;
+          o.x = rs * (g[k].x * d.x - s1 - xh.x * s2) + av[k].x;
+          o.y = rs * (g[k].y * d.y - s1 - xh.y * s2) + av[k].y;
+          o.z = rs * (g[k].z * d.z - s1 - xh.z * s2) + av[k].z;
+          o.w = rs * (g[k].w * d.w - s1 - xh.w * s2) + av[k].w;
+          reinterpret_cast<float4*>(dx)[off4 + c4] = o;
         }
       }
     }
   }
   if (dgamma) {
 #pragma unroll
-    for (int k = 0; k < NC; k++) {
-      const int c = lane + 32 * k;
-      if (c < D) { red[(warp * 2) * D + c] = ag[k]; red[(warp * 2 + 1) * D + c] = ab[k]; }
+    for (int k = 0; k < NV; k++) {
+      const int c4 = lane + 32 * k;
+      if (c4 < D4) {
+        reinterpret_cast<float4*>(red + (warp * 2) * D)[c4] = ag[k];
+        reinterpret_cast<float4*>(red + (warp * 2 + 1) * D)[c4] = ab[k];
+      }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < D; c += 256) {
@@ -161,12 +181,16 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* __restri
   }
 }
 
-template <int NC>
+template <int NV>
 static int launch_ln_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                                float* dx, float* dgamma, float* dbeta, int M, int D, const float* addend) {
   const size_t smem = sizeof(float) * 16 * (size_t)D;
-  NT_CHECK(nt::launch_k(ln_bwd_fused_kernel<NC>, dim3(ceil_div(M, LN_ROWS)), dim3(256), smem, dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D,
-                                                                         addend));
+  // rows per CTA: every CTA ends with 2*D same-address atomics, so large M uses taller CTAs
+  int rows = 32;
+  if (const char* e = getenv("NTB200_LN_ROWS")) rows = atoi(e);
+  else if (M >= 32768) rows = 128;
+  NT_CHECK(nt::launch_k(ln_bwd_fused_kernel<NV>, dim3(ceil_div(M, rows)), dim3(256), smem, dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D,
+                                                                         addend, rows));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -193,11 +217,14 @@ int nt_layernorm_bwd(const float* dy, const float* x, const float* mean, const f
   NT_ENTRY();
   NT_REQUIRE(M >= 0 && D > 0, "nt_layernorm_bwd: bad shape M=%d D=%d", M, D);
   if (M == 0) return 0;
-  if (D <= 768 && (dgamma != nullptr) == (dbeta != nullptr)) {
-    if (D <= 128) return launch_ln_bwd_fused<4>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
-    if (D <= 256) return launch_ln_bwd_fused<8>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
-    if (D <= 384) return launch_ln_bwd_fused<12>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
-    return launch_ln_bwd_fused<24>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
+  static int split_big = -1;
+  if (split_big < 0) { const char* e = getenv("NTB200_LN_SPLIT"); split_big = e ? atoi(e) : 0; }
+  const bool vec_ok = (D % 4 == 0) && ((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)addend | (uintptr_t)gamma) & 15) == 0);
+  if (D <= 768 && vec_ok && (dgamma != nullptr) == (dbeta != nullptr) && !(split_big && M >= 32768)) {
+    if (D <= 128) return launch_ln_bwd_fused<1>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
+    if (D <= 256) return launch_ln_bwd_fused<2>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
+    if (D <= 384) return launch_ln_bwd_fused<3>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
+    return launch_ln_bwd_fused<6>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
   }
   if (dgamma && dbeta) {
     int rows_per_block = M >= 8192 ? 512 : 128;
