@@ -341,6 +341,19 @@ __device__ __forceinline__ void load_b_kn(const float* M, int ld, int k0, int n0
   b[1] = M[(k0 + t + 4) * ld + n0 + g];
 }
 
+// asynchronous global->shared copies (LDGSTS): the whole operand set of a CTA is in flight at once instead of
+// being serialised through registers (ncu: long-scoreboard stalls dominated the first version of these kernels)
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 template <int DH>
 struct AttMma {
   static constexpr int LDA = DH + 4;                       // = 4 (mod 32) for DH in {24, 64}... (28 / 68)
@@ -367,17 +380,19 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(const float* __restri
   const float* base = qkv + (long long)b * N * 3 * D + h * DH;
   for (int e = tid; e < 64 * (DH / 4); e += 128) {
     const int i = e / (DH / 4), d4 = (e % (DH / 4)) * 4;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q;
     if (i < N) {
       const float* r = base + (long long)i * 3 * D + d4;
-      q = __ldg(reinterpret_cast<const float4*>(r));
-      k = __ldg(reinterpret_cast<const float4*>(r + D));
-      v = __ldg(reinterpret_cast<const float4*>(r + 2 * D));
+      cp_async16(sQ + i * C::LDA + d4, r);
+      cp_async16(sK + i * C::LDA + d4, r + D);
+      cp_async16(sV + i * C::LDB + d4, r + 2 * D);
+    } else {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(sQ + i * C::LDA + d4) = z;
+      *reinterpret_cast<float4*>(sK + i * C::LDA + d4) = z;
+      *reinterpret_cast<float4*>(sV + i * C::LDB + d4) = z;
     }
-    *reinterpret_cast<float4*>(sQ + i * C::LDA + d4) = q;
-    *reinterpret_cast<float4*>(sK + i * C::LDA + d4) = k;
-    *reinterpret_cast<float4*>(sV + i * C::LDB + d4) = v;
   }
+  cp_async_wait_all();
   __syncthreads();
   const int i0 = warp * 16;
   if (i0 >= N) return;                     // no further CTA-wide barriers below
@@ -507,23 +522,26 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const float* __restri
   const float* base = qkv + (long long)b * N * 3 * D + h * DH;
   for (int e = tid; e < 64 * (DH / 4); e += 128) {
     const int i = e / (DH / 4), d4 = (e % (DH / 4)) * 4;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q, go = q;
     if (i < N) {
       const float* r = base + (long long)i * 3 * D + d4;
-      q = __ldg(reinterpret_cast<const float4*>(r));
-      k = __ldg(reinterpret_cast<const float4*>(r + D));
-      v = __ldg(reinterpret_cast<const float4*>(r + 2 * D));
-      go = __ldg(reinterpret_cast<const float4*>(dout + ((long long)b * N + i) * D + h * DH + d4));
+      cp_async16(sQ + i * C::LDB + d4, r);
+      cp_async16(sK + i * C::LDB + d4, r + D);
+      cp_async16(sV + i * C::LDA + d4, r + 2 * D);
+      cp_async16(sdO + i * C::LDA + d4, dout + ((long long)b * N + i) * D + h * DH + d4);
+    } else {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(sQ + i * C::LDB + d4) = z;
+      *reinterpret_cast<float4*>(sK + i * C::LDB + d4) = z;
+      *reinterpret_cast<float4*>(sV + i * C::LDA + d4) = z;
+      *reinterpret_cast<float4*>(sdO + i * C::LDA + d4) = z;
     }
-    *reinterpret_cast<float4*>(sQ + i * C::LDB + d4) = q;
-    *reinterpret_cast<float4*>(sK + i * C::LDB + d4) = k;
-    *reinterpret_cast<float4*>(sV + i * C::LDA + d4) = v;
-    *reinterpret_cast<float4*>(sdO + i * C::LDA + d4) = go;
   }
   for (int e = tid; e < 64 * 64; e += 128) {
     const int i = e >> 6, j = e & 63;
-    sP[i * C::LDP + j] = (i < N && j < N) ? __ldg(P + (long long)bh * N * N + i * N + j) : 0.f;
+    if (i < N && j < N) cp_async4(sP + i * C::LDP + j, P + (long long)bh * N * N + i * N + j);
+    else sP[i * C::LDP + j] = 0.f;
   }
+  cp_async_wait_all();
   __syncthreads();
   const int NT = (N + 7) >> 3;
   const int i0 = warp * 16;

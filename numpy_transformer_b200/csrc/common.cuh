@@ -99,6 +99,7 @@ struct Epilogue {
   const float* addend = nullptr;    // [M,N] row stride ldc, added last
   float alpha = 1.0f;               // scale on the accumulator
   int atomic = 0;                   // 1: atomicAdd into C (split-K / accumulate semantics)
+  float* colsum = nullptr;          // [N] += column sums of the MN-major B operand (db of the weight-gradient GEMM)
 };
 
 // C(m,n) = alpha * sum_k A(m,k) B(k,n), generic strides, two-level batch (z = z0*nb1 + z1)
@@ -109,6 +110,7 @@ struct GemmDesc {
   int nb0 = 1, nb1 = 1;
   long long bA0 = 0, bA1 = 0, bB0 = 0, bB1 = 0, bC0 = 0, bC1 = 0;
   int splitk = 1;
+  bool* colsum_done = nullptr;       // set by the engine that fused ep.colsum
   Epilogue ep;
 };
 int gemm_simt(const GemmDesc& d);

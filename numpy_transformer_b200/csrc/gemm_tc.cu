@@ -155,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* conv = bars + 2 * p.stages;
   uint64_t* tmem_full = bars + 3 * p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
+  float* cs_s = reinterpret_cast<float*>(tmem_slot + 4);      // [128] column sums of the B tile (db fusion)
 
   pdl_launch_dependents();            // the next kernel may start its own prologue now
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -191,13 +192,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int j = 0; j < p.BN / 32; j++) tma_load_2d(sb + j * (BK * 128), &tmB, &full[s], n0 + 32 * j, k0);
     }
   };
+  // db = colsum(dY) rides along with dW = x^T dY: the worker warps already sweep every landed B tile
+  const bool do_colsum = (p.ep.colsum != nullptr) && p.b_mn && blockIdx.y == 0;
+  if (threadIdx.x < 128) cs_s[threadIdx.x] = 0.f;
   const int prologue = nkb < p.stages ? nkb : p.stages;
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int s = 0; s < p.stages; s++) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], (p.passes == 1 && do_colsum) ? 1 + TC_WORKERS : 1);
       mbar_init(&conv[s], TC_WORKERS);
     }
     mbar_init(tmem_full, 1);
@@ -274,7 +278,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===================== converters (3xTF32 split), then epilogue =====================
     const int ct = threadIdx.x - 64;     // 0 .. 32*TC_WORKERS-1
-    if (p.passes == 3) {
+    float4 cs[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) cs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.passes == 3 || do_colsum) {
       const uint32_t hi_bytes = a_bytes + b_bytes;
       for (int i = 0; i < nkb; i++) {
         const int s = i % p.stages;
@@ -282,25 +289,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&full[s], ph);
         if (ct == 0 && i == 0) TC_STAMP(2);
         const float4* hi = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
-        float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + hi_bytes);
-        const int n4 = hi_bytes / 16;
+        if (p.passes == 3) {
+          float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + hi_bytes);
+          const int n4 = hi_bytes / 16;
 #pragma unroll 4
-        for (int e = ct; e < n4; e += 32 * TC_WORKERS) {
-          // kind::tf32 ignores the low 13 mantissa bits of its operands (measured: matches a truncated
-          // reference to 2.6e-7, a rounded one only to 1e-3), so the landed tile IS hi; only lo is written.
-          const float4 x = hi[e];
-          float4 l;
-          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          lo[e] = l;
+          for (int e = ct; e < n4; e += 32 * TC_WORKERS) {
+            // kind::tf32 ignores the low 13 mantissa bits of its operands (measured: matches a truncated
+            // reference to 2.6e-7, a rounded one only to 1e-3), so the landed tile IS hi; only lo is written.
+            const float4 x = hi[e];
+            float4 l;
+            l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+            l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+            l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+            l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+            lo[e] = l;
+          }
         }
-        if (p.dbg_mma != 5) fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&conv[s]);
+        if (do_colsum) {
+          // thread ct owns (k-row ct/8, 16-byte chunk ct%8) of every 32-column box of the B tile
+          const float4* bt = hi + a_bytes / 16;
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (j * 32 < p.BN) {
+              const float4 v = bt[j * 256 + ct];
+              cs[j].x += v.x; cs[j].y += v.y; cs[j].z += v.z; cs[j].w += v.w;
+            }
+        }
+        if (p.passes == 3) {
+          if (p.dbg_mma != 5) fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&conv[s]);
+        } else {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);    // single pass: the stage is free once MMA *and* the sweep are done
+        }
         if (ct == 0 && i == 0) TC_STAMP(3);
       }
+    }
+    if (do_colsum) {
+      // Combine the per-thread partials.  The same lane of the 8 worker warps holds the same columns (k-rows
+      // q, q+4, ..), so first sum across warps through shared memory (the pipeline stages are idle once the
+      // accumulator is complete), then un-swizzle (Swizzle<2,5,2>: 32-byte chunk ^= k-row & 3) with a 4-way
+      // shared atomic, then one red.add per column per CTA.
+      mbar_wait(tmem_full, 0);
+      float4* red = reinterpret_cast<float4*>(smem);          // [box][warp][lane]
+      const int wq = warp - 2;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (j * 32 < p.BN) red[(j * TC_WORKERS + wq) * 32 + lane] = cs[j];
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_WORKERS) : "memory");
+      if (ct < p.BN) {
+        const int j = ct >> 5, ln = ct & 31;
+        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < TC_WORKERS; w++) {
+          const float4 v = red[(j * TC_WORKERS + w) * 32 + ln];
+          tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
+        }
+        const int q = ln >> 3, c16 = ln & 7;
+        const int colb = j * 32 + (((c16 >> 1) ^ q) << 3) + ((c16 & 1) << 2);
+        atomicAdd(&cs_s[colb + 0], tot.x);
+        atomicAdd(&cs_s[colb + 1], tot.y);
+        atomicAdd(&cs_s[colb + 2], tot.z);
+        atomicAdd(&cs_s[colb + 3], tot.w);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_WORKERS) : "memory");
+      if (ct < p.BN && n0 + ct < p.N) atomicAdd(p.ep.colsum + n0 + ct, cs_s[ct]);
     }
     if (ct == 0) TC_STAMP(4);
     // ---- epilogue: this warp owns TMEM lanes 32*(warp%4) .. +31  == output rows.
@@ -552,7 +606,7 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   if (passes == 1 && (long long)ceil_div(d.N, p.BN) * ceil_div(d.M, BM) * splits >= 2LL * g_sm_count && stages > 2) stages = 2;
   if (const char* e = getenv("NTB200_STAGES")) { int v = atoi(e); if (v >= 1 && v <= stages) stages = v; }
   p.stages = stages;
-  const size_t smem = stages * stage + (3 * stages + 2) * 8 + 1024;
+  const size_t smem = stages * stage + (3 * stages + 2) * 8 + 16 + 128 * 4 + 1024;
 
   CUtensorMap tmA, tmB;
   const bool use3d = getenv("NTB200_TMA_2D") == nullptr;
@@ -586,6 +640,7 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
 #undef NT_TC_CASE
   if (rc < 0) return 0;                   // epilogue combination without a tensor-core instance -> SIMT
   if (rc) return rc;
+  if (d.ep.colsum && d.colsum_done) *d.colsum_done = (b_mn != 0);
   *handled = true;
   return 0;
 }

@@ -1,5 +1,6 @@
 // Linear layer entry points (net/fullconnect.py) -> GEMM descriptors.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace nt {
 
@@ -102,9 +103,14 @@ int nt_linear_bwd_params(const float* x, const float* dy, float* dw, float* db, 
   int want = ceil_div(2 * g_sm_count, tiles);
   int maxsplit = ceil_div(M, 128);
   d.splitk = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
+  bool db_fused = false;
+  static int fuse_db = -1;
+  if (fuse_db < 0) { const char* e = getenv("NTB200_FUSE_DB"); fuse_db = e ? atoi(e) : 1; }
+  d.ep.colsum = fuse_db ? db : nullptr;
+  d.colsum_done = &db_fused;
   int rc = gemm_dispatch(d);
   if (rc) return rc;
-  if (db) {
+  if (db && !db_fused) {
     int rows_per_block = 256;
     dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_block));
     NT_CHECK(nt::launch_k(colsum_kernel, dim3(grid), dim3(dim3(32, 8)), 0, dy, db, M, N, rows_per_block));
