@@ -550,7 +550,9 @@ static int pick_bn(int M, int N, int splits_hint) {
     if (bn > 32 && bn >= 2 * N) continue;
     const int tiles = mt * ceil_div(N, bn);
     const long long waste = (long long)ceil_div(N, bn) * bn - N;          // padded columns
-    const int fill = tiles >= (g_sm_count * 3) / 4 ? g_sm_count : tiles;   // >= 3/4 wave counts as full
+    static int target = -1;
+    if (target < 0) { const char* e = getenv("NTB200_WAVE_SMS"); target = e ? atoi(e) : g_sm_count; }
+    const int fill = tiles >= (target * 3) / 4 ? target : tiles;   // >= 3/4 wave counts as full
     const long long score = (long long)fill * 1000000 - waste * 1000 + bn;
     if (score > best_score) { best_score = score; best = bn; }
   }
