@@ -123,9 +123,11 @@ int nt_scale(float* x, float alpha, size_t n);
 #define NT_MASK_DENSE 2
 int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S,
                      int B, int N, int H, int dh, const float* residual);
-/* dqkv[B,N,3*H*dh] from dout[B,N,H*dh]; scratch must hold B*H*N*N floats (dS). */
+/* dqkv[B,N,3*H*dh] from dout[B,N,H*dh]; scratch must hold B*H*N*N floats (dS) when N > 64.
+ * mask_kind is the forward's mask kind: NT_MASK_CAUSAL lets the kernels skip the upper-triangular
+ * blocks (P is exactly 0 there); any other value processes the full matrix. */
 int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch,
-                     int B, int N, int H, int dh);
+                     int B, int N, int H, int dh, int mask_kind);
 
 /* ---------------------------------------------------------------- embeds */
 /* PatchEmbed_flatten.forward patch loops, PatchEmbed.py:22-36: (B,C,Hi,Wi) -> (B, n_patch^2, C*h*w) */

@@ -664,6 +664,379 @@ __global__ void __launch_bounds__(128) attn_bwd_mma_kernel(const float* __restri
   }
 }
 
+static bool g_att_mma_long = true;          // NTB200_ATT_LONG=0 falls back to batched SIMT GEMMs
+// ---------------------------------------------------------------- mma.sync long-sequence kernels (GPT: T=256, dh=64)
+// Same fragment machinery, tiled 64 queries x 64 keys.  The reference keeps the full softmax matrix P
+// (atg__, gpt/attdecoderblock.py:64), so forward is two passes over the key chunks: pass 1 writes the scaled,
+// masked scores into P and tracks the running row max / sum, pass 2 re-reads them, normalises in place and
+// accumulates O = P V.  Backward is two kernels: per query block (dP -> row sums -> dS -> dQ, dS parked in the
+// caller's scratch) and per key block (dK = dS^T Q, dV = P^T dO).  Causal masks skip the upper-triangular blocks.
+constexpr int LQ = 64;
+template <int DH>
+__device__ __forceinline__ void load_rows_async(float* dst, int ld, const float* src, long long src_ld, int row0, int N,
+                                                int tid) {
+  // 64 rows x DH floats, rows >= N zero-filled
+  for (int e = tid; e < LQ * (DH / 4); e += 128) {
+    const int i = e / (DH / 4), d4 = (e % (DH / 4)) * 4;
+    if (row0 + i < N) cp_async16(dst + i * ld + d4, src + (long long)(row0 + i) * src_ld + d4);
+    else *reinterpret_cast<float4*>(dst + i * ld + d4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+// 64x64 tile of an [N][N] matrix (N % 4 == 0), origin (r0, c0), out-of-range entries zero-filled
+__device__ __forceinline__ void load_tile_async(float* dst, int ld, const float* src, int N, int r0, int c0, int tid) {
+  for (int e = tid; e < LQ * 16; e += 128) {
+    const int i = e >> 4, c4 = (e & 15) * 4;
+    if (r0 + i < N && c0 + c4 < N) cp_async16(dst + i * ld + c4, src + (long long)(r0 + i) * N + c0 + c4);
+    else *reinterpret_cast<float4*>(dst + i * ld + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128) attn_fwd_mma_long_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
+                                                                int mask_kind, float* __restrict__ out, float* P,
+                                                                float* __restrict__ S, int N, int H,
+                                                                const float* __restrict__ residual) {
+  pdl_prologue();
+  using C = AttMma<DH>;
+  extern __shared__ __align__(16) float sm[];
+  float* sQ = sm;                          // [64][LDA]
+  float* sK = sQ + 64 * C::LDA;            // [64][LDA]
+  float* sV = sK + 64 * C::LDA;            // [64][LDB]
+  float* sP = sV + 64 * C::LDB;            // [64][LDP]
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int q0 = blockIdx.x * LQ;
+  const int D = H * DH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const float* base = qkv + (long long)b * N * 3 * D + h * DH;
+  float* Pb = P + (long long)bh * N * N;
+  const int nchunks_all = (N + LQ - 1) / LQ;
+  // the optional score dump (att_col) is PRE-mask, so it needs every block even under a causal mask
+  const int nchunks = (mask_kind == NT_MASK_CAUSAL && S == nullptr) ? min(nchunks_all, (int)blockIdx.x + 1) : nchunks_all;
+  load_rows_async<DH>(sQ, C::LDA, base, 3 * D, q0, N, tid);
+  const int i0 = warp * 16;
+  const int r0 = q0 + i0 + g, r1 = r0 + 8;
+  const float scale = 1.0f / sqrtf((float)DH);
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  // ---------------- pass 1: scores -> P (raw), running max / sum
+  for (int kc = 0; kc < nchunks; kc++) {
+    __syncthreads();
+    load_rows_async<DH>(sK, C::LDA, base + D, 3 * D, kc * LQ, N, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < C::KD; ks++) {
+      float a[4];
+      uint32_t ah[4], al[4];
+      load_a(sQ, C::LDA, i0, ks * 8, g, t, a);
+      split_frag<4>(a, ah, al);
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) {
+        float bb[2];
+        uint32_t bh_[2], bl_[2];
+        load_b_nk(sK, C::LDA, nt * 8, ks * 8, g, t, bb);
+        split_frag<2>(bb, bh_, bl_);
+        mma3(acc[nt], ah, al, bh_, bl_);
+      }
+    }
+    float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int row = (c < 2) ? r0 : r1, col = kc * LQ + nt * 8 + 2 * t + (c & 1);
+        float v = acc[nt][c] * scale;                                          // attdecoderblock.py:57
+        if (col < N && row < N) {
+          if (S) S[(long long)bh * N * N + (long long)row * N + col] = v;       // att_col
+          if (mask_kind == NT_MASK_CAUSAL) { if (col > row) v = -INFINITY; }
+          else if (mask_kind == NT_MASK_DENSE) v += mask[(long long)row * N + col];
+          Pb[(long long)row * N + col] = v;                                     // parked for pass 2
+        } else {
+          v = -INFINITY;
+        }
+        acc[nt][c] = v;
+        if (c < 2) cm0 = fmaxf(cm0, v); else cm1 = fmaxf(cm1, v);
+      }
+    }
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+    const float n0_ = fmaxf(m0, cm0), n1_ = fmaxf(m1, cm1);
+    float s0 = 0.f, s1 = 0.f;
+    if (n0_ > -INFINITY) {
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) s0 += expf(acc[nt][0] - n0_) + expf(acc[nt][1] - n0_);
+    }
+    if (n1_ > -INFINITY) {
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) s1 += expf(acc[nt][2] - n1_) + expf(acc[nt][3] - n1_);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    l0 = (n0_ > -INFINITY ? l0 * expf(m0 - n0_) : 0.f) + s0;
+    l1 = (n1_ > -INFINITY ? l1 * expf(m1 - n1_) : 0.f) + s1;
+    m0 = n0_;
+    m1 = n1_;
+  }
+  const float inv0 = (r0 < N && l0 > 0.f) ? 1.0f / l0 : 0.f, inv1 = (r1 < N && l1 > 0.f) ? 1.0f / l1 : 0.f;
+  if (!(m0 > -INFINITY)) m0 = 0.f;
+  if (!(m1 > -INFINITY)) m1 = 0.f;
+  // ---------------- pass 2: normalise P in place, O = P V
+  float o[C::KD][4];
+#pragma unroll
+  for (int nd = 0; nd < C::KD; nd++) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+  for (int kc = 0; kc < nchunks; kc++) {
+    __syncthreads();
+    load_rows_async<DH>(sV, C::LDB, base + 2 * D, 3 * D, kc * LQ, N, tid);
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      const int col = kc * LQ + nt * 8 + 2 * t;
+      float p00 = 0.f, p01 = 0.f, p10 = 0.f, p11 = 0.f;
+      if (r0 < N) {
+        if (col < N) { p00 = expf(Pb[(long long)r0 * N + col] - m0) * inv0; Pb[(long long)r0 * N + col] = p00; }
+        if (col + 1 < N) { p01 = expf(Pb[(long long)r0 * N + col + 1] - m0) * inv0; Pb[(long long)r0 * N + col + 1] = p01; }
+      }
+      if (r1 < N) {
+        if (col < N) { p10 = expf(Pb[(long long)r1 * N + col] - m1) * inv1; Pb[(long long)r1 * N + col] = p10; }
+        if (col + 1 < N) { p11 = expf(Pb[(long long)r1 * N + col + 1] - m1) * inv1; Pb[(long long)r1 * N + col + 1] = p11; }
+      }
+      *reinterpret_cast<float2*>(sP + (i0 + g) * C::LDP + nt * 8 + 2 * t) = make_float2(p00, p01);
+      *reinterpret_cast<float2*>(sP + (i0 + g + 8) * C::LDP + nt * 8 + 2 * t) = make_float2(p10, p11);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int kt = 0; kt < 8; kt++) {
+      float a[4];
+      uint32_t ah[4], al[4];
+      load_a(sP, C::LDP, i0, kt * 8, g, t, a);
+      split_frag<4>(a, ah, al);
+#pragma unroll
+      for (int nd = 0; nd < C::KD; nd++) {
+        float bb[2];
+        uint32_t bh_[2], bl_[2];
+        load_b_kn(sV, C::LDB, kt * 8, nd * 8, g, t, bb);
+        split_frag<2>(bb, bh_, bl_);
+        mma3(o[nd], ah, al, bh_, bl_);
+      }
+    }
+  }
+  // causal: the skipped upper-triangular blocks of P are exactly zero
+  if (nchunks < nchunks_all) {
+    for (int e = tid; e < LQ * (nchunks_all - nchunks) * LQ; e += 128) {
+      const int i = e / ((nchunks_all - nchunks) * LQ), c = nchunks * LQ + e % ((nchunks_all - nchunks) * LQ);
+      if (q0 + i < N && c < N) Pb[(long long)(q0 + i) * N + c] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int nd = 0; nd < C::KD; nd++) {
+    const int col = h * DH + nd * 8 + 2 * t;
+    if (r0 < N) {
+      const long long oi = ((long long)b * N + r0) * D + col;
+      float2 v = make_float2(o[nd][0], o[nd][1]);
+      if (residual) { const float2 rr = __ldg(reinterpret_cast<const float2*>(residual + oi)); v.x += rr.x; v.y += rr.y; }
+      *reinterpret_cast<float2*>(out + oi) = v;
+    }
+    if (r1 < N) {
+      const long long oi = ((long long)b * N + r1) * D + col;
+      float2 v = make_float2(o[nd][2], o[nd][3]);
+      if (residual) { const float2 rr = __ldg(reinterpret_cast<const float2*>(residual + oi)); v.x += rr.x; v.y += rr.y; }
+      *reinterpret_cast<float2*>(out + oi) = v;
+    }
+  }
+}
+
+// backward, per query block: dS (parked in `scratch`) and dQ
+template <int DH>
+__global__ void __launch_bounds__(128) attn_bwd_mma_long_q_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
+                                                                  const float* __restrict__ P, float* __restrict__ dqkv,
+                                                                  float* scratch, int N, int H, int causal) {
+  pdl_prologue();
+  using C = AttMma<DH>;
+  extern __shared__ __align__(16) float sm[];
+  float* sdO = sm;                         // [64][LDA]  A in dP
+  float* sV = sdO + 64 * C::LDA;           // [64][LDA]  B(k=d, n=j) = V[j][d]
+  float* sK = sV + 64 * C::LDA;            // [64][LDB]  B(k=j, n=d) = K[j][d]
+  float* sdS = sK + 64 * C::LDB;           // [64][LDP]
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int q0 = blockIdx.x * LQ;
+  const int D = H * DH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const float* base = qkv + (long long)b * N * 3 * D + h * DH;
+  const float* Pb = P + (long long)bh * N * N;
+  float* Sb = scratch + (long long)bh * N * N;
+  const int nchunks_all = (N + LQ - 1) / LQ;
+  const int nchunks = causal ? min(nchunks_all, (int)blockIdx.x + 1) : nchunks_all;
+  load_rows_async<DH>(sdO, C::LDA, dout + (long long)b * N * D + h * DH, D, q0, N, tid);
+  const int i0 = warp * 16;
+  const int r0 = q0 + i0 + g, r1 = r0 + 8;
+  float d0 = 0.f, d1 = 0.f;                // rowsum(dP o P)
+  for (int kc = 0; kc < nchunks; kc++) {
+    __syncthreads();
+    load_rows_async<DH>(sV, C::LDA, base + 2 * D, 3 * D, kc * LQ, N, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < C::KD; ks++) {
+      float a[4];
+      uint32_t ah[4], al[4];
+      load_a(sdO, C::LDA, i0, ks * 8, g, t, a);
+      split_frag<4>(a, ah, al);
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) {
+        float bb[2];
+        uint32_t bh_[2], bl_[2];
+        load_b_nk(sV, C::LDA, nt * 8, ks * 8, g, t, bb);
+        split_frag<2>(bb, bh_, bl_);
+        mma3(acc[nt], ah, al, bh_, bl_);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      const int col = kc * LQ + nt * 8 + 2 * t;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int row = (c < 2) ? r0 : r1, cc = col + (c & 1);
+        if (row < N && cc < N) {
+          const long long idx = (long long)row * N + cc;
+          Sb[idx] = acc[nt][c];                                    // dP parked for pass 2
+          const float pv = Pb[idx];
+          if (c < 2) d0 = fmaf(acc[nt][c], pv, d0); else d1 = fmaf(acc[nt][c], pv, d1);
+        }
+      }
+    }
+  }
+  d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+  d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+  float o[C::KD][4];
+#pragma unroll
+  for (int nd = 0; nd < C::KD; nd++) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+  for (int kc = 0; kc < nchunks; kc++) {
+    __syncthreads();
+    load_rows_async<DH>(sK, C::LDB, base + D, 3 * D, kc * LQ, N, tid);
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      const int col = kc * LQ + nt * 8 + 2 * t;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int row = (c < 2) ? r0 : r1, cc = col + (c & 1);
+        if (row < N && cc < N) {
+          const long long idx = (long long)row * N + cc;
+          v[c] = Pb[idx] * (Sb[idx] - ((c < 2) ? d0 : d1));         // dS = P o (dP - rowsum)
+          Sb[idx] = v[c];
+        }
+      }
+      *reinterpret_cast<float2*>(sdS + (i0 + g) * C::LDP + nt * 8 + 2 * t) = make_float2(v[0], v[1]);
+      *reinterpret_cast<float2*>(sdS + (i0 + g + 8) * C::LDP + nt * 8 + 2 * t) = make_float2(v[2], v[3]);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int kt = 0; kt < 8; kt++) {
+      float a[4];
+      uint32_t ah[4], al[4];
+      load_a(sdS, C::LDP, i0, kt * 8, g, t, a);
+      split_frag<4>(a, ah, al);
+#pragma unroll
+      for (int nd = 0; nd < C::KD; nd++) {
+        float bb[2];
+        uint32_t bh_[2], bl_[2];
+        load_b_kn(sK, C::LDB, kt * 8, nd * 8, g, t, bb);
+        split_frag<2>(bb, bh_, bl_);
+        mma3(o[nd], ah, al, bh_, bl_);
+      }
+    }
+  }
+  const float scale = 1.0f / sqrtf((float)DH);
+  float* obase = dqkv + (long long)b * N * 3 * D + h * DH;
+#pragma unroll
+  for (int nd = 0; nd < C::KD; nd++) {
+    const int col = nd * 8 + 2 * t;
+    if (r0 < N) *reinterpret_cast<float2*>(obase + (long long)r0 * 3 * D + col) = make_float2(o[nd][0] * scale, o[nd][1] * scale);
+    if (r1 < N) *reinterpret_cast<float2*>(obase + (long long)r1 * 3 * D + col) = make_float2(o[nd][2] * scale, o[nd][3] * scale);
+  }
+}
+
+// backward, per key block: dK = dS^T Q / sqrt(dh), dV = P^T dO
+template <int DH>
+__global__ void __launch_bounds__(128) attn_bwd_mma_long_k_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
+                                                                  const float* __restrict__ P, float* __restrict__ dqkv,
+                                                                  const float* __restrict__ scratch, int N, int H, int causal) {
+  pdl_prologue();
+  using C = AttMma<DH>;
+  extern __shared__ __align__(16) float sm[];
+  float* sQ = sm;                          // [64][LDB]  B(k=i, n=d)
+  float* sdO = sQ + 64 * C::LDB;           // [64][LDB]  B(k=i, n=d)
+  float* sP = sdO + 64 * C::LDB;           // [64 q][LDP]  read transposed
+  float* sdS = sP + 64 * C::LDP;           // [64 q][LDP]
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int k0 = blockIdx.x * LQ;
+  const int D = H * DH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const float* base = qkv + (long long)b * N * 3 * D + h * DH;
+  const float* Pb = P + (long long)bh * N * N;
+  const float* Sb = scratch + (long long)bh * N * N;
+  const int nchunks_all = (N + LQ - 1) / LQ;
+  const int qc_begin = causal ? blockIdx.x : 0;
+  const int j0 = warp * 16;
+  float ok[C::KD][4], ov[C::KD][4];
+#pragma unroll
+  for (int nd = 0; nd < C::KD; nd++) {
+    ok[nd][0] = ok[nd][1] = ok[nd][2] = ok[nd][3] = 0.f;
+    ov[nd][0] = ov[nd][1] = ov[nd][2] = ov[nd][3] = 0.f;
+  }
+  for (int qc = qc_begin; qc < nchunks_all; qc++) {
+    __syncthreads();
+    load_rows_async<DH>(sQ, C::LDB, base, 3 * D, qc * LQ, N, tid);
+    load_rows_async<DH>(sdO, C::LDB, dout + (long long)b * N * D + h * DH, D, qc * LQ, N, tid);
+    load_tile_async(sP, C::LDP, Pb, N, qc * LQ, k0, tid);
+    load_tile_async(sdS, C::LDP, Sb, N, qc * LQ, k0, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    for (int kt = 0; kt < 8; kt++) {       // contraction over the 64 query rows of this chunk
+      float a[4];
+      uint32_t sh[4], sl[4], ph[4], pl[4];
+      load_at(sdS, C::LDP, j0, kt * 8, g, t, a);
+      split_frag<4>(a, sh, sl);
+      load_at(sP, C::LDP, j0, kt * 8, g, t, a);
+      split_frag<4>(a, ph, pl);
+#pragma unroll
+      for (int nd = 0; nd < C::KD; nd++) {
+        float bb[2];
+        uint32_t bh_[2], bl_[2];
+        load_b_kn(sQ, C::LDB, kt * 8, nd * 8, g, t, bb);
+        split_frag<2>(bb, bh_, bl_);
+        mma3(ok[nd], sh, sl, bh_, bl_);
+        load_b_kn(sdO, C::LDB, kt * 8, nd * 8, g, t, bb);
+        split_frag<2>(bb, bh_, bl_);
+        mma3(ov[nd], ph, pl, bh_, bl_);
+      }
+    }
+  }
+  const float scale = 1.0f / sqrtf((float)DH);
+  float* obase = dqkv + (long long)b * N * 3 * D + h * DH;
+  const int kr0 = k0 + j0 + g, kr1 = kr0 + 8;
+#pragma unroll
+  for (int nd = 0; nd < C::KD; nd++) {
+    const int col = nd * 8 + 2 * t;
+    if (kr0 < N) {
+      float* o = obase + (long long)kr0 * 3 * D + col;
+      *reinterpret_cast<float2*>(o + D) = make_float2(ok[nd][0] * scale, ok[nd][1] * scale);
+      *reinterpret_cast<float2*>(o + 2 * D) = make_float2(ov[nd][0], ov[nd][1]);
+    }
+    if (kr1 < N) {
+      float* o = obase + (long long)kr1 * 3 * D + col;
+      *reinterpret_cast<float2*>(o + D) = make_float2(ok[nd][2] * scale, ok[nd][3] * scale);
+      *reinterpret_cast<float2*>(o + 2 * D) = make_float2(ov[nd][2], ov[nd][3]);
+    }
+  }
+}
+
+static bool long_ok(int N, int dh) { return g_att_mma_long && N > 64 && dh == 64 && (N % 4) == 0; }
+
 template <int DH>
 static size_t fwd_mma_smem() { using C = AttMma<DH>; return sizeof(float) * (64 * C::LDA * 2 + 64 * C::LDB + 64 * C::LDP); }
 template <int DH>
@@ -743,6 +1116,16 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
     NT_LAUNCH_OK();
     return 0;
   }
+  if (const char* e = getenv("NTB200_ATT_LONG")) g_att_mma_long = (e[0] != '0');
+  if (long_ok(N, dh)) {
+    using C = AttMma<64>;
+    const size_t smem = sizeof(float) * (64 * C::LDA * 2 + 64 * C::LDB + 64 * C::LDP);
+    static bool cfg = false;
+    if (!cfg) { NT_CHECK(cudaFuncSetAttribute(attn_fwd_mma_long_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+    NT_CHECK(nt::launch_k(attn_fwd_mma_long_kernel<64>, dim3(ceil_div(N, LQ), B * H), dim3(128), smem, qkv, mask, mask_kind, out, P, S, N, H, residual));
+    NT_LAUNCH_OK();
+    return 0;
+  }
   // general path: S = scale * Q K^T (batched over (b,h)) -> masked softmax -> O = P V
   GemmDesc g{};
   g.A = qkv; g.B = qkv + D; g.C = S ? S : P;
@@ -769,7 +1152,7 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
 }
 
 int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch, int B, int N,
-                     int H, int dh) {
+                     int H, int dh, int mask_kind) {
   NT_ENTRY();
   NT_REQUIRE(B >= 0 && N > 0 && H > 0 && dh > 0, "nt_attention_bwd: bad shape");
   if (B == 0) return 0;
@@ -809,6 +1192,23 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
     return 0;
   }
   NT_REQUIRE(scratch, "nt_attention_bwd: general path needs a B*H*N*N scratch buffer");
+  if (long_ok(N, dh)) {
+    using C = AttMma<64>;
+    const int causal = (mask_kind == NT_MASK_CAUSAL) ? 1 : 0;
+    const size_t smem_q = sizeof(float) * (64 * C::LDA * 2 + 64 * C::LDB + 64 * C::LDP);
+    const size_t smem_k = sizeof(float) * (64 * C::LDB * 2 + 64 * C::LDP * 2);
+    static bool cfg = false;
+    if (!cfg) {
+      NT_CHECK(cudaFuncSetAttribute(attn_bwd_mma_long_q_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+      NT_CHECK(cudaFuncSetAttribute(attn_bwd_mma_long_k_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
+      cfg = true;
+    }
+    NT_CHECK(nt::launch_k(attn_bwd_mma_long_q_kernel<64>, dim3(ceil_div(N, LQ), B * H), dim3(128), smem_q, dout, qkv, P, dqkv, scratch, N, H, causal));
+    NT_LAUNCH_OK();
+    NT_CHECK(nt::launch_k(attn_bwd_mma_long_k_kernel<64>, dim3(ceil_div(N, LQ), B * H), dim3(128), smem_k, dout, qkv, P, dqkv, (const float*)scratch, N, H, causal));
+    NT_LAUNCH_OK();
+    return 0;
+  }
   const long long bhs = (long long)N * N;
   const float scale = 1.0f / sqrtf((float)dh);
   // dP = dO V^T

@@ -30,6 +30,7 @@ class attention_layer():
         x = as_device(inputs)
         self.batch, self.block, _ = x.shape
         kind, dmask = ops.detect_mask(masks, self.block)
+        self._mask_kind = kind
         self.out = self.norm._forward(x)
         self.qkv = self.qkvfc._forward(self.out)                       # (B,N,3D): [q,k,v][head][dh]
         input1, self.P, _ = ops.attention_fwd(self.qkv, self.num_h, dmask, kind, residual=x)
@@ -42,7 +43,7 @@ class attention_layer():
         d = self.fc1._backward(delta, self.out2, ops.ACT_GELU, self.pre2)   # fc1.backward + gelu.backward
         d = self.fc0._backward(d, self.out1)
         delta0 = self.norm1._backward(d, addend=delta)                 # delta0 += delta (attention.py:62)
-        self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h)
+        self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h, self._mask_kind)
         d = self.qkvfc._backward(self.delta_qkv, self.out)
         return self.norm._backward(d, addend=delta0)                   # input_delta += delta0 (attention.py:88)
 

@@ -34,6 +34,7 @@ class attdecoderblock_layer():
         self.masks = masks
         self.batch, self.block, _ = x.shape
         kind, dmask = ops.detect_mask(masks, self.block)
+        self._mask_kind = kind
         self.out0 = self.norm._forward(x)
         self.out2, self.pre2 = self.fc0._forward(self.out0, ops.ACT_RELU, want_pre=True)
         self.out6 = self.fc1._forward(self.out2, residual=x)
@@ -49,7 +50,7 @@ class attdecoderblock_layer():
     def backward(self, delta):
         delta = as_device(delta, self.norm.host_dtype)
         delta0 = self.fc_out._backward(delta, self.rkk)
-        self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h)
+        self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h, self._mask_kind)
         d = self.qkvfc._backward(self.delta_qkv, self.outnorm)
         qkvdelta = self.norm1._backward(d, addend=delta)               # + delta (attdecoderblock.py:105)
         d = self.fc1._backward(qkvdelta, self.out2, ops.ACT_RELU, self.pre2)   # fc1.backward + relu.backward

@@ -66,13 +66,13 @@ def attention_fwd(qkv, H, mask=None, mask_kind=MASK_NONE, residual=None, want_sc
     return out, P, S
 
 
-def attention_bwd(dout, qkv, P, H):
+def attention_bwd(dout, qkv, P, H, mask_kind=MASK_NONE):
     B, N, three_d = qkv.shape
     D = three_d // 3
     dh = D // H
     dqkv = qkv.empty_like()
     scratch = None if (N <= 64 and dh <= 64 and dh % 4 == 0) else P.empty_like()
-    lib.nt_attention_bwd(dout.ptr, qkv.ptr, P.ptr, dqkv.ptr, ptr_or_null(scratch), B, N, H, dh)
+    lib.nt_attention_bwd(dout.ptr, qkv.ptr, P.ptr, dqkv.ptr, ptr_or_null(scratch), B, N, H, dh, int(mask_kind))
     return dqkv
 
 

@@ -181,6 +181,31 @@ def test_trainstep_gpt_adam_matches_oracle(nt):
     assert layers[1].fc0.t == 5
 
 
+def test_trainstep_gpt_long_context_matches_oracle(nt):
+    """T = 128 > 64 routes attention through the tiled mma.sync kernels (two-pass forward, q-/k-block backward,
+    causal block skipping); SGD so the parameter comparison is not clouded by Adam*'s noise amplification.
+    The Linear layers run on the exact-fp32 engine here: with 131k ReLU pre-activations per block a 3e-6 absolute
+    GEMM error flips the sign of ~0.5 of them per step (measured: one flip = 2e-2 of a weight-gradient tensor), a
+    discontinuity of ReLU rather than an error of either implementation, and this test is about attention."""
+    from numpy_transformer_b200 import trainer
+    nt.set_gemm_mode(0)
+    cfg = M.GPTConfig(batch=2, context=128, embed_dim=128, heads=2, blocks=2, vocab=50)
+    params = M.gpt_init(cfg, 0)
+    tokens, labels = M.synthetic_gpt_batch(cfg, 1)
+    layers = trainer.build_gpt_layers(2, 128, 128, 2, 2, 50, adam=False, seed=0)
+    ts = trainer.TrainStep(layers, "gpt", tokens.shape, lr=0.05, adam=False)
+    for step in range(3):
+        ref = M.gpt_step(params, None, tokens, labels, 0.05, cfg, adam=False)
+        loss, amax = ts.step(tokens, labels, want_argmax=True)
+        assert abs(loss - ref["loss"]) < TOL * abs(ref["loss"]), step
+        assert np.mean(amax == ref["argmax"]) > 0.995
+        params = ref["params"]
+        mine = trainer.save_walk(layers)
+        mine[0] = [[np.asarray(layers[0].text_embedding.params)], [np.asarray(layers[0].pos_embedding.params)]]
+        _leaves_close(mine, params, TOL, "step %d" % step)
+    nt.set_gemm_mode(1)
+
+
 def test_vit_readme_trajectory_vs_reference(nt):
     """Full README-size ViT (B=100, D=96, 6x4 heads): two steps against numbers produced by the
     unmodified reference (tests/golden/vit_readme_traj.npz)."""

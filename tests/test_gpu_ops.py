@@ -221,7 +221,9 @@ def test_gpt_block_golden_neg_inf_mask(nt, prims):
 
 
 @pytest.mark.parametrize("B,N,H,dh,causal", [(2, 49, 4, 24, False), (3, 49, 6, 64, False), (2, 5, 3, 64, True),
-                                             (2, 256, 2, 64, True), (1, 100, 2, 32, False), (1, 64, 1, 64, True)])
+                                             (2, 256, 2, 64, True), (1, 100, 2, 32, False), (1, 64, 1, 64, True),
+                                             (1, 128, 2, 64, False), (2, 192, 3, 64, True), (1, 68, 1, 64, True),
+                                             (1, 50, 2, 24, True), (1, 70, 1, 64, False), (1, 33, 2, 16, False)])
 def test_attention_core_vs_oracle(nt, B, N, H, dh, causal):
     from numpy_transformer_b200 import ops, DeviceArray
     rs = np.random.RandomState(N + dh)
@@ -233,7 +235,7 @@ def test_attention_core_vs_oracle(nt, B, N, H, dh, causal):
     dq = DeviceArray.from_host(qkv)
     out, dP, dS = ops.attention_fwd(dq, H, None, ops.MASK_CAUSAL if causal else ops.MASK_NONE, want_scores=True)
     assert rel_err(out, O) < TOL and rel_err(dP, P) < TOL and rel_err(dS, S) < TOL
-    dqkv = ops.attention_bwd(DeviceArray.from_host(dout), dq, dP, H)
+    dqkv = ops.attention_bwd(DeviceArray.from_host(dout), dq, dP, H, ops.MASK_CAUSAL if causal else ops.MASK_NONE)
     assert rel_err(dqkv, R.attention_bwd(dout, qkv, P, H)) < TOL
     if causal:
         out2, P2, _ = ops.attention_fwd(dq, H, DeviceArray.from_host(M.causal_mask(N, -1e6)), ops.MASK_DENSE)
