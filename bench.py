@@ -102,7 +102,7 @@ def op_cost(name, a, kind, c):
         B, N, H, dh = a[-4:]
         return 4.0 * B * H * N * N * dh, 4.0 * (4 * B * N * H * dh + B * H * N * N)
     if name == "nt_attention_bwd":
-        B, N, H, dh = a[-4:]
+        B, N, H, dh = a[-5:-1]                  # trailing int is the mask kind
         return 8.0 * B * H * N * N * dh, 4.0 * (7 * B * N * H * dh + B * H * N * N)
     if name == "nt_layernorm_fwd":
         M, D = a[0], a[1]

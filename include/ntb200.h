@@ -53,6 +53,7 @@ int nt_graph_end(void** graph_exec, int* n_kernel_nodes);
 int nt_graph_launch(void* graph_exec);
 /* Fork/join of a side branch inside a captured step (no-ops outside capture): ops enqueued between
  * begin/end run concurrently with the main chain; join before anything consumes their results. */
+int nt_set_side_branch(int enabled);      /* 0: capture everything on the main stream (clean per-op timing) */
 int nt_side_begin(void);
 int nt_side_end(void);
 int nt_side_join(void);

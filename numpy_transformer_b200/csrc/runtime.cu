@@ -30,6 +30,7 @@ static cudaStream_t g_chain_stream[kMaxChains] = {};
 static cudaEvent_t g_chain_done[kMaxChains] = {};
 static bool g_chain_dirty[kMaxChains] = {};
 static int g_chain_active = -1;
+static bool g_side_enabled = true;
 static const size_t kFlushBytes = 256ull << 20;
 struct GraphRec { cudaGraphExec_t exec; cudaGraph_t graph; int kernels; };
 
@@ -250,9 +251,10 @@ int nt_graph_destroy(void* graph_exec) {
 // on the backward critical path consumes).  nt_side_join makes the main stream wait for all of it.  Outside
 // capture the calls are no-ops: the pooled allocator's reuse rule assumes a single stream, and only a
 // captured step pins every buffer for the lifetime of the graph.
+int nt_set_side_branch(int enabled) { g_side_enabled = (enabled != 0); return 0; }
 int nt_side_begin(void) {
   NT_ENTRY();
-  if (!g_capturing || g_side_active || g_chain_active >= 0) return 0;
+  if (!g_capturing || !g_side_enabled || g_side_active || g_chain_active >= 0) return 0;
   NT_CHECK(cudaEventRecord(g_ev_fork, g_main_stream));
   NT_CHECK(cudaStreamWaitEvent(g_side_stream, g_ev_fork, 0));
   g_stream = g_side_stream;

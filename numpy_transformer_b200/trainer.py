@@ -264,6 +264,7 @@ class TrainStep:
         (graph, records); after `lib.nt_graph_launch(graph)` + sync, `lib.profile_read(records)` yields the
         per-op device durations of that replay.  Every replay is a real training step."""
         lib.nt_sync()
+        lib.nt_set_side_branch(0)               # serial capture: per-op times free of side-branch interference
         with keep_allocations() as keep:
             lib.profile_begin(external=True)
             lib.nt_graph_begin()
@@ -274,6 +275,7 @@ class TrainStep:
                 g = ctypes.c_void_p()
                 nk = ctypes.c_int(0)
                 lib.nt_graph_end(ctypes.byref(g), ctypes.byref(nk))
+        lib.nt_set_side_branch(1)
         self._prof_buffers = keep.buffers
         return g, recs
 
