@@ -130,6 +130,38 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
 int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch,
                      int B, int N, int H, int dh, int mask_kind);
 
+/* ---------------------------------------------------------------- fused ViT encoder blocks
+ * attention_layer.forward / backward (attention.py:20-55, 57-89) for a whole stack of blocks in ONE launch
+ * each way: one CTA per image walks every block (LN -> qkv -> attention -> +res -> LN1 -> fc0 -> GELU ->
+ * fc1 -> +res, and the hand-derived adjoint in reverse).  Only the launch-bound shapes are supported
+ * (N <= 64 tokens, (D,H) in {(96,4),(96,6),(64,4),(64,2),(32,2)}, no mask); contractions are BF16x3
+ * error-compensated mma (fp32-class accuracy).  All members are DEVICE pointers; the array itself is HOST memory
+ * and is copied into the kernel arguments (<= 16 blocks per call). */
+typedef struct NtVitBlock {
+  const float *ln_g, *ln_b;        /* norm:  gamma, beta [D]                      attention.py:12 */
+  const float *wqkv, *bqkv;        /* qkvfc: [D,3D], [3D], columns [q,k,v][head][dh]  :14,:24 */
+  const float *ln1_g, *ln1_b;      /* norm1                                       :13 */
+  const float *w0, *b0;            /* fc0: [D,2D], [2D]                           :15 */
+  const float *w1, *b1;            /* fc1: [2D,D], [D]                            :16 */
+  float *d_ln_g, *d_ln_b, *d_wqkv, *d_bqkv, *d_ln1_g, *d_ln1_b, *d_w0, *d_b0, *d_w1, *d_b1;  /* accumulate (+=) */
+  float *qkv;                      /* [B,N,3D]   kept for backward                :23 */
+  float *P;                        /* [B,H,N,N]  softmax, the reference's atg__   :41 */
+  float *h;                        /* [B,N,D]    input1 = x + attention           :46 */
+  float *pre2;                     /* [B,N,2D]   fc0 output before GELU           :49 */
+  float *out;                      /* [B,N,D]    block output                     :53 */
+  void *wfrag;                     /* scratch, nt_vit_blocks_wfrag_bytes(D): forward fills it with the
+                                      bf16 hi/lo mma-fragment-ordered copies of the three weight matrices,
+                                      backward of the same step re-uses it */
+} NtVitBlock;
+int nt_vit_blocks_supported(int N, int D, int H, int* ok);
+int nt_vit_blocks_wfrag_bytes(int D, size_t* bytes);
+/* x [B,N,D] is the input of blocks[0]; blocks[i].out feeds blocks[i+1]. */
+int nt_vit_blocks_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H);
+/* dout [B,N,D] = gradient w.r.t. blocks[nblocks-1].out; dx [B,N,D] receives the gradient w.r.t. x;
+ * scratch holds 2*B*N*D floats.  Parameter gradients accumulate into the d_* members. */
+int nt_vit_blocks_bwd(const NtVitBlock* blocks, int nblocks, const float* x, const float* dout, float* dx,
+                      float* scratch, int B, int N, int D, int H);
+
 /* ---------------------------------------------------------------- embeds */
 /* PatchEmbed_flatten.forward patch loops, PatchEmbed.py:22-36: (B,C,Hi,Wi) -> (B, n_patch^2, C*h*w) */
 int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, int n_patch);

@@ -1,0 +1,997 @@
+// Fused ViT encoder blocks (attention.py:20-89) for the launch-bound shapes (N <= 64 tokens, D in {32,64,96}).
+//
+// One CTA per image walks ALL blocks of the stack: the residual stream of an image never depends on another
+// image, so the forward of a whole stack (and its backward) is a single launch instead of ~9 launches per
+// block.  Inside a CTA (8 warps):
+//   * every contraction is mma.sync.m16n8k16 BF16 with fp32 accumulation, error-compensated: each fp32 operand
+//     is split x = hi + lo (two bf16) and a product is lo*hi + hi*lo + hi*hi (fp32-class accuracy, ~1e-5
+//     relative; tools/mma_red_bench.cu measures the legacy tensor path at 0.92 mma/ns/SM for both TF32 k8 and
+//     BF16 k16, so the BF16 split does the same work in half the instructions of a TF32 split);
+//   * activations that feed an MMA live in shared memory already split (hi/lo bf16, row pitch = 16 mod 128 bytes
+//     so every ldmatrix phase is conflict-free); fragments come from ldmatrix(.trans), never scalar LDS;
+//   * weights are pre-split once per step into mma-B-fragment order (vit_wsplit_kernel) so a lane fetches the
+//     hi and lo fragments of one (k16, n8) tile with ONE coalesced 16-byte load, straight into registers;
+//   * fp32 tensors that feed row-wise math (residual stream, LayerNorm inputs) go through global memory (L2/L1
+//     resident, written and re-read by the same CTA) — they are the tensors the backward needs anyway;
+//   * weight gradients are contracted over the image's tokens in the CTA and accumulated with red.global.add.v2
+//     (the reference's `+=` into *_delta until setzero).
+// Tokens are padded to 64 rows (4 m16 tiles); padded rows are kept exactly zero in every shared operand.
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace nt {
+namespace vb {
+
+constexpr int MAXB = 16;      // blocks per launch (kernel parameter space)
+constexpr int ROWS = 64;      // padded tokens
+constexpr int LDP = 72;       // pitch (elements) of the [64][64] score tiles
+
+struct Args {
+  NtVitBlock blk[MAXB];
+  int nblocks;
+  int N;
+  const float* x;       // [B,N,D] input of block 0
+  const float* dout;    // [B,N,D] gradient w.r.t. the last block's output      (backward)
+  float* dx;            // [B,N,D] gradient w.r.t. x                              (backward)
+  float* dh;            // [B,N,D] scratch: gradient w.r.t. h                     (backward)
+  float* tmp;           // [B,N,D] scratch: LayerNorm-backward input              (backward)
+};
+
+// ---------------------------------------------------------------- primitives
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ void split1(float a, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(a);
+  lo = __float2bfloat16_rn(a - __bfloat162float(hi));
+}
+
+// a [64][ld] bf16 operand array stored as two planes (hi, then lo)
+struct SArr {
+  char* ptr;        // generic pointer to the hi plane
+  uint32_t addr;    // shared-window address of the hi plane
+  uint32_t ldb;     // row pitch in bytes
+  uint32_t lo;      // byte offset hi -> lo plane
+};
+__device__ __forceinline__ SArr make_arr(char* p, int ld_elems, int rows = ROWS) {
+  SArr a;
+  a.ptr = p;
+  a.addr = (uint32_t)__cvta_generic_to_shared(p);
+  a.ldb = ld_elems * 2;
+  a.lo = rows * ld_elems * 2;
+  return a;
+}
+__device__ __forceinline__ void st2(const SArr& a, int row, int col, float v0, float v1) {
+  uint32_t hi, lo;
+  split2(v0, v1, hi, lo);
+  char* p = a.ptr + row * a.ldb + col * 2;
+  *reinterpret_cast<uint32_t*>(p) = hi;
+  *reinterpret_cast<uint32_t*>(p + a.lo) = lo;
+}
+__device__ __forceinline__ void st1(const SArr& a, int row, int col, float v) {
+  __nv_bfloat16 hi, lo;
+  split1(v, hi, lo);
+  char* p = a.ptr + row * a.ldb + col * 2;
+  *reinterpret_cast<__nv_bfloat16*>(p) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(p + a.lo) = lo;
+}
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm2t(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0));
+}
+// error-compensated product: small terms first
+__device__ __forceinline__ void mma16x3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                        uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma16(d, al, bh0, bh1);
+  mma16(d, ah, bl0, bl1);
+  mma16(d, ah, bh0, bh1);
+}
+__device__ __forceinline__ void mma8x3(float (&d)[4], const uint32_t (&ah)[2], const uint32_t (&al)[2], uint32_t bh,
+                                       uint32_t bl) {
+  mma8(d, al[0], al[1], bh);
+  mma8(d, ah[0], ah[1], bl);
+  mma8(d, ah[0], ah[1], bh);
+}
+__device__ __forceinline__ void red2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+template <int MT, int NT>
+__device__ __forceinline__ void zero_acc(float (&acc)[MT][NT][4]) {
+#pragma unroll
+  for (int m = 0; m < MT; m++)
+#pragma unroll
+    for (int n = 0; n < NT; n++) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+}
+
+// acc[mt][nt] += A(rows, k) * W, A row-major in shared memory (hi/lo planes), W as pre-split B fragments in
+// global memory ([k16 step][n8 tile][lane] uint4 = {b0.hi, b1.hi, b0.lo, b1.lo}), next k-step prefetched.
+// a_addr(ks): shared address (hi plane) of this lane's ldmatrix row for m-tile 0 at k-step ks.
+template <int MT, int NTW, class AF>
+__device__ __forceinline__ void gemm_wf(float (&acc)[MT][NTW][4], AF a_addr, uint32_t a_lo, uint32_t a_mt_stride,
+                                        int ksteps, const uint4* __restrict__ wf, int ks_stride) {
+  uint4 bc[NTW], bn[NTW];
+#pragma unroll
+  for (int nt = 0; nt < NTW; nt++) bc[nt] = __ldg(wf + nt * 32);
+  for (int ks = 0; ks < ksteps; ks++) {
+    if (ks + 1 < ksteps) {
+#pragma unroll
+      for (int nt = 0; nt < NTW; nt++) bn[nt] = __ldg(wf + (size_t)(ks + 1) * ks_stride + nt * 32);
+    }
+    uint32_t ah[MT][4], al[MT][4];
+    const uint32_t a0 = a_addr(ks);
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      ldsm4(ah[mt], a0 + mt * a_mt_stride);
+      ldsm4(al[mt], a0 + mt * a_mt_stride + a_lo);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) mma16x3(acc[mt][nt], ah[mt], al[mt], bc[nt].x, bc[nt].y, bc[nt].z, bc[nt].w);
+    if (ks + 1 < ksteps) {
+#pragma unroll
+      for (int nt = 0; nt < NTW; nt++) bc[nt] = bn[nt];
+    }
+  }
+}
+
+// acc[mt][nt] += A^T B with both operands stored [k][*] in shared memory (contraction over the row index = tokens):
+// A(m, k) = SA[k][m0 + m], B(k, n) = SB[k][n0 + n]; fragments via ldmatrix.trans.
+template <int MT, int NTW>
+__device__ __forceinline__ void gemm_tt(float (&acc)[MT][NTW][4], const SArr& A, int m0, const SArr& B, int n0,
+                                        int ksteps, int lane) {
+  const uint32_t a_lane = A.addr + ((lane & 7) + ((lane >> 4) & 1) * 8) * A.ldb + (m0 + ((lane >> 3) & 1) * 8) * 2;
+  const uint32_t b_lane = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + (n0 + (lane >> 4) * 8) * 2;
+  const uint32_t b_lane2 = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + n0 * 2;
+  for (int ks = 0; ks < ksteps; ks++) {
+    uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      ldsm4t(ah[mt], a_lane + ks * 16 * A.ldb + mt * 32);
+      ldsm4t(al[mt], a_lane + ks * 16 * A.ldb + mt * 32 + A.lo);
+    }
+#pragma unroll
+    for (int nt = 0; nt + 1 < NTW; nt += 2) {
+      uint32_t bh[4], bl[4];
+      ldsm4t(bh, b_lane + ks * 16 * B.ldb + nt * 16);
+      ldsm4t(bl, b_lane + ks * 16 * B.ldb + nt * 16 + B.lo);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) {
+        mma16x3(acc[mt][nt], ah[mt], al[mt], bh[0], bh[1], bl[0], bl[1]);
+        mma16x3(acc[mt][nt + 1], ah[mt], al[mt], bh[2], bh[3], bl[2], bl[3]);
+      }
+    }
+    if (NTW & 1) {
+      constexpr int nt = NTW - 1;
+      uint32_t bh[2], bl[2];
+      ldsm2t(bh, b_lane2 + ks * 16 * B.ldb + nt * 16);
+      ldsm2t(bl, b_lane2 + ks * 16 * B.ldb + nt * 16 + B.lo);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) mma16x3(acc[mt][nt], ah[mt], al[mt], bh[0], bh[1], bl[0], bl[1]);
+    }
+  }
+}
+
+// s[nt] += A(16 rows at a_row0, k over [kcol, kcol+DH)) * Bt where B is stored [n][k] ("nk": rows = output
+// columns).  8 output tiles (64 columns) in pairs; DH = 16*a + 8*b.
+template <int DH>
+__device__ __forceinline__ void gemm_rowk_nk(float (&s)[8][4], const SArr& A, int a_row0, const SArr& B, int kcol,
+                                             int npairs, int lane) {
+  const uint32_t a_lane = A.addr + (a_row0 + (lane & 15)) * A.ldb + (kcol + (lane >> 4) * 8) * 2;
+  const uint32_t b_lane = B.addr + ((lane & 7) + (lane >> 4) * 8) * B.ldb + (kcol + ((lane >> 3) & 1) * 8) * 2;
+#pragma unroll
+  for (int kk = 0; kk < DH / 16; kk++) {
+    uint32_t ah[4], al[4];
+    ldsm4(ah, a_lane + kk * 32);
+    ldsm4(al, a_lane + kk * 32 + A.lo);
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      if (p < npairs) {
+        uint32_t bh[4], bl[4];
+        ldsm4(bh, b_lane + p * 16 * B.ldb + kk * 32);
+        ldsm4(bl, b_lane + p * 16 * B.ldb + kk * 32 + B.lo);
+        mma16x3(s[2 * p], ah, al, bh[0], bh[1], bl[0], bl[1]);
+        mma16x3(s[2 * p + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+      }
+    }
+  }
+  if (DH % 16) {
+    constexpr int k0 = (DH / 16) * 16;
+    const uint32_t a2 = A.addr + (a_row0 + (lane & 15)) * A.ldb + (kcol + k0) * 2;
+    const uint32_t b2 = B.addr + (lane & 15) * B.ldb + (kcol + k0) * 2;
+    uint32_t ah[2], al[2];
+    ldsm2(ah, a2);
+    ldsm2(al, a2 + A.lo);
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      if (p < npairs) {
+        uint32_t bh[2], bl[2];
+        ldsm2(bh, b2 + p * 16 * B.ldb);
+        ldsm2(bl, b2 + p * 16 * B.ldb + B.lo);
+        mma8x3(s[2 * p], ah, al, bh[0], bl[0]);
+        mma8x3(s[2 * p + 1], ah, al, bh[1], bl[1]);
+      }
+    }
+  }
+}
+
+// o[nd] += A(16 rows at a_row0, k = tokens 0..16*ksteps) * B where B is stored [k][n] ("kn"), columns
+// ncol .. ncol+DH.  A row-major [row][token].
+template <int DH>
+__device__ __forceinline__ void gemm_rowk_kn(float (&o)[DH / 8][4], const SArr& A, int a_row0, const SArr& B, int ncol,
+                                             int ksteps, int lane) {
+  constexpr int NDT = DH / 8;
+  const uint32_t a_lane = A.addr + (a_row0 + (lane & 15)) * A.ldb + ((lane >> 4) * 8) * 2;
+  const uint32_t b_lane = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + (ncol + (lane >> 4) * 8) * 2;
+  const uint32_t b_lane2 = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + ncol * 2;
+  for (int kk = 0; kk < ksteps; kk++) {
+    uint32_t ah[4], al[4];
+    ldsm4(ah, a_lane + kk * 32);
+    ldsm4(al, a_lane + kk * 32 + A.lo);
+#pragma unroll
+    for (int nd = 0; nd + 1 < NDT; nd += 2) {
+      uint32_t bh[4], bl[4];
+      ldsm4t(bh, b_lane + kk * 16 * B.ldb + nd * 16);
+      ldsm4t(bl, b_lane + kk * 16 * B.ldb + nd * 16 + B.lo);
+      mma16x3(o[nd], ah, al, bh[0], bh[1], bl[0], bl[1]);
+      mma16x3(o[nd + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+    }
+    if (NDT & 1) {
+      constexpr int nd = NDT - 1;
+      uint32_t bh[2], bl[2];
+      ldsm2t(bh, b_lane2 + kk * 16 * B.ldb + nd * 16);
+      ldsm2t(bl, b_lane2 + kk * 16 * B.ldb + nd * 16 + B.lo);
+      mma16x3(o[nd], ah, al, bh[0], bh[1], bl[0], bl[1]);
+    }
+  }
+}
+
+// o[nd] += A^T(16 output rows = columns m0.. of SA, k = rows of SA) * B ("kn"): both stored [k][*]
+template <int DH>
+__device__ __forceinline__ void gemm_colk_kn(float (&o)[DH / 8][4], const SArr& A, int m0, const SArr& B, int ncol,
+                                             int ksteps, int lane) {
+  constexpr int NDT = DH / 8;
+  const uint32_t a_lane = A.addr + ((lane & 7) + ((lane >> 4) & 1) * 8) * A.ldb + (m0 + ((lane >> 3) & 1) * 8) * 2;
+  const uint32_t b_lane = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + (ncol + (lane >> 4) * 8) * 2;
+  const uint32_t b_lane2 = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + ncol * 2;
+  for (int kk = 0; kk < ksteps; kk++) {
+    uint32_t ah[4], al[4];
+    ldsm4t(ah, a_lane + kk * 16 * A.ldb);
+    ldsm4t(al, a_lane + kk * 16 * A.ldb + A.lo);
+#pragma unroll
+    for (int nd = 0; nd + 1 < NDT; nd += 2) {
+      uint32_t bh[4], bl[4];
+      ldsm4t(bh, b_lane + kk * 16 * B.ldb + nd * 16);
+      ldsm4t(bl, b_lane + kk * 16 * B.ldb + nd * 16 + B.lo);
+      mma16x3(o[nd], ah, al, bh[0], bh[1], bl[0], bl[1]);
+      mma16x3(o[nd + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+    }
+    if (NDT & 1) {
+      constexpr int nd = NDT - 1;
+      uint32_t bh[2], bl[2];
+      ldsm2t(bh, b_lane2 + kk * 16 * B.ldb + nd * 16);
+      ldsm2t(bl, b_lane2 + kk * 16 * B.ldb + nd * 16 + B.lo);
+      mma16x3(o[nd], ah, al, bh[0], bh[1], bl[0], bl[1]);
+    }
+  }
+}
+
+// LayerNorm of rows of a global [N][D] fp32 tensor into a split shared operand (net/layernorm.py:100-114);
+// rows >= N are zero-filled.  One warp per row; mean / rstd optionally kept for the backward formula.
+template <int D>
+__device__ __forceinline__ void ln_rows(const float* src, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        const SArr& dst, int N, float* s_mean, float* s_rstd, int warp, int lane) {
+  constexpr int E = D / 32;
+  float gm[E], bt[E];
+#pragma unroll
+  for (int e = 0; e < E; e++) { gm[e] = __ldg(gamma + lane + 32 * e); bt[e] = __ldg(beta + lane + 32 * e); }
+  for (int r = warp; r < ROWS; r += 8) {
+    if (r < N) {
+      float v[E], s = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; e++) { v[e] = src[r * D + lane + 32 * e]; s += v[e]; }
+      const float mean = warp_sum(s) * (1.0f / D);
+      float q = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; e++) { const float d = v[e] - mean; q += d * d; }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+      if (s_mean && lane == 0) { s_mean[r] = mean; s_rstd[r] = rstd; }
+#pragma unroll
+      for (int e = 0; e < E; e++) st1(dst, r, lane + 32 * e, (v[e] - mean) * rstd * gm[e] + bt[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; e++) st1(dst, r, lane + 32 * e, 0.f);
+    }
+  }
+}
+
+// dx = addend + rstd*(g*dy - mean(g*dy) - xhat*mean(g*dy*xhat))  (net/layernorm.py:126-128) per row; the result
+// goes to global fp32 (`out`) and, split, to `dst`.  dgamma/dbeta (and optionally the column sums of `addend`,
+// i.e. the bias gradient of the layer whose output gradient `addend` is) are accumulated per lane over the
+// warp's rows and flushed with one atomic per column per warp.
+template <int D>
+__device__ __forceinline__ void ln_bwd_rows(const float* dy, const float* xin, const float* __restrict__ gamma,
+                                            const float* addend, float* out, const SArr& dst, int N,
+                                            const float* s_mean, const float* s_rstd, float* dgamma, float* dbeta,
+                                            float* dbias_addend, int warp, int lane) {
+  constexpr int E = D / 32;
+  float gm[E], ag[E], ab[E], aa[E];
+#pragma unroll
+  for (int e = 0; e < E; e++) { gm[e] = __ldg(gamma + lane + 32 * e); ag[e] = ab[e] = aa[e] = 0.f; }
+  for (int r = warp; r < ROWS; r += 8) {
+    if (r < N) {
+      const float mu = s_mean[r], rs = s_rstd[r];
+      float g[E], xh[E], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const float d = dy[r * D + lane + 32 * e];
+        xh[e] = (xin[r * D + lane + 32 * e] - mu) * rs;
+        g[e] = gm[e] * d;
+        s1 += g[e];
+        s2 += g[e] * xh[e];
+        ag[e] += xh[e] * d;
+        ab[e] += d;
+      }
+      s1 = warp_sum(s1) * (1.0f / D);
+      s2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const float a = addend[r * D + lane + 32 * e];
+        aa[e] += a;
+        const float o = a + rs * (g[e] - s1 - xh[e] * s2);
+        out[r * D + lane + 32 * e] = o;
+        st1(dst, r, lane + 32 * e, o);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; e++) st1(dst, r, lane + 32 * e, 0.f);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    atomicAdd(dgamma + lane + 32 * e, ag[e]);
+    atomicAdd(dbeta + lane + 32 * e, ab[e]);
+    if (dbias_addend) atomicAdd(dbias_addend + lane + 32 * e, aa[e]);
+  }
+}
+
+// column sums of the two fragment rows held by the 8 `g` lanes -> lanes with g == 0 hold the totals
+__device__ __forceinline__ float colsum_g(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+template <int D, int H>
+struct Cfg {
+  static constexpr int DH = D / H;
+  static constexpr int LD = D + 8;          // pitch of [64][D] operands: 2*LD bytes = 16 (mod 128) or 80 (mod 128)
+  static constexpr int LD2 = 2 * D + 8;
+  static constexpr int ARR = ROWS * LD * 2 * 2;        // bytes of one [64][D] hi/lo pair
+  static constexpr int ARR2 = ROWS * LD2 * 2 * 2;
+  static constexpr int PARR = ROWS * LDP * 2 * 2;      // one [64][64] hi/lo pair
+  static constexpr int PW = 16 * LDP * 2 * 2;          // one warp's [16][64] hi/lo pair
+  // weight-fragment scratch, in uint4 units: forward order (qkv, fc0, fc1) then backward order
+  static constexpr int F_QKV = 0;
+  static constexpr int F_FC0 = F_QKV + 3 * D * D / 4;
+  static constexpr int F_FC1 = F_FC0 + 2 * D * D / 4;
+  static constexpr int B_QKV = F_FC1 + 2 * D * D / 4;
+  static constexpr int B_FC0 = B_QKV + 3 * D * D / 4;
+  static constexpr int B_FC1 = B_FC0 + 2 * D * D / 4;
+  static constexpr int F_TOTAL = B_FC1 + 2 * D * D / 4;     // = 3.5 D^2 uint4 = 8 bytes per weight
+  static constexpr size_t FWD_SMEM = 4 * (size_t)ARR + 8 * (size_t)PW;
+  static constexpr size_t BWD_SMEM = 4 * (size_t)ARR + 4 * (size_t)PARR + 2 * ROWS * sizeof(float);
+  static_assert(D % 32 == 0 && DH % 8 == 0 && DH * H == D, "fused ViT block: D % 32 == 0, dh % 8 == 0");
+  static_assert(ARR2 <= 2 * ARR && ARR2 <= 4 * PARR && ARR <= 4 * PARR, "aliasing plan");
+};
+
+// ---------------------------------------------------------------- weight pre-split
+// W [K][Nw] row-major fp32 -> B fragments.  fwd order: B(k, n) = W[k][n]; bwd order: B(k, n) = W[n][k].
+__device__ __forceinline__ void wsplit_entry(const float* __restrict__ W, int ldw, bool bwd, int KS, int NT, int e,
+                                             uint4* out) {
+  const int lane = e & 31, tile = e >> 5, nt = tile % NT, ks = tile / NT;
+  const int g = lane >> 2, t = lane & 3;
+  float v[4];
+  if (!bwd) {
+    const int n = 8 * nt + g, k0 = 16 * ks + 2 * t;
+    v[0] = W[(size_t)k0 * ldw + n]; v[1] = W[(size_t)(k0 + 1) * ldw + n];
+    v[2] = W[(size_t)(k0 + 8) * ldw + n]; v[3] = W[(size_t)(k0 + 9) * ldw + n];
+  } else {
+    const float* r = W + (size_t)(8 * nt + g) * ldw + 16 * ks + 2 * t;
+    v[0] = r[0]; v[1] = r[1]; v[2] = r[8]; v[3] = r[9];
+  }
+  uint4 o;
+  split2(v[0], v[1], o.x, o.z);
+  split2(v[2], v[3], o.y, o.w);
+  out[e] = o;
+  (void)KS;
+}
+
+template <int D, int H>
+__global__ void __launch_bounds__(256) vit_wsplit_kernel(Args a) {
+  pdl_prologue();
+  using C = Cfg<D, H>;
+  const NtVitBlock& P = a.blk[blockIdx.y];
+  uint4* wf = reinterpret_cast<uint4*>(P.wfrag);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < C::F_TOTAL; e += gridDim.x * blockDim.x) {
+    if (e < C::F_FC0) wsplit_entry(P.wqkv, 3 * D, false, D / 16, 3 * D / 8, e - C::F_QKV, wf + C::F_QKV);
+    else if (e < C::F_FC1) wsplit_entry(P.w0, 2 * D, false, D / 16, 2 * D / 8, e - C::F_FC0, wf + C::F_FC0);
+    else if (e < C::B_QKV) wsplit_entry(P.w1, D, false, 2 * D / 16, D / 8, e - C::F_FC1, wf + C::F_FC1);
+    else if (e < C::B_FC0) wsplit_entry(P.wqkv, 3 * D, true, 3 * D / 16, D / 8, e - C::B_QKV, wf + C::B_QKV);
+    else if (e < C::B_FC1) wsplit_entry(P.w0, 2 * D, true, 2 * D / 16, D / 8, e - C::B_FC0, wf + C::B_FC0);
+    else wsplit_entry(P.w1, D, true, D / 16, 2 * D / 8, e - C::B_FC1, wf + C::B_FC1);
+  }
+}
+
+// ---------------------------------------------------------------- forward
+template <int D, int H>
+__global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
+  pdl_prologue();
+  using C = Cfg<D, H>;
+  constexpr int DH = C::DH;
+  extern __shared__ __align__(128) char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int N = a.N, b = blockIdx.x;
+  const SArr sU = make_arr(smem, C::LD);
+  const SArr sQ = make_arr(smem + C::ARR, C::LD);
+  const SArr sK = make_arr(smem + 2 * C::ARR, C::LD);
+  const SArr sV = make_arr(smem + 3 * C::ARR, C::LD);
+  const SArr sG = make_arr(smem + C::ARR, C::LD2);                       // aliases sQ|sK after attention
+  const SArr sPw = make_arr(smem + 4 * C::ARR + warp * C::PW, LDP, 16);  // this warp's P tile
+  const int NTK = (N + 7) >> 3, NPAIR = (NTK + 1) >> 1, KT = (N + 15) >> 4;
+  const float scale = 1.0f / sqrtf((float)DH);
+  const size_t img = (size_t)b * N * D;
+  const float* xcur = a.x + img;
+
+  for (int bi = 0; bi < a.nblocks; bi++) {
+    const NtVitBlock& P = a.blk[bi];
+    const uint4* wf = reinterpret_cast<const uint4*>(P.wfrag);
+    // ---- u = LN(x)                                                      attention.py:22
+    ln_rows<D>(xcur, P.ln_g, P.ln_b, sU, N, nullptr, nullptr, warp, lane);
+    __syncthreads();
+    // ---- qkv = u Wqkv + b                                               attention.py:23-24
+    {
+      constexpr int NTW = 3 * D / 32;
+      float acc[2][NTW][4];
+      zero_acc(acc);
+      const uint32_t a_lane = sU.addr + (wm * 32 + (lane & 15)) * sU.ldb + ((lane >> 4) * 8) * 2;
+      gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sU.lo, 16 * sU.ldb, D / 16,
+                      wf + C::F_QKV + (wn * NTW) * 32 + lane, (3 * D / 8) * 32);
+      float* qg = P.qkv + (size_t)b * N * 3 * D;
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++) {
+          const int col = (wn * NTW + nt) * 8 + 2 * t;
+          const float2 bb = __ldg(reinterpret_cast<const float2*>(P.bqkv + col));
+          const int which = col / D, cc = col - which * D;
+          const SArr& dst = which == 0 ? sQ : (which == 1 ? sK : sV);
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            const int row = wm * 32 + mt * 16 + g + hf * 8;
+            float v0 = acc[mt][nt][2 * hf] + bb.x, v1 = acc[mt][nt][2 * hf + 1] + bb.y;
+            if (row < N) *reinterpret_cast<float2*>(qg + (size_t)row * 3 * D + col) = make_float2(v0, v1);
+            else v0 = v1 = 0.f;
+            st2(dst, row, cc, v0, v1);
+          }
+        }
+    }
+    __syncthreads();
+    // ---- attention, one (head, 16-query tile) per warp pass              attention.py:31-45
+    for (int item = warp; item < 4 * H; item += 8) {
+      const int hd = item >> 2, i0 = (item & 3) * 16;
+      if (i0 >= N) continue;
+      float s[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      gemm_rowk_nk<DH>(s, sQ, i0, sK, hd * DH, NPAIR, lane);
+      const int r0 = i0 + g, r1 = r0 + 8;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int col = nt * 8 + 2 * t + (c & 1);
+          const float v = col < N ? s[nt][c] * scale : -INFINITY;          // attention.py:37; padded keys never win
+          s[nt][c] = v;
+          if (c < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+        }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) {
+        s[nt][0] = expf(s[nt][0] - mx0); s[nt][1] = expf(s[nt][1] - mx0);
+        s[nt][2] = expf(s[nt][2] - mx1); s[nt][3] = expf(s[nt][3] - mx1);
+        s0 += s[nt][0] + s[nt][1];
+        s1 += s[nt][2] + s[nt][3];
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float inv0 = r0 < N ? 1.0f / s0 : 0.f, inv1 = r1 < N ? 1.0f / s1 : 0.f;
+      float* pg = P.P + ((size_t)b * H + hd) * N * N;
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) {
+        const int col = nt * 8 + 2 * t;
+        const float p00 = s[nt][0] * inv0, p01 = s[nt][1] * inv0, p10 = s[nt][2] * inv1, p11 = s[nt][3] * inv1;
+        st2(sPw, g, col, p00, p01);
+        st2(sPw, g + 8, col, p10, p11);
+        if (r0 < N) { if (col < N) pg[r0 * N + col] = p00; if (col + 1 < N) pg[r0 * N + col + 1] = p01; }   // atg__
+        if (r1 < N) { if (col < N) pg[r1 * N + col] = p10; if (col + 1 < N) pg[r1 * N + col + 1] = p11; }
+      }
+      __syncwarp();
+      float o[DH / 8][4];
+#pragma unroll
+      for (int nd = 0; nd < DH / 8; nd++) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+      gemm_rowk_kn<DH>(o, sPw, 0, sV, hd * DH, KT, lane);
+      float* hg = P.h + img;
+#pragma unroll
+      for (int nd = 0; nd < DH / 8; nd++) {
+        const int col = hd * DH + nd * 8 + 2 * t;
+        if (r0 < N) {
+          const float2 xr = *reinterpret_cast<const float2*>(xcur + r0 * D + col);
+          *reinterpret_cast<float2*>(hg + r0 * D + col) = make_float2(xr.x + o[nd][0], xr.y + o[nd][1]);   // attention.py:46
+        }
+        if (r1 < N) {
+          const float2 xr = *reinterpret_cast<const float2*>(xcur + r1 * D + col);
+          *reinterpret_cast<float2*>(hg + r1 * D + col) = make_float2(xr.x + o[nd][2], xr.y + o[nd][3]);
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // ---- u1 = LN1(h)                                                     attention.py:48
+    ln_rows<D>(P.h + img, P.ln1_g, P.ln1_b, sU, N, nullptr, nullptr, warp, lane);
+    __syncthreads();
+    // ---- pre2 = u1 W0 + b0 ; G = GELU(pre2)                              attention.py:49-50
+    {
+      constexpr int NTW = 2 * D / 32;
+      float acc[2][NTW][4];
+      zero_acc(acc);
+      const uint32_t a_lane = sU.addr + (wm * 32 + (lane & 15)) * sU.ldb + ((lane >> 4) * 8) * 2;
+      gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sU.lo, 16 * sU.ldb, D / 16,
+                      wf + C::F_FC0 + (wn * NTW) * 32 + lane, (2 * D / 8) * 32);
+      float* pg = P.pre2 + (size_t)b * N * 2 * D;
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++) {
+          const int col = (wn * NTW + nt) * 8 + 2 * t;
+          const float2 bb = __ldg(reinterpret_cast<const float2*>(P.b0 + col));
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            const int row = wm * 32 + mt * 16 + g + hf * 8;
+            float v0 = acc[mt][nt][2 * hf] + bb.x, v1 = acc[mt][nt][2 * hf + 1] + bb.y;
+            if (row < N) {
+              *reinterpret_cast<float2*>(pg + (size_t)row * 2 * D + col) = make_float2(v0, v1);
+              v0 = gelu_f(v0); v1 = gelu_f(v1);
+            } else {
+              v0 = v1 = 0.f;
+            }
+            st2(sG, row, col, v0, v1);
+          }
+        }
+    }
+    __syncthreads();
+    // ---- out = h + G W1 + b1                                              attention.py:51-53
+    {
+      constexpr int NTW = D / 32;
+      float acc[2][NTW][4];
+      zero_acc(acc);
+      const uint32_t a_lane = sG.addr + (wm * 32 + (lane & 15)) * sG.ldb + ((lane >> 4) * 8) * 2;
+      gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sG.lo, 16 * sG.ldb, 2 * D / 16,
+                      wf + C::F_FC1 + (wn * NTW) * 32 + lane, (D / 8) * 32);
+      const float* hg = P.h + img;
+      float* og = P.out + img;
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++) {
+          const int col = (wn * NTW + nt) * 8 + 2 * t;
+          const float2 bb = __ldg(reinterpret_cast<const float2*>(P.b1 + col));
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            const int row = wm * 32 + mt * 16 + g + hf * 8;
+            if (row < N) {
+              const float2 hr = *reinterpret_cast<const float2*>(hg + row * D + col);
+              *reinterpret_cast<float2*>(og + row * D + col) =
+                  make_float2(acc[mt][nt][2 * hf] + bb.x + hr.x, acc[mt][nt][2 * hf + 1] + bb.y + hr.y);
+            }
+          }
+        }
+    }
+    __syncthreads();
+    xcur = P.out + img;
+  }
+}
+
+// ---------------------------------------------------------------- backward
+template <int D, int H>
+__global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
+  pdl_prologue();
+  using C = Cfg<D, H>;
+  constexpr int DH = C::DH, NDT = DH / 8;
+  extern __shared__ __align__(128) char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int N = a.N, b = blockIdx.x;
+  // regions: R_D | R_Q | R_K | R_V | R_PS(4 score planes) | stats
+  char* rD = smem;
+  char* rQ = smem + C::ARR;
+  char* rK = smem + 2 * C::ARR;
+  char* rV = smem + 3 * C::ARR;
+  char* rPS = smem + 4 * C::ARR;
+  float* s_mean = reinterpret_cast<float*>(smem + 4 * C::ARR + 4 * C::PARR);
+  float* s_rstd = s_mean + ROWS;
+  const SArr sD = make_arr(rD, C::LD);
+  const SArr sQ = make_arr(rQ, C::LD), sK = make_arr(rK, C::LD), sV = make_arr(rV, C::LD);
+  const SArr sU1 = make_arr(rQ, C::LD);          // MLP phase: LN1(h)
+  const SArr sDP = make_arr(rK, C::LD2);         // MLP phase: d(pre2)   (spans R_K|R_V)
+  const SArr sG = make_arr(rPS, C::LD2);         // MLP phase: GELU(pre2)
+  const SArr sU = make_arr(rPS, C::LD);          // QKV phase: LN(x)
+  const int KT = (N + 15) >> 4;                  // k16 steps over tokens
+  const int NTK = (N + 7) >> 3, NPAIR = (NTK + 1) >> 1;
+  const float scale = 1.0f / sqrtf((float)DH);
+  const size_t img = (size_t)b * N * D;
+  float* dh = a.dh + img;
+  float* tmp = a.tmp + img;
+  float* dxo = a.dx + img;
+  const float* dcur = a.dout + img;
+
+  // incoming gradient -> split operand
+  for (int r = warp; r < ROWS; r += 8)
+#pragma unroll
+    for (int e = 0; e < D / 32; e++) st1(sD, r, lane + 32 * e, r < N ? dcur[r * D + lane + 32 * e] : 0.f);
+
+  for (int bi = a.nblocks - 1; bi >= 0; bi--) {
+    const NtVitBlock& P = a.blk[bi];
+    const uint4* wf = reinterpret_cast<const uint4*>(P.wfrag);
+    const float* xin = (bi ? a.blk[bi - 1].out : a.x) + img;
+    const float* hg = P.h + img;
+    // ---- S0: recompute u1 = LN1(h) (operand of dW0) and its row statistics
+    ln_rows<D>(hg, P.ln1_g, P.ln1_b, sU1, N, s_mean, s_rstd, warp, lane);
+    __syncthreads();
+    // ---- S1: dG = d W1^T ; dpre = dG * gelu'(pre2) ; G = gelu(pre2)        attention.py:58-59
+    {
+      constexpr int NTW = 2 * D / 32;
+      float acc[2][NTW][4];
+      zero_acc(acc);
+      const uint32_t a_lane = sD.addr + (wm * 32 + (lane & 15)) * sD.ldb + ((lane >> 4) * 8) * 2;
+      gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sD.lo, 16 * sD.ldb, D / 16,
+                      wf + C::B_FC1 + (wn * NTW) * 32 + lane, (2 * D / 8) * 32);
+      const float* pg = P.pre2 + (size_t)b * N * 2 * D;
+#pragma unroll
+      for (int nt = 0; nt < NTW; nt++) {
+        const int col = (wn * NTW + nt) * 8 + 2 * t;
+        float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            const int row = wm * 32 + mt * 16 + g + hf * 8;
+            float d0 = 0.f, d1 = 0.f, g0 = 0.f, g1 = 0.f;
+            if (row < N) {
+              const float2 pr = *reinterpret_cast<const float2*>(pg + (size_t)row * 2 * D + col);
+              d0 = acc[mt][nt][2 * hf] * gelu_grad_f(pr.x);
+              d1 = acc[mt][nt][2 * hf + 1] * gelu_grad_f(pr.y);
+              g0 = gelu_f(pr.x); g1 = gelu_f(pr.y);
+            }
+            st2(sDP, row, col, d0, d1);
+            st2(sG, row, col, g0, g1);
+            c0 += d0; c1 += d1;
+          }
+        c0 = colsum_g(c0); c1 = colsum_g(c1);                                 // db0 += colsum(dpre)  fullconnect.py:122
+        if (g == 0) { atomicAdd(P.d_b0 + col, c0); atomicAdd(P.d_b0 + col + 1, c1); }
+      }
+    }
+    __syncthreads();
+    // ---- S2: dW1 += G^T d                                                  fullconnect.py:118-121
+    {
+      constexpr int MT = D / 32, NTW = D / 16;
+      float acc[MT][NTW][4];
+      zero_acc(acc);
+      const int m0 = (warp >> 1) * (MT * 16), n0 = (warp & 1) * (NTW * 8);
+      gemm_tt<MT, NTW>(acc, sG, m0, sD, n0, KT, lane);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++) {
+          float* w = P.d_w1 + (size_t)(m0 + mt * 16 + g) * D + n0 + nt * 8 + 2 * t;
+          red2(w, acc[mt][nt][0], acc[mt][nt][1]);
+          red2(w + 8 * D, acc[mt][nt][2], acc[mt][nt][3]);
+        }
+    }
+    // ---- S3: dU1 = dpre W0^T -> tmp                                         attention.py:60
+    {
+      constexpr int NTW = D / 32;
+      float acc[2][NTW][4];
+      zero_acc(acc);
+      const uint32_t a_lane = sDP.addr + (wm * 32 + (lane & 15)) * sDP.ldb + ((lane >> 4) * 8) * 2;
+      gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sDP.lo, 16 * sDP.ldb, 2 * D / 16,
+                      wf + C::B_FC0 + (wn * NTW) * 32 + lane, (D / 8) * 32);
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            const int row = wm * 32 + mt * 16 + g + hf * 8, col = (wn * NTW + nt) * 8 + 2 * t;
+            if (row < N) *reinterpret_cast<float2*>(tmp + row * D + col) = make_float2(acc[mt][nt][2 * hf], acc[mt][nt][2 * hf + 1]);
+          }
+    }
+    // ---- S4: dW0 += u1^T dpre
+    {
+      constexpr int MT = D / 32, NTW = D / 16;
+      float acc[MT][NTW][4];
+      zero_acc(acc);
+      const int m0 = wm * (MT * 16), n0 = wn * (NTW * 8);
+      gemm_tt<MT, NTW>(acc, sU1, m0, sDP, n0, KT, lane);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++) {
+          float* w = P.d_w0 + (size_t)(m0 + mt * 16 + g) * 2 * D + n0 + nt * 8 + 2 * t;
+          red2(w, acc[mt][nt][0], acc[mt][nt][1]);
+          red2(w + 8 * 2 * D, acc[mt][nt][2], acc[mt][nt][3]);
+        }
+    }
+    __syncthreads();
+    // ---- S5: dh = d + LN1-backward(dU1) ; db1 += colsum(d)                  attention.py:61-62
+    ln_bwd_rows<D>(tmp, hg, P.ln1_g, dcur, dh, sD, N, s_mean, s_rstd, P.d_ln1_g, P.d_ln1_b, P.d_b1, warp, lane);
+    // ---- S6: attention backward.  q/k/v -> shared (split)
+    {
+      const float* qg = P.qkv + (size_t)b * N * 3 * D;
+      for (int e = tid; e < ROWS * (3 * D / 2); e += 256) {
+        const int row = e / (3 * D / 2), c2 = (e - row * (3 * D / 2)) * 2;
+        const int which = c2 / D, cc = c2 - which * D;
+        float2 v = make_float2(0.f, 0.f);
+        if (row < N) v = *reinterpret_cast<const float2*>(qg + (size_t)row * 3 * D + c2);
+        st2(which == 0 ? sQ : (which == 1 ? sK : sV), row, cc, v.x, v.y);
+      }
+    }
+    __syncthreads();
+    for (int rnd = 0; rnd < (H + 1) / 2; rnd++) {
+      const int hl = warp >> 2, hd = 2 * rnd + hl, i0 = (warp & 3) * 16;
+      const bool head_ok = hd < H;
+      const bool valid = head_ok && i0 < N;
+      const SArr sP = make_arr(rPS + (2 * hl) * C::PARR, LDP);
+      const SArr sdS = make_arr(rPS + (2 * hl + 1) * C::PARR, LDP);
+      const int r0 = i0 + g, r1 = r0 + 8;
+      float dq[NDT][4], dk[NDT][4], dv[NDT][4];
+#pragma unroll
+      for (int nd = 0; nd < NDT; nd++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) dq[nd][c] = dk[nd][c] = dv[nd][c] = 0.f;
+      // phase 1: dP = dO V^T, dS = P o (dP - rowsum(dP o P)), dQ = dS K / sqrt(dh)      attention.py:74-78
+      if (valid) {
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        gemm_rowk_nk<DH>(s, sD, i0, sV, hd * DH, NPAIR, lane);
+        const float* pg = P.P + ((size_t)b * H + hd) * N * N;
+        float p[8][4], t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+          const int col = nt * 8 + 2 * t;
+          p[nt][0] = (r0 < N && col < N) ? pg[r0 * N + col] : 0.f;
+          p[nt][1] = (r0 < N && col + 1 < N) ? pg[r0 * N + col + 1] : 0.f;
+          p[nt][2] = (r1 < N && col < N) ? pg[r1 * N + col] : 0.f;
+          p[nt][3] = (r1 < N && col + 1 < N) ? pg[r1 * N + col + 1] : 0.f;
+          t0 += s[nt][0] * p[nt][0] + s[nt][1] * p[nt][1];
+          t1 += s[nt][2] * p[nt][2] + s[nt][3] * p[nt][3];
+        }
+        t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t0 += __shfl_xor_sync(0xffffffffu, t0, 2);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+          const int col = nt * 8 + 2 * t;
+          st2(sP, r0, col, p[nt][0], p[nt][1]);
+          st2(sP, r1, col, p[nt][2], p[nt][3]);
+          st2(sdS, r0, col, p[nt][0] * (s[nt][0] - t0), p[nt][1] * (s[nt][1] - t0));
+          st2(sdS, r1, col, p[nt][2] * (s[nt][2] - t1), p[nt][3] * (s[nt][3] - t1));
+        }
+        __syncwarp();
+        gemm_rowk_kn<DH>(dq, sdS, i0, sK, hd * DH, KT, lane);
+      } else if (head_ok) {
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+          const int col = nt * 8 + 2 * t;
+          st2(sP, r0, col, 0.f, 0.f); st2(sP, r1, col, 0.f, 0.f);
+          st2(sdS, r0, col, 0.f, 0.f); st2(sdS, r1, col, 0.f, 0.f);
+        }
+      }
+      __syncthreads();
+      // phase 2: this warp's 16 KEYS: dK = dS^T Q / sqrt(dh), dV = P^T dO                attention.py:76,79
+      if (valid) {
+        gemm_colk_kn<DH>(dk, sdS, i0, sQ, hd * DH, KT, lane);
+        gemm_colk_kn<DH>(dv, sP, i0, sD, hd * DH, KT, lane);
+      }
+      __syncthreads();
+      // q/k/v of these heads are dead: overwrite them with dq/dk/dv (attention.py:81-83) + bias gradient
+      if (head_ok) {
+#pragma unroll
+        for (int nd = 0; nd < NDT; nd++) {
+          const int col = hd * DH + nd * 8 + 2 * t;
+          st2(sQ, r0, col, dq[nd][0] * scale, dq[nd][1] * scale);
+          st2(sQ, r1, col, dq[nd][2] * scale, dq[nd][3] * scale);
+          st2(sK, r0, col, dk[nd][0] * scale, dk[nd][1] * scale);
+          st2(sK, r1, col, dk[nd][2] * scale, dk[nd][3] * scale);
+          st2(sV, r0, col, dv[nd][0], dv[nd][1]);
+          st2(sV, r1, col, dv[nd][2], dv[nd][3]);
+          float c[6] = {(dq[nd][0] + dq[nd][2]) * scale, (dq[nd][1] + dq[nd][3]) * scale,
+                        (dk[nd][0] + dk[nd][2]) * scale, (dk[nd][1] + dk[nd][3]) * scale,
+                        dv[nd][0] + dv[nd][2], dv[nd][1] + dv[nd][3]};
+#pragma unroll
+          for (int i = 0; i < 6; i++) c[i] = colsum_g(c[i]);
+          if (g == 0 && valid) {
+            atomicAdd(P.d_bqkv + col, c[0]); atomicAdd(P.d_bqkv + col + 1, c[1]);
+            atomicAdd(P.d_bqkv + D + col, c[2]); atomicAdd(P.d_bqkv + D + col + 1, c[3]);
+            atomicAdd(P.d_bqkv + 2 * D + col, c[4]); atomicAdd(P.d_bqkv + 2 * D + col + 1, c[5]);
+          }
+        }
+      }
+    }
+    // ---- S7: u = LN(x) (operand of dWqkv) + statistics                    (sP/sdS are dead: all warps passed the last barrier)
+    ln_rows<D>(xin, P.ln_g, P.ln_b, sU, N, s_mean, s_rstd, warp, lane);
+    __syncthreads();
+    // ---- S8: dU = dqkv Wqkv^T -> tmp ; dWqkv += u^T dqkv                   attention.py:85-86
+    {
+      constexpr int NTW = D / 32;
+      float acc[2][NTW][4];
+      zero_acc(acc);
+      const uint32_t a_lane = sQ.addr + (wm * 32 + (lane & 15)) * sQ.ldb + ((lane >> 4) * 8) * 2;
+      // k runs over the 3D columns of dqkv = [dq | dk | dv], three arrays C::ARR bytes apart
+      gemm_wf<2, NTW>(acc, [&](int ks) { const int seg = ks / (D / 16); return a_lane + seg * C::ARR + (ks - seg * (D / 16)) * 32; },
+                      sQ.lo, 16 * sQ.ldb, 3 * D / 16, wf + C::B_QKV + (wn * NTW) * 32 + lane, (D / 8) * 32);
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            const int row = wm * 32 + mt * 16 + g + hf * 8, col = (wn * NTW + nt) * 8 + 2 * t;
+            if (row < N) *reinterpret_cast<float2*>(tmp + row * D + col) = make_float2(acc[mt][nt][2 * hf], acc[mt][nt][2 * hf + 1]);
+          }
+    }
+#pragma unroll 1
+    for (int seg = 0; seg < 3; seg++) {
+      constexpr int MT = D / 32, NTW = D / 32;
+      float acc[MT][NTW][4];
+      zero_acc(acc);
+      const int m0 = wm * (MT * 16), n0 = wn * (NTW * 8);
+      const SArr& sB = seg == 0 ? sQ : (seg == 1 ? sK : sV);
+      gemm_tt<MT, NTW>(acc, sU, m0, sB, n0, KT, lane);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++) {
+          float* w = P.d_wqkv + (size_t)(m0 + mt * 16 + g) * 3 * D + seg * D + n0 + nt * 8 + 2 * t;
+          red2(w, acc[mt][nt][0], acc[mt][nt][1]);
+          red2(w + 8 * 3 * D, acc[mt][nt][2], acc[mt][nt][3]);
+        }
+    }
+    __syncthreads();
+    // ---- S9: dx = dh + LN-backward(dU)                                     attention.py:87-88
+    ln_bwd_rows<D>(tmp, xin, P.ln_g, dh, dxo, sD, N, s_mean, s_rstd, P.d_ln_g, P.d_ln_b, nullptr, warp, lane);
+    __syncthreads();
+    dcur = dxo;
+  }
+}
+
+template <int D, int H>
+static int ensure_attrs() {
+  using C = Cfg<D, H>;
+  static bool attr = false;
+  if (!attr) {
+    NT_CHECK(cudaFuncSetAttribute(vit_fwd_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::FWD_SMEM));
+    NT_CHECK(cudaFuncSetAttribute(vit_bwd_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BWD_SMEM));
+    attr = true;
+  }
+  return 0;
+}
+template <int D, int H>
+static int launch_fwd(const Args& a, int B) {
+  using C = Cfg<D, H>;
+  if (int rc = ensure_attrs<D, H>()) return rc;
+  NT_CHECK(launch_k(vit_wsplit_kernel<D, H>, dim3(ceil_div(C::F_TOTAL, 256 * 4), a.nblocks), dim3(256), 0, a));
+  NT_LAUNCH_OK();
+  NT_CHECK(launch_k(vit_fwd_kernel<D, H>, dim3(B), dim3(256), C::FWD_SMEM, a));
+  NT_LAUNCH_OK();
+  return 0;
+}
+template <int D, int H>
+static int launch_bwd(const Args& a, int B) {
+  using C = Cfg<D, H>;
+  if (int rc = ensure_attrs<D, H>()) return rc;
+  NT_CHECK(launch_k(vit_bwd_kernel<D, H>, dim3(B), dim3(256), C::BWD_SMEM, a));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+static bool supported(int N, int D, int H) {
+  if (N < 1 || N > ROWS) return false;
+  return (D == 96 && H == 4) || (D == 64 && H == 4) || (D == 32 && H == 2) || (D == 64 && H == 2) || (D == 96 && H == 6);
+}
+
+#define VB_DISPATCH(fn, ...)                                               \
+  do {                                                                     \
+    if (D == 96 && H == 4) return fn<96, 4>(__VA_ARGS__);                  \
+    if (D == 96 && H == 6) return fn<96, 6>(__VA_ARGS__);                  \
+    if (D == 64 && H == 4) return fn<64, 4>(__VA_ARGS__);                  \
+    if (D == 64 && H == 2) return fn<64, 2>(__VA_ARGS__);                  \
+    if (D == 32 && H == 2) return fn<32, 2>(__VA_ARGS__);                  \
+  } while (0)
+
+static int run_fwd(const Args& a, int B, int D, int H) { VB_DISPATCH(launch_fwd, a, B); return 2; }
+static int run_bwd(const Args& a, int B, int D, int H) { VB_DISPATCH(launch_bwd, a, B); return 2; }
+
+}  // namespace vb
+}  // namespace nt
+using namespace nt;
+
+extern "C" {
+
+int nt_vit_blocks_supported(int N, int D, int H, int* ok) {
+  *ok = vb::supported(N, D, H) ? 1 : 0;
+  return 0;
+}
+
+int nt_vit_blocks_wfrag_bytes(int D, size_t* bytes) {
+  *bytes = (size_t)56 * D * D;          // 8 bytes per weight element of the block's three Linear layers (7 D^2)
+  return 0;
+}
+
+int nt_vit_blocks_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H) {
+  NT_ENTRY();
+  NT_REQUIRE(vb::supported(N, D, H), "nt_vit_blocks_fwd: unsupported shape N=%d D=%d H=%d", N, D, H);
+  NT_REQUIRE(nblocks >= 1 && nblocks <= vb::MAXB, "nt_vit_blocks_fwd: 1..%d blocks per call, got %d", vb::MAXB, nblocks);
+  if (B == 0) return 0;
+  vb::Args a{};
+  for (int i = 0; i < nblocks; i++) a.blk[i] = blocks[i];
+  a.nblocks = nblocks; a.N = N; a.x = x;
+  return vb::run_fwd(a, B, D, H);
+}
+
+int nt_vit_blocks_bwd(const NtVitBlock* blocks, int nblocks, const float* x, const float* dout, float* dx,
+                      float* scratch, int B, int N, int D, int H) {
+  NT_ENTRY();
+  NT_REQUIRE(vb::supported(N, D, H), "nt_vit_blocks_bwd: unsupported shape N=%d D=%d H=%d", N, D, H);
+  NT_REQUIRE(nblocks >= 1 && nblocks <= vb::MAXB, "nt_vit_blocks_bwd: 1..%d blocks per call, got %d", vb::MAXB, nblocks);
+  if (B == 0) return 0;
+  vb::Args a{};
+  for (int i = 0; i < nblocks; i++) a.blk[i] = blocks[i];
+  a.nblocks = nblocks; a.N = N; a.x = x; a.dout = dout; a.dx = dx;
+  a.dh = scratch; a.tmp = scratch + (size_t)B * N * D;
+  return vb::run_bwd(a, B, D, H);
+}
+
+}

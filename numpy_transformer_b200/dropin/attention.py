@@ -11,6 +11,7 @@ from net.fullconnect import fclayer
 from net.activation import Softmax, GELU
 from numpy_transformer_b200.device import as_device
 from numpy_transformer_b200 import ops
+from numpy_transformer_b200 import fused_vit
 
 
 class attention_layer():
@@ -31,6 +32,9 @@ class attention_layer():
         self.batch, self.block, _ = x.shape
         kind, dmask = ops.detect_mask(masks, self.block)
         self._mask_kind = kind
+        self._fused = False
+        if kind == ops.MASK_NONE and fused_vit.supported(self.block, self.embed_dim, self.num_h):
+            return fused_vit.forward_stack([self], x)             # whole block in one launch (csrc/vit_block.cu)
         self.out = self.norm._forward(x)
         self.qkv = self.qkvfc._forward(self.out)                       # (B,N,3D): [q,k,v][head][dh]
         input1, self.P, _ = ops.attention_fwd(self.qkv, self.num_h, dmask, kind, residual=x)
@@ -40,6 +44,8 @@ class attention_layer():
 
     def backward(self, delta):
         delta = as_device(delta)
+        if getattr(self, "_fused", False):
+            return fused_vit.backward_stack([self], delta)
         d = self.fc1._backward(delta, self.out2, ops.ACT_GELU, self.pre2)   # fc1.backward + gelu.backward
         d = self.fc0._backward(d, self.out1)
         delta0 = self.norm1._backward(d, addend=delta)                 # delta0 += delta (attention.py:62)

@@ -1,0 +1,113 @@
+"""Host side of the fused ViT-block kernels (csrc/vit_block.cu, `nt_vit_blocks_fwd/bwd` in include/ntb200.h).
+
+A run of consecutive `attention.attention_layer` objects (attention.py:6-114) is executed as ONE forward launch
+and ONE backward launch: every image walks the whole stack inside a single CTA.  The layer objects keep the
+reference's observable state (`qkv`, `atg__`/`P`, parameter `*_delta` accumulators, pickle layout); only the
+launch granularity changes.  Shapes the kernels do not cover fall back to the per-op path of the layer."""
+import ctypes
+import os
+
+from ._lib import lib
+from .device import DeviceArray, get_gemm_mode
+
+_PTR_FIELDS = ["ln_g", "ln_b", "wqkv", "bqkv", "ln1_g", "ln1_b", "w0", "b0", "w1", "b1",
+               "d_ln_g", "d_ln_b", "d_wqkv", "d_bqkv", "d_ln1_g", "d_ln1_b", "d_w0", "d_b0", "d_w1", "d_b1",
+               "qkv", "P", "h", "pre2", "out", "wfrag"]
+
+
+class NtVitBlock(ctypes.Structure):
+    """Mirror of `struct NtVitBlock` (include/ntb200.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in _PTR_FIELDS]
+
+
+def enabled():
+    return os.environ.get("NTB200_FUSED_VIT", "1") != "0"
+
+
+def supported(N, D, H):
+    """True when the fused kernels cover this shape in the current GEMM mode (mode 1 = fp32-class tensor-core path)."""
+    if not enabled() or get_gemm_mode() != 1:
+        return False
+    ok = ctypes.c_int(0)
+    lib.nt_vit_blocks_supported(int(N), int(D), int(H), ctypes.byref(ok))
+    return bool(ok.value)
+
+
+def _wfrag(layer, D):
+    w = getattr(layer, "_wfrag", None)
+    if w is None:
+        nbytes = ctypes.c_size_t(0)
+        lib.nt_vit_blocks_wfrag_bytes(int(D), ctypes.byref(nbytes))
+        w = layer._wfrag = DeviceArray((nbytes.value // 4,))
+    return w
+
+
+def _block_array(layers):
+    arr = (NtVitBlock * len(layers))()
+    for s, l in zip(arr, layers):
+        s.ln_g, s.ln_b = l.norm.gamma.ptr, l.norm.beta.ptr
+        s.wqkv, s.bqkv = l.qkvfc.params.ptr, l.qkvfc.bias_params.ptr
+        s.ln1_g, s.ln1_b = l.norm1.gamma.ptr, l.norm1.beta.ptr
+        s.w0, s.b0 = l.fc0.params.ptr, l.fc0.bias_params.ptr
+        s.w1, s.b1 = l.fc1.params.ptr, l.fc1.bias_params.ptr
+        s.d_ln_g, s.d_ln_b = l.norm.gamma_delta.ptr, l.norm.beta_delta.ptr
+        s.d_wqkv, s.d_bqkv = l.qkvfc.params_delta.ptr, l.qkvfc.bias_delta.ptr
+        s.d_ln1_g, s.d_ln1_b = l.norm1.gamma_delta.ptr, l.norm1.beta_delta.ptr
+        s.d_w0, s.d_b0 = l.fc0.params_delta.ptr, l.fc0.bias_delta.ptr
+        s.d_w1, s.d_b1 = l.fc1.params_delta.ptr, l.fc1.bias_delta.ptr
+        s.qkv, s.P, s.h, s.pre2, s.out = l.qkv.ptr, l.P.ptr, l.input1.ptr, l.pre2.ptr, l._out.ptr
+        s.wfrag = l._wfrag.ptr
+    return arr
+
+
+def forward_stack(layers, x):
+    """attention_layer.forward (attention.py:20-55) of every layer in `layers`, chained, in one launch."""
+    B, N, D = x.shape
+    H = layers[0].num_h
+    hd = x.host_dtype
+    for l in layers:
+        assert l.embed_dim == D and l.num_h == H, "fused stack needs identical blocks"
+        l.batch, l.block = B, N
+        l._mask_kind = 0
+        l.qkv = DeviceArray((B, N, 3 * D), host_dtype=hd)
+        l.P = DeviceArray((B, H, N, N), host_dtype=hd)
+        l.input1 = DeviceArray((B, N, D), host_dtype=hd)
+        l.pre2 = DeviceArray((B, N, 2 * D), host_dtype=hd)
+        l._out = DeviceArray((B, N, D), host_dtype=hd)
+        l.out = l.out1 = l.out2 = None          # LN outputs / GELU output are recomputed in backward, not stored
+        l._fused = True
+        _wfrag(l, D)
+    layers[0]._x_in = x
+    for prev, l in zip(layers, layers[1:]):
+        l._x_in = prev._out
+    arr = _block_array(layers)
+    lib.nt_vit_blocks_fwd(ctypes.addressof(arr), len(layers), x.ptr, B, N, D, H)
+    return layers[-1]._out
+
+
+def backward_stack(layers, delta):
+    """attention_layer.backward (attention.py:57-89) of the stack, last layer first, in one launch."""
+    x = layers[0]._x_in
+    B, N, D = x.shape
+    H = layers[0].num_h
+    dx = DeviceArray((B, N, D), host_dtype=delta.host_dtype)
+    scratch = DeviceArray((2, B, N, D))
+    arr = _block_array(layers)
+    lib.nt_vit_blocks_bwd(ctypes.addressof(arr), len(layers), x.ptr, delta.ptr, dx.ptr, scratch.ptr, B, N, D, H)
+    return dx
+
+
+def fusable_run(layers, start, block_type, x_shape):
+    """Length of the run of fusable `block_type` layers beginning at layers[start] (0 if the first is not)."""
+    if len(x_shape) != 3:
+        return 0
+    _, N, D = x_shape
+    n = 0
+    while start + n < len(layers) and n < 16:
+        l = layers[start + n]
+        if type(l) is not block_type or l.embed_dim != D or l.num_h != layers[start].num_h:
+            break
+        n += 1
+    if n and not supported(N, D, layers[start].num_h):
+        return 0
+    return n

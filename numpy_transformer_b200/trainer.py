@@ -20,6 +20,7 @@ from . import install
 from ._lib import lib
 from .device import DeviceArray, PinnedBuffer, as_device, init, keep_allocations
 from . import ops
+from . import fused_vit
 
 
 def _import_layers():
@@ -181,6 +182,7 @@ class TrainStep:
         self.loss = self.logits = self.probs = self.argmax = None
         L = _import_layers()
         self._block_t = L["attdecoderblock_layer"]
+        self._vit_block_t = L["attention_layer"]
 
     # ------------------------------------------------------------------ the step body (enqueue only)
     def _enqueue_chain(self, c, layers):
@@ -190,21 +192,39 @@ class TrainStep:
         in_elems = self.d_in.size // nc
         x = self.d_in.view(c * in_elems, (bs,) + self.input_shape[1:])
         lab = self.d_lab.view(c * rows, (rows,))
-        for l in layers:
+        runs = {}                                    # start index -> fused run of ViT blocks (one launch each way)
+        i = 0
+        while i < len(layers):
+            l = layers[i]
+            n = fused_vit.fusable_run(layers, i, self._vit_block_t, x.shape) if type(l) is self._vit_block_t else 0
+            if n:
+                runs[i] = layers[i:i + n]
+                x = fused_vit.forward_stack(runs[i], x)
+                i += n
+                continue
             if isinstance(l, self._block_t):
                 x = l.forward(x, "causal")
             else:
                 x = l.forward(x)
+            i += 1
         flat = x.reshape(rows, x.shape[-1])
         loss, grad, probs, amax = ops.cross_entropy(flat, lab, None, self.n_norm, loss_out=self.d_loss.view(c, ()),
                                                     argmax_out=self.d_amax.view(c * rows, (rows,)))
         delta = grad.reshape(x.shape)
         first = layers[0]
-        for l in reversed(layers):
+        ends = {s + len(r) - 1: s for s, r in runs.items()}
+        i = len(layers) - 1
+        while i >= 0:
+            l = layers[i]
+            if i in ends:
+                delta = fused_vit.backward_stack(runs[ends[i]], delta)
+                i = ends[i] - 1
+                continue
             if l is first and hasattr(l, "fullconnect"):
                 delta = l.backward(delta, want_dx=False)     # nobody consumes the patch-space gradient
             else:
                 delta = l.backward(delta)
+            i -= 1
         return x, probs
 
     def _enqueue(self):
