@@ -147,14 +147,18 @@ typedef struct NtVitBlock {
   float *qkv;                      /* [B,N,3D]   kept for backward                :23 */
   float *P;                        /* [B,H,N,N]  softmax, the reference's atg__   :41 */
   float *h;                        /* [B,N,D]    input1 = x + attention           :46 */
-  float *pre2;                     /* [B,N,2D]   fc0 output before GELU           :49 */
+  float *dgelu;                    /* [B,N,2D]   GELU'(fc0 output), the factor GELU.backward applies (net/activation.py:144-148) */
   float *out;                      /* [B,N,D]    block output                     :53 */
+  void *save;                      /* B * nt_vit_blocks_save_bytes(D): MMA operands of the backward exactly as the
+                                      forward held them in shared memory (bf16 hi/lo split LN(x), q|k|v, LN1(h),
+                                      GELU(pre)) + LayerNorm statistics; moved with 1-D TMA bulk copies */
   void *wfrag;                     /* scratch, nt_vit_blocks_wfrag_bytes(D): forward fills it with the
                                       bf16 hi/lo mma-fragment-ordered copies of the three weight matrices,
                                       backward of the same step re-uses it */
 } NtVitBlock;
 int nt_vit_blocks_supported(int N, int D, int H, int* ok);
 int nt_vit_blocks_wfrag_bytes(int D, size_t* bytes);
+int nt_vit_blocks_save_bytes(int D, size_t* bytes_per_image);
 /* x [B,N,D] is the input of blocks[0]; blocks[i].out feeds blocks[i+1]. */
 int nt_vit_blocks_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H);
 /* dout [B,N,D] = gradient w.r.t. blocks[nblocks-1].out; dx [B,N,D] receives the gradient w.r.t. x;

@@ -95,28 +95,15 @@ __device__ __forceinline__ void ldsm2t(uint32_t (&r)[2], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
 __device__ __forceinline__ void mma16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void mma8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(b0));
-}
-// error-compensated product: small terms first
-__device__ __forceinline__ void mma16x3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
-                                        uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-  mma16(d, al, bh0, bh1);
-  mma16(d, ah, bl0, bl1);
-  mma16(d, ah, bh0, bh1);
-}
-__device__ __forceinline__ void mma8x3(float (&d)[4], const uint32_t (&ah)[2], const uint32_t (&al)[2], uint32_t bh,
-                                       uint32_t bl) {
-  mma8(d, al[0], al[1], bh);
-  mma8(d, ah[0], ah[1], bl);
-  mma8(d, ah[0], ah[1], bh);
 }
 __device__ __forceinline__ void red2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
@@ -151,10 +138,19 @@ __device__ __forceinline__ void gemm_wf(float (&acc)[MT][NTW][4], AF a_addr, uin
       ldsm4(ah[mt], a0 + mt * a_mt_stride);
       ldsm4(al[mt], a0 + mt * a_mt_stride + a_lo);
     }
+    // pass-major: consecutive MMAs hit different accumulators (no back-to-back RAW on the tensor pipe)
 #pragma unroll
     for (int nt = 0; nt < NTW; nt++)
 #pragma unroll
-      for (int mt = 0; mt < MT; mt++) mma16x3(acc[mt][nt], ah[mt], al[mt], bc[nt].x, bc[nt].y, bc[nt].z, bc[nt].w);
+      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], al[mt], bc[nt].x, bc[nt].y);
+#pragma unroll
+    for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], ah[mt], bc[nt].z, bc[nt].w);
+#pragma unroll
+    for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], ah[mt], bc[nt].x, bc[nt].y);
     if (ks + 1 < ksteps) {
 #pragma unroll
       for (int nt = 0; nt < NTW; nt++) bc[nt] = bn[nt];
@@ -177,30 +173,37 @@ __device__ __forceinline__ void gemm_tt(float (&acc)[MT][NTW][4], const SArr& A,
       ldsm4t(ah[mt], a_lane + ks * 16 * A.ldb + mt * 32);
       ldsm4t(al[mt], a_lane + ks * 16 * A.ldb + mt * 32 + A.lo);
     }
+    uint32_t bh[NTW][2], bl[NTW][2];
 #pragma unroll
     for (int nt = 0; nt + 1 < NTW; nt += 2) {
-      uint32_t bh[4], bl[4];
-      ldsm4t(bh, b_lane + ks * 16 * B.ldb + nt * 16);
-      ldsm4t(bl, b_lane + ks * 16 * B.ldb + nt * 16 + B.lo);
-#pragma unroll
-      for (int mt = 0; mt < MT; mt++) {
-        mma16x3(acc[mt][nt], ah[mt], al[mt], bh[0], bh[1], bl[0], bl[1]);
-        mma16x3(acc[mt][nt + 1], ah[mt], al[mt], bh[2], bh[3], bl[2], bl[3]);
-      }
+      uint32_t h4[4], l4[4];
+      ldsm4t(h4, b_lane + ks * 16 * B.ldb + nt * 16);
+      ldsm4t(l4, b_lane + ks * 16 * B.ldb + nt * 16 + B.lo);
+      bh[nt][0] = h4[0]; bh[nt][1] = h4[1]; bh[nt + 1][0] = h4[2]; bh[nt + 1][1] = h4[3];
+      bl[nt][0] = l4[0]; bl[nt][1] = l4[1]; bl[nt + 1][0] = l4[2]; bl[nt + 1][1] = l4[3];
     }
     if (NTW & 1) {
-      constexpr int nt = NTW - 1;
-      uint32_t bh[2], bl[2];
-      ldsm2t(bh, b_lane2 + ks * 16 * B.ldb + nt * 16);
-      ldsm2t(bl, b_lane2 + ks * 16 * B.ldb + nt * 16 + B.lo);
-#pragma unroll
-      for (int mt = 0; mt < MT; mt++) mma16x3(acc[mt][nt], ah[mt], al[mt], bh[0], bh[1], bl[0], bl[1]);
+      ldsm2t(bh[NTW - 1], b_lane2 + ks * 16 * B.ldb + (NTW - 1) * 16);
+      ldsm2t(bl[NTW - 1], b_lane2 + ks * 16 * B.ldb + (NTW - 1) * 16 + B.lo);
     }
+#pragma unroll
+    for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], al[mt], bh[nt][0], bh[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], ah[mt], bl[nt][0], bl[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
   }
 }
 
 // s[nt] += A(16 rows at a_row0, k over [kcol, kcol+DH)) * Bt where B is stored [n][k] ("nk": rows = output
-// columns).  8 output tiles (64 columns) in pairs; DH = 16*a + 8*b.
+// columns).  8 output tiles (64 columns) in pairs; DH = 16*a + 8*b.  MMAs are issued pass-major so that
+// consecutive instructions never share an accumulator.
 template <int DH>
 __device__ __forceinline__ void gemm_rowk_nk(float (&s)[8][4], const SArr& A, int a_row0, const SArr& B, int kcol,
                                              int npairs, int lane) {
@@ -208,38 +211,79 @@ __device__ __forceinline__ void gemm_rowk_nk(float (&s)[8][4], const SArr& A, in
   const uint32_t b_lane = B.addr + ((lane & 7) + (lane >> 4) * 8) * B.ldb + (kcol + ((lane >> 3) & 1) * 8) * 2;
 #pragma unroll
   for (int kk = 0; kk < DH / 16; kk++) {
-    uint32_t ah[4], al[4];
+    uint32_t ah[4], al[4], bh[4][4], bl[4][4];
     ldsm4(ah, a_lane + kk * 32);
     ldsm4(al, a_lane + kk * 32 + A.lo);
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
+    for (int p = 0; p < 4; p++)
       if (p < npairs) {
-        uint32_t bh[4], bl[4];
-        ldsm4(bh, b_lane + p * 16 * B.ldb + kk * 32);
-        ldsm4(bl, b_lane + p * 16 * B.ldb + kk * 32 + B.lo);
-        mma16x3(s[2 * p], ah, al, bh[0], bh[1], bl[0], bl[1]);
-        mma16x3(s[2 * p + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+        ldsm4(bh[p], b_lane + p * 16 * B.ldb + kk * 32);
+        ldsm4(bl[p], b_lane + p * 16 * B.ldb + kk * 32 + B.lo);
       }
-    }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+      if (p < npairs) { mma16(s[2 * p], al, bh[p][0], bh[p][1]); mma16(s[2 * p + 1], al, bh[p][2], bh[p][3]); }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+      if (p < npairs) { mma16(s[2 * p], ah, bl[p][0], bl[p][1]); mma16(s[2 * p + 1], ah, bl[p][2], bl[p][3]); }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+      if (p < npairs) { mma16(s[2 * p], ah, bh[p][0], bh[p][1]); mma16(s[2 * p + 1], ah, bh[p][2], bh[p][3]); }
   }
   if (DH % 16) {
     constexpr int k0 = (DH / 16) * 16;
     const uint32_t a2 = A.addr + (a_row0 + (lane & 15)) * A.ldb + (kcol + k0) * 2;
     const uint32_t b2 = B.addr + (lane & 15) * B.ldb + (kcol + k0) * 2;
-    uint32_t ah[2], al[2];
+    uint32_t ah[2], al[2], bh[4][2], bl[4][2];
     ldsm2(ah, a2);
     ldsm2(al, a2 + A.lo);
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
+    for (int p = 0; p < 4; p++)
       if (p < npairs) {
-        uint32_t bh[2], bl[2];
-        ldsm2(bh, b2 + p * 16 * B.ldb);
-        ldsm2(bl, b2 + p * 16 * B.ldb + B.lo);
-        mma8x3(s[2 * p], ah, al, bh[0], bl[0]);
-        mma8x3(s[2 * p + 1], ah, al, bh[1], bl[1]);
+        ldsm2(bh[p], b2 + p * 16 * B.ldb);
+        ldsm2(bl[p], b2 + p * 16 * B.ldb + B.lo);
       }
-    }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+      if (p < npairs) { mma8(s[2 * p], al[0], al[1], bh[p][0]); mma8(s[2 * p + 1], al[0], al[1], bh[p][1]); }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+      if (p < npairs) { mma8(s[2 * p], ah[0], ah[1], bl[p][0]); mma8(s[2 * p + 1], ah[0], ah[1], bl[p][1]); }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+      if (p < npairs) { mma8(s[2 * p], ah[0], ah[1], bh[p][0]); mma8(s[2 * p + 1], ah[0], ah[1], bh[p][1]); }
   }
+}
+
+// B fragments of NDT n8 tiles at columns ncol.. of a [k][n] ("kn") operand for one k16 step
+template <int NDT>
+__device__ __forceinline__ void load_b_kn(uint32_t (&bh)[NDT][2], uint32_t (&bl)[NDT][2], const SArr& B, uint32_t b_lane,
+                                          uint32_t b_lane2, int kk) {
+#pragma unroll
+  for (int nd = 0; nd + 1 < NDT; nd += 2) {
+    uint32_t h4[4], l4[4];
+    ldsm4t(h4, b_lane + kk * 16 * B.ldb + nd * 16);
+    ldsm4t(l4, b_lane + kk * 16 * B.ldb + nd * 16 + B.lo);
+    bh[nd][0] = h4[0]; bh[nd][1] = h4[1]; bh[nd + 1][0] = h4[2]; bh[nd + 1][1] = h4[3];
+    bl[nd][0] = l4[0]; bl[nd][1] = l4[1]; bl[nd + 1][0] = l4[2]; bl[nd + 1][1] = l4[3];
+  }
+  if (NDT & 1) {
+    ldsm2t(bh[NDT - 1], b_lane2 + kk * 16 * B.ldb + (NDT - 1) * 16);
+    ldsm2t(bl[NDT - 1], b_lane2 + kk * 16 * B.ldb + (NDT - 1) * 16 + B.lo);
+  }
+}
+// the three passes of one k16 step on NDT output tiles; the small cross terms accumulate in `os`, hi*hi in `o`,
+// so the dependent chain per accumulator is one MMA per k-step per set
+template <int NDT>
+__device__ __forceinline__ void mma_passes(float (&o)[NDT][4], float (&os)[NDT][4], const uint32_t (&ah)[4],
+                                           const uint32_t (&al)[4], const uint32_t (&bh)[NDT][2],
+                                           const uint32_t (&bl)[NDT][2]) {
+#pragma unroll
+  for (int nd = 0; nd < NDT; nd++) mma16(os[nd], al, bh[nd][0], bh[nd][1]);
+#pragma unroll
+  for (int nd = 0; nd < NDT; nd++) mma16(o[nd], ah, bh[nd][0], bh[nd][1]);
+#pragma unroll
+  for (int nd = 0; nd < NDT; nd++) mma16(os[nd], ah, bl[nd][0], bl[nd][1]);
 }
 
 // o[nd] += A(16 rows at a_row0, k = tokens 0..16*ksteps) * B where B is stored [k][n] ("kn"), columns
@@ -251,26 +295,20 @@ __device__ __forceinline__ void gemm_rowk_kn(float (&o)[DH / 8][4], const SArr& 
   const uint32_t a_lane = A.addr + (a_row0 + (lane & 15)) * A.ldb + ((lane >> 4) * 8) * 2;
   const uint32_t b_lane = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + (ncol + (lane >> 4) * 8) * 2;
   const uint32_t b_lane2 = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + ncol * 2;
+  float os[NDT][4];
+#pragma unroll
+  for (int nd = 0; nd < NDT; nd++) os[nd][0] = os[nd][1] = os[nd][2] = os[nd][3] = 0.f;
   for (int kk = 0; kk < ksteps; kk++) {
-    uint32_t ah[4], al[4];
+    uint32_t ah[4], al[4], bh[NDT][2], bl[NDT][2];
     ldsm4(ah, a_lane + kk * 32);
     ldsm4(al, a_lane + kk * 32 + A.lo);
-#pragma unroll
-    for (int nd = 0; nd + 1 < NDT; nd += 2) {
-      uint32_t bh[4], bl[4];
-      ldsm4t(bh, b_lane + kk * 16 * B.ldb + nd * 16);
-      ldsm4t(bl, b_lane + kk * 16 * B.ldb + nd * 16 + B.lo);
-      mma16x3(o[nd], ah, al, bh[0], bh[1], bl[0], bl[1]);
-      mma16x3(o[nd + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
-    }
-    if (NDT & 1) {
-      constexpr int nd = NDT - 1;
-      uint32_t bh[2], bl[2];
-      ldsm2t(bh, b_lane2 + kk * 16 * B.ldb + nd * 16);
-      ldsm2t(bl, b_lane2 + kk * 16 * B.ldb + nd * 16 + B.lo);
-      mma16x3(o[nd], ah, al, bh[0], bh[1], bl[0], bl[1]);
-    }
+    load_b_kn<NDT>(bh, bl, B, b_lane, b_lane2, kk);
+    mma_passes<NDT>(o, os, ah, al, bh, bl);
   }
+#pragma unroll
+  for (int nd = 0; nd < NDT; nd++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) o[nd][c] += os[nd][c];
 }
 
 // o[nd] += A^T(16 output rows = columns m0.. of SA, k = rows of SA) * B ("kn"): both stored [k][*]
@@ -281,54 +319,113 @@ __device__ __forceinline__ void gemm_colk_kn(float (&o)[DH / 8][4], const SArr& 
   const uint32_t a_lane = A.addr + ((lane & 7) + ((lane >> 4) & 1) * 8) * A.ldb + (m0 + ((lane >> 3) & 1) * 8) * 2;
   const uint32_t b_lane = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + (ncol + (lane >> 4) * 8) * 2;
   const uint32_t b_lane2 = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + ncol * 2;
+  float os[NDT][4];
+#pragma unroll
+  for (int nd = 0; nd < NDT; nd++) os[nd][0] = os[nd][1] = os[nd][2] = os[nd][3] = 0.f;
   for (int kk = 0; kk < ksteps; kk++) {
-    uint32_t ah[4], al[4];
+    uint32_t ah[4], al[4], bh[NDT][2], bl[NDT][2];
     ldsm4t(ah, a_lane + kk * 16 * A.ldb);
     ldsm4t(al, a_lane + kk * 16 * A.ldb + A.lo);
-#pragma unroll
-    for (int nd = 0; nd + 1 < NDT; nd += 2) {
-      uint32_t bh[4], bl[4];
-      ldsm4t(bh, b_lane + kk * 16 * B.ldb + nd * 16);
-      ldsm4t(bl, b_lane + kk * 16 * B.ldb + nd * 16 + B.lo);
-      mma16x3(o[nd], ah, al, bh[0], bh[1], bl[0], bl[1]);
-      mma16x3(o[nd + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
-    }
-    if (NDT & 1) {
-      constexpr int nd = NDT - 1;
-      uint32_t bh[2], bl[2];
-      ldsm2t(bh, b_lane2 + kk * 16 * B.ldb + nd * 16);
-      ldsm2t(bl, b_lane2 + kk * 16 * B.ldb + nd * 16 + B.lo);
-      mma16x3(o[nd], ah, al, bh[0], bh[1], bl[0], bl[1]);
-    }
+    load_b_kn<NDT>(bh, bl, B, b_lane, b_lane2, kk);
+    mma_passes<NDT>(o, os, ah, al, bh, bl);
   }
+#pragma unroll
+  for (int nd = 0; nd < NDT; nd++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) o[nd][c] += os[nd][c];
+}
+
+// ---------------------------------------------------------------- async bulk copies (TMA, 1-D) + mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 24); ++it) {     // bounded: a protocol bug traps instead of hanging the GPU
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global (bulk async-group of the issuing thread)
+__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// GELU (exact-erf form, net/activation.py:139-148) and its derivative from one shared exponential.
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): erf(s) = 1 - (a1 t + .. + a5 t^5) exp(-s^2), t = 1/(1 + p|s|).
+__device__ __forceinline__ void gelu_both(float x, float& y, float& dy) {
+  const float s = x * 0.70710678118654752f;
+  const float e = __expf(-s * s);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, fabsf(s), 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float er = copysignf(fmaf(-poly * t, e, 1.0f), s);
+  const float cdf = fmaf(0.5f, er, 0.5f);
+  y = x * cdf;
+  dy = fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
+// interleaved butterfly reductions of R independent values (ILP across the rows a warp owns)
+template <int R>
+__device__ __forceinline__ void warp_sum_multi(float (&v)[R]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < R; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
 }
 
 // LayerNorm of rows of a global [N][D] fp32 tensor into a split shared operand (net/layernorm.py:100-114);
-// rows >= N are zero-filled.  One warp per row; mean / rstd optionally kept for the backward formula.
+// rows >= N are zero-filled.  A warp owns rows warp, warp+8, ...; all of them are loaded and reduced together.
+// mean / rstd go to shared memory when requested (the backward formula needs them).
 template <int D>
 __device__ __forceinline__ void ln_rows(const float* src, const float* __restrict__ gamma, const float* __restrict__ beta,
                                         const SArr& dst, int N, float* s_mean, float* s_rstd, int warp, int lane) {
-  constexpr int E = D / 32;
-  float gm[E], bt[E];
+  constexpr int E = D / 32, RPW = ROWS / 8;
+  float gm[E], bt[E], v[RPW][E], s[RPW], q[RPW];
 #pragma unroll
   for (int e = 0; e < E; e++) { gm[e] = __ldg(gamma + lane + 32 * e); bt[e] = __ldg(beta + lane + 32 * e); }
-  for (int r = warp; r < ROWS; r += 8) {
-    if (r < N) {
-      float v[E], s = 0.f;
 #pragma unroll
-      for (int e = 0; e < E; e++) { v[e] = src[r * D + lane + 32 * e]; s += v[e]; }
-      const float mean = warp_sum(s) * (1.0f / D);
-      float q = 0.f;
+  for (int i = 0; i < RPW; i++) {
+    const int r = warp + 8 * i;
+    s[i] = 0.f;
 #pragma unroll
-      for (int e = 0; e < E; e++) { const float d = v[e] - mean; q += d * d; }
-      const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
-      if (s_mean && lane == 0) { s_mean[r] = mean; s_rstd[r] = rstd; }
+    for (int e = 0; e < E; e++) { v[i][e] = r < N ? src[r * D + lane + 32 * e] : 0.f; s[i] += v[i][e]; }
+  }
+  warp_sum_multi<RPW>(s);
 #pragma unroll
-      for (int e = 0; e < E; e++) st1(dst, r, lane + 32 * e, (v[e] - mean) * rstd * gm[e] + bt[e]);
-    } else {
+  for (int i = 0; i < RPW; i++) {
+    s[i] *= (1.0f / D);
+    q[i] = 0.f;
 #pragma unroll
-      for (int e = 0; e < E; e++) st1(dst, r, lane + 32 * e, 0.f);
-    }
+    for (int e = 0; e < E; e++) { v[i][e] -= s[i]; q[i] += v[i][e] * v[i][e]; }
+  }
+  warp_sum_multi<RPW>(q);
+#pragma unroll
+  for (int i = 0; i < RPW; i++) {
+    const int r = warp + 8 * i;
+    const float rstd = rsqrtf(q[i] * (1.0f / D) + 1e-5f);
+    if (s_mean && lane == 0) { s_mean[r] = s[i]; s_rstd[r] = rstd; }
+#pragma unroll
+    for (int e = 0; e < E; e++) st1(dst, r, lane + 32 * e, r < N ? v[i][e] * rstd * gm[e] + bt[e] : 0.f);
   }
 }
 
@@ -341,37 +438,51 @@ __device__ __forceinline__ void ln_bwd_rows(const float* dy, const float* xin, c
                                             const float* addend, float* out, const SArr& dst, int N,
                                             const float* s_mean, const float* s_rstd, float* dgamma, float* dbeta,
                                             float* dbias_addend, int warp, int lane) {
-  constexpr int E = D / 32;
+  constexpr int E = D / 32, RPW = ROWS / 8;
   float gm[E], ag[E], ab[E], aa[E];
 #pragma unroll
   for (int e = 0; e < E; e++) { gm[e] = __ldg(gamma + lane + 32 * e); ag[e] = ab[e] = aa[e] = 0.f; }
-  for (int r = warp; r < ROWS; r += 8) {
-    if (r < N) {
-      const float mu = s_mean[r], rs = s_rstd[r];
-      float g[E], xh[E], s1 = 0.f, s2 = 0.f;
+  float g[RPW][E], xh[RPW][E], va[RPW][E], s1[RPW], s2[RPW], rs[RPW];
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const float d = dy[r * D + lane + 32 * e];
-        xh[e] = (xin[r * D + lane + 32 * e] - mu) * rs;
-        g[e] = gm[e] * d;
-        s1 += g[e];
-        s2 += g[e] * xh[e];
-        ag[e] += xh[e] * d;
-        ab[e] += d;
-      }
-      s1 = warp_sum(s1) * (1.0f / D);
-      s2 = warp_sum(s2) * (1.0f / D);
+  for (int i = 0; i < RPW; i++) {
+    const int r = warp + 8 * i;
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const float a = addend[r * D + lane + 32 * e];
-        aa[e] += a;
-        const float o = a + rs * (g[e] - s1 - xh[e] * s2);
-        out[r * D + lane + 32 * e] = o;
-        st1(dst, r, lane + 32 * e, o);
-      }
-    } else {
+    for (int e = 0; e < E; e++) {
+      const int o = r * D + lane + 32 * e;
+      g[i][e] = r < N ? dy[o] : 0.f;
+      xh[i][e] = r < N ? xin[o] : 0.f;
+      va[i][e] = r < N ? addend[o] : 0.f;
+    }
+  }
 #pragma unroll
-      for (int e = 0; e < E; e++) st1(dst, r, lane + 32 * e, 0.f);
+  for (int i = 0; i < RPW; i++) {
+    const int r = warp + 8 * i;
+    const float mu = s_mean[r];
+    rs[i] = s_rstd[r];
+    s1[i] = s2[i] = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const float d = g[i][e];
+      xh[i][e] = r < N ? (xh[i][e] - mu) * rs[i] : 0.f;
+      ag[e] += xh[i][e] * d;
+      ab[e] += d;
+      aa[e] += va[i][e];
+      g[i][e] = gm[e] * d;
+      s1[i] += g[i][e];
+      s2[i] += g[i][e] * xh[i][e];
+    }
+  }
+  warp_sum_multi<RPW>(s1);
+  warp_sum_multi<RPW>(s2);
+#pragma unroll
+  for (int i = 0; i < RPW; i++) {
+    const int r = warp + 8 * i;
+    const float m1 = s1[i] * (1.0f / D), m2 = s2[i] * (1.0f / D);
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const float o = va[i][e] + rs[i] * (g[i][e] - m1 - xh[i][e] * m2);
+      if (r < N) out[r * D + lane + 32 * e] = o;
+      st1(dst, r, lane + 32 * e, r < N ? o : 0.f);
     }
   }
 #pragma unroll
@@ -407,10 +518,19 @@ struct Cfg {
   static constexpr int B_FC0 = B_QKV + 3 * D * D / 4;
   static constexpr int B_FC1 = B_FC0 + 2 * D * D / 4;
   static constexpr int F_TOTAL = B_FC1 + 2 * D * D / 4;     // = 3.5 D^2 uint4 = 8 bytes per weight
-  static constexpr size_t FWD_SMEM = 4 * (size_t)ARR + 8 * (size_t)PW;
-  static constexpr size_t BWD_SMEM = 4 * (size_t)ARR + 4 * (size_t)PARR + 2 * ROWS * sizeof(float);
+  // per-image operand save area written by the forward, bulk-loaded by the backward (bytes):
+  // split LN(x) | split q,k,v | split LN1(h) | split GELU(pre2) | mean, rstd of LN and LN1
+  static constexpr int SV_U = 0;
+  static constexpr int SV_QKV = SV_U + ARR;
+  static constexpr int SV_U1 = SV_QKV + 3 * ARR;
+  static constexpr int SV_G = SV_U1 + ARR;
+  static constexpr int SV_STAT = SV_G + ARR2;
+  static constexpr int SV_BYTES = SV_STAT + 4 * ROWS * (int)sizeof(float);
+  static constexpr size_t FWD_SMEM = 4 * (size_t)ARR + 8 * (size_t)PW + 4 * ROWS * sizeof(float);
+  static constexpr size_t BWD_SMEM = 4 * (size_t)ARR + 4 * (size_t)PARR + 4 * ROWS * sizeof(float) + 16;
   static_assert(D % 32 == 0 && DH % 8 == 0 && DH * H == D, "fused ViT block: D % 32 == 0, dh % 8 == 0");
   static_assert(ARR2 <= 2 * ARR && ARR2 <= 4 * PARR && ARR <= 4 * PARR, "aliasing plan");
+  static_assert(ARR % 16 == 0 && ARR2 % 16 == 0 && SV_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 };
 
 // ---------------------------------------------------------------- weight pre-split
@@ -467,17 +587,21 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
   const SArr sV = make_arr(smem + 3 * C::ARR, C::LD);
   const SArr sG = make_arr(smem + C::ARR, C::LD2);                       // aliases sQ|sK after attention
   const SArr sPw = make_arr(smem + 4 * C::ARR + warp * C::PW, LDP, 16);  // this warp's P tile
+  float* s_stat = reinterpret_cast<float*>(smem + 4 * C::ARR + 8 * C::PW);   // mean, rstd (LN) | mean, rstd (LN1)
   const int NTK = (N + 7) >> 3, NPAIR = (NTK + 1) >> 1, KT = (N + 15) >> 4;
-  const float scale = 1.0f / sqrtf((float)DH);
+  const float scale = rsqrtf((float)DH);
   const size_t img = (size_t)b * N * D;
   const float* xcur = a.x + img;
 
   for (int bi = 0; bi < a.nblocks; bi++) {
     const NtVitBlock& P = a.blk[bi];
     const uint4* wf = reinterpret_cast<const uint4*>(P.wfrag);
+    char* sv = reinterpret_cast<char*>(P.save) + (size_t)b * C::SV_BYTES;
     // ---- u = LN(x)                                                      attention.py:22
-    ln_rows<D>(xcur, P.ln_g, P.ln_b, sU, N, nullptr, nullptr, warp, lane);
+    ln_rows<D>(xcur, P.ln_g, P.ln_b, sU, N, s_stat, s_stat + ROWS, warp, lane);
+    fence_async_smem();
     __syncthreads();
+    if (tid == 0) bulk_store(sv + C::SV_U, sU.ptr, C::ARR);               // operand of dWqkv in the backward
     // ---- qkv = u Wqkv + b                                               attention.py:23-24
     {
       constexpr int NTW = 3 * D / 32;
@@ -487,25 +611,29 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
       gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sU.lo, 16 * sU.ldb, D / 16,
                       wf + C::F_QKV + (wn * NTW) * 32 + lane, (3 * D / 8) * 32);
       float* qg = P.qkv + (size_t)b * N * 3 * D;
+      float2 bb[NTW];
+#pragma unroll
+      for (int nt = 0; nt < NTW; nt++) bb[nt] = __ldg(reinterpret_cast<const float2*>(P.bqkv + (wn * NTW + nt) * 8 + 2 * t));
 #pragma unroll
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
         for (int nt = 0; nt < NTW; nt++) {
           const int col = (wn * NTW + nt) * 8 + 2 * t;
-          const float2 bb = __ldg(reinterpret_cast<const float2*>(P.bqkv + col));
           const int which = col / D, cc = col - which * D;
           const SArr& dst = which == 0 ? sQ : (which == 1 ? sK : sV);
 #pragma unroll
           for (int hf = 0; hf < 2; hf++) {
             const int row = wm * 32 + mt * 16 + g + hf * 8;
-            float v0 = acc[mt][nt][2 * hf] + bb.x, v1 = acc[mt][nt][2 * hf + 1] + bb.y;
+            float v0 = acc[mt][nt][2 * hf] + bb[nt].x, v1 = acc[mt][nt][2 * hf + 1] + bb[nt].y;
             if (row < N) *reinterpret_cast<float2*>(qg + (size_t)row * 3 * D + col) = make_float2(v0, v1);
             else v0 = v1 = 0.f;
             st2(dst, row, cc, v0, v1);
           }
         }
     }
+    fence_async_smem();
     __syncthreads();
+    if (tid == 0) bulk_store(sv + C::SV_QKV, sQ.ptr, 3 * C::ARR);         // q, k, v operands of the attention backward
     // ---- attention, one (head, 16-query tile) per warp pass              attention.py:31-45
     for (int item = warp; item < 4 * H; item += 8) {
       const int hd = item >> 2, i0 = (item & 3) * 16;
@@ -530,14 +658,14 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
-        s[nt][0] = expf(s[nt][0] - mx0); s[nt][1] = expf(s[nt][1] - mx0);
-        s[nt][2] = expf(s[nt][2] - mx1); s[nt][3] = expf(s[nt][3] - mx1);
+        s[nt][0] = __expf(s[nt][0] - mx0); s[nt][1] = __expf(s[nt][1] - mx0);
+        s[nt][2] = __expf(s[nt][2] - mx1); s[nt][3] = __expf(s[nt][3] - mx1);
         s0 += s[nt][0] + s[nt][1];
         s1 += s[nt][2] + s[nt][3];
       }
       s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
       s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      const float inv0 = r0 < N ? 1.0f / s0 : 0.f, inv1 = r1 < N ? 1.0f / s1 : 0.f;
+      const float inv0 = r0 < N ? __fdividef(1.0f, s0) : 0.f, inv1 = r1 < N ? __fdividef(1.0f, s1) : 0.f;
       float* pg = P.P + ((size_t)b * H + hd) * N * N;
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
@@ -554,24 +682,28 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
       for (int nd = 0; nd < DH / 8; nd++) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
       gemm_rowk_kn<DH>(o, sPw, 0, sV, hd * DH, KT, lane);
       float* hg = P.h + img;
+      float2 xr0[DH / 8], xr1[DH / 8];
 #pragma unroll
       for (int nd = 0; nd < DH / 8; nd++) {
         const int col = hd * DH + nd * 8 + 2 * t;
-        if (r0 < N) {
-          const float2 xr = *reinterpret_cast<const float2*>(xcur + r0 * D + col);
-          *reinterpret_cast<float2*>(hg + r0 * D + col) = make_float2(xr.x + o[nd][0], xr.y + o[nd][1]);   // attention.py:46
-        }
-        if (r1 < N) {
-          const float2 xr = *reinterpret_cast<const float2*>(xcur + r1 * D + col);
-          *reinterpret_cast<float2*>(hg + r1 * D + col) = make_float2(xr.x + o[nd][2], xr.y + o[nd][3]);
-        }
+        xr0[nd] = r0 < N ? *reinterpret_cast<const float2*>(xcur + r0 * D + col) : make_float2(0.f, 0.f);
+        xr1[nd] = r1 < N ? *reinterpret_cast<const float2*>(xcur + r1 * D + col) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int nd = 0; nd < DH / 8; nd++) {
+        const int col = hd * DH + nd * 8 + 2 * t;
+        if (r0 < N) *reinterpret_cast<float2*>(hg + r0 * D + col) = make_float2(xr0[nd].x + o[nd][0], xr0[nd].y + o[nd][1]);   // attention.py:46
+        if (r1 < N) *reinterpret_cast<float2*>(hg + r1 * D + col) = make_float2(xr1[nd].x + o[nd][2], xr1[nd].y + o[nd][3]);
       }
       __syncwarp();
     }
+    if (tid == 0) bulk_store_wait_read();        // the bulk stores have finished READING sU / sQ|sK|sV
     __syncthreads();
     // ---- u1 = LN1(h)                                                     attention.py:48
-    ln_rows<D>(P.h + img, P.ln1_g, P.ln1_b, sU, N, nullptr, nullptr, warp, lane);
+    ln_rows<D>(P.h + img, P.ln1_g, P.ln1_b, sU, N, s_stat + 2 * ROWS, s_stat + 3 * ROWS, warp, lane);
+    fence_async_smem();
     __syncthreads();
+    if (tid == 0) bulk_store(sv + C::SV_U1, sU.ptr, C::ARR);              // operand of dW0 in the backward
     // ---- pre2 = u1 W0 + b0 ; G = GELU(pre2)                              attention.py:49-50
     {
       constexpr int NTW = 2 * D / 32;
@@ -580,28 +712,34 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
       const uint32_t a_lane = sU.addr + (wm * 32 + (lane & 15)) * sU.ldb + ((lane >> 4) * 8) * 2;
       gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sU.lo, 16 * sU.ldb, D / 16,
                       wf + C::F_FC0 + (wn * NTW) * 32 + lane, (2 * D / 8) * 32);
-      float* pg = P.pre2 + (size_t)b * N * 2 * D;
+      float* dg = P.dgelu + (size_t)b * N * 2 * D;
+      float2 bb[NTW];
+#pragma unroll
+      for (int nt = 0; nt < NTW; nt++) bb[nt] = __ldg(reinterpret_cast<const float2*>(P.b0 + (wn * NTW + nt) * 8 + 2 * t));
 #pragma unroll
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
         for (int nt = 0; nt < NTW; nt++) {
           const int col = (wn * NTW + nt) * 8 + 2 * t;
-          const float2 bb = __ldg(reinterpret_cast<const float2*>(P.b0 + col));
 #pragma unroll
           for (int hf = 0; hf < 2; hf++) {
             const int row = wm * 32 + mt * 16 + g + hf * 8;
-            float v0 = acc[mt][nt][2 * hf] + bb.x, v1 = acc[mt][nt][2 * hf + 1] + bb.y;
+            float y0 = 0.f, y1 = 0.f;
             if (row < N) {
-              *reinterpret_cast<float2*>(pg + (size_t)row * 2 * D + col) = make_float2(v0, v1);
-              v0 = gelu_f(v0); v1 = gelu_f(v1);
-            } else {
-              v0 = v1 = 0.f;
+              float d0, d1;
+              gelu_both(acc[mt][nt][2 * hf] + bb[nt].x, y0, d0);
+              gelu_both(acc[mt][nt][2 * hf + 1] + bb[nt].y, y1, d1);
+              *reinterpret_cast<float2*>(dg + (size_t)row * 2 * D + col) = make_float2(d0, d1);   // GELU'(pre2) for the backward
             }
-            st2(sG, row, col, v0, v1);
+            st2(sG, row, col, y0, y1);
           }
         }
     }
+    fence_async_smem();
     __syncthreads();
+    if (tid == 0) bulk_store(sv + C::SV_G, sG.ptr, C::ARR2);              // operand of dW1 in the backward
+    if (tid < 4 * ROWS / 4)                                                // LN / LN1 statistics for the backward formula
+      reinterpret_cast<float4*>(sv + C::SV_STAT)[tid] = reinterpret_cast<const float4*>(s_stat)[tid];
     // ---- out = h + G W1 + b1                                              attention.py:51-53
     {
       constexpr int NTW = D / 32;
@@ -612,26 +750,35 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
                       wf + C::F_FC1 + (wn * NTW) * 32 + lane, (D / 8) * 32);
       const float* hg = P.h + img;
       float* og = P.out + img;
+      float2 bb[NTW], hr[2][NTW][2];
+#pragma unroll
+      for (int nt = 0; nt < NTW; nt++) bb[nt] = __ldg(reinterpret_cast<const float2*>(P.b1 + (wn * NTW + nt) * 8 + 2 * t));
 #pragma unroll
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-        for (int nt = 0; nt < NTW; nt++) {
-          const int col = (wn * NTW + nt) * 8 + 2 * t;
-          const float2 bb = __ldg(reinterpret_cast<const float2*>(P.b1 + col));
+        for (int nt = 0; nt < NTW; nt++)
 #pragma unroll
           for (int hf = 0; hf < 2; hf++) {
-            const int row = wm * 32 + mt * 16 + g + hf * 8;
-            if (row < N) {
-              const float2 hr = *reinterpret_cast<const float2*>(hg + row * D + col);
-              *reinterpret_cast<float2*>(og + row * D + col) =
-                  make_float2(acc[mt][nt][2 * hf] + bb.x + hr.x, acc[mt][nt][2 * hf + 1] + bb.y + hr.y);
-            }
+            const int row = wm * 32 + mt * 16 + g + hf * 8, col = (wn * NTW + nt) * 8 + 2 * t;
+            hr[mt][nt][hf] = row < N ? *reinterpret_cast<const float2*>(hg + row * D + col) : make_float2(0.f, 0.f);
           }
-        }
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            const int row = wm * 32 + mt * 16 + g + hf * 8, col = (wn * NTW + nt) * 8 + 2 * t;
+            if (row < N)
+              *reinterpret_cast<float2*>(og + row * D + col) =
+                  make_float2(acc[mt][nt][2 * hf] + bb[nt].x + hr[mt][nt][hf].x, acc[mt][nt][2 * hf + 1] + bb[nt].y + hr[mt][nt][hf].y);
+          }
     }
+    if (tid == 0) bulk_store_wait_read();        // sU / sG may be overwritten by the next block
     __syncthreads();
     xcur = P.out + img;
   }
+  if (tid == 0) bulk_store_wait_all();
 }
 
 // ---------------------------------------------------------------- backward
@@ -644,14 +791,14 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;
   const int N = a.N, b = blockIdx.x;
-  // regions: R_D | R_Q | R_K | R_V | R_PS(4 score planes) | stats
+  // regions: R_D | R_Q | R_K | R_V | R_PS(4 score planes) | stats | mbarrier
   char* rD = smem;
   char* rQ = smem + C::ARR;
   char* rK = smem + 2 * C::ARR;
   char* rV = smem + 3 * C::ARR;
   char* rPS = smem + 4 * C::ARR;
-  float* s_mean = reinterpret_cast<float*>(smem + 4 * C::ARR + 4 * C::PARR);
-  float* s_rstd = s_mean + ROWS;
+  float* s_stat = reinterpret_cast<float*>(smem + 4 * C::ARR + 4 * C::PARR);   // mean, rstd (LN) | mean, rstd (LN1)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_stat + 4 * ROWS);
   const SArr sD = make_arr(rD, C::LD);
   const SArr sQ = make_arr(rQ, C::LD), sK = make_arr(rK, C::LD), sV = make_arr(rV, C::LD);
   const SArr sU1 = make_arr(rQ, C::LD);          // MLP phase: LN1(h)
@@ -660,27 +807,38 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
   const SArr sU = make_arr(rPS, C::LD);          // QKV phase: LN(x)
   const int KT = (N + 15) >> 4;                  // k16 steps over tokens
   const int NTK = (N + 7) >> 3, NPAIR = (NTK + 1) >> 1;
-  const float scale = 1.0f / sqrtf((float)DH);
+  const float scale = rsqrtf((float)DH);
   const size_t img = (size_t)b * N * D;
   float* dh = a.dh + img;
   float* tmp = a.tmp + img;
   float* dxo = a.dx + img;
   const float* dcur = a.dout + img;
+  uint32_t parity = 0;
 
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   // incoming gradient -> split operand
   for (int r = warp; r < ROWS; r += 8)
 #pragma unroll
     for (int e = 0; e < D / 32; e++) st1(sD, r, lane + 32 * e, r < N ? dcur[r * D + lane + 32 * e] : 0.f);
+  __syncthreads();
 
   for (int bi = a.nblocks - 1; bi >= 0; bi--) {
     const NtVitBlock& P = a.blk[bi];
     const uint4* wf = reinterpret_cast<const uint4*>(P.wfrag);
     const float* xin = (bi ? a.blk[bi - 1].out : a.x) + img;
     const float* hg = P.h + img;
-    // ---- S0: recompute u1 = LN1(h) (operand of dW0) and its row statistics
-    ln_rows<D>(hg, P.ln1_g, P.ln1_b, sU1, N, s_mean, s_rstd, warp, lane);
-    __syncthreads();
-    // ---- S1: dG = d W1^T ; dpre = dG * gelu'(pre2) ; G = gelu(pre2)        attention.py:58-59
+    const char* sv = reinterpret_cast<const char*>(P.save) + (size_t)b * C::SV_BYTES;
+    // ---- S0: operands the forward saved: u1 = LN1(h) -> R_Q, G = GELU(pre2) -> R_PS (async), LN statistics
+    if (tid == 0) {
+      mbar_expect_tx(bar, C::ARR + C::ARR2);
+      bulk_load(rQ, sv + C::SV_U1, C::ARR, bar);
+      bulk_load(rPS, sv + C::SV_G, C::ARR2, bar);
+    }
+    if (tid < 4 * ROWS / 4) reinterpret_cast<float4*>(s_stat)[tid] = reinterpret_cast<const float4*>(sv + C::SV_STAT)[tid];
+    // ---- S1: dG = d W1^T ; dpre = dG * gelu'(pre2)                          attention.py:58-59
     {
       constexpr int NTW = 2 * D / 32;
       float acc[2][NTW][4];
@@ -688,7 +846,17 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
       const uint32_t a_lane = sD.addr + (wm * 32 + (lane & 15)) * sD.ldb + ((lane >> 4) * 8) * 2;
       gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sD.lo, 16 * sD.ldb, D / 16,
                       wf + C::B_FC1 + (wn * NTW) * 32 + lane, (2 * D / 8) * 32);
-      const float* pg = P.pre2 + (size_t)b * N * 2 * D;
+      const float* dg = P.dgelu + (size_t)b * N * 2 * D;
+      float2 gp[2][NTW][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTW; nt++)
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            const int row = wm * 32 + mt * 16 + g + hf * 8, col = (wn * NTW + nt) * 8 + 2 * t;
+            gp[mt][nt][hf] = row < N ? *reinterpret_cast<const float2*>(dg + (size_t)row * 2 * D + col) : make_float2(0.f, 0.f);
+          }
 #pragma unroll
       for (int nt = 0; nt < NTW; nt++) {
         const int col = (wn * NTW + nt) * 8 + 2 * t;
@@ -698,21 +866,15 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
 #pragma unroll
           for (int hf = 0; hf < 2; hf++) {
             const int row = wm * 32 + mt * 16 + g + hf * 8;
-            float d0 = 0.f, d1 = 0.f, g0 = 0.f, g1 = 0.f;
-            if (row < N) {
-              const float2 pr = *reinterpret_cast<const float2*>(pg + (size_t)row * 2 * D + col);
-              d0 = acc[mt][nt][2 * hf] * gelu_grad_f(pr.x);
-              d1 = acc[mt][nt][2 * hf + 1] * gelu_grad_f(pr.y);
-              g0 = gelu_f(pr.x); g1 = gelu_f(pr.y);
-            }
+            const float d0 = acc[mt][nt][2 * hf] * gp[mt][nt][hf].x, d1 = acc[mt][nt][2 * hf + 1] * gp[mt][nt][hf].y;
             st2(sDP, row, col, d0, d1);
-            st2(sG, row, col, g0, g1);
             c0 += d0; c1 += d1;
           }
         c0 = colsum_g(c0); c1 = colsum_g(c1);                                 // db0 += colsum(dpre)  fullconnect.py:122
         if (g == 0) { atomicAdd(P.d_b0 + col, c0); atomicAdd(P.d_b0 + col + 1, c1); }
       }
     }
+    mbar_wait(bar, parity); parity ^= 1;
     __syncthreads();
     // ---- S2: dW1 += G^T d                                                  fullconnect.py:118-121
     {
@@ -764,22 +926,21 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
           red2(w + 8 * 2 * D, acc[mt][nt][2], acc[mt][nt][3]);
         }
     }
+    fence_async_smem();
     __syncthreads();
-    // ---- S5: dh = d + LN1-backward(dU1) ; db1 += colsum(d)                  attention.py:61-62
-    ln_bwd_rows<D>(tmp, hg, P.ln1_g, dcur, dh, sD, N, s_mean, s_rstd, P.d_ln1_g, P.d_ln1_b, P.d_b1, warp, lane);
-    // ---- S6: attention backward.  q/k/v -> shared (split)
-    {
-      const float* qg = P.qkv + (size_t)b * N * 3 * D;
-      for (int e = tid; e < ROWS * (3 * D / 2); e += 256) {
-        const int row = e / (3 * D / 2), c2 = (e - row * (3 * D / 2)) * 2;
-        const int which = c2 / D, cc = c2 - which * D;
-        float2 v = make_float2(0.f, 0.f);
-        if (row < N) v = *reinterpret_cast<const float2*>(qg + (size_t)row * 3 * D + c2);
-        st2(which == 0 ? sQ : (which == 1 ? sK : sV), row, cc, v.x, v.y);
-      }
+    // ---- q, k, v (split, as the forward left them) -> R_Q|R_K|R_V, overlapped with the LayerNorm backward
+    if (tid == 0) {
+      mbar_expect_tx(bar, 3 * C::ARR);
+      bulk_load(rQ, sv + C::SV_QKV, 3 * C::ARR, bar);
     }
+    // ---- S5: dh = d + LN1-backward(dU1) ; db1 += colsum(d)                  attention.py:61-62
+    ln_bwd_rows<D>(tmp, hg, P.ln1_g, dcur, dh, sD, N, s_stat + 2 * ROWS, s_stat + 3 * ROWS, P.d_ln1_g, P.d_ln1_b, P.d_b1,
+                   warp, lane);
+    mbar_wait(bar, parity); parity ^= 1;
     __syncthreads();
-    for (int rnd = 0; rnd < (H + 1) / 2; rnd++) {
+    // ---- S6: attention backward, two heads per round
+    const int rounds = (H + 1) / 2;
+    for (int rnd = 0; rnd < rounds; rnd++) {
       const int hl = warp >> 2, hd = 2 * rnd + hl, i0 = (warp & 3) * 16;
       const bool head_ok = hd < H;
       const bool valid = head_ok && i0 < N;
@@ -793,12 +954,8 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
         for (int c = 0; c < 4; c++) dq[nd][c] = dk[nd][c] = dv[nd][c] = 0.f;
       // phase 1: dP = dO V^T, dS = P o (dP - rowsum(dP o P)), dQ = dS K / sqrt(dh)      attention.py:74-78
       if (valid) {
-        float s[8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; nt++) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        gemm_rowk_nk<DH>(s, sD, i0, sV, hd * DH, NPAIR, lane);
         const float* pg = P.P + ((size_t)b * H + hd) * N * N;
-        float p[8][4], t0 = 0.f, t1 = 0.f;
+        float p[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
           const int col = nt * 8 + 2 * t;
@@ -806,6 +963,14 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
           p[nt][1] = (r0 < N && col + 1 < N) ? pg[r0 * N + col + 1] : 0.f;
           p[nt][2] = (r1 < N && col < N) ? pg[r1 * N + col] : 0.f;
           p[nt][3] = (r1 < N && col + 1 < N) ? pg[r1 * N + col + 1] : 0.f;
+        }
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        gemm_rowk_nk<DH>(s, sD, i0, sV, hd * DH, NPAIR, lane);
+        float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
           t0 += s[nt][0] * p[nt][0] + s[nt][1] * p[nt][1];
           t1 += s[nt][2] * p[nt][2] + s[nt][3] * p[nt][3];
         }
@@ -835,7 +1000,12 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
         gemm_colk_kn<DH>(dk, sdS, i0, sQ, hd * DH, KT, lane);
         gemm_colk_kn<DH>(dv, sP, i0, sD, hd * DH, KT, lane);
       }
+      if (rnd == rounds - 1) fence_async_smem();
       __syncthreads();
+      if (rnd == rounds - 1 && tid == 0) {       // score planes are dead: fetch u = LN(x) (operand of dWqkv) into R_PS
+        mbar_expect_tx(bar, C::ARR);
+        bulk_load(rPS, sv + C::SV_U, C::ARR, bar);
+      }
       // q/k/v of these heads are dead: overwrite them with dq/dk/dv (attention.py:81-83) + bias gradient
       if (head_ok) {
 #pragma unroll
@@ -860,8 +1030,7 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
         }
       }
     }
-    // ---- S7: u = LN(x) (operand of dWqkv) + statistics                    (sP/sdS are dead: all warps passed the last barrier)
-    ln_rows<D>(xin, P.ln_g, P.ln_b, sU, N, s_mean, s_rstd, warp, lane);
+    mbar_wait(bar, parity); parity ^= 1;
     __syncthreads();
     // ---- S8: dU = dqkv Wqkv^T -> tmp ; dWqkv += u^T dqkv                   attention.py:85-86
     {
@@ -901,7 +1070,8 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
     }
     __syncthreads();
     // ---- S9: dx = dh + LN-backward(dU)                                     attention.py:87-88
-    ln_bwd_rows<D>(tmp, xin, P.ln_g, dh, dxo, sD, N, s_mean, s_rstd, P.d_ln_g, P.d_ln_b, nullptr, warp, lane);
+    ln_bwd_rows<D>(tmp, xin, P.ln_g, dh, dxo, sD, N, s_stat, s_stat + ROWS, P.d_ln_g, P.d_ln_b, nullptr, warp, lane);
+    fence_async_smem();
     __syncthreads();
     dcur = dxo;
   }
@@ -967,6 +1137,12 @@ int nt_vit_blocks_supported(int N, int D, int H, int* ok) {
 
 int nt_vit_blocks_wfrag_bytes(int D, size_t* bytes) {
   *bytes = (size_t)56 * D * D;          // 8 bytes per weight element of the block's three Linear layers (7 D^2)
+  return 0;
+}
+
+int nt_vit_blocks_save_bytes(int D, size_t* bytes_per_image) {
+  const size_t arr = (size_t)vb::ROWS * (D + 8) * 4, arr2 = (size_t)vb::ROWS * (2 * D + 8) * 4;
+  *bytes_per_image = 5 * arr + arr2 + 4 * vb::ROWS * sizeof(float);
   return 0;
 }
 

@@ -12,7 +12,7 @@ from .device import DeviceArray, get_gemm_mode
 
 _PTR_FIELDS = ["ln_g", "ln_b", "wqkv", "bqkv", "ln1_g", "ln1_b", "w0", "b0", "w1", "b1",
                "d_ln_g", "d_ln_b", "d_wqkv", "d_bqkv", "d_ln1_g", "d_ln1_b", "d_w0", "d_b0", "d_w1", "d_b1",
-               "qkv", "P", "h", "pre2", "out", "wfrag"]
+               "qkv", "P", "h", "dgelu", "out", "save", "wfrag"]
 
 
 class NtVitBlock(ctypes.Structure):
@@ -31,6 +31,17 @@ def supported(N, D, H):
     ok = ctypes.c_int(0)
     lib.nt_vit_blocks_supported(int(N), int(D), int(H), ctypes.byref(ok))
     return bool(ok.value)
+
+
+_SAVE_BYTES = {}
+
+
+def _save_bytes(D):
+    if D not in _SAVE_BYTES:
+        n = ctypes.c_size_t(0)
+        lib.nt_vit_blocks_save_bytes(int(D), ctypes.byref(n))
+        _SAVE_BYTES[D] = n.value
+    return _SAVE_BYTES[D]
 
 
 def _wfrag(layer, D):
@@ -55,7 +66,8 @@ def _block_array(layers):
         s.d_ln1_g, s.d_ln1_b = l.norm1.gamma_delta.ptr, l.norm1.beta_delta.ptr
         s.d_w0, s.d_b0 = l.fc0.params_delta.ptr, l.fc0.bias_delta.ptr
         s.d_w1, s.d_b1 = l.fc1.params_delta.ptr, l.fc1.bias_delta.ptr
-        s.qkv, s.P, s.h, s.pre2, s.out = l.qkv.ptr, l.P.ptr, l.input1.ptr, l.pre2.ptr, l._out.ptr
+        s.qkv, s.P, s.h, s.dgelu, s.out = l.qkv.ptr, l.P.ptr, l.input1.ptr, l._dgelu.ptr, l._out.ptr
+        s.save = l._save.ptr
         s.wfrag = l._wfrag.ptr
     return arr
 
@@ -72,7 +84,8 @@ def forward_stack(layers, x):
         l.qkv = DeviceArray((B, N, 3 * D), host_dtype=hd)
         l.P = DeviceArray((B, H, N, N), host_dtype=hd)
         l.input1 = DeviceArray((B, N, D), host_dtype=hd)
-        l.pre2 = DeviceArray((B, N, 2 * D), host_dtype=hd)
+        l._dgelu = DeviceArray((B, N, 2 * D), host_dtype=hd)
+        l._save = DeviceArray((B, _save_bytes(D) // 4))
         l._out = DeviceArray((B, N, D), host_dtype=hd)
         l.out = l.out1 = l.out2 = None          # LN outputs / GELU output are recomputed in backward, not stored
         l._fused = True
