@@ -98,6 +98,13 @@ def op_cost(name, a, kind, c):
     if name in ("nt_linear_fwd", "nt_linear_bwd_input", "nt_linear_bwd_params"):
         M, K, N = a[0], a[1], a[2]
         return 2.0 * M * K * N, 4.0 * (M * K + K * N + M * N)
+    if name in ("nt_vit_blocks_fwd", "nt_vit_blocks_bwd"):
+        # fused ViT block stack: L blocks x B images; per image and block the three Linear layers (7 D^2 weights)
+        # and the attention core (QK^T and PV over N tokens); backward = 2x forward
+        L, B, N, D, H = a[-5:]
+        fwd = L * B * (2.0 * N * 7 * D * D + 4.0 * N * N * D)
+        act = 4.0 * L * B * N * (3 * D + H * N + D + 2 * D + D)      # qkv, P, h, dgelu, out
+        return (fwd, act) if name.endswith("fwd") else (2.0 * fwd, act)
     if name == "nt_attention_fwd":
         B, N, H, dh = a[-4:]
         return 4.0 * B * H * N * N * dh, 4.0 * (4 * B * N * H * dh + B * H * N * N)

@@ -117,43 +117,66 @@ __device__ __forceinline__ void zero_acc(float (&acc)[MT][NT][4]) {
     for (int n = 0; n < NT; n++) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
 }
 
+// first k-step of a weight-fragment stream: issued a whole phase ahead of the GEMM that consumes it, so the L2
+// round trip overlaps the LayerNorm / epilogue in between instead of stalling the first MMAs
+template <int NTW>
+__device__ __forceinline__ void wf_first(uint4 (&b0)[NTW], const uint4* __restrict__ wf) {
+#pragma unroll
+  for (int nt = 0; nt < NTW; nt++) b0[nt] = __ldg(wf + nt * 32);
+}
+
 // acc[mt][nt] += A(rows, k) * W, A row-major in shared memory (hi/lo planes), W as pre-split B fragments in
-// global memory ([k16 step][n8 tile][lane] uint4 = {b0.hi, b1.hi, b0.lo, b1.lo}), next k-step prefetched.
+// global memory ([k16 step][n8 tile][lane] uint4 = {b0.hi, b1.hi, b0.lo, b1.lo}).  KS k-steps, fully unrolled:
+// B fragments run PF k-steps ahead in a register ring, A fragments one k-step ahead.
 // a_addr(ks): shared address (hi plane) of this lane's ldmatrix row for m-tile 0 at k-step ks.
-template <int MT, int NTW, class AF>
+template <int MT, int NTW, int KS, int PF, class AF>
 __device__ __forceinline__ void gemm_wf(float (&acc)[MT][NTW][4], AF a_addr, uint32_t a_lo, uint32_t a_mt_stride,
-                                        int ksteps, const uint4* __restrict__ wf, int ks_stride) {
-  uint4 bc[NTW], bn[NTW];
+                                        const uint4* __restrict__ wf, int ks_stride, const uint4 (&b0)[NTW]) {
+  uint4 b[PF + 1][NTW];
 #pragma unroll
-  for (int nt = 0; nt < NTW; nt++) bc[nt] = __ldg(wf + nt * 32);
-  for (int ks = 0; ks < ksteps; ks++) {
-    if (ks + 1 < ksteps) {
+  for (int nt = 0; nt < NTW; nt++) b[0][nt] = b0[nt];
 #pragma unroll
-      for (int nt = 0; nt < NTW; nt++) bn[nt] = __ldg(wf + (size_t)(ks + 1) * ks_stride + nt * 32);
+  for (int p = 1; p <= PF; p++)
+    if (p < KS) {
+#pragma unroll
+      for (int nt = 0; nt < NTW; nt++) b[p][nt] = __ldg(wf + (size_t)p * ks_stride + nt * 32);
     }
-    uint32_t ah[MT][4], al[MT][4];
-    const uint32_t a0 = a_addr(ks);
+  uint32_t ah[2][MT][4], al[2][MT][4];
+  {
+    const uint32_t a0 = a_addr(0);
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) {
-      ldsm4(ah[mt], a0 + mt * a_mt_stride);
-      ldsm4(al[mt], a0 + mt * a_mt_stride + a_lo);
+      ldsm4(ah[0][mt], a0 + mt * a_mt_stride);
+      ldsm4(al[0][mt], a0 + mt * a_mt_stride + a_lo);
+    }
+  }
+#pragma unroll
+  for (int ks = 0; ks < KS; ks++) {
+    const int ab = ks & 1, slot = ks % (PF + 1);
+    if (ks + 1 < KS) {
+      const uint32_t a1 = a_addr(ks + 1);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) {
+        ldsm4(ah[ab ^ 1][mt], a1 + mt * a_mt_stride);
+        ldsm4(al[ab ^ 1][mt], a1 + mt * a_mt_stride + a_lo);
+      }
     }
     // pass-major: consecutive MMAs hit different accumulators (no back-to-back RAW on the tensor pipe)
 #pragma unroll
     for (int nt = 0; nt < NTW; nt++)
 #pragma unroll
-      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], al[mt], bc[nt].x, bc[nt].y);
+      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], al[ab][mt], b[slot][nt].x, b[slot][nt].y);
 #pragma unroll
     for (int nt = 0; nt < NTW; nt++)
 #pragma unroll
-      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], ah[mt], bc[nt].z, bc[nt].w);
+      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], ah[ab][mt], b[slot][nt].z, b[slot][nt].w);
 #pragma unroll
     for (int nt = 0; nt < NTW; nt++)
 #pragma unroll
-      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], ah[mt], bc[nt].x, bc[nt].y);
-    if (ks + 1 < ksteps) {
+      for (int mt = 0; mt < MT; mt++) mma16(acc[mt][nt], ah[ab][mt], b[slot][nt].x, b[slot][nt].y);
+    if (ks + PF + 1 < KS) {
 #pragma unroll
-      for (int nt = 0; nt < NTW; nt++) bc[nt] = bn[nt];
+      for (int nt = 0; nt < NTW; nt++) b[slot][nt] = __ldg(wf + (size_t)(ks + PF + 1) * ks_stride + nt * 32);
     }
   }
 }
@@ -597,6 +620,8 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
     const NtVitBlock& P = a.blk[bi];
     const uint4* wf = reinterpret_cast<const uint4*>(P.wfrag);
     char* sv = reinterpret_cast<char*>(P.save) + (size_t)b * C::SV_BYTES;
+    uint4 bq0[3 * D / 32];
+    wf_first(bq0, wf + C::F_QKV + (wn * (3 * D / 32)) * 32 + lane);
     // ---- u = LN(x)                                                      attention.py:22
     ln_rows<D>(xcur, P.ln_g, P.ln_b, sU, N, s_stat, s_stat + ROWS, warp, lane);
     fence_async_smem();
@@ -608,8 +633,8 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
       float acc[2][NTW][4];
       zero_acc(acc);
       const uint32_t a_lane = sU.addr + (wm * 32 + (lane & 15)) * sU.ldb + ((lane >> 4) * 8) * 2;
-      gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sU.lo, 16 * sU.ldb, D / 16,
-                      wf + C::F_QKV + (wn * NTW) * 32 + lane, (3 * D / 8) * 32);
+      gemm_wf<2, NTW, D / 16, 1>(acc, [&](int ks) { return a_lane + ks * 32; }, sU.lo, 16 * sU.ldb,
+                                 wf + C::F_QKV + (wn * NTW) * 32 + lane, (3 * D / 8) * 32, bq0);
       float* qg = P.qkv + (size_t)b * N * 3 * D;
       float2 bb[NTW];
 #pragma unroll
@@ -698,6 +723,8 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
       __syncwarp();
     }
     if (tid == 0) bulk_store_wait_read();        // the bulk stores have finished READING sU / sQ|sK|sV
+    uint4 bf0[2 * D / 32];
+    wf_first(bf0, wf + C::F_FC0 + (wn * (2 * D / 32)) * 32 + lane);
     __syncthreads();
     // ---- u1 = LN1(h)                                                     attention.py:48
     ln_rows<D>(P.h + img, P.ln1_g, P.ln1_b, sU, N, s_stat + 2 * ROWS, s_stat + 3 * ROWS, warp, lane);
@@ -705,13 +732,15 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
     __syncthreads();
     if (tid == 0) bulk_store(sv + C::SV_U1, sU.ptr, C::ARR);              // operand of dW0 in the backward
     // ---- pre2 = u1 W0 + b0 ; G = GELU(pre2)                              attention.py:49-50
+    uint4 bg0[D / 32];
     {
       constexpr int NTW = 2 * D / 32;
       float acc[2][NTW][4];
       zero_acc(acc);
       const uint32_t a_lane = sU.addr + (wm * 32 + (lane & 15)) * sU.ldb + ((lane >> 4) * 8) * 2;
-      gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sU.lo, 16 * sU.ldb, D / 16,
-                      wf + C::F_FC0 + (wn * NTW) * 32 + lane, (2 * D / 8) * 32);
+      gemm_wf<2, NTW, D / 16, 2>(acc, [&](int ks) { return a_lane + ks * 32; }, sU.lo, 16 * sU.ldb,
+                                 wf + C::F_FC0 + (wn * NTW) * 32 + lane, (2 * D / 8) * 32, bf0);
+      wf_first(bg0, wf + C::F_FC1 + (wn * (D / 32)) * 32 + lane);
       float* dg = P.dgelu + (size_t)b * N * 2 * D;
       float2 bb[NTW];
 #pragma unroll
@@ -746,8 +775,8 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
       float acc[2][NTW][4];
       zero_acc(acc);
       const uint32_t a_lane = sG.addr + (wm * 32 + (lane & 15)) * sG.ldb + ((lane >> 4) * 8) * 2;
-      gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sG.lo, 16 * sG.ldb, 2 * D / 16,
-                      wf + C::F_FC1 + (wn * NTW) * 32 + lane, (D / 8) * 32);
+      gemm_wf<2, NTW, 2 * D / 16, 3>(acc, [&](int ks) { return a_lane + ks * 32; }, sG.lo, 16 * sG.ldb,
+                                     wf + C::F_FC1 + (wn * NTW) * 32 + lane, (D / 8) * 32, bg0);
       const float* hg = P.h + img;
       float* og = P.out + img;
       float2 bb[NTW], hr[2][NTW][2];
@@ -831,6 +860,8 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
     const float* xin = (bi ? a.blk[bi - 1].out : a.x) + img;
     const float* hg = P.h + img;
     const char* sv = reinterpret_cast<const char*>(P.save) + (size_t)b * C::SV_BYTES;
+    uint4 b10[2 * D / 32];
+    wf_first(b10, wf + C::B_FC1 + (wn * (2 * D / 32)) * 32 + lane);
     // ---- S0: operands the forward saved: u1 = LN1(h) -> R_Q, G = GELU(pre2) -> R_PS (async), LN statistics
     if (tid == 0) {
       mbar_expect_tx(bar, C::ARR + C::ARR2);
@@ -844,8 +875,8 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
       float acc[2][NTW][4];
       zero_acc(acc);
       const uint32_t a_lane = sD.addr + (wm * 32 + (lane & 15)) * sD.ldb + ((lane >> 4) * 8) * 2;
-      gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sD.lo, 16 * sD.ldb, D / 16,
-                      wf + C::B_FC1 + (wn * NTW) * 32 + lane, (2 * D / 8) * 32);
+      gemm_wf<2, NTW, D / 16, 2>(acc, [&](int ks) { return a_lane + ks * 32; }, sD.lo, 16 * sD.ldb,
+                                 wf + C::B_FC1 + (wn * NTW) * 32 + lane, (2 * D / 8) * 32, b10);
       const float* dg = P.dgelu + (size_t)b * N * 2 * D;
       float2 gp[2][NTW][2];
 #pragma unroll
@@ -874,6 +905,8 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
         if (g == 0) { atomicAdd(P.d_b0 + col, c0); atomicAdd(P.d_b0 + col + 1, c1); }
       }
     }
+    uint4 b00[D / 32];
+    wf_first(b00, wf + C::B_FC0 + (wn * (D / 32)) * 32 + lane);
     mbar_wait(bar, parity); parity ^= 1;
     __syncthreads();
     // ---- S2: dW1 += G^T d                                                  fullconnect.py:118-121
@@ -898,8 +931,8 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
       float acc[2][NTW][4];
       zero_acc(acc);
       const uint32_t a_lane = sDP.addr + (wm * 32 + (lane & 15)) * sDP.ldb + ((lane >> 4) * 8) * 2;
-      gemm_wf<2, NTW>(acc, [&](int ks) { return a_lane + ks * 32; }, sDP.lo, 16 * sDP.ldb, 2 * D / 16,
-                      wf + C::B_FC0 + (wn * NTW) * 32 + lane, (D / 8) * 32);
+      gemm_wf<2, NTW, 2 * D / 16, 3>(acc, [&](int ks) { return a_lane + ks * 32; }, sDP.lo, 16 * sDP.ldb,
+                                     wf + C::B_FC0 + (wn * NTW) * 32 + lane, (D / 8) * 32, b00);
 #pragma unroll
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
@@ -1030,6 +1063,8 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
         }
       }
     }
+    uint4 bu0[D / 32];
+    wf_first(bu0, wf + C::B_QKV + (wn * (D / 32)) * 32 + lane);
     mbar_wait(bar, parity); parity ^= 1;
     __syncthreads();
     // ---- S8: dU = dqkv Wqkv^T -> tmp ; dWqkv += u^T dqkv                   attention.py:85-86
@@ -1039,8 +1074,8 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
       zero_acc(acc);
       const uint32_t a_lane = sQ.addr + (wm * 32 + (lane & 15)) * sQ.ldb + ((lane >> 4) * 8) * 2;
       // k runs over the 3D columns of dqkv = [dq | dk | dv], three arrays C::ARR bytes apart
-      gemm_wf<2, NTW>(acc, [&](int ks) { const int seg = ks / (D / 16); return a_lane + seg * C::ARR + (ks - seg * (D / 16)) * 32; },
-                      sQ.lo, 16 * sQ.ldb, 3 * D / 16, wf + C::B_QKV + (wn * NTW) * 32 + lane, (D / 8) * 32);
+      gemm_wf<2, NTW, 3 * D / 16, 3>(acc, [&](int ks) { const int seg = ks / (D / 16); return a_lane + seg * C::ARR + (ks - seg * (D / 16)) * 32; },
+                                     sQ.lo, 16 * sQ.ldb, wf + C::B_QKV + (wn * NTW) * 32 + lane, (D / 8) * 32, bu0);
 #pragma unroll
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
