@@ -189,6 +189,7 @@ __device__ __forceinline__ void gemm_tt(float (&acc)[MT][NTW][4], const SArr& A,
   const uint32_t a_lane = A.addr + ((lane & 7) + ((lane >> 4) & 1) * 8) * A.ldb + (m0 + ((lane >> 3) & 1) * 8) * 2;
   const uint32_t b_lane = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + (n0 + (lane >> 4) * 8) * 2;
   const uint32_t b_lane2 = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + n0 * 2;
+#pragma unroll
   for (int ks = 0; ks < ksteps; ks++) {
     uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
@@ -321,6 +322,7 @@ __device__ __forceinline__ void gemm_rowk_kn(float (&o)[DH / 8][4], const SArr& 
   float os[NDT][4];
 #pragma unroll
   for (int nd = 0; nd < NDT; nd++) os[nd][0] = os[nd][1] = os[nd][2] = os[nd][3] = 0.f;
+#pragma unroll
   for (int kk = 0; kk < ksteps; kk++) {
     uint32_t ah[4], al[4], bh[NDT][2], bl[NDT][2];
     ldsm4(ah, a_lane + kk * 32);
@@ -345,6 +347,7 @@ __device__ __forceinline__ void gemm_colk_kn(float (&o)[DH / 8][4], const SArr& 
   float os[NDT][4];
 #pragma unroll
   for (int nd = 0; nd < NDT; nd++) os[nd][0] = os[nd][1] = os[nd][2] = os[nd][3] = 0.f;
+#pragma unroll
   for (int kk = 0; kk < ksteps; kk++) {
     uint32_t ah[4], al[4], bh[NDT][2], bl[NDT][2];
     ldsm4t(ah, a_lane + kk * 16 * A.ldb);
@@ -420,8 +423,9 @@ __device__ __forceinline__ void warp_sum_multi(float (&v)[R]) {
 // rows >= N are zero-filled.  A warp owns rows warp, warp+8, ...; all of them are loaded and reduced together.
 // mean / rstd go to shared memory when requested (the backward formula needs them).
 template <int D>
-__device__ __forceinline__ void ln_rows(const float* src, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                        const SArr& dst, int N, float* s_mean, float* s_rstd, int warp, int lane) {
+__device__ __forceinline__ void ln_rows(const float* src, int src_ld, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, const SArr& dst, int N, float* s_mean,
+                                        float* s_rstd, int warp, int lane) {
   constexpr int E = D / 32, RPW = ROWS / 8;
   float gm[E], bt[E], v[RPW][E], s[RPW], q[RPW];
 #pragma unroll
@@ -431,7 +435,7 @@ __device__ __forceinline__ void ln_rows(const float* src, const float* __restric
     const int r = warp + 8 * i;
     s[i] = 0.f;
 #pragma unroll
-    for (int e = 0; e < E; e++) { v[i][e] = r < N ? src[r * D + lane + 32 * e] : 0.f; s[i] += v[i][e]; }
+    for (int e = 0; e < E; e++) { v[i][e] = r < N ? src[r * src_ld + lane + 32 * e] : 0.f; s[i] += v[i][e]; }
   }
   warp_sum_multi<RPW>(s);
 #pragma unroll
@@ -457,10 +461,9 @@ __device__ __forceinline__ void ln_rows(const float* src, const float* __restric
 // i.e. the bias gradient of the layer whose output gradient `addend` is) are accumulated per lane over the
 // warp's rows and flushed with one atomic per column per warp.
 template <int D>
-__device__ __forceinline__ void ln_bwd_rows(const float* dy, const float* xin, const float* __restrict__ gamma,
+__device__ __forceinline__ void ln_bwd_rows(const float* dy, int dy_ld, const float* xin, const float* __restrict__ gamma,
                                             const float* addend, float* out, const SArr& dst, int N,
-                                            const float* s_mean, const float* s_rstd, float* dgamma, float* dbeta,
-                                            float* dbias_addend, int warp, int lane) {
+                                            const float* s_mean, const float* s_rstd, float* s_red, int warp, int lane) {
   constexpr int E = D / 32, RPW = ROWS / 8;
   float gm[E], ag[E], ab[E], aa[E];
 #pragma unroll
@@ -472,7 +475,7 @@ __device__ __forceinline__ void ln_bwd_rows(const float* dy, const float* xin, c
 #pragma unroll
     for (int e = 0; e < E; e++) {
       const int o = r * D + lane + 32 * e;
-      g[i][e] = r < N ? dy[o] : 0.f;
+      g[i][e] = r < N ? dy[r * dy_ld + lane + 32 * e] : 0.f;
       xh[i][e] = r < N ? xin[o] : 0.f;
       va[i][e] = r < N ? addend[o] : 0.f;
     }
@@ -508,11 +511,27 @@ __device__ __forceinline__ void ln_bwd_rows(const float* dy, const float* xin, c
       st1(dst, r, lane + 32 * e, r < N ? o : 0.f);
     }
   }
+  // per-warp column partials -> shared memory [8 warps][3][D]; ln_bwd_flush() adds them up after the next barrier
 #pragma unroll
   for (int e = 0; e < E; e++) {
-    atomicAdd(dgamma + lane + 32 * e, ag[e]);
-    atomicAdd(dbeta + lane + 32 * e, ab[e]);
-    if (dbias_addend) atomicAdd(dbias_addend + lane + 32 * e, aa[e]);
+    float* p = s_red + warp * 3 * D + lane + 32 * e;
+    p[0] = ag[e];
+    p[D] = ab[e];
+    p[2 * D] = aa[e];
+  }
+}
+
+// one atomic per column per CTA: dgamma += sum xhat*dy, dbeta += sum dy, and (optionally) the bias gradient of the
+// layer whose output gradient was the addend (net/layernorm.py:130-133, net/fullconnect.py:122)
+template <int D>
+__device__ __forceinline__ void ln_bwd_flush(const float* s_red, float* dgamma, float* dbeta, float* dbias, int tid) {
+  for (int c = tid; c < 3 * D; c += 256) {
+    float* dst = c < D ? dgamma + c : (c < 2 * D ? dbeta + (c - D) : (dbias ? dbias + (c - 2 * D) : nullptr));
+    if (!dst) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) v += s_red[w * 3 * D + c];
+    atomicAdd(dst, v);
   }
 }
 
@@ -549,8 +568,10 @@ struct Cfg {
   static constexpr int SV_G = SV_U1 + ARR;
   static constexpr int SV_STAT = SV_G + ARR2;
   static constexpr int SV_BYTES = SV_STAT + 4 * ROWS * (int)sizeof(float);
-  static constexpr size_t FWD_SMEM = 4 * (size_t)ARR + 8 * (size_t)PW + 4 * ROWS * sizeof(float);
-  static constexpr size_t BWD_SMEM = 4 * (size_t)ARR + 4 * (size_t)PARR + 4 * ROWS * sizeof(float) + 16;
+  static constexpr int XLD = D + 8;                     // pitch (floats) of the fp32 residual / LN-input buffers
+  static constexpr int XARR = ROWS * XLD * 4;
+  static constexpr size_t FWD_SMEM = 4 * (size_t)ARR + 8 * (size_t)PW + 4 * ROWS * sizeof(float) + XARR;
+  static constexpr size_t BWD_SMEM = 4 * (size_t)ARR + 4 * (size_t)PARR + 4 * ROWS * sizeof(float) + 16 + XARR + 8 * 3 * D * sizeof(float);
   static_assert(D % 32 == 0 && DH % 8 == 0 && DH * H == D, "fused ViT block: D % 32 == 0, dh % 8 == 0");
   static_assert(ARR2 <= 2 * ARR && ARR2 <= 4 * PARR && ARR <= 4 * PARR, "aliasing plan");
   static_assert(ARR % 16 == 0 && ARR2 % 16 == 0 && SV_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
@@ -611,10 +632,19 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
   const SArr sG = make_arr(smem + C::ARR, C::LD2);                       // aliases sQ|sK after attention
   const SArr sPw = make_arr(smem + 4 * C::ARR + warp * C::PW, LDP, 16);  // this warp's P tile
   float* s_stat = reinterpret_cast<float*>(smem + 4 * C::ARR + 8 * C::PW);   // mean, rstd (LN) | mean, rstd (LN1)
-  const int NTK = (N + 7) >> 3, NPAIR = (NTK + 1) >> 1, KT = (N + 15) >> 4;
+  // token contractions always run over the 64 padded rows / keys (pad rows are exact zeros, padded keys are masked):
+  // compile-time trip counts let the compiler software-pipeline the fragment loads
+  constexpr int NPAIR = ROWS / 16, KT = ROWS / 16;
   const float scale = rsqrtf((float)DH);
   const size_t img = (size_t)b * N * D;
-  const float* xcur = a.x + img;
+  // fp32 residual stream of this image: x -> h -> out in place (every element is updated by the thread that read it)
+  float* sX = reinterpret_cast<float*>(smem + 4 * C::ARR + 8 * C::PW + 4 * ROWS * sizeof(float));
+  for (int e = tid; e < ROWS * (D / 4); e += 256) {
+    const int r = e / (D / 4), c4 = (e - r * (D / 4)) * 4;
+    *reinterpret_cast<float4*>(sX + r * C::XLD + c4) =
+        r < N ? __ldg(reinterpret_cast<const float4*>(a.x + img + r * D + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
 
   for (int bi = 0; bi < a.nblocks; bi++) {
     const NtVitBlock& P = a.blk[bi];
@@ -623,7 +653,7 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
     uint4 bq0[3 * D / 32];
     wf_first(bq0, wf + C::F_QKV + (wn * (3 * D / 32)) * 32 + lane);
     // ---- u = LN(x)                                                      attention.py:22
-    ln_rows<D>(xcur, P.ln_g, P.ln_b, sU, N, s_stat, s_stat + ROWS, warp, lane);
+    ln_rows<D>(sX, C::XLD, P.ln_g, P.ln_b, sU, N, s_stat, s_stat + ROWS, warp, lane);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) bulk_store(sv + C::SV_U, sU.ptr, C::ARR);               // operand of dWqkv in the backward
@@ -711,14 +741,16 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
 #pragma unroll
       for (int nd = 0; nd < DH / 8; nd++) {
         const int col = hd * DH + nd * 8 + 2 * t;
-        xr0[nd] = r0 < N ? *reinterpret_cast<const float2*>(xcur + r0 * D + col) : make_float2(0.f, 0.f);
-        xr1[nd] = r1 < N ? *reinterpret_cast<const float2*>(xcur + r1 * D + col) : make_float2(0.f, 0.f);
+        xr0[nd] = *reinterpret_cast<const float2*>(sX + r0 * C::XLD + col);
+        xr1[nd] = *reinterpret_cast<const float2*>(sX + r1 * C::XLD + col);
       }
 #pragma unroll
       for (int nd = 0; nd < DH / 8; nd++) {
         const int col = hd * DH + nd * 8 + 2 * t;
-        if (r0 < N) *reinterpret_cast<float2*>(hg + r0 * D + col) = make_float2(xr0[nd].x + o[nd][0], xr0[nd].y + o[nd][1]);   // attention.py:46
-        if (r1 < N) *reinterpret_cast<float2*>(hg + r1 * D + col) = make_float2(xr1[nd].x + o[nd][2], xr1[nd].y + o[nd][3]);
+        const float2 h0 = make_float2(xr0[nd].x + o[nd][0], xr0[nd].y + o[nd][1]);                 // attention.py:46
+        const float2 h1 = make_float2(xr1[nd].x + o[nd][2], xr1[nd].y + o[nd][3]);
+        if (r0 < N) { *reinterpret_cast<float2*>(sX + r0 * C::XLD + col) = h0; *reinterpret_cast<float2*>(hg + r0 * D + col) = h0; }
+        if (r1 < N) { *reinterpret_cast<float2*>(sX + r1 * C::XLD + col) = h1; *reinterpret_cast<float2*>(hg + r1 * D + col) = h1; }
       }
       __syncwarp();
     }
@@ -727,7 +759,7 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
     wf_first(bf0, wf + C::F_FC0 + (wn * (2 * D / 32)) * 32 + lane);
     __syncthreads();
     // ---- u1 = LN1(h)                                                     attention.py:48
-    ln_rows<D>(P.h + img, P.ln1_g, P.ln1_b, sU, N, s_stat + 2 * ROWS, s_stat + 3 * ROWS, warp, lane);
+    ln_rows<D>(sX, C::XLD, P.ln1_g, P.ln1_b, sU, N, s_stat + 2 * ROWS, s_stat + 3 * ROWS, warp, lane);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) bulk_store(sv + C::SV_U1, sU.ptr, C::ARR);              // operand of dW0 in the backward
@@ -777,9 +809,8 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
       const uint32_t a_lane = sG.addr + (wm * 32 + (lane & 15)) * sG.ldb + ((lane >> 4) * 8) * 2;
       gemm_wf<2, NTW, 2 * D / 16, 3>(acc, [&](int ks) { return a_lane + ks * 32; }, sG.lo, 16 * sG.ldb,
                                      wf + C::F_FC1 + (wn * NTW) * 32 + lane, (D / 8) * 32, bg0);
-      const float* hg = P.h + img;
       float* og = P.out + img;
-      float2 bb[NTW], hr[2][NTW][2];
+      float2 bb[NTW];
 #pragma unroll
       for (int nt = 0; nt < NTW; nt++) bb[nt] = __ldg(reinterpret_cast<const float2*>(P.b1 + (wn * NTW + nt) * 8 + 2 * t));
 #pragma unroll
@@ -789,23 +820,17 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
 #pragma unroll
           for (int hf = 0; hf < 2; hf++) {
             const int row = wm * 32 + mt * 16 + g + hf * 8, col = (wn * NTW + nt) * 8 + 2 * t;
-            hr[mt][nt][hf] = row < N ? *reinterpret_cast<const float2*>(hg + row * D + col) : make_float2(0.f, 0.f);
-          }
-#pragma unroll
-      for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-        for (int nt = 0; nt < NTW; nt++)
-#pragma unroll
-          for (int hf = 0; hf < 2; hf++) {
-            const int row = wm * 32 + mt * 16 + g + hf * 8, col = (wn * NTW + nt) * 8 + 2 * t;
-            if (row < N)
-              *reinterpret_cast<float2*>(og + row * D + col) =
-                  make_float2(acc[mt][nt][2 * hf] + bb[nt].x + hr[mt][nt][hf].x, acc[mt][nt][2 * hf + 1] + bb[nt].y + hr[mt][nt][hf].y);
+            if (row < N) {
+              float2* xs = reinterpret_cast<float2*>(sX + row * C::XLD + col);
+              const float2 hr = *xs;
+              const float2 ov = make_float2(acc[mt][nt][2 * hf] + bb[nt].x + hr.x, acc[mt][nt][2 * hf + 1] + bb[nt].y + hr.y);
+              *xs = ov;
+              *reinterpret_cast<float2*>(og + row * D + col) = ov;
+            }
           }
     }
     if (tid == 0) bulk_store_wait_read();        // sU / sG may be overwritten by the next block
     __syncthreads();
-    xcur = P.out + img;
   }
   if (tid == 0) bulk_store_wait_all();
 }
@@ -834,12 +859,12 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
   const SArr sDP = make_arr(rK, C::LD2);         // MLP phase: d(pre2)   (spans R_K|R_V)
   const SArr sG = make_arr(rPS, C::LD2);         // MLP phase: GELU(pre2)
   const SArr sU = make_arr(rPS, C::LD);          // QKV phase: LN(x)
-  const int KT = (N + 15) >> 4;                  // k16 steps over tokens
-  const int NTK = (N + 7) >> 3, NPAIR = (NTK + 1) >> 1;
+  constexpr int KT = ROWS / 16, NPAIR = ROWS / 16;   // token contractions cover the 64 padded rows (pads are exact zeros)
   const float scale = rsqrtf((float)DH);
   const size_t img = (size_t)b * N * D;
   float* dh = a.dh + img;
-  float* tmp = a.tmp + img;
+  float* sT = reinterpret_cast<float*>(smem + 4 * C::ARR + 4 * C::PARR + 4 * ROWS * sizeof(float) + 16);   // fp32 [64][XLD]
+  float* s_red = sT + ROWS * C::XLD;                                                                      // [8][3][D]
   float* dxo = a.dx + img;
   const float* dcur = a.dout + img;
   uint32_t parity = 0;
@@ -940,7 +965,7 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
 #pragma unroll
           for (int hf = 0; hf < 2; hf++) {
             const int row = wm * 32 + mt * 16 + g + hf * 8, col = (wn * NTW + nt) * 8 + 2 * t;
-            if (row < N) *reinterpret_cast<float2*>(tmp + row * D + col) = make_float2(acc[mt][nt][2 * hf], acc[mt][nt][2 * hf + 1]);
+            *reinterpret_cast<float2*>(sT + row * C::XLD + col) = make_float2(acc[mt][nt][2 * hf], acc[mt][nt][2 * hf + 1]);
           }
     }
     // ---- S4: dW0 += u1^T dpre
@@ -967,10 +992,10 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
       bulk_load(rQ, sv + C::SV_QKV, 3 * C::ARR, bar);
     }
     // ---- S5: dh = d + LN1-backward(dU1) ; db1 += colsum(d)                  attention.py:61-62
-    ln_bwd_rows<D>(tmp, hg, P.ln1_g, dcur, dh, sD, N, s_stat + 2 * ROWS, s_stat + 3 * ROWS, P.d_ln1_g, P.d_ln1_b, P.d_b1,
-                   warp, lane);
+    ln_bwd_rows<D>(sT, C::XLD, hg, P.ln1_g, dcur, dh, sD, N, s_stat + 2 * ROWS, s_stat + 3 * ROWS, s_red, warp, lane);
     mbar_wait(bar, parity); parity ^= 1;
     __syncthreads();
+    ln_bwd_flush<D>(s_red, P.d_ln1_g, P.d_ln1_b, P.d_b1, tid);
     // ---- S6: attention backward, two heads per round
     const int rounds = (H + 1) / 2;
     for (int rnd = 0; rnd < rounds; rnd++) {
@@ -1083,7 +1108,7 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
 #pragma unroll
           for (int hf = 0; hf < 2; hf++) {
             const int row = wm * 32 + mt * 16 + g + hf * 8, col = (wn * NTW + nt) * 8 + 2 * t;
-            if (row < N) *reinterpret_cast<float2*>(tmp + row * D + col) = make_float2(acc[mt][nt][2 * hf], acc[mt][nt][2 * hf + 1]);
+            *reinterpret_cast<float2*>(sT + row * C::XLD + col) = make_float2(acc[mt][nt][2 * hf], acc[mt][nt][2 * hf + 1]);
           }
     }
 #pragma unroll 1
@@ -1105,9 +1130,10 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
     }
     __syncthreads();
     // ---- S9: dx = dh + LN-backward(dU)                                     attention.py:87-88
-    ln_bwd_rows<D>(tmp, xin, P.ln_g, dh, dxo, sD, N, s_stat, s_stat + ROWS, P.d_ln_g, P.d_ln_b, nullptr, warp, lane);
+    ln_bwd_rows<D>(sT, C::XLD, xin, P.ln_g, dh, dxo, sD, N, s_stat, s_stat + ROWS, s_red, warp, lane);
     fence_async_smem();
     __syncthreads();
+    ln_bwd_flush<D>(s_red, P.d_ln_g, P.d_ln_b, nullptr, tid);
     dcur = dxo;
   }
 }
