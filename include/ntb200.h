@@ -159,8 +159,12 @@ typedef struct NtVitBlock {
 int nt_vit_blocks_supported(int N, int D, int H, int* ok);
 int nt_vit_blocks_wfrag_bytes(int D, size_t* bytes);
 int nt_vit_blocks_save_bytes(int D, size_t* bytes_per_image);
-/* x [B,N,D] is the input of blocks[0]; blocks[i].out feeds blocks[i+1]. */
-int nt_vit_blocks_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H);
+/* Re-split the CURRENT weights of the blocks into wfrag (one small launch).  Needed once after every parameter
+ * update; a captured step issues it on the side branch so it overlaps the patch embedding. */
+int nt_vit_blocks_prepare(const NtVitBlock* blocks, int nblocks, int D, int H);
+/* x [B,N,D] is the input of blocks[0]; blocks[i].out feeds blocks[i+1].  prepared != 0: the caller already ran
+ * nt_vit_blocks_prepare for the current weights; 0: the call does it first. */
+int nt_vit_blocks_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H, int prepared);
 /* dout [B,N,D] = gradient w.r.t. blocks[nblocks-1].out; dx [B,N,D] receives the gradient w.r.t. x;
  * scratch holds 2*B*N*D floats.  Parameter gradients accumulate into the d_* members. */
 int nt_vit_blocks_bwd(const NtVitBlock* blocks, int nblocks, const float* x, const float* dout, float* dx,

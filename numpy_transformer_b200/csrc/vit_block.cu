@@ -1150,11 +1150,16 @@ static int ensure_attrs() {
   return 0;
 }
 template <int D, int H>
+static int launch_split(const Args& a, int) {
+  using C = Cfg<D, H>;
+  NT_CHECK(launch_k(vit_wsplit_kernel<D, H>, dim3(ceil_div(C::F_TOTAL, 256 * 4), a.nblocks), dim3(256), 0, a));
+  NT_LAUNCH_OK();
+  return 0;
+}
+template <int D, int H>
 static int launch_fwd(const Args& a, int B) {
   using C = Cfg<D, H>;
   if (int rc = ensure_attrs<D, H>()) return rc;
-  NT_CHECK(launch_k(vit_wsplit_kernel<D, H>, dim3(ceil_div(C::F_TOTAL, 256 * 4), a.nblocks), dim3(256), 0, a));
-  NT_LAUNCH_OK();
   NT_CHECK(launch_k(vit_fwd_kernel<D, H>, dim3(B), dim3(256), C::FWD_SMEM, a));
   NT_LAUNCH_OK();
   return 0;
@@ -1182,6 +1187,7 @@ static bool supported(int N, int D, int H) {
     if (D == 32 && H == 2) return fn<32, 2>(__VA_ARGS__);                  \
   } while (0)
 
+static int run_split(const Args& a, int D, int H) { VB_DISPATCH(launch_split, a, 0); return 2; }
 static int run_fwd(const Args& a, int B, int D, int H) { VB_DISPATCH(launch_fwd, a, B); return 2; }
 static int run_bwd(const Args& a, int B, int D, int H) { VB_DISPATCH(launch_bwd, a, B); return 2; }
 
@@ -1207,7 +1213,17 @@ int nt_vit_blocks_save_bytes(int D, size_t* bytes_per_image) {
   return 0;
 }
 
-int nt_vit_blocks_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H) {
+int nt_vit_blocks_prepare(const NtVitBlock* blocks, int nblocks, int D, int H) {
+  NT_ENTRY();
+  NT_REQUIRE(vb::supported(1, D, H), "nt_vit_blocks_prepare: unsupported shape D=%d H=%d", D, H);
+  NT_REQUIRE(nblocks >= 1 && nblocks <= vb::MAXB, "nt_vit_blocks_prepare: 1..%d blocks per call, got %d", vb::MAXB, nblocks);
+  vb::Args a{};
+  for (int i = 0; i < nblocks; i++) a.blk[i] = blocks[i];
+  a.nblocks = nblocks;
+  return vb::run_split(a, D, H);
+}
+
+int nt_vit_blocks_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H, int prepared) {
   NT_ENTRY();
   NT_REQUIRE(vb::supported(N, D, H), "nt_vit_blocks_fwd: unsupported shape N=%d D=%d H=%d", N, D, H);
   NT_REQUIRE(nblocks >= 1 && nblocks <= vb::MAXB, "nt_vit_blocks_fwd: 1..%d blocks per call, got %d", vb::MAXB, nblocks);
@@ -1215,6 +1231,9 @@ int nt_vit_blocks_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int
   vb::Args a{};
   for (int i = 0; i < nblocks; i++) a.blk[i] = blocks[i];
   a.nblocks = nblocks; a.N = N; a.x = x;
+  if (!prepared) {
+    if (int rc = vb::run_split(a, D, H)) return rc;
+  }
   return vb::run_fwd(a, B, D, H);
 }
 

@@ -53,9 +53,25 @@ def _wfrag(layer, D):
     return w
 
 
-def _block_array(layers):
+def _null_ptr(x):
+    return None if x is None else x.ptr
+
+
+def prepare(layers):
+    """Split the current weights of `layers` into mma-fragment order ahead of forward_stack(..., prepared=True)."""
+    D, H = layers[0].embed_dim, layers[0].num_h
+    for l in layers:
+        _wfrag(l, D)
+    arr = _block_array(layers, weights_only=True)
+    lib.nt_vit_blocks_prepare(ctypes.addressof(arr), len(layers), D, H)
+
+
+def _block_array(layers, weights_only=False):
     arr = (NtVitBlock * len(layers))()
     for s, l in zip(arr, layers):
+        if weights_only:
+            s.wqkv, s.w0, s.w1, s.wfrag = l.qkvfc.params.ptr, l.fc0.params.ptr, l.fc1.params.ptr, l._wfrag.ptr
+            continue
         s.ln_g, s.ln_b = l.norm.gamma.ptr, l.norm.beta.ptr
         s.wqkv, s.bqkv = l.qkvfc.params.ptr, l.qkvfc.bias_params.ptr
         s.ln1_g, s.ln1_b = l.norm1.gamma.ptr, l.norm1.beta.ptr
@@ -72,7 +88,7 @@ def _block_array(layers):
     return arr
 
 
-def forward_stack(layers, x):
+def forward_stack(layers, x, prepared=False):
     """attention_layer.forward (attention.py:20-55) of every layer in `layers`, chained, in one launch."""
     B, N, D = x.shape
     H = layers[0].num_h
@@ -94,7 +110,7 @@ def forward_stack(layers, x):
     for prev, l in zip(layers, layers[1:]):
         l._x_in = prev._out
     arr = _block_array(layers)
-    lib.nt_vit_blocks_fwd(ctypes.addressof(arr), len(layers), x.ptr, B, N, D, H)
+    lib.nt_vit_blocks_fwd(ctypes.addressof(arr), len(layers), x.ptr, B, N, D, H, int(bool(prepared)))
     return layers[-1]._out
 
 

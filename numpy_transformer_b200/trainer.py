@@ -193,13 +193,18 @@ class TrainStep:
         x = self.d_in.view(c * in_elems, (bs,) + self.input_shape[1:])
         lab = self.d_lab.view(c * rows, (rows,))
         runs = {}                                    # start index -> fused run of ViT blocks (one launch each way)
+        early = {}     # runs whose weights were split ahead of time (fused_vit.prepare); measured: forking the split onto
+        # the side branch costs more in graph dependencies than the 5 us launch it hides, so it stays in the forward call
         i = 0
         while i < len(layers):
             l = layers[i]
             n = fused_vit.fusable_run(layers, i, self._vit_block_t, x.shape) if type(l) is self._vit_block_t else 0
             if n:
                 runs[i] = layers[i:i + n]
-                x = fused_vit.forward_stack(runs[i], x)
+                prepared = early.get(i) == n
+                if prepared:
+                    lib.nt_side_join()
+                x = fused_vit.forward_stack(runs[i], x, prepared=prepared)
                 i += n
                 continue
             if isinstance(l, self._block_t):

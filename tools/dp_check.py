@@ -19,12 +19,20 @@ def main():
     nt.init(int(os.environ.get("LOCAL_RANK", "0")))
     dp.init_nccl()
     world, rank = dp.world, dp.rank
+    worst_all = 0.0
+    for dim in (48, 64):            # 48: per-op path; 64: fused ViT-block kernels (csrc/vit_block.cu)
+        worst_all = max(worst_all, run(dp, world, rank, dim))
+    dp.shutdown()
+    sys.exit(0 if worst_all < 1e-4 else 1)
+
+
+def run(dp, world, rank, dim):
     per = 6
-    cfg = M.ViTConfig(batch=per * world, embed_dim=48, heads=4, blocks=2)
+    cfg = M.ViTConfig(batch=per * world, embed_dim=dim, heads=4, blocks=2)
     params = M.vit_init(cfg, 0)
     images, labels, onehot = M.synthetic_vit_batch(cfg, 1)
     lo, hi = shard_range(cfg.batch, rank, world)
-    layers = trainer.build_vit_layers(per, embed_dim=48, heads=4, blocks=2, seed=0)
+    layers = trainer.build_vit_layers(per, embed_dim=dim, heads=4, blocks=2, seed=0)
     ts = trainer.TrainStep(layers, "vit", (per,) + images.shape[1:], lr=0.02, dp=dp, grad_buckets=3)
     worst = 0.0
     for step in range(4):
@@ -40,10 +48,10 @@ def main():
             print("step %d loss %.6f (oracle %.6f) max rel param err %.2e graph=%s" % (step, loss, ref["loss"], err, ts.graph is not None), flush=True)
     worst = dp.max_over_ranks(worst)
     if rank == 0:
-        print("DP_CHECK world=%d worst=%.2e %s" % (world, worst, "OK" if worst < 1e-4 else "FAIL"), flush=True)
+        fused = any(getattr(l, "_fused", False) for l in layers)
+        print("DP_CHECK world=%d dim=%d fused=%s worst=%.2e %s" % (world, dim, fused, worst, "OK" if worst < 1e-4 else "FAIL"), flush=True)
     ts.close()
-    dp.shutdown()
-    sys.exit(0 if worst < 1e-4 else 1)
+    return worst
 
 
 main()
