@@ -259,6 +259,17 @@ def run_ours(args):
         roof = dict(bound="hbm", kernel=tname, achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
                     traffic=None, share_of_step=tc["ms"] / total_ms, launches_per_step=tc["n"] / prof_steps,
                     peak_source=pk["source"] + " copy")
+    # traffic: DRAM bytes of the dominant op from the committed ncu capture (null when none was taken for this workload)
+    try:
+        roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload, {}).get(tname)
+    except Exception:
+        pass
+    if tname.startswith("nt_vit_blocks"):
+        # the fused blocks execute every product as three BF16 MMA passes on 64 padded rows per 49-token image
+        roof["executed_mma_tflops"] = ach * 3.0 * 64.0 / 49.0
+        roof["note"] = ("algorithmic FLOPs / measured time vs the dense BF16 tcgen05 peak; the kernel issues 3 BF16 mma.sync passes "
+                        "per product (fp32-class accuracy) on 64/49 padded rows with one image per CTA (B of 148 SMs busy); the "
+                        "legacy mma.sync path peaks at 556 TFLOP/s chip-wide (tools/mma_red_bench.cu)")
     fl_step = step_flops(kind, c)
     step_tf = fl_step * world / (dev_s_max / K) / 1e12
     op_table = sorted(((n, round(v["ms"] / prof_steps, 4), v["n"] // prof_steps,
