@@ -88,6 +88,23 @@ int nt_linear_bwd_input(const float* dy, const float* w, float* dx,
  * db may be NULL. Accumulates. */
 int nt_linear_bwd_params(const float* x, const float* dy, float* dw, float* db, int M, int K, int N);
 
+/* BF16x3 engine for the large Linear shapes (fp32-class accuracy at twice the tensor rate of the TF32 split):
+ * every fp32 operand is first split in HBM into hi = bf16(x), lo = bf16(x - hi) (optionally transposed so that the
+ * contraction dimension is contiguous), then the GEMM accumulates lo*hi + hi*lo + hi*hi with tcgen05 kind::f16.
+ * nt_split_bf16: x [rows, cols] fp32 -> planes hi / lo of bf16; transpose = 0: [rows][ld_out] (ld_out >= cols),
+ * transpose = 1: [cols][ld_out] (ld_out >= rows, pad to a multiple of 8). */
+int nt_split_bf16(const float* x, void* hi, void* lo, int rows, int cols, int ld_out, int transpose);
+/* fclayer.forward (net/fullconnect.py:99-106) from split x [M][K] and split w^T [N][K]; epilogue as nt_linear_fwd. */
+int nt_linear_fwd_bf16x3(const void* x_hi, const void* x_lo, const void* wt_hi, const void* wt_lo, const float* b, float* y,
+                         int M, int K, int N, int act, float* pre, const float* residual);
+/* fclayer.backward input half (:114) from split dy [M][N] and split w [K][N]; epilogue as nt_linear_bwd_input. */
+int nt_linear_bwd_input_bf16x3(const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, float* dx, int M, int K,
+                               int N, int act, const float* pre, const float* addend);
+/* fclayer.backward parameter half (:118-125) from transposed splits x^T [K][ld_t], dy^T [N][ld_t] (ld_t >= M);
+ * db (may be NULL) += colsum(dy) from the fp32 dy.  Accumulates. */
+int nt_linear_bwd_params_bf16x3(const void* xt_hi, const void* xt_lo, const void* dyt_hi, const void* dyt_lo, int ld_t,
+                                const float* dy, float* dw, float* db, int M, int K, int N);
+
 /* ---------------------------------------------------------------- LayerNorm (net/layernorm.py) */
 /* layer_norm.forward, net/layernorm.py:88-114: rows of width D, biased variance, eps inside sqrt.
  * mean/rstd (length M) are kept for backward.  post_add (may be NULL) is a [period,D] table added

@@ -110,6 +110,9 @@ struct GemmDesc {
   int nb0 = 1, nb1 = 1;
   long long bA0 = 0, bA1 = 0, bB0 = 0, bB1 = 0, bC0 = 0, bC1 = 0;
   int splitk = 1;
+  // optional pre-split operands (bf16 hi/lo, contraction dim contiguous): A_b[M][lda_b], B_b[N][ldb_b] -> BF16x3 tcgen05 path
+  const void* A_hi = nullptr; const void* A_lo = nullptr; const void* B_hi = nullptr; const void* B_lo = nullptr;
+  long long lda_b = 0, ldb_b = 0;
   bool* colsum_done = nullptr;       // set by the engine that fused ep.colsum
   Epilogue ep;
 };

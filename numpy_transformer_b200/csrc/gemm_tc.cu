@@ -37,6 +37,7 @@ struct TcParams {
   int dbg_skip_a;         // experiment: do not load A (results are garbage)
   int dbg_mma;            // experiment: MMAs issued per k-block (default 4)
   int a_3d, b_3d;         // MN-major operand described by a 3-D map {32, k, chunk}: one TMA per k-block
+  int bf16;               // 1: operands are pre-split bf16 hi/lo K-major copies (4 tensor maps), kind::f16, 64 k per stage
   long long ldc;
   float* C;
   Epilogue ep;
@@ -92,6 +93,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint6
       ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -140,7 +148,8 @@ __device__ unsigned long long g_tc_times[16384 * 8];
 // 4-row store group, which measured ~250 cycles per group on a path that runs once per CTA.
 template <int ACT, int DACT, bool PRE_OUT, bool ATOMIC, bool ADDEND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages] x { A hi | B hi | (A lo | B lo) }, then barriers
   // offset arithmetic on the __shared__ array (not on a generic uintptr_t) keeps the address space known,
@@ -161,7 +170,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TC_STAMP(0);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * p.BN;
-  const int total_kb = (p.K + BK - 1) / BK;
+  const int bke = p.bf16 ? 2 * BK : BK;        // elements per 128-byte k-block row (bf16: 64, fp32: 32)
+  const int total_kb = (p.K + bke - 1) / bke;
   const int kb_begin = blockIdx.z * p.kblocks_per_split;
   const int kb_end = min(total_kb, kb_begin + p.kblocks_per_split);
   const int nkb = kb_end - kb_begin;       // >= 1 by construction of the grid
@@ -174,7 +184,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int s = i % p.stages;
     uint8_t* st = smem + (size_t)s * stage_bytes;
     const uint32_t sa = smem_u32(st), sb = sa + a_bytes_;
-    const int k0 = (kb_begin + i) * BK;
+    const int k0 = (kb_begin + i) * bke;
+    if (p.bf16) {
+      // pre-split operands: hi and lo tiles of A and B arrive by TMA (no in-kernel conversion)
+      mbar_expect_tx(&full[s], 2 * (a_bytes_ + b_bytes));
+      tma_load_2d(sa, &tmA, &full[s], k0, m0);                              // box {64 k, 128 m} bf16
+      tma_load_2d(sb, &tmB, &full[s], k0, n0);                              // box {64 k, BN n}
+      tma_load_2d(sb + b_bytes, &tmAl, &full[s], k0, m0);
+      tma_load_2d(sb + b_bytes + a_bytes_, &tmBl, &full[s], k0, n0);
+      return;
+    }
     mbar_expect_tx(&full[s], (p.dbg_skip_a ? 0 : a_bytes_) + b_bytes);
     if (p.dbg_skip_a) {
     } else if (!p.a_mn) {
@@ -199,6 +218,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    if (p.bf16) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAl)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBl)) : "memory");
+    }
     for (int s = 0; s < p.stages; s++) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], (p.passes == 1 && do_colsum) ? 1 + TC_WORKERS : 1);
@@ -237,7 +260,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer (one lane) =====================
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+      // (A/B format: 2 = TF32 for kind::tf32; 1 = BF16 for kind::f16)
+      const uint32_t fmt = p.bf16 ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                              ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       // per-MMA (K = 8 fp32) start-address advance and descriptor strides
       const uint32_t a_adv = p.a_mn ? 8 * 128 : 32, b_adv = p.b_mn ? 8 * 128 : 32;
@@ -249,7 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = 0; i < nkb; i++) {
         const int s = i % p.stages;
         const uint32_t ph = (i / p.stages) & 1;
-        mbar_wait(p.passes == 3 ? &conv[s] : &full[s], ph);
+        mbar_wait((p.passes == 3 && !p.bf16) ? &conv[s] : &full[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
         const uint32_t sal = sb + b_bytes, sbl = sal + a_bytes;
@@ -258,7 +283,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (k >= p.dbg_mma && p.dbg_mma < 4) break;
           const uint64_t ah = make_smem_desc(sa + k * a_adv, a_lbo, a_sbo, a_lay);
           const uint64_t bh = make_smem_desc(sb + k * b_adv, b_lbo, b_sbo, b_lay);
-          if (p.passes == 3) {
+          if (p.bf16) {
+            // 16 bf16 per MMA = the same 32-byte advance as 8 fp32: descriptors are identical to the K-major fp32 case
+            const uint64_t al = make_smem_desc(sal + k * a_adv, a_lbo, a_sbo, a_lay);
+            const uint64_t bl = make_smem_desc(sbl + k * b_adv, b_lbo, b_sbo, b_lay);
+            umma_f16(tmem_base, al, bh, idesc, accum);       // small terms first
+            umma_f16(tmem_base, ah, bl, idesc, 1);
+            umma_f16(tmem_base, ah, bh, idesc, 1);
+          } else if (p.passes == 3) {
             const uint64_t al = make_smem_desc(sal + k * a_adv, a_lbo, a_sbo, a_lay);
             const uint64_t bl = make_smem_desc(sbl + k * b_adv, b_lbo, b_sbo, b_lay);
             umma_tf32(tmem_base, al, bh, idesc, accum);      // small terms first
@@ -281,7 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float4 cs[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) cs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.passes == 3 || do_colsum) {
+    if ((p.passes == 3 && !p.bf16) || do_colsum) {
       const uint32_t hi_bytes = a_bytes + b_bytes;
       for (int i = 0; i < nkb; i++) {
         const int s = i % p.stages;
@@ -508,15 +540,30 @@ static int make_tmap(CUtensorMap* tm, const float* base, long long inner, long l
   return 0;
 }
 
+// 2-D bf16 K-major tensor map: `inner` contraction elements contiguous, `outer` rows of `ld` elements; box {64, box_outer}
+static int make_tmap_bf16(CUtensorMap* tm, const void* base, long long inner, long long outer, long long ld, int box_outer) {
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(bf16) failed (%d) inner=%lld outer=%lld ld=%lld box=%d", (int)r, inner,
+             outer, ld, box_outer);
+  return 0;
+}
+
 template <int ACT, int DACT, bool PRE_OUT, bool ATOMIC, bool ADDEND>
-static int launch_tc(dim3 grid, size_t smem, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
+static int launch_tc(dim3 grid, size_t smem, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmAl,
+                     const CUtensorMap& tmBl, const TcParams& p) {
   static bool configured = false;
   if (!configured) {
     NT_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<ACT, DACT, PRE_OUT, ATOMIC, ADDEND>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     configured = true;
   }
-  NT_CHECK(nt::launch_k(gemm_tc_kernel<ACT, DACT, PRE_OUT, ATOMIC, ADDEND>, dim3(grid), dim3(TC_THREADS), smem, tmA, tmB, p));
+  NT_CHECK(nt::launch_k(gemm_tc_kernel<ACT, DACT, PRE_OUT, ATOMIC, ADDEND>, dim3(grid), dim3(TC_THREADS), smem, tmA, tmB, tmAl, tmBl, p));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -563,12 +610,20 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   *handled = false;
   if (d.nb0 * d.nb1 != 1) return 0;                       // batched (attention) shapes stay on the SIMT path
   if (d.M < 1 || d.N < 8 || d.K < 1) return 0;
-  const bool a_k = (d.sAk == 1), a_mn = (d.sAm == 1 && !a_k);
-  const bool b_k = (d.sBk == 1), b_mn = (d.sBn == 1 && !b_k);
+  // pre-split bf16 hi/lo K-major operands (A_b[M][lda_b], B_b[N][ldb_b]): error-compensated BF16x3 on kind::f16
+  const bool bf = (d.A_hi != nullptr) && passes == 3;
+  const bool a_k = bf || (d.sAk == 1), a_mn = !bf && (d.sAm == 1 && !a_k);
+  const bool b_k = bf || (d.sBk == 1), b_mn = !bf && (d.sBn == 1 && !b_k);
   if (!(a_k || a_mn) || !(b_k || b_mn)) return 0;
-  const long long lda = a_k ? d.sAm : d.sAk, ldb = b_k ? d.sBn : d.sBk;
+  const long long lda = bf ? d.lda_b : (a_k ? d.sAm : d.sAk), ldb = bf ? d.ldb_b : (b_k ? d.sBn : d.sBk);
   // TMA needs 16-byte aligned bases and row pitches
-  if ((lda & 3) || (ldb & 3) || ((uintptr_t)d.A & 15) || ((uintptr_t)d.B & 15)) return 0;
+  if (bf) {
+    if ((lda & 7) || (ldb & 7) || ((uintptr_t)d.A_hi & 15) || ((uintptr_t)d.A_lo & 15) || ((uintptr_t)d.B_hi & 15) ||
+        ((uintptr_t)d.B_lo & 15)) {
+      set_error("gemm_tc: bf16 operands need 16-byte aligned bases and pitches (lda %lld ldb %lld)", lda, ldb);
+      return 1;
+    }
+  } else if ((lda & 3) || (ldb & 3) || ((uintptr_t)d.A & 15) || ((uintptr_t)d.B & 15)) return 0;
   if (d.splitk > 1 && !d.ep.atomic) return 0;
   if (load_encode()) return 1;
 
@@ -582,13 +637,14 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   }
   p.a_mn = a_mn; p.b_mn = b_mn;
   p.passes = passes;
+  p.bf16 = bf ? 1 : 0;
   p.ldc = d.ldc;
   p.C = d.C;
   p.ep = d.ep;
   { const char* e = getenv("NTB200_DBG_MMA"); p.dbg_mma = e ? atoi(e) : 4; }
   { const char* e = getenv("NTB200_DBG_SKIP_A"); p.dbg_skip_a = (e && e[0] == '1') ? 1 : 0; }
   if (const char* e = getenv("NTB200_BN")) { int v = atoi(e); if (v == 32 || v == 64 || v == 96 || v == 128) p.BN = v; }
-  const int total_kb = ceil_div(d.K, BK);
+  const int total_kb = ceil_div(d.K, bf ? 2 * BK : BK);
   int splits = 1;
   if (d.splitk > 1) {
     // split the long contraction (dW: K = batch rows) so the grid covers the SMs; >= 4 k-blocks per split
@@ -610,24 +666,32 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   p.stages = stages;
   const size_t smem = stages * stage + (3 * stages + 2) * 8 + 16 + 128 * 4 + 1024;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmAl, tmBl;
+  if (bf) {
+    if (make_tmap_bf16(&tmA, d.A_hi, d.K, d.M, lda, BM) || make_tmap_bf16(&tmAl, d.A_lo, d.K, d.M, lda, BM) ||
+        make_tmap_bf16(&tmB, d.B_hi, d.K, d.N, ldb, p.BN) || make_tmap_bf16(&tmBl, d.B_lo, d.K, d.N, ldb, p.BN))
+      return 1;
+  }
   const bool use3d = getenv("NTB200_TMA_2D") == nullptr;
   p.a_3d = (a_mn && use3d && d.M % 32 == 0 && ld_ok3(lda)) ? 1 : 0;
   p.b_3d = (b_mn && use3d && d.N % 32 == 0 && ld_ok3(ldb)) ? 1 : 0;
-  if (a_k) { if (make_tmap(&tmA, d.A, d.K, d.M, lda, BM, false)) return 1; }
+  if (bf) {}
+  else if (a_k) { if (make_tmap(&tmA, d.A, d.K, d.M, lda, BM, false)) return 1; }
   else if (p.a_3d) { if (make_tmap_mn3d(&tmA, d.A, d.M, d.K, lda, BM / 32)) return 1; }
   else     { if (make_tmap(&tmA, d.A, d.M, d.K, lda, BK, true)) return 1; }
-  if (b_k) { if (make_tmap(&tmB, d.B, d.K, d.N, ldb, p.BN, false)) return 1; }
+  if (bf) {}
+  else if (b_k) { if (make_tmap(&tmB, d.B, d.K, d.N, ldb, p.BN, false)) return 1; }
   else if (p.b_3d) { if (make_tmap_mn3d(&tmB, d.B, d.N, d.K, ldb, p.BN / 32)) return 1; }
   else     { if (make_tmap(&tmB, d.B, d.N, d.K, ldb, BK, true)) return 1; }
 
+  if (!bf) { tmAl = tmA; tmBl = tmB; }
   dim3 grid(ceil_div(d.N, p.BN), ceil_div(d.M, BM), splits);
   const Epilogue& e = d.ep;
   int rc = -1;
 #define NT_TC_CASE(A_, D_, P_, T_, X_)                                                                   \
   if (rc < 0 && e.act == A_ && e.dact == D_ && (e.pre_out != nullptr) == P_ && (e.atomic != 0) == T_ &&   \
       (e.addend != nullptr) == X_)                                                                        \
-    rc = launch_tc<A_, D_, P_, T_, X_>(grid, smem, tmA, tmB, p);
+    rc = launch_tc<A_, D_, P_, T_, X_>(grid, smem, tmA, tmB, tmAl, tmBl, p);
   NT_TC_CASE(0, 0, false, false, false)   // y = xW + b ; dx = dy W^T
   NT_TC_CASE(0, 0, false, false, true)    // + residual
   NT_TC_CASE(NT_ACT_GELU, 0, true, false, false)

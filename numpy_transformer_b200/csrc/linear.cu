@@ -119,4 +119,63 @@ int nt_linear_bwd_params(const float* x, const float* dy, float* dw, float* db, 
   return 0;
 }
 
+// ---- BF16x3 variants: operands pre-split by nt_split_bf16 (hi/lo bf16, contraction dim contiguous)
+int nt_linear_fwd_bf16x3(const void* x_hi, const void* x_lo, const void* wt_hi, const void* wt_lo, const float* b, float* y,
+                         int M, int K, int N, int act, float* pre, const float* residual) {
+  NT_ENTRY();
+  NT_REQUIRE(M >= 0 && K > 0 && N > 0 && (K & 7) == 0, "nt_linear_fwd_bf16x3: bad shape M=%d K=%d N=%d (K %% 8)", M, K, N);
+  NT_REQUIRE(act >= 0 && act <= 2, "nt_linear_fwd_bf16x3: act %d", act);
+  if (M == 0) return 0;
+  GemmDesc d{};
+  d.C = y; d.M = M; d.N = N; d.K = K; d.ldc = N;
+  d.A_hi = x_hi; d.A_lo = x_lo; d.lda_b = K;          // x  [M][K]
+  d.B_hi = wt_hi; d.B_lo = wt_lo; d.ldb_b = K;        // w^T [N][K]
+  d.ep.bias = b; d.ep.act = act; d.ep.pre_out = pre; d.ep.addend = residual;
+  bool handled = false;
+  int rc = gemm_tc(d, 3, &handled);
+  if (rc) return rc;
+  NT_REQUIRE(handled, "nt_linear_fwd_bf16x3: shape/epilogue not supported by the tensor-core engine (M=%d K=%d N=%d)", M, K, N);
+  return 0;
+}
+
+int nt_linear_bwd_input_bf16x3(const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, float* dx, int M, int K,
+                               int N, int act, const float* pre, const float* addend) {
+  NT_ENTRY();
+  NT_REQUIRE(M >= 0 && K > 0 && N > 0 && (N & 7) == 0, "nt_linear_bwd_input_bf16x3: bad shape M=%d K=%d N=%d (N %% 8)", M, K, N);
+  if (M == 0) return 0;
+  GemmDesc d{};
+  d.C = dx; d.M = M; d.N = K; d.K = N; d.ldc = K;
+  d.A_hi = dy_hi; d.A_lo = dy_lo; d.lda_b = N;        // dy [M][N]
+  d.B_hi = w_hi; d.B_lo = w_lo; d.ldb_b = N;          // w  [K][N]: row k_in is output column k_in, contraction over N
+  d.ep.dact = act; d.ep.pre_in = pre; d.ep.addend = addend;
+  bool handled = false;
+  int rc = gemm_tc(d, 3, &handled);
+  if (rc) return rc;
+  NT_REQUIRE(handled, "nt_linear_bwd_input_bf16x3: shape/epilogue not supported by the tensor-core engine (M=%d K=%d N=%d)", M, K, N);
+  return 0;
+}
+
+int nt_linear_bwd_params_bf16x3(const void* xt_hi, const void* xt_lo, const void* dyt_hi, const void* dyt_lo, int ld_t,
+                                const float* dy, float* dw, float* db, int M, int K, int N) {
+  NT_ENTRY();
+  NT_REQUIRE(M >= 0 && K > 0 && N > 0 && (ld_t & 7) == 0 && ld_t >= M, "nt_linear_bwd_params_bf16x3: bad shape M=%d K=%d N=%d ld %d", M, K, N, ld_t);
+  if (M == 0) return 0;
+  GemmDesc d{};
+  d.C = dw; d.M = K; d.N = N; d.K = M; d.ldc = N;
+  d.A_hi = xt_hi; d.A_lo = xt_lo; d.lda_b = ld_t;     // x^T  [K][M]
+  d.B_hi = dyt_hi; d.B_lo = dyt_lo; d.ldb_b = ld_t;   // dy^T [N][M]
+  d.ep.atomic = 1;                                    // dw += (accumulate-until-setzero, fullconnect.py:120-121)
+  d.splitk = 2;
+  bool handled = false;
+  int rc = gemm_tc(d, 3, &handled);
+  if (rc) return rc;
+  NT_REQUIRE(handled, "nt_linear_bwd_params_bf16x3: shape not supported by the tensor-core engine (M=%d K=%d N=%d)", M, K, N);
+  if (db) {
+    const int rpb = 512;
+    NT_CHECK(nt::launch_k(colsum_kernel, dim3(ceil_div(N, 32), ceil_div(M, rpb)), dim3(32, 8), 0, dy, db, M, N, rpb));
+    NT_LAUNCH_OK();
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -2,11 +2,31 @@
 Nothing here touches the host copy of a tensor, so every function is graph-capturable."""
 import numpy as np
 from ._lib import lib
-from .device import DeviceArray, as_device, ptr_or_null, _prod
+from .device import DeviceArray, as_device, ptr_or_null, _prod, get_gemm_mode
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 MASK_NONE, MASK_CAUSAL, MASK_DENSE = 0, 1, 2
 LN_EPS = 1e-5        # net/layernorm.py:86
+
+
+def bf16x3_ok(M, K, N):
+    """Large Linear shapes in GEMM mode 1 run on the BF16x3 tcgen05 engine (operands split to bf16 hi/lo in HBM,
+    csrc/split_bf16.cu): fp32-class accuracy at twice the tensor rate of the in-kernel TF32 split.  Small shapes are
+    latency-bound and stay on the TF32x3 kernel (no extra split launches).  NTB200_BF16X3=0 disables it."""
+    import os
+    if os.environ.get("NTB200_BF16X3", "1") == "0" or get_gemm_mode() != 1:
+        return False
+    return M >= int(os.environ.get("NTB200_BF16X3_MIN_ROWS", "2048")) and K % 8 == 0 and N % 8 == 0 and K >= 32 and N >= 32
+
+
+def split_bf16(x, rows, cols, transpose=False):
+    """-> (hi, lo, pitch): bf16 planes of x [rows, cols] (or of its transpose, pitch padded to a multiple of 8)."""
+    ld = cols if not transpose else (rows + 7) // 8 * 8
+    out_rows = cols if transpose else rows
+    hi = DeviceArray((out_rows * ld // 2,))          # two bf16 per fp32 word
+    lo = DeviceArray((out_rows * ld // 2,))
+    lib.nt_split_bf16(x.ptr, hi.ptr, lo.ptr, int(rows), int(cols), int(ld), int(bool(transpose)))
+    return hi, lo, ld
 
 
 def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None):
@@ -15,6 +35,12 @@ def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None):
     M = x.size // K
     y = DeviceArray(x.shape[:-1] + (N,), host_dtype=x.host_dtype)
     pre = y.empty_like() if want_pre else None
+    if bf16x3_ok(M, K, N):
+        xh, xl, _ = split_bf16(x, M, K)
+        wh, wl, _ = split_bf16(w, K, N, transpose=True)            # w^T [N][K]
+        lib.nt_linear_fwd_bf16x3(xh.ptr, xl.ptr, wh.ptr, wl.ptr, ptr_or_null(b), y.ptr, M, K, N, act, ptr_or_null(pre),
+                                 ptr_or_null(residual))
+        return (y, pre) if want_pre else y
     lib.nt_linear_fwd(x.ptr, w.ptr, ptr_or_null(b), y.ptr, M, K, N, act, ptr_or_null(pre), ptr_or_null(residual))
     return (y, pre) if want_pre else y
 
@@ -23,6 +49,11 @@ def linear_bwd_input(dy, w, act=ACT_NONE, pre=None, addend=None):
     K, N = w.shape
     M = dy.size // N
     dx = DeviceArray(dy.shape[:-1] + (K,), host_dtype=dy.host_dtype)
+    if bf16x3_ok(M, N, K):
+        dh, dl, _ = split_bf16(dy, M, N)
+        wh, wl, _ = split_bf16(w, K, N)                            # w [K][N]: contraction over N is contiguous
+        lib.nt_linear_bwd_input_bf16x3(dh.ptr, dl.ptr, wh.ptr, wl.ptr, dx.ptr, M, K, N, act, ptr_or_null(pre), ptr_or_null(addend))
+        return dx
     lib.nt_linear_bwd_input(dy.ptr, w.ptr, dx.ptr, M, K, N, act, ptr_or_null(pre), ptr_or_null(addend))
     return dx
 
@@ -31,6 +62,11 @@ def linear_bwd_params(x, dy, dw, db=None):
     K, N = dw.shape
     M = dy.size // N
     assert x.size == M * K, "linear_bwd_params: x %s vs dy %s" % (x.shape, dy.shape)
+    if bf16x3_ok(M, K, N):
+        xh, xl, ld = split_bf16(x, M, K, transpose=True)           # x^T [K][M]
+        dh, dl, _ = split_bf16(dy, M, N, transpose=True)           # dy^T [N][M]
+        lib.nt_linear_bwd_params_bf16x3(xh.ptr, xl.ptr, dh.ptr, dl.ptr, ld, dy.ptr, dw.ptr, ptr_or_null(db), M, K, N)
+        return
     lib.nt_linear_bwd_params(x.ptr, dy.ptr, dw.ptr, ptr_or_null(db), M, K, N)
 
 
