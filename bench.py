@@ -98,6 +98,18 @@ def op_cost(name, a, kind, c):
     if name in ("nt_linear_fwd", "nt_linear_bwd_input", "nt_linear_bwd_params"):
         M, K, N = a[0], a[1], a[2]
         return 2.0 * M * K * N, 4.0 * (M * K + K * N + M * N)
+    if name in ("nt_linear_fwd_bf16x3", "nt_linear_bwd_input_bf16x3"):
+        M, K, N = a[0], a[1], a[2]
+        return 2.0 * M * K * N, 4.0 * (M * K + K * N + M * N)
+    if name == "nt_linear_bwd_params_bf16x3":
+        M, K, N = a[-3:]
+        return 2.0 * M * K * N, 4.0 * (M * K + K * N + M * N)
+    if name == "nt_split_bf16":
+        rows, cols = a[0], a[1]
+        return 0.0, 8.0 * rows * cols                       # read fp32, write bf16 hi + lo
+    if name == "nt_split_bf16_both":
+        rows, cols = a[0], a[1]
+        return 0.0, 12.0 * rows * cols                      # read fp32 once, write both layouts
     if name in ("nt_vit_blocks_fwd", "nt_vit_blocks_bwd"):
         # fused ViT block stack: L blocks x B images; per image and block the three Linear layers (7 D^2 weights)
         # and the attention core (QK^T and PV over N tokens); backward = 2x forward

@@ -94,6 +94,9 @@ int nt_linear_bwd_params(const float* x, const float* dy, float* dw, float* db, 
  * nt_split_bf16: x [rows, cols] fp32 -> planes hi / lo of bf16; transpose = 0: [rows][ld_out] (ld_out >= cols),
  * transpose = 1: [cols][ld_out] (ld_out >= rows, pad to a multiple of 8). */
 int nt_split_bf16(const float* x, void* hi, void* lo, int rows, int cols, int ld_out, int transpose);
+/* both layouts in one pass over x: hi / lo [rows][cols] and hi_t / lo_t [cols][ld_t] (a Linear layer's input feeds
+ * the forward GEMM as-is and the weight-gradient GEMM transposed; its output gradient feeds dX and dW likewise). */
+int nt_split_bf16_both(const float* x, void* hi, void* lo, void* hi_t, void* lo_t, int rows, int cols, int ld_t);
 /* fclayer.forward (net/fullconnect.py:99-106) from split x [M][K] and split w^T [N][K]; epilogue as nt_linear_fwd. */
 int nt_linear_fwd_bf16x3(const void* x_hi, const void* x_lo, const void* wt_hi, const void* wt_lo, const float* b, float* y,
                          int M, int K, int N, int act, float* pre, const float* residual);

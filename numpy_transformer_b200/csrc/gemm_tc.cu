@@ -662,6 +662,10 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   // single-pass tiles are small (32 KB/stage): with two stages three CTAs share an SM and one CTA's
   // prologue / epilogue hides behind another's main loop (measured 218 -> 115 us on 50176x384x1152)
   if (passes == 1 && (long long)ceil_div(d.N, p.BN) * ceil_div(d.M, BM) * splits >= 2LL * g_sm_count && stages > 2) stages = 2;
+  // pre-split bf16 tiles need no converter hand-off: with a short contraction (<= 16 k-blocks) one 64 KB stage lets
+  // three CTAs share an SM, so loads, MMAs and epilogues of different tiles overlap (measured on V2: forward / dX
+  // GEMMs 6.5 -> 4.6 ms); the long split-K weight-gradient contraction keeps the deep ring
+  if (bf && p.kblocks_per_split <= 16) stages = 1;
   if (const char* e = getenv("NTB200_STAGES")) { int v = atoi(e); if (v >= 1 && v <= stages) stages = v; }
   p.stages = stages;
   const size_t smem = stages * stage + (3 * stages + 2) * 8 + 16 + 128 * 4 + 1024;

@@ -37,8 +37,12 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
 }
 
 // transposing split: x [rows][cols] fp32 -> hiT / loT [cols][ld_out] (ld_out >= rows, % 4 == 0); 64 x 64 tiles
+// BOTH != 0: the same pass also writes the untransposed planes hi / lo [rows][cols] (cols % 4 == 0), so a tensor
+// that feeds one GEMM as-is and another transposed (x: forward and dW; dy: dX and dW) is read from HBM once.
+template <int BOTH>
 __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hiT,
-                                                              __nv_bfloat16* __restrict__ loT, int rows, int cols, int ld_out) {
+                                                              __nv_bfloat16* __restrict__ loT, int rows, int cols, int ld_out,
+                                                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   pdl_prologue();
   __shared__ float tile[64][65];
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
@@ -60,6 +64,14 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
       }
     }
     tile[r][c] = v.x; tile[r][c + 1] = v.y; tile[r][c + 2] = v.z; tile[r][c + 3] = v.w;
+    if (BOTH && r0 + r < rows && c0 + c < cols) {
+      uint2 h, l;
+      split2_bf16(v.x, v.y, h.x, l.x);
+      split2_bf16(v.z, v.w, h.y, l.y);
+      const long long o = (long long)(r0 + r) * cols + c0 + c;
+      *reinterpret_cast<uint2*>(hi + o) = h;
+      *reinterpret_cast<uint2*>(lo + o) = l;
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -94,9 +106,21 @@ int nt_split_bf16(const float* x, void* hi, void* lo, int rows, int cols, int ld
                       cols, ld_out));
   } else {
     NT_REQUIRE(ld_out >= rows, "nt_split_bf16: transposed pitch %d < rows %d", ld_out, rows);
-    NT_CHECK(launch_k(split_transpose_kernel, dim3(ceil_div(cols, 64), ceil_div(rows, 64)), dim3(256), 0, x,
-                      (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, cols, ld_out));
+    NT_CHECK(launch_k(split_transpose_kernel<0>, dim3(ceil_div(cols, 64), ceil_div(rows, 64)), dim3(256), 0, x,
+                      (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, cols, ld_out, (__nv_bfloat16*)nullptr,
+                      (__nv_bfloat16*)nullptr));
   }
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_split_bf16_both(const float* x, void* hi, void* lo, void* hi_t, void* lo_t, int rows, int cols, int ld_t) {
+  NT_ENTRY();
+  NT_REQUIRE(rows >= 0 && cols > 0 && (cols & 3) == 0 && (ld_t & 3) == 0 && ld_t >= rows,
+             "nt_split_bf16_both: rows %d cols %d (cols %% 4) ld_t %d", rows, cols, ld_t);
+  if (rows == 0) return 0;
+  NT_CHECK(launch_k(split_transpose_kernel<1>, dim3(ceil_div(cols, 64), ceil_div(rows, 64)), dim3(256), 0, x,
+                    (__nv_bfloat16*)hi_t, (__nv_bfloat16*)lo_t, rows, cols, ld_t, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo));
   NT_LAUNCH_OK();
   return 0;
 }

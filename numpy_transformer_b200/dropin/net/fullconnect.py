@@ -42,16 +42,29 @@ class fclayer(object):
     # --- extended forms used by the fused composite layers
     def _forward(self, x, act=ops.ACT_NONE, want_pre=False, residual=None):
         self.inputs = x
-        return ops.linear_fwd(x, self.params, self.bias_params if self.bias else None, act, want_pre, residual)
+        keep = []
+        out = ops.linear_fwd(x, self.params, self.bias_params if self.bias else None, act, want_pre, residual, keep_xt=keep)
+        self._xt = (x, keep[0]) if keep else None       # BF16x3 path: transposed split of x, made in the forward's pass
+        return out
 
     def _backward(self, dy, x, act=ops.ACT_NONE, pre=None, addend=None, want_dx=True):
+        K, N = self.params.shape
+        M = dy.size // N
+        xt = dy_split = dyt = None
+        if ops.bf16x3_ok(M, K, N):
+            cached = getattr(self, "_xt", None)
+            if cached is not None and cached[0] is x:
+                xt = cached[1]
+            if want_dx:
+                dy_split, dyt = ops.split_bf16_both(dy, M, N)      # dy feeds dX as-is and dW transposed: one pass
         # dW / db feed nothing on the backward critical path: inside a captured step they run on a side branch
         lib.nt_side_begin()
-        ops.linear_bwd_params(x, dy, self.params_delta, self.bias_delta)
+        ops.linear_bwd_params(x, dy, self.params_delta, self.bias_delta, xt_split=xt, dyt_split=dyt)
         lib.nt_side_end()
+        self._xt = None
         if not want_dx:
             return None
-        return ops.linear_bwd_input(dy, self.params, act, pre, addend)
+        return ops.linear_bwd_input(dy, self.params, act, pre, addend, dy_split=dy_split)
 
     # --- reference protocol
     def forward(self, inputs):

@@ -29,14 +29,29 @@ def split_bf16(x, rows, cols, transpose=False):
     return hi, lo, ld
 
 
-def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None):
+def split_bf16_both(x, rows, cols):
+    """-> ((hi, lo), (hi_t, lo_t, pitch)): both layouts of x [rows, cols] from one pass over the fp32 tensor."""
+    ld = (rows + 7) // 8 * 8
+    hi, lo = DeviceArray((rows * cols // 2,)), DeviceArray((rows * cols // 2,))
+    hit, lot = DeviceArray((cols * ld // 2,)), DeviceArray((cols * ld // 2,))
+    lib.nt_split_bf16_both(x.ptr, hi.ptr, lo.ptr, hit.ptr, lot.ptr, int(rows), int(cols), int(ld))
+    return (hi, lo), (hit, lot, ld)
+
+
+def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None, keep_xt=None):
+    """keep_xt: a list; on the BF16x3 path the transposed split of x (operand of the weight-gradient GEMM) is
+    produced in the same pass as the forward operand and appended to it for linear_bwd_params."""
     K, N = w.shape
     assert x.shape[-1] == K, "linear_fwd: input feature %d != %d" % (x.shape[-1], K)
     M = x.size // K
     y = DeviceArray(x.shape[:-1] + (N,), host_dtype=x.host_dtype)
     pre = y.empty_like() if want_pre else None
     if bf16x3_ok(M, K, N):
-        xh, xl, _ = split_bf16(x, M, K)
+        if keep_xt is not None:
+            (xh, xl), xt = split_bf16_both(x, M, K)
+            keep_xt.append(xt)
+        else:
+            xh, xl, _ = split_bf16(x, M, K)
         wh, wl, _ = split_bf16(w, K, N, transpose=True)            # w^T [N][K]
         lib.nt_linear_fwd_bf16x3(xh.ptr, xl.ptr, wh.ptr, wl.ptr, ptr_or_null(b), y.ptr, M, K, N, act, ptr_or_null(pre),
                                  ptr_or_null(residual))
@@ -45,12 +60,12 @@ def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None):
     return (y, pre) if want_pre else y
 
 
-def linear_bwd_input(dy, w, act=ACT_NONE, pre=None, addend=None):
+def linear_bwd_input(dy, w, act=ACT_NONE, pre=None, addend=None, dy_split=None):
     K, N = w.shape
     M = dy.size // N
     dx = DeviceArray(dy.shape[:-1] + (K,), host_dtype=dy.host_dtype)
     if bf16x3_ok(M, N, K):
-        dh, dl, _ = split_bf16(dy, M, N)
+        dh, dl = dy_split if dy_split is not None else split_bf16(dy, M, N)[:2]
         wh, wl, _ = split_bf16(w, K, N)                            # w [K][N]: contraction over N is contiguous
         lib.nt_linear_bwd_input_bf16x3(dh.ptr, dl.ptr, wh.ptr, wl.ptr, dx.ptr, M, K, N, act, ptr_or_null(pre), ptr_or_null(addend))
         return dx
@@ -58,13 +73,13 @@ def linear_bwd_input(dy, w, act=ACT_NONE, pre=None, addend=None):
     return dx
 
 
-def linear_bwd_params(x, dy, dw, db=None):
+def linear_bwd_params(x, dy, dw, db=None, xt_split=None, dyt_split=None):
     K, N = dw.shape
     M = dy.size // N
     assert x.size == M * K, "linear_bwd_params: x %s vs dy %s" % (x.shape, dy.shape)
     if bf16x3_ok(M, K, N):
-        xh, xl, ld = split_bf16(x, M, K, transpose=True)           # x^T [K][M]
-        dh, dl, _ = split_bf16(dy, M, N, transpose=True)           # dy^T [N][M]
+        xh, xl, ld = xt_split if xt_split is not None else split_bf16(x, M, K, transpose=True)      # x^T [K][M]
+        dh, dl, _ = dyt_split if dyt_split is not None else split_bf16(dy, M, N, transpose=True)    # dy^T [N][M]
         lib.nt_linear_bwd_params_bf16x3(xh.ptr, xl.ptr, dh.ptr, dl.ptr, ld, dy.ptr, dw.ptr, ptr_or_null(db), M, K, N)
         return
     lib.nt_linear_bwd_params(x.ptr, dy.ptr, dw.ptr, ptr_or_null(db), M, K, N)
