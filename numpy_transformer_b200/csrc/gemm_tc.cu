@@ -643,7 +643,7 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   p.ep = d.ep;
   { const char* e = getenv("NTB200_DBG_MMA"); p.dbg_mma = e ? atoi(e) : 4; }
   { const char* e = getenv("NTB200_DBG_SKIP_A"); p.dbg_skip_a = (e && e[0] == '1') ? 1 : 0; }
-  if (const char* e = getenv("NTB200_BN")) { int v = atoi(e); if (v == 32 || v == 64 || v == 96 || v == 128) p.BN = v; }
+  if (const char* e = getenv("NTB200_BN")) { int v = atoi(e); if (v == 32 || v == 64 || v == 96 || v == 128 || (bf && v == 256 && d.N >= 256)) p.BN = v; }
   const int total_kb = ceil_div(d.K, bf ? 2 * BK : BK);
   int splits = 1;
   if (d.splitk > 1) {

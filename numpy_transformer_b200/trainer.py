@@ -117,6 +117,16 @@ class ParamArena:
                     setattr(obj, name, nv)
         self.n_params = sum(getattr(o, pn).size for o, pn, *_ in slots)
 
+    def first_offset(self, layer):
+        """Arena offset of the first parameter slot owned by `layer` (None if it has no parameters)."""
+        if not hasattr(layer, "_slots"):
+            return None
+        owned = {id(s[0]) for s in layer._slots()}
+        for (obj, *_), off in zip(self.slots, self.offsets):
+            if id(obj) in owned:
+                return off
+        return None
+
     def share_with(self, layers):
         """Point another replica of the same layer list (same constructor order) at these arenas: the
         replica keeps its own activations but reads / accumulates the same parameters and gradients."""
@@ -222,6 +232,16 @@ class TrainStep:
         while i >= 0:
             l = layers[i]
             if i in ends:
+                if self.dp is not None and self.dp.world > 1 and len(self.chains) == 1 and self._early_from is None:
+                    # data parallel: the gradients of everything AFTER the fused stack (final LayerNorm + head, more than
+                    # half of the V1 arena) are complete -> all-reduce them now, under the fused backward launch
+                    offs = [self.arena.first_offset(l) for l in layers[i + 1:]]
+                    offs = [o for o in offs if o is not None]
+                    if offs:
+                        lib.nt_side_join()
+                        lo = min(offs)
+                        lib.nt_dp_allreduce_sum(self.arena.grads.ptr + 4 * lo, self.arena.n - lo)
+                        self._early_from = lo
                 delta = fused_vit.backward_stack(runs[ends[i]], delta)
                 i = ends[i] - 1
                 continue
@@ -235,6 +255,7 @@ class TrainStep:
     def _enqueue(self):
         nc = len(self.chains)
         outs = []
+        self._early_from = None          # arena offset from which the gradients were all-reduced early (DP only)
         for c, layers in enumerate(self.chains):
             if nc > 1:
                 lib.nt_chain_begin(c)
@@ -248,7 +269,10 @@ class TrainStep:
         a = self.arena
         lib.nt_side_join()                       # weight-gradient branch must land before all-reduce / update
         if self.dp is not None and self.dp.world > 1:
-            self.dp.allreduce_buckets(a.grads, self.grad_buckets)
+            if self._early_from is None:
+                self.dp.allreduce_buckets(a.grads, self.grad_buckets)
+            elif self._early_from > 0:
+                self.dp.allreduce_buckets(a.grads.view(0, (self._early_from,)), self.grad_buckets)
             lib.nt_dp_join()
         if self.adam:
             lib.nt_adam_star(a.params.ptr, a.grads.ptr, a.m.ptr, a.v.ptr, a.n, 0.0, self.d_lr.ptr, 0, self.d_t.ptr, 1)
