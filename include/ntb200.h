@@ -144,7 +144,9 @@ int nt_scale(float* x, float alpha, size_t n);
 #define NT_MASK_DENSE 2
 int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S,
                      int B, int N, int H, int dh, const float* residual);
-/* dqkv[B,N,3*H*dh] from dout[B,N,H*dh]; scratch must hold B*H*N*N floats (dS) when N > 64.
+/* dqkv[B,N,3*H*dh] from dout[B,N,H*dh]; scratch must hold B*H*N*N floats (dS) when N > 64.  With dh == 64 in GEMM
+ * mode 1 a non-NULL scratch of >= B*H*N floats selects the BF16x3 kernels (attention_bf16.cu: dS is recomputed,
+ * only the softmax-backward row sums are parked in scratch).
  * mask_kind is the forward's mask kind: NT_MASK_CAUSAL lets the kernels skip the upper-triangular
  * blocks (P is exactly 0 there); any other value processes the full matrix. */
 int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch,

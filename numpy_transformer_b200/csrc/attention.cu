@@ -6,6 +6,11 @@
 #include <cstdlib>
 
 namespace nt {
+bool attention_bf16_ok(int N, int H, int dh);
+int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S, int B, int N, int H,
+                       const float* residual);
+int attention_bwd_bf16(const float* dout, const float* qkv, const float* P, float* dqkv, float* tsum, int B, int N, int H,
+                       int causal);
 
 // p = softmax(x + mask) along rows; one warp per row. mask_kind as in ntb200.h; qi = row % N.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, float* __restrict__ p,
@@ -1080,6 +1085,7 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
   NT_REQUIRE(mask_kind != NT_MASK_DENSE || mask, "nt_attention_fwd: dense mask_kind needs a mask");
   if (B == 0) return 0;
   const int D = H * dh;
+  if (nt::attention_bf16_ok(N, H, dh)) return nt::attention_fwd_bf16(qkv, mask, mask_kind, out, P, S, B, N, H, residual);
   if (const char* e = getenv("NTB200_ATT_MMA")) g_att_mma = (e[0] != '0');
   if (mma_ok(N, dh)) {
     if (dh == 24) {
@@ -1157,6 +1163,9 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
   NT_REQUIRE(B >= 0 && N > 0 && H > 0 && dh > 0, "nt_attention_bwd: bad shape");
   if (B == 0) return 0;
   const int D = H * dh;
+  // BF16x3 kernels (attention_bf16.cu): `scratch` only carries the B*H*N softmax-backward row sums
+  if (scratch && nt::attention_bf16_ok(N, H, dh))
+    return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0);
   if (mma_ok(N, dh)) {
     if (dh == 24) {
       const size_t smem = bwd_mma_smem<24>();

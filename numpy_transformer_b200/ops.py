@@ -122,7 +122,12 @@ def attention_bwd(dout, qkv, P, H, mask_kind=MASK_NONE):
     D = three_d // 3
     dh = D // H
     dqkv = qkv.empty_like()
-    scratch = None if (N <= 64 and dh <= 64 and dh % 4 == 0) else P.empty_like()
+    import os
+    if (dh == 64 and N >= int(os.environ.get("NTB200_ATT_BF16_MIN_N", "65")) and get_gemm_mode() == 1
+            and os.environ.get("NTB200_ATT_BF16", "1") != "0"):
+        scratch = DeviceArray((B * H * N,))             # BF16x3 kernels: row sums of dP o P only
+    else:
+        scratch = None if (N <= 64 and dh <= 64 and dh % 4 == 0) else P.empty_like()
     lib.nt_attention_bwd(dout.ptr, qkv.ptr, P.ptr, dqkv.ptr, ptr_or_null(scratch), B, N, H, dh, int(mask_kind))
     return dqkv
 

@@ -242,6 +242,23 @@ def test_attention_core_vs_oracle(nt, B, N, H, dh, causal):
         assert rel_err(out2, O) < TOL
 
 
+@pytest.mark.parametrize("N,causal", [(49, False), (5, True), (64, True)])
+def test_attention_bf16_kernels_single_block(nt, N, causal, monkeypatch):
+    """The BF16x3 attention kernels (csrc/attention_bf16.cu) are only selected for N > 64 by default; force them
+    for single-block shapes so that path stays covered too."""
+    from numpy_transformer_b200 import ops, DeviceArray
+    monkeypatch.setenv("NTB200_ATT_BF16_MIN_N", "1")
+    rs = np.random.RandomState(N)
+    B, H, dh = 2, 3, 64
+    qkv, dout = rs.randn(B, N, 3 * H * dh) * 0.7, rs.randn(B, N, H * dh)
+    O, P, S = R.attention_fwd(qkv, H, M.causal_mask(N) if causal else None)
+    dq = DeviceArray.from_host(qkv)
+    out, dP, dS = ops.attention_fwd(dq, H, None, ops.MASK_CAUSAL if causal else ops.MASK_NONE, want_scores=True)
+    assert rel_err(out, O) < TOL and rel_err(dP, P) < TOL and rel_err(dS, S) < TOL
+    dqkv = ops.attention_bwd(DeviceArray.from_host(dout), dq, dP, H, ops.MASK_CAUSAL if causal else ops.MASK_NONE)
+    assert rel_err(dqkv, R.attention_bwd(dout, qkv, P, H)) < TOL
+
+
 def test_empty_batch_and_errors(nt):
     from net.fullconnect import fclayer
     from net.activation import Softmax
