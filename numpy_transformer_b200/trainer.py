@@ -328,15 +328,19 @@ class TrainStep:
         self._prof_buffers = keep.buffers
         return g, recs
 
-    def load(self, inputs, labels):
-        """Host -> pinned staging -> device (async on the compute stream)."""
-        np.copyto(self.h_in.array, np.asarray(inputs).reshape(self.input_shape), casting="unsafe")
-        np.copyto(self.h_lab.array, np.asarray(labels).reshape(-1), casting="unsafe")
+    def load(self, inputs=None, labels=None):
+        """Host -> pinned staging -> device (async on the compute stream).  With inputs / labels omitted the batch
+        is taken from the pinned staging buffers as they are (`self.h_in.array`, `self.h_lab.array`): a loader that
+        writes its batches straight into pinned memory skips the extra host copy / dtype cast."""
+        if inputs is not None:
+            np.copyto(self.h_in.array, np.asarray(inputs).reshape(self.input_shape), casting="unsafe")
+        if labels is not None:
+            np.copyto(self.h_lab.array, np.asarray(labels).reshape(-1), casting="unsafe")
         lib.nt_h2d(self.d_in.ptr, self.h_in.ptr, self.h_in.nbytes)
         lib.nt_h2d(self.d_lab.ptr, self.h_lab.ptr, self.h_lab.nbytes)
 
-    def step(self, inputs, labels, lr=None, want_argmax=False):
-        """End-to-end public call: host batch in, host loss (and argmax) out."""
+    def step(self, inputs=None, labels=None, lr=None, want_argmax=False):
+        """End-to-end public call: host batch in (or already in the pinned staging buffers), host loss (and argmax) out."""
         if lr is not None:
             self.set_lr(lr)
         self.load(inputs, labels)
