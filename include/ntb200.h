@@ -192,6 +192,39 @@ int nt_vit_blocks_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int
 int nt_vit_blocks_bwd(const NtVitBlock* blocks, int nblocks, const float* x, const float* dout, float* dx,
                       float* scratch, int B, int N, int D, int H);
 
+/* ---------------------------------------------------------------- the two ends of the launch-bound ViT step
+ * stem = PatchEmbed_flatten.forward/backward (PatchEmbed.py:22-49, patchnorm) + the positional add
+ * (Position_add.py:20-23); head = final layer_norm -> flatten -> classify_layer (classify.py:20-47, FC0 -> ReLU -> FC1)
+ * -> cross_entropy_loss (net/loss.py:46-51) + argmax (transformer_of_image.py:151) and the backward of all of them.
+ * Five launches instead of ~17 around the fused block stack.  All members are DEVICE pointers. */
+typedef struct NtVitEnds {
+  const float *images;                       /* [B,C,Hi,Wi] */
+  const float *wpe, *bpe, *pe_g, *pe_b;      /* patch Linear [C*h*w, D], [D]; patch LayerNorm gamma, beta [D] */
+  const float *pos;                          /* [N,D] table added after the LayerNorm (NULL: none) */
+  float *d_wpe, *d_bpe, *d_pe_g, *d_pe_b;    /* accumulate (+=) */
+  float *pe_lin;                             /* [B,N,D]  Linear output before the LayerNorm (kept for backward) */
+  float *pe_stat;                            /* [B,N,2]  mean, rstd of the patch LayerNorm */
+  float *x0;                                 /* [B,N,D]  stem output = input of the first block */
+  const float *xl;                           /* [B,N,D]  output of the last block */
+  const float *tl_g, *tl_b;                  /* final LayerNorm gamma, beta [D] */
+  const float *w0, *b0;                      /* classify fc0 [N*D, D0], [D0] */
+  const float *w1, *b1;                      /* classify fc1 [D0, C1], [C1] */
+  float *d_tl_g, *d_tl_b, *d_w0, *d_b0, *d_w1, *d_b1;   /* accumulate (+=) */
+  const int32_t *labels;                     /* [B] class indices */
+  float *tl_stat;                            /* [B,N,2] */
+  float *h0;                                 /* [B,D0]  fc0 accumulator: must be ZERO on entry, is zero again on return */
+  float *dh0;                                /* [B,D0] */
+  float *logits, *probs;                     /* [B,C1] */
+  int32_t *argmax;                           /* [B] np.argmax(probs, -1), first index on ties */
+  float *loss;                               /* scalar: sum_rows -log(p_label + 1e-10) / n_norm */
+  float *dxl;                                /* [B,N,D]  gradient w.r.t. xl */
+} NtVitEnds;
+int nt_vit_ends_supported(int B, int C, int Hi, int Wi, int n_patch, int D, int D0, int C1, int* ok);
+int nt_vit_stem_fwd(const NtVitEnds* e, int B, int C, int Hi, int Wi, int n_patch, int D);
+int nt_vit_stem_bwd(const NtVitEnds* e, const float* dx0, int B, int C, int Hi, int Wi, int n_patch, int D);
+/* forward, loss and backward of the head in three launches; n_norm is the GLOBAL row count under data parallelism */
+int nt_vit_head(const NtVitEnds* e, int B, int N, int D, int D0, int C1, float n_norm);
+
 /* ---------------------------------------------------------------- embeds */
 /* PatchEmbed_flatten.forward patch loops, PatchEmbed.py:22-36: (B,C,Hi,Wi) -> (B, n_patch^2, C*h*w) */
 int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, int n_patch);

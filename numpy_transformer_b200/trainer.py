@@ -193,9 +193,82 @@ class TrainStep:
         L = _import_layers()
         self._block_t = L["attdecoderblock_layer"]
         self._vit_block_t = L["attention_layer"]
+        self._layer_types = L
+
+    # ------------------------------------------------------------------ fully fused ViT step (README layer list)
+    def _vit_fast_plan(self, layers):
+        """The README layer list (transformer_of_image.py:56-77: PatchEmbed_flatten(patchnorm) -> fixed position table ->
+        attention blocks -> layer_norm -> flatten -> classify_layer(relu, no cls token)) at shapes the fused kernels
+        cover runs as 9 launches: stem, weight split, block stack, 3 x head, block stack backward, stem backward, update."""
+        if self.kind != "vit" or len(self.chains) != 1 or len(layers) < 6:
+            return None
+        L = self._layer_types
+        pe, pos, ln, fl, head = layers[0], layers[1], layers[-3], layers[-2], layers[-1]
+        blocks = layers[2:-3]
+        if not (type(pe) is L["PatchEmbed_flatten"] and type(pos) is L["Position_learnable"] and type(ln) is L["layer_norm"]
+                and type(fl) is L["flatten_layer"] and type(head) is L["classify_layer"]):
+            return None
+        if not (pe.patchnorm and pos.fixed and not head.cls_token and head.reluact and ln.elementwise_affine
+                and pe.fullconnect.bias and head.fc0.bias and head.fc1.bias):
+            return None
+        B, C, Hi, Wi = self.input_shape
+        N, D = pe.n_patch ** 2, pe.embed_dim
+        if Hi % pe.n_patch or Wi % pe.n_patch or not blocks:
+            return None
+        if fused_vit.fusable_run(layers, 2, self._vit_block_t, (B, N, D)) != len(blocks):
+            return None
+        D0, C1 = head.fc0.params.shape[1], head.fc1.params.shape[1]
+        if head.fc0.params.shape[0] != N * D or not fused_vit.ends_supported(B, C, Hi, Wi, pe.n_patch, D, D0, C1):
+            return None
+        return dict(pe=pe, pos=pos, ln=ln, head=head, blocks=blocks, B=B, C=C, Hi=Hi, Wi=Wi, N=N, D=D, D0=D0, C1=C1)
+
+    def _enqueue_vit_fast(self, plan, layers):
+        import ctypes
+        pe, pos, ln, head, blocks = plan["pe"], plan["pos"], plan["ln"], plan["head"], plan["blocks"]
+        B, C, Hi, Wi, N, D, D0, C1 = (plan[k] for k in ("B", "C", "Hi", "Wi", "N", "D", "D0", "C1"))
+        if getattr(self, "_ends_h0", None) is None:
+            self._ends_h0 = DeviceArray.zeros((B, D0))           # fc0 accumulator: zero between steps (the kernel re-zeroes it)
+        e = fused_vit.NtVitEnds()
+        x0, pe_lin, pe_stat = DeviceArray((B, N, D)), DeviceArray((B, N, D)), DeviceArray((B, N, 2))
+        tl_stat, dh0, dxl = DeviceArray((B, N, 2)), DeviceArray((B, D0)), DeviceArray((B, N, D))
+        logits, probs = DeviceArray((B, C1)), DeviceArray((B, C1))
+        fc, n0 = pe.fullconnect, pe.norm
+        e.images = self.d_in.ptr
+        e.wpe, e.bpe, e.pe_g, e.pe_b = fc.params.ptr, fc.bias_params.ptr, n0.gamma.ptr, n0.beta.ptr
+        e.pos = pos.table().ptr
+        e.d_wpe, e.d_bpe, e.d_pe_g, e.d_pe_b = fc.params_delta.ptr, fc.bias_delta.ptr, n0.gamma_delta.ptr, n0.beta_delta.ptr
+        e.pe_lin, e.pe_stat, e.x0 = pe_lin.ptr, pe_stat.ptr, x0.ptr
+        e.tl_g, e.tl_b = ln.gamma.ptr, ln.beta.ptr
+        e.w0, e.b0, e.w1, e.b1 = head.fc0.params.ptr, head.fc0.bias_params.ptr, head.fc1.params.ptr, head.fc1.bias_params.ptr
+        e.d_tl_g, e.d_tl_b = ln.gamma_delta.ptr, ln.beta_delta.ptr
+        e.d_w0, e.d_b0 = head.fc0.params_delta.ptr, head.fc0.bias_delta.ptr
+        e.d_w1, e.d_b1 = head.fc1.params_delta.ptr, head.fc1.bias_delta.ptr
+        e.labels = self.d_lab.ptr
+        e.tl_stat, e.h0, e.dh0 = tl_stat.ptr, self._ends_h0.ptr, dh0.ptr
+        e.logits, e.probs, e.argmax, e.loss = logits.ptr, probs.ptr, self.d_amax.ptr, self.d_loss.ptr
+        e.dxl = dxl.ptr
+        n0._lead = ln._lead = 2                                  # gamma/beta host shape after a forward (layernorm.py:105-108)
+        lib.nt_vit_stem_fwd(ctypes.addressof(e), B, C, Hi, Wi, pe.n_patch, D)
+        xl = fused_vit.forward_stack(blocks, x0)
+        e.xl = xl.ptr
+        lib.nt_vit_head(ctypes.addressof(e), B, N, D, D0, C1, self.n_norm)
+        if self.dp is not None and self.dp.world > 1:
+            # gradients of the final LayerNorm + head (the tail of the arena) are complete: all-reduce them under the
+            # fused backward launch
+            lo = min(o for o in (self.arena.first_offset(ln), self.arena.first_offset(head)) if o is not None)
+            lib.nt_dp_allreduce_sum(self.arena.grads.ptr + 4 * lo, self.arena.n - lo)
+            self._early_from = lo
+        dx0 = fused_vit.backward_stack(blocks, dxl)
+        lib.nt_vit_stem_bwd(ctypes.addressof(e), dx0.ptr, B, C, Hi, Wi, pe.n_patch, D)
+        probs._argmax = self.d_amax
+        self._ends_keep = (e, x0, pe_lin, pe_stat, tl_stat, dh0, dxl, logits, probs)
+        return logits, probs
 
     # ------------------------------------------------------------------ the step body (enqueue only)
     def _enqueue_chain(self, c, layers):
+        plan = self._vit_fast_plan(layers)
+        if plan is not None:
+            return self._enqueue_vit_fast(plan, layers)
         nc = len(self.chains)
         bs = self.input_shape[0] // nc
         rows = self.rows // nc
