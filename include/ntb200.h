@@ -103,7 +103,8 @@ int nt_linear_fwd_bf16x3(const void* x_hi, const void* x_lo, const void* wt_hi, 
 /* fclayer.backward input half (:114) from split dy [M][N] and split w [K][N]; epilogue as nt_linear_bwd_input. */
 int nt_linear_bwd_input_bf16x3(const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, float* dx, int M, int K,
                                int N, int act, const float* pre, const float* addend);
-/* fclayer.backward parameter half (:118-125) from transposed splits x^T [K][ld_t], dy^T [N][ld_t] (ld_t >= M);
+/* fclayer.backward parameter half (:118-125) from transposed splits x^T [K][ld_t], dy^T [N][ld_t] (ld_t >= M), or, with
+ * ld_t == 0, from the UNtransposed splits x [M][K], dy [M][N] (MN-major tensor-core operands: no transposed copies);
  * db (may be NULL) += colsum(dy) from the fp32 dy.  Accumulates. */
 int nt_linear_bwd_params_bf16x3(const void* xt_hi, const void* xt_lo, const void* dyt_hi, const void* dyt_lo, int ld_t,
                                 const float* dy, float* dw, float* db, int M, int K, int N);

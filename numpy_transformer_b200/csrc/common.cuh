@@ -113,6 +113,7 @@ struct GemmDesc {
   // optional pre-split operands (bf16 hi/lo, contraction dim contiguous): A_b[M][lda_b], B_b[N][ldb_b] -> BF16x3 tcgen05 path
   const void* A_hi = nullptr; const void* A_lo = nullptr; const void* B_hi = nullptr; const void* B_lo = nullptr;
   long long lda_b = 0, ldb_b = 0;
+  bool a_b_mn = false, b_b_mn = false;   // split operand stored [K][M] / [K][N] (MN-major) instead of [M][K] / [N][K]
   bool* colsum_done = nullptr;       // set by the engine that fused ep.colsum
   Epilogue ep;
 };

@@ -188,10 +188,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.bf16) {
       // pre-split operands: hi and lo tiles of A and B arrive by TMA (no in-kernel conversion)
       mbar_expect_tx(&full[s], 2 * (a_bytes_ + b_bytes));
-      tma_load_2d(sa, &tmA, &full[s], k0, m0);                              // box {64 k, 128 m} bf16
-      tma_load_2d(sb, &tmB, &full[s], k0, n0);                              // box {64 k, BN n}
-      tma_load_2d(sb + b_bytes, &tmAl, &full[s], k0, m0);
-      tma_load_2d(sb + b_bytes + a_bytes_, &tmBl, &full[s], k0, n0);
+      const uint32_t sal_ = sb + b_bytes, sbl_ = sal_ + a_bytes_;
+      if (!p.a_mn) {
+        tma_load_2d(sa, &tmA, &full[s], k0, m0);                            // box {64 k, 128 m} bf16
+        tma_load_2d(sal_, &tmAl, &full[s], k0, m0);
+      } else {
+        // MN-major: [k rows][64 m] boxes of 64 x 128 B, one per 64-wide chunk of the tile (chunk stride 8 KB)
+        for (int j = 0; j < BM / 64; j++) {
+          tma_load_2d(sa + j * 8192, &tmA, &full[s], m0 + 64 * j, k0);
+          tma_load_2d(sal_ + j * 8192, &tmAl, &full[s], m0 + 64 * j, k0);
+        }
+      }
+      if (!p.b_mn) {
+        tma_load_2d(sb, &tmB, &full[s], k0, n0);                            // box {64 k, BN n}
+        tma_load_2d(sbl_, &tmBl, &full[s], k0, n0);
+      } else {
+        for (int j = 0; j < p.BN / 64; j++) {
+          tma_load_2d(sb + j * 8192, &tmB, &full[s], n0 + 64 * j, k0);
+          tma_load_2d(sbl_ + j * 8192, &tmBl, &full[s], n0 + 64 * j, k0);
+        }
+      }
       return;
     }
     mbar_expect_tx(&full[s], (p.dbg_skip_a ? 0 : a_bytes_) + b_bytes);
@@ -265,11 +281,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                              ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       // per-MMA (K = 8 fp32) start-address advance and descriptor strides
-      const uint32_t a_adv = p.a_mn ? 8 * 128 : 32, b_adv = p.b_mn ? 8 * 128 : 32;
-      const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, a_sbo = p.a_mn ? 512 : 1024;
-      const uint32_t b_lbo = p.b_mn ? BK * 128 : 16, b_sbo = p.b_mn ? 512 : 1024;
-      const uint32_t a_lay = p.a_mn ? LAYOUT_SW128_BASE32B : LAYOUT_SW128;
-      const uint32_t b_lay = p.b_mn ? LAYOUT_SW128_BASE32B : LAYOUT_SW128;
+      // MN-major canonical layouts (cute mma_traits_sm100.hpp): 64-wide MN chunks of [k rows][128 B]; LBO = chunk
+      // stride, SBO = stride between swizzle atoms along K (8 k-rows for 16-bit SW128, 4 for the 32-bit BASE32B atom)
+      const uint32_t mn_adv = p.bf16 ? 16 * 128 : 8 * 128, mn_lbo = p.bf16 ? 64 * 128 : BK * 128, mn_sbo = p.bf16 ? 1024 : 512;
+      const uint32_t mn_lay = p.bf16 ? LAYOUT_SW128 : LAYOUT_SW128_BASE32B;
+      const uint32_t a_adv = p.a_mn ? mn_adv : 32, b_adv = p.b_mn ? mn_adv : 32;
+      const uint32_t a_lbo = p.a_mn ? mn_lbo : 16, a_sbo = p.a_mn ? mn_sbo : 1024;
+      const uint32_t b_lbo = p.b_mn ? mn_lbo : 16, b_sbo = p.b_mn ? mn_sbo : 1024;
+      const uint32_t a_lay = p.a_mn ? mn_lay : LAYOUT_SW128;
+      const uint32_t b_lay = p.b_mn ? mn_lay : LAYOUT_SW128;
       uint32_t accum = 0;
       for (int i = 0; i < nkb; i++) {
         const int s = i % p.stages;
@@ -612,8 +632,8 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   if (d.M < 1 || d.N < 8 || d.K < 1) return 0;
   // pre-split bf16 hi/lo K-major operands (A_b[M][lda_b], B_b[N][ldb_b]): error-compensated BF16x3 on kind::f16
   const bool bf = (d.A_hi != nullptr) && passes == 3;
-  const bool a_k = bf || (d.sAk == 1), a_mn = !bf && (d.sAm == 1 && !a_k);
-  const bool b_k = bf || (d.sBk == 1), b_mn = !bf && (d.sBn == 1 && !b_k);
+  const bool a_k = bf ? !d.a_b_mn : (d.sAk == 1), a_mn = bf ? d.a_b_mn : (d.sAm == 1 && !a_k);
+  const bool b_k = bf ? !d.b_b_mn : (d.sBk == 1), b_mn = bf ? d.b_b_mn : (d.sBn == 1 && !b_k);
   if (!(a_k || a_mn) || !(b_k || b_mn)) return 0;
   const long long lda = bf ? d.lda_b : (a_k ? d.sAm : d.sAk), ldb = bf ? d.ldb_b : (b_k ? d.sBn : d.sBk);
   // TMA needs 16-byte aligned bases and row pitches
@@ -638,6 +658,7 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   p.a_mn = a_mn; p.b_mn = b_mn;
   p.passes = passes;
   p.bf16 = bf ? 1 : 0;
+  if (bf && b_mn && (p.BN % 64)) p.BN = d.N > 64 ? 128 : 64;       // MN-major bf16 tiles come in 64-wide chunks
   p.ldc = d.ldc;
   p.C = d.C;
   p.ep = d.ep;
@@ -672,13 +693,17 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
 
   CUtensorMap tmA, tmB, tmAl, tmBl;
   if (bf) {
-    if (make_tmap_bf16(&tmA, d.A_hi, d.K, d.M, lda, BM) || make_tmap_bf16(&tmAl, d.A_lo, d.K, d.M, lda, BM) ||
-        make_tmap_bf16(&tmB, d.B_hi, d.K, d.N, ldb, p.BN) || make_tmap_bf16(&tmBl, d.B_lo, d.K, d.N, ldb, p.BN))
+    // K-major: [rows = M or N][K contiguous], box {64 k, rows of the tile}; MN-major: [K rows][M or N contiguous], box {64, 64}
+    if (a_mn ? (make_tmap_bf16(&tmA, d.A_hi, d.M, d.K, lda, 64) || make_tmap_bf16(&tmAl, d.A_lo, d.M, d.K, lda, 64))
+             : (make_tmap_bf16(&tmA, d.A_hi, d.K, d.M, lda, BM) || make_tmap_bf16(&tmAl, d.A_lo, d.K, d.M, lda, BM)))
+      return 1;
+    if (b_mn ? (make_tmap_bf16(&tmB, d.B_hi, d.N, d.K, ldb, 64) || make_tmap_bf16(&tmBl, d.B_lo, d.N, d.K, ldb, 64))
+             : (make_tmap_bf16(&tmB, d.B_hi, d.K, d.N, ldb, p.BN) || make_tmap_bf16(&tmBl, d.B_lo, d.K, d.N, ldb, p.BN)))
       return 1;
   }
   const bool use3d = getenv("NTB200_TMA_2D") == nullptr;
-  p.a_3d = (a_mn && use3d && d.M % 32 == 0 && ld_ok3(lda)) ? 1 : 0;
-  p.b_3d = (b_mn && use3d && d.N % 32 == 0 && ld_ok3(ldb)) ? 1 : 0;
+  p.a_3d = (!bf && a_mn && use3d && d.M % 32 == 0 && ld_ok3(lda)) ? 1 : 0;
+  p.b_3d = (!bf && b_mn && use3d && d.N % 32 == 0 && ld_ok3(ldb)) ? 1 : 0;
   if (bf) {}
   else if (a_k) { if (make_tmap(&tmA, d.A, d.K, d.M, lda, BM, false)) return 1; }
   else if (p.a_3d) { if (make_tmap_mn3d(&tmA, d.A, d.M, d.K, lda, BM / 32)) return 1; }

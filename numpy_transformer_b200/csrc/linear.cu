@@ -158,12 +158,20 @@ int nt_linear_bwd_input_bf16x3(const void* dy_hi, const void* dy_lo, const void*
 int nt_linear_bwd_params_bf16x3(const void* xt_hi, const void* xt_lo, const void* dyt_hi, const void* dyt_lo, int ld_t,
                                 const float* dy, float* dw, float* db, int M, int K, int N) {
   NT_ENTRY();
-  NT_REQUIRE(M >= 0 && K > 0 && N > 0 && (ld_t & 7) == 0 && ld_t >= M, "nt_linear_bwd_params_bf16x3: bad shape M=%d K=%d N=%d ld %d", M, K, N, ld_t);
+  NT_REQUIRE(M >= 0 && K > 0 && N > 0, "nt_linear_bwd_params_bf16x3: bad shape M=%d K=%d N=%d", M, K, N);
   if (M == 0) return 0;
   GemmDesc d{};
   d.C = dw; d.M = K; d.N = N; d.K = M; d.ldc = N;
-  d.A_hi = xt_hi; d.A_lo = xt_lo; d.lda_b = ld_t;     // x^T  [K][M]
-  d.B_hi = dyt_hi; d.B_lo = dyt_lo; d.ldb_b = ld_t;   // dy^T [N][M]
+  if (ld_t == 0) {
+    // untransposed splits x [M][K], dy [M][N]: both operands are MN-major for this GEMM (contraction over rows)
+    NT_REQUIRE((K & 7) == 0 && (N & 7) == 0, "nt_linear_bwd_params_bf16x3: K %d and N %d must be multiples of 8", K, N);
+    d.A_hi = xt_hi; d.A_lo = xt_lo; d.lda_b = K; d.a_b_mn = true;
+    d.B_hi = dyt_hi; d.B_lo = dyt_lo; d.ldb_b = N; d.b_b_mn = true;
+  } else {
+    NT_REQUIRE((ld_t & 7) == 0 && ld_t >= M, "nt_linear_bwd_params_bf16x3: transposed pitch %d (M=%d)", ld_t, M);
+    d.A_hi = xt_hi; d.A_lo = xt_lo; d.lda_b = ld_t;     // x^T  [K][M]
+    d.B_hi = dyt_hi; d.B_lo = dyt_lo; d.ldb_b = ld_t;   // dy^T [N][M]
+  }
   d.ep.atomic = 1;                                    // dw += (accumulate-until-setzero, fullconnect.py:120-121)
   d.splitk = 2;
   bool handled = false;

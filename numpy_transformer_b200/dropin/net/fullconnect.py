@@ -55,7 +55,10 @@ class fclayer(object):
             cached = getattr(self, "_xt", None)
             if cached is not None and cached[0] is x:
                 xt = cached[1]
-            if want_dx:
+            if ops._mn_major():
+                dh, dl, _ = ops.split_bf16(dy, M, N)               # one split of dy feeds dX and (MN-major) dW
+                dy_split, dyt = (dh, dl), (dh, dl, 0)
+            elif want_dx:
                 dy_split, dyt = ops.split_bf16_both(dy, M, N)      # dy feeds dX as-is and dW transposed: one pass
         # dW / db feed nothing on the backward critical path: inside a captured step they run on a side branch
         lib.nt_side_begin()

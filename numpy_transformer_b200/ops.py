@@ -38,20 +38,29 @@ def split_bf16_both(x, rows, cols):
     return (hi, lo), (hit, lot, ld)
 
 
+def _mn_major():
+    """dW reads the UNtransposed splits as MN-major tensor-core operands (default); NTB200_BF16X3_MN=0 restores the
+    transposed copies."""
+    import os
+    return os.environ.get("NTB200_BF16X3_MN", "1") != "0"
+
+
 def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None, keep_xt=None):
-    """keep_xt: a list; on the BF16x3 path the transposed split of x (operand of the weight-gradient GEMM) is
-    produced in the same pass as the forward operand and appended to it for linear_bwd_params."""
+    """keep_xt: a list; on the BF16x3 path the split of x that the weight-gradient GEMM will need (the forward's own
+    operand when dW reads MN-major operands, else the transposed split made in the same pass) is appended to it."""
     K, N = w.shape
     assert x.shape[-1] == K, "linear_fwd: input feature %d != %d" % (x.shape[-1], K)
     M = x.size // K
     y = DeviceArray(x.shape[:-1] + (N,), host_dtype=x.host_dtype)
     pre = y.empty_like() if want_pre else None
     if bf16x3_ok(M, K, N):
-        if keep_xt is not None:
+        if keep_xt is not None and not _mn_major():
             (xh, xl), xt = split_bf16_both(x, M, K)
             keep_xt.append(xt)
         else:
             xh, xl, _ = split_bf16(x, M, K)
+            if keep_xt is not None:
+                keep_xt.append((xh, xl, 0))             # pitch 0 = untransposed
         wh, wl, _ = split_bf16(w, K, N, transpose=True)            # w^T [N][K]
         lib.nt_linear_fwd_bf16x3(xh.ptr, xl.ptr, wh.ptr, wl.ptr, ptr_or_null(b), y.ptr, M, K, N, act, ptr_or_null(pre),
                                  ptr_or_null(residual))
@@ -78,8 +87,14 @@ def linear_bwd_params(x, dy, dw, db=None, xt_split=None, dyt_split=None):
     M = dy.size // N
     assert x.size == M * K, "linear_bwd_params: x %s vs dy %s" % (x.shape, dy.shape)
     if bf16x3_ok(M, K, N):
-        xh, xl, ld = xt_split if xt_split is not None else split_bf16(x, M, K, transpose=True)      # x^T [K][M]
-        dh, dl, _ = dyt_split if dyt_split is not None else split_bf16(dy, M, N, transpose=True)    # dy^T [N][M]
+        if _mn_major():
+            # x [M][K] and dy [M][N] as they are: MN-major operands of the contraction over the M rows
+            xh, xl = xt_split[:2] if (xt_split is not None and xt_split[2] == 0) else split_bf16(x, M, K)[:2]
+            dh, dl = dyt_split[:2] if (dyt_split is not None and dyt_split[2] == 0) else split_bf16(dy, M, N)[:2]
+            lib.nt_linear_bwd_params_bf16x3(xh.ptr, xl.ptr, dh.ptr, dl.ptr, 0, dy.ptr, dw.ptr, ptr_or_null(db), M, K, N)
+            return
+        xh, xl, ld = xt_split if (xt_split is not None and xt_split[2]) else split_bf16(x, M, K, transpose=True)      # x^T [K][M]
+        dh, dl, _ = dyt_split if (dyt_split is not None and dyt_split[2]) else split_bf16(dy, M, N, transpose=True)    # dy^T [N][M]
         lib.nt_linear_bwd_params_bf16x3(xh.ptr, xl.ptr, dh.ptr, dl.ptr, ld, dy.ptr, dw.ptr, ptr_or_null(db), M, K, N)
         return
     lib.nt_linear_bwd_params(x.ptr, dy.ptr, dw.ptr, ptr_or_null(db), M, K, N)
