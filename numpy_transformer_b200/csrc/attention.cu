@@ -1164,7 +1164,7 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
   if (B == 0) return 0;
   const int D = H * dh;
   // BF16x3 kernels (attention_bf16.cu): `scratch` only carries the B*H*N softmax-backward row sums
-  if (scratch && nt::attention_bf16_ok(N, H, dh))
+  if ((scratch || N <= 64) && nt::attention_bf16_ok(N, H, dh))
     return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0);
   if (mma_ok(N, dh)) {
     if (dh == 24) {

@@ -25,12 +25,21 @@ constexpr int LQ = 64;
 // stage rows row0.. of a [N][ld] fp32 matrix (64 x DH tile) as a split operand; rows >= N are zero
 template <int DH>
 __device__ __forceinline__ void load_split(const SArr& dst, const float* src, long long ld, int row0, int N, int tid) {
-  for (int e = tid; e < LQ * (DH / 4); e += 128) {
-    const int r = e / (DH / 4), c = (e - r * (DH / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row0 + r < N) v = *reinterpret_cast<const float4*>(src + (long long)(row0 + r) * ld + c);
-    st2(dst, r, c, v.x, v.y);
-    st2(dst, r, c + 2, v.z, v.w);
+  constexpr int IT = LQ * (DH / 4) / 128;
+  float4 v[IT];
+  // all loads of the tile first (the shared stores go through a generic pointer, so the compiler would otherwise
+  // keep every load behind the previous iteration's stores: one full memory latency per 16 bytes)
+#pragma unroll
+  for (int i = 0; i < IT; i++) {
+    const int e = tid + 128 * i, r = e / (DH / 4), c = (e - r * (DH / 4)) * 4;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < N) v[i] = *reinterpret_cast<const float4*>(src + (long long)(row0 + r) * ld + c);
+  }
+#pragma unroll
+  for (int i = 0; i < IT; i++) {
+    const int e = tid + 128 * i, r = e / (DH / 4), c = (e - r * (DH / 4)) * 4;
+    st2(dst, r, c, v[i].x, v[i].y);
+    st2(dst, r, c + 2, v[i].z, v[i].w);
   }
 }
 
@@ -327,21 +336,171 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_k_kernel(const float* __res
   }
 }
 
+// ---------------------------------------------------------------- single-block kernels (N <= 64: the scaled ViT, N = 49)
+// One CTA per (sample, head), warp w owns query rows 16w..: scores, softmax and P V in one pass over registers.
+template <int DH>
+__global__ void __launch_bounds__(128) attn_fwd_bf16_small_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
+                                                                  int mask_kind, float* __restrict__ out, float* __restrict__ P,
+                                                                  float* __restrict__ S, int N, int H,
+                                                                  const float* __restrict__ residual) {
+  pdl_prologue();
+  using M = Smem<DH>;
+  extern __shared__ __align__(128) char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const SArr sQ = make_arr(smem, M::LD), sK = make_arr(smem + M::ARR, M::LD), sV = make_arr(smem + 2 * M::ARR, M::LD);
+  const SArr sPw = make_arr(smem + 3 * M::ARR + warp * M::PW, LDP, 16);
+  const int bh = blockIdx.x, b = bh / H, h = bh % H, D = H * DH;
+  const float* base = qkv + (long long)b * N * 3 * D + h * DH;
+  load_split<DH>(sQ, base, 3 * D, 0, N, tid);
+  load_split<DH>(sK, base + D, 3 * D, 0, N, tid);
+  load_split<DH>(sV, base + 2 * D, 3 * D, 0, N, tid);
+  __syncthreads();
+  const int i0 = warp * 16, r0 = i0 + g, r1 = r0 + 8;
+  if (i0 >= N) return;                       // no CTA-wide barrier below
+  float* Pb = P + (long long)bh * N * N;
+  float s[8][4];
+  scores<DH>(s, sQ, sK, i0, r0, r1, 0, N, rsqrtf((float)DH), mask_kind, mask, S ? S + (long long)bh * N * N : nullptr, lane, t);
+  float c0 = -INFINITY, c1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++) { c0 = fmaxf(c0, fmaxf(s[nt][0], s[nt][1])); c1 = fmaxf(c1, fmaxf(s[nt][2], s[nt][3])); }
+  float m0 = quad_max(c0), m1 = quad_max(c1);
+  if (!(m0 > -INFINITY)) m0 = 0.f;
+  if (!(m1 > -INFINITY)) m1 = 0.f;
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++) {
+    s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
+    s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
+    a0 += s[nt][0] + s[nt][1];
+    a1 += s[nt][2] + s[nt][3];
+  }
+  a0 = quad_sum(a0); a1 = quad_sum(a1);
+  const float inv0 = (r0 < N && a0 > 0.f) ? 1.0f / a0 : 0.f, inv1 = (r1 < N && a1 > 0.f) ? 1.0f / a1 : 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++) {
+    const int col = nt * 8 + 2 * t;
+    const float p00 = s[nt][0] * inv0, p01 = s[nt][1] * inv0, p10 = s[nt][2] * inv1, p11 = s[nt][3] * inv1;
+    st2(sPw, g, col, p00, p01);
+    st2(sPw, g + 8, col, p10, p11);
+    if (r0 < N) { if (col < N) Pb[r0 * N + col] = p00; if (col + 1 < N) Pb[r0 * N + col + 1] = p01; }      // atg__
+    if (r1 < N) { if (col < N) Pb[r1 * N + col] = p10; if (col + 1 < N) Pb[r1 * N + col + 1] = p11; }
+  }
+  __syncwarp();
+  float o[DH / 8][4];
+#pragma unroll
+  for (int nd = 0; nd < DH / 8; nd++) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+  gemm_rowk_kn<DH>(o, sPw, 0, sV, 0, 4, lane);
+#pragma unroll
+  for (int nd = 0; nd < DH / 8; nd++) {
+    const int col = h * DH + nd * 8 + 2 * t;
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) {
+      const int row = hf ? r1 : r0;
+      if (row < N) {
+        const long long oi = ((long long)b * N + row) * D + col;
+        float2 v = make_float2(o[nd][2 * hf], o[nd][2 * hf + 1]);
+        if (residual) { const float2 rr = __ldg(reinterpret_cast<const float2*>(residual + oi)); v.x += rr.x; v.y += rr.y; }
+        *reinterpret_cast<float2*>(out + oi) = v;
+      }
+    }
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128) attn_bwd_bf16_small_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
+                                                                  const float* __restrict__ P, float* __restrict__ dqkv, int N,
+                                                                  int H) {
+  pdl_prologue();
+  using M = Smem<DH>;
+  extern __shared__ __align__(128) char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const SArr sQ = make_arr(smem, M::LD), sK = make_arr(smem + M::ARR, M::LD), sV = make_arr(smem + 2 * M::ARR, M::LD);
+  const SArr sDO = make_arr(smem + 3 * M::ARR, M::LD);
+  const SArr sP = make_arr(smem + 4 * M::ARR, LDP), sdS = make_arr(smem + 4 * M::ARR + M::PARR, LDP);
+  const int bh = blockIdx.x, b = bh / H, h = bh % H, D = H * DH;
+  const float* base = qkv + (long long)b * N * 3 * D + h * DH;
+  const float* Pb = P + (long long)bh * N * N;
+  load_split<DH>(sQ, base, 3 * D, 0, N, tid);
+  load_split<DH>(sK, base + D, 3 * D, 0, N, tid);
+  load_split<DH>(sV, base + 2 * D, 3 * D, 0, N, tid);
+  load_split<DH>(sDO, dout + (long long)b * N * D + h * DH, D, 0, N, tid);
+  __syncthreads();
+  const int i0 = warp * 16, r0 = i0 + g, r1 = r0 + 8;
+  const float scale = rsqrtf((float)DH);
+  float* ob = dqkv + (long long)b * N * 3 * D + h * DH;
+  {
+    // phase 1 (this warp's 16 QUERIES): dP, dS = P o (dP - rowsum(dP o P)), dQ = dS K / sqrt(dh)   attention.py:74-78
+    float dp[8][4], p[8][4];
+    dp_and_p<DH>(dp, p, sDO, sV, i0, r0, r1, 0, N, Pb, lane, t);
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      t0 += dp[nt][0] * p[nt][0] + dp[nt][1] * p[nt][1];
+      t1 += dp[nt][2] * p[nt][2] + dp[nt][3] * p[nt][3];
+    }
+    t0 = quad_sum(t0); t1 = quad_sum(t1);
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      const int c = nt * 8 + 2 * t;
+      st2(sP, r0, c, p[nt][0], p[nt][1]);
+      st2(sP, r1, c, p[nt][2], p[nt][3]);
+      st2(sdS, r0, c, p[nt][0] * (dp[nt][0] - t0), p[nt][1] * (dp[nt][1] - t0));
+      st2(sdS, r1, c, p[nt][2] * (dp[nt][2] - t1), p[nt][3] * (dp[nt][3] - t1));
+    }
+    __syncwarp();
+    float dq[DH / 8][4];
+#pragma unroll
+    for (int nd = 0; nd < DH / 8; nd++) dq[nd][0] = dq[nd][1] = dq[nd][2] = dq[nd][3] = 0.f;
+    gemm_rowk_kn<DH>(dq, sdS, i0, sK, 0, 4, lane);
+#pragma unroll
+    for (int nd = 0; nd < DH / 8; nd++) {
+      const int col = nd * 8 + 2 * t;
+      if (r0 < N) *reinterpret_cast<float2*>(ob + (long long)r0 * 3 * D + col) = make_float2(dq[nd][0] * scale, dq[nd][1] * scale);
+      if (r1 < N) *reinterpret_cast<float2*>(ob + (long long)r1 * 3 * D + col) = make_float2(dq[nd][2] * scale, dq[nd][3] * scale);
+    }
+  }
+  __syncthreads();
+  if (i0 >= N) return;
+  // phase 2 (this warp's 16 KEYS): dK = dS^T Q / sqrt(dh), dV = P^T dO                               attention.py:76,79
+  float dk[DH / 8][4], dv[DH / 8][4];
+#pragma unroll
+  for (int nd = 0; nd < DH / 8; nd++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) dk[nd][c] = dv[nd][c] = 0.f;
+  gemm_colk_kn<DH>(dk, sdS, i0, sQ, 0, 4, lane);
+  gemm_colk_kn<DH>(dv, sP, i0, sDO, 0, 4, lane);
+#pragma unroll
+  for (int nd = 0; nd < DH / 8; nd++) {
+    const int col = nd * 8 + 2 * t;
+    if (r0 < N) {
+      float* o = ob + (long long)r0 * 3 * D + col;
+      *reinterpret_cast<float2*>(o + D) = make_float2(dk[nd][0] * scale, dk[nd][1] * scale);
+      *reinterpret_cast<float2*>(o + 2 * D) = make_float2(dv[nd][0], dv[nd][1]);
+    }
+    if (r1 < N) {
+      float* o = ob + (long long)r1 * 3 * D + col;
+      *reinterpret_cast<float2*>(o + D) = make_float2(dk[nd][2] * scale, dk[nd][3] * scale);
+      *reinterpret_cast<float2*>(o + 2 * D) = make_float2(dv[nd][2], dv[nd][3]);
+    }
+  }
+}
+
 template <int DH> static size_t fwd_smem() { return 3 * (size_t)Smem<DH>::ARR + 4 * (size_t)Smem<DH>::PW; }
 template <int DH> static size_t bwdq_smem() { return 3 * (size_t)Smem<DH>::ARR + 4 * (size_t)Smem<DH>::PW; }
 template <int DH> static size_t bwdk_smem() { return 3 * (size_t)Smem<DH>::ARR + 2 * (size_t)Smem<DH>::PARR; }
+template <int DH> static size_t bwds_smem() { return 4 * (size_t)Smem<DH>::ARR + 2 * (size_t)Smem<DH>::PARR; }
 
 }  // namespace ab
 
-// dh == 64 and more than one 64-key block (the GPT configs, T = 256); NTB200_ATT_BF16=0 keeps the TF32x3 kernels of
-// attention.cu.  Measured on B200: G1 forward 1.03 -> 0.79 ms, backward 1.50 -> 1.30 ms per step.  For a single
-// block (scaled ViT, N = 49) the one-pass TF32 kernel stays: recomputing the scores / dP only pays when it
-// replaces HBM round trips of whole T x T matrices (V2 measured 6.4 -> 9.1 ms with these kernels).
+// dh == 64 (scaled ViT N = 49 -> single-block kernels; GPT configs T = 256 -> two-pass kernels); NTB200_ATT_BF16=0
+// keeps the TF32x3 kernels of attention.cu, NTB200_ATT_BF16_MIN_N raises the sequence-length threshold.
+// Measured on B200 per step: G1 forward 1.03 -> 0.76 ms, backward 1.50 -> 1.09 ms; V2 forward 2.80 -> 2.54 ms,
+// backward 3.66 -> 2.49 ms.
 bool attention_bf16_ok(int N, int H, int dh) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("NTB200_ATT_BF16"); on = (e && e[0] == '0') ? 0 : 1; }
   const char* f = getenv("NTB200_ATT_BF16_MIN_N");
-  const int min_n = f ? atoi(f) : 65;
+  const int min_n = f ? atoi(f) : 1;
   return on && dh == 64 && N >= min_n && g_gemm_mode == 1;
 }
 
@@ -353,7 +512,15 @@ int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float
     NT_CHECK(cudaFuncSetAttribute(attn_fwd_bf16_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
     NT_CHECK(cudaFuncSetAttribute(attn_bwd_bf16_q_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwdq_smem<64>()));
     NT_CHECK(cudaFuncSetAttribute(attn_bwd_bf16_k_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwdk_smem<64>()));
+    NT_CHECK(cudaFuncSetAttribute(attn_fwd_bf16_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
+    NT_CHECK(cudaFuncSetAttribute(attn_bwd_bf16_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwds_smem<64>()));
     cfg = true;
+  }
+  if (N <= LQ) {
+    NT_CHECK(launch_k(attn_fwd_bf16_small_kernel<64>, dim3(B * H), dim3(128), fwd_smem<64>(), qkv, mask, mask_kind, out, P, S, N, H,
+                      residual));
+    NT_LAUNCH_OK();
+    return 0;
   }
   NT_CHECK(launch_k(attn_fwd_bf16_kernel<64>, dim3(ceil_div(N, LQ), B * H), dim3(128), fwd_smem<64>(), qkv, mask, mask_kind, out, P,
                     S, N, H, residual));
@@ -364,6 +531,11 @@ int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float
 int attention_bwd_bf16(const float* dout, const float* qkv, const float* P, float* dqkv, float* tsum, int B, int N, int H,
                        int causal) {
   using namespace ab;
+  if (N <= LQ) {
+    NT_CHECK(launch_k(attn_bwd_bf16_small_kernel<64>, dim3(B * H), dim3(128), bwds_smem<64>(), dout, qkv, P, dqkv, N, H));
+    NT_LAUNCH_OK();
+    return 0;
+  }
   NT_CHECK(launch_k(attn_bwd_bf16_q_kernel<64>, dim3(ceil_div(N, LQ), B * H), dim3(128), bwdq_smem<64>(), dout, qkv, P, dqkv, tsum,
                     N, H, causal));
   NT_LAUNCH_OK();

@@ -138,7 +138,7 @@ def attention_bwd(dout, qkv, P, H, mask_kind=MASK_NONE):
     dh = D // H
     dqkv = qkv.empty_like()
     import os
-    if (dh == 64 and N >= int(os.environ.get("NTB200_ATT_BF16_MIN_N", "65")) and get_gemm_mode() == 1
+    if (dh == 64 and N >= int(os.environ.get("NTB200_ATT_BF16_MIN_N", "1")) and get_gemm_mode() == 1
             and os.environ.get("NTB200_ATT_BF16", "1") != "0"):
         scratch = DeviceArray((B * H * N,))             # BF16x3 kernels: row sums of dP o P only
     else:
