@@ -193,19 +193,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_load_2d(sa, &tmA, &full[s], k0, m0);                            // box {64 k, 128 m} bf16
         tma_load_2d(sal_, &tmAl, &full[s], k0, m0);
       } else {
-        // MN-major: [k rows][64 m] boxes of 64 x 128 B, one per 64-wide chunk of the tile (chunk stride 8 KB)
-        for (int j = 0; j < BM / 64; j++) {
-          tma_load_2d(sa + j * 8192, &tmA, &full[s], m0 + 64 * j, k0);
-          tma_load_2d(sal_ + j * 8192, &tmAl, &full[s], m0 + 64 * j, k0);
+        // MN-major: [k rows][64 m] boxes of 64 x 128 B, one per 64-wide chunk of the tile (chunk stride 8 KB);
+        // a 3-D map {64, k, chunk} lands all chunks with one instruction when the extent is a multiple of 64
+        if (p.a_3d) {
+          tma_load_3d(sa, &tmA, &full[s], 0, k0, m0 >> 6);
+          tma_load_3d(sal_, &tmAl, &full[s], 0, k0, m0 >> 6);
+        } else {
+          for (int j = 0; j < BM / 64; j++) {
+            tma_load_2d(sa + j * 8192, &tmA, &full[s], m0 + 64 * j, k0);
+            tma_load_2d(sal_ + j * 8192, &tmAl, &full[s], m0 + 64 * j, k0);
+          }
         }
       }
       if (!p.b_mn) {
         tma_load_2d(sb, &tmB, &full[s], k0, n0);                            // box {64 k, BN n}
         tma_load_2d(sbl_, &tmBl, &full[s], k0, n0);
       } else {
-        for (int j = 0; j < p.BN / 64; j++) {
-          tma_load_2d(sb + j * 8192, &tmB, &full[s], n0 + 64 * j, k0);
-          tma_load_2d(sbl_ + j * 8192, &tmBl, &full[s], n0 + 64 * j, k0);
+        if (p.b_3d) {
+          tma_load_3d(sb, &tmB, &full[s], 0, k0, n0 >> 6);
+          tma_load_3d(sbl_, &tmBl, &full[s], 0, k0, n0 >> 6);
+        } else {
+          for (int j = 0; j < p.BN / 64; j++) {
+            tma_load_2d(sb + j * 8192, &tmB, &full[s], n0 + 64 * j, k0);
+            tma_load_2d(sbl_ + j * 8192, &tmBl, &full[s], n0 + 64 * j, k0);
+          }
         }
       }
       return;
@@ -574,6 +585,19 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, long long inner, lo
   return 0;
 }
 
+// MN-major bf16 operand [k rows][mn] whose contiguous extent is a multiple of 64: view as {64, k, mn/64}, box {64, 64, chunks}
+static int make_tmap_bf16_mn3d(CUtensorMap* tm, const void* base, long long mn, long long k, long long ld, int chunks) {
+  cuuint64_t dims[3] = {64, (cuuint64_t)k, (cuuint64_t)(mn / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
+  cuuint32_t box[3] = {64, 64, (cuuint32_t)chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(bf16 3d) failed (%d) mn=%lld k=%lld ld=%lld", (int)r, mn, k, ld);
+  return 0;
+}
+
 template <int ACT, int DACT, bool PRE_OUT, bool ATOMIC, bool ADDEND>
 static int launch_tc(dim3 grid, size_t smem, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmAl,
                      const CUtensorMap& tmBl, const TcParams& p) {
@@ -694,16 +718,23 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   CUtensorMap tmA, tmB, tmAl, tmBl;
   if (bf) {
     // K-major: [rows = M or N][K contiguous], box {64 k, rows of the tile}; MN-major: [K rows][M or N contiguous], box {64, 64}
-    if (a_mn ? (make_tmap_bf16(&tmA, d.A_hi, d.M, d.K, lda, 64) || make_tmap_bf16(&tmAl, d.A_lo, d.M, d.K, lda, 64))
-             : (make_tmap_bf16(&tmA, d.A_hi, d.K, d.M, lda, BM) || make_tmap_bf16(&tmAl, d.A_lo, d.K, d.M, lda, BM)))
+    const bool three_d = getenv("NTB200_TMA_2D") == nullptr;
+    p.a_3d = (a_mn && three_d && d.M % 64 == 0) ? 1 : 0;
+    p.b_3d = (b_mn && three_d && d.N % 64 == 0) ? 1 : 0;
+    if (p.a_3d ? (make_tmap_bf16_mn3d(&tmA, d.A_hi, d.M, d.K, lda, BM / 64) || make_tmap_bf16_mn3d(&tmAl, d.A_lo, d.M, d.K, lda, BM / 64))
+        : a_mn ? (make_tmap_bf16(&tmA, d.A_hi, d.M, d.K, lda, 64) || make_tmap_bf16(&tmAl, d.A_lo, d.M, d.K, lda, 64))
+               : (make_tmap_bf16(&tmA, d.A_hi, d.K, d.M, lda, BM) || make_tmap_bf16(&tmAl, d.A_lo, d.K, d.M, lda, BM)))
       return 1;
-    if (b_mn ? (make_tmap_bf16(&tmB, d.B_hi, d.N, d.K, ldb, 64) || make_tmap_bf16(&tmBl, d.B_lo, d.N, d.K, ldb, 64))
-             : (make_tmap_bf16(&tmB, d.B_hi, d.K, d.N, ldb, p.BN) || make_tmap_bf16(&tmBl, d.B_lo, d.K, d.N, ldb, p.BN)))
+    if (p.b_3d ? (make_tmap_bf16_mn3d(&tmB, d.B_hi, d.N, d.K, ldb, p.BN / 64) || make_tmap_bf16_mn3d(&tmBl, d.B_lo, d.N, d.K, ldb, p.BN / 64))
+        : b_mn ? (make_tmap_bf16(&tmB, d.B_hi, d.N, d.K, ldb, 64) || make_tmap_bf16(&tmBl, d.B_lo, d.N, d.K, ldb, 64))
+               : (make_tmap_bf16(&tmB, d.B_hi, d.K, d.N, ldb, p.BN) || make_tmap_bf16(&tmBl, d.B_lo, d.K, d.N, ldb, p.BN)))
       return 1;
   }
   const bool use3d = getenv("NTB200_TMA_2D") == nullptr;
-  p.a_3d = (!bf && a_mn && use3d && d.M % 32 == 0 && ld_ok3(lda)) ? 1 : 0;
-  p.b_3d = (!bf && b_mn && use3d && d.N % 32 == 0 && ld_ok3(ldb)) ? 1 : 0;
+  if (!bf) {
+    p.a_3d = (a_mn && use3d && d.M % 32 == 0 && ld_ok3(lda)) ? 1 : 0;
+    p.b_3d = (b_mn && use3d && d.N % 32 == 0 && ld_ok3(ldb)) ? 1 : 0;
+  }
   if (bf) {}
   else if (a_k) { if (make_tmap(&tmA, d.A, d.K, d.M, lda, BM, false)) return 1; }
   else if (p.a_3d) { if (make_tmap_mn3d(&tmA, d.A, d.M, d.K, lda, BM / 32)) return 1; }
