@@ -695,6 +695,9 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
     // split the long contraction (dW: K = batch rows) so the grid covers the SMs; >= 4 k-blocks per split
     const int tiles = ceil_div(d.N, p.BN) * ceil_div(d.M, BM);
     splits = ceil_div(g_sm_count, tiles);
+    // the deep-ring bf16 configuration runs ONE CTA per SM: a grid a little above the SM count costs a whole second
+    // wave (ncu: 162 CTAs = 148 + 14 ran at 33 % SM throughput), so round the split count DOWN to stay within one wave
+    if (bf && tiles <= g_sm_count) { splits = g_sm_count / tiles; if (splits < 1) splits = 1; }
     const int maxs = total_kb / 4 < 1 ? 1 : total_kb / 4;
     if (splits > maxs) splits = maxs;
   }
@@ -707,10 +710,11 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   // single-pass tiles are small (32 KB/stage): with two stages three CTAs share an SM and one CTA's
   // prologue / epilogue hides behind another's main loop (measured 218 -> 115 us on 50176x384x1152)
   if (passes == 1 && (long long)ceil_div(d.N, p.BN) * ceil_div(d.M, BM) * splits >= 2LL * g_sm_count && stages > 2) stages = 2;
-  // pre-split bf16 tiles need no converter hand-off: with a short contraction (<= 16 k-blocks) one 64 KB stage lets
-  // three CTAs share an SM, so loads, MMAs and epilogues of different tiles overlap (measured on V2: forward / dX
-  // GEMMs 6.5 -> 4.6 ms); the long split-K weight-gradient contraction keeps the deep ring
-  if (bf && p.kblocks_per_split <= 16) stages = 1;
+  // pre-split bf16 tiles need no converter hand-off: without split-K (forward / dX, <= 64 k-blocks) one 64 KB stage
+  // lets three CTAs share an SM, so loads, MMAs and epilogues of different tiles overlap (measured on V2: forward /
+  // dX GEMMs 6.5 -> 4.6 ms; G2 dX 9.0 -> 8.0 ms); the long split-K weight-gradient contraction keeps the deep ring
+  { static int lim = -1; if (lim < 0) { const char* e = getenv("NTB200_BF16_1STAGE_KB"); lim = e ? atoi(e) : 64; }
+    if (bf && splits == 1 && p.kblocks_per_split <= lim) stages = 1; }
   if (const char* e = getenv("NTB200_STAGES")) { int v = atoi(e); if (v >= 1 && v <= stages) stages = v; }
   p.stages = stages;
   const size_t smem = stages * stage + (3 * stages + 2) * 8 + 16 + 128 * 4 + 1024;
