@@ -97,12 +97,15 @@ int nt_split_bf16(const float* x, void* hi, void* lo, int rows, int cols, int ld
 /* both layouts in one pass over x: hi / lo [rows][cols] and hi_t / lo_t [cols][ld_t] (a Linear layer's input feeds
  * the forward GEMM as-is and the weight-gradient GEMM transposed; its output gradient feeds dX and dW likewise). */
 int nt_split_bf16_both(const float* x, void* hi, void* lo, void* hi_t, void* lo_t, int rows, int cols, int ld_t);
-/* fclayer.forward (net/fullconnect.py:99-106) from split x [M][K] and split w^T [N][K]; epilogue as nt_linear_fwd. */
+/* Producer-side splits: ops whose output feeds a BF16x3 GEMM can emit the bf16 hi / lo planes of that output
+ * themselves (y_hi / y_lo, dx_hi / dx_lo ...: dense [rows][cols] planes, NULL = not wanted), so no separate split
+ * pass has to read the fp32 tensor back from HBM.
+ * fclayer.forward (net/fullconnect.py:99-106) from split x [M][K] and split w^T [N][K]; epilogue as nt_linear_fwd. */
 int nt_linear_fwd_bf16x3(const void* x_hi, const void* x_lo, const void* wt_hi, const void* wt_lo, const float* b, float* y,
-                         int M, int K, int N, int act, float* pre, const float* residual);
+                         int M, int K, int N, int act, float* pre, const float* residual, void* y_hi, void* y_lo);
 /* fclayer.backward input half (:114) from split dy [M][N] and split w [K][N]; epilogue as nt_linear_bwd_input. */
 int nt_linear_bwd_input_bf16x3(const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, float* dx, int M, int K,
-                               int N, int act, const float* pre, const float* addend);
+                               int N, int act, const float* pre, const float* addend, void* dx_hi, void* dx_lo);
 /* fclayer.backward parameter half (:118-125) from transposed splits x^T [K][ld_t], dy^T [N][ld_t] (ld_t >= M), or, with
  * ld_t == 0, from the UNtransposed splits x [M][K], dy [M][N] (MN-major tensor-core operands: no transposed copies);
  * db (may be NULL) += colsum(dy) from the fp32 dy.  Accumulates. */
@@ -121,6 +124,11 @@ int nt_layernorm_fwd(const float* x, const float* gamma, const float* beta, floa
 int nt_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                      const float* gamma, float* dx, float* dgamma, float* dbeta,
                      int M, int D, const float* addend);
+/* the same with the output also written as bf16 hi / lo planes (operand of the next BF16x3 GEMM) */
+int nt_layernorm_fwd_split(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                           int M, int D, float eps, const float* post_add, int period, void* y_hi, void* y_lo);
+int nt_layernorm_bwd_split(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                           float* dx, float* dgamma, float* dbeta, int M, int D, const float* addend, void* dx_hi, void* dx_lo);
 
 /* ---------------------------------------------------------------- activations (net/activation.py) */
 int nt_gelu_fwd(const float* x, float* y, size_t n);                       /* :139-142 */
@@ -152,6 +160,12 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
  * blocks (P is exactly 0 there); any other value processes the full matrix. */
 int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch,
                      int B, int N, int H, int dh, int mask_kind);
+/* BF16x3 kernels only (dh == 64, GEMM mode 1): out / dqkv additionally as bf16 hi / lo planes for the Linear that
+ * consumes them (fc_out forward, qkvfc backward). */
+int nt_attention_fwd_split(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S,
+                           int B, int N, int H, int dh, const float* residual, void* out_hi, void* out_lo);
+int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch,
+                           int B, int N, int H, int dh, int mask_kind, void* dqkv_hi, void* dqkv_lo);
 
 /* ---------------------------------------------------------------- fused ViT encoder blocks
  * attention_layer.forward / backward (attention.py:20-55, 57-89) for a whole stack of blocks in ONE launch

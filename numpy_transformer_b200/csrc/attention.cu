@@ -8,9 +8,9 @@
 namespace nt {
 bool attention_bf16_ok(int N, int H, int dh);
 int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S, int B, int N, int H,
-                       const float* residual);
+                       const float* residual, void* o_hi, void* o_lo);
 int attention_bwd_bf16(const float* dout, const float* qkv, const float* P, float* dqkv, float* tsum, int B, int N, int H,
-                       int causal);
+                       int causal, void* g_hi, void* g_lo);
 
 // p = softmax(x + mask) along rows; one warp per row. mask_kind as in ntb200.h; qi = row % N.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, float* __restrict__ p,
@@ -1085,7 +1085,7 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
   NT_REQUIRE(mask_kind != NT_MASK_DENSE || mask, "nt_attention_fwd: dense mask_kind needs a mask");
   if (B == 0) return 0;
   const int D = H * dh;
-  if (nt::attention_bf16_ok(N, H, dh)) return nt::attention_fwd_bf16(qkv, mask, mask_kind, out, P, S, B, N, H, residual);
+  if (nt::attention_bf16_ok(N, H, dh)) return nt::attention_fwd_bf16(qkv, mask, mask_kind, out, P, S, B, N, H, residual, nullptr, nullptr);
   if (const char* e = getenv("NTB200_ATT_MMA")) g_att_mma = (e[0] != '0');
   if (mma_ok(N, dh)) {
     if (dh == 24) {
@@ -1165,7 +1165,7 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
   const int D = H * dh;
   // BF16x3 kernels (attention_bf16.cu): `scratch` only carries the B*H*N softmax-backward row sums
   if ((scratch || N <= 64) && nt::attention_bf16_ok(N, H, dh))
-    return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0);
+    return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0, nullptr, nullptr);
   if (mma_ok(N, dh)) {
     if (dh == 24) {
       const size_t smem = bwd_mma_smem<24>();
@@ -1257,6 +1257,28 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
   k.B = qkv; k.C = dqkv + D;
   k.sAm = 1; k.sAk = N;
   return gemm_simt(k);
+}
+
+int nt_attention_fwd_split(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S, int B, int N,
+                           int H, int dh, const float* residual, void* out_hi, void* out_lo) {
+  NT_ENTRY();
+  NT_REQUIRE(B >= 0 && N > 0 && H > 0 && dh > 0, "nt_attention_fwd_split: bad shape");
+  NT_REQUIRE(mask_kind != NT_MASK_DENSE || mask, "nt_attention_fwd_split: dense mask_kind needs a mask");
+  NT_REQUIRE(nt::attention_bf16_ok(N, H, dh), "nt_attention_fwd_split: only the BF16x3 kernels (dh == 64, GEMM mode 1) emit split outputs");
+  NT_REQUIRE((out_hi != nullptr) == (out_lo != nullptr), "nt_attention_fwd_split: pass both split planes or neither");
+  if (B == 0) return 0;
+  return nt::attention_fwd_bf16(qkv, mask, mask_kind, out, P, S, B, N, H, residual, out_hi, out_lo);
+}
+
+int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch, int B, int N,
+                           int H, int dh, int mask_kind, void* dqkv_hi, void* dqkv_lo) {
+  NT_ENTRY();
+  NT_REQUIRE(B >= 0 && N > 0 && H > 0 && dh > 0, "nt_attention_bwd_split: bad shape");
+  NT_REQUIRE(nt::attention_bf16_ok(N, H, dh) && (scratch || N <= 64),
+             "nt_attention_bwd_split: only the BF16x3 kernels (dh == 64, GEMM mode 1, scratch of B*H*N floats) emit split outputs");
+  NT_REQUIRE((dqkv_hi != nullptr) == (dqkv_lo != nullptr), "nt_attention_bwd_split: pass both split planes or neither");
+  if (B == 0) return 0;
+  return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0, dqkv_hi, dqkv_lo);
 }
 
 }  // extern "C"

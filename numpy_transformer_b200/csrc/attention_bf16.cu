@@ -43,6 +43,18 @@ __device__ __forceinline__ void load_split(const SArr& dst, const float* src, lo
   }
 }
 
+// dqkv element pair -> fp32 and, when wanted, the bf16 hi / lo planes (same [B,N,3D] layout)
+__device__ __forceinline__ void store_g(float* base, uint32_t* g_hi, uint32_t* g_lo, const float* dq0, long long off, float a, float b) {
+  *reinterpret_cast<float2*>(base + off) = make_float2(a, b);
+  if (g_hi) {
+    uint32_t hh, ll;
+    split2(a, b, hh, ll);
+    const long long e = (base + off) - dq0;
+    g_hi[e >> 1] = hh;
+    g_lo[e >> 1] = ll;
+  }
+}
+
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -89,7 +101,8 @@ template <int DH>
 __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
                                                             int mask_kind, float* __restrict__ out, float* __restrict__ P,
                                                             float* __restrict__ S, int N, int H,
-                                                            const float* __restrict__ residual) {
+                                                            const float* __restrict__ residual, uint32_t* __restrict__ o_hi,
+                                                            uint32_t* __restrict__ o_lo) {
   pdl_prologue();
   using M = Smem<DH>;
   extern __shared__ __align__(128) char smem[];
@@ -181,6 +194,7 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const float* __restr
         float2 v = make_float2(o[nd][2 * hf], o[nd][2 * hf + 1]);
         if (residual) { const float2 rr = __ldg(reinterpret_cast<const float2*>(residual + oi)); v.x += rr.x; v.y += rr.y; }
         *reinterpret_cast<float2*>(out + oi) = v;
+        if (o_hi) { uint32_t hh, ll; split2(v.x, v.y, hh, ll); o_hi[oi >> 1] = hh; o_lo[oi >> 1] = ll; }
       }
     }
   }
@@ -206,7 +220,8 @@ __device__ __forceinline__ void dp_and_p(float (&dp)[8][4], float (&p)[8][4], co
 template <int DH>
 __global__ void __launch_bounds__(128) attn_bwd_bf16_q_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
                                                               const float* __restrict__ P, float* __restrict__ dqkv,
-                                                              float* __restrict__ tsum, int N, int H, int causal) {
+                                                              float* __restrict__ tsum, int N, int H, int causal,
+                                                              uint32_t* __restrict__ g_hi, uint32_t* __restrict__ g_lo) {
   pdl_prologue();
   using M = Smem<DH>;
   extern __shared__ __align__(128) char smem[];
@@ -265,8 +280,8 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_q_kernel(const float* __res
 #pragma unroll
   for (int nd = 0; nd < DH / 8; nd++) {
     const int col = nd * 8 + 2 * t;
-    if (r0 < N) *reinterpret_cast<float2*>(ob + (long long)r0 * 3 * D + col) = make_float2(dq[nd][0] * scale, dq[nd][1] * scale);
-    if (r1 < N) *reinterpret_cast<float2*>(ob + (long long)r1 * 3 * D + col) = make_float2(dq[nd][2] * scale, dq[nd][3] * scale);
+    if (r0 < N) store_g(ob, g_hi, g_lo, dqkv, (long long)r0 * 3 * D + col, dq[nd][0] * scale, dq[nd][1] * scale);
+    if (r1 < N) store_g(ob, g_hi, g_lo, dqkv, (long long)r1 * 3 * D + col, dq[nd][2] * scale, dq[nd][3] * scale);
   }
 }
 
@@ -274,7 +289,8 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_q_kernel(const float* __res
 template <int DH>
 __global__ void __launch_bounds__(128) attn_bwd_bf16_k_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
                                                               const float* __restrict__ P, float* __restrict__ dqkv,
-                                                              const float* __restrict__ tsum, int N, int H, int causal) {
+                                                              const float* __restrict__ tsum, int N, int H, int causal,
+                                                              uint32_t* __restrict__ g_hi, uint32_t* __restrict__ g_lo) {
   pdl_prologue();
   using M = Smem<DH>;
   extern __shared__ __align__(128) char smem[];
@@ -324,14 +340,12 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_k_kernel(const float* __res
   for (int nd = 0; nd < DH / 8; nd++) {
     const int col = nd * 8 + 2 * t;
     if (j0 < N) {
-      float* o = ob + (long long)j0 * 3 * D + col;
-      *reinterpret_cast<float2*>(o + D) = make_float2(dk[nd][0] * scale, dk[nd][1] * scale);
-      *reinterpret_cast<float2*>(o + 2 * D) = make_float2(dv[nd][0], dv[nd][1]);
+      store_g(ob, g_hi, g_lo, dqkv, (long long)j0 * 3 * D + col + D, dk[nd][0] * scale, dk[nd][1] * scale);
+      store_g(ob, g_hi, g_lo, dqkv, (long long)j0 * 3 * D + col + 2 * D, dv[nd][0], dv[nd][1]);
     }
     if (j1 < N) {
-      float* o = ob + (long long)j1 * 3 * D + col;
-      *reinterpret_cast<float2*>(o + D) = make_float2(dk[nd][2] * scale, dk[nd][3] * scale);
-      *reinterpret_cast<float2*>(o + 2 * D) = make_float2(dv[nd][2], dv[nd][3]);
+      store_g(ob, g_hi, g_lo, dqkv, (long long)j1 * 3 * D + col + D, dk[nd][2] * scale, dk[nd][3] * scale);
+      store_g(ob, g_hi, g_lo, dqkv, (long long)j1 * 3 * D + col + 2 * D, dv[nd][2], dv[nd][3]);
     }
   }
 }
@@ -342,7 +356,8 @@ template <int DH>
 __global__ void __launch_bounds__(128) attn_fwd_bf16_small_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
                                                                   int mask_kind, float* __restrict__ out, float* __restrict__ P,
                                                                   float* __restrict__ S, int N, int H,
-                                                                  const float* __restrict__ residual) {
+                                                                  const float* __restrict__ residual,
+                                                                  uint32_t* __restrict__ o_hi, uint32_t* __restrict__ o_lo) {
   pdl_prologue();
   using M = Smem<DH>;
   extern __shared__ __align__(128) char smem[];
@@ -401,6 +416,7 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_small_kernel(const float* _
         float2 v = make_float2(o[nd][2 * hf], o[nd][2 * hf + 1]);
         if (residual) { const float2 rr = __ldg(reinterpret_cast<const float2*>(residual + oi)); v.x += rr.x; v.y += rr.y; }
         *reinterpret_cast<float2*>(out + oi) = v;
+        if (o_hi) { uint32_t hh, ll; split2(v.x, v.y, hh, ll); o_hi[oi >> 1] = hh; o_lo[oi >> 1] = ll; }
       }
     }
   }
@@ -409,7 +425,7 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_small_kernel(const float* _
 template <int DH>
 __global__ void __launch_bounds__(128) attn_bwd_bf16_small_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
                                                                   const float* __restrict__ P, float* __restrict__ dqkv, int N,
-                                                                  int H) {
+                                                                  int H, uint32_t* __restrict__ g_hi, uint32_t* __restrict__ g_lo) {
   pdl_prologue();
   using M = Smem<DH>;
   extern __shared__ __align__(128) char smem[];
@@ -455,8 +471,8 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_small_kernel(const float* _
 #pragma unroll
     for (int nd = 0; nd < DH / 8; nd++) {
       const int col = nd * 8 + 2 * t;
-      if (r0 < N) *reinterpret_cast<float2*>(ob + (long long)r0 * 3 * D + col) = make_float2(dq[nd][0] * scale, dq[nd][1] * scale);
-      if (r1 < N) *reinterpret_cast<float2*>(ob + (long long)r1 * 3 * D + col) = make_float2(dq[nd][2] * scale, dq[nd][3] * scale);
+      if (r0 < N) store_g(ob, g_hi, g_lo, dqkv, (long long)r0 * 3 * D + col, dq[nd][0] * scale, dq[nd][1] * scale);
+      if (r1 < N) store_g(ob, g_hi, g_lo, dqkv, (long long)r1 * 3 * D + col, dq[nd][2] * scale, dq[nd][3] * scale);
     }
   }
   __syncthreads();
@@ -473,14 +489,12 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_small_kernel(const float* _
   for (int nd = 0; nd < DH / 8; nd++) {
     const int col = nd * 8 + 2 * t;
     if (r0 < N) {
-      float* o = ob + (long long)r0 * 3 * D + col;
-      *reinterpret_cast<float2*>(o + D) = make_float2(dk[nd][0] * scale, dk[nd][1] * scale);
-      *reinterpret_cast<float2*>(o + 2 * D) = make_float2(dv[nd][0], dv[nd][1]);
+      store_g(ob, g_hi, g_lo, dqkv, (long long)r0 * 3 * D + col + D, dk[nd][0] * scale, dk[nd][1] * scale);
+      store_g(ob, g_hi, g_lo, dqkv, (long long)r0 * 3 * D + col + 2 * D, dv[nd][0], dv[nd][1]);
     }
     if (r1 < N) {
-      float* o = ob + (long long)r1 * 3 * D + col;
-      *reinterpret_cast<float2*>(o + D) = make_float2(dk[nd][2] * scale, dk[nd][3] * scale);
-      *reinterpret_cast<float2*>(o + 2 * D) = make_float2(dv[nd][2], dv[nd][3]);
+      store_g(ob, g_hi, g_lo, dqkv, (long long)r1 * 3 * D + col + D, dk[nd][2] * scale, dk[nd][3] * scale);
+      store_g(ob, g_hi, g_lo, dqkv, (long long)r1 * 3 * D + col + 2 * D, dv[nd][2], dv[nd][3]);
     }
   }
 }
@@ -505,7 +519,7 @@ bool attention_bf16_ok(int N, int H, int dh) {
 }
 
 int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S, int B, int N, int H,
-                       const float* residual) {
+                       const float* residual, void* o_hi, void* o_lo) {
   using namespace ab;
   static bool cfg = false;
   if (!cfg) {
@@ -518,29 +532,29 @@ int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float
   }
   if (N <= LQ) {
     NT_CHECK(launch_k(attn_fwd_bf16_small_kernel<64>, dim3(B * H), dim3(128), fwd_smem<64>(), qkv, mask, mask_kind, out, P, S, N, H,
-                      residual));
+                      residual, (uint32_t*)o_hi, (uint32_t*)o_lo));
     NT_LAUNCH_OK();
     return 0;
   }
   NT_CHECK(launch_k(attn_fwd_bf16_kernel<64>, dim3(ceil_div(N, LQ), B * H), dim3(128), fwd_smem<64>(), qkv, mask, mask_kind, out, P,
-                    S, N, H, residual));
+                    S, N, H, residual, (uint32_t*)o_hi, (uint32_t*)o_lo));
   NT_LAUNCH_OK();
   return 0;
 }
 
 int attention_bwd_bf16(const float* dout, const float* qkv, const float* P, float* dqkv, float* tsum, int B, int N, int H,
-                       int causal) {
+                       int causal, void* g_hi, void* g_lo) {
   using namespace ab;
   if (N <= LQ) {
-    NT_CHECK(launch_k(attn_bwd_bf16_small_kernel<64>, dim3(B * H), dim3(128), bwds_smem<64>(), dout, qkv, P, dqkv, N, H));
+    NT_CHECK(launch_k(attn_bwd_bf16_small_kernel<64>, dim3(B * H), dim3(128), bwds_smem<64>(), dout, qkv, P, dqkv, N, H, (uint32_t*)g_hi, (uint32_t*)g_lo));
     NT_LAUNCH_OK();
     return 0;
   }
   NT_CHECK(launch_k(attn_bwd_bf16_q_kernel<64>, dim3(ceil_div(N, LQ), B * H), dim3(128), bwdq_smem<64>(), dout, qkv, P, dqkv, tsum,
-                    N, H, causal));
+                    N, H, causal, (uint32_t*)g_hi, (uint32_t*)g_lo));
   NT_LAUNCH_OK();
   NT_CHECK(launch_k(attn_bwd_bf16_k_kernel<64>, dim3(ceil_div(N, LQ), B * H), dim3(128), bwdk_smem<64>(), dout, qkv, P, dqkv,
-                    (const float*)tsum, N, H, causal));
+                    (const float*)tsum, N, H, causal, (uint32_t*)g_hi, (uint32_t*)g_lo));
   NT_LAUNCH_OK();
   return 0;
 }

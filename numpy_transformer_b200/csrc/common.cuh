@@ -100,6 +100,8 @@ struct Epilogue {
   float alpha = 1.0f;               // scale on the accumulator
   int atomic = 0;                   // 1: atomicAdd into C (split-K / accumulate semantics)
   float* colsum = nullptr;          // [N] += column sums of the MN-major B operand (db of the weight-gradient GEMM)
+  void* out_hi = nullptr;           // optional: the final output also as bf16 hi / lo planes [M][ldc] (operand of the next
+  void* out_lo = nullptr;           //           BF16x3 GEMM, so no separate split pass reads C back)
 };
 
 // C(m,n) = alpha * sum_k A(m,k) B(k,n), generic strides, two-level batch (z = z0*nb1 + z1)

@@ -18,6 +18,7 @@
 //     zero fill + guarded stores.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 namespace nt {
@@ -99,6 +100,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
       ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
+}
+// bf16 hi/lo split of two fp32 values (same arithmetic as split_bf16.cu)
+__device__ __forceinline__ void tc_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -503,6 +512,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               if (ATOMIC) atomicAdd(reinterpret_cast<float4*>(p.C + idx), v);
               else *reinterpret_cast<float4*>(p.C + idx) = v;
+              if (!ATOMIC && ep.out_hi) {
+                uint2 h, l;
+                tc_split2(v.x, v.y, h.x, l.x);
+                tc_split2(v.z, v.w, h.y, l.y);
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out_hi) + idx) = h;
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out_lo) + idx) = l;
+              }
             }
           }
         }
@@ -524,6 +540,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (add_on) v += __ldg(ep.addend + idx);
             if (ATOMIC) atomicAdd(p.C + idx, v);
             else p.C[idx] = v;
+            if (!ATOMIC && ep.out_hi) {
+              const __nv_bfloat16 h = __float2bfloat16_rn(v);
+              reinterpret_cast<__nv_bfloat16*>(ep.out_hi)[idx] = h;
+              reinterpret_cast<__nv_bfloat16*>(ep.out_lo)[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+            }
           }
         }
       }

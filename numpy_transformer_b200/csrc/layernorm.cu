@@ -1,5 +1,6 @@
 // LayerNorm forward/backward (net/layernorm.py:88-135): one warp per row, shuffle reductions.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 namespace nt {
@@ -9,7 +10,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      const float* __restrict__ beta, float* __restrict__ y,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      int M, int D, float eps, const float* __restrict__ post_add,
-                                                     int period) {
+                                                     int period, __nv_bfloat16* __restrict__ y_hi,
+                                                     __nv_bfloat16* __restrict__ y_lo) {
   pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -29,6 +31,11 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     float o = (xr[c] - mean) * rstd * gamma[c] + beta[c];
     if (pa) o += pa[c];
     yr[c] = o;
+    if (y_hi) {                                    // operand of the next BF16x3 GEMM: hi = bf16(y), lo = bf16(y - hi)
+      const __nv_bfloat16 h = __float2bfloat16_rn(o);
+      y_hi[(long long)warp * D + c] = h;
+      y_lo[(long long)warp * D + c] = __float2bfloat16_rn(o - __bfloat162float(h));
+    }
   }
 }
 
@@ -100,7 +107,8 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* __restri
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma, float* __restrict__ dx,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
-                                                           int D, const float* __restrict__ addend, int LN_ROWS) {
+                                                           int D, const float* __restrict__ addend, int LN_ROWS,
+                                                           uint2* __restrict__ dx_hi, uint2* __restrict__ dx_lo) {
   pdl_prologue();
   extern __shared__ float red[];                 // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,6 +165,13 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* __restri
           o.z = rs * (g[k].z * d.z - s1 - xh.z * s2) + av[k].z;
           o.w = rs * (g[k].w * d.w - s1 - xh.w * s2) + av[k].w;
           reinterpret_cast<float4*>(dx)[off4 + c4] = o;
+          if (dx_hi) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+            dx_hi[off4 + c4] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+            dx_lo[off4 + c4] = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+          }
         }
       }
     }
@@ -183,14 +198,15 @@ __global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const float* __restri
 
 template <int NV>
 static int launch_ln_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                               float* dx, float* dgamma, float* dbeta, int M, int D, const float* addend) {
+                               float* dx, float* dgamma, float* dbeta, int M, int D, const float* addend, void* dx_hi,
+                               void* dx_lo) {
   const size_t smem = sizeof(float) * 16 * (size_t)D;
   // rows per CTA: every CTA ends with 2*D same-address atomics, so large M uses taller CTAs
   int rows = 32;
   if (const char* e = getenv("NTB200_LN_ROWS")) rows = atoi(e);
   else if (M >= 32768) rows = 128;
   NT_CHECK(nt::launch_k(ln_bwd_fused_kernel<NV>, dim3(ceil_div(M, rows)), dim3(256), smem, dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D,
-                                                                         addend, rows));
+                                                                         addend, rows, (uint2*)dx_hi, (uint2*)dx_lo));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -200,32 +216,58 @@ using namespace nt;
 
 extern "C" {
 
-int nt_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
-                     int M, int D, float eps, const float* post_add, int period) {
+static int ln_fwd_impl(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int M, int D,
+                       float eps, const float* post_add, int period, void* y_hi, void* y_lo) {
   NT_ENTRY();
   NT_REQUIRE(M >= 0 && D > 0, "nt_layernorm_fwd: bad shape M=%d D=%d", M, D);
   NT_REQUIRE(!post_add || period > 0, "nt_layernorm_fwd: post_add needs period > 0");
+  NT_REQUIRE((y_hi != nullptr) == (y_lo != nullptr), "nt_layernorm_fwd_split: pass both split planes or neither");
   if (M == 0) return 0;
   NT_CHECK(nt::launch_k(ln_fwd_kernel, dim3(ceil_div((long long)M * 32, 256)), dim3(256), 0, x, gamma, beta, y, mean, rstd, M, D, eps,
-                                                                        post_add, period));
+                                                                        post_add, period, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo));
   NT_LAUNCH_OK();
   return 0;
 }
 
+int nt_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                     int M, int D, float eps, const float* post_add, int period) {
+  return ln_fwd_impl(x, gamma, beta, y, mean, rstd, M, D, eps, post_add, period, nullptr, nullptr);
+}
+
+int nt_layernorm_fwd_split(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                           int M, int D, float eps, const float* post_add, int period, void* y_hi, void* y_lo) {
+  return ln_fwd_impl(x, gamma, beta, y, mean, rstd, M, D, eps, post_add, period, y_hi, y_lo);
+}
+
+static int ln_bwd_impl(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       float* dx, float* dgamma, float* dbeta, int M, int D, const float* addend, void* dx_hi, void* dx_lo);
+
 int nt_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                      float* dx, float* dgamma, float* dbeta, int M, int D, const float* addend) {
+  return ln_bwd_impl(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend, nullptr, nullptr);
+}
+
+int nt_layernorm_bwd_split(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                           float* dx, float* dgamma, float* dbeta, int M, int D, const float* addend, void* dx_hi, void* dx_lo) {
+  return ln_bwd_impl(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend, dx_hi, dx_lo);
+}
+
+static int ln_bwd_impl(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       float* dx, float* dgamma, float* dbeta, int M, int D, const float* addend, void* dx_hi, void* dx_lo) {
   NT_ENTRY();
+  NT_REQUIRE((dx_hi != nullptr) == (dx_lo != nullptr), "nt_layernorm_bwd_split: pass both split planes or neither");
   NT_REQUIRE(M >= 0 && D > 0, "nt_layernorm_bwd: bad shape M=%d D=%d", M, D);
   if (M == 0) return 0;
   static int split_big = -1;
   if (split_big < 0) { const char* e = getenv("NTB200_LN_SPLIT"); split_big = e ? atoi(e) : 0; }
   const bool vec_ok = (D % 4 == 0) && ((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)addend | (uintptr_t)gamma) & 15) == 0);
   if (D <= 768 && vec_ok && (dgamma != nullptr) == (dbeta != nullptr) && !(split_big && M >= 32768)) {
-    if (D <= 128) return launch_ln_bwd_fused<1>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
-    if (D <= 256) return launch_ln_bwd_fused<2>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
-    if (D <= 384) return launch_ln_bwd_fused<3>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
-    return launch_ln_bwd_fused<6>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend);
+    if (D <= 128) return launch_ln_bwd_fused<1>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend, dx_hi, dx_lo);
+    if (D <= 256) return launch_ln_bwd_fused<2>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend, dx_hi, dx_lo);
+    if (D <= 384) return launch_ln_bwd_fused<3>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend, dx_hi, dx_lo);
+    return launch_ln_bwd_fused<6>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend, dx_hi, dx_lo);
   }
+  NT_REQUIRE(!dx_hi, "nt_layernorm_bwd_split: split output needs the fused kernel (D %% 4 == 0, D <= 768, aligned pointers)");
   if (dgamma && dbeta) {
     int rows_per_block = M >= 8192 ? 512 : 128;
     dim3 grid(ceil_div(D, 32), ceil_div(M, rows_per_block));

@@ -121,7 +121,7 @@ int nt_linear_bwd_params(const float* x, const float* dy, float* dw, float* db, 
 
 // ---- BF16x3 variants: operands pre-split by nt_split_bf16 (hi/lo bf16, contraction dim contiguous)
 int nt_linear_fwd_bf16x3(const void* x_hi, const void* x_lo, const void* wt_hi, const void* wt_lo, const float* b, float* y,
-                         int M, int K, int N, int act, float* pre, const float* residual) {
+                         int M, int K, int N, int act, float* pre, const float* residual, void* y_hi, void* y_lo) {
   NT_ENTRY();
   NT_REQUIRE(M >= 0 && K > 0 && N > 0 && (K & 7) == 0, "nt_linear_fwd_bf16x3: bad shape M=%d K=%d N=%d (K %% 8)", M, K, N);
   NT_REQUIRE(act >= 0 && act <= 2, "nt_linear_fwd_bf16x3: act %d", act);
@@ -131,6 +131,8 @@ int nt_linear_fwd_bf16x3(const void* x_hi, const void* x_lo, const void* wt_hi, 
   d.A_hi = x_hi; d.A_lo = x_lo; d.lda_b = K;          // x  [M][K]
   d.B_hi = wt_hi; d.B_lo = wt_lo; d.ldb_b = K;        // w^T [N][K]
   d.ep.bias = b; d.ep.act = act; d.ep.pre_out = pre; d.ep.addend = residual;
+  NT_REQUIRE((y_hi != nullptr) == (y_lo != nullptr), "nt_linear_fwd_bf16x3: pass both split output planes or neither");
+  d.ep.out_hi = y_hi; d.ep.out_lo = y_lo;
   bool handled = false;
   int rc = gemm_tc(d, 3, &handled);
   if (rc) return rc;
@@ -139,7 +141,7 @@ int nt_linear_fwd_bf16x3(const void* x_hi, const void* x_lo, const void* wt_hi, 
 }
 
 int nt_linear_bwd_input_bf16x3(const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, float* dx, int M, int K,
-                               int N, int act, const float* pre, const float* addend) {
+                               int N, int act, const float* pre, const float* addend, void* dx_hi, void* dx_lo) {
   NT_ENTRY();
   NT_REQUIRE(M >= 0 && K > 0 && N > 0 && (N & 7) == 0, "nt_linear_bwd_input_bf16x3: bad shape M=%d K=%d N=%d (N %% 8)", M, K, N);
   if (M == 0) return 0;
@@ -148,6 +150,8 @@ int nt_linear_bwd_input_bf16x3(const void* dy_hi, const void* dy_lo, const void*
   d.A_hi = dy_hi; d.A_lo = dy_lo; d.lda_b = N;        // dy [M][N]
   d.B_hi = w_hi; d.B_lo = w_lo; d.ldb_b = N;          // w  [K][N]: row k_in is output column k_in, contraction over N
   d.ep.dact = act; d.ep.pre_in = pre; d.ep.addend = addend;
+  NT_REQUIRE((dx_hi != nullptr) == (dx_lo != nullptr), "nt_linear_bwd_input_bf16x3: pass both split output planes or neither");
+  d.ep.out_hi = dx_hi; d.ep.out_lo = dx_lo;
   bool handled = false;
   int rc = gemm_tc(d, 3, &handled);
   if (rc) return rc;

@@ -110,6 +110,7 @@ class DeviceArray:
         self.host_dtype = np.dtype(host_dtype) if host_dtype is not None else (
             np.dtype(np.float64) if self.dtype.kind == "f" else np.dtype(np.int64))
         self._argmax = None
+        self._split = None          # (hi, lo) bf16 planes of this tensor emitted by its producer (ops.split_bf16 reuses them)
 
     # ------------------------------------------------------------------ construction
     @staticmethod
@@ -167,6 +168,7 @@ class DeviceArray:
             shape[i] = self.size // rest if rest else 0
         assert _prod(shape) == self.size, "reshape %s -> %s" % (self.shape, shape)
         out = DeviceArray(shape, self.dtype, buf=self._buf, offset=self._off, host_dtype=self.host_dtype)
+        out._split = self._split          # the planes are dense copies in the same element order
         return out
 
     def view(self, offset_elems, shape):

@@ -35,23 +35,24 @@ class attention_layer():
         self._fused = False
         if kind == ops.MASK_NONE and fused_vit.supported(self.block, self.embed_dim, self.num_h):
             return fused_vit.forward_stack([self], x)             # whole block in one launch (csrc/vit_block.cu)
-        self.out = self.norm._forward(x)
+        # split_out: producers whose output feeds a Linear also emit its bf16 hi/lo planes (BF16x3 engine, large shapes)
+        self.out = self.norm._forward(x, split_out=True)
         self.qkv = self.qkvfc._forward(self.out)                       # (B,N,3D): [q,k,v][head][dh]
         input1, self.P, _ = ops.attention_fwd(self.qkv, self.num_h, dmask, kind, residual=x)
-        self.out1 = self.norm1._forward(input1)
-        self.out2, self.pre2 = self.fc0._forward(self.out1, ops.ACT_GELU, want_pre=True)
+        self.out1 = self.norm1._forward(input1, split_out=True)
+        self.out2, self.pre2 = self.fc0._forward(self.out1, ops.ACT_GELU, want_pre=True, split_out=True)
         return self.fc1._forward(self.out2, residual=input1)          # out6 + input1
 
     def backward(self, delta):
         delta = as_device(delta)
         if getattr(self, "_fused", False):
             return fused_vit.backward_stack([self], delta)
-        d = self.fc1._backward(delta, self.out2, ops.ACT_GELU, self.pre2)   # fc1.backward + gelu.backward
+        d = self.fc1._backward(delta, self.out2, ops.ACT_GELU, self.pre2, split_out=True)   # fc1.backward + gelu.backward
         d = self.fc0._backward(d, self.out1)
         delta0 = self.norm1._backward(d, addend=delta)                 # delta0 += delta (attention.py:62)
-        self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h, self._mask_kind)
+        self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h, self._mask_kind, split_out=True)
         d = self.qkvfc._backward(self.delta_qkv, self.out)
-        return self.norm._backward(d, addend=delta0)                   # input_delta += delta0 (attention.py:88)
+        return self.norm._backward(d, addend=delta0, split_out=True)   # input_delta += delta0 (attention.py:88)
 
     @property
     def atg__(self):

@@ -35,13 +35,14 @@ class attdecoderblock_layer():
         self.batch, self.block, _ = x.shape
         kind, dmask = ops.detect_mask(masks, self.block)
         self._mask_kind = kind
-        self.out0 = self.norm._forward(x)
-        self.out2, self.pre2 = self.fc0._forward(self.out0, ops.ACT_RELU, want_pre=True)
+        # split_out: producers whose output feeds a Linear also emit its bf16 hi/lo planes (BF16x3 engine, large shapes)
+        self.out0 = self.norm._forward(x, split_out=True)
+        self.out2, self.pre2 = self.fc0._forward(self.out0, ops.ACT_RELU, want_pre=True, split_out=True)
         self.out6 = self.fc1._forward(self.out2, residual=x)
-        self.outnorm = self.norm1._forward(self.out6)
+        self.outnorm = self.norm1._forward(self.out6, split_out=True)
         self.qkv = self.qkvfc._forward(self.outnorm)
         self.rkk, self.P, self.S = ops.attention_fwd(self.qkv, self.num_h, dmask, kind,
-                                                     want_scores=self.return_attention)
+                                                     want_scores=self.return_attention, split_out=True)
         input1 = self.fc_out._forward(self.rkk, residual=self.out6)
         if self.return_attention:
             return self.atg__, self.att_col
@@ -50,12 +51,12 @@ class attdecoderblock_layer():
     def backward(self, delta):
         delta = as_device(delta, self.norm.host_dtype)
         delta0 = self.fc_out._backward(delta, self.rkk)
-        self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h, self._mask_kind)
+        self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h, self._mask_kind, split_out=True)
         d = self.qkvfc._backward(self.delta_qkv, self.outnorm)
-        qkvdelta = self.norm1._backward(d, addend=delta)               # + delta (attdecoderblock.py:105)
-        d = self.fc1._backward(qkvdelta, self.out2, ops.ACT_RELU, self.pre2)   # fc1.backward + relu.backward
+        qkvdelta = self.norm1._backward(d, addend=delta, split_out=True)               # + delta (attdecoderblock.py:105)
+        d = self.fc1._backward(qkvdelta, self.out2, ops.ACT_RELU, self.pre2, split_out=True)   # fc1.backward + relu.backward
         d = self.fc0._backward(d, self.out0)
-        return self.norm._backward(d, addend=qkvdelta)                 # += qkvdelta (attdecoderblock.py:110)
+        return self.norm._backward(d, addend=qkvdelta, split_out=True)                 # += qkvdelta (attdecoderblock.py:110)
 
     @property
     def atg__(self):

@@ -40,14 +40,15 @@ class fclayer(object):
         self.inputs = None
 
     # --- extended forms used by the fused composite layers
-    def _forward(self, x, act=ops.ACT_NONE, want_pre=False, residual=None):
+    def _forward(self, x, act=ops.ACT_NONE, want_pre=False, residual=None, split_out=False):
         self.inputs = x
         keep = []
-        out = ops.linear_fwd(x, self.params, self.bias_params if self.bias else None, act, want_pre, residual, keep_xt=keep)
+        out = ops.linear_fwd(x, self.params, self.bias_params if self.bias else None, act, want_pre, residual, keep_xt=keep,
+                             split_out=split_out)
         self._xt = (x, keep[0]) if keep else None       # BF16x3 path: transposed split of x, made in the forward's pass
         return out
 
-    def _backward(self, dy, x, act=ops.ACT_NONE, pre=None, addend=None, want_dx=True):
+    def _backward(self, dy, x, act=ops.ACT_NONE, pre=None, addend=None, want_dx=True, split_out=False):
         K, N = self.params.shape
         M = dy.size // N
         xt = dy_split = dyt = None
@@ -67,7 +68,7 @@ class fclayer(object):
         self._xt = None
         if not want_dx:
             return None
-        return ops.linear_bwd_input(dy, self.params, act, pre, addend, dy_split=dy_split)
+        return ops.linear_bwd_input(dy, self.params, act, pre, addend, dy_split=dy_split, split_out=split_out)
 
     # --- reference protocol
     def forward(self, inputs):

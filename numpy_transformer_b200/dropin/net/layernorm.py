@@ -30,16 +30,18 @@ class layer_norm(object):
         self._lead = 0          # the reference expands gamma/beta to the input rank on first forward (:105-108)
         self.inputs = self.mean = self.rstd = None
 
-    def _forward(self, x, post_add=None):
+    def _forward(self, x, post_add=None, split_out=False):
+        """split_out: the output feeds a Linear; emit its bf16 hi/lo planes too when that Linear will run BF16x3."""
         self.inputs = x
         self._lead = x.ndim - len(self.normalized_shape)
-        y, self.mean, self.rstd = ops.layernorm_fwd(x, self.gamma, self.beta, post_add)
+        y, self.mean, self.rstd = ops.layernorm_fwd(x, self.gamma, self.beta, post_add, split_out=split_out)
         return y
 
-    def _backward(self, dy, addend=None, want_dx=True):
+    def _backward(self, dy, addend=None, want_dx=True, split_out=False):
         aff = self.elementwise_affine
         return ops.layernorm_bwd(dy, self.inputs, self.mean, self.rstd, self.gamma,
-                                 self.gamma_delta if aff else None, self.beta_delta if aff else None, addend, want_dx)
+                                 self.gamma_delta if aff else None, self.beta_delta if aff else None, addend, want_dx,
+                                 split_out=split_out)
 
     def forward(self, inputs):
         return self._forward(as_device(inputs, self.host_dtype))

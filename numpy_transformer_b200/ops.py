@@ -19,8 +19,22 @@ def bf16x3_ok(M, K, N):
     return M >= int(os.environ.get("NTB200_BF16X3_MIN_ROWS", "2048")) and K % 8 == 0 and N % 8 == 0 and K >= 32 and N >= 32
 
 
+def want_split(rows, cols):
+    """A producer whose [rows, cols] output feeds a Linear should also emit the bf16 hi / lo planes (the consumer will
+    take the BF16x3 engine): saves the separate split pass over the fp32 tensor.  NTB200_PRODUCER_SPLIT=0 disables it."""
+    import os
+    return os.environ.get("NTB200_PRODUCER_SPLIT", "1") != "0" and bf16x3_ok(rows, cols, cols)
+
+
+def new_planes(n_elems):
+    return DeviceArray((n_elems // 2,)), DeviceArray((n_elems // 2,))          # two bf16 per fp32 word
+
+
 def split_bf16(x, rows, cols, transpose=False):
-    """-> (hi, lo, pitch): bf16 planes of x [rows, cols] (or of its transpose, pitch padded to a multiple of 8)."""
+    """-> (hi, lo, pitch): bf16 planes of x [rows, cols] (or of its transpose, pitch padded to a multiple of 8).
+    Planes attached by the producer of x (x._split) are reused."""
+    if not transpose and getattr(x, "_split", None) is not None:
+        return x._split[0], x._split[1], cols
     ld = cols if not transpose else (rows + 7) // 8 * 8
     out_rows = cols if transpose else rows
     hi = DeviceArray((out_rows * ld // 2,))          # two bf16 per fp32 word
@@ -45,7 +59,7 @@ def _mn_major():
     return os.environ.get("NTB200_BF16X3_MN", "1") != "0"
 
 
-def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None, keep_xt=None):
+def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None, keep_xt=None, split_out=False):
     """keep_xt: a list; on the BF16x3 path the split of x that the weight-gradient GEMM will need (the forward's own
     operand when dW reads MN-major operands, else the transposed split made in the same pass) is appended to it."""
     K, N = w.shape
@@ -62,21 +76,30 @@ def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None, keep_x
             if keep_xt is not None:
                 keep_xt.append((xh, xl, 0))             # pitch 0 = untransposed
         wh, wl, _ = split_bf16(w, K, N, transpose=True)            # w^T [N][K]
+        yh = yl = None
+        if split_out and want_split(M, N):
+            yh, yl = new_planes(M * N)
+            y._split = (yh, yl)
         lib.nt_linear_fwd_bf16x3(xh.ptr, xl.ptr, wh.ptr, wl.ptr, ptr_or_null(b), y.ptr, M, K, N, act, ptr_or_null(pre),
-                                 ptr_or_null(residual))
+                                 ptr_or_null(residual), ptr_or_null(yh), ptr_or_null(yl))
         return (y, pre) if want_pre else y
     lib.nt_linear_fwd(x.ptr, w.ptr, ptr_or_null(b), y.ptr, M, K, N, act, ptr_or_null(pre), ptr_or_null(residual))
     return (y, pre) if want_pre else y
 
 
-def linear_bwd_input(dy, w, act=ACT_NONE, pre=None, addend=None, dy_split=None):
+def linear_bwd_input(dy, w, act=ACT_NONE, pre=None, addend=None, dy_split=None, split_out=False):
     K, N = w.shape
     M = dy.size // N
     dx = DeviceArray(dy.shape[:-1] + (K,), host_dtype=dy.host_dtype)
     if bf16x3_ok(M, N, K):
         dh, dl = dy_split if dy_split is not None else split_bf16(dy, M, N)[:2]
         wh, wl, _ = split_bf16(w, K, N)                            # w [K][N]: contraction over N is contiguous
-        lib.nt_linear_bwd_input_bf16x3(dh.ptr, dl.ptr, wh.ptr, wl.ptr, dx.ptr, M, K, N, act, ptr_or_null(pre), ptr_or_null(addend))
+        xh_ = xl_ = None
+        if split_out and want_split(M, K):
+            xh_, xl_ = new_planes(M * K)
+            dx._split = (xh_, xl_)
+        lib.nt_linear_bwd_input_bf16x3(dh.ptr, dl.ptr, wh.ptr, wl.ptr, dx.ptr, M, K, N, act, ptr_or_null(pre), ptr_or_null(addend),
+                                       ptr_or_null(xh_), ptr_or_null(xl_))
         return dx
     lib.nt_linear_bwd_input(dy.ptr, w.ptr, dx.ptr, M, K, N, act, ptr_or_null(pre), ptr_or_null(addend))
     return dx
@@ -100,47 +123,74 @@ def linear_bwd_params(x, dy, dw, db=None, xt_split=None, dyt_split=None):
     lib.nt_linear_bwd_params(x.ptr, dy.ptr, dw.ptr, ptr_or_null(db), M, K, N)
 
 
-def layernorm_fwd(x, gamma, beta, post_add=None):
+def layernorm_fwd(x, gamma, beta, post_add=None, split_out=False):
     D = gamma.size
     M = x.size // D
     y = x.empty_like()
     mean = DeviceArray((M,))
     rstd = DeviceArray((M,))
     period = 0 if post_add is None else post_add.size // D
+    if split_out and want_split(M, D):
+        yh, yl = new_planes(M * D)
+        y._split = (yh, yl)
+        lib.nt_layernorm_fwd_split(x.ptr, gamma.ptr, beta.ptr, y.ptr, mean.ptr, rstd.ptr, M, D, LN_EPS,
+                                   ptr_or_null(post_add), period, yh.ptr, yl.ptr)
+        return y, mean, rstd
     lib.nt_layernorm_fwd(x.ptr, gamma.ptr, beta.ptr, y.ptr, mean.ptr, rstd.ptr, M, D, LN_EPS,
                          ptr_or_null(post_add), period)
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, addend=None, want_dx=True):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, addend=None, want_dx=True, split_out=False):
     D = gamma.size
     M = x.size // D
     dx = x.empty_like() if want_dx else None
+    if (split_out and want_dx and want_split(M, D) and D <= 768 and (dgamma is None) == (dbeta is None)):
+        dh, dl = new_planes(M * D)
+        dx._split = (dh, dl)
+        lib.nt_layernorm_bwd_split(dy.ptr, x.ptr, mean.ptr, rstd.ptr, gamma.ptr, dx.ptr, ptr_or_null(dgamma), ptr_or_null(dbeta),
+                                   M, D, ptr_or_null(addend), dh.ptr, dl.ptr)
+        return dx
     lib.nt_layernorm_bwd(dy.ptr, x.ptr, mean.ptr, rstd.ptr, gamma.ptr, ptr_or_null(dx), ptr_or_null(dgamma),
                          ptr_or_null(dbeta), M, D, ptr_or_null(addend))
     return dx
 
 
-def attention_fwd(qkv, H, mask=None, mask_kind=MASK_NONE, residual=None, want_scores=False):
+def _att_bf16(N, dh):
+    import os
+    return (dh == 64 and N >= int(os.environ.get("NTB200_ATT_BF16_MIN_N", "1")) and get_gemm_mode() == 1
+            and os.environ.get("NTB200_ATT_BF16", "1") != "0")
+
+
+def attention_fwd(qkv, H, mask=None, mask_kind=MASK_NONE, residual=None, want_scores=False, split_out=False):
     B, N, three_d = qkv.shape
     D = three_d // 3
     out = DeviceArray((B, N, D), host_dtype=qkv.host_dtype)
     P = DeviceArray((B, H, N, N), host_dtype=qkv.host_dtype)
     S = P.empty_like() if want_scores else None
+    if split_out and _att_bf16(N, D // H) and want_split(B * N, D):
+        oh, ol = new_planes(B * N * D)
+        out._split = (oh, ol)
+        lib.nt_attention_fwd_split(qkv.ptr, ptr_or_null(mask), mask_kind, out.ptr, P.ptr, ptr_or_null(S), B, N, H, D // H,
+                                   ptr_or_null(residual), oh.ptr, ol.ptr)
+        return out, P, S
     lib.nt_attention_fwd(qkv.ptr, ptr_or_null(mask), mask_kind, out.ptr, P.ptr, ptr_or_null(S), B, N, H, D // H,
                          ptr_or_null(residual))
     return out, P, S
 
 
-def attention_bwd(dout, qkv, P, H, mask_kind=MASK_NONE):
+def attention_bwd(dout, qkv, P, H, mask_kind=MASK_NONE, split_out=False):
     B, N, three_d = qkv.shape
     D = three_d // 3
     dh = D // H
     dqkv = qkv.empty_like()
-    import os
-    if (dh == 64 and N >= int(os.environ.get("NTB200_ATT_BF16_MIN_N", "1")) and get_gemm_mode() == 1
-            and os.environ.get("NTB200_ATT_BF16", "1") != "0"):
+    if _att_bf16(N, dh):
         scratch = DeviceArray((B * H * N,))             # BF16x3 kernels: row sums of dP o P only
+        if split_out and want_split(B * N, 3 * D):
+            gh, gl = new_planes(B * N * 3 * D)
+            dqkv._split = (gh, gl)
+            lib.nt_attention_bwd_split(dout.ptr, qkv.ptr, P.ptr, dqkv.ptr, scratch.ptr, B, N, H, dh, int(mask_kind), gh.ptr, gl.ptr)
+            return dqkv
     else:
         scratch = None if (N <= 64 and dh <= 64 and dh % 4 == 0) else P.empty_like()
     lib.nt_attention_bwd(dout.ptr, qkv.ptr, P.ptr, dqkv.ptr, ptr_or_null(scratch), B, N, H, dh, int(mask_kind))
