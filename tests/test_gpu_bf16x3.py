@@ -95,3 +95,47 @@ def test_fclayer_uses_engine_and_matches_tf32x3_path(nt):
     os.environ["NTB200_BF16X3_MIN_ROWS"] = "1"
     for a, b_ in zip(*outs):
         assert rel_err(a, b_) < TOL
+
+
+def test_vit_per_op_path_with_producer_splits(nt):
+    """Whole ViT step on the per-op path (D = 128 is outside the fused block kernels) with the BF16x3 engine forced:
+    LayerNorm, GEMM-epilogue and attention kernels hand their bf16 planes to the next Linear (DeviceArray._split)."""
+    from numpy_transformer_b200 import trainer
+    from oracle import models as M
+    cfg = M.ViTConfig(batch=4, embed_dim=128, heads=2, blocks=2)
+    params = M.vit_init(cfg, 0)
+    images, labels, onehot = M.synthetic_vit_batch(cfg, 1)
+    layers = trainer.build_vit_layers(4, embed_dim=128, heads=2, blocks=2, seed=0)
+    ts = trainer.TrainStep(layers, "vit", images.shape, lr=0.02)
+    for step in range(3):
+        ref = M.vit_step(params, images, onehot, 0.02, cfg)
+        loss, amax = ts.step(images, labels, want_argmax=True)
+        assert abs(loss - ref["loss"]) < TOL * abs(ref["loss"]), step
+        assert np.array_equal(amax, ref["argmax"])
+        params = ref["params"]
+        for i, (a, b_) in enumerate(zip(M.tree_leaves(trainer.save_walk(layers)), M.tree_leaves(params))):
+            assert rel_err(a.reshape(-1), b_.reshape(-1)) < TOL, "step %d leaf %d" % (step, i)
+    blk = layers[2]
+    assert not getattr(blk, "_fused", False)
+    assert blk.out._split is not None and blk.out1._split is not None and blk.out2._split is not None   # LN, LN, GELU epilogue
+    assert blk.delta_qkv._split is not None                                                            # attention backward
+
+
+def test_gpt_step_with_producer_splits(nt):
+    """GPT blocks (dh = 64, T = 128) with the BF16x3 engine forced: loss of the first step and after two SGD updates
+    (which carries every gradient) against the oracle; attention forward / backward and LayerNorm backward emit the
+    planes their consumers read."""
+    from numpy_transformer_b200 import trainer
+    from oracle import models as M
+    cfg = M.GPTConfig(batch=2, context=128, embed_dim=128, heads=2, blocks=2, vocab=48)
+    params = M.gpt_init(cfg, 0)
+    tokens, labels = M.synthetic_gpt_batch(cfg, 1)
+    layers = trainer.build_gpt_layers(2, 128, 128, 2, 2, 48, adam=False, seed=0)
+    ts = trainer.TrainStep(layers, "gpt", tokens.shape, lr=0.05, adam=False)
+    for step in range(3):
+        ref = M.gpt_step(params, None, tokens, labels, 0.05, cfg, adam=False)
+        loss = ts.step(tokens, labels)
+        assert abs(loss - ref["loss"]) < TOL * abs(ref["loss"]), step
+        params = ref["params"]
+    blk = layers[1]
+    assert blk.rkk._split is not None and blk.delta_qkv._split is not None and blk.out0._split is not None
