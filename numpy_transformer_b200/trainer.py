@@ -436,6 +436,36 @@ class TrainStep:
         for obj, *_ in self.arena.slots:
             obj.t = t
 
+    # ------------------------------------------------------------------ resumable checkpoints
+    def state_dict(self):
+        """Everything needed to resume bit-for-bit: the reference's own checkpoint tree (`save_walk`, what its
+        trainers pickle: transformer_of_image.py:200-208) PLUS the optimizer state the reference never saves
+        (Adam* moments and step counter, net/fullconnect.py:66-73,97) and the current learning rate."""
+        self.sync_layer_counters()
+        out = {"model": save_walk(self.layers), "lr": self._lr, "steps_done": self.steps_done, "adam": bool(self.adam),
+               "t": int(self.d_t)}
+        if self.adam:
+            out["adam_m"] = self.arena.m.numpy().copy()
+            out["adam_v"] = self.arena.v.numpy().copy()
+            out["arena_size"] = self.arena.n
+        return out
+
+    def load_state_dict(self, state):
+        """Inverse of state_dict().  A plain reference checkpoint (the nested list alone) is accepted too: parameters are
+        restored and the optimizer state starts fresh, exactly what the reference's own restore does."""
+        if not isinstance(state, dict):
+            state = {"model": state}
+        restore_walk(self.layers, state["model"])
+        if "lr" in state:
+            self.set_lr(state["lr"])
+        if self.adam and "adam_m" in state:
+            assert state.get("arena_size") == self.arena.n, "optimizer state belongs to a different model"
+            self.arena.m.set(state["adam_m"])
+            self.arena.v.set(state["adam_v"])
+            self.d_t.set(np.array([state["t"]], dtype=np.int32))
+            self.sync_layer_counters()
+        lib.nt_sync()
+
     def close(self):
         """Destroy the captured graphs (required before DataParallel.shutdown: they hold NCCL kernels)."""
         lib.nt_sync()
