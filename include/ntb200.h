@@ -167,6 +167,16 @@ int nt_attention_fwd_split(const float* qkv, const float* mask, int mask_kind, f
 int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch,
                            int B, int N, int H, int dh, int mask_kind, void* dqkv_hi, void* dqkv_lo);
 
+/* KV-cache decode.  The reference generates by re-running the whole window for every new token
+ * (gpt/gpt_predict_poetrythree.py:108-121, gpt/gpt_train_potry3000.py:300-342); while the window is still growing the
+ * keys / values of earlier tokens are unchanged, so they are cached per block.
+ * nt_kv_append: copy the k and v columns of qkv [B,T,3D] into caches [B,Tmax,D] at rows pos0..pos0+T-1.
+ * nt_attention_decode: out[b, h*dh..] = softmax(q K^T / sqrt(dh)) V for the single new query qkv_new [B,3D] over cache
+ * rows 0..len-1 (its own k, v already appended). */
+int nt_kv_append(const float* qkv, float* kcache, float* vcache, int B, int T, int Tmax, int pos0, int D);
+int nt_attention_decode(const float* qkv_new, const float* kcache, const float* vcache, float* out, int B, int Tmax, int len,
+                        int H, int dh);
+
 /* ---------------------------------------------------------------- fused ViT encoder blocks
  * attention_layer.forward / backward (attention.py:20-55, 57-89) for a whole stack of blocks in ONE launch
  * each way: one CTA per image walks every block (LN -> qkv -> attention -> +res -> LN1 -> fc0 -> GELU ->

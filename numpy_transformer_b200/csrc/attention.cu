@@ -1058,6 +1058,61 @@ static int softmax_rows(const float* x, float* p, long long rows, int cols, cons
   return 0;
 }
 
+// ---------------------------------------------------------------- KV-cache decode step
+// The reference regenerates by re-running the whole window for every new token (gpt_predict_poetrythree.py:108-121,
+// gpt_train_potry3000.py:300-342).  While the window is still growing the keys / values of the earlier tokens do not
+// change (causal mask, learned positions fixed per index), so they are cached per block and one step only attends
+// the new token's query over them.
+__global__ void kv_append_kernel(const float* __restrict__ qkv, float* __restrict__ kc, float* __restrict__ vc, int B, int T,
+                                 int Tmax, int pos0, int D) {
+  pdl_prologue();
+  const long long total = (long long)B * T * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long long bt = i / D;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const float* row = qkv + ((long long)b * T + t) * 3 * D;
+    const long long o = ((long long)b * Tmax + pos0 + t) * D + d;
+    kc[o] = row[D + d];
+    vc[o] = row[2 * D + d];
+  }
+}
+
+// one warp per (sample, head): scores over the cached keys, softmax, weighted sum of the cached values
+__global__ void __launch_bounds__(32) attn_decode_kernel(const float* __restrict__ qkv_new, const float* __restrict__ kc,
+                                                         const float* __restrict__ vc, float* __restrict__ out, int Tmax,
+                                                         int len, int H, int dh) {
+  pdl_prologue();
+  extern __shared__ float sm[];          // [dh] q, [len] p
+  float* sq = sm;
+  float* sp = sm + dh;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H, D = H * dh, lane = threadIdx.x;
+  for (int d = lane; d < dh; d += 32) sq[d] = qkv_new[(long long)b * 3 * D + h * dh + d];
+  __syncwarp();
+  const float scale = 1.0f / sqrtf((float)dh);
+  const float* kb = kc + (long long)b * Tmax * D + h * dh;
+  const float* vb = vc + (long long)b * Tmax * D + h * dh;
+  float mx = -INFINITY;
+  for (int j = lane; j < len; j += 32) {
+    float s = 0.f;
+    for (int d = 0; d < dh; d++) s = fmaf(sq[d], kb[(long long)j * D + d], s);
+    s *= scale;                                       // attdecoderblock.py:57; the new token sees every cached key
+    sp[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < len; j += 32) { const float e = expf(sp[j] - mx); sp[j] = e; sum += e; }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.0f / sum;
+  for (int d = lane; d < dh; d += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < len; j++) acc = fmaf(sp[j], vb[(long long)j * D + d], acc);
+    out[(long long)b * D + h * dh + d] = acc * inv;
+  }
+}
+
 }  // namespace nt
 using namespace nt;
 
@@ -1279,6 +1334,29 @@ int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, 
   NT_REQUIRE((dqkv_hi != nullptr) == (dqkv_lo != nullptr), "nt_attention_bwd_split: pass both split planes or neither");
   if (B == 0) return 0;
   return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0, dqkv_hi, dqkv_lo);
+}
+
+int nt_kv_append(const float* qkv, float* kcache, float* vcache, int B, int T, int Tmax, int pos0, int D) {
+  NT_ENTRY();
+  NT_REQUIRE(B >= 0 && T >= 0 && pos0 >= 0 && pos0 + T <= Tmax && D > 0, "nt_kv_append: rows %d..%d do not fit a cache of %d", pos0, pos0 + T, Tmax);
+  const long long total = (long long)B * T * D;
+  if (total == 0) return 0;
+  NT_CHECK(nt::launch_k(kv_append_kernel, dim3((unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184)), dim3(256), 0, qkv, kcache,
+                        vcache, B, T, Tmax, pos0, D));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_attention_decode(const float* qkv_new, const float* kcache, const float* vcache, float* out, int B, int Tmax, int len,
+                        int H, int dh) {
+  NT_ENTRY();
+  NT_REQUIRE(B >= 0 && len >= 1 && len <= Tmax && H > 0 && dh > 0, "nt_attention_decode: bad shape (len %d, cache %d)", len, Tmax);
+  if (B == 0) return 0;
+  const size_t smem = sizeof(float) * ((size_t)dh + len);
+  NT_REQUIRE(smem <= 48 * 1024, "nt_attention_decode: context %d too long", len);
+  NT_CHECK(nt::launch_k(attn_decode_kernel, dim3(B * H), dim3(32), smem, qkv_new, kcache, vcache, out, Tmax, len, H, dh));
+  NT_LAUNCH_OK();
+  return 0;
 }
 
 }  // extern "C"
