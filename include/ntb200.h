@@ -176,6 +176,17 @@ int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, 
 int nt_kv_append(const float* qkv, float* kcache, float* vcache, int B, int T, int Tmax, int pos0, int D);
 int nt_attention_decode(const float* qkv_new, const float* kcache, const float* vcache, float* out, int B, int Tmax, int len,
                         int H, int dh);
+/* The same steps with the position read from device memory (*d_pos = index of the new token; len = *d_pos + 1), so ONE
+ * captured CUDA graph replays for every decode step: nt_decode_embed (token row + position row *d_pos,
+ * PatchEmbed.py:132-138), nt_kv_append_at (T = 1), nt_attention_decode_at, nt_argmax_next (greedy choice,
+ * gpt_predict_poetrythree.py:115-117 with np.argmax: tok[b] and hist[b, *d_pos + 1] = first maximum of logits[b, :cols]),
+ * then nt_increment(d_pos). */
+int nt_decode_embed(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int D, int Tmax,
+                    const int32_t* d_pos);
+int nt_kv_append_at(const float* qkv, float* kcache, float* vcache, int B, int Tmax, int D, const int32_t* d_pos);
+int nt_attention_decode_at(const float* qkv_new, const float* kcache, const float* vcache, float* out, int B, int Tmax, int H,
+                           int dh, const int32_t* d_pos);
+int nt_argmax_next(const float* logits, int ld, int cols, int B, int32_t* tok, int32_t* hist, int hist_ld, const int32_t* d_pos);
 
 /* ---------------------------------------------------------------- fused ViT encoder blocks
  * attention_layer.forward / backward (attention.py:20-55, 57-89) for a whole stack of blocks in ONE launch

@@ -1063,9 +1063,12 @@ static int softmax_rows(const float* x, float* p, long long rows, int cols, cons
 // gpt_train_potry3000.py:300-342).  While the window is still growing the keys / values of the earlier tokens do not
 // change (causal mask, learned positions fixed per index), so they are cached per block and one step only attends
 // the new token's query over them.
+// `d_pos` (may be NULL): position read from device memory, so one captured graph serves every decode step.
 __global__ void kv_append_kernel(const float* __restrict__ qkv, float* __restrict__ kc, float* __restrict__ vc, int B, int T,
-                                 int Tmax, int pos0, int D) {
+                                 int Tmax, int pos0, int D, const int32_t* __restrict__ d_pos) {
   pdl_prologue();
+  if (d_pos) pos0 = *d_pos;
+  if (pos0 + T > Tmax) return;                          // full window: the host falls back to the sliding recompute
   const long long total = (long long)B * T * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int d = (int)(i % D);
@@ -1078,39 +1081,61 @@ __global__ void kv_append_kernel(const float* __restrict__ qkv, float* __restric
   }
 }
 
-// one warp per (sample, head): scores over the cached keys, softmax, weighted sum of the cached values
-__global__ void __launch_bounds__(32) attn_decode_kernel(const float* __restrict__ qkv_new, const float* __restrict__ kc,
-                                                         const float* __restrict__ vc, float* __restrict__ out, int Tmax,
-                                                         int len, int H, int dh) {
+// one 4-warp CTA per (sample, head): scores over the cached keys (one key per thread, float4 loads), softmax, then the
+// weighted sum of the cached values (warp w takes keys w, w+4, ...; lanes run along dh so every load is one 128-byte line)
+constexpr int DEC_THREADS = 128;
+__global__ void __launch_bounds__(DEC_THREADS) attn_decode_kernel(const float* __restrict__ qkv_new, const float* __restrict__ kc,
+                                                                  const float* __restrict__ vc, float* __restrict__ out, int Tmax,
+                                                                  int len, int H, int dh, const int32_t* __restrict__ d_pos) {
   pdl_prologue();
-  extern __shared__ float sm[];          // [dh] q, [len] p
+  if (d_pos) len = min(*d_pos + 1, Tmax);
+  extern __shared__ __align__(16) float sm[];          // [dh] q | [4][dh] partial outputs | [8] reductions | [len] p
   float* sq = sm;
-  float* sp = sm + dh;
-  const int bh = blockIdx.x, b = bh / H, h = bh % H, D = H * dh, lane = threadIdx.x;
-  for (int d = lane; d < dh; d += 32) sq[d] = qkv_new[(long long)b * 3 * D + h * dh + d];
-  __syncwarp();
+  float* so = sm + dh;
+  float* sr = so + 4 * dh;
+  float* sp = sr + 8;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H, D = H * dh, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int d = tid; d < dh; d += DEC_THREADS) sq[d] = qkv_new[(long long)b * 3 * D + h * dh + d];
+  __syncthreads();
   const float scale = 1.0f / sqrtf((float)dh);
   const float* kb = kc + (long long)b * Tmax * D + h * dh;
   const float* vb = vc + (long long)b * Tmax * D + h * dh;
+  const bool vec = (dh % 4 == 0) && (D % 4 == 0);
   float mx = -INFINITY;
-  for (int j = lane; j < len; j += 32) {
+  for (int j = tid; j < len; j += DEC_THREADS) {
+    const float* kr = kb + (long long)j * D;
     float s = 0.f;
-    for (int d = 0; d < dh; d++) s = fmaf(sq[d], kb[(long long)j * D + d], s);
+    if (vec) {
+      for (int d = 0; d < dh; d += 4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+        const float4 q4 = *reinterpret_cast<const float4*>(sq + d);
+        s = fmaf(q4.x, k4.x, s); s = fmaf(q4.y, k4.y, s); s = fmaf(q4.z, k4.z, s); s = fmaf(q4.w, k4.w, s);
+      }
+    } else {
+      for (int d = 0; d < dh; d++) s = fmaf(sq[d], kr[d], s);
+    }
     s *= scale;                                       // attdecoderblock.py:57; the new token sees every cached key
     sp[j] = s;
     mx = fmaxf(mx, s);
   }
   mx = warp_max(mx);
+  if (lane == 0) sr[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(sr[0], sr[1]), fmaxf(sr[2], sr[3]));
   float sum = 0.f;
-  for (int j = lane; j < len; j += 32) { const float e = expf(sp[j] - mx); sp[j] = e; sum += e; }
+  for (int j = tid; j < len; j += DEC_THREADS) { const float e = expf(sp[j] - mx); sp[j] = e; sum += e; }
   sum = warp_sum(sum);
-  __syncwarp();
-  const float inv = 1.0f / sum;
+  if (lane == 0) sr[4 + warp] = sum;
+  __syncthreads();
+  const float inv = 1.0f / (sr[4] + sr[5] + sr[6] + sr[7]);
   for (int d = lane; d < dh; d += 32) {
     float acc = 0.f;
-    for (int j = 0; j < len; j++) acc = fmaf(sp[j], vb[(long long)j * D + d], acc);
-    out[(long long)b * D + h * dh + d] = acc * inv;
+    for (int j = warp; j < len; j += 4) acc = fmaf(sp[j], vb[(long long)j * D + d], acc);
+    so[warp * dh + d] = acc;
   }
+  __syncthreads();
+  for (int d = tid; d < dh; d += DEC_THREADS)
+    out[(long long)b * D + h * dh + d] = (so[d] + so[dh + d] + so[2 * dh + d] + so[3 * dh + d]) * inv;
 }
 
 }  // namespace nt
@@ -1342,7 +1367,18 @@ int nt_kv_append(const float* qkv, float* kcache, float* vcache, int B, int T, i
   const long long total = (long long)B * T * D;
   if (total == 0) return 0;
   NT_CHECK(nt::launch_k(kv_append_kernel, dim3((unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184)), dim3(256), 0, qkv, kcache,
-                        vcache, B, T, Tmax, pos0, D));
+                        vcache, B, T, Tmax, pos0, D, (const int32_t*)nullptr));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_kv_append_at(const float* qkv, float* kcache, float* vcache, int B, int Tmax, int D, const int32_t* d_pos) {
+  NT_ENTRY();
+  NT_REQUIRE(B >= 0 && Tmax > 0 && D > 0 && d_pos, "nt_kv_append_at: bad arguments");
+  const long long total = (long long)B * D;
+  if (total == 0) return 0;
+  NT_CHECK(nt::launch_k(kv_append_kernel, dim3((unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184)), dim3(256), 0, qkv, kcache,
+                        vcache, B, 1, Tmax, 0, D, d_pos));
   NT_LAUNCH_OK();
   return 0;
 }
@@ -1352,9 +1388,22 @@ int nt_attention_decode(const float* qkv_new, const float* kcache, const float* 
   NT_ENTRY();
   NT_REQUIRE(B >= 0 && len >= 1 && len <= Tmax && H > 0 && dh > 0, "nt_attention_decode: bad shape (len %d, cache %d)", len, Tmax);
   if (B == 0) return 0;
-  const size_t smem = sizeof(float) * ((size_t)dh + len);
+  const size_t smem = sizeof(float) * (5 * (size_t)dh + 8 + len);
   NT_REQUIRE(smem <= 48 * 1024, "nt_attention_decode: context %d too long", len);
-  NT_CHECK(nt::launch_k(attn_decode_kernel, dim3(B * H), dim3(32), smem, qkv_new, kcache, vcache, out, Tmax, len, H, dh));
+  NT_CHECK(nt::launch_k(attn_decode_kernel, dim3(B * H), dim3(DEC_THREADS), smem, qkv_new, kcache, vcache, out, Tmax, len, H, dh,
+                        (const int32_t*)nullptr));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_attention_decode_at(const float* qkv_new, const float* kcache, const float* vcache, float* out, int B, int Tmax, int H,
+                           int dh, const int32_t* d_pos) {
+  NT_ENTRY();
+  NT_REQUIRE(B >= 0 && Tmax >= 1 && H > 0 && dh > 0 && d_pos, "nt_attention_decode_at: bad arguments");
+  if (B == 0) return 0;
+  const size_t smem = sizeof(float) * (5 * (size_t)dh + 8 + Tmax);
+  NT_REQUIRE(smem <= 48 * 1024, "nt_attention_decode_at: context %d too long", Tmax);
+  NT_CHECK(nt::launch_k(attn_decode_kernel, dim3(B * H), dim3(DEC_THREADS), smem, qkv_new, kcache, vcache, out, Tmax, 0, H, dh, d_pos));
   NT_LAUNCH_OK();
   return 0;
 }

@@ -89,6 +89,48 @@ __global__ void embedding_fwd_kernel(const int32_t* __restrict__ idx, const floa
   }
 }
 
+// one decode step: out[b] = etok[idx[b]] + epos[*d_pos]  (PatchEmbed.py:132-138 for the single new position)
+__global__ void decode_embed_kernel(const int32_t* __restrict__ idx, const float* __restrict__ etok,
+                                    const float* __restrict__ epos, float* __restrict__ out, int D, int Tmax,
+                                    const int32_t* __restrict__ d_pos) {
+  pdl_prologue();
+  const int row = blockIdx.x, tok = idx[row], t = min(*d_pos, Tmax - 1);
+  for (int c = threadIdx.x; c < D; c += blockDim.x)
+    out[(long long)row * D + c] = etok[(long long)tok * D + c] + epos[(long long)t * D + c];
+}
+
+// greedy choice on device: tok[b] = argmax(logits[b, :cols]) (first index on ties, like np.argmax), also recorded at
+// hist[b, *d_pos + 1] so a whole continuation is read back with one copy
+__global__ void __launch_bounds__(256) argmax_next_kernel(const float* __restrict__ logits, int ld, int cols,
+                                                          int32_t* __restrict__ tok, int32_t* __restrict__ hist, int hist_ld,
+                                                          const int32_t* __restrict__ d_pos) {
+  pdl_prologue();
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float v = -INFINITY;
+  int idx = 0x7fffffff;
+  for (int c = tid; c < cols; c += 256) {
+    const float x = logits[(long long)row * ld + c];
+    if (x > v) { v = x; idx = c; }                    // ascending c per thread: the first maximum is kept
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  if (lane == 0) { sv[warp] = v; si[warp] = idx; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; w++)
+      if (sv[w] > v || (sv[w] == v && si[w] < idx)) { v = sv[w]; idx = si[w]; }
+    tok[row] = idx;
+    const int p = *d_pos + 1;
+    if (hist && p < hist_ld) hist[(long long)row * hist_ld + p] = idx;
+  }
+}
+
 __global__ void embedding_bwd_tok_kernel(const int32_t* __restrict__ idx, const float* __restrict__ dy,
                                          float* __restrict__ detok, int BT, int D) {
   pdl_prologue();
@@ -222,6 +264,25 @@ int nt_adam_star(float* p, float* g, float* m, float* v, size_t n, float lr, con
   NT_ENTRY();
   if (n == 0) return 0;
   NT_CHECK(nt::launch_k(adam_star_kernel, dim3(grid_for(n)), dim3(256), 0, p, g, m, v, n, lr, lr_dev, t, t_dev, zero_grad));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_decode_embed(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int D, int Tmax,
+                    const int32_t* d_pos) {
+  NT_ENTRY();
+  NT_REQUIRE(idx && etok && epos && out && d_pos && D > 0 && Tmax > 0, "nt_decode_embed: bad arguments");
+  if (B == 0) return 0;
+  NT_CHECK(nt::launch_k(decode_embed_kernel, dim3(B), dim3(D >= 256 ? 256 : 128), 0, idx, etok, epos, out, D, Tmax, d_pos));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_argmax_next(const float* logits, int ld, int cols, int B, int32_t* tok, int32_t* hist, int hist_ld, const int32_t* d_pos) {
+  NT_ENTRY();
+  NT_REQUIRE(logits && tok && d_pos && cols > 0 && ld >= cols, "nt_argmax_next: bad arguments");
+  if (B == 0) return 0;
+  NT_CHECK(nt::launch_k(argmax_next_kernel, dim3(B), dim3(256), 0, logits, ld, cols, tok, hist, hist_ld, d_pos));
   NT_LAUNCH_OK();
   return 0;
 }

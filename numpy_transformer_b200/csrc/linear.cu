@@ -24,6 +24,89 @@ __global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ 
   }
 }
 
+// ---- skinny forward: M <= 8 rows (one decode step of the KV-cache generator, tiny heads).  A 128-row tensor-core tile
+// would be >= 94 % padding and walk K serially in one CTA (20-50 us measured for 1 x 384 x {384..2350}); here the weight
+// panel is streamed once by N/32 CTAs, 32 k-groups x 8 lanes x float4 each, exact fp32 FMAs, and the bias / activation /
+// residual epilogue of net/fullconnect.py:96-104 follows the in-CTA reduction.
+template <int MR, bool VEC>
+__global__ void __launch_bounds__(256) linear_skinny_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ b, float* __restrict__ y, int M, int K,
+                                                            int N, int act, float* __restrict__ pre,
+                                                            const float* __restrict__ residual) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float sk[];
+  float* sx = sk;                          // [MR][K]
+  float* red = sk + ((MR * K + 3) & ~3);   // [32 k-groups][MR][32 columns]
+  const int tid = threadIdx.x, cl = tid & 7, kg = tid >> 3;
+  const int n0 = blockIdx.x * 32 + cl * 4;
+  for (int e = tid; e < MR * K; e += 256) sx[e] = e < M * K ? x[e] : 0.f;
+  __syncthreads();
+  float acc[MR][4];
+#pragma unroll
+  for (int r = 0; r < MR; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+  if (n0 < N) {
+#pragma unroll 4
+    for (int k = kg; k < K; k += 32) {
+      float wv[4];
+      const float* wr = w + (long long)k * N + n0;
+      if (VEC) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(wr));
+        wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++) wv[c] = n0 + c < N ? __ldg(wr + c) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < MR; r++) {
+        const float xv = sx[r * K + k];
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[r][c] = fmaf(xv, wv[c], acc[r][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < MR; r++)
+    *reinterpret_cast<float4*>(red + (kg * MR + r) * 32 + cl * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  __syncthreads();
+  for (int e = tid; e < MR * 32; e += 256) {
+    const int r = e >> 5, c = e & 31, n = blockIdx.x * 32 + c;
+    if (r >= M || n >= N) continue;
+    float v = 0.f;
+#pragma unroll 8
+    for (int g = 0; g < 32; g++) v += red[(g * MR + r) * 32 + c];
+    if (b) v += b[n];
+    const long long o = (long long)r * N + n;
+    if (pre) pre[o] = v;
+    if (act == NT_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == NT_ACT_GELU) v = gelu_f(v);
+    if (residual) v += residual[o];
+    y[o] = v;
+  }
+}
+
+template <int MR>
+static int linear_skinny_launch(const float* x, const float* w, const float* b, float* y, int M, int K, int N, int act,
+                                float* pre, const float* residual) {
+  const size_t smem = sizeof(float) * ((((size_t)MR * K + 3) & ~(size_t)3) + 32 * MR * 32);
+  const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
+  auto kern = vec ? linear_skinny_kernel<MR, true> : linear_skinny_kernel<MR, false>;
+  static size_t configured[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > configured[vec]) {
+    NT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[vec] = smem;
+  }
+  NT_CHECK(launch_k(kern, dim3(ceil_div(N, 32)), dim3(256), smem, x, w, b, y, M, K, N, act, pre, residual));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+// M <= 8 and the row panel fits shared memory
+static bool linear_skinny_ok(int M, int K) {
+  if (const char* e = getenv("NTB200_SKINNY")) if (e[0] == '0') return false;
+  const int mr = M <= 1 ? 1 : (M <= 2 ? 2 : (M <= 4 ? 4 : 8));
+  return M >= 1 && M <= 8 && sizeof(float) * ((size_t)mr * K + 4 + 32 * mr * 32) <= 200 * 1024;
+}
+
 int gemm_dispatch(const GemmDesc& d) {
   if (g_gemm_mode != 0) {
     bool handled = false;
@@ -44,6 +127,12 @@ int nt_linear_fwd(const float* x, const float* w, const float* b, float* y, int 
   NT_ENTRY();
   NT_REQUIRE(M >= 0 && K > 0 && N > 0, "nt_linear_fwd: bad shape M=%d K=%d N=%d", M, K, N);
   NT_REQUIRE(act >= 0 && act <= 2, "nt_linear_fwd: act %d", act);
+  if (linear_skinny_ok(M, K)) {
+    if (M <= 1) return linear_skinny_launch<1>(x, w, b, y, M, K, N, act, pre, residual);
+    if (M <= 2) return linear_skinny_launch<2>(x, w, b, y, M, K, N, act, pre, residual);
+    if (M <= 4) return linear_skinny_launch<4>(x, w, b, y, M, K, N, act, pre, residual);
+    return linear_skinny_launch<8>(x, w, b, y, M, K, N, act, pre, residual);
+  }
   GemmDesc d{};
   d.A = x; d.B = w; d.C = y;
   d.M = M; d.N = N; d.K = K;

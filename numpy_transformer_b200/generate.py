@@ -10,25 +10,36 @@ full-window recomputation from there on — the same arithmetic the reference pe
 
 Layers are the drop-in objects of a GPT layer list (Position_Embedding, attdecoderblock_layer ..., layer_norm,
 classify_layer(relu=False)); parameters are shared with training, nothing is copied."""
+import ctypes
+
 import numpy as np
 
 from ._lib import lib
-from .device import DeviceArray
+from .device import DeviceArray, keep_allocations
 from . import ops
 
 
 class KVGenerator:
-    def __init__(self, layers):
+    """use_graph: the decode step reads its position from a device scalar, so after one eager step (sizes the pool,
+    loads modules) it is captured once into a CUDA graph and every later token is one graph launch; greedy
+    continuations (`generate(..., sample=None)`) also pick the next token on the device and replay without any host
+    round trip until the window is full."""
+
+    def __init__(self, layers, use_graph=True):
         self.layers = layers
         self.embed = layers[0]
         self.blocks = [l for l in layers if type(l).__name__ == "attdecoderblock_layer"]
         self.final_norm, self.head = layers[-2], layers[-1]
         assert type(self.embed).__name__ == "Position_Embedding" and self.blocks, "KVGenerator needs a GPT layer list"
-        assert not getattr(self.head, "reluact", False) or True
         self.context = self.embed.context_length
         self.D = self.embed.embed_dim
+        self.use_graph = use_graph
         self.len = 0
         self.k = self.v = None
+        self.graph = None
+        self.graph_kernels = 0
+        self._graph_buffers = None
+        self._eager_done = False
 
     # ------------------------------------------------------------------ full window (the reference's way)
     def full_logits(self, tokens):
@@ -44,8 +55,14 @@ class KVGenerator:
         tokens = np.asarray(tokens).astype(np.int64)
         B, T0 = tokens.shape
         assert T0 <= self.context
-        self.k = [DeviceArray.zeros((B, self.context, self.D)) for _ in self.blocks]
-        self.v = [DeviceArray.zeros((B, self.context, self.D)) for _ in self.blocks]
+        if self.k is None or self.k[0].shape[0] != B:
+            self.close()
+            self.k = [DeviceArray.zeros((B, self.context, self.D)) for _ in self.blocks]
+            self.v = [DeviceArray.zeros((B, self.context, self.D)) for _ in self.blocks]
+            self.d_pos = DeviceArray.zeros((1,), np.int32)                      # index of the token the next step consumes
+            self.d_tok = DeviceArray.zeros((B,), np.int32)                      # that token
+            self.d_hist = DeviceArray.zeros((B, self.context + 1), np.int32)    # greedy choices by position
+            self._logits = None
         x = DeviceArray.from_host(tokens)
         bi = 0
         for l in self.layers:
@@ -56,38 +73,92 @@ class KVGenerator:
             else:
                 x = l.forward(x)
         self.len = T0
+        self.d_pos.set(np.array([T0], np.int32))
         return np.asarray(x)[:, -1, :]
 
-    def step(self, token):
-        """Push one new token per sample ([B] ints) through the stack using the caches; returns its logits [B, V]."""
-        assert self.k is not None and self.len < self.context, "prefill first / window is full"
-        tok = np.asarray(token).astype(np.int64).reshape(-1, 1)
-        B, D, pos = tok.shape[0], self.D, self.len
-        idx = DeviceArray.from_host(tok)
+    def _enqueue_step(self):
+        """One decode step on the device: consumes d_tok at position *d_pos, leaves the logits in self._logits, the
+        greedy next token in d_tok / d_hist[:, *d_pos + 1], and advances d_pos."""
+        B, D = self.d_tok.shape[0], self.D
         x = DeviceArray((B, 1, D), host_dtype=self.embed.text_embedding.host_dtype)
-        lib.nt_embedding_fwd(idx.ptr, self.embed.text_embedding.params.ptr, self.embed.pos_embedding.params.ptr + 4 * pos * D,
-                             x.ptr, B, 1, D)                       # token row + position row `pos` (PatchEmbed.py:132-138)
+        lib.nt_decode_embed(self.d_tok.ptr, self.embed.text_embedding.params.ptr, self.embed.pos_embedding.params.ptr, x.ptr,
+                            B, D, self.context, self.d_pos.ptr)       # token row + position row (PatchEmbed.py:132-138)
         for bi, blk in enumerate(self.blocks):
             u = blk.norm._forward(x)
             hdn = blk.fc0._forward(u, ops.ACT_RELU)
             h = blk.fc1._forward(hdn, residual=x)
             u1 = blk.norm1._forward(h)
             qkv = blk.qkvfc._forward(u1)                           # [B,1,3D]
-            lib.nt_kv_append(qkv.ptr, self.k[bi].ptr, self.v[bi].ptr, B, 1, self.context, pos, D)
+            lib.nt_kv_append_at(qkv.ptr, self.k[bi].ptr, self.v[bi].ptr, B, self.context, D, self.d_pos.ptr)
             att = DeviceArray((B, 1, D), host_dtype=x.host_dtype)
-            lib.nt_attention_decode(qkv.ptr, self.k[bi].ptr, self.v[bi].ptr, att.ptr, B, self.context, pos + 1, blk.num_h,
-                                    D // blk.num_h)
+            lib.nt_attention_decode_at(qkv.ptr, self.k[bi].ptr, self.v[bi].ptr, att.ptr, B, self.context, blk.num_h,
+                                       D // blk.num_h, self.d_pos.ptr)
             x = blk.fc_out._forward(att, residual=h)
         z = self.final_norm._forward(x)
         logits = self.head.forward(z)
-        self.len = pos + 1
-        return np.asarray(logits).reshape(B, -1)
+        V = logits.size // B
+        lib.nt_argmax_next(logits.ptr, V, V, B, self.d_tok.ptr, self.d_hist.ptr, self.context + 1, self.d_pos.ptr)
+        lib.nt_increment(self.d_pos.ptr)
+        self._logits = logits
+
+    def _run_step(self):
+        """Eager the first time, captured the second, replayed afterwards (same protocol as TrainStep.run_device)."""
+        if not self.use_graph or not self._eager_done:
+            self._enqueue_step()
+            self._eager_done = True
+        elif self.graph is None:
+            lib.nt_sync()
+            with keep_allocations() as keep:
+                lib.nt_graph_begin()
+                try:
+                    self._enqueue_step()
+                finally:
+                    g = ctypes.c_void_p()
+                    nk = ctypes.c_int(0)
+                    lib.nt_graph_end(ctypes.byref(g), ctypes.byref(nk))
+            self._graph_buffers = keep.buffers
+            self.graph, self.graph_kernels = g, nk.value
+            lib.nt_graph_launch(self.graph)
+        else:
+            lib.nt_graph_launch(self.graph)
+        self.len += 1
+
+    def step(self, token):
+        """Push one new token per sample ([B] ints) through the stack using the caches; returns its logits [B, V]."""
+        assert self.k is not None and self.len < self.context, "prefill first / window is full"
+        self.d_tok.set(np.asarray(token).astype(np.int32).reshape(-1))
+        self._run_step()
+        return np.asarray(self._logits).reshape(self.d_tok.shape[0], -1)
+
+    def greedy_steps(self, first_token, n):
+        """n cached steps with the arg-max taken on the device (np.argmax tie-break): no host round trip between tokens.
+        `first_token` [B] is the token at position self.len; returns the n tokens that follow it, [B, n]."""
+        assert self.k is not None and self.len + n <= self.context, "prefill first / window too short for n cached steps"
+        p0 = self.len
+        self.d_tok.set(np.asarray(first_token).astype(np.int32).reshape(-1))
+        for _ in range(n):
+            self._run_step()
+        return self.d_hist.numpy()[:, p0 + 1:p0 + 1 + n].astype(np.int64)
+
+    def close(self):
+        """Destroy the captured graph (it pins the buffers of one batch size)."""
+        if self.graph is not None:
+            lib.nt_graph_destroy(self.graph)
+        self.graph = self._graph_buffers = None
+        self._eager_done = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def generate(self, prompt, n_new, sample=None):
         """Greedy (sample=None) or sampled (sample(probs [B,V]) -> [B] ints) continuation of prompt [B, T0]."""
         out = [list(map(int, row)) for row in np.asarray(prompt)]
         logits = self.prefill(np.asarray(prompt)[:, -self.context:])
-        for _ in range(n_new):
+        produced = 0
+        while produced < n_new:
             if sample is None:
                 nxt = np.argmax(logits, axis=-1)
             else:
@@ -95,7 +166,19 @@ class KVGenerator:
                 nxt = np.asarray(sample(e / e.sum(-1, keepdims=True)))
             for row, t in zip(out, nxt):
                 row.append(int(t))
-            if self.len < self.context:
+            produced += 1
+            if produced == n_new:
+                break
+            room = self.context - self.len
+            if room > 0 and sample is None:
+                # greedy: every remaining cached step in one go; the last one's logits decide the token after them
+                n = min(room, n_new - produced)
+                toks = self.greedy_steps(nxt, n)
+                for row, ts in zip(out, toks[:, :n - 1] if n > 1 else toks[:, :0]):
+                    row.extend(int(t) for t in ts)
+                produced += n - 1
+                logits = np.asarray(self._logits).reshape(len(out), -1)
+            elif room > 0:
                 logits = self.step(nxt)
             else:                                                  # window full: it slides, every position index changes
                 logits = self.full_logits(np.array([row[-self.context:] for row in out]))
