@@ -42,10 +42,11 @@ class fclayer(object):
     # --- extended forms used by the fused composite layers
     def _forward(self, x, act=ops.ACT_NONE, want_pre=False, residual=None, split_out=False):
         self.inputs = x
-        keep = []
+        keep, keep_w = [], []
         out = ops.linear_fwd(x, self.params, self.bias_params if self.bias else None, act, want_pre, residual, keep_xt=keep,
-                             split_out=split_out)
+                             split_out=split_out, keep_w=keep_w)
         self._xt = (x, keep[0]) if keep else None       # BF16x3 path: transposed split of x, made in the forward's pass
+        self._wsplit = keep_w[0] if keep_w else None    # BF16x3 path: split of the weights for dX (valid until update)
         return out
 
     def _backward(self, dy, x, act=ops.ACT_NONE, pre=None, addend=None, want_dx=True, split_out=False):
@@ -66,9 +67,10 @@ class fclayer(object):
         ops.linear_bwd_params(x, dy, self.params_delta, self.bias_delta, xt_split=xt, dyt_split=dyt)
         lib.nt_side_end()
         self._xt = None
+        w_split, self._wsplit = getattr(self, "_wsplit", None), None
         if not want_dx:
             return None
-        return ops.linear_bwd_input(dy, self.params, act, pre, addend, dy_split=dy_split, split_out=split_out)
+        return ops.linear_bwd_input(dy, self.params, act, pre, addend, dy_split=dy_split, split_out=split_out, w_split=w_split)
 
     # --- reference protocol
     def forward(self, inputs):
@@ -85,6 +87,7 @@ class fclayer(object):
             self.bias_delta.fill_zero()
 
     def update(self, lr=1e-10):
+        self._wsplit = None                              # the cached bf16 split describes the weights before this update
         if self.adam:
             ops.adam_star(self.params, self.params_delta, self.moment_p, self.rmsprop_p, lr, self.t)
             if self.bias:
@@ -133,6 +136,7 @@ class fclayer(object):
             full[:, :n] = w
             w = full
         self.params.set(w)
+        self._wsplit = None
         if self.bias:
             b = np.asarray(models[1]).reshape(n)
             if n != self.outfeature:

@@ -59,9 +59,11 @@ def _mn_major():
     return os.environ.get("NTB200_BF16X3_MN", "1") != "0"
 
 
-def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None, keep_xt=None, split_out=False):
+def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None, keep_xt=None, split_out=False, keep_w=None):
     """keep_xt: a list; on the BF16x3 path the split of x that the weight-gradient GEMM will need (the forward's own
-    operand when dW reads MN-major operands, else the transposed split made in the same pass) is appended to it."""
+    operand when dW reads MN-major operands, else the transposed split made in the same pass) is appended to it.
+    keep_w: a list; the UNtransposed split of w (the operand of the dX GEMM) is made in the same pass as the forward's
+    transposed one and appended, so the backward does not read w again."""
     K, N = w.shape
     assert x.shape[-1] == K, "linear_fwd: input feature %d != %d" % (x.shape[-1], K)
     M = x.size // K
@@ -75,7 +77,11 @@ def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None, keep_x
             xh, xl, _ = split_bf16(x, M, K)
             if keep_xt is not None:
                 keep_xt.append((xh, xl, 0))             # pitch 0 = untransposed
-        wh, wl, _ = split_bf16(w, K, N, transpose=True)            # w^T [N][K]
+        if keep_w is not None:
+            wu, (wh, wl, _) = split_bf16_both(w, K, N)             # w [K][N] for dX and w^T [N][K]: one pass over w
+            keep_w.append(wu)
+        else:
+            wh, wl, _ = split_bf16(w, K, N, transpose=True)        # w^T [N][K]
         yh = yl = None
         if split_out and want_split(M, N):
             yh, yl = new_planes(M * N)
@@ -87,13 +93,13 @@ def linear_fwd(x, w, b=None, act=ACT_NONE, want_pre=False, residual=None, keep_x
     return (y, pre) if want_pre else y
 
 
-def linear_bwd_input(dy, w, act=ACT_NONE, pre=None, addend=None, dy_split=None, split_out=False):
+def linear_bwd_input(dy, w, act=ACT_NONE, pre=None, addend=None, dy_split=None, split_out=False, w_split=None):
     K, N = w.shape
     M = dy.size // N
     dx = DeviceArray(dy.shape[:-1] + (K,), host_dtype=dy.host_dtype)
     if bf16x3_ok(M, N, K):
         dh, dl = dy_split if dy_split is not None else split_bf16(dy, M, N)[:2]
-        wh, wl, _ = split_bf16(w, K, N)                            # w [K][N]: contraction over N is contiguous
+        wh, wl = w_split if w_split is not None else split_bf16(w, K, N)[:2]   # w [K][N]: contraction over N is contiguous
         xh_ = xl_ = None
         if split_out and want_split(M, K):
             xh_, xl_ = new_planes(M * K)
