@@ -161,11 +161,13 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
 int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch,
                      int B, int N, int H, int dh, int mask_kind);
 /* BF16x3 kernels only (dh == 64, GEMM mode 1): out / dqkv additionally as bf16 hi / lo planes for the Linear that
- * consumes them (fc_out forward, qkvfc backward). */
+ * consumes them (fc_out forward, qkvfc backward; both may be NULL).  att_out (may be NULL): the forward's attention
+ * output [B,N,H*dh] WITHOUT a residual; when given, the softmax-backward row sums sum_j dP_ij P_ij are taken as
+ * dout_i . att_out_i (same quantity, attention.py:75) instead of a sweep over the key blocks. */
 int nt_attention_fwd_split(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S,
                            int B, int N, int H, int dh, const float* residual, void* out_hi, void* out_lo);
 int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch,
-                           int B, int N, int H, int dh, int mask_kind, void* dqkv_hi, void* dqkv_lo);
+                           int B, int N, int H, int dh, int mask_kind, void* dqkv_hi, void* dqkv_lo, const float* att_out);
 
 /* KV-cache decode.  The reference generates by re-running the whole window for every new token
  * (gpt/gpt_predict_poetrythree.py:108-121, gpt/gpt_train_potry3000.py:300-342); while the window is still growing the

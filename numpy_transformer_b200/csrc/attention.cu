@@ -10,7 +10,7 @@ bool attention_bf16_ok(int N, int H, int dh);
 int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S, int B, int N, int H,
                        const float* residual, void* o_hi, void* o_lo);
 int attention_bwd_bf16(const float* dout, const float* qkv, const float* P, float* dqkv, float* tsum, int B, int N, int H,
-                       int causal, void* g_hi, void* g_lo);
+                       int causal, void* g_hi, void* g_lo, const float* att_out);
 
 // p = softmax(x + mask) along rows; one warp per row. mask_kind as in ntb200.h; qi = row % N.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, float* __restrict__ p,
@@ -1245,7 +1245,7 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
   const int D = H * dh;
   // BF16x3 kernels (attention_bf16.cu): `scratch` only carries the B*H*N softmax-backward row sums
   if ((scratch || N <= 64) && nt::attention_bf16_ok(N, H, dh))
-    return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0, nullptr, nullptr);
+    return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0, nullptr, nullptr, nullptr);
   if (mma_ok(N, dh)) {
     if (dh == 24) {
       const size_t smem = bwd_mma_smem<24>();
@@ -1351,14 +1351,14 @@ int nt_attention_fwd_split(const float* qkv, const float* mask, int mask_kind, f
 }
 
 int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch, int B, int N,
-                           int H, int dh, int mask_kind, void* dqkv_hi, void* dqkv_lo) {
+                           int H, int dh, int mask_kind, void* dqkv_hi, void* dqkv_lo, const float* att_out) {
   NT_ENTRY();
   NT_REQUIRE(B >= 0 && N > 0 && H > 0 && dh > 0, "nt_attention_bwd_split: bad shape");
   NT_REQUIRE(nt::attention_bf16_ok(N, H, dh) && (scratch || N <= 64),
              "nt_attention_bwd_split: only the BF16x3 kernels (dh == 64, GEMM mode 1, scratch of B*H*N floats) emit split outputs");
   NT_REQUIRE((dqkv_hi != nullptr) == (dqkv_lo != nullptr), "nt_attention_bwd_split: pass both split planes or neither");
   if (B == 0) return 0;
-  return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0, dqkv_hi, dqkv_lo);
+  return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0, dqkv_hi, dqkv_lo, att_out);
 }
 
 int nt_kv_append(const float* qkv, float* kcache, float* vcache, int B, int T, int Tmax, int pos0, int D) {

@@ -108,7 +108,6 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const float* __restr
   extern __shared__ __align__(128) char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const SArr sQ = make_arr(smem, M::LD), sK = make_arr(smem + M::ARR, M::LD), sV = make_arr(smem + 2 * M::ARR, M::LD);
-  const SArr sPw = make_arr(smem + 3 * M::ARR + warp * M::PW, LDP, 16);
   const int bh = blockIdx.y, b = bh / H, h = bh % H;
   const int q0 = blockIdx.x * LQ, D = H * DH;
   const float* base = qkv + (long long)b * N * 3 * D + h * DH;
@@ -164,16 +163,12 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const float* __restr
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
       const int col = kc * LQ + nt * 8 + 2 * t;
-      const float p00 = __expf(s[nt][0] - m0) * inv0, p01 = __expf(s[nt][1] - m0) * inv0;
-      const float p10 = __expf(s[nt][2] - m1) * inv1, p11 = __expf(s[nt][3] - m1) * inv1;
-      st2(sPw, g, nt * 8 + 2 * t, p00, p01);
-      st2(sPw, g + 8, nt * 8 + 2 * t, p10, p11);
-      if (r0 < N) { if (col < N) Pb[(long long)r0 * N + col] = p00; if (col + 1 < N) Pb[(long long)r0 * N + col + 1] = p01; }   // atg__
-      if (r1 < N) { if (col < N) Pb[(long long)r1 * N + col] = p10; if (col + 1 < N) Pb[(long long)r1 * N + col + 1] = p11; }
+      s[nt][0] = __expf(s[nt][0] - m0) * inv0; s[nt][1] = __expf(s[nt][1] - m0) * inv0;
+      s[nt][2] = __expf(s[nt][2] - m1) * inv1; s[nt][3] = __expf(s[nt][3] - m1) * inv1;
+      if (r0 < N) { if (col < N) Pb[(long long)r0 * N + col] = s[nt][0]; if (col + 1 < N) Pb[(long long)r0 * N + col + 1] = s[nt][1]; }   // atg__
+      if (r1 < N) { if (col < N) Pb[(long long)r1 * N + col] = s[nt][2]; if (col + 1 < N) Pb[(long long)r1 * N + col + 1] = s[nt][3]; }
     }
-    __syncwarp();
-    gemm_rowk_kn<DH>(o, sPw, 0, sV, 0, 4, lane);
-    __syncwarp();
+    gemm_regA_kn<DH>(o, s, sV, 0, 4, lane);            // P feeds the MMA straight from its accumulator fragments
   }
   // causal: the skipped upper-triangular blocks of P are exactly zero
   if (nchunks < nall) {
@@ -218,16 +213,16 @@ __device__ __forceinline__ void dp_and_p(float (&dp)[8][4], float (&p)[8][4], co
 
 // backward, per query block: row sums t (-> tsum) and dQ
 template <int DH>
-__global__ void __launch_bounds__(128) attn_bwd_bf16_q_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
+__global__ void __launch_bounds__(128, 3) attn_bwd_bf16_q_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
                                                               const float* __restrict__ P, float* __restrict__ dqkv,
                                                               float* __restrict__ tsum, int N, int H, int causal,
-                                                              uint32_t* __restrict__ g_hi, uint32_t* __restrict__ g_lo) {
+                                                              uint32_t* __restrict__ g_hi, uint32_t* __restrict__ g_lo,
+                                                              const float* __restrict__ att_out) {
   pdl_prologue();
   using M = Smem<DH>;
   extern __shared__ __align__(128) char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const SArr sDO = make_arr(smem, M::LD), sK = make_arr(smem + M::ARR, M::LD), sV = make_arr(smem + 2 * M::ARR, M::LD);
-  const SArr sSw = make_arr(smem + 3 * M::ARR + warp * M::PW, LDP, 16);        // this warp's dS tile
   const int bh = blockIdx.y, b = bh / H, h = bh % H;
   const int q0 = blockIdx.x * LQ, D = H * DH;
   const float* base = qkv + (long long)b * N * 3 * D + h * DH;
@@ -237,18 +232,38 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_q_kernel(const float* __res
   const int i0 = warp * 16, r0 = q0 + i0 + g, r1 = r0 + 8;
   const float scale = rsqrtf((float)DH);
   load_split<DH>(sDO, dout + (long long)b * N * D + h * DH, D, q0, N, tid);
-  // pass 1: t_i = sum_j dP_ij P_ij
+  // pass 1: t_i = sum_j dP_ij P_ij.  With the forward's attention output O = P V at hand this is the row dot product
+  // dO_i . O_i (sum_j P_ij (dO_i . V_j) = dO_i . sum_j P_ij V_j), exact fp32 and no sweep over the key blocks.
   float t0 = 0.f, t1 = 0.f;
-  for (int kc = 0; kc < nchunks; kc++) {
-    __syncthreads();
-    load_split<DH>(sV, base + 2 * D, 3 * D, kc * LQ, N, tid);
-    __syncthreads();
-    float dp[8][4], p[8][4];
-    dp_and_p<DH>(dp, p, sDO, sV, i0, r0, r1, kc, N, Pb, lane, t);
+  if (att_out) {
+    const float* dob = dout + (long long)b * N * D + h * DH;
+    const float* aob = att_out + (long long)b * N * D + h * DH;
 #pragma unroll
-    for (int nt = 0; nt < 8; nt++) {
-      t0 += dp[nt][0] * p[nt][0] + dp[nt][1] * p[nt][1];
-      t1 += dp[nt][2] * p[nt][2] + dp[nt][3] * p[nt][3];
+    for (int nd = 0; nd < DH / 8; nd++) {
+      const int col = nd * 8 + 2 * t;
+      if (r0 < N) {
+        const float2 a = *reinterpret_cast<const float2*>(dob + (long long)r0 * D + col);
+        const float2 o = *reinterpret_cast<const float2*>(aob + (long long)r0 * D + col);
+        t0 = fmaf(a.x, o.x, fmaf(a.y, o.y, t0));
+      }
+      if (r1 < N) {
+        const float2 a = *reinterpret_cast<const float2*>(dob + (long long)r1 * D + col);
+        const float2 o = *reinterpret_cast<const float2*>(aob + (long long)r1 * D + col);
+        t1 = fmaf(a.x, o.x, fmaf(a.y, o.y, t1));
+      }
+    }
+  } else {
+    for (int kc = 0; kc < nchunks; kc++) {
+      __syncthreads();
+      load_split<DH>(sV, base + 2 * D, 3 * D, kc * LQ, N, tid);
+      __syncthreads();
+      float dp[8][4], p[8][4];
+      dp_and_p<DH>(dp, p, sDO, sV, i0, r0, r1, kc, N, Pb, lane, t);
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) {
+        t0 += dp[nt][0] * p[nt][0] + dp[nt][1] * p[nt][1];
+        t1 += dp[nt][2] * p[nt][2] + dp[nt][3] * p[nt][3];
+      }
     }
   }
   t0 = quad_sum(t0); t1 = quad_sum(t1);
@@ -269,12 +284,10 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_q_kernel(const float* __res
     dp_and_p<DH>(dp, p, sDO, sV, i0, r0, r1, kc, N, Pb, lane, t);
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
-      st2(sSw, g, nt * 8 + 2 * t, p[nt][0] * (dp[nt][0] - t0), p[nt][1] * (dp[nt][1] - t0));
-      st2(sSw, g + 8, nt * 8 + 2 * t, p[nt][2] * (dp[nt][2] - t1), p[nt][3] * (dp[nt][3] - t1));
+      dp[nt][0] = p[nt][0] * (dp[nt][0] - t0); dp[nt][1] = p[nt][1] * (dp[nt][1] - t0);
+      dp[nt][2] = p[nt][2] * (dp[nt][2] - t1); dp[nt][3] = p[nt][3] * (dp[nt][3] - t1);
     }
-    __syncwarp();
-    gemm_rowk_kn<DH>(dq, sSw, 0, sK, 0, 4, lane);                              // dQ = dS K    attention.py:78
-    __syncwarp();
+    gemm_regA_kn<DH>(dq, dp, sK, 0, 4, lane);                                  // dQ = dS K    attention.py:78
   }
   float* ob = dqkv + (long long)b * N * 3 * D + h * DH;
 #pragma unroll
@@ -363,7 +376,6 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_small_kernel(const float* _
   extern __shared__ __align__(128) char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const SArr sQ = make_arr(smem, M::LD), sK = make_arr(smem + M::ARR, M::LD), sV = make_arr(smem + 2 * M::ARR, M::LD);
-  const SArr sPw = make_arr(smem + 3 * M::ARR + warp * M::PW, LDP, 16);
   const int bh = blockIdx.x, b = bh / H, h = bh % H, D = H * DH;
   const float* base = qkv + (long long)b * N * 3 * D + h * DH;
   load_split<DH>(sQ, base, 3 * D, 0, N, tid);
@@ -394,17 +406,14 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_small_kernel(const float* _
 #pragma unroll
   for (int nt = 0; nt < 8; nt++) {
     const int col = nt * 8 + 2 * t;
-    const float p00 = s[nt][0] * inv0, p01 = s[nt][1] * inv0, p10 = s[nt][2] * inv1, p11 = s[nt][3] * inv1;
-    st2(sPw, g, col, p00, p01);
-    st2(sPw, g + 8, col, p10, p11);
-    if (r0 < N) { if (col < N) Pb[r0 * N + col] = p00; if (col + 1 < N) Pb[r0 * N + col + 1] = p01; }      // atg__
-    if (r1 < N) { if (col < N) Pb[r1 * N + col] = p10; if (col + 1 < N) Pb[r1 * N + col + 1] = p11; }
+    s[nt][0] *= inv0; s[nt][1] *= inv0; s[nt][2] *= inv1; s[nt][3] *= inv1;
+    if (r0 < N) { if (col < N) Pb[r0 * N + col] = s[nt][0]; if (col + 1 < N) Pb[r0 * N + col + 1] = s[nt][1]; }      // atg__
+    if (r1 < N) { if (col < N) Pb[r1 * N + col] = s[nt][2]; if (col + 1 < N) Pb[r1 * N + col + 1] = s[nt][3]; }
   }
-  __syncwarp();
   float o[DH / 8][4];
 #pragma unroll
   for (int nd = 0; nd < DH / 8; nd++) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
-  gemm_rowk_kn<DH>(o, sPw, 0, sV, 0, 4, lane);
+  gemm_regA_kn<DH>(o, s, sV, 0, 4, lane);              // P feeds the MMA straight from its accumulator fragments
 #pragma unroll
   for (int nd = 0; nd < DH / 8; nd++) {
     const int col = h * DH + nd * 8 + 2 * t;
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_small_kernel(const float* _
 }
 
 template <int DH>
-__global__ void __launch_bounds__(128) attn_bwd_bf16_small_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
+__global__ void __launch_bounds__(128, 3) attn_bwd_bf16_small_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
                                                                   const float* __restrict__ P, float* __restrict__ dqkv, int N,
                                                                   int H, uint32_t* __restrict__ g_hi, uint32_t* __restrict__ g_lo) {
   pdl_prologue();
@@ -432,7 +441,8 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_small_kernel(const float* _
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const SArr sQ = make_arr(smem, M::LD), sK = make_arr(smem + M::ARR, M::LD), sV = make_arr(smem + 2 * M::ARR, M::LD);
   const SArr sDO = make_arr(smem + 3 * M::ARR, M::LD);
-  const SArr sP = make_arr(smem + 4 * M::ARR, LDP), sdS = make_arr(smem + 4 * M::ARR + M::PARR, LDP);
+  static_assert(M::PARR <= M::ARR, "P / dS reuse the K / V buffers");
+  const SArr sP = make_arr(smem + M::ARR, LDP), sdS = make_arr(smem + 2 * M::ARR, LDP);     // alias sK / sV (phase 2 only)
   const int bh = blockIdx.x, b = bh / H, h = bh % H, D = H * DH;
   const float* base = qkv + (long long)b * N * 3 * D + h * DH;
   const float* Pb = P + (long long)bh * N * N;
@@ -457,22 +467,28 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_small_kernel(const float* _
     t0 = quad_sum(t0); t1 = quad_sum(t1);
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
-      const int c = nt * 8 + 2 * t;
-      st2(sP, r0, c, p[nt][0], p[nt][1]);
-      st2(sP, r1, c, p[nt][2], p[nt][3]);
-      st2(sdS, r0, c, p[nt][0] * (dp[nt][0] - t0), p[nt][1] * (dp[nt][1] - t0));
-      st2(sdS, r1, c, p[nt][2] * (dp[nt][2] - t1), p[nt][3] * (dp[nt][3] - t1));
+      dp[nt][0] = p[nt][0] * (dp[nt][0] - t0); dp[nt][1] = p[nt][1] * (dp[nt][1] - t0);
+      dp[nt][2] = p[nt][2] * (dp[nt][2] - t1); dp[nt][3] = p[nt][3] * (dp[nt][3] - t1);
     }
-    __syncwarp();
     float dq[DH / 8][4];
 #pragma unroll
     for (int nd = 0; nd < DH / 8; nd++) dq[nd][0] = dq[nd][1] = dq[nd][2] = dq[nd][3] = 0.f;
-    gemm_rowk_kn<DH>(dq, sdS, i0, sK, 0, 4, lane);
+    gemm_regA_kn<DH>(dq, dp, sK, 0, 4, lane);            // dS feeds the MMA straight from its accumulator fragments
 #pragma unroll
     for (int nd = 0; nd < DH / 8; nd++) {
       const int col = nd * 8 + 2 * t;
       if (r0 < N) store_g(ob, g_hi, g_lo, dqkv, (long long)r0 * 3 * D + col, dq[nd][0] * scale, dq[nd][1] * scale);
       if (r1 < N) store_g(ob, g_hi, g_lo, dqkv, (long long)r1 * 3 * D + col, dq[nd][2] * scale, dq[nd][3] * scale);
+    }
+    // K and V are dead from here on: P and dS (needed TRANSPOSED by phase 2) take their place in shared memory
+    __syncthreads();
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      const int c = nt * 8 + 2 * t;
+      st2(sP, r0, c, p[nt][0], p[nt][1]);
+      st2(sP, r1, c, p[nt][2], p[nt][3]);
+      st2(sdS, r0, c, dp[nt][0], dp[nt][1]);
+      st2(sdS, r1, c, dp[nt][2], dp[nt][3]);
     }
   }
   __syncthreads();
@@ -499,10 +515,10 @@ __global__ void __launch_bounds__(128) attn_bwd_bf16_small_kernel(const float* _
   }
 }
 
-template <int DH> static size_t fwd_smem() { return 3 * (size_t)Smem<DH>::ARR + 4 * (size_t)Smem<DH>::PW; }
-template <int DH> static size_t bwdq_smem() { return 3 * (size_t)Smem<DH>::ARR + 4 * (size_t)Smem<DH>::PW; }
+template <int DH> static size_t fwd_smem() { return 3 * (size_t)Smem<DH>::ARR; }
+template <int DH> static size_t bwdq_smem() { return 3 * (size_t)Smem<DH>::ARR; }
 template <int DH> static size_t bwdk_smem() { return 3 * (size_t)Smem<DH>::ARR + 2 * (size_t)Smem<DH>::PARR; }
-template <int DH> static size_t bwds_smem() { return 4 * (size_t)Smem<DH>::ARR + 2 * (size_t)Smem<DH>::PARR; }
+template <int DH> static size_t bwds_smem() { return 4 * (size_t)Smem<DH>::ARR; }
 
 }  // namespace ab
 
@@ -543,7 +559,7 @@ int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float
 }
 
 int attention_bwd_bf16(const float* dout, const float* qkv, const float* P, float* dqkv, float* tsum, int B, int N, int H,
-                       int causal, void* g_hi, void* g_lo) {
+                       int causal, void* g_hi, void* g_lo, const float* att_out) {
   using namespace ab;
   if (N <= LQ) {
     NT_CHECK(launch_k(attn_bwd_bf16_small_kernel<64>, dim3(B * H), dim3(128), bwds_smem<64>(), dout, qkv, P, dqkv, N, H, (uint32_t*)g_hi, (uint32_t*)g_lo));
@@ -551,7 +567,7 @@ int attention_bwd_bf16(const float* dout, const float* qkv, const float* P, floa
     return 0;
   }
   NT_CHECK(launch_k(attn_bwd_bf16_q_kernel<64>, dim3(ceil_div(N, LQ), B * H), dim3(128), bwdq_smem<64>(), dout, qkv, P, dqkv, tsum,
-                    N, H, causal, (uint32_t*)g_hi, (uint32_t*)g_lo));
+                    N, H, causal, (uint32_t*)g_hi, (uint32_t*)g_lo, att_out));
   NT_LAUNCH_OK();
   NT_CHECK(launch_k(attn_bwd_bf16_k_kernel<64>, dim3(ceil_div(N, LQ), B * H), dim3(128), bwdk_smem<64>(), dout, qkv, P, dqkv,
                     (const float*)tsum, N, H, causal, (uint32_t*)g_hi, (uint32_t*)g_lo));

@@ -310,6 +310,35 @@ __device__ __forceinline__ void gemm_rowk_kn(float (&o)[DH / 8][4], const SArr& 
     for (int c = 0; c < 4; c++) o[nd][c] += os[nd][c];
 }
 
+// o[nd] += P * B with P (16 rows x 16*ksteps k) still in the accumulator-fragment layout of the MMA that produced it:
+// the C fragments of two adjacent n8 tiles ARE the A fragment of one k16 step (rows g / g+8, columns 2t.. and 2t+8..),
+// so the probabilities never travel through shared memory.  Same split (hi, lo) values as st2 + ldmatrix would give.
+template <int DH>
+__device__ __forceinline__ void gemm_regA_kn(float (&o)[DH / 8][4], const float (&p)[8][4], const SArr& B, int ncol,
+                                             int ksteps, int lane) {
+  constexpr int NDT = DH / 8;
+  const uint32_t b_lane = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + (ncol + (lane >> 4) * 8) * 2;
+  const uint32_t b_lane2 = B.addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * B.ldb + ncol * 2;
+  float os[NDT][4];
+#pragma unroll
+  for (int nd = 0; nd < NDT; nd++) os[nd][0] = os[nd][1] = os[nd][2] = os[nd][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; kk++)
+    if (kk < ksteps) {
+      uint32_t ah[4], al[4], bh[NDT][2], bl[NDT][2];
+      split2(p[2 * kk][0], p[2 * kk][1], ah[0], al[0]);
+      split2(p[2 * kk][2], p[2 * kk][3], ah[1], al[1]);
+      split2(p[2 * kk + 1][0], p[2 * kk + 1][1], ah[2], al[2]);
+      split2(p[2 * kk + 1][2], p[2 * kk + 1][3], ah[3], al[3]);
+      load_b_kn<NDT>(bh, bl, B, b_lane, b_lane2, kk);
+      mma_passes<NDT>(o, os, ah, al, bh, bl);
+    }
+#pragma unroll
+  for (int nd = 0; nd < NDT; nd++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) o[nd][c] += os[nd][c];
+}
+
 // o[nd] += A^T(16 output rows = columns m0.. of SA, k = rows of SA) * B ("kn"): both stored [k][*]
 template <int DH>
 __device__ __forceinline__ void gemm_colk_kn(float (&o)[DH / 8][4], const SArr& A, int m0, const SArr& B, int ncol,

@@ -51,7 +51,8 @@ class attdecoderblock_layer():
     def backward(self, delta):
         delta = as_device(delta, self.norm.host_dtype)
         delta0 = self.fc_out._backward(delta, self.rkk)
-        self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h, self._mask_kind, split_out=True)
+        self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h, self._mask_kind, split_out=True,
+                                           att_out=self.rkk)
         d = self.qkvfc._backward(self.delta_qkv, self.outnorm)
         qkvdelta = self.norm1._backward(d, addend=delta, split_out=True)               # + delta (attdecoderblock.py:105)
         d = self.fc1._backward(qkvdelta, self.out2, ops.ACT_RELU, self.pre2, split_out=True)   # fc1.backward + relu.backward

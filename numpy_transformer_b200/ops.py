@@ -185,17 +185,22 @@ def attention_fwd(qkv, H, mask=None, mask_kind=MASK_NONE, residual=None, want_sc
     return out, P, S
 
 
-def attention_bwd(dout, qkv, P, H, mask_kind=MASK_NONE, split_out=False):
+def attention_bwd(dout, qkv, P, H, mask_kind=MASK_NONE, split_out=False, att_out=None):
+    """att_out: the forward's attention output without a residual (lets the long-sequence BF16x3 kernel take the
+    softmax-backward row sums as dout . att_out instead of a sweep over the key blocks)."""
     B, N, three_d = qkv.shape
     D = three_d // 3
     dh = D // H
     dqkv = qkv.empty_like()
     if _att_bf16(N, dh):
         scratch = DeviceArray((B * H * N,))             # BF16x3 kernels: row sums of dP o P only
+        gh = gl = None
         if split_out and want_split(B * N, 3 * D):
             gh, gl = new_planes(B * N * 3 * D)
             dqkv._split = (gh, gl)
-            lib.nt_attention_bwd_split(dout.ptr, qkv.ptr, P.ptr, dqkv.ptr, scratch.ptr, B, N, H, dh, int(mask_kind), gh.ptr, gl.ptr)
+        if gh is not None or att_out is not None:
+            lib.nt_attention_bwd_split(dout.ptr, qkv.ptr, P.ptr, dqkv.ptr, scratch.ptr, B, N, H, dh, int(mask_kind),
+                                       ptr_or_null(gh), ptr_or_null(gl), ptr_or_null(att_out))
             return dqkv
     else:
         scratch = None if (N <= 64 and dh <= 64 and dh % 4 == 0) else P.empty_like()

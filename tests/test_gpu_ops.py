@@ -236,7 +236,11 @@ def test_attention_core_vs_oracle(nt, B, N, H, dh, causal):
     out, dP, dS = ops.attention_fwd(dq, H, None, ops.MASK_CAUSAL if causal else ops.MASK_NONE, want_scores=True)
     assert rel_err(out, O) < TOL and rel_err(dP, P) < TOL and rel_err(dS, S) < TOL
     dqkv = ops.attention_bwd(DeviceArray.from_host(dout), dq, dP, H, ops.MASK_CAUSAL if causal else ops.MASK_NONE)
-    assert rel_err(dqkv, R.attention_bwd(dout, qkv, P, H)) < TOL
+    ref_dqkv = R.attention_bwd(dout, qkv, P, H)
+    assert rel_err(dqkv, ref_dqkv) < TOL
+    # with the forward's output at hand the softmax-backward row sums are dout . out (BF16x3 long-sequence kernels)
+    dqkv2 = ops.attention_bwd(DeviceArray.from_host(dout), dq, dP, H, ops.MASK_CAUSAL if causal else ops.MASK_NONE, att_out=out)
+    assert rel_err(dqkv2, ref_dqkv) < TOL
     if causal:
         out2, P2, _ = ops.attention_fwd(dq, H, DeviceArray.from_host(M.causal_mask(N, -1e6)), ops.MASK_DENSE)
         assert rel_err(out2, O) < TOL
