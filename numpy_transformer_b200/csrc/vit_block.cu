@@ -243,7 +243,7 @@ struct Cfg {
   static constexpr int SV_BYTES = SV_STAT + 4 * ROWS * (int)sizeof(float);
   static constexpr int XLD = D + 8;                     // pitch (floats) of the fp32 residual / LN-input buffers
   static constexpr int XARR = ROWS * XLD * 4;
-  static constexpr size_t FWD_SMEM = 4 * (size_t)ARR + 8 * (size_t)PW + 4 * ROWS * sizeof(float) + XARR;
+  static constexpr size_t FWD_SMEM = 4 * (size_t)ARR + 4 * ROWS * sizeof(float) + XARR;
   static constexpr size_t BWD_SMEM = 4 * (size_t)ARR + 4 * (size_t)PARR + 4 * ROWS * sizeof(float) + 16 + XARR + 8 * 3 * D * sizeof(float);
   static_assert(D % 32 == 0 && DH % 8 == 0 && DH * H == D, "fused ViT block: D % 32 == 0, dh % 8 == 0");
   static_assert(ARR2 <= 2 * ARR && ARR2 <= 4 * PARR && ARR <= 4 * PARR, "aliasing plan");
@@ -303,15 +303,14 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
   const SArr sK = make_arr(smem + 2 * C::ARR, C::LD);
   const SArr sV = make_arr(smem + 3 * C::ARR, C::LD);
   const SArr sG = make_arr(smem + C::ARR, C::LD2);                       // aliases sQ|sK after attention
-  const SArr sPw = make_arr(smem + 4 * C::ARR + warp * C::PW, LDP, 16);  // this warp's P tile
-  float* s_stat = reinterpret_cast<float*>(smem + 4 * C::ARR + 8 * C::PW);   // mean, rstd (LN) | mean, rstd (LN1)
+  float* s_stat = reinterpret_cast<float*>(smem + 4 * C::ARR);   // mean, rstd (LN) | mean, rstd (LN1)
   // token contractions always run over the 64 padded rows / keys (pad rows are exact zeros, padded keys are masked):
   // compile-time trip counts let the compiler software-pipeline the fragment loads
   constexpr int NPAIR = ROWS / 16, KT = ROWS / 16;
   const float scale = rsqrtf((float)DH);
   const size_t img = (size_t)b * N * D;
   // fp32 residual stream of this image: x -> h -> out in place (every element is updated by the thread that read it)
-  float* sX = reinterpret_cast<float*>(smem + 4 * C::ARR + 8 * C::PW + 4 * ROWS * sizeof(float));
+  float* sX = reinterpret_cast<float*>(smem + 4 * C::ARR + 4 * ROWS * sizeof(float));
   for (int e = tid; e < ROWS * (D / 4); e += 256) {
     const int r = e / (D / 4), c4 = (e - r * (D / 4)) * 4;
     *reinterpret_cast<float4*>(sX + r * C::XLD + c4) =
@@ -398,17 +397,14 @@ __global__ void __launch_bounds__(256, 1) vit_fwd_kernel(Args a) {
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
         const int col = nt * 8 + 2 * t;
-        const float p00 = s[nt][0] * inv0, p01 = s[nt][1] * inv0, p10 = s[nt][2] * inv1, p11 = s[nt][3] * inv1;
-        st2(sPw, g, col, p00, p01);
-        st2(sPw, g + 8, col, p10, p11);
-        if (r0 < N) { if (col < N) pg[r0 * N + col] = p00; if (col + 1 < N) pg[r0 * N + col + 1] = p01; }   // atg__
-        if (r1 < N) { if (col < N) pg[r1 * N + col] = p10; if (col + 1 < N) pg[r1 * N + col + 1] = p11; }
+        s[nt][0] *= inv0; s[nt][1] *= inv0; s[nt][2] *= inv1; s[nt][3] *= inv1;
+        if (r0 < N) { if (col < N) pg[r0 * N + col] = s[nt][0]; if (col + 1 < N) pg[r0 * N + col + 1] = s[nt][1]; }   // atg__
+        if (r1 < N) { if (col < N) pg[r1 * N + col] = s[nt][2]; if (col + 1 < N) pg[r1 * N + col + 1] = s[nt][3]; }
       }
-      __syncwarp();
       float o[DH / 8][4];
 #pragma unroll
       for (int nd = 0; nd < DH / 8; nd++) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
-      gemm_rowk_kn<DH>(o, sPw, 0, sV, hd * DH, KT, lane);
+      gemm_regA_kn<DH>(o, s, sV, hd * DH, KT, lane);     // P feeds the MMA straight from its accumulator fragments
       float* hg = P.h + img;
       float2 xr0[DH / 8], xr1[DH / 8];
 #pragma unroll
@@ -712,11 +708,12 @@ __global__ void __launch_bounds__(256, 1) vit_bwd_kernel(Args a) {
           const int col = nt * 8 + 2 * t;
           st2(sP, r0, col, p[nt][0], p[nt][1]);
           st2(sP, r1, col, p[nt][2], p[nt][3]);
-          st2(sdS, r0, col, p[nt][0] * (s[nt][0] - t0), p[nt][1] * (s[nt][1] - t0));
-          st2(sdS, r1, col, p[nt][2] * (s[nt][2] - t1), p[nt][3] * (s[nt][3] - t1));
+          s[nt][0] = p[nt][0] * (s[nt][0] - t0); s[nt][1] = p[nt][1] * (s[nt][1] - t0);
+          s[nt][2] = p[nt][2] * (s[nt][2] - t1); s[nt][3] = p[nt][3] * (s[nt][3] - t1);
+          st2(sdS, r0, col, s[nt][0], s[nt][1]);          // phase 2 needs dS transposed: through shared memory
+          st2(sdS, r1, col, s[nt][2], s[nt][3]);
         }
-        __syncwarp();
-        gemm_rowk_kn<DH>(dq, sdS, i0, sK, hd * DH, KT, lane);
+        gemm_regA_kn<DH>(dq, s, sK, hd * DH, KT, lane);   // dQ takes dS straight from the accumulator fragments
       } else if (head_ok) {
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
