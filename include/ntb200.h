@@ -138,6 +138,12 @@ int nt_relu_bwd(const float* dy, const float* x_pre, float* dx, size_t n); /* :1
 int nt_softmax_fwd(const float* x, float* p, int rows, int cols);          /* :76-84, axis=-1 */
 int nt_softmax_bwd(const float* dp, const float* p, float* dx, int rows, int cols); /* :86-129 closed form */
 int nt_add(const float* a, const float* b, float* out, size_t n);          /* residual adds */
+int nt_sigmoid_fwd(const float* x, float* y, size_t n);                    /* :27-30  */
+int nt_sigmoid_bwd(const float* dy, const float* y, float* dx, size_t n);  /* :32-33, y = forward output */
+int nt_tanh_fwd(const float* x, float* y, size_t n);                       /* :43-47  */
+int nt_tanh_bwd(const float* dy, const float* y, float* dx, size_t n);     /* :49-50, y = forward output */
+int nt_silu_fwd(const float* x, float* y, size_t n);                       /* :59-63  */
+int nt_silu_bwd(const float* dy, const float* x, float* dx, size_t n);     /* :65-67, x = forward input */
 int nt_add_rows(const float* x, const float* table, float* out, int rows, int period, int D); /* Position_add.py:20-23 */
 int nt_scale(float* x, float alpha, size_t n);
 
@@ -266,6 +272,14 @@ int nt_vit_head(const NtVitEnds* e, int B, int N, int D, int D0, int C1, float n
 /* ---------------------------------------------------------------- embeds */
 /* PatchEmbed_flatten.forward patch loops, PatchEmbed.py:22-36: (B,C,Hi,Wi) -> (B, n_patch^2, C*h*w) */
 int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, int n_patch);
+
+/* convolution_layer (net/Convolution.py:37-248) = im2col + the Linear entry points above.
+ * nt_im2col: col[(n, oh, ow)][(c, kh, kw)] of the zero-padded input (:66-84, :114-119); OH = (H + 2 PH - KH) / SH + 1.
+ * nt_col2im: its adjoint, dx[N,C,H,W] from dcol (the input gradient of :196-223), written (not accumulated).
+ * nt_transpose_last2: y[b][c][r] = x[b][r][c] (NHWC <-> NCHW, kernel tensor <-> Linear weight). */
+int nt_im2col(const float* x, float* col, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW);
+int nt_col2im(const float* dcol, float* dx, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW);
+int nt_transpose_last2(const float* x, float* y, int batch, int rows, int cols);
 /* Position_Embedding.forward, PatchEmbed.py:132-138 + Embedding_layer.forward net/Embedding.py:50-55:
  * out[b,t,:] = etok[idx[b,t],:] + epos[t,:]  (epos may be NULL). */
 int nt_embedding_fwd(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int T, int D);
@@ -286,6 +300,12 @@ int nt_cross_entropy(const float* logits, const int32_t* labels, const float* on
 /* ---------------------------------------------------------------- optimiser */
 /* fclayer.update SGD branch + setzero, net/fullconnect.py:150-153,129-132: p -= lr*g ; g = 0 if zero_grad.
  * lr_dev (device float*, may be NULL) overrides lr so a captured graph can follow a schedule. */
+/* net/loss.py:53-57 binary_cross_entropy_logit_loss: loss = -mean(y log(s + 1e-10) + (1 - y) log(1 - s + 1e-10)),
+ * grad = (s - y) / n, sigmoid = s (grad / sigmoid may be NULL);  net/loss.py:68-71 mean_square_loss: loss = mean((p - y)^2),
+ * grad = 2 (p - y) / n.  n = number of elements. */
+int nt_bce_logit_loss(const float* logits, const float* label, float* loss, float* grad, float* sigmoid, size_t n);
+int nt_mse_loss(const float* predict, const float* label, float* loss, float* grad, size_t n);
+
 int nt_sgd(float* p, float* g, size_t n, float lr, const float* lr_dev, int zero_grad);
 /* fclayer.update Adam branch, net/fullconnect.py:137-149 (sqrt on both bias corrections, eps 1e-8
  * outside the sqrt).  t_dev (device int*, may be NULL) overrides t. */

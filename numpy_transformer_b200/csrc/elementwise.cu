@@ -3,7 +3,8 @@
 
 namespace nt {
 
-enum { OP_GELU_F, OP_GELU_B, OP_RELU_F, OP_RELU_B, OP_ADD, OP_SCALE };
+enum { OP_GELU_F, OP_GELU_B, OP_RELU_F, OP_RELU_B, OP_ADD, OP_SCALE, OP_SIGMOID_F, OP_SIGMOID_B, OP_TANH_F, OP_TANH_B,
+       OP_SILU_F, OP_SILU_B };
 
 template <int OP>
 __global__ void __launch_bounds__(256) ew_kernel(const float* __restrict__ a, const float* __restrict__ b,
@@ -19,6 +20,15 @@ __global__ void __launch_bounds__(256) ew_kernel(const float* __restrict__ a, co
     if (OP == OP_RELU_F) return x < 0.f ? 0.f : x;
     if (OP == OP_RELU_B) return y > 0.f ? x : 0.f;           // a = dy, b = pre
     if (OP == OP_ADD) return x + y;
+    if (OP == OP_SIGMOID_F) return 1.0f / (1.0f + expf(-x));                 // net/activation.py:27-30
+    if (OP == OP_SIGMOID_B) return y * (1.0f - y) * x;                        // :32-33   a = dy, b = y
+    if (OP == OP_TANH_F) return tanhf(x);                                     // :43-47
+    if (OP == OP_TANH_B) return (1.0f - y * y) * x;                           // :49-50   a = dy, b = y
+    if (OP == OP_SILU_F) return x / (1.0f + expf(-x));                        // :59-63
+    if (OP == OP_SILU_B) {                                                    // :65-67   a = dy, b = x
+      const float d = 1.0f / (1.0f + expf(-y));                               // (div + out * e^-x * div) = d (1 + x (1 - d))
+      return d * (1.0f + y * (1.0f - d)) * x;
+    }
     return x * alpha;
   };
   if (al) {
@@ -72,6 +82,72 @@ __global__ void patchify_kernel(const float* __restrict__ img, float* __restrict
     int pi = r % P; r /= P;
     int b = (int)r;
     out[i] = img[(((long long)b * C + c) * Hi + pi * hl + h) * Wi + pj * wl + w];
+  }
+}
+
+// ---- convolution as im2col + Linear (net/Convolution.py:66-84, 104-131, 163-225)
+struct ConvGeom { int N, C, H, W, KH, KW, SH, SW, PH, PW, OH, OW; };
+
+// col[(n, oh, ow)][(c, kh, kw)] = x[n, c, oh*SH + kh - PH, ow*SW + kw - PW] (zero outside the image)
+__global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, ConvGeom g) {
+  pdl_prologue();
+  const long long K = (long long)g.C * g.KH * g.KW, total = (long long)g.N * g.OH * g.OW * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int kw = r % g.KW; r /= g.KW;
+    const int kh = r % g.KH; r /= g.KH;
+    const int c = r % g.C; r /= g.C;
+    const int ow = r % g.OW; r /= g.OW;
+    const int oh = r % g.OH; r /= g.OH;
+    const int n = (int)r;
+    const int h = oh * g.SH + kh - g.PH, w = ow * g.SW + kw - g.PW;
+    col[i] = (h >= 0 && h < g.H && w >= 0 && w < g.W) ? x[(((long long)n * g.C + c) * g.H + h) * g.W + w] : 0.f;
+  }
+}
+
+// dx[n, c, h, w] = sum of dcol over every window position that covers the pixel: a gather, so no atomics and a
+// deterministic summation order (the reference's rotated-kernel full convolution, Convolution.py:196-223)
+__global__ void col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx, ConvGeom g) {
+  pdl_prologue();
+  const long long K = (long long)g.C * g.KH * g.KW, total = (long long)g.N * g.C * g.H * g.W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int w = r % g.W; r /= g.W;
+    const int h = r % g.H; r /= g.H;
+    const int c = r % g.C; r /= g.C;
+    const int n = (int)r;
+    float acc = 0.f;
+    for (int kh = 0; kh < g.KH; kh++) {
+      const int hn = h + g.PH - kh;
+      if (hn < 0 || hn % g.SH) continue;
+      const int oh = hn / g.SH;
+      if (oh >= g.OH) continue;
+      for (int kw = 0; kw < g.KW; kw++) {
+        const int wn = w + g.PW - kw;
+        if (wn < 0 || wn % g.SW) continue;
+        const int ow = wn / g.SW;
+        if (ow >= g.OW) continue;
+        acc += dcol[(((long long)n * g.OH + oh) * g.OW + ow) * K + ((long long)c * g.KH + kh) * g.KW + kw];
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+// y[b][c][r] = x[b][r][c]: NHWC <-> NCHW and the (OC, C*KH*KW) <-> (C*KH*KW, OC) views of the kernel tensor
+__global__ void transpose_last2_kernel(const float* __restrict__ x, float* __restrict__ y, int rows, int cols) {
+  pdl_prologue();
+  __shared__ float tile[32][33];
+  const long long base = (long long)blockIdx.z * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = x[base + (long long)r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) y[base + (long long)c * rows + r] = tile[threadIdx.x][j];
   }
 }
 
@@ -206,6 +282,12 @@ int nt_gelu_bwd(const float* dy, const float* x, float* dx, size_t n) { NT_ENTRY
 int nt_relu_fwd(const float* x, float* y, size_t n) { NT_ENTRY(); return launch_ew<OP_RELU_F>(x, nullptr, y, n); }
 int nt_relu_bwd(const float* dy, const float* pre, float* dx, size_t n) { NT_ENTRY(); return launch_ew<OP_RELU_B>(dy, pre, dx, n); }
 int nt_add(const float* a, const float* b, float* out, size_t n) { NT_ENTRY(); return launch_ew<OP_ADD>(a, b, out, n); }
+int nt_sigmoid_fwd(const float* x, float* y, size_t n) { NT_ENTRY(); return launch_ew<OP_SIGMOID_F>(x, nullptr, y, n); }
+int nt_sigmoid_bwd(const float* dy, const float* y, float* dx, size_t n) { NT_ENTRY(); return launch_ew<OP_SIGMOID_B>(dy, y, dx, n); }
+int nt_tanh_fwd(const float* x, float* y, size_t n) { NT_ENTRY(); return launch_ew<OP_TANH_F>(x, nullptr, y, n); }
+int nt_tanh_bwd(const float* dy, const float* y, float* dx, size_t n) { NT_ENTRY(); return launch_ew<OP_TANH_B>(dy, y, dx, n); }
+int nt_silu_fwd(const float* x, float* y, size_t n) { NT_ENTRY(); return launch_ew<OP_SILU_F>(x, nullptr, y, n); }
+int nt_silu_bwd(const float* dy, const float* x, float* dx, size_t n) { NT_ENTRY(); return launch_ew<OP_SILU_B>(dy, x, dx, n); }
 int nt_scale(float* x, float alpha, size_t n) { NT_ENTRY(); return launch_ew<OP_SCALE>(x, nullptr, x, n, alpha); }
 
 int nt_add_rows(const float* x, const float* table, float* out, int rows, int period, int D) {
@@ -225,6 +307,44 @@ int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, i
   long long total = (long long)B * n_patch * n_patch * C * hl * wl;
   if (total == 0) return 0;
   NT_CHECK(nt::launch_k(patchify_kernel, dim3(grid_for(total)), dim3(256), 0, images, out, B, C, Hi, Wi, n_patch, hl, wl));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+static bool conv_geom(ConvGeom& g, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW) {
+  if (N < 0 || C <= 0 || H <= 0 || W <= 0 || KH <= 0 || KW <= 0 || SH <= 0 || SW <= 0 || PH < 0 || PW < 0) return false;
+  if (H + 2 * PH < KH || W + 2 * PW < KW) return false;
+  g = ConvGeom{N, C, H, W, KH, KW, SH, SW, PH, PW, (H + 2 * PH - KH) / SH + 1, (W + 2 * PW - KW) / SW + 1};
+  return true;
+}
+
+int nt_im2col(const float* x, float* col, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW) {
+  NT_ENTRY();
+  ConvGeom g;
+  NT_REQUIRE(conv_geom(g, N, C, H, W, KH, KW, SH, SW, PH, PW), "nt_im2col: bad geometry");
+  const long long total = (long long)N * g.OH * g.OW * C * KH * KW;
+  if (total == 0) return 0;
+  NT_CHECK(nt::launch_k(im2col_kernel, dim3(grid_for(total)), dim3(256), 0, x, col, g));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_col2im(const float* dcol, float* dx, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW) {
+  NT_ENTRY();
+  ConvGeom g;
+  NT_REQUIRE(conv_geom(g, N, C, H, W, KH, KW, SH, SW, PH, PW), "nt_col2im: bad geometry");
+  const long long total = (long long)N * C * H * W;
+  if (total == 0) return 0;
+  NT_CHECK(nt::launch_k(col2im_kernel, dim3(grid_for(total)), dim3(256), 0, dcol, dx, g));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_transpose_last2(const float* x, float* y, int batch, int rows, int cols) {
+  NT_ENTRY();
+  NT_REQUIRE(batch >= 0 && rows >= 0 && cols >= 0 && batch <= 65535, "nt_transpose_last2: bad shape");
+  if ((long long)batch * rows * cols == 0) return 0;
+  NT_CHECK(nt::launch_k(transpose_last2_kernel, dim3(ceil_div(cols, 32), ceil_div(rows, 32), batch), dim3(32, 8), 0, x, y, rows, cols));
   NT_LAUNCH_OK();
   return 0;
 }

@@ -101,8 +101,57 @@ __global__ void __launch_bounds__(256) ce_reduce_kernel(const float* __restrict_
   if (threadIdx.x == 0) *loss = s * inv_n;
 }
 
+// Element-wise losses of net/loss.py:53-57 (BCE on logits) and :68-71 (MSE): gradient (and sigmoid) per element, the
+// scalar as per-CTA partial sums folded with one atomic each into a zeroed accumulator.
+template <int KIND>      // 0: BCE with logits, 1: MSE
+__global__ void __launch_bounds__(256) elem_loss_kernel(const float* __restrict__ pred, const float* __restrict__ label,
+                                                        float* __restrict__ loss, float* __restrict__ grad,
+                                                        float* __restrict__ prob, size_t n, float inv_n) {
+  pdl_prologue();
+  __shared__ float sv[8];
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float p = pred[i], y = label[i];
+    if (KIND == 0) {
+      const float s = 1.0f / (1.0f + expf(-p));
+      acc -= y * logf(s + 1e-10f) + (1.0f - y) * logf((1.0f - s) + 1e-10f);
+      if (grad) grad[i] = (s - y) * inv_n;
+      if (prob) prob[i] = s;
+    } else {
+      const float d = p - y;
+      acc += d * d;
+      if (grad) grad[i] = 2.0f * d * inv_n;
+    }
+  }
+  acc = block_sum(acc, sv);
+  if (threadIdx.x == 0) atomicAdd(loss, acc * inv_n);
+}
+
+template <int KIND>
+static int elem_loss(const float* pred, const float* label, float* loss, float* grad, float* prob, size_t n) {
+  NT_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), g_stream));
+  if (n == 0) return 0;
+  size_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+  if (blocks > (size_t)g_sm_count * 4) blocks = (size_t)g_sm_count * 4;
+  NT_CHECK(nt::launch_k(elem_loss_kernel<KIND>, dim3((unsigned)blocks), dim3(256), 0, pred, label, loss, grad, prob, n, 1.0f / (float)n));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace nt
 using namespace nt;
+
+extern "C" int nt_bce_logit_loss(const float* logits, const float* label, float* loss, float* grad, float* sigmoid, size_t n) {
+  NT_ENTRY();
+  NT_REQUIRE(logits && label && loss, "nt_bce_logit_loss: logits, label and loss are required");
+  return elem_loss<0>(logits, label, loss, grad, sigmoid, n);
+}
+
+extern "C" int nt_mse_loss(const float* predict, const float* label, float* loss, float* grad, size_t n) {
+  NT_ENTRY();
+  NT_REQUIRE(predict && label && loss, "nt_mse_loss: predict, label and loss are required");
+  return elem_loss<1>(predict, label, loss, grad, nullptr, n);
+}
 
 extern "C" int nt_cross_entropy(const float* logits, const int32_t* labels, const float* onehot, float n_norm,
                                 float* loss, float* row_loss, float* grad, float* prob, int32_t* argmax, int rows,

@@ -68,8 +68,56 @@ class PatchEmbed_flatten(object):
 
 
 class PatchEmbed_convolution(object):
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("PatchEmbed_convolution is outside the B200 hot-path scope (SURVEY.md §8f rank 4)")
+    """PatchEmbed.py:73-122: convolution with kernel = stride = patch size, then (n, patches, embed_dim).  As in the
+    reference, forward runs the LayerNorm but hands back the tensor BEFORE it (:90-93 returns `out`), while backward
+    pushes the incoming gradient through the norm's backward; both quirks are kept (tests/golden/conv.npz)."""
+
+    def __init__(self, embed_dim, images_shape, n_patch, patchnorm=True):
+        self.embed_dim = embed_dim
+        n, c, h, w = images_shape
+        self.batch = n
+        self.h_length, self.w_length = h // n_patch, w // n_patch
+        self.n_patch, self.patchnorm = n_patch, patchnorm
+        self.convolution = convolution_layer(c, embed_dim, kernel_size=self.w_length, stride=self.w_length)
+        if patchnorm:
+            self.norm = layer_norm(self.embed_dim)
+
+    def forward(self, images):
+        out = self.convolution._forward_nhwc(images)           # already (n, ph*pw, embed_dim): no NCHW round trip
+        if self.patchnorm:
+            self.norm._forward(out)
+        return out
+
+    def backward(self, delta, want_dx=True):
+        delta = as_device(delta)
+        if self.patchnorm:
+            delta = self.norm._backward(delta)
+        return self.convolution._backward_nhwc(delta, want_dx=want_dx)
+
+    def update(self, lr):
+        if self.patchnorm:
+            self.norm.update(lr)
+        self.convolution.update(lr)
+
+    def setzero(self):
+        if self.patchnorm:
+            self.norm.setzero()
+        self.convolution.setzero()
+
+    def save_model(self):
+        model = []
+        if self.patchnorm:
+            model.append(self.norm.save_model())
+        model.append(self.convolution.save_model())
+        return model
+
+    def restore_model(self, models):
+        if self.patchnorm:
+            self.norm.restore_model(models[0])
+        self.convolution.restore_model(models[-1])
+
+    def _slots(self):
+        return (self.norm._slots() if self.patchnorm else []) + self.convolution._slots()
 
 
 class Position_Embedding(Embedding_layer):

@@ -1,4 +1,4 @@
-"""net.activation.{ReLU, Softmax, GELU} on the B200 backend (mirrors net/activation.py:9-23,75-154).
+"""net.activation.{ReLU, sigmoid, tanh, SiLU, Softmax, GELU} on the B200 backend (mirrors net/activation.py:9-154).
 As in the reference these classes have no save_model/restore_model, so checkpoint walkers skip them."""
 import numpy as np
 from numpy_transformer_b200._lib import lib
@@ -26,6 +26,43 @@ class ReLU(object):
 
     def update(self, lr=1e-10):
         pass
+
+
+class _Elementwise(object):
+    """y = f(x); backward needs either the output (sigmoid, tanh) or the input (SiLU)."""
+    _fwd = _bwd = None
+    _keep_output = True
+
+    def forward(self, inputs):
+        x = as_device(inputs)
+        self.inputs = x
+        self.y = x.empty_like()
+        getattr(lib, self._fwd)(x.ptr, self.y.ptr, x.size)
+        return self.y
+
+    def backward(self, delta):
+        d = as_device(delta)
+        out = d.empty_like()
+        getattr(lib, self._bwd)(d.ptr, (self.y if self._keep_output else self.inputs).ptr, out.ptr, d.size)
+        return out
+
+    def setzero(self):
+        pass
+
+    def update(self, lr=1e-10):
+        pass
+
+
+class sigmoid(_Elementwise):          # net/activation.py:25-39
+    _fwd, _bwd = "nt_sigmoid_fwd", "nt_sigmoid_bwd"
+
+
+class tanh(_Elementwise):             # net/activation.py:41-56
+    _fwd, _bwd = "nt_tanh_fwd", "nt_tanh_bwd"
+
+
+class SiLU(_Elementwise):             # net/activation.py:58-73
+    _fwd, _bwd, _keep_output = "nt_silu_fwd", "nt_silu_bwd", False
 
 
 class GELU(object):

@@ -1,5 +1,7 @@
-"""net.loss on the B200 backend (mirrors net/loss.py:46-51, 66-71)."""
+"""net.loss on the B200 backend (mirrors net/loss.py:46-57, 68-71; the reference's binary_cross_entropy_loss :59-66
+reads an undefined name and cannot run, so it has no counterpart)."""
 import numpy as np
+from numpy_transformer_b200._lib import lib
 from numpy_transformer_b200.device import DeviceArray, as_device
 from numpy_transformer_b200 import ops
 
@@ -47,8 +49,20 @@ def cross_entropy_loss(predict, label, n_norm=None):
 
 
 def mean_square_loss(predict, label):
-    """net/loss.py:66-71 — host-side (not on the hot path of any BASELINE config)."""
-    p, l = np.asarray(predict), np.asarray(label)
-    loss = np.sum(np.square(p - l)) / p.size
-    partial = 2 * (p - l) / p.size
-    return loss, partial
+    """net/loss.py:68-71: loss = mean((p - y)^2), partial = 2 (p - y) / size."""
+    p = as_device(predict)
+    l = as_device(label, p.host_dtype)
+    assert p.size == l.size, "mean_square_loss: %s vs %s" % (p.shape, l.shape)
+    loss, grad = DeviceArray((), host_dtype=np.float64), p.empty_like()
+    lib.nt_mse_loss(p.ptr, l.ptr, loss.ptr, grad.ptr, p.size)
+    return loss, grad
+
+
+def binary_cross_entropy_logit_loss(predict, label):
+    """net/loss.py:53-57: sigmoid inside the loss; returns (loss, partial, sigmoid)."""
+    p = as_device(predict)
+    l = as_device(label, p.host_dtype)
+    assert p.size == l.size, "binary_cross_entropy_logit_loss: %s vs %s" % (p.shape, l.shape)
+    loss, grad, sig = DeviceArray((), host_dtype=np.float64), p.empty_like(), p.empty_like()
+    lib.nt_bce_logit_loss(p.ptr, l.ptr, loss.ptr, grad.ptr, sig.ptr, p.size)
+    return loss, grad, sig

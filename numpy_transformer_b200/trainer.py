@@ -318,7 +318,7 @@ class TrainStep:
                 delta = fused_vit.backward_stack(runs[ends[i]], delta)
                 i = ends[i] - 1
                 continue
-            if l is first and hasattr(l, "fullconnect"):
+            if l is first and (hasattr(l, "fullconnect") or hasattr(l, "convolution")):
                 delta = l.backward(delta, want_dx=False)     # nobody consumes the patch-space gradient
             else:
                 delta = l.backward(delta)

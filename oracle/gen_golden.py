@@ -30,6 +30,11 @@ from gpt.classify_gpt import classify_layer as classify_layer_gpt  # noqa: E402
 
 from oracle import models as M                          # noqa: E402
 
+if not hasattr(np.lib, "pad"):          # net/Convolution.py:114,201 call np.lib.pad, which NumPy 2 dropped: harness shim
+    np.lib.pad = np.pad
+from net.Convolution import convolution_layer           # noqa: E402
+from PatchEmbed import PatchEmbed_convolution           # noqa: E402
+
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
@@ -339,8 +344,65 @@ def gen_gpt_tiny():
     print("gpt_tiny.npz losses", d["loss_0"], d["loss_1"], d["loss_2"])
 
 
+# ------------------------------------------------------------------ convolution
+CONV_CASES = [  # n, c, h, w, oc, kernel, stride, padding
+    (2, 1, 8, 8, 5, 4, 4, 0), (2, 2, 6, 7, 3, 3, 1, 1), (1, 2, 7, 7, 3, 3, 2, 1), (2, 3, 9, 8, 4, (2, 3), (2, 1), (0, 1)),
+    (1, 1, 10, 10, 2, 3, 3, 0), (1, 2, 8, 9, 3, 3, 2, 0)]
+
+
+def gen_conv():
+    """net/Convolution.py:37-248 forward / backward and PatchEmbed.py:73-122 (conv patch embedding, incl. its forward
+    returning the PRE-LayerNorm tensor while backward still goes through the norm)."""
+    d = {}
+    for i, (n, c, h, w, oc, k, s, p) in enumerate(CONV_CASES):
+        np.random.seed(100 + i)
+        x = np.random.randn(n, c, h, w)
+        conv = convolution_layer(c, oc, k, stride=s, padding=p)
+        d["c%d_x" % i], d["c%d_W" % i], d["c%d_b" % i] = x, conv.params.copy(), conv.bias_params.copy()
+        y = conv.forward(x)
+        g = np.random.randn(*y.shape)
+        d["c%d_y" % i], d["c%d_g" % i] = y, g
+        d["c%d_dx" % i] = conv.backward(g)
+        d["c%d_dW" % i], d["c%d_db" % i] = conv.params_delta.copy(), conv.bias_delta.copy()
+        conv.backward(g)                                  # accumulate-until-setzero
+        d["c%d_dW2" % i] = conv.params_delta.copy()
+        conv.update(0.05)
+        d["c%d_W1" % i], d["c%d_b1" % i] = conv.params.copy(), conv.bias_params.copy()
+    np.random.seed(7)
+    pe = PatchEmbed_convolution(12, (3, 2, 8, 8), 2, patchnorm=True)
+    x = np.random.randn(3, 2, 8, 8)
+    d["pe_x"], d["pe_W"], d["pe_b"] = x, pe.convolution.params.copy(), pe.convolution.bias_params.copy()
+    d["pe_y"] = pe.forward(x)
+    g = np.random.randn(3, 4, 12)
+    d["pe_g"] = g
+    d["pe_dx"] = pe.backward(g)
+    d["pe_dW"], d["pe_db"] = pe.convolution.params_delta.copy(), pe.convolution.bias_delta.copy()
+    d["pe_dgamma"], d["pe_dbeta"] = np.array(pe.norm.gamma_delta).reshape(-1), np.array(pe.norm.beta_delta).reshape(-1)
+    # net/activation.py:25-73 sigmoid / tanh / SiLU; net/loss.py:53-57 BCE on logits, :68-71 MSE
+    from net.activation import sigmoid, tanh, SiLU
+    from net.loss import binary_cross_entropy_logit_loss, mean_square_loss
+    np.random.seed(21)
+    x, dy = np.random.randn(4, 9) * 2, np.random.randn(4, 9)
+    d["act_x"], d["act_dy"] = x, dy
+    for name, cls in (("sigmoid", sigmoid), ("tanh", tanh), ("silu", SiLU)):
+        a = cls()
+        d[name + "_y"] = a.forward(x.copy())
+        d[name + "_dx"] = a.backward(dy)
+    lab = (np.random.rand(4, 9) > 0.5).astype(np.float64)
+    d["bce_label"] = lab
+    d["bce_loss"], d["bce_partial"], d["bce_sigmoid"] = binary_cross_entropy_logit_loss(x, lab)
+    tgt = np.random.randn(4, 9)
+    d["mse_label"] = tgt
+    d["mse_loss"], d["mse_partial"] = mean_square_loss(x, tgt)
+    np.savez_compressed(os.path.join(OUT, "conv.npz"), **d)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--only-conv" in sys.argv:
+        gen_conv()
+        sys.exit(0)
+    gen_conv()
     gen_prims()
     gen_vit_tiny()
     gen_gpt_tiny()

@@ -241,3 +241,94 @@ def adam_star_update(p, g, m, v, t, lr):
     vh = v / np.sqrt(1 - ADAM_B2 ** t)
     p = p - (mh * lr / (np.sqrt(vh) + ADAM_EPS))
     return p, m, v
+
+
+# ----------------------------------------------------------------------------- Convolution
+def _pair(v):
+    return [v, v] if isinstance(v, int) else list(v)
+
+
+def conv_im2col(x, kernel, stride, padding):
+    """net/Convolution.py:66-84 (im2col) on the zero-padded input (:114-119): rows = (n, oh, ow), columns = (c, kh, kw)."""
+    (kh, kw), (sh, sw), (ph, pw) = _pair(kernel), _pair(stride), _pair(padding)
+    n, c, h, w = x.shape
+    oh, ow = (h + 2 * ph - kh) // sh + 1, (w + 2 * pw - kw) // sw + 1
+    xp = np.pad(x, ((0, 0), (0, 0), (ph, ph), (pw, pw)))
+    col = np.empty((n, oh, ow, c, kh, kw), dtype=x.dtype)
+    for i in range(kh):
+        for j in range(kw):
+            col[:, :, :, :, i, j] = xp[:, :, i:i + sh * oh:sh, j:j + sw * ow:sw].transpose(0, 2, 3, 1)
+    return col.reshape(n * oh * ow, c * kh * kw), (n, oh, ow)
+
+
+def conv_fwd(x, W, b, stride=1, padding=0):
+    """net/Convolution.py:104-131  out[n, oc, oh, ow] = sum_{c,kh,kw} xpad[n, c, oh*sh+kh, ow*sw+kw] W[oc, c, kh, kw] (+ b[oc])."""
+    oc = W.shape[0]
+    col, (n, oh, ow) = conv_im2col(x, W.shape[2:], stride, padding)
+    y = col @ W.reshape(oc, -1).T
+    if b is not None:
+        y = y + b[np.newaxis, :]
+    return y.reshape(n, oh, ow, oc).transpose(0, 3, 1, 2)
+
+
+def conv_bwd(delta, x, W, stride=1, padding=0):
+    """net/Convolution.py:163-225 (and the loop form :133-161): db = sum over (n, oh, ow); dW[oc] = sum delta * window;
+    dx = scatter of W * delta back through the windows, cropped to the un-padded input."""
+    (kh, kw), (sh, sw), (ph, pw) = _pair(W.shape[2:]), _pair(stride), _pair(padding)
+    n, c, h, w = x.shape
+    oc = W.shape[0]
+    col, (_, oh, ow) = conv_im2col(x, (kh, kw), stride, padding)
+    d2 = delta.transpose(0, 2, 3, 1).reshape(-1, oc)
+    db = d2.sum(axis=0)
+    dW = (d2.T @ col).reshape(W.shape)
+    dcol = (d2 @ W.reshape(oc, -1)).reshape(n, oh, ow, c, kh, kw)
+    dxp = np.zeros((n, c, h + 2 * ph, w + 2 * pw), dtype=x.dtype)
+    for i in range(kh):
+        for j in range(kw):
+            dxp[:, :, i:i + sh * oh:sh, j:j + sw * ow:sw] += dcol[:, :, :, :, i, j].transpose(0, 3, 1, 2)
+    return dxp[:, :, ph:ph + h, pw:pw + w], dW, db
+
+
+# ----------------------------------------------------------------------------- remaining activations / losses
+def sigmoid_fwd(x):
+    """net/activation.py:27-30."""
+    return 1 / (1 + np.exp(-x))
+
+
+def sigmoid_bwd(dy, y):
+    """net/activation.py:32-33 (y = forward output)."""
+    return y * (1 - y) * dy
+
+
+def tanh_fwd(x):
+    """net/activation.py:43-47."""
+    return np.tanh(x)
+
+
+def tanh_bwd(dy, y):
+    """net/activation.py:49-50 (y = forward output)."""
+    return (1 - y ** 2) * dy
+
+
+def silu_fwd(x):
+    """net/activation.py:59-63."""
+    return x / (1 + np.exp(-x))
+
+
+def silu_bwd(dy, x):
+    """net/activation.py:65-67: (div + out * e^-x * div) * dy."""
+    e = np.exp(-x)
+    div = 1 / (1 + e)
+    return (div + x * div * e * div) * dy
+
+
+def bce_logit_loss(predict, label):
+    """net/loss.py:53-57."""
+    s = 1 / (1 + np.exp(-predict))
+    loss = -np.sum(label * np.log(s + 1e-10) + (1 - label) * np.log((1 - s) + 1e-10)) / predict.size
+    return loss, (s - label) / predict.size, s
+
+
+def mse_loss(predict, label):
+    """net/loss.py:68-71."""
+    return np.sum(np.square(predict - label)) / predict.size, 2 * (predict - label) / predict.size

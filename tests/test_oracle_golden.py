@@ -182,3 +182,48 @@ def test_vit_readme_trajectory_losses():
             assert np.allclose([np.abs(g).max() for g in gl], d["grad_absmax"], rtol=1e-9)
             assert rel_err(gl[4], d["grad_qkv0"]) < 1e-6      # stored as fp32
         params = out["params"]
+
+
+CONV_CASES = [(4, 0), (1, 1), (2, 1), ((2, 1), (0, 1)), (3, 0), (2, 0)]      # (stride, padding) of oracle/gen_golden.py:CONV_CASES
+
+
+@pytest.mark.parametrize("i", range(len(CONV_CASES)))
+def test_convolution(i):
+    """net/Convolution.py:104-131 forward, :163-225 backward (accumulating), :236-239 update."""
+    g = load_golden("conv.npz")
+    s, p = CONV_CASES[i]
+    x, W, b = g["c%d_x" % i], g["c%d_W" % i], g["c%d_b" % i]
+    assert rel_err(R.conv_fwd(x, W, b, s, p), g["c%d_y" % i]) < TOL
+    dx, dW, db = R.conv_bwd(g["c%d_g" % i], x, W, s, p)
+    assert rel_err(dx, g["c%d_dx" % i]) < TOL and rel_err(dW, g["c%d_dW" % i]) < TOL and rel_err(db, g["c%d_db" % i]) < TOL
+    assert rel_err(2 * dW, g["c%d_dW2" % i]) < TOL
+    assert rel_err(R.sgd_update(W, 2 * dW, 0.05), g["c%d_W1" % i]) < TOL
+    assert rel_err(R.sgd_update(b, 2 * db, 0.05), g["c%d_b1" % i]) < TOL
+
+
+def test_patch_embed_convolution():
+    """PatchEmbed.py:73-122: conv with kernel = stride = patch, NCHW -> (n, patches, embed); forward hands back the tensor
+    BEFORE the LayerNorm (:90-93 returns `out`), backward still runs the norm's backward on the incoming gradient."""
+    g = load_golden("conv.npz")
+    x, W, b = g["pe_x"], g["pe_W"], g["pe_b"]
+    y = R.conv_fwd(x, W, b, 4, 0).transpose(0, 2, 3, 1).reshape(3, -1, 12)
+    assert rel_err(y, g["pe_y"]) < TOL
+    _, xhat, var = R.layernorm_fwd(y, np.ones(12), np.zeros(12))
+    d, dgam, dbet = R.layernorm_bwd(g["pe_g"], xhat, var, np.ones(12))
+    assert rel_err(dgam, g["pe_dgamma"]) < TOL and rel_err(dbet, g["pe_dbeta"]) < TOL
+    dx, dW, db = R.conv_bwd(d.reshape(3, 2, 2, 12).transpose(0, 3, 1, 2), x, W, 4, 0)
+    assert rel_err(dx, g["pe_dx"]) < TOL and rel_err(dW, g["pe_dW"]) < TOL and rel_err(db, g["pe_db"]) < TOL
+
+
+def test_remaining_activations_and_losses():
+    """net/activation.py:25-73 (sigmoid, tanh, SiLU), net/loss.py:53-57 (BCE on logits), :68-71 (MSE)."""
+    g = load_golden("conv.npz")
+    x, dy = g["act_x"], g["act_dy"]
+    assert rel_err(R.sigmoid_fwd(x), g["sigmoid_y"]) < TOL and rel_err(R.sigmoid_bwd(dy, g["sigmoid_y"]), g["sigmoid_dx"]) < TOL
+    assert rel_err(R.tanh_fwd(x), g["tanh_y"]) < TOL and rel_err(R.tanh_bwd(dy, g["tanh_y"]), g["tanh_dx"]) < TOL
+    assert rel_err(R.silu_fwd(x), g["silu_y"]) < TOL and rel_err(R.silu_bwd(dy, x), g["silu_dx"]) < TOL
+    loss, partial, s = R.bce_logit_loss(x, g["bce_label"])
+    assert abs(loss - g["bce_loss"]) < TOL * abs(g["bce_loss"]) and rel_err(partial, g["bce_partial"]) < TOL
+    assert rel_err(s, g["bce_sigmoid"]) < TOL
+    loss, partial = R.mse_loss(x, g["mse_label"])
+    assert abs(loss - g["mse_loss"]) < TOL * abs(g["mse_loss"]) and rel_err(partial, g["mse_partial"]) < TOL
