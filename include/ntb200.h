@@ -273,6 +273,17 @@ int nt_vit_head(const NtVitEnds* e, int B, int N, int D, int D0, int C1, float n
 /* PatchEmbed_flatten.forward patch loops, PatchEmbed.py:22-36: (B,C,Hi,Wi) -> (B, n_patch^2, C*h*w) */
 int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, int n_patch);
 
+/* Batch construction on the device: the data set stays resident, a step's batch is one gather.
+ * nt_gather_images_u8: out[b, :] = lut256[src[perm[first + b], :]] — the shuffled, normalised slice of
+ *   transformer_of_image.py:99-100,128-137 (lut256[v] = float32(v / 255.0), built by the host so values are bit-identical);
+ * nt_gather_i32: out[b] = src[perm[first + b]] (labels);
+ * nt_gather_windows: inputs[b, t] = corpus[start[b] + t], labels[b, t] = corpus[start[b] + t + 1]
+ *   (getinputs, gpt/gpt_train_potry3000.py:106-133). */
+int nt_gather_images_u8(const unsigned char* src, const int32_t* perm, int first, const float* lut256, float* out, int B,
+                        int pixels);
+int nt_gather_i32(const int32_t* src, const int32_t* perm, int first, int32_t* out, int B);
+int nt_gather_windows(const int32_t* corpus, const int32_t* start, int32_t* inputs, int32_t* labels, int B, int T);
+
 /* convolution_layer (net/Convolution.py:37-248) = im2col + the Linear entry points above.
  * nt_im2col: col[(n, oh, ow)][(c, kh, kw)] of the zero-padded input (:66-84, :114-119); OH = (H + 2 PH - KH) / SH + 1.
  * nt_col2im: its adjoint, dx[N,C,H,W] from dcol (the input gradient of :196-223), written (not accumulated).

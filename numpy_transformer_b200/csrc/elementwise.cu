@@ -85,6 +85,39 @@ __global__ void patchify_kernel(const float* __restrict__ img, float* __restrict
   }
 }
 
+// ---- batch construction on the device
+// images[b] = lut[src[perm[first + b]]]: the shuffled, /255-normalised MNIST slice of transformer_of_image.py:99-100,
+// 128-137 without touching the host; lut[v] = float32(v / 255.0) is computed on the host so that the values are bit-identical
+// to the reference's fp64 division followed by the fp32 upload cast.  labels likewise.
+__global__ void gather_images_u8_kernel(const unsigned char* __restrict__ src, const int32_t* __restrict__ perm, int first,
+                                        const float* __restrict__ lut, float* __restrict__ out, int B, int pixels) {
+  pdl_prologue();
+  const long long total = (long long)B * pixels;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / pixels), p = (int)(i - (long long)b * pixels);
+    out[i] = lut[src[(long long)perm[first + b] * pixels + p]];
+  }
+}
+
+__global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ perm, int first,
+                                  int32_t* __restrict__ out, int B) {
+  pdl_prologue();
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) out[b] = src[perm[first + b]];
+}
+
+// inputs[b, t] = corpus[start[b] + t], labels[b, t] = corpus[start[b] + t + 1]   (gpt/gpt_train_potry3000.py:106-133)
+__global__ void gather_windows_kernel(const int32_t* __restrict__ corpus, const int32_t* __restrict__ start,
+                                      int32_t* __restrict__ inputs, int32_t* __restrict__ labels, int B, int T) {
+  pdl_prologue();
+  const long long total = (long long)B * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / T), t = (int)(i - (long long)b * T);
+    const long long o = (long long)start[b] + t;
+    inputs[i] = corpus[o];
+    labels[i] = corpus[o + 1];
+  }
+}
+
 // ---- convolution as im2col + Linear (net/Convolution.py:66-84, 104-131, 163-225)
 struct ConvGeom { int N, C, H, W, KH, KW, SH, SW, PH, PW, OH, OW; };
 
@@ -307,6 +340,34 @@ int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, i
   long long total = (long long)B * n_patch * n_patch * C * hl * wl;
   if (total == 0) return 0;
   NT_CHECK(nt::launch_k(patchify_kernel, dim3(grid_for(total)), dim3(256), 0, images, out, B, C, Hi, Wi, n_patch, hl, wl));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_gather_images_u8(const unsigned char* src, const int32_t* perm, int first, const float* lut256, float* out, int B,
+                        int pixels) {
+  NT_ENTRY();
+  NT_REQUIRE(src && perm && lut256 && out && first >= 0 && B >= 0 && pixels > 0, "nt_gather_images_u8: bad arguments");
+  if (B == 0) return 0;
+  NT_CHECK(nt::launch_k(gather_images_u8_kernel, dim3(grid_for((size_t)B * pixels)), dim3(256), 0, src, perm, first, lut256, out, B, pixels));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_gather_i32(const int32_t* src, const int32_t* perm, int first, int32_t* out, int B) {
+  NT_ENTRY();
+  NT_REQUIRE(src && perm && out && first >= 0 && B >= 0, "nt_gather_i32: bad arguments");
+  if (B == 0) return 0;
+  NT_CHECK(nt::launch_k(gather_i32_kernel, dim3(ceil_div(B, 256)), dim3(256), 0, src, perm, first, out, B));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+int nt_gather_windows(const int32_t* corpus, const int32_t* start, int32_t* inputs, int32_t* labels, int B, int T) {
+  NT_ENTRY();
+  NT_REQUIRE(corpus && start && inputs && labels && B >= 0 && T > 0, "nt_gather_windows: bad arguments");
+  if (B == 0) return 0;
+  NT_CHECK(nt::launch_k(gather_windows_kernel, dim3(grid_for((size_t)B * T)), dim3(256), 0, corpus, start, inputs, labels, B, T));
   NT_LAUNCH_OK();
   return 0;
 }
