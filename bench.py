@@ -244,6 +244,8 @@ def run_ours(args):
     recs = []
     for _ in range(prof_steps):
         lib.nt_flush_l2()
+        if dp is not None:
+            dp.barrier()                # ranks enter the replay together: the all-reduce wait is not charged with their skew
         lib.nt_graph_launch(pg)
         lib.nt_sync()
         recs += lib.profile_read(precs)
@@ -263,7 +265,8 @@ def run_ours(args):
         cl["n"] += n
         cl["flops"] += fl * n
         cl["bytes"] += by * n
-    top = max(classes.items(), key=lambda kv: kv[1]["ms"])
+    # the dominant KERNEL: waits on the collective (nt_dp_*) stay in the op table but are not a kernel of this repo
+    top = max(((k, v) for k, v in classes.items() if not k.startswith("nt_dp_")), key=lambda kv: kv[1]["ms"])
     tname, tc = top
     if tc["flops"] > 0:
         ach = tc["flops"] / (tc["ms"] / 1e3) / 1e12
