@@ -4,10 +4,11 @@
 // Same arithmetic contract as the TF32x3 kernels of attention.cu (fp32-class: every product is lo*hi + hi*lo + hi*hi
 // of bf16 splits, fp32 accumulate), but m16n8k16 MMAs fed by ldmatrix from operands that are split ONCE when a tile
 // is staged in shared memory — half the tensor instructions and no per-fragment conversions.
-//   forward   one CTA per (64-query block, sample, head), 4 warps x 16 query rows.  Pass 1 sweeps the key blocks
-//             for the row max / sum only; pass 2 recomputes the scores (cheap on the tensor pipe), writes the
-//             normalised softmax P (the reference keeps it: atg__) once and accumulates O = P V.  No raw-score
-//             round trip through P as in the TF32 kernel.
+//   forward   one CTA per (64-query block, sample, head), 4 warps x 16 query rows.  Pass 1 sweeps the key blocks:
+//             scores, row max / sum, scores parked in the P buffer; pass 2 re-reads them (same thread, L2-resident),
+//             writes the normalised softmax P (the reference keeps it: atg__) and accumulates O = P V with P fed
+//             from the accumulator fragments.  (The first version recomputed Q K^T in pass 2; the kernel is bound by
+//             shared-memory operand traffic, not by the tensor pipe, so the round trip is cheaper.)
 //   backward  kernel Q per query block: t_i = sum_j dP_ij P_ij, then dS = P o (dP - t), dQ = dS K / sqrt(dh);
 //             kernel K per key block: recomputes dP = dO V^T and dS for its keys, dK = dS^T Q / sqrt(dh),
 //             dV = P^T dO.  Only the row sums t travel between the two (first B*H*N floats of `scratch`);
@@ -118,17 +119,30 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const float* __restr
   const int i0 = warp * 16, r0 = q0 + i0 + g, r1 = r0 + 8;
   const float scale = rsqrtf((float)DH);
   load_split<DH>(sQ, base, 3 * D, q0, N, tid);
-  // ---------------- pass 1: row max / sum over the key blocks
+  // ---------------- pass 1: scores once; row max / sum over the key blocks.  The scaled + masked scores are parked in
+  // the P buffer (each thread re-reads exactly the elements it wrote, so no synchronisation is needed) instead of being
+  // recomputed in pass 2: ncu showed the kernel bound by shared-memory operand traffic (L1 75 % busy, tensor pipe 24 %),
+  // and the second Q K^T cost a K-tile staging + 20 KB of fragment loads per warp and block; the round trip through P
+  // costs 2 x 16 KB of L2-resident global traffic instead.  The optional pre-mask score dump (att_col is dense) needs
+  // every block even under a causal mask.
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  for (int kc = 0; kc < nchunks; kc++) {
+  const int npass1 = Sb ? nall : nchunks;
+  for (int kc = 0; kc < npass1; kc++) {
     __syncthreads();
     load_split<DH>(sK, base + D, 3 * D, kc * LQ, N, tid);
     __syncthreads();
     float s[8][4];
-    scores<DH>(s, sQ, sK, i0, r0, r1, kc, N, scale, mask_kind, mask, nullptr, lane, t);
+    scores<DH>(s, sQ, sK, i0, r0, r1, kc, N, scale, mask_kind, mask, Sb, lane, t);
+    if (kc >= nchunks) continue;              // beyond the causal frontier: only the score dump was needed
     float c0 = -INFINITY, c1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < 8; nt++) { c0 = fmaxf(c0, fmaxf(s[nt][0], s[nt][1])); c1 = fmaxf(c1, fmaxf(s[nt][2], s[nt][3])); }
+    for (int nt = 0; nt < 8; nt++) {
+      const int col = kc * LQ + nt * 8 + 2 * t;
+      if (r0 < N) { if (col < N) Pb[(long long)r0 * N + col] = s[nt][0]; if (col + 1 < N) Pb[(long long)r0 * N + col + 1] = s[nt][1]; }
+      if (r1 < N) { if (col < N) Pb[(long long)r1 * N + col] = s[nt][2]; if (col + 1 < N) Pb[(long long)r1 * N + col + 1] = s[nt][3]; }
+      c0 = fmaxf(c0, fmaxf(s[nt][0], s[nt][1]));
+      c1 = fmaxf(c1, fmaxf(s[nt][2], s[nt][3]));
+    }
     const float n0 = fmaxf(m0, quad_max(c0)), n1 = fmaxf(m1, quad_max(c1));
     float a0 = 0.f, a1 = 0.f;
     if (n0 > -INFINITY) {
@@ -146,20 +160,23 @@ __global__ void __launch_bounds__(128) attn_fwd_bf16_kernel(const float* __restr
   const float inv0 = (r0 < N && l0 > 0.f) ? 1.0f / l0 : 0.f, inv1 = (r1 < N && l1 > 0.f) ? 1.0f / l1 : 0.f;
   if (!(m0 > -INFINITY)) m0 = 0.f;
   if (!(m1 > -INFINITY)) m1 = 0.f;
-  // ---------------- pass 2: P = exp(s - m) / l (written once), O = P V.  The optional pre-mask score dump needs
-  // every block even under a causal mask (att_col is dense).
+  // ---------------- pass 2: P = exp(s - m) / l (written once, over the parked scores), O = P V
   float o[DH / 8][4];
 #pragma unroll
   for (int nd = 0; nd < DH / 8; nd++) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
-  const int npass2 = Sb ? nall : nchunks;
-  for (int kc = 0; kc < npass2; kc++) {
+  for (int kc = 0; kc < nchunks; kc++) {
     __syncthreads();
-    load_split<DH>(sK, base + D, 3 * D, kc * LQ, N, tid);
     load_split<DH>(sV, base + 2 * D, 3 * D, kc * LQ, N, tid);
-    __syncthreads();
     float s[8][4];
-    scores<DH>(s, sQ, sK, i0, r0, r1, kc, N, scale, mask_kind, mask, Sb, lane, t);
-    if (kc >= nchunks) continue;              // beyond the causal frontier: only the score dump was needed
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      const int col = kc * LQ + nt * 8 + 2 * t;
+      s[nt][0] = (r0 < N && col < N) ? Pb[(long long)r0 * N + col] : -INFINITY;
+      s[nt][1] = (r0 < N && col + 1 < N) ? Pb[(long long)r0 * N + col + 1] : -INFINITY;
+      s[nt][2] = (r1 < N && col < N) ? Pb[(long long)r1 * N + col] : -INFINITY;
+      s[nt][3] = (r1 < N && col + 1 < N) ? Pb[(long long)r1 * N + col + 1] : -INFINITY;
+    }
+    __syncthreads();
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
       const int col = kc * LQ + nt * 8 + 2 * t;
