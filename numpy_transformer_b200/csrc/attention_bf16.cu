@@ -540,14 +540,14 @@ template <int DH> static size_t bwds_smem() { return 4 * (size_t)Smem<DH>::ARR; 
 }  // namespace ab
 
 // dh == 64 (scaled ViT N = 49 -> single-block kernels; GPT configs T = 256 -> two-pass kernels); NTB200_ATT_BF16=0
-// keeps the TF32x3 kernels of attention.cu, NTB200_ATT_BF16_MIN_N raises the sequence-length threshold.
+// keeps the TF32x3 kernels of attention.cu, NTB200_ATT_BF16_MIN_N (default 16) moves the sequence-length threshold.
 // Measured on B200 per step: G1 forward 1.03 -> 0.76 ms, backward 1.50 -> 1.09 ms; V2 forward 2.80 -> 2.54 ms,
 // backward 3.66 -> 2.49 ms.
 bool attention_bf16_ok(int N, int H, int dh) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("NTB200_ATT_BF16"); on = (e && e[0] == '0') ? 0 : 1; }
   const char* f = getenv("NTB200_ATT_BF16_MIN_N");
-  const int min_n = f ? atoi(f) : 1;
+  const int min_n = f ? atoi(f) : 16;         // below ~16 tokens the TF32x3 single-block kernels are faster (G0, T = 5: -7 us/step)
   return on && dh == 64 && N >= min_n && g_gemm_mode == 1;
 }
 
