@@ -143,7 +143,6 @@ def run_ours(args):
     import numpy_transformer_b200 as nt
     from numpy_transformer_b200 import trainer
     from numpy_transformer_b200.parallel import DataParallel
-    from oracle import models as M      # synthetic batches + cpu_baseline leg only (never on the timed GPU path)
 
     kind, c = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
