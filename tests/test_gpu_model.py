@@ -238,6 +238,29 @@ def test_full_size_properties(nt):
     assert not np.any(ts.arena.grads.numpy())
 
 
+def test_full_size_properties_gpt(nt):
+    """The same kind of checks at the poetry3000 shape (B=64, T=256, D=384, 6 heads, 5 blocks, V=2350: BF16x3 GEMMs, the
+    long-sequence attention kernels, Adam*): loss falls on a repeated batch, every softmax row sums to 1, the causal upper
+    triangle of P is EXACTLY zero, the returned arg-max is the first maximum of the returned probabilities."""
+    from numpy_transformer_b200 import trainer
+    rs = np.random.RandomState(4)
+    B, T, V = 64, 256, 2350
+    tokens, labels = rs.randint(0, V, (B, T)), rs.randint(0, V, (B, T))
+    layers = trainer.build_gpt_layers(B, T, 384, 6, 5, V, adam=True, seed=1)
+    ts = trainer.TrainStep(layers, "gpt", tokens.shape, lr=3e-4, adam=True)
+    out = [ts.step(tokens, labels, want_argmax=True) for _ in range(4)]
+    losses = [o[0] for o in out]
+    assert np.all(np.isfinite(losses)) and losses[-1] < losses[0]
+    P = np.asarray(layers[3].P)
+    assert P.shape == (B, 6, T, T)
+    assert np.allclose(P.sum(-1), 1.0, atol=2e-5)
+    assert not np.any(np.triu(P[::7, :, :, :], k=1))
+    probs = np.asarray(ts.probs).reshape(B * T, -1)[:, :V]      # the head's logits are padded to a multiple of 4 columns
+    assert np.allclose(probs[::97].sum(-1), 1.0, atol=2e-5)
+    assert np.array_equal(out[-1][1].reshape(-1)[::13], np.argmax(probs[::13], axis=-1))
+    assert not np.any(ts.arena.grads.numpy())
+
+
 def test_trainstep_state_dict_resumes_adam(nt):
     """Optimizer-state checkpoint: params + Adam* moments + step counter survive a pickle round trip,
     and the resumed run continues exactly like the uninterrupted one (the reference saves parameters only:
