@@ -82,6 +82,10 @@ int nt_linear_fwd(const float* x, const float* w, const float* b, float* y,
 /* fclayer.backward input half, net/fullconnect.py:114:  dx[M,K] = (dy[M,N] @ w[K,N]^T) * act'(pre[M,K]) + addend[M,K].
  * act' is GELU.backward (net/activation.py:144-148) or ReLU.backward (:16-17) of the layer that
  * PRODUCED x; pre / addend may be NULL. */
+/* Decode-step form (1..8 rows): y = act(LayerNorm(x; ln_g, ln_b) W + b) + residual in one launch (layernorm.py:100-114 followed
+ * by fullconnect.py:99-106); nothing is saved for a backward. */
+int nt_linear_ln_skinny(const float* x, const float* ln_g, const float* ln_b, const float* w, const float* b, float* y, int M,
+                        int K, int N, int act, const float* residual);
 int nt_linear_bwd_input(const float* dy, const float* w, float* dx,
                         int M, int K, int N, int act, const float* pre, const float* addend);
 /* fclayer.backward parameter half, net/fullconnect.py:118-125:  dw[K,N] += x^T @ dy ; db[N] += colsum(dy).
@@ -192,8 +196,8 @@ int nt_attention_decode(const float* qkv_new, const float* kcache, const float* 
 int nt_decode_embed(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int D, int Tmax,
                     const int32_t* d_pos);
 int nt_kv_append_at(const float* qkv, float* kcache, float* vcache, int B, int Tmax, int D, const int32_t* d_pos);
-int nt_attention_decode_at(const float* qkv_new, const float* kcache, const float* vcache, float* out, int B, int Tmax, int H,
-                           int dh, const int32_t* d_pos);
+int nt_attention_decode_at(const float* qkv_new, float* kcache, float* vcache, float* out, int B, int Tmax, int H,
+                           int dh, const int32_t* d_pos, int append);   /* append != 0: nt_kv_append_at folded in */
 int nt_argmax_next(const float* logits, int ld, int cols, int B, int32_t* tok, int32_t* hist, int hist_ld, const int32_t* d_pos);
 
 /* ---------------------------------------------------------------- fused ViT encoder blocks

@@ -1084,9 +1084,11 @@ __global__ void kv_append_kernel(const float* __restrict__ qkv, float* __restric
 // one 4-warp CTA per (sample, head): scores over the cached keys (one key per thread, float4 loads), softmax, then the
 // weighted sum of the cached values (warp w takes keys w, w+4, ...; lanes run along dh so every load is one 128-byte line)
 constexpr int DEC_THREADS = 128;
-__global__ void __launch_bounds__(DEC_THREADS) attn_decode_kernel(const float* __restrict__ qkv_new, const float* __restrict__ kc,
-                                                                  const float* __restrict__ vc, float* __restrict__ out, int Tmax,
-                                                                  int len, int H, int dh, const int32_t* __restrict__ d_pos) {
+// `append`: the CTA first stores the new token's k / v slice of its head into cache row len-1 (nt_kv_append folded in; the
+// caches are therefore plain pointers: the rows are re-read by the same CTA after the barrier).
+__global__ void __launch_bounds__(DEC_THREADS) attn_decode_kernel(const float* __restrict__ qkv_new, float* kc, float* vc,
+                                                                  float* __restrict__ out, int Tmax, int len, int H, int dh,
+                                                                  const int32_t* __restrict__ d_pos, int append) {
   pdl_prologue();
   if (d_pos) len = min(*d_pos + 1, Tmax);
   extern __shared__ __align__(16) float sm[];          // [dh] q | [4][dh] partial outputs | [8] reductions | [len] p
@@ -1095,7 +1097,15 @@ __global__ void __launch_bounds__(DEC_THREADS) attn_decode_kernel(const float* _
   float* sr = so + 4 * dh;
   float* sp = sr + 8;
   const int bh = blockIdx.x, b = bh / H, h = bh % H, D = H * dh, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int d = tid; d < dh; d += DEC_THREADS) sq[d] = qkv_new[(long long)b * 3 * D + h * dh + d];
+  for (int d = tid; d < dh; d += DEC_THREADS) {
+    const long long qo = (long long)b * 3 * D + h * dh + d;
+    sq[d] = qkv_new[qo];
+    if (append) {
+      const long long co = ((long long)b * Tmax + (len - 1)) * D + h * dh + d;
+      kc[co] = qkv_new[qo + D];
+      vc[co] = qkv_new[qo + 2 * D];
+    }
+  }
   __syncthreads();
   const float scale = 1.0f / sqrtf((float)dh);
   const float* kb = kc + (long long)b * Tmax * D + h * dh;
@@ -1390,20 +1400,21 @@ int nt_attention_decode(const float* qkv_new, const float* kcache, const float* 
   if (B == 0) return 0;
   const size_t smem = sizeof(float) * (5 * (size_t)dh + 8 + len);
   NT_REQUIRE(smem <= 48 * 1024, "nt_attention_decode: context %d too long", len);
-  NT_CHECK(nt::launch_k(attn_decode_kernel, dim3(B * H), dim3(DEC_THREADS), smem, qkv_new, kcache, vcache, out, Tmax, len, H, dh,
-                        (const int32_t*)nullptr));
+  NT_CHECK(nt::launch_k(attn_decode_kernel, dim3(B * H), dim3(DEC_THREADS), smem, qkv_new, const_cast<float*>(kcache),
+                        const_cast<float*>(vcache), out, Tmax, len, H, dh, (const int32_t*)nullptr, 0));
   NT_LAUNCH_OK();
   return 0;
 }
 
-int nt_attention_decode_at(const float* qkv_new, const float* kcache, const float* vcache, float* out, int B, int Tmax, int H,
-                           int dh, const int32_t* d_pos) {
+int nt_attention_decode_at(const float* qkv_new, float* kcache, float* vcache, float* out, int B, int Tmax, int H,
+                           int dh, const int32_t* d_pos, int append) {
   NT_ENTRY();
   NT_REQUIRE(B >= 0 && Tmax >= 1 && H > 0 && dh > 0 && d_pos, "nt_attention_decode_at: bad arguments");
   if (B == 0) return 0;
   const size_t smem = sizeof(float) * (5 * (size_t)dh + 8 + Tmax);
   NT_REQUIRE(smem <= 48 * 1024, "nt_attention_decode_at: context %d too long", Tmax);
-  NT_CHECK(nt::launch_k(attn_decode_kernel, dim3(B * H), dim3(DEC_THREADS), smem, qkv_new, kcache, vcache, out, Tmax, 0, H, dh, d_pos));
+  NT_CHECK(nt::launch_k(attn_decode_kernel, dim3(B * H), dim3(DEC_THREADS), smem, qkv_new, kcache, vcache, out, Tmax, 0, H, dh, d_pos,
+                        append ? 1 : 0));
   NT_LAUNCH_OK();
   return 0;
 }

@@ -28,25 +28,42 @@ __global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ 
 // would be >= 94 % padding and walk K serially in one CTA (20-50 us measured for 1 x 384 x {384..2350}); here the weight
 // panel is streamed once by N/32 CTAs, 32 k-groups x 8 lanes x float4 each, exact fp32 FMAs, and the bias / activation /
 // residual epilogue of net/fullconnect.py:96-104 follows the in-CTA reduction.
-template <int MR, bool VEC>
+// ln_g / ln_b (may be NULL): the rows are LayerNorm-ed first (net/layernorm.py:100-114, biased variance, eps 1e-5) — every
+// CTA normalises its own copy of the <= 8 rows, which is cheaper than a separate launch in the decode step.
+template <int MR, int CL, bool VEC>      // CL lanes x float4 = 4*CL columns per CTA, 256/CL k-groups
 __global__ void __launch_bounds__(256) linear_skinny_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ b, float* __restrict__ y, int M, int K,
                                                             int N, int act, float* __restrict__ pre,
-                                                            const float* __restrict__ residual) {
+                                                            const float* __restrict__ residual,
+                                                            const float* __restrict__ ln_g, const float* __restrict__ ln_b) {
   pdl_prologue();
+  constexpr int COLS = 4 * CL, KG = 256 / CL;
   extern __shared__ __align__(16) float sk[];
   float* sx = sk;                          // [MR][K]
-  float* red = sk + ((MR * K + 3) & ~3);   // [32 k-groups][MR][32 columns]
-  const int tid = threadIdx.x, cl = tid & 7, kg = tid >> 3;
-  const int n0 = blockIdx.x * 32 + cl * 4;
+  float* red = sk + ((MR * K + 3) & ~3);   // [8 warps][MR][COLS]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, cl = tid % CL, kg = tid / CL;
+  const int n0 = blockIdx.x * COLS + cl * 4;
   for (int e = tid; e < MR * K; e += 256) sx[e] = e < M * K ? x[e] : 0.f;
   __syncthreads();
+  if (ln_g) {
+    for (int r = warp; r < M; r += 8) {      // one warp per row: two-pass mean / variance like layernorm.cu
+      float* row = sx + r * K;
+      float s = 0.f;
+      for (int k = lane; k < K; k += 32) s += row[k];
+      const float mean = warp_sum(s) / K;
+      float q = 0.f;
+      for (int k = lane; k < K; k += 32) { const float d = row[k] - mean; q += d * d; }
+      const float rstd = rsqrtf(warp_sum(q) / K + 1e-5f);
+      for (int k = lane; k < K; k += 32) row[k] = (row[k] - mean) * rstd * ln_g[k] + ln_b[k];
+    }
+    __syncthreads();
+  }
   float acc[MR][4];
 #pragma unroll
   for (int r = 0; r < MR; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
   if (n0 < N) {
 #pragma unroll 4
-    for (int k = kg; k < K; k += 32) {
+    for (int k = kg; k < K; k += KG) {
       float wv[4];
       const float* wr = w + (long long)k * N + n0;
       if (VEC) {
@@ -64,16 +81,25 @@ __global__ void __launch_bounds__(256) linear_skinny_kernel(const float* __restr
       }
     }
   }
+  // k-groups of one warp sit CL lanes apart: butterfly over the upper lane bits, then one partial per warp in shared memory
 #pragma unroll
-  for (int r = 0; r < MR; r++)
-    *reinterpret_cast<float4*>(red + (kg * MR + r) * 32 + cl * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  for (int off = 16; off >= CL; off >>= 1)
+#pragma unroll
+    for (int r = 0; r < MR; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], off);
+  if (lane < CL) {
+#pragma unroll
+    for (int r = 0; r < MR; r++)
+      *reinterpret_cast<float4*>(red + (warp * MR + r) * COLS + lane * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  }
   __syncthreads();
-  for (int e = tid; e < MR * 32; e += 256) {
-    const int r = e >> 5, c = e & 31, n = blockIdx.x * 32 + c;
+  for (int e = tid; e < MR * COLS; e += 256) {
+    const int r = e / COLS, c = e % COLS, n = blockIdx.x * COLS + c;
     if (r >= M || n >= N) continue;
     float v = 0.f;
-#pragma unroll 8
-    for (int g = 0; g < 32; g++) v += red[(g * MR + r) * 32 + c];
+#pragma unroll
+    for (int g = 0; g < 8; g++) v += red[(g * MR + r) * COLS + c];
     if (b) v += b[n];
     const long long o = (long long)r * N + n;
     if (pre) pre[o] = v;
@@ -84,20 +110,30 @@ __global__ void __launch_bounds__(256) linear_skinny_kernel(const float* __restr
   }
 }
 
-template <int MR>
-static int linear_skinny_launch(const float* x, const float* w, const float* b, float* y, int M, int K, int N, int act,
-                                float* pre, const float* residual) {
-  const size_t smem = sizeof(float) * ((((size_t)MR * K + 3) & ~(size_t)3) + 32 * MR * 32);
+template <int MR, int CL>
+static int linear_skinny_launch_cl(const float* x, const float* w, const float* b, float* y, int M, int K, int N, int act,
+                                   float* pre, const float* residual, const float* ln_g, const float* ln_b) {
+  const size_t smem = sizeof(float) * ((((size_t)MR * K + 3) & ~(size_t)3) + 8 * MR * 4 * CL);
   const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
-  auto kern = vec ? linear_skinny_kernel<MR, true> : linear_skinny_kernel<MR, false>;
+  auto kern = vec ? linear_skinny_kernel<MR, CL, true> : linear_skinny_kernel<MR, CL, false>;
   static size_t configured[2] = {0, 0};
   if (smem > 48 * 1024 && smem > configured[vec]) {
     NT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[vec] = smem;
   }
-  NT_CHECK(launch_k(kern, dim3(ceil_div(N, 32)), dim3(256), smem, x, w, b, y, M, K, N, act, pre, residual));
+  NT_CHECK(launch_k(kern, dim3(ceil_div(N, 4 * CL)), dim3(256), smem, x, w, b, y, M, K, N, act, pre, residual, ln_g, ln_b));
   NT_LAUNCH_OK();
   return 0;
+}
+
+// Columns per CTA shrink with N so that the weight panel is pulled by ~50-100 SMs instead of N/32 (12 for N = 384):
+// the decode-step GEMVs are latency-bound, not bandwidth-bound (1 x 1536 x 384: 8 us with 12 CTAs).
+template <int MR>
+static int linear_skinny_launch(const float* x, const float* w, const float* b, float* y, int M, int K, int N, int act,
+                                float* pre, const float* residual, const float* ln_g = nullptr, const float* ln_b = nullptr) {
+  if (N <= 768) return linear_skinny_launch_cl<MR, 2>(x, w, b, y, M, K, N, act, pre, residual, ln_g, ln_b);
+  if (N <= 1536) return linear_skinny_launch_cl<MR, 4>(x, w, b, y, M, K, N, act, pre, residual, ln_g, ln_b);
+  return linear_skinny_launch_cl<MR, 8>(x, w, b, y, M, K, N, act, pre, residual, ln_g, ln_b);
 }
 
 // M <= 8 and the row panel fits shared memory
@@ -162,6 +198,18 @@ int nt_linear_fwd(const float* x, const float* w, const float* b, float* y, int 
   }
   d.ep.bias = b; d.ep.act = act; d.ep.pre_out = pre; d.ep.addend = residual;
   return gemm_dispatch(d);
+}
+
+int nt_linear_ln_skinny(const float* x, const float* ln_g, const float* ln_b, const float* w, const float* b, float* y, int M,
+                        int K, int N, int act, const float* residual) {
+  NT_ENTRY();
+  NT_REQUIRE(M >= 1 && M <= 8 && K > 0 && N > 0 && ln_g && ln_b, "nt_linear_ln_skinny: needs 1..8 rows and the LayerNorm parameters (M=%d)", M);
+  NT_REQUIRE(act >= 0 && act <= 2, "nt_linear_ln_skinny: act %d", act);
+  NT_REQUIRE(linear_skinny_ok(M, K), "nt_linear_ln_skinny: K=%d does not fit the row panel", K);
+  if (M <= 1) return linear_skinny_launch<1>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
+  if (M <= 2) return linear_skinny_launch<2>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
+  if (M <= 4) return linear_skinny_launch<4>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
+  return linear_skinny_launch<8>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
 }
 
 int nt_linear_bwd_input(const float* dy, const float* w, float* dx, int M, int K, int N, int act,

@@ -11,6 +11,7 @@ full-window recomputation from there on — the same arithmetic the reference pe
 Layers are the drop-in objects of a GPT layer list (Position_Embedding, attdecoderblock_layer ..., layer_norm,
 classify_layer(relu=False)); parameters are shared with training, nothing is copied."""
 import ctypes
+import os
 
 import numpy as np
 
@@ -83,23 +84,43 @@ class KVGenerator:
         x = DeviceArray((B, 1, D), host_dtype=self.embed.text_embedding.host_dtype)
         lib.nt_decode_embed(self.d_tok.ptr, self.embed.text_embedding.params.ptr, self.embed.pos_embedding.params.ptr, x.ptr,
                             B, D, self.context, self.d_pos.ptr)       # token row + position row (PatchEmbed.py:132-138)
+        fused = B <= 8 and os.environ.get("NTB200_DECODE_FUSED", "1") != "0"
         for bi, blk in enumerate(self.blocks):
-            u = blk.norm._forward(x)
-            hdn = blk.fc0._forward(u, ops.ACT_RELU)
-            h = blk.fc1._forward(hdn, residual=x)
-            u1 = blk.norm1._forward(h)
-            qkv = blk.qkvfc._forward(u1)                           # [B,1,3D]
-            lib.nt_kv_append_at(qkv.ptr, self.k[bi].ptr, self.v[bi].ptr, B, self.context, D, self.d_pos.ptr)
+            if fused:       # LayerNorm inside the skinny GEMV, KV append inside the decode attention: 6 launches per block
+                hdn = self._ln_linear(x, blk.norm, blk.fc0, ops.ACT_RELU)
+                h = blk.fc1._forward(hdn, residual=x)
+                qkv = self._ln_linear(h, blk.norm1, blk.qkvfc)     # [B,1,3D]
+            else:
+                u = blk.norm._forward(x)
+                hdn = blk.fc0._forward(u, ops.ACT_RELU)
+                h = blk.fc1._forward(hdn, residual=x)
+                u1 = blk.norm1._forward(h)
+                qkv = blk.qkvfc._forward(u1)
+                lib.nt_kv_append_at(qkv.ptr, self.k[bi].ptr, self.v[bi].ptr, B, self.context, D, self.d_pos.ptr)
             att = DeviceArray((B, 1, D), host_dtype=x.host_dtype)
             lib.nt_attention_decode_at(qkv.ptr, self.k[bi].ptr, self.v[bi].ptr, att.ptr, B, self.context, blk.num_h,
-                                       D // blk.num_h, self.d_pos.ptr)
+                                       D // blk.num_h, self.d_pos.ptr, 1 if fused else 0)
             x = blk.fc_out._forward(att, residual=h)
-        z = self.final_norm._forward(x)
-        logits = self.head.forward(z)
+        if fused and not getattr(self.head, "reluact", False):
+            z1 = self._ln_linear(x, self.final_norm, self.head.fc0)
+            logits = self.head.fc1._forward(z1)
+        else:
+            z = self.final_norm._forward(x)
+            logits = self.head.forward(z)
         V = logits.size // B
         lib.nt_argmax_next(logits.ptr, V, V, B, self.d_tok.ptr, self.d_hist.ptr, self.context + 1, self.d_pos.ptr)
         lib.nt_increment(self.d_pos.ptr)
         self._logits = logits
+
+    @staticmethod
+    def _ln_linear(x, norm, fc, act=ops.ACT_NONE):
+        """fc(LayerNorm(x)) for the <= 8 rows of a decode step in one launch (nt_linear_ln_skinny)."""
+        K, N = fc.params.shape
+        M = x.size // K
+        y = DeviceArray(x.shape[:-1] + (N,), host_dtype=x.host_dtype)
+        lib.nt_linear_ln_skinny(x.ptr, norm.gamma.ptr, norm.beta.ptr, fc.params.ptr, fc.bias_params.ptr if fc.bias else None,
+                                y.ptr, M, K, N, act, None)
+        return y
 
     def _run_step(self):
         """Eager the first time, captured the second, replayed afterwards (same protocol as TrainStep.run_device)."""
@@ -128,7 +149,12 @@ class KVGenerator:
         assert self.k is not None and self.len < self.context, "prefill first / window is full"
         self.d_tok.set(np.asarray(token).astype(np.int32).reshape(-1))
         self._run_step()
-        return np.asarray(self._logits).reshape(self.d_tok.shape[0], -1)
+        return self._host_logits()
+
+    def _host_logits(self):
+        """[B, V]: a head padded by TrainStep (fclayer._pad_out) carries dummy classes with bias -1e30 behind the vocabulary."""
+        fc1 = self.head.fc1
+        return np.asarray(self._logits).reshape(self.d_tok.shape[0], -1)[:, :getattr(fc1, "_logical_out", fc1.outfeature)]
 
     def greedy_steps(self, first_token, n):
         """n cached steps with the arg-max taken on the device (np.argmax tie-break): no host round trip between tokens.
@@ -177,7 +203,7 @@ class KVGenerator:
                 for row, ts in zip(out, toks[:, :n - 1] if n > 1 else toks[:, :0]):
                     row.extend(int(t) for t in ts)
                 produced += n - 1
-                logits = np.asarray(self._logits).reshape(len(out), -1)
+                logits = self._host_logits()
             elif room > 0:
                 logits = self.step(nxt)
             else:                                                  # window full: it slides, every position index changes

@@ -277,3 +277,25 @@ def test_empty_batch_and_errors(nt):
         sm.backward(np.zeros((2, 3, 4)), np.zeros((2, 3, 4)))
     with pytest.raises(nt.NtError):
         nt.lib.nt_cross_entropy(None, None, None, 1.0, None, None, None, None, None, 0, 0)
+
+
+@pytest.mark.parametrize("M_,K,N", [(1, 384, 384), (2, 1536, 384), (4, 384, 1152), (5, 100, 10), (8, 384, 2350), (3, 67, 1537)])
+def test_skinny_linear_forward_and_layernorm_fusion(nt, M_, K, N):
+    """<= 8-row Linear forward (linear_skinny_kernel: every column-width variant, vector and scalar weight loads, bias /
+    activation / pre-activation / residual epilogue) and its LayerNorm-fused decode form nt_linear_ln_skinny, vs the oracle."""
+    from numpy_transformer_b200 import ops, DeviceArray
+    from numpy_transformer_b200._lib import lib
+    rs = np.random.RandomState(M_ + K + N)
+    x, W, b, res = rs.randn(M_, K), rs.randn(K, N) / np.sqrt(K), rs.randn(N), rs.randn(M_, N)
+    dx, dW, db, dres = (DeviceArray.from_host(a) for a in (x, W, b, res))
+    before = nt.launch_count()
+    y, pre = ops.linear_fwd(dx, dW, db, ops.ACT_GELU, want_pre=True, residual=dres)
+    assert nt.launch_count() - before == 1
+    ref_pre = R.linear_fwd(x, W, b)
+    assert rel_err(pre, ref_pre) < 1e-5 and rel_err(y, R.gelu_fwd(ref_pre) + res) < 1e-5
+    assert rel_err(ops.linear_fwd(dx, dW, None, ops.ACT_RELU), np.maximum(R.linear_fwd(x, W), 0)) < 1e-5
+    g, be = rs.randn(K) * 0.5 + 1, rs.randn(K) * 0.1
+    out, dg, dbe = DeviceArray((M_, N)), DeviceArray.from_host(g), DeviceArray.from_host(be)
+    lib.nt_linear_ln_skinny(dx.ptr, dg.ptr, dbe.ptr, dW.ptr, db.ptr, out.ptr, M_, K, N, ops.ACT_RELU, dres.ptr)
+    u = R.layernorm_fwd(x, g, be)[0]
+    assert rel_err(out, np.maximum(R.linear_fwd(u, W, b), 0) + res) < 1e-5
