@@ -78,7 +78,8 @@ def test_dropin_module_surface(nt):
     nt.install()
     import importlib
     for mod, names in [("net.fullconnect", ["fclayer"]), ("net.layernorm", ["layer_norm"]),
-                       ("net.activation", ["ReLU", "Softmax", "GELU"]), ("net.loss", ["cross_entropy_loss", "mean_square_loss"]),
+                       ("net.activation", ["ReLU", "sigmoid", "tanh", "SiLU", "Softmax", "GELU"]),
+                       ("net.loss", ["cross_entropy_loss", "binary_cross_entropy_logit_loss", "mean_square_loss"]),
                        ("net.flatten", ["flatten_layer"]), ("net.Embedding", ["Embedding_layer"]),
                        ("net.Convolution", ["convolution_layer"]), ("attention", ["attention_layer"]),
                        ("classify", ["classify_layer"]),
