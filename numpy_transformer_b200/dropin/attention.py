@@ -12,9 +12,10 @@ from net.activation import Softmax, GELU
 from numpy_transformer_b200.device import as_device
 from numpy_transformer_b200 import ops
 from numpy_transformer_b200 import fused_vit
+from numpy_transformer_b200.layer_arena import LayerArenaMixin
 
 
-class attention_layer():
+class attention_layer(LayerArenaMixin):
     def __init__(self, embed_dim, num_h):
         self.embed_dim = embed_dim
         self.num_h = num_h
@@ -64,10 +65,14 @@ class attention_layer():
         return [self.norm, self.qkvfc, self.norm1, self.fc0, self.fc1]
 
     def update(self, lr):
+        if self._arena_update(lr):                        # one kernel for the block's parameter tensors
+            return
         for c in (self.norm, self.norm1, self.qkvfc, self.fc0, self.fc1):
             c.update(lr)
 
     def setzero(self):
+        if self._arena_setzero():                         # one memset
+            return
         for c in self._children():
             c.setzero()
 

@@ -10,9 +10,10 @@ from net.fullconnect import fclayer
 from net.activation import Softmax, GELU, ReLU
 from numpy_transformer_b200.device import as_device
 from numpy_transformer_b200 import ops
+from numpy_transformer_b200.layer_arena import LayerArenaMixin
 
 
-class attdecoderblock_layer():
+class attdecoderblock_layer(LayerArenaMixin):
     def __init__(self, embed_dim, num_h, adam=False, float32=False, float16=False, return_attention=False):
         self.embed_dim = embed_dim
         self.num_h = num_h
@@ -75,10 +76,14 @@ class attdecoderblock_layer():
         return [self.norm, self.qkvfc, self.norm1, self.fc0, self.fc1, self.fc_out]
 
     def update(self, lr):
+        if self._arena_update(lr):                        # one kernel for the block's parameter tensors
+            return
         for c in (self.norm, self.norm1, self.qkvfc, self.fc0, self.fc1, self.fc_out):
             c.update(lr)
 
     def setzero(self):
+        if self._arena_setzero():                         # one memset
+            return
         for c in self._children():
             c.setzero()
 
