@@ -61,22 +61,47 @@ def launch_count():
 
 def set_gemm_mode(mode):
     lib.nt_set_gemm_mode(int(mode))
+    _state["gemm_mode"] = None
 
 
 def get_gemm_mode():
-    m = ctypes.c_int(0)
-    lib.nt_get_gemm_mode(ctypes.byref(m))
-    return m.value
+    """Cached: the engine choice of every Linear / attention call asks for it."""
+    if _state.get("gemm_mode") is None:
+        m = ctypes.c_int(0)
+        lib.nt_get_gemm_mode(ctypes.byref(m))
+        _state["gemm_mode"] = m.value
+    return _state["gemm_mode"]
+
+
+def _size_class(b):
+    """The pool's size classes (csrc/runtime.cu:size_class)."""
+    if b < 512:
+        return 512
+    if b < (1 << 20):
+        return (b + 511) & ~511
+    return (b + (1 << 16) - 1) & ~((1 << 16) - 1)
+
+
+# Free blocks by size class, kept on the Python side: the launch-bound shapes allocate ~70 small tensors per step, and
+# two ctypes round trips per tensor (nt_malloc / nt_free) cost more host time than the kernels they feed.  Same
+# stream-ordered reuse rule as the C pool behind it (every consumer runs on the library stream).
+_free_blocks = {}
+_CACHE_LIMIT = 64 << 20
 
 
 class _Buffer:
-    __slots__ = ("ptr", "nbytes")
+    __slots__ = ("ptr", "nbytes", "_cls")
 
     def __init__(self, nbytes):
         init()
-        p = ctypes.c_void_p()
-        lib.nt_malloc(ctypes.byref(p), max(int(nbytes), 4))
-        self.ptr = p.value
+        self._cls = _size_class(max(int(nbytes), 4))
+        cached = _free_blocks.get(self._cls)
+        if cached:
+            self.ptr = cached.pop()
+        else:
+            p = ctypes.c_void_p()
+            lib.nt_malloc(ctypes.byref(p), self._cls)
+            self.ptr = p.value
         self.nbytes = int(nbytes)
         if _state["keep"] is not None:          # graph capture: pin every buffer the graph will touch
             _state["keep"].append(self)
@@ -84,7 +109,10 @@ class _Buffer:
     def __del__(self):
         try:
             if self.ptr:
-                lib.nt_free(self.ptr)
+                if self._cls <= _CACHE_LIMIT:
+                    _free_blocks.setdefault(self._cls, []).append(self.ptr)
+                else:
+                    lib.nt_free(self.ptr)
         except Exception:
             pass
 
