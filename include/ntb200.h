@@ -82,7 +82,7 @@ int nt_linear_fwd(const float* x, const float* w, const float* b, float* y,
 /* fclayer.backward input half, net/fullconnect.py:114:  dx[M,K] = (dy[M,N] @ w[K,N]^T) * act'(pre[M,K]) + addend[M,K].
  * act' is GELU.backward (net/activation.py:144-148) or ReLU.backward (:16-17) of the layer that
  * PRODUCED x; pre / addend may be NULL. */
-/* Decode-step form (1..8 rows): y = act(LayerNorm(x; ln_g, ln_b) W + b) + residual in one launch (layernorm.py:100-114 followed
+/* Decode-step form (1..16 rows): y = act(LayerNorm(x; ln_g, ln_b) W + b) + residual in one launch (layernorm.py:100-114 followed
  * by fullconnect.py:99-106); nothing is saved for a backward. */
 int nt_linear_ln_skinny(const float* x, const float* ln_g, const float* ln_b, const float* w, const float* b, float* y, int M,
                         int K, int N, int act, const float* residual);

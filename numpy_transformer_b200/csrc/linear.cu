@@ -136,11 +136,12 @@ static int linear_skinny_launch(const float* x, const float* w, const float* b, 
   return linear_skinny_launch_cl<MR, 8>(x, w, b, y, M, K, N, act, pre, residual, ln_g, ln_b);
 }
 
-// M <= 8 and the row panel fits shared memory
+// M <= 16 (a decode step, the heads of tiny batches, the 10-row Linears of the gpt_character config) and the row panel
+// fits shared memory
 static bool linear_skinny_ok(int M, int K) {
   if (const char* e = getenv("NTB200_SKINNY")) if (e[0] == '0') return false;
-  const int mr = M <= 1 ? 1 : (M <= 2 ? 2 : (M <= 4 ? 4 : 8));
-  return M >= 1 && M <= 8 && sizeof(float) * ((size_t)mr * K + 4 + 32 * mr * 32) <= 200 * 1024;
+  const int mr = M <= 1 ? 1 : (M <= 2 ? 2 : (M <= 4 ? 4 : (M <= 8 ? 8 : 16)));
+  return M >= 1 && M <= 16 && sizeof(float) * ((size_t)mr * K + 4 + 32 * mr * 32) <= 200 * 1024;
 }
 
 int gemm_dispatch(const GemmDesc& d) {
@@ -167,7 +168,8 @@ int nt_linear_fwd(const float* x, const float* w, const float* b, float* y, int 
     if (M <= 1) return linear_skinny_launch<1>(x, w, b, y, M, K, N, act, pre, residual);
     if (M <= 2) return linear_skinny_launch<2>(x, w, b, y, M, K, N, act, pre, residual);
     if (M <= 4) return linear_skinny_launch<4>(x, w, b, y, M, K, N, act, pre, residual);
-    return linear_skinny_launch<8>(x, w, b, y, M, K, N, act, pre, residual);
+    if (M <= 8) return linear_skinny_launch<8>(x, w, b, y, M, K, N, act, pre, residual);
+    return linear_skinny_launch<16>(x, w, b, y, M, K, N, act, pre, residual);
   }
   GemmDesc d{};
   d.A = x; d.B = w; d.C = y;
@@ -203,13 +205,14 @@ int nt_linear_fwd(const float* x, const float* w, const float* b, float* y, int 
 int nt_linear_ln_skinny(const float* x, const float* ln_g, const float* ln_b, const float* w, const float* b, float* y, int M,
                         int K, int N, int act, const float* residual) {
   NT_ENTRY();
-  NT_REQUIRE(M >= 1 && M <= 8 && K > 0 && N > 0 && ln_g && ln_b, "nt_linear_ln_skinny: needs 1..8 rows and the LayerNorm parameters (M=%d)", M);
+  NT_REQUIRE(M >= 1 && M <= 16 && K > 0 && N > 0 && ln_g && ln_b, "nt_linear_ln_skinny: needs 1..16 rows and the LayerNorm parameters (M=%d)", M);
   NT_REQUIRE(act >= 0 && act <= 2, "nt_linear_ln_skinny: act %d", act);
   NT_REQUIRE(linear_skinny_ok(M, K), "nt_linear_ln_skinny: K=%d does not fit the row panel", K);
   if (M <= 1) return linear_skinny_launch<1>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
   if (M <= 2) return linear_skinny_launch<2>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
   if (M <= 4) return linear_skinny_launch<4>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
-  return linear_skinny_launch<8>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
+  if (M <= 8) return linear_skinny_launch<8>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
+  return linear_skinny_launch<16>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
 }
 
 int nt_linear_bwd_input(const float* dy, const float* w, float* dx, int M, int K, int N, int act,

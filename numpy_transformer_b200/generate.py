@@ -84,7 +84,7 @@ class KVGenerator:
         x = DeviceArray((B, 1, D), host_dtype=self.embed.text_embedding.host_dtype)
         lib.nt_decode_embed(self.d_tok.ptr, self.embed.text_embedding.params.ptr, self.embed.pos_embedding.params.ptr, x.ptr,
                             B, D, self.context, self.d_pos.ptr)       # token row + position row (PatchEmbed.py:132-138)
-        fused = B <= 8 and os.environ.get("NTB200_DECODE_FUSED", "1") != "0"
+        fused = B <= 16 and os.environ.get("NTB200_DECODE_FUSED", "1") != "0"
         for bi, blk in enumerate(self.blocks):
             if fused:       # LayerNorm inside the skinny GEMV, KV append inside the decode attention: 6 launches per block
                 hdn = self._ln_linear(x, blk.norm, blk.fc0, ops.ACT_RELU)

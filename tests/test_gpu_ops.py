@@ -279,9 +279,10 @@ def test_empty_batch_and_errors(nt):
         nt.lib.nt_cross_entropy(None, None, None, 1.0, None, None, None, None, None, 0, 0)
 
 
-@pytest.mark.parametrize("M_,K,N", [(1, 384, 384), (2, 1536, 384), (4, 384, 1152), (5, 100, 10), (8, 384, 2350), (3, 67, 1537)])
+@pytest.mark.parametrize("M_,K,N", [(1, 384, 384), (2, 1536, 384), (4, 384, 1152), (5, 100, 10), (8, 384, 2350), (3, 67, 1537),
+                                    (10, 192, 576), (16, 768, 192), (13, 960, 26)])
 def test_skinny_linear_forward_and_layernorm_fusion(nt, M_, K, N):
-    """<= 8-row Linear forward (linear_skinny_kernel: every column-width variant, vector and scalar weight loads, bias /
+    """<= 16-row Linear forward (linear_skinny_kernel: every column-width variant, vector and scalar weight loads, bias /
     activation / pre-activation / residual epilogue) and its LayerNorm-fused decode form nt_linear_ln_skinny, vs the oracle."""
     from numpy_transformer_b200 import ops, DeviceArray
     from numpy_transformer_b200._lib import lib
