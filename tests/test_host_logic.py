@@ -104,3 +104,23 @@ def test_sincos_table_matches_oracle(nt):
     from gpt.FixedEmbed import sincos_table
     from oracle.numpy_ref import posk_table
     assert np.array_equal(sincos_table(49, 96)[None], posk_table(49, 96))
+
+
+def test_python_block_cache_uses_the_pool_size_classes():
+    """device._size_class must mirror csrc/runtime.cu:size_class — blocks recycled on the Python side are handed out by
+    class, so a mismatch would hand a too-small block to a larger tensor."""
+    import re
+    from numpy_transformer_b200.device import _size_class
+    src = open(os.path.join(ROOT, "numpy_transformer_b200", "csrc", "runtime.cu")).read()
+    body = src[src.index("static size_t size_class(size_t b)"):]
+    body = body[:body.index("}") + 1]
+    assert re.search(r"b < 512\) return 512", body) and "(1u << 20)" in body and "(1u << 16)" in body and "511" in body
+
+    def c_size_class(b):                       # the C function, restated from the text checked above
+        if b < 512:
+            return 512
+        if b < (1 << 20):
+            return (b + 511) & ~511
+        return (b + (1 << 16) - 1) & ~((1 << 16) - 1)
+    for b in [1, 4, 511, 512, 513, 4096, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, 77 * 1024 * 1024 + 3]:
+        assert _size_class(b) == c_size_class(b) >= b
