@@ -3,16 +3,22 @@
 (forward + backward + update), B200 vs host NumPy.
 
   python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+  python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference's layers on the host CPU (rank 0 only)
 
 One "step" = forward of every layer + cross_entropy_loss + backward + update + setzero for one
 batch (transformer_of_image.py:141-159).  Workloads: vit_readme (default, the config the metric is
 quoted on: B=100/GPU, D=96, 6x4 heads), vit_scaled, gpt_poetry, gpt_scaled, gpt_char.
 Data parallel runs are weak-scaled: every rank processes a full per-GPU batch, gradients are
 all-reduced over NCCL, value = global units / max-over-ranks device time.
+
+The default workload's line also carries the other BASELINE.json configs (`other_configs`: vit_scaled, gpt_scaled,
+gpt_poetry at the same N, fewer steps) so that the driver's scaling record holds the north-star configs too, and —
+at N=1 — `e2e_layer_api`: the reference's own per-layer loop (host arrays in, host loss / argmax out every step)
+through the drop-in classes, i.e. what an UNCHANGED trainer script gets.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -33,6 +39,7 @@ WORKLOADS = {
     "gpt_char": ("gpt", dict(batch=2, context=5, embed_dim=192, heads=3, blocks=1, vocab=26, lr=3e-3, adam=True)),
 }
 METRIC = "train images/s (ViT-MNIST fwd+bwd+update)"
+GPT_METRIC = "train sequences/s (GPT fwd+bwd+update)"
 
 
 def peaks():
@@ -45,7 +52,9 @@ def peaks():
 
 
 def step_flops(kind, c):
-    """Algorithmic FLOPs per step (GEMM + attention, bwd = 2x fwd), SURVEY.md §8(d)."""
+    """Algorithmic FLOPs per step (GEMM + attention, bwd = 2x fwd), SURVEY.md §8(d).  Includes the first layer's dX
+    (2*M*P*D for the ViT patch embedding: 0.1 % of the step), which the reference computes and TrainStep skips because
+    nothing consumes the patch-space gradient (trainer.py `want_dx=False`)."""
     D, H, L, B = c["embed_dim"], c["heads"], c["blocks"], c["batch"]
     if kind == "vit":
         N, P, C = 49, 16, 10
@@ -89,12 +98,13 @@ class ClockSampler(threading.Thread):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         smmax = max([int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()] or [0])
+        pw = [float(r[3]) for r in self.rows if len(r) > 3 and r[3].replace(".", "", 1).isdigit()]
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=smmax or None, reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), power_w_max=max(pw) if pw else None)
 
 
 def op_cost(name, a, kind, c):
-    """(flops, bytes) of one profiled C-ABI op from its integer arguments."""
+    """(flops, bytes) of one profiled C-ABI op from its integer / float arguments (pointers are dropped by the profiler)."""
     if name in ("nt_linear_fwd", "nt_linear_bwd_input", "nt_linear_bwd_params"):
         M, K, N = a[0], a[1], a[2]
         return 2.0 * M * K * N, 4.0 * (M * K + K * N + M * N)
@@ -110,25 +120,27 @@ def op_cost(name, a, kind, c):
     if name == "nt_split_bf16_both":
         rows, cols = a[0], a[1]
         return 0.0, 12.0 * rows * cols                      # read fp32 once, write both layouts
-    if name in ("nt_vit_blocks_fwd", "nt_vit_blocks_bwd"):
-        # fused ViT block stack: L blocks x B images; per image and block the three Linear layers (7 D^2 weights)
-        # and the attention core (QK^T and PV over N tokens); backward = 2x forward
-        L, B, N, D, H = a[-5:]
+    if name.startswith("nt_vit_blocks_fwd") or name.startswith("nt_vit_blocks_bwd") or name.startswith("nt_vit_tc_"):
+        # fused ViT block stack: int arguments are (nblocks, B, N, D, H[, ...]).  Per image and block the three Linear
+        # layers (7 D^2 weights) and the attention core (QK^T and PV over N tokens); backward = 2x forward
+        L, B, N, D, H = a[0:5]
         fwd = L * B * (2.0 * N * 7 * D * D + 4.0 * N * N * D)
         act = 4.0 * L * B * N * (3 * D + H * N + D + 2 * D + D)      # qkv, P, h, dgelu, out
-        return (fwd, act) if name.endswith("fwd") else (2.0 * fwd, act)
-    if name == "nt_attention_fwd":
-        B, N, H, dh = a[-4:]
+        return (fwd, act) if "fwd" in name else (2.0 * fwd, act)
+    if name in ("nt_attention_fwd", "nt_attention_fwd_split"):
+        # ints: (mask_kind, B, N, H, dh)
+        B, N, H, dh = a[1:5]
         return 4.0 * B * H * N * N * dh, 4.0 * (4 * B * N * H * dh + B * H * N * N)
-    if name == "nt_attention_bwd":
-        B, N, H, dh = a[-5:-1]                  # trailing int is the mask kind
+    if name in ("nt_attention_bwd", "nt_attention_bwd_split"):
+        # ints: (B, N, H, dh, mask_kind)
+        B, N, H, dh = a[0:4]
         return 8.0 * B * H * N * N * dh, 4.0 * (7 * B * N * H * dh + B * H * N * N)
-    if name == "nt_layernorm_fwd":
+    if name in ("nt_layernorm_fwd", "nt_layernorm_fwd_split"):
         M, D = a[0], a[1]
-        return 0.0, 8.0 * M * D
-    if name == "nt_layernorm_bwd":
+        return 0.0, (8.0 if name.endswith("fwd") else 12.0) * M * D
+    if name in ("nt_layernorm_bwd", "nt_layernorm_bwd_split"):
         M, D = a[0], a[1]
-        return 0.0, 16.0 * M * D
+        return 0.0, (16.0 if name.endswith("bwd") else 20.0) * M * D
     if name == "nt_cross_entropy":
         r, cc = a[-2], a[-1]
         return 0.0, 12.0 * r * cc
@@ -139,53 +151,53 @@ def op_cost(name, a, kind, c):
     return 0.0, 0.0
 
 
-def run_ours(args):
-    import numpy_transformer_b200 as nt
-    from numpy_transformer_b200 import trainer
-    from numpy_transformer_b200.parallel import DataParallel
-
-    kind, c = WORKLOADS[args.workload]
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with: python -m torch.distributed.run --nproc-per-node %d bench.py --gpus %d ..." % (args.gpus, args.gpus))
-    dp = DataParallel(rank, world) if world > 1 else None
-    nt.init(local)
-    if args.gemm_mode is not None:
-        nt.set_gemm_mode(args.gemm_mode)
-    if dp:
-        dp.init_nccl()
+def synthetic(kind, c, rank):
+    rs = np.random.RandomState(1 + rank)
     B = c["batch"]
-    chains = args.chains if args.chains is not None else 1
     if kind == "vit":
-        reps = [trainer.build_vit_layers(B // chains, embed_dim=c["embed_dim"], heads=c["heads"], blocks=c["blocks"], seed=0)
-                for _ in range(chains)]
-        layers = reps[0]
-        rs = np.random.RandomState(1 + rank)
-        inputs = rs.rand(B, 1, 28, 28)
-        labels = rs.randint(0, 10, B)
-        units, unit = B, "images/s"
-    else:
-        reps = [trainer.build_gpt_layers(B // chains, c["context"], c["embed_dim"], c["heads"], c["blocks"], c["vocab"], adam=True, seed=0)
-                for _ in range(chains)]
-        layers = reps[0]
-        rs = np.random.RandomState(1 + rank)
-        inputs = rs.randint(0, c["vocab"], (B, c["context"]))
-        labels = rs.randint(0, c["vocab"], (B, c["context"]))
-        units, unit = B, "sequences/s"
-    ts = trainer.TrainStep(layers, kind, inputs.shape, lr=c["lr"], adam=c["adam"], dp=dp, grad_buckets=args.buckets,
-                           replicas=reps[1:])
+        return rs.rand(B, 1, 28, 28), rs.randint(0, 10, B), "images/s"
+    return rs.randint(0, c["vocab"], (B, c["context"])), rs.randint(0, c["vocab"], (B, c["context"])), "sequences/s"
 
-    W = max(3, args.warmup)
-    K = args.steps
+
+def build_step(workload, dp, buckets=1):
+    from numpy_transformer_b200 import trainer
+    kind, c = WORKLOADS[workload]
+    B = c["batch"]
+    if kind == "vit":
+        layers = trainer.build_vit_layers(B, embed_dim=c["embed_dim"], heads=c["heads"], blocks=c["blocks"], seed=0)
+    else:
+        layers = trainer.build_gpt_layers(B, c["context"], c["embed_dim"], c["heads"], c["blocks"], c["vocab"], adam=True, seed=0)
+    rank = dp.rank if dp else 0
+    inputs, labels, unit = synthetic(kind, c, rank)
+    ts = trainer.TrainStep(layers, kind, inputs.shape, lr=c["lr"], adam=c["adam"], dp=dp, grad_buckets=buckets)
+    return ts, layers, inputs, labels, unit
+
+
+def measure(workload, dp, K, W, full, local, buckets=1, min_region_s=0.6):
+    """Device-timed steps (inputs resident, L2 flushed between steps) and end-to-end steps (pinned host batch in, host
+    loss out) of one workload.  The K-step timed region is repeated `rounds` times so that it lasts >= min_region_s and
+    the 100 ms clock sampler sees the GPU under load; every round is K real training steps, all rounds count."""
+    import ctypes
+    import numpy_transformer_b200 as nt
+    from numpy_transformer_b200._lib import lib
+    kind, c = WORKLOADS[workload]
+    world = dp.world if dp else 1
+    rank = dp.rank if dp else 0
+    ts, layers, inputs, labels, unit = build_step(workload, dp, buckets)
+    B = c["batch"]
     for _ in range(W):
         ts.step(inputs, labels)
-    from numpy_transformer_b200._lib import lib
-    import ctypes
+    # estimate the step time to size the number of rounds
+    lib.nt_sync()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ts.run_device()
+    lib.nt_sync()
+    est = max((time.perf_counter() - t0) / 3, 1e-5)
+    rounds = int(min(400, max(1, math.ceil(min_region_s / (K * est)))))
+    if dp:
+        rounds = int(dp.max_over_ranks(rounds))
 
-    # ---------------- device-timed region: inputs resident in HBM, L2 flushed between timed steps
     ev = []
     for _ in range(2 * K):
         e = ctypes.c_void_p()
@@ -197,48 +209,68 @@ def run_ours(args):
         dp.barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    time.sleep(0.15)
     launches0 = nt.launch_count()
-    t_wall0 = time.perf_counter()
-    for i in range(K):
-        lib.nt_flush_l2()
-        lib.nt_event_record(ev[2 * i])
-        ts.run_device()
-        lib.nt_event_record(ev[2 * i + 1])
-    lib.nt_sync()
-    t_wall = time.perf_counter() - t_wall0
+    ms = ctypes.c_float(0)
+    dev_s, per_round = 0.0, []
+    for r in range(rounds):
+        for i in range(K):
+            lib.nt_flush_l2()
+            lib.nt_event_record(ev[2 * i])
+            ts.run_device()
+            lib.nt_event_record(ev[2 * i + 1])
+        lib.nt_sync()
+        tot = 0.0
+        for i in range(K):
+            lib.nt_event_elapsed_ms(ev[2 * i], ev[2 * i + 1], ctypes.byref(ms))
+            tot += ms.value
+        per_round.append(tot / K)
+        dev_s += tot / 1e3
     launches = nt.launch_count() - launches0
     if dp:
         dp.barrier()
-    ms = ctypes.c_float(0)
-    per_step = []
-    for i in range(K):
-        lib.nt_event_elapsed_ms(ev[2 * i], ev[2 * i + 1], ctypes.byref(ms))
-        per_step.append(ms.value)
-    dev_s = sum(per_step) / 1e3
     dev_s_max = dp.max_over_ranks(dev_s) if dp else dev_s
-    value = units * world * K / dev_s_max
+    n_steps = K * rounds
+    value = B * world * n_steps / dev_s_max
 
     # ---------------- end-to-end through the public call: pinned host batch in, host loss out
     lib.nt_sync()
     if dp:
         dp.barrier()
-    # the synthetic batch sits in the step's pinned staging buffers (a loader with pinned output buffers); every
-    # timed step copies it host -> device from there, runs the step and reads the loss back
     ts.h_in.array[...] = np.asarray(inputs).reshape(ts.input_shape)
     ts.h_lab.array[...] = np.asarray(labels).reshape(-1)
     t0 = time.perf_counter()
-    for _ in range(K):
+    for _ in range(n_steps):
         loss = ts.step()
     e2e_s = time.perf_counter() - t0
     e2e_s_max = dp.max_over_ranks(e2e_s) if dp else e2e_s
     clocks = sampler.stop()
-    e2e = dict(value=units * world * K / e2e_s_max, unit=unit, h2d_bytes_per_step=ts.h2d_bytes, d2h_bytes_per_step=4 * chains,
-               timing="host wall clock around K public TrainStep.step() calls (batch in pinned host memory -> H2D -> step -> D2H loss), max over ranks")
-
-    # ---------------- roofline of the dominant kernel: the same step captured with a CUDA-event pair around every op
-    # (event-record graph nodes), replayed; durations are device times with no host gaps between ops
+    e2e = dict(value=B * world * n_steps / e2e_s_max, unit=unit, h2d_bytes_per_step=ts.h2d_bytes, d2h_bytes_per_step=4,
+               timing="host wall clock around %d public TrainStep.step() calls (batch in pinned host memory -> H2D -> step -> "
+                      "D2H loss), max over ranks" % n_steps)
+    res = dict(workload=workload, kind=kind, unit=unit, value=value, ms_per_step=dev_s_max / n_steps * 1e3, rounds=rounds,
+               ms_per_step_round_min=min(per_round), ms_per_step_round_max=max(per_round),
+               e2e=e2e, clocks=clocks, launches=int(launches), loss=loss, graph_kernels=ts.graph_kernels,
+               params=ts.arena.n_params, gemm_mode=nt.get_gemm_mode())
+    fl_step = step_flops(kind, c)
+    step_tf = fl_step * world / (dev_s_max / n_steps) / 1e12
     pk = peaks()
-    prof_steps = 5
+    res["step_roofline"] = {"flops_per_step": fl_step, "achieved_tflops": step_tf,
+                            "frac_of_bf16_sustained": step_tf / (pk["tf_sustained"] * world),
+                            "note": "algorithmic GEMM + attention FLOPs incl. the first layer's dX (0.1 %), which TrainStep skips"}
+    if full:
+        res.update(profile_ops(ts, dp, kind, c, workload))
+    ts.close()
+    del ts, layers
+    return res
+
+
+def profile_ops(ts, dp, kind, c, workload, prof_steps=5):
+    """Roofline of the dominant kernel: the same step captured with a CUDA-event pair around every C-ABI op
+    (event-record graph nodes), replayed; durations are device times with no host gaps between ops.  The profiled graph
+    is SERIAL (no side branch, events between ops), so its ops add up to more than the overlapped step."""
+    from numpy_transformer_b200._lib import lib
+    pk = peaks()
     pg, precs = ts.capture_profiled()
     recs = []
     for _ in range(prof_steps):
@@ -251,8 +283,7 @@ def run_ours(args):
     ts.steps_done += prof_steps
     agg = {}
     for name, a, ms_ in recs:
-        key = (name, a)
-        r = agg.setdefault(key, [0.0, 0])
+        r = agg.setdefault((name, a), [0.0, 0])
         r[0] += ms_
         r[1] += 1
     total_ms = sum(v[0] for v in agg.values())
@@ -265,158 +296,353 @@ def run_ours(args):
         cl["flops"] += fl * n
         cl["bytes"] += by * n
     # the dominant KERNEL: waits on the collective (nt_dp_*) stay in the op table but are not a kernel of this repo
-    top = max(((k, v) for k, v in classes.items() if not k.startswith("nt_dp_")), key=lambda kv: kv[1]["ms"])
-    tname, tc = top
+    tname, tc = max(((k, v) for k, v in classes.items() if not k.startswith("nt_dp_")), key=lambda kv: kv[1]["ms"])
     if tc["flops"] > 0:
         ach = tc["flops"] / (tc["ms"] / 1e3) / 1e12
         roof = dict(bound="tensor", kernel=tname, achieved=ach, peak=pk["tf_burst"], unit="TFLOP/s", frac=ach / pk["tf_burst"],
                     traffic=None, share_of_step=tc["ms"] / total_ms, launches_per_step=tc["n"] / prof_steps,
-                    peak_source=pk["source"] + " bf16 burst")
+                    avg_launch_ms=tc["ms"] / tc["n"], peak_source=pk["source"] + " bf16 burst (of measured)")
     else:
         ach = tc["bytes"] / (tc["ms"] / 1e3) / 1e9
         roof = dict(bound="hbm", kernel=tname, achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
                     traffic=None, share_of_step=tc["ms"] / total_ms, launches_per_step=tc["n"] / prof_steps,
-                    peak_source=pk["source"] + " copy")
-    # traffic: DRAM bytes of the dominant op from the committed ncu capture (null when none was taken for this workload)
-    try:
-        roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload, {}).get(tname)
+                    avg_launch_ms=tc["ms"] / tc["n"], peak_source=pk["source"] + " copy (of measured)")
+    try:    # DRAM bytes per launch of the dominant op from the committed ncu capture (null when none was taken)
+        roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(workload, {}).get(tname)
     except Exception:
         pass
-    if tname.startswith("nt_vit_blocks"):
-        # the fused blocks execute every product as three BF16 MMA passes on 64 padded rows per 49-token image
-        roof["executed_mma_tflops"] = ach * 3.0 * 64.0 / 49.0
-        roof["note"] = ("algorithmic FLOPs / measured time vs the dense BF16 tcgen05 peak; the kernel issues 3 BF16 mma.sync passes "
-                        "per product (fp32-class accuracy) on 64/49 padded rows with one image per CTA (B of 148 SMs busy); the "
-                        "legacy mma.sync path peaks at 556 TFLOP/s chip-wide (tools/mma_red_bench.cu)")
-    fl_step = step_flops(kind, c)
-    step_tf = fl_step * world / (dev_s_max / K) / 1e12
-    op_table = sorted(((n, round(v["ms"] / prof_steps, 4), v["n"] // prof_steps,
-                        round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 3), round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 2))
-                       for n, v in classes.items()), key=lambda r: -r[1])
+    if "vit_blocks" in tname or "vit_tc" in tname:
+        roof["executed_mma_tflops"] = ach * 3.0
+        roof["note"] = ("algorithmic FLOPs / measured time vs the dense BF16 peak; every product is issued as 3 BF16 MMA passes "
+                        "(hi*hi + hi*lo + lo*hi, fp32-class accuracy) on token tiles padded 49 -> 64 rows")
+    table = sorted(((n, round(v["ms"] / prof_steps, 4), v["n"] // prof_steps,
+                     round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 3), round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 2))
+                    for n, v in classes.items()), key=lambda r: -r[1])
+    lib.nt_graph_destroy(pg)
+    return {"roofline": roof,
+            "op_table(name, ms/step, launches/step, TFLOP/s algorithmic, GB/s algorithmic)": table[:14],
+            "op_table_serial_sum_ms": total_ms / prof_steps}
 
+
+def layer_api_e2e(n_steps=60, warm=8):
+    """transformer_of_image.py:141-159 verbatim on the drop-in classes (README shape): per-layer forward from a host
+    fp64 batch, cross_entropy_loss against host one-hot labels, np.argmax on the returned probabilities, per-layer
+    backward / update / setzero, loss read on the host every step."""
+    import numpy_transformer_b200 as nt
+    from numpy_transformer_b200 import trainer
+    nt.install()
+    from net.loss import cross_entropy_loss
+    from classify import classify_layer
+    c = WORKLOADS["vit_readme"][1]
+    B = c["batch"]
+    layers = trainer.build_vit_layers(B, seed=0)
+    rs = np.random.RandomState(1)
+    images0 = rs.rand(B, 28, 28)
+    lab = rs.randint(0, 10, B)
+    label = np.zeros((B, 10))
+    label[np.arange(B), lab] = 1
+    lr, cls_token = c["lr"], 0
+
+    def step():
+        images = images0[:, np.newaxis, :, :]
+        for l in range(len(layers)):
+            if isinstance(layers[l], classify_layer):
+                images = layers[l].forward(images[:, 0]) if cls_token else layers[l].forward(images)
+            else:
+                images = layers[l].forward(images)
+        loss, delta, predict = cross_entropy_loss(images, label)
+        p = np.argmax(predict, axis=-1)
+        precision = np.sum(lab == p) / len(lab)
+        text = "loss: {:.6f}, precision: {:.6f}".format(loss, precision)       # the scripts format both every step
+        for l in range(len(layers) - 1, -1, -1):
+            delta = layers[l].backward(delta)
+            layers[l].update(lr)
+            layers[l].setzero()
+        return text
+
+    for _ in range(warm):
+        step()
+    nt.synchronize()
+    c0 = nt.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        step()
+    nt.synchronize()
+    dt = (time.perf_counter() - t0) / n_steps
+    return dict(value=B / dt, unit="images/s", ms_per_step=dt * 1e3, h2d_bytes_per_step=int(images0.size * 4 + label.size * 4),
+                d2h_bytes_per_step=int(4 + B * 10 * 4), launches_per_step=(nt.launch_count() - c0) // n_steps,
+                what="the reference's per-layer loop (transformer_of_image.py:141-159) on the drop-in classes: host batch in, "
+                     "host loss + argmax out every step, eager launches")
+
+
+def run_ours(args):
+    import numpy_transformer_b200 as nt
+    from numpy_transformer_b200.parallel import DataParallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with: python -m torch.distributed.run --nproc-per-node %d bench.py --gpus %d ..." % (args.gpus, args.gpus))
+    dp = DataParallel(rank, world) if world > 1 else None
+    nt.init(local)
+    if args.gemm_mode is not None:
+        nt.set_gemm_mode(args.gemm_mode)
+    if dp:
+        dp.init_nccl()
+    W, K = max(3, args.warmup), max(1, args.steps)
+    kind, c = WORKLOADS[args.workload]
+    m = measure(args.workload, dp, K, W, True, local, args.buckets)
     out = None
     if rank == 0:
         out = {
-            "metric": METRIC if kind == "vit" else "train sequences/s (GPT fwd+bwd+update)",
-            "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_s_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC if kind == "vit" else GPT_METRIC,
+            "value": m["value"], "unit": m["unit"], "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": B * world, **{k: v for k, v in c.items() if k not in ("batch",)},
-                       "parallelism": "dp%d" % world, "micro_batch_chains_per_gpu": chains, "gemm_mode": nt.get_gemm_mode(),
+            "config": {"workload": args.workload, "per_gpu_batch": c["batch"], "global_batch": c["batch"] * world,
+                       **{k: v for k, v in c.items() if k != "batch"}, "parallelism": "dp%d" % world,
+                       "gemm_mode": m["gemm_mode"], "timed_rounds_of_K_steps": m["rounds"],
+                       "ms_per_step_round_min_max": [m["ms_per_step_round_min"], m["ms_per_step_round_max"]],
                        "l2": "256 MB memset between timed steps (working set is L2-resident)",
-                       "graph_kernels_per_step": ts.graph_kernels, "params": ts.arena.n_params},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof,
-            "step_roofline": {"flops_per_step": fl_step, "achieved_tflops": step_tf, "frac_of_bf16_sustained": step_tf / (pk["tf_sustained"] * world)},
-            "op_table_ms_per_step(name,ms,launches,GFLOP/s,GB/s)": op_table[:12],
-            "loss": loss,
+                       "graph_kernels_per_step": m["graph_kernels"], "params": m["params"]},
+            "clocks": m["clocks"], "e2e": m["e2e"], "gpu_launches": m["launches"],
+            "roofline": m["roofline"], "step_roofline": m["step_roofline"],
+            "op_table(name, ms/step, launches/step, TFLOP/s algorithmic, GB/s algorithmic)":
+                m["op_table(name, ms/step, launches/step, TFLOP/s algorithmic, GB/s algorithmic)"],
+            "op_table_note": "per-op times come from a SERIAL profiled replay (no side branch; event nodes between ops): they sum to "
+                             "%.4f ms against the %.4f ms of the overlapped step" % (m["op_table_serial_sum_ms"], m["ms_per_step"]),
+            "loss": m["loss"],
         }
-        if world == 1 and not args.no_cpu:
+    # the other BASELINE.json configs at the same N (short runs; the north star's scaling target is on the scaled ones)
+    if args.workload == "vit_readme" and not args.no_extra:
+        others = {}
+        for wl in ("vit_scaled", "gpt_scaled", "gpt_poetry"):
+            try:
+                r = measure(wl, dp, max(2, min(K, 5)), 3, False, local, args.buckets, min_region_s=0.3)
+                others[wl] = {"metric": METRIC if r["kind"] == "vit" else GPT_METRIC, "value": r["value"], "unit": r["unit"],
+                              "ms_per_step": r["ms_per_step"], "n_gpus": world, "per_gpu_batch": WORKLOADS[wl][1]["batch"],
+                              "e2e": {k: r["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                              "clocks": r["clocks"], "achieved_tflops": r["step_roofline"]["achieved_tflops"],
+                              "frac_of_bf16_sustained": r["step_roofline"]["frac_of_bf16_sustained"], "loss": r["loss"],
+                              "gpu_launches": r["launches"]}
+            except Exception as e:        # a secondary config must not take the headline line down
+                others[wl] = {"error": "%s: %s" % (type(e).__name__, e)}
+        if rank == 0:
+            out["other_configs"] = others
+    if world == 1 and rank == 0:
+        if args.workload == "vit_readme" and not args.no_extra:
+            out["e2e_layer_api"] = layer_api_e2e()
+        if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
-    lib.nt_graph_destroy(pg)
-    ts.close()
     if dp:
         dp.shutdown()
     return out
 
 
-def cpu_baseline(workload, budget_s=20.0, refstruct_too=True):
-    """Oracle port of the reference step timed on this host (all BLAS threads NumPy uses)."""
-    from oracle import models as M
-    kind, c = WORKLOADS[workload]
+# ====================================================================================================== CPU arms
+def _blas_threads():
+    """Use every host core (torchrun exports OMP_NUM_THREADS=1, which would pin the BLAS to one thread)."""
+    n = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
-        cores = max([i.get("num_threads", 1) for i in threadpool_info()] or [os.cpu_count()])
+        from threadpoolctl import threadpool_limits, threadpool_info
+        threadpool_limits(limits=n)
+        return max([i.get("num_threads", 1) for i in threadpool_info()] or [n])
     except Exception:
-        cores = os.cpu_count()
-    if kind != "vit":
-        return cpu_baseline_gpt(workload, budget_s, cores)
-    B = min(c["batch"], 100)
-    cfg = M.ViTConfig(batch=B, embed_dim=c["embed_dim"], heads=c["heads"], blocks=c["blocks"])
-    params = M.vit_init(cfg, 0)
-    images, labels, onehot = M.synthetic_vit_batch(cfg, 1)
-    M.vit_step(params, images, onehot, c["lr"], cfg)
-    n, t0 = 0, time.perf_counter()
-    while True:
-        out = M.vit_step(params, images, onehot, c["lr"], cfg)
-        params = out["params"]
-        n += 1
-        if time.perf_counter() - t0 > budget_s * 0.5 or n >= 20:
-            break
-    fast = B * n / (time.perf_counter() - t0)
-    res = dict(value=fast, unit="images/s", cores=cores, kind="port",
-               sample="%d steps of batch %d of %s (closed-form softmax backward, vectorised over batch x heads)" % (n, B, workload))
-    if refstruct_too:
-        Bs = min(B, 20)
-        cfg2 = M.ViTConfig(batch=Bs, embed_dim=c["embed_dim"], heads=c["heads"], blocks=c["blocks"])
-        im2, _, oh2 = M.synthetic_vit_batch(cfg2, 1)
-        p2 = M.vit_init(cfg2, 0)
-        t0 = time.perf_counter()
-        M.vit_step(p2, im2, oh2, c["lr"], cfg2, refstruct=True)
-        res["reference_structured"] = dict(value=Bs / (time.perf_counter() - t0), unit="images/s",
-                                           sample="1 step of batch %d with the reference's per-sample/per-head loops and per-row softmax Jacobian (no ThreadPool churn)" % Bs)
+        return n
+
+
+class ReferenceModel:
+    """The UNMODIFIED reference's layer objects (oracle/_ref/tree, a byte-identical copy made by build()) driven exactly
+    like its trainers drive them.  depathologise=True swaps Softmax.backward (net/activation.py:93-129: a ThreadPool is
+    created and an N x N Jacobian materialised per row, 83 % of the reference's step) for the closed form — a LABELLED
+    variant, not the reference."""
+
+    def __init__(self, workload, batch, depathologise=False):
+        from oracle import ref_tree
+        if not ref_tree.available():
+            raise RuntimeError("oracle/_ref/tree is missing (run __graft_entry__.build() in the build container)")
+        for p in (ref_tree.MPL_STUB, os.path.join(ref_tree.TREE, "gpt"), ref_tree.TREE):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        for m in [m for m in sys.modules if m.split(".")[0] in ("net", "gpt", "attention", "classify", "PatchEmbed",
+                                                                 "Position_add", "attdecoderblock")]:
+            del sys.modules[m]
+        if not hasattr(np.lib, "pad"):
+            np.lib.pad = np.pad
+        from net.loss import cross_entropy_loss
+        from net.layernorm import layer_norm
+        from net.flatten import flatten_layer
+        import net.activation as act
+        if depathologise:
+            def closed_form(self, delta, out):
+                return out * (delta - np.sum(delta * out, axis=-1, keepdims=True))
+            act.Softmax.backward = closed_form
+        self.kind, c = WORKLOADS[workload]
+        self.c, self.B, self.ce = c, batch, cross_entropy_loss
+        np.random.seed(0)
+        D, H, L = c["embed_dim"], c["heads"], c["blocks"]
+        rs = np.random.RandomState(1)
+        if self.kind == "vit":
+            from PatchEmbed import PatchEmbed_flatten
+            from Position_add import Position_learnable
+            from attention import attention_layer
+            from classify import classify_layer
+            self.layers = [PatchEmbed_flatten(D, (batch, 1, 28, 28), 7, patchnorm=True), Position_learnable(7, D, fixed=1)]
+            self.layers += [attention_layer(D, H) for _ in range(L)]
+            self.layers += [layer_norm(D), flatten_layer(), classify_layer(D, batch, 7, 10, 0)]
+            self.x = rs.rand(batch, 1, 28, 28)
+            lab = rs.randint(0, 10, batch)
+            self.onehot = np.zeros((batch, 10))
+            self.onehot[np.arange(batch), lab] = 1
+            self.block_t, self.mask = (), None
+        else:
+            from PatchEmbed import Position_Embedding
+            from attdecoderblock import attdecoderblock_layer
+            from gpt.classify_gpt import classify_layer
+            T, V = c["context"], c["vocab"]
+            kw = dict(adam=True, float32=True, float16=False)
+            self.layers = [Position_Embedding(T, V, D, **kw)] + [attdecoderblock_layer(D, H, **kw) for _ in range(L)]
+            self.layers += [layer_norm(D, **kw), classify_layer(D, batch, 1, V, cls_token=False, relu=False, **kw)]
+            self.x = rs.randint(0, V, (batch, T))
+            self.lab = rs.randint(0, V, (batch, T))
+            self.block_t = attdecoderblock_layer
+            m = np.tril(np.ones((T, T)))
+            m[m == 0] = -np.inf
+            m[m == 1] = 0
+            self.mask = m
+
+    def step(self):
+        layers, lr = self.layers, self.c["lr"]
+        x = self.x
+        for l in layers:
+            x = l.forward(x, self.mask) if self.block_t and isinstance(l, self.block_t) else l.forward(x)
+        if self.kind == "vit":
+            loss, delta, predict = self.ce(x, self.onehot)
+        else:
+            ishape = x.shape
+            flat = np.reshape(x, (-1, self.c["vocab"]))
+            labels = np.zeros_like(flat)
+            labels[np.arange(len(flat)), self.lab.reshape(-1)] = 1
+            loss, delta, predict = self.ce(flat, labels)
+            delta = np.reshape(delta, ishape)
+        np.argmax(predict, axis=-1)
+        for l in range(len(layers) - 1, -1, -1):
+            delta = layers[l].backward(delta)
+            layers[l].update(lr)
+            layers[l].setzero()
+        return float(loss)
+
+
+# seconds of reference CPU time per unit, used only to SIZE the bounded sample (survey-time probe: 6.8 img/s, ~130 tok/s)
+_REF_UNIT_S = {"vit_readme": 0.15, "vit_scaled": 1.6, "gpt_poetry": 2.0, "gpt_scaled": 12.0, "gpt_char": 0.05}
+
+
+def _time_model(model, warm, steps):
+    for _ in range(warm):
+        model.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = model.step()
+    return (time.perf_counter() - t0) / steps, loss
+
+
+def cpu_baseline(workload, budget_s=25.0):
+    """Reported baseline (not the target): the unmodified reference on a bounded sample of the workload, on this host's
+    cores, plus two labelled extras — the same layers with Softmax.backward in closed form, and the oracle port."""
+    cores = _blas_threads()
+    kind, c = WORKLOADS[workload]
+    unit = "images/s" if kind == "vit" else "sequences/s"
+    b = int(max(1, min(c["batch"], (0.4 * budget_s / 3) / _REF_UNIT_S[workload])))
+    res = None
+    try:
+        dt, _ = _time_model(ReferenceModel(workload, b), 1, 2)
+        res = dict(value=b / dt, unit=unit, cores=cores, kind="reference",
+                   sample="2 timed steps (1 warm-up) of batch %d of %s through the UNMODIFIED reference layers (oracle/_ref/tree), "
+                          "os.cpu_count()=%d, BLAS threads=%d, NumPy %s" % (b, workload, os.cpu_count(), cores, np.__version__))
+        b2 = int(min(c["batch"], max(b, 4 * b)))
+        dt2, _ = _time_model(ReferenceModel(workload, b2, depathologise=True), 1, 2)
+        res["reference_depathologised"] = dict(value=b2 / dt2, unit=unit,
+                                               sample="batch %d, the same layers with Softmax.backward replaced by the closed form "
+                                                      "(no per-call ThreadPool / per-row Jacobian) — NOT the reference" % b2)
+    except Exception as e:
+        res = dict(value=None, unit=unit, cores=cores, kind="port", error="reference arm failed: %s: %s" % (type(e).__name__, e))
+    try:
+        port = port_baseline(workload, budget_s * 0.3)
+        if res.get("value") is None:
+            res.update(value=port["value"], sample=port["sample"])
+        res["oracle_port"] = port
+    except Exception as e:
+        res["oracle_port"] = {"error": str(e)}
     return res
 
 
-def cpu_baseline_gpt(workload, budget_s, cores):
+def port_baseline(workload, budget_s):
+    """The oracle's closed-form, batch-vectorised restatement (oracle/models.py) — the fastest honest NumPy version."""
     from oracle import models as M
     kind, c = WORKLOADS[workload]
-    B = min(c["batch"], 2)
-    cfg = M.GPTConfig(batch=B, context=c["context"], embed_dim=c["embed_dim"], heads=c["heads"], blocks=c["blocks"], vocab=c["vocab"])
-    params = M.gpt_init(cfg, 0)
-    opt = M.adam_state(params)
-    tokens, labels = M.synthetic_gpt_batch(cfg, 1)
-    t0 = time.perf_counter()
-    M.gpt_step(params, opt, tokens, labels, c["lr"], cfg)
-    return dict(value=B / (time.perf_counter() - t0), unit="sequences/s", cores=cores, kind="port",
-                sample="1 step of batch %d of %s" % (B, workload))
-
-
-def run_reference(args):
-    """The reference's own CPU path (oracle port: the Python reference cannot travel to the GPU box)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return None
-    from oracle import models as M
-    kind, c = WORKLOADS[args.workload]
-    world = args.gpus
-    W, K = max(1, min(args.warmup, 2)), max(1, min(args.steps, 10))
     if kind == "vit":
         B = min(c["batch"], 100)
         cfg = M.ViTConfig(batch=B, embed_dim=c["embed_dim"], heads=c["heads"], blocks=c["blocks"])
         params = M.vit_init(cfg, 0)
         images, labels, onehot = M.synthetic_vit_batch(cfg, 1)
-        for _ in range(W):
-            params = M.vit_step(params, images, onehot, c["lr"], cfg)["params"]
-        t0 = time.perf_counter()
-        for _ in range(K):
-            params = M.vit_step(params, images, onehot, c["lr"], cfg)["params"]
-        dt = time.perf_counter() - t0
-        unit, metric = "images/s", METRIC
+        step = lambda p: M.vit_step(p, images, onehot, c["lr"], cfg)["params"]
+        unit = "images/s"
     else:
         B = min(c["batch"], 2)
         cfg = M.GPTConfig(batch=B, context=c["context"], embed_dim=c["embed_dim"], heads=c["heads"], blocks=c["blocks"], vocab=c["vocab"])
-        params, tokens_labels = M.gpt_init(cfg, 0), M.synthetic_gpt_batch(cfg, 1)
-        opt = M.adam_state(params)
-        K, W = min(K, 2), 0
-        t0 = time.perf_counter()
-        for _ in range(K):
-            o = M.gpt_step(params, opt, tokens_labels[0], tokens_labels[1], c["lr"], cfg)
-            params, opt = o["params"], o["opt"]
-        dt = time.perf_counter() - t0
-        unit, metric = "sequences/s", "train sequences/s (GPT fwd+bwd+update)"
+        params = M.gpt_init(cfg, 0)
+        opt = [M.adam_state(params)]
+        tokens, labels = M.synthetic_gpt_batch(cfg, 1)
+
+        def step(p):
+            o = M.gpt_step(p, opt[0], tokens, labels, c["lr"], cfg)
+            opt[0] = o["opt"]
+            return o["params"]
+        unit = "sequences/s"
+    params = step(params)
+    n, t0 = 0, time.perf_counter()
+    while n < 20:
+        params = step(params)
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return dict(value=B * n / (time.perf_counter() - t0), unit=unit,
+                sample="%d steps of batch %d of %s, oracle port (closed-form softmax backward, vectorised over batch x heads)" % (n, B, workload))
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the step — its unmodified layer classes from
+    oracle/_ref/tree — on this host's cores.  Each of the K (+W) steps is a bounded sample (batch b <= the config's batch)
+    sized so that the whole run ends within a few minutes.  Rank 0 only; other ranks exit without work."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    cores = _blas_threads()
+    kind, c = WORKLOADS[args.workload]
+    W, K = max(0, args.warmup), max(1, args.steps)
+    unit = "images/s" if kind == "vit" else "sequences/s"
+    b = int(max(1, min(c["batch"], args.ref_budget / ((K + W) * _REF_UNIT_S[args.workload]))))
+    kind_used = "reference"
     try:
-        from threadpoolctl import threadpool_info
-        cores = max([i.get("num_threads", 1) for i in threadpool_info()] or [os.cpu_count()])
-    except Exception:
-        cores = os.cpu_count()
-    v = B * K / dt
-    sample = "%d steps of batch %d of %s on the host CPU (oracle port of the reference, closed-form softmax backward)" % (K, B, args.workload)
-    return {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": args.workload, "per_gpu_batch": B, **{k: v_ for k, v_ in c.items() if k != "batch"}},
-            "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        model = ReferenceModel(args.workload, b)
+        dt, loss = _time_model(model, W, K)
+        sample = ("%d timed steps (%d warm-up) of batch %d of %s through the UNMODIFIED reference layers (oracle/_ref/tree: "
+                  "attention.py, net/*.py ... byte-identical copies; ThreadPool softmax backward and all), os.cpu_count()=%d, "
+                  "BLAS threads=%d, NumPy %s" % (K, W, b, args.workload, os.cpu_count(), cores, np.__version__))
+    except RuntimeError as e:
+        kind_used = "port"
+        p = port_baseline(args.workload, 30.0)
+        b, dt, loss = 1, 1.0 / p["value"], None
+        sample = p["sample"] + " [reference tree unavailable: %s]" % e
+    v = b / dt
+    return {"impl": "reference", "metric": METRIC if kind == "vit" else GPT_METRIC, "value": v, "unit": unit, "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if kind == "vit" else "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "per_gpu_batch": c["batch"], "sample_batch_per_step": b,
+                       **{k: v_ for k, v_ in c.items() if k != "batch"}},
+            "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": kind_used, "sample": sample},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0, "loss": loss}
 
 
 def main():
@@ -428,9 +654,10 @@ def main():
     ap.add_argument("--workload", default="vit_readme", choices=sorted(WORKLOADS))
     ap.add_argument("--gemm-mode", type=int, default=None)
     ap.add_argument("--buckets", type=int, default=1)
-    ap.add_argument("--chains", type=int, default=None, help="parallel micro-batch branches per GPU (default 1; measured slower than 1 on B200 for vit_readme, see DESIGN.md)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--no-extra", action="store_true", help="skip other_configs / e2e_layer_api on the default workload")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU time the reference arm aims for")
     args = ap.parse_args()
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:

@@ -45,6 +45,7 @@ int nt_event_create(void** ev);
 int nt_event_record(void* ev);
 int nt_event_record_external(void* ev);                   /* capturable: becomes a graph event-record node */
 int nt_event_elapsed_ms(void* ev0, void* ev1, float* ms);  /* synchronises on ev1 */
+int nt_event_synchronize(void* ev);                        /* host waits for the event (pinned staging reuse) */
 int nt_event_destroy(void* ev);
 /* CUDA-graph capture of whatever is enqueued between begin and end (one step of the trainer
  * loop transformer_of_image.py:141-159 / gpt/gpt_train_potry3000.py:256-288). */
@@ -57,10 +58,6 @@ int nt_set_side_branch(int enabled);      /* 0: capture everything on the main s
 int nt_side_begin(void);
 int nt_side_end(void);
 int nt_side_join(void);
-/* Parallel branches for independent sample groups inside a captured step (intra-GPU data parallelism). */
-int nt_chain_begin(int idx);
-int nt_chain_end(void);
-int nt_chain_join(void);
 int nt_graph_destroy(void* graph_exec);
 /* number of this library's kernels launched so far (graph replays count their kernel nodes) */
 int nt_launch_count(long long* n);
@@ -194,7 +191,7 @@ int nt_attention_decode(const float* qkv_new, const float* kcache, const float* 
  * gpt_predict_poetrythree.py:115-117 with np.argmax: tok[b] and hist[b, *d_pos + 1] = first maximum of logits[b, :cols]),
  * then nt_increment(d_pos). */
 int nt_decode_embed(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int D, int Tmax,
-                    const int32_t* d_pos);
+                    const int32_t* d_pos, int num_embeddings);
 int nt_kv_append_at(const float* qkv, float* kcache, float* vcache, int B, int Tmax, int D, const int32_t* d_pos);
 int nt_attention_decode_at(const float* qkv_new, float* kcache, float* vcache, float* out, int B, int Tmax, int H,
                            int dh, const int32_t* d_pos, int append);   /* append != 0: nt_kv_append_at folded in */
@@ -240,39 +237,6 @@ int nt_vit_blocks_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int
 int nt_vit_blocks_bwd(const NtVitBlock* blocks, int nblocks, const float* x, const float* dout, float* dx,
                       float* scratch, int B, int N, int D, int H);
 
-/* ---------------------------------------------------------------- the two ends of the launch-bound ViT step
- * stem = PatchEmbed_flatten.forward/backward (PatchEmbed.py:22-49, patchnorm) + the positional add
- * (Position_add.py:20-23); head = final layer_norm -> flatten -> classify_layer (classify.py:20-47, FC0 -> ReLU -> FC1)
- * -> cross_entropy_loss (net/loss.py:46-51) + argmax (transformer_of_image.py:151) and the backward of all of them.
- * Five launches instead of ~17 around the fused block stack.  All members are DEVICE pointers. */
-typedef struct NtVitEnds {
-  const float *images;                       /* [B,C,Hi,Wi] */
-  const float *wpe, *bpe, *pe_g, *pe_b;      /* patch Linear [C*h*w, D], [D]; patch LayerNorm gamma, beta [D] */
-  const float *pos;                          /* [N,D] table added after the LayerNorm (NULL: none) */
-  float *d_wpe, *d_bpe, *d_pe_g, *d_pe_b;    /* accumulate (+=) */
-  float *pe_lin;                             /* [B,N,D]  Linear output before the LayerNorm (kept for backward) */
-  float *pe_stat;                            /* [B,N,2]  mean, rstd of the patch LayerNorm */
-  float *x0;                                 /* [B,N,D]  stem output = input of the first block */
-  const float *xl;                           /* [B,N,D]  output of the last block */
-  const float *tl_g, *tl_b;                  /* final LayerNorm gamma, beta [D] */
-  const float *w0, *b0;                      /* classify fc0 [N*D, D0], [D0] */
-  const float *w1, *b1;                      /* classify fc1 [D0, C1], [C1] */
-  float *d_tl_g, *d_tl_b, *d_w0, *d_b0, *d_w1, *d_b1;   /* accumulate (+=) */
-  const int32_t *labels;                     /* [B] class indices */
-  float *tl_stat;                            /* [B,N,2] */
-  float *h0;                                 /* [B,D0]  fc0 accumulator: must be ZERO on entry, is zero again on return */
-  float *dh0;                                /* [B,D0] */
-  float *logits, *probs;                     /* [B,C1] */
-  int32_t *argmax;                           /* [B] np.argmax(probs, -1), first index on ties */
-  float *loss;                               /* scalar: sum_rows -log(p_label + 1e-10) / n_norm */
-  float *dxl;                                /* [B,N,D]  gradient w.r.t. xl */
-} NtVitEnds;
-int nt_vit_ends_supported(int B, int C, int Hi, int Wi, int n_patch, int D, int D0, int C1, int* ok);
-int nt_vit_stem_fwd(const NtVitEnds* e, int B, int C, int Hi, int Wi, int n_patch, int D);
-int nt_vit_stem_bwd(const NtVitEnds* e, const float* dx0, int B, int C, int Hi, int Wi, int n_patch, int D);
-/* forward, loss and backward of the head in three launches; n_norm is the GLOBAL row count under data parallelism */
-int nt_vit_head(const NtVitEnds* e, int B, int N, int D, int D0, int C1, float n_norm);
-
 /* ---------------------------------------------------------------- embeds */
 /* PatchEmbed_flatten.forward patch loops, PatchEmbed.py:22-36: (B,C,Hi,Wi) -> (B, n_patch^2, C*h*w) */
 int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, int n_patch);
@@ -297,10 +261,16 @@ int nt_col2im(const float* dcol, float* dx, int N, int C, int H, int W, int KH, 
 int nt_transpose_last2(const float* x, float* y, int batch, int rows, int cols);
 /* Position_Embedding.forward, PatchEmbed.py:132-138 + Embedding_layer.forward net/Embedding.py:50-55:
  * out[b,t,:] = etok[idx[b,t],:] + epos[t,:]  (epos may be NULL). */
-int nt_embedding_fwd(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int T, int D);
+int nt_embedding_fwd(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int T, int D,
+                     int num_embeddings);
 /* Position_Embedding.backward, PatchEmbed.py:140-144 + Embedding_layer.backward net/Embedding.py:57-70:
  * detok[idx[b,t],:] += dy[b,t,:] ; depos[t,:] += sum_b dy[b,t,:]  (either may be NULL). Accumulates. */
-int nt_embedding_bwd(const int32_t* idx, const float* dy, float* detok, float* depos, int B, int T, int D);
+int nt_embedding_bwd(const int32_t* idx, const float* dy, float* detok, float* depos, int B, int T, int D,
+                     int num_embeddings);
+/* Index errors: ids in [-num_embeddings, 0) wrap like NumPy's negative indexing (Embedding.py:46 `self.params[inputs]`);
+ * ids outside [-num_embeddings, num_embeddings) — the reference raises IndexError — never touch memory: the lookup
+ * yields zeros, the scatter is skipped, and the NEXT nt_sync / nt_d2h returns non-zero with the reason in
+ * nt_last_error().  nt_cross_entropy does the same for an int label outside [0, cols). */
 
 /* ---------------------------------------------------------------- loss (net/loss.py:46-51) */
 /* cross_entropy_loss: p = softmax(logits), loss = -sum(label*log(p+1e-10))/n_norm, grad = (p-label)/n_norm.
@@ -334,6 +304,8 @@ int nt_dp_unique_id(void* uid128);
 int nt_dp_init(const void* uid128, int rank, int world);
 int nt_dp_allreduce_sum(float* buf, size_t n);   /* in place, on the comm stream, ordered after compute */
 int nt_dp_join(void);                            /* compute stream waits for outstanding all-reduces */
+/* replicas must start identical: rank `root`'s buffer (n 4-byte words) overwrites every other rank's, on the compute stream */
+int nt_dp_broadcast(void* buf, size_t n, int root);
 int nt_dp_shutdown(void);
 
 #ifdef __cplusplus

@@ -14,6 +14,10 @@ extern int g_gemm_mode;
 extern long long g_launches;
 extern bool g_capturing;
 extern bool g_use_pdl;
+// Device-side argument errors (token id >= vocabulary, label >= classes): kernels cannot return a status, so they set
+// this word (pinned, host-mapped) and skip the access; nt_sync / nt_d2h report it at the next synchronisation.
+extern int* g_dev_error;
+enum { NT_DEVERR_TOKEN = 1, NT_DEVERR_LABEL = 2 };
 void set_error(const char* fmt, ...);
 bool ensure_init();
 

@@ -53,6 +53,13 @@ int nt_dp_allreduce_sum(float* buf, size_t n) {
   return 0;
 }
 
+int nt_dp_broadcast(void* buf, size_t n, int root) {
+  NT_ENTRY();
+  NT_REQUIRE(g_comm, "nt_dp_broadcast: nt_dp_init has not been called");
+  NT_NCCL(ncclBroadcast(buf, buf, n, ncclFloat, root, g_comm, g_stream));
+  return 0;
+}
+
 int nt_dp_join(void) {
   NT_ENTRY();
   if (!g_pending) return 0;

@@ -185,14 +185,18 @@ __global__ void transpose_last2_kernel(const float* __restrict__ x, float* __res
 }
 
 __global__ void embedding_fwd_kernel(const int32_t* __restrict__ idx, const float* __restrict__ etok,
-                                     const float* __restrict__ epos, float* __restrict__ out, int BT, int T, int D) {
+                                     const float* __restrict__ epos, float* __restrict__ out, int BT, int T, int D,
+                                     int vocab, int* err) {
   pdl_prologue();
   const int row = blockIdx.x;
   if (row >= BT) return;
-  const int tok = idx[row];
+  int tok = idx[row];
+  if (tok < 0) tok += vocab;                    // NumPy wraps negative indices (Embedding.py:46: self.params[inputs])
+  const bool bad = tok < 0 || tok >= vocab;     // ... and raises IndexError beyond the table: flag it, read nothing
+  if (bad && threadIdx.x == 0) *err = NT_DEVERR_TOKEN;
   const int t = row % T;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float v = etok[(long long)tok * D + c];
+    float v = bad ? 0.f : etok[(long long)tok * D + c];
     if (epos) v += epos[(long long)t * D + c];
     out[(long long)row * D + c] = v;
   }
@@ -201,11 +205,15 @@ __global__ void embedding_fwd_kernel(const int32_t* __restrict__ idx, const floa
 // one decode step: out[b] = etok[idx[b]] + epos[*d_pos]  (PatchEmbed.py:132-138 for the single new position)
 __global__ void decode_embed_kernel(const int32_t* __restrict__ idx, const float* __restrict__ etok,
                                     const float* __restrict__ epos, float* __restrict__ out, int D, int Tmax,
-                                    const int32_t* __restrict__ d_pos) {
+                                    const int32_t* __restrict__ d_pos, int vocab, int* err) {
   pdl_prologue();
-  const int row = blockIdx.x, tok = idx[row], t = min(*d_pos, Tmax - 1);
+  const int row = blockIdx.x, t = min(*d_pos, Tmax - 1);
+  int tok = idx[row];
+  if (tok < 0) tok += vocab;
+  const bool bad = tok < 0 || tok >= vocab;
+  if (bad && threadIdx.x == 0) *err = NT_DEVERR_TOKEN;
   for (int c = threadIdx.x; c < D; c += blockDim.x)
-    out[(long long)row * D + c] = etok[(long long)tok * D + c] + epos[(long long)t * D + c];
+    out[(long long)row * D + c] = (bad ? 0.f : etok[(long long)tok * D + c]) + epos[(long long)t * D + c];
 }
 
 // greedy choice on device: tok[b] = argmax(logits[b, :cols]) (first index on ties, like np.argmax), also recorded at
@@ -241,11 +249,16 @@ __global__ void __launch_bounds__(256) argmax_next_kernel(const float* __restric
 }
 
 __global__ void embedding_bwd_tok_kernel(const int32_t* __restrict__ idx, const float* __restrict__ dy,
-                                         float* __restrict__ detok, int BT, int D) {
+                                         float* __restrict__ detok, int BT, int D, int vocab, int* err) {
   pdl_prologue();
   const int row = blockIdx.x;
   if (row >= BT) return;
-  const int tok = idx[row];
+  int tok = idx[row];
+  if (tok < 0) tok += vocab;
+  if (tok < 0 || tok >= vocab) {                // never scatter outside the gradient table
+    if (threadIdx.x == 0) *err = NT_DEVERR_TOKEN;
+    return;
+  }
   for (int c = threadIdx.x; c < D; c += blockDim.x) atomicAdd(detok + (long long)tok * D + c, dy[(long long)row * D + c]);
 }
 
@@ -256,7 +269,7 @@ __global__ void embedding_bwd_pos_kernel(const float* __restrict__ dy, float* __
   if (i >= total) return;
   float s = 0.f;
   for (int b = 0; b < B; b++) s += dy[(long long)b * total + i];
-  atomicAdd(depos + i, s);     // several micro-batch chains may accumulate concurrently
+  atomicAdd(depos + i, s);     // += : accumulate until setzero (PatchEmbed.py:142-143)
 }
 
 __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, float* __restrict__ g, size_t n, float lr,
@@ -410,19 +423,23 @@ int nt_transpose_last2(const float* x, float* y, int batch, int rows, int cols) 
   return 0;
 }
 
-int nt_embedding_fwd(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int T, int D) {
+int nt_embedding_fwd(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int T, int D, int vocab) {
   NT_ENTRY();
+  NT_REQUIRE(vocab > 0, "nt_embedding_fwd: num_embeddings must be positive");
   if (B * T == 0) return 0;
-  NT_CHECK(nt::launch_k(embedding_fwd_kernel, dim3(B * T), dim3(D >= 256 ? 256 : 128), 0, idx, etok, epos, out, B * T, T, D));
+  NT_CHECK(nt::launch_k(embedding_fwd_kernel, dim3(B * T), dim3(D >= 256 ? 256 : 128), 0, idx, etok, epos, out, B * T, T, D, vocab,
+                        g_dev_error));
   NT_LAUNCH_OK();
   return 0;
 }
 
-int nt_embedding_bwd(const int32_t* idx, const float* dy, float* detok, float* depos, int B, int T, int D) {
+int nt_embedding_bwd(const int32_t* idx, const float* dy, float* detok, float* depos, int B, int T, int D, int vocab) {
   NT_ENTRY();
   if (B * T == 0) return 0;
   if (detok) {
-    NT_CHECK(nt::launch_k(embedding_bwd_tok_kernel, dim3(B * T), dim3(D >= 256 ? 256 : 128), 0, idx, dy, detok, B * T, D));
+    NT_REQUIRE(vocab > 0, "nt_embedding_bwd: num_embeddings must be positive");
+    NT_CHECK(nt::launch_k(embedding_bwd_tok_kernel, dim3(B * T), dim3(D >= 256 ? 256 : 128), 0, idx, dy, detok, B * T, D, vocab,
+                          g_dev_error));
     NT_LAUNCH_OK();
   }
   if (depos) {
@@ -450,11 +467,12 @@ int nt_adam_star(float* p, float* g, float* m, float* v, size_t n, float lr, con
 }
 
 int nt_decode_embed(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int D, int Tmax,
-                    const int32_t* d_pos) {
+                    const int32_t* d_pos, int vocab) {
   NT_ENTRY();
-  NT_REQUIRE(idx && etok && epos && out && d_pos && D > 0 && Tmax > 0, "nt_decode_embed: bad arguments");
+  NT_REQUIRE(idx && etok && epos && out && d_pos && D > 0 && Tmax > 0 && vocab > 0, "nt_decode_embed: bad arguments");
   if (B == 0) return 0;
-  NT_CHECK(nt::launch_k(decode_embed_kernel, dim3(B), dim3(D >= 256 ? 256 : 128), 0, idx, etok, epos, out, D, Tmax, d_pos));
+  NT_CHECK(nt::launch_k(decode_embed_kernel, dim3(B), dim3(D >= 256 ? 256 : 128), 0, idx, etok, epos, out, D, Tmax, d_pos, vocab,
+                        g_dev_error));
   NT_LAUNCH_OK();
   return 0;
 }

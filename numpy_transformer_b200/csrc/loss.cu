@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128) ce_row_kernel(const float* __restrict__ l
                                                      const float* __restrict__ onehot, float inv_n,
                                                      float* __restrict__ row_loss, float* __restrict__ grad,
                                                      float* __restrict__ prob, int32_t* __restrict__ argmax_out,
-                                                     int cols) {
+                                                     int cols, int* err) {
   pdl_prologue();
   __shared__ float sv[4];
   __shared__ int si[4];
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(128) ce_row_kernel(const float* __restrict__ l
   s = block_sum(s, sv);
   const float inv = 1.0f / s;
   const int lab = labels ? labels[row] : -1;
+  if (labels && (lab < 0 || lab >= cols) && threadIdx.x == 0) *err = NT_DEVERR_LABEL;   // no class to credit: flagged, loss 0
   float lossacc = 0.f;
   float pm = -INFINITY;
   int pi = 0x7fffffff;
@@ -161,7 +162,8 @@ extern "C" int nt_cross_entropy(const float* logits, const int32_t* labels, cons
   NT_REQUIRE((labels != nullptr) != (onehot != nullptr), "nt_cross_entropy: pass exactly one of labels / onehot");
   NT_REQUIRE(n_norm > 0.f && row_loss && loss, "nt_cross_entropy: n_norm, row_loss and loss are required");
   const float inv_n = 1.0f / n_norm;
-  NT_CHECK(nt::launch_k(ce_row_kernel, dim3(rows), dim3(128), 0, logits, labels, onehot, inv_n, row_loss, grad, prob, argmax, cols));
+  NT_CHECK(nt::launch_k(ce_row_kernel, dim3(rows), dim3(128), 0, logits, labels, onehot, inv_n, row_loss, grad, prob, argmax, cols,
+                        g_dev_error));
   NT_LAUNCH_OK();
   NT_CHECK(nt::launch_k(ce_reduce_kernel, dim3(1), dim3(256), 0, row_loss, loss, rows, inv_n));
   NT_LAUNCH_OK();

@@ -14,6 +14,7 @@ int g_gemm_mode = 1;   // default: tcgen05 3xTF32 (fp32-class accuracy)
 long long g_launches = 0;
 bool g_capturing = false;
 bool g_use_pdl = true;
+int* g_dev_error = nullptr;
 static int g_device = -1;
 static thread_local char g_err[1024] = "";
 static char g_err_global[1024] = "";
@@ -25,11 +26,6 @@ static void* g_flush_buf = nullptr;
 static cudaStream_t g_main_stream = nullptr, g_side_stream = nullptr;
 static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
 static bool g_side_active = false, g_side_dirty = false;
-static const int kMaxChains = 8;
-static cudaStream_t g_chain_stream[kMaxChains] = {};
-static cudaEvent_t g_chain_done[kMaxChains] = {};
-static bool g_chain_dirty[kMaxChains] = {};
-static int g_chain_active = -1;
 static bool g_side_enabled = true;
 static const size_t kFlushBytes = 256ull << 20;
 struct GraphRec { cudaGraphExec_t exec; cudaGraph_t graph; int kernels; };
@@ -85,8 +81,22 @@ int nt_init(int device) {
   NT_CHECK(cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking));
   NT_CHECK(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
   NT_CHECK(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+  NT_CHECK(cudaHostAlloc((void**)&g_dev_error, sizeof(int), cudaHostAllocMapped));
+  *g_dev_error = 0;
   g_device = device;
   return 0;
+}
+
+// after a synchronisation: did a kernel flag a bad index since the last check?
+static int check_dev_error(const char* where) {
+  if (!g_dev_error || *(volatile int*)g_dev_error == 0) return 0;
+  const int code = *(volatile int*)g_dev_error;
+  *(volatile int*)g_dev_error = 0;
+  set_error("%s: %s", where,
+            code == NT_DEVERR_TOKEN ? "index out of range in an embedding lookup (token id >= num_embeddings; the reference raises "
+                                      "IndexError, net/Embedding.py:46)"
+                                    : "label out of range in cross_entropy (label >= number of classes)");
+  return 4;
 }
 
 int nt_sm_count(int* n) { NT_ENTRY(); *n = g_sm_count; return 0; }
@@ -162,7 +172,7 @@ int nt_d2h(void* dst, const void* src, size_t bytes) {
   NT_ENTRY();
   NT_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
   NT_CHECK(cudaStreamSynchronize(g_stream));
-  return 0;
+  return check_dev_error("nt_d2h");
 }
 int nt_d2d(void* dst, const void* src, size_t bytes) {
   NT_ENTRY();
@@ -174,7 +184,7 @@ int nt_memset(void* dst, int value, size_t bytes) {
   NT_CHECK(cudaMemsetAsync(dst, value, bytes, g_stream));
   return 0;
 }
-int nt_sync(void) { NT_ENTRY(); NT_CHECK(cudaStreamSynchronize(g_stream)); return 0; }
+int nt_sync(void) { NT_ENTRY(); NT_CHECK(cudaStreamSynchronize(g_stream)); return check_dev_error("nt_sync"); }
 int nt_stream_handle(void** s) { NT_ENTRY(); *s = (void*)g_stream; return 0; }
 
 int nt_event_create(void** ev) {
@@ -196,6 +206,7 @@ int nt_event_elapsed_ms(void* e0, void* e1, float* ms) {
   NT_CHECK(cudaEventElapsedTime(ms, (cudaEvent_t)e0, (cudaEvent_t)e1));
   return 0;
 }
+int nt_event_synchronize(void* ev) { NT_CHECK(cudaEventSynchronize((cudaEvent_t)ev)); return 0; }
 int nt_event_destroy(void* ev) { NT_CHECK(cudaEventDestroy((cudaEvent_t)ev)); return 0; }
 
 int nt_graph_begin(void) {
@@ -208,11 +219,22 @@ int nt_graph_begin(void) {
 int nt_graph_end(void** graph_exec, int* n_kernel_nodes) {
   NT_ENTRY();
   NT_REQUIRE(g_capturing, "nt_graph_end: not capturing");
-  if (nt_side_join()) return 1;
-  if (nt_chain_join()) return 1;
+  // whatever happens below, the capture is over when this call returns: a failed join (or a kernel launch that
+  // invalidated the capture) must not leave g_capturing set / the stream in capture mode, or every later
+  // nt_graph_begin would fail
+  const int join_rc = nt_side_join();
   g_capturing = false;
+  g_stream = g_main_stream;
+  g_side_active = g_side_dirty = false;
   cudaGraph_t graph = nullptr;
-  NT_CHECK(cudaStreamEndCapture(g_stream, &graph));
+  const cudaError_t end_rc = cudaStreamEndCapture(g_main_stream, &graph);
+  if (join_rc) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return 1;                          // nt_side_join recorded the error text
+  }
+  NT_CHECK(end_rc);
+  NT_REQUIRE(graph != nullptr, "nt_graph_end: the capture was invalidated");
   size_t n = 0;
   NT_CHECK(cudaGraphGetNodes(graph, nullptr, &n));
   std::vector<cudaGraphNode_t> nodes(n);
@@ -254,7 +276,7 @@ int nt_graph_destroy(void* graph_exec) {
 int nt_set_side_branch(int enabled) { g_side_enabled = (enabled != 0); return 0; }
 int nt_side_begin(void) {
   NT_ENTRY();
-  if (!g_capturing || !g_side_enabled || g_side_active || g_chain_active >= 0) return 0;
+  if (!g_capturing || !g_side_enabled || g_side_active) return 0;
   NT_CHECK(cudaEventRecord(g_ev_fork, g_main_stream));
   NT_CHECK(cudaStreamWaitEvent(g_side_stream, g_ev_fork, 0));
   g_stream = g_side_stream;
@@ -276,45 +298,6 @@ int nt_side_join(void) {
   NT_CHECK(cudaEventRecord(g_ev_join, g_side_stream));
   NT_CHECK(cudaStreamWaitEvent(g_main_stream, g_ev_join, 0));
   g_side_dirty = false;
-  return 0;
-}
-
-// Micro-batch chains: inside a captured step, work enqueued between nt_chain_begin(i)/nt_chain_end goes to
-// stream i, forked from the main stream.  Independent sample groups (data parallelism inside one GPU) then
-// run as parallel graph branches: the per-kernel latencies of the tiny ViT shapes overlap instead of adding
-// up.  nt_chain_join makes the main stream wait for every branch.  No-ops outside capture.
-int nt_chain_begin(int idx) {
-  NT_ENTRY();
-  NT_REQUIRE(idx >= 0 && idx < kMaxChains, "nt_chain_begin: idx %d out of range", idx);
-  if (!g_capturing) return 0;
-  NT_REQUIRE(g_chain_active < 0 && !g_side_active, "nt_chain_begin: a branch is already open");
-  if (!g_chain_stream[idx]) {
-    NT_CHECK(cudaStreamCreateWithFlags(&g_chain_stream[idx], cudaStreamNonBlocking));
-    NT_CHECK(cudaEventCreateWithFlags(&g_chain_done[idx], cudaEventDisableTiming));
-  }
-  NT_CHECK(cudaEventRecord(g_ev_fork, g_main_stream));
-  NT_CHECK(cudaStreamWaitEvent(g_chain_stream[idx], g_ev_fork, 0));
-  g_stream = g_chain_stream[idx];
-  g_chain_active = idx;
-  g_chain_dirty[idx] = true;
-  return 0;
-}
-int nt_chain_end(void) {
-  NT_ENTRY();
-  if (g_chain_active < 0) return 0;
-  NT_CHECK(cudaEventRecord(g_chain_done[g_chain_active], g_stream));
-  g_stream = g_main_stream;
-  g_chain_active = -1;
-  return 0;
-}
-int nt_chain_join(void) {
-  NT_ENTRY();
-  if (g_chain_active >= 0) nt_chain_end();
-  for (int i = 0; i < kMaxChains; i++)
-    if (g_chain_dirty[i]) {
-      NT_CHECK(cudaStreamWaitEvent(g_main_stream, g_chain_done[i], 0));
-      g_chain_dirty[i] = false;
-    }
   return 0;
 }
 

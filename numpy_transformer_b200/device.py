@@ -53,6 +53,17 @@ def synchronize():
     lib.nt_sync()
 
 
+def rehome_generation():
+    """Bumped whenever parameter tensors move to new device buffers (ParamArena re-homing, fclayer._pad_out).  A
+    captured CUDA graph bakes raw parameter addresses in: its owner compares this counter before every replay and
+    re-adopts / re-captures when it moved (TrainStep._readopt, KVGenerator._params_moved)."""
+    return _state.get("rehome", 0)
+
+
+def bump_rehome():
+    _state["rehome"] = _state.get("rehome", 0) + 1
+
+
 def launch_count():
     n = ctypes.c_longlong(0)
     lib.nt_launch_count(ctypes.byref(n))

@@ -60,6 +60,9 @@ class PatchEmbed_flatten(object):
 
     def restore_model(self, models):
         if self.patchnorm:
+            self.norm._check_model(models[0])
+        self.fullconnect._check_model(models[-1])
+        if self.patchnorm:
             self.norm.restore_model(models[0])
         self.fullconnect.restore_model(models[-1])
 
@@ -135,14 +138,14 @@ class Position_Embedding(Embedding_layer):
         self.idx = idx
         out = DeviceArray((n, T, self.embed_dim), host_dtype=self.text_embedding.host_dtype)
         lib.nt_embedding_fwd(idx.ptr, self.text_embedding.params.ptr, self.pos_embedding.params.ptr, out.ptr,
-                             n, T, self.embed_dim)
+                             n, T, self.embed_dim, self.text_embedding.num_embeddings)
         return out
 
     def backward(self, delta):
         d = as_device(delta)
         n, T = self.idx.shape
         lib.nt_embedding_bwd(self.idx.ptr, d.ptr, self.text_embedding.delta.ptr, self.pos_embedding.delta.ptr,
-                             n, T, self.embed_dim)
+                             n, T, self.embed_dim, self.text_embedding.num_embeddings)
         return self.text_embedding.delta
 
     def update(self, lr):
@@ -157,6 +160,8 @@ class Position_Embedding(Embedding_layer):
         return [self.text_embedding.save_model(), self.pos_embedding.save_model()]
 
     def restore_model(self, models):
+        self.text_embedding._check_model(models[0])
+        self.pos_embedding._check_model(models[1])
         self.text_embedding.restore_model(models[0])
         self.pos_embedding.restore_model(models[1])
 

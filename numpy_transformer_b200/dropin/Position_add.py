@@ -28,7 +28,7 @@ class Position_learnable():
     def backward(self, delta):
         d = as_device(delta)
         if not self.fixed:
-            lib.nt_embedding_bwd(None, d.ptr, None, self.param_delta.ptr, d.shape[0], self.n, self.embed_dim)
+            lib.nt_embedding_bwd(None, d.ptr, None, self.param_delta.ptr, d.shape[0], self.n, self.embed_dim, 1)
         return d
 
     def update(self, lr):

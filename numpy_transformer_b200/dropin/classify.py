@@ -54,7 +54,12 @@ class classify_layer():
     def save_model(self):
         return [self.fc0.save_model(), self.fc1.save_model()]
 
+    def _check_model(self, models):
+        self.fc0._check_model(models[0])
+        self.fc1._check_model(models[1])
+
     def restore_model(self, models):
+        self._check_model(models)
         self.fc0.restore_model(models[0])
         self.fc1.restore_model(models[1])
 

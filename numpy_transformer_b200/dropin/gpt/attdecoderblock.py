@@ -90,9 +90,17 @@ class attdecoderblock_layer(LayerArenaMixin):
     def save_model(self):
         return [c.save_model() for c in self._children()]
 
+    def _check_model(self, models):
+        for i, c in enumerate(self._children()):
+            c._check_model(models[i])
+
     def restore_model(self, models):
-        for c, m in zip(self._children(), models):
-            c.restore_model(m)
+        """The reference indexes models[0..] child by child and raises on a tree that is not a block's (a LayerNorm's
+        [gamma, beta], say); gpt_train_potry3000.py:219-229 relies on that exception to seed a newly added block from
+        the previous one.  Validate the whole tree first so a failed restore leaves the block untouched."""
+        self._check_model(models)
+        for i, c in enumerate(self._children()):
+            c.restore_model(models[i])
 
     def _slots(self):
         return [s for c in self._children() for s in c._slots()]

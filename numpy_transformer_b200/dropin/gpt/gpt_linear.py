@@ -36,6 +36,8 @@ class gpt_linear_layer():
         return [self.fc0.save_model(), self.fc1.save_model(), self.norm.save_model()]
 
     def restore_model(self, models):
+        for c, i in ((self.fc0, 0), (self.fc1, 1), (self.norm, 2)):
+            c._check_model(models[i])
         self.fc0.restore_model(models[0])
         self.fc1.restore_model(models[1])
         self.norm.restore_model(models[2])

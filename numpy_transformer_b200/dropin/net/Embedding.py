@@ -33,13 +33,13 @@ class Embedding_layer(object):
         self.flatten = idx.reshape(-1)
         out = DeviceArray(idx.shape + (self.embedding_dim,), host_dtype=self.host_dtype)
         n = idx.size
-        lib.nt_embedding_fwd(idx.ptr, self.params.ptr, None, out.ptr, 1, n, self.embedding_dim)
+        lib.nt_embedding_fwd(idx.ptr, self.params.ptr, None, out.ptr, 1, n, self.embedding_dim, self.num_embeddings)
         return out
 
     def backward(self, delta, flatten=[]):
         idx = self._idx(flatten).reshape(-1) if len(flatten) else self.flatten
         d = as_device(delta)
-        lib.nt_embedding_bwd(idx.ptr, d.ptr, self.delta.ptr, None, 1, idx.size, self.embedding_dim)
+        lib.nt_embedding_bwd(idx.ptr, d.ptr, self.delta.ptr, None, 1, idx.size, self.embedding_dim, self.num_embeddings)
         return self.delta
 
     def setzero(self):
@@ -61,7 +61,11 @@ class Embedding_layer(object):
     def save_model(self):
         return [np.asarray(self.params).astype(np.float32)]          # Embedding.py:93
 
+    def _check_model(self, models):
+        np.asarray(models[0]).reshape(self.params.shape)
+
     def restore_model(self, models):
+        self._check_model(models)
         self.params.set(np.asarray(models[0]).reshape(self.params.shape))
 
     def _slots(self):

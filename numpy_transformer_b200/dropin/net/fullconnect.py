@@ -121,6 +121,8 @@ class fclayer(object):
             self.moment_p, self.rmsprop_p = DeviceArray.zeros((self.infeature, Np)), DeviceArray.zeros((self.infeature, Np))
             self.moment_b, self.rmsprop_b = DeviceArray.zeros((Np,)), DeviceArray.zeros((Np,))
         self._logical_out, self.outfeature = N, Np
+        from numpy_transformer_b200.device import bump_rehome
+        bump_rehome()
 
     def save_model(self):
         n = getattr(self, "_logical_out", self.outfeature)
@@ -128,7 +130,16 @@ class fclayer(object):
             return [np.asarray(self.params)[:, :n], np.asarray(self.bias_params)[:n]]
         return [np.asarray(self.params)[:, :n]]
 
+    def _check_model(self, models):
+        """Raises what the reference's `models[i].reshape(self.params.shape)` raises on a tree that is not this layer's
+        (IndexError: too short, ValueError: wrong size) WITHOUT touching the parameters (fullconnect.py:161-164)."""
+        n = getattr(self, "_logical_out", self.outfeature)
+        np.asarray(models[0]).reshape(self.infeature, n)
+        if self.bias:
+            np.asarray(models[1]).reshape(n)
+
     def restore_model(self, models):
+        self._check_model(models)
         n = getattr(self, "_logical_out", self.outfeature)
         w = np.asarray(models[0]).reshape(self.infeature, n)
         if n != self.outfeature:

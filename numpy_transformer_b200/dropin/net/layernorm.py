@@ -70,7 +70,13 @@ class layer_norm(object):
     def save_model(self):
         return [np.asarray(self.gamma).reshape(self._host_shape()), np.asarray(self.beta).reshape(self._host_shape())]
 
+    def _check_model(self, models):
+        """layernorm.py:162-164 reshapes models[0] / models[1] to the parameter shapes: same errors, nothing overwritten."""
+        np.asarray(models[0]).reshape(self.gamma.shape)
+        np.asarray(models[1]).reshape(self.beta.shape)
+
     def restore_model(self, models):
+        self._check_model(models)
         self.gamma.set(np.asarray(models[0]).reshape(-1))
         self.beta.set(np.asarray(models[1]).reshape(-1))
 

@@ -20,30 +20,8 @@ class NtVitBlock(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in _PTR_FIELDS]
 
 
-_ENDS_FIELDS = ["images", "wpe", "bpe", "pe_g", "pe_b", "pos", "d_wpe", "d_bpe", "d_pe_g", "d_pe_b", "pe_lin", "pe_stat", "x0",
-                "xl", "tl_g", "tl_b", "w0", "b0", "w1", "b1", "d_tl_g", "d_tl_b", "d_w0", "d_b0", "d_w1", "d_b1", "labels",
-                "tl_stat", "h0", "dh0", "logits", "probs", "argmax", "loss", "dxl"]
-
-
-class NtVitEnds(ctypes.Structure):
-    """Mirror of `struct NtVitEnds` (include/ntb200.h)."""
-    _fields_ = [(n, ctypes.c_void_p) for n in _ENDS_FIELDS]
-
-
 def enabled():
     return os.environ.get("NTB200_FUSED_VIT", "1") != "0"
-
-
-def ends_supported(B, C, Hi, Wi, n_patch, D, D0, C1):
-    """Stem / head kernels (csrc/vit_ends.cu) cover this shape.  OPT-IN (NTB200_FUSED_ENDS=1): measured on B200 the
-    nine-launch step is SLOWER than the 21-launch one (0.637 vs 0.487 ms, README ViT) — the five FFMA kernels with
-    49-100 CTAs take 19-68 us each while the tcgen05 / bandwidth kernels they replace total ~70 us — so the per-op
-    layers stay the default around the fused block stack."""
-    if not enabled() or os.environ.get("NTB200_FUSED_ENDS", "0") != "1" or get_gemm_mode() != 1:
-        return False
-    ok = ctypes.c_int(0)
-    lib.nt_vit_ends_supported(int(B), int(C), int(Hi), int(Wi), int(n_patch), int(D), int(D0), int(C1), ctypes.byref(ok))
-    return bool(ok.value)
 
 
 def supported(N, D, H):

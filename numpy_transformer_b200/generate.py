@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 from ._lib import lib
-from .device import DeviceArray, keep_allocations
+from .device import DeviceArray, keep_allocations, rehome_generation
 from . import ops
 
 
@@ -41,6 +41,21 @@ class KVGenerator:
         self.graph_kernels = 0
         self._graph_buffers = None
         self._eager_done = False
+        self._gen = self._ptrs = None
+
+    def _param_ptrs(self):
+        return tuple(getattr(o, pn).ptr for l in self.layers if hasattr(l, "_slots") for o, pn, *_ in l._slots())
+
+    def _params_moved(self):
+        """The captured decode graph holds raw parameter addresses.  Training re-homes parameters (ParamArena,
+        LayerArenaMixin, fclayer._pad_out) and recycles the old buffers; replaying against them would silently produce
+        garbage.  Cheap check (one counter) before every replay; on a real move the graph is dropped and re-captured."""
+        if self._gen == rehome_generation():
+            return False
+        self._gen = rehome_generation()
+        ptrs = self._param_ptrs()
+        moved, self._ptrs = ptrs != self._ptrs, ptrs
+        return moved
 
     # ------------------------------------------------------------------ full window (the reference's way)
     def full_logits(self, tokens):
@@ -83,7 +98,8 @@ class KVGenerator:
         B, D = self.d_tok.shape[0], self.D
         x = DeviceArray((B, 1, D), host_dtype=self.embed.text_embedding.host_dtype)
         lib.nt_decode_embed(self.d_tok.ptr, self.embed.text_embedding.params.ptr, self.embed.pos_embedding.params.ptr, x.ptr,
-                            B, D, self.context, self.d_pos.ptr)       # token row + position row (PatchEmbed.py:132-138)
+                            B, D, self.context, self.d_pos.ptr,       # token row + position row (PatchEmbed.py:132-138)
+                            self.embed.text_embedding.num_embeddings)
         fused = B <= 16 and os.environ.get("NTB200_DECODE_FUSED", "1") != "0"
         for bi, blk in enumerate(self.blocks):
             if fused:       # LayerNorm inside the skinny GEMV, KV append inside the decode attention: 6 launches per block
@@ -124,6 +140,11 @@ class KVGenerator:
 
     def _run_step(self):
         """Eager the first time, captured the second, replayed afterwards (same protocol as TrainStep.run_device)."""
+        if self.graph is not None and self._params_moved():
+            lib.nt_sync()
+            lib.nt_graph_destroy(self.graph)                   # parameters live elsewhere now: capture again
+            self.graph = self._graph_buffers = None
+            self._eager_done = False
         if not self.use_graph or not self._eager_done:
             self._enqueue_step()
             self._eager_done = True
@@ -139,6 +160,7 @@ class KVGenerator:
                     lib.nt_graph_end(ctypes.byref(g), ctypes.byref(nk))
             self._graph_buffers = keep.buffers
             self.graph, self.graph_kernels = g, nk.value
+            self._gen, self._ptrs = rehome_generation(), self._param_ptrs()
             lib.nt_graph_launch(self.graph)
         else:
             lib.nt_graph_launch(self.graph)

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import install
 from ._lib import lib
-from .device import DeviceArray, PinnedBuffer, as_device, init, keep_allocations
+from .device import DeviceArray, PinnedBuffer, as_device, init, keep_allocations, rehome_generation, bump_rehome
 from . import ops
 from . import fused_vit
 
@@ -71,12 +71,28 @@ def save_walk(layers):
     return [l.save_model() for l in layers if 'save_model' in dir(l) and 'restore_model' in dir(l)]
 
 
-def restore_walk(layers, tree):
-    """Restore walk of transformer_of_image.py:84-92."""
-    it = iter(tree)
+def restore_walk(layers, tree, grow=False):
+    """Restore walk of transformer_of_image.py:84-92.  grow=True is the progressive-growth restore of
+    gpt/gpt_train_potry3000.py:212-231: the checkpoint was written by a model with FEWER decoder blocks; a layer whose
+    entry does not fit (the new block meets the final LayerNorm's [gamma, beta]) is seeded from the PREVIOUS entry — the
+    block before it — and the walk continues without consuming an entry.  A trailing int (the step counter `jk` the
+    trainer appends, :370) is returned; -> (step counter or None, number of layers seeded from their predecessor)."""
+    tree = list(tree)
+    jk = tree[-1] if tree and isinstance(tree[-1], (int, np.integer)) else None
+    cnt = grown = 0
     for l in layers:
         if 'save_model' in dir(l) and 'restore_model' in dir(l):
-            l.restore_model(next(it))
+            if not grow:
+                l.restore_model(tree[cnt])
+            else:
+                try:
+                    l.restore_model(tree[cnt])
+                except (IndexError, ValueError, TypeError):
+                    l.restore_model(tree[cnt - 1])
+                    grown += 1
+                    continue
+            cnt += 1
+    return (None if grown else jk), grown
 
 
 class ParamArena:
@@ -116,6 +132,31 @@ class ParamArena:
                         lib.nt_d2d(nv.ptr, old.ptr, old.nbytes)
                     setattr(obj, name, nv)
         self.n_params = sum(getattr(o, pn).size for o, pn, *_ in slots)
+        self.adam = adam
+        bump_rehome()
+
+    def readopt(self):
+        """Bring back every tensor that has left this arena since it was built (a layer re-homed into its own arena by
+        a hand-made layer.update(), a head padded by another TrainStep ...): its current values are copied into the
+        arena slot and the attribute points at the slot again, so a graph captured over the arena stays valid and
+        save_walk() sees what the graph trains.  -> number of tensors moved back."""
+        moved = 0
+        for (obj, pn, gn, mn, vn), off in zip(self.slots, self.offsets):
+            names = [(pn, self.params), (gn, self.grads)]
+            if self.adam and mn is not None:
+                names += [(mn, self.m), (vn, self.v)]
+            for name, arena in names:
+                cur = getattr(obj, name)
+                want = arena.ptr + 4 * off
+                if cur is None or cur.ptr == want:
+                    continue
+                view = arena.view(off, cur.shape)
+                view.host_dtype = cur.host_dtype
+                assert view.size == cur.size, "parameter %s changed shape after the arena was built" % name
+                lib.nt_d2d(view.ptr, cur.ptr, cur.nbytes)
+                setattr(obj, name, view)
+                moved += 1
+        return moved
 
     def first_offset(self, layer):
         """Arena offset of the first parameter slot owned by `layer` (None if it has no parameters)."""
@@ -127,19 +168,19 @@ class ParamArena:
                 return off
         return None
 
-    def share_with(self, layers):
-        """Point another replica of the same layer list (same constructor order) at these arenas: the
-        replica keeps its own activations but reads / accumulates the same parameters and gradients."""
-        other = []
-        for l in layers:
-            if hasattr(l, "_slots"):
-                other.extend(l._slots())
-        assert len(other) == len(self.slots), "replica has a different parameter structure"
-        for (o0, pn, gn, mn, vn), (o1, pn1, gn1, mn1, vn1) in zip(self.slots, other):
-            assert getattr(o0, pn).shape == getattr(o1, pn1).shape
-            for a in (pn, gn, mn, vn):
-                if a is not None and getattr(o0, a, None) is not None:
-                    setattr(o1, a, getattr(o0, a))
+    def optimizer_runs(self, adam):
+        """[(is_adam, first float, count)]: maximal runs of consecutive slots updated by the same rule.  A slot is
+        Adam* when the step is adam AND the layer declares moments for it AND the owning layer was built with adam
+        (fullconnect.py:134-153); everything else is plain SGD (e.g. Position_learnable.param)."""
+        runs = []
+        for (obj, pn, gn, mn, vn), off in zip(self.slots, self.offsets):
+            size = (getattr(obj, pn).size + 3) // 4 * 4
+            is_adam = bool(adam and mn is not None and getattr(obj, "adam", True))
+            if runs and runs[-1][0] == is_adam and runs[-1][1] + runs[-1][2] == off:
+                runs[-1][2] += size
+            else:
+                runs.append([is_adam, off, size])
+        return [tuple(r) for r in runs]
 
 
 class TrainStep:
@@ -151,36 +192,30 @@ class TrainStep:
         the loss/gradient normaliser is the GLOBAL row count.
     """
 
-    def __init__(self, layers, kind, input_shape, lr, adam=False, dp=None, use_graph=True, grad_buckets=1,
-                 replicas=()):
-        """replicas: extra copies of the layer list (same constructors).  With r replicas the local batch is
-        cut into r+1 micro-batches that run as parallel branches of the captured step (intra-GPU data
-        parallelism: same parameters, gradients accumulate atomically into the same arena, loss normalised
-        by the full row count) — the tiny ViT kernels are latency-bound, so their latencies overlap."""
+    def __init__(self, layers, kind, input_shape, lr, adam=False, dp=None, use_graph=True, grad_buckets=1):
         init()
         self.layers, self.kind, self.adam, self.dp = layers, kind, adam, dp
         self.use_graph = use_graph
-        self.chains = [layers] + [list(r) for r in replicas]
-        for ch in self.chains:                  # the head feeds cross_entropy directly: pad its class axis
-            head = ch[-1]
-            if hasattr(head, "fc1") and hasattr(head.fc1, "_pad_out"):
-                head.fc1._pad_out(4)
+        head = layers[-1]                       # the head feeds cross_entropy directly: pad its class axis
+        if hasattr(head, "fc1") and hasattr(head.fc1, "_pad_out"):
+            head.fc1._pad_out(4)
         self.arena = ParamArena(layers, adam)
-        for r in self.chains[1:]:
-            self.arena.share_with(r)
-        assert input_shape[0] % len(self.chains) == 0, "batch must divide evenly into micro-batch chains"
         self.input_shape = tuple(input_shape)
         in_dtype = np.float32 if kind == "vit" else np.int32
         self.rows = input_shape[0] if kind == "vit" else input_shape[0] * input_shape[1]
         world = 1 if dp is None else dp.world
         self.n_norm = float(self.rows * world)
-        self.h_in = PinnedBuffer(self.input_shape, in_dtype)
-        self.h_lab = PinnedBuffer((self.rows,), np.int32)
+        # two pinned staging sets: load() fills one while the H2D copy of the previous batch may still be reading the
+        # other (pipelined load()/run_device() without a sync in between)
+        self._stage = [(PinnedBuffer(self.input_shape, in_dtype), PinnedBuffer((self.rows,), np.int32), self._new_event())
+                       for _ in range(2)]
+        self._stage_i = 0
+        self._stage_used = [False, False]
         self.h_out = PinnedBuffer((8,), np.float32)
         self.h_amax = PinnedBuffer((self.rows,), np.int32)
         self.d_in = DeviceArray(self.input_shape, in_dtype)
         self.d_lab = DeviceArray((self.rows,), np.int32)
-        self.d_loss = DeviceArray.zeros((len(self.chains),))
+        self.d_loss = DeviceArray.zeros((1,))
         self.d_amax = DeviceArray.zeros((self.rows,), dtype=np.int32)
         self.d_lr = DeviceArray.from_host(np.array([lr], dtype=np.float32)).reshape(())
         self.d_t = DeviceArray.from_host(np.array([1], dtype=np.int32)).reshape(())
@@ -194,100 +229,54 @@ class TrainStep:
         self._block_t = L["attdecoderblock_layer"]
         self._vit_block_t = L["attention_layer"]
         self._layer_types = L
+        self._opt_runs = self.arena.optimizer_runs(adam)
+        self._gen = rehome_generation()
+        self.sync_replicas()
 
-    # ------------------------------------------------------------------ fully fused ViT step (README layer list)
-    def _vit_fast_plan(self, layers):
-        """The README layer list (transformer_of_image.py:56-77: PatchEmbed_flatten(patchnorm) -> fixed position table ->
-        attention blocks -> layer_norm -> flatten -> classify_layer(relu, no cls token)) at shapes the fused kernels
-        cover runs as 9 launches: stem, weight split, block stack, 3 x head, block stack backward, stem backward, update."""
-        if self.kind != "vit" or len(self.chains) != 1 or len(layers) < 6:
-            return None
-        L = self._layer_types
-        pe, pos, ln, fl, head = layers[0], layers[1], layers[-3], layers[-2], layers[-1]
-        blocks = layers[2:-3]
-        if not (type(pe) is L["PatchEmbed_flatten"] and type(pos) is L["Position_learnable"] and type(ln) is L["layer_norm"]
-                and type(fl) is L["flatten_layer"] and type(head) is L["classify_layer"]):
-            return None
-        if not (pe.patchnorm and pos.fixed and not head.cls_token and head.reluact and ln.elementwise_affine
-                and pe.fullconnect.bias and head.fc0.bias and head.fc1.bias):
-            return None
-        B, C, Hi, Wi = self.input_shape
-        N, D = pe.n_patch ** 2, pe.embed_dim
-        if Hi % pe.n_patch or Wi % pe.n_patch or not blocks:
-            return None
-        if fused_vit.fusable_run(layers, 2, self._vit_block_t, (B, N, D)) != len(blocks):
-            return None
-        D0, C1 = head.fc0.params.shape[1], head.fc1.params.shape[1]
-        if head.fc0.params.shape[0] != N * D or not fused_vit.ends_supported(B, C, Hi, Wi, pe.n_patch, D, D0, C1):
-            return None
-        return dict(pe=pe, pos=pos, ln=ln, head=head, blocks=blocks, B=B, C=C, Hi=Hi, Wi=Wi, N=N, D=D, D0=D0, C1=C1)
+    @staticmethod
+    def _new_event():
+        e = ctypes.c_void_p()
+        lib.nt_event_create(ctypes.byref(e))
+        return e
 
-    def _enqueue_vit_fast(self, plan, layers):
-        import ctypes
-        pe, pos, ln, head, blocks = plan["pe"], plan["pos"], plan["ln"], plan["head"], plan["blocks"]
-        B, C, Hi, Wi, N, D, D0, C1 = (plan[k] for k in ("B", "C", "Hi", "Wi", "N", "D", "D0", "C1"))
-        if getattr(self, "_ends_h0", None) is None:
-            self._ends_h0 = DeviceArray.zeros((B, D0))           # fc0 accumulator: zero between steps (the kernel re-zeroes it)
-        e = fused_vit.NtVitEnds()
-        x0, pe_lin, pe_stat = DeviceArray((B, N, D)), DeviceArray((B, N, D)), DeviceArray((B, N, 2))
-        tl_stat, dh0, dxl = DeviceArray((B, N, 2)), DeviceArray((B, D0)), DeviceArray((B, N, D))
-        logits, probs = DeviceArray((B, C1)), DeviceArray((B, C1))
-        fc, n0 = pe.fullconnect, pe.norm
-        e.images = self.d_in.ptr
-        e.wpe, e.bpe, e.pe_g, e.pe_b = fc.params.ptr, fc.bias_params.ptr, n0.gamma.ptr, n0.beta.ptr
-        e.pos = pos.table().ptr
-        e.d_wpe, e.d_bpe, e.d_pe_g, e.d_pe_b = fc.params_delta.ptr, fc.bias_delta.ptr, n0.gamma_delta.ptr, n0.beta_delta.ptr
-        e.pe_lin, e.pe_stat, e.x0 = pe_lin.ptr, pe_stat.ptr, x0.ptr
-        e.tl_g, e.tl_b = ln.gamma.ptr, ln.beta.ptr
-        e.w0, e.b0, e.w1, e.b1 = head.fc0.params.ptr, head.fc0.bias_params.ptr, head.fc1.params.ptr, head.fc1.bias_params.ptr
-        e.d_tl_g, e.d_tl_b = ln.gamma_delta.ptr, ln.beta_delta.ptr
-        e.d_w0, e.d_b0 = head.fc0.params_delta.ptr, head.fc0.bias_delta.ptr
-        e.d_w1, e.d_b1 = head.fc1.params_delta.ptr, head.fc1.bias_delta.ptr
-        e.labels = self.d_lab.ptr
-        e.tl_stat, e.h0, e.dh0 = tl_stat.ptr, self._ends_h0.ptr, dh0.ptr
-        e.logits, e.probs, e.argmax, e.loss = logits.ptr, probs.ptr, self.d_amax.ptr, self.d_loss.ptr
-        e.dxl = dxl.ptr
-        n0._lead = ln._lead = 2                                  # gamma/beta host shape after a forward (layernorm.py:105-108)
-        lib.nt_vit_stem_fwd(ctypes.addressof(e), B, C, Hi, Wi, pe.n_patch, D)
-        xl = fused_vit.forward_stack(blocks, x0)
-        e.xl = xl.ptr
-        lib.nt_vit_head(ctypes.addressof(e), B, N, D, D0, C1, self.n_norm)
-        if self.dp is not None and self.dp.world > 1:
-            # gradients of the final LayerNorm + head (the tail of the arena) are complete: all-reduce them under the
-            # fused backward launch
-            lo = min(o for o in (self.arena.first_offset(ln), self.arena.first_offset(head)) if o is not None)
-            lib.nt_dp_allreduce_sum(self.arena.grads.ptr + 4 * lo, self.arena.n - lo)
-            self._early_from = lo
-        dx0 = fused_vit.backward_stack(blocks, dxl)
-        lib.nt_vit_stem_bwd(ctypes.addressof(e), dx0.ptr, B, C, Hi, Wi, pe.n_patch, D)
-        probs._argmax = self.d_amax
-        self._ends_keep = (e, x0, pe_lin, pe_stat, tl_stat, dh0, dxl, logits, probs)
-        return logits, probs
+    @property
+    def h_in(self):
+        """The pinned input staging buffer the NEXT load() / step() without arguments will upload."""
+        return self._stage[self._stage_i][0]
+
+    @property
+    def h_lab(self):
+        return self._stage[self._stage_i][1]
+
+    def sync_replicas(self):
+        """Data parallel: every rank must hold rank 0's parameters and optimizer state (the reference has one model;
+        ranks that seeded np.random differently, or restored different checkpoints, would otherwise train different
+        models without any error).  Broadcast the arenas from rank 0, then verify with a checksum all-reduce."""
+        dp = self.dp
+        if dp is None or dp.world == 1 or not dp.nccl_ready:
+            return
+        a = self.arena
+        bufs = [a.params] + ([a.m, a.v] if self.adam else [])
+        for b in bufs:
+            lib.nt_dp_broadcast(b.ptr, b.size, 0)
+        lib.nt_dp_broadcast(self.d_t.ptr, 1, 0)            # int32 moved as one 4-byte word
+        lib.nt_sync()
+        mine = float(np.asarray(a.params.numpy(), dtype=np.float64).sum())
+        if abs(dp.max_over_ranks(mine) + dp.max_over_ranks(-mine)) > 0:
+            raise RuntimeError("data-parallel replicas differ after the parameter broadcast")
 
     # ------------------------------------------------------------------ the step body (enqueue only)
-    def _enqueue_chain(self, c, layers):
-        plan = self._vit_fast_plan(layers)
-        if plan is not None:
-            return self._enqueue_vit_fast(plan, layers)
-        nc = len(self.chains)
-        bs = self.input_shape[0] // nc
-        rows = self.rows // nc
-        in_elems = self.d_in.size // nc
-        x = self.d_in.view(c * in_elems, (bs,) + self.input_shape[1:])
-        lab = self.d_lab.view(c * rows, (rows,))
+    def _enqueue_body(self):
+        layers = self.layers
+        x, lab, rows = self.d_in, self.d_lab, self.rows
         runs = {}                                    # start index -> fused run of ViT blocks (one launch each way)
-        early = {}     # runs whose weights were split ahead of time (fused_vit.prepare); measured: forking the split onto
-        # the side branch costs more in graph dependencies than the 5 us launch it hides, so it stays in the forward call
         i = 0
         while i < len(layers):
             l = layers[i]
             n = fused_vit.fusable_run(layers, i, self._vit_block_t, x.shape) if type(l) is self._vit_block_t else 0
             if n:
                 runs[i] = layers[i:i + n]
-                prepared = early.get(i) == n
-                if prepared:
-                    lib.nt_side_join()
-                x = fused_vit.forward_stack(runs[i], x, prepared=prepared)
+                x = fused_vit.forward_stack(runs[i], x)
                 i += n
                 continue
             if isinstance(l, self._block_t):
@@ -296,8 +285,8 @@ class TrainStep:
                 x = l.forward(x)
             i += 1
         flat = x.reshape(rows, x.shape[-1])
-        loss, grad, probs, amax = ops.cross_entropy(flat, lab, None, self.n_norm, loss_out=self.d_loss.view(c, ()),
-                                                    argmax_out=self.d_amax.view(c * rows, (rows,)))
+        loss, grad, probs, amax = ops.cross_entropy(flat, lab, None, self.n_norm, loss_out=self.d_loss.view(0, ()),
+                                                    argmax_out=self.d_amax)
         delta = grad.reshape(x.shape)
         first = layers[0]
         ends = {s + len(r) - 1: s for s, r in runs.items()}
@@ -305,7 +294,7 @@ class TrainStep:
         while i >= 0:
             l = layers[i]
             if i in ends:
-                if self.dp is not None and self.dp.world > 1 and len(self.chains) == 1 and self._early_from is None:
+                if self.dp is not None and self.dp.world > 1 and self._early_from is None:
                     # data parallel: the gradients of everything AFTER the fused stack (final LayerNorm + head, more than
                     # half of the V1 arena) are complete -> all-reduce them now, under the fused backward launch
                     offs = [self.arena.first_offset(l) for l in layers[i + 1:]]
@@ -326,18 +315,8 @@ class TrainStep:
         return x, probs
 
     def _enqueue(self):
-        nc = len(self.chains)
-        outs = []
         self._early_from = None          # arena offset from which the gradients were all-reduced early (DP only)
-        for c, layers in enumerate(self.chains):
-            if nc > 1:
-                lib.nt_chain_begin(c)
-            outs.append(self._enqueue_chain(c, layers))
-            if nc > 1:
-                lib.nt_chain_end()
-        if nc > 1:
-            lib.nt_chain_join()
-        self.logits, self.probs = outs[0] if nc == 1 else ([o[0] for o in outs], [o[1] for o in outs])
+        self.logits, self.probs = self._enqueue_body()
         self.loss, self.argmax = self.d_loss, self.d_amax
         a = self.arena
         lib.nt_side_join()                       # weight-gradient branch must land before all-reduce / update
@@ -347,11 +326,16 @@ class TrainStep:
             elif self._early_from > 0:
                 self.dp.allreduce_buckets(a.grads.view(0, (self._early_from,)), self.grad_buckets)
             lib.nt_dp_join()
+        # one launch per run of slots that share an optimizer: Adam* where the layer has moments and adam=True, plain SGD
+        # elsewhere (Position_learnable.param has no moments in the reference: Position_add.py:26-28 is always SGD)
+        for is_adam, lo, n in self._opt_runs:
+            if is_adam:
+                lib.nt_adam_star(a.params.ptr + 4 * lo, a.grads.ptr + 4 * lo, a.m.ptr + 4 * lo, a.v.ptr + 4 * lo, n, 0.0,
+                                 self.d_lr.ptr, 0, self.d_t.ptr, 1)
+            else:
+                lib.nt_sgd(a.params.ptr + 4 * lo, a.grads.ptr + 4 * lo, n, 0.0, self.d_lr.ptr, 1)
         if self.adam:
-            lib.nt_adam_star(a.params.ptr, a.grads.ptr, a.m.ptr, a.v.ptr, a.n, 0.0, self.d_lr.ptr, 0, self.d_t.ptr, 1)
             lib.nt_increment(self.d_t.ptr)
-        else:
-            lib.nt_sgd(a.params.ptr, a.grads.ptr, a.n, 0.0, self.d_lr.ptr, 1)
 
     def set_lr(self, lr):
         if float(lr) != self._lr:
@@ -362,6 +346,11 @@ class TrainStep:
         """One step on whatever is in the device input buffers (no host traffic).  Call 1 runs
         eagerly (sizes the pool, loads modules), call 2 captures the graph and launches it, later
         calls replay it; every call is exactly one training step."""
+        if rehome_generation() != self._gen:
+            # some parameter tensor moved since the arena was built / the graph captured (generate.py and the layers'
+            # own update() re-home tensors): pull strays back so the captured addresses stay the live ones
+            self.arena.readopt()
+            self._gen = rehome_generation()
         if not self.use_graph or self.steps_done == 0:
             self._enqueue()
         elif self.graph is None:
@@ -403,14 +392,24 @@ class TrainStep:
 
     def load(self, inputs=None, labels=None):
         """Host -> pinned staging -> device (async on the compute stream).  With inputs / labels omitted the batch
-        is taken from the pinned staging buffers as they are (`self.h_in.array`, `self.h_lab.array`): a loader that
-        writes its batches straight into pinned memory skips the extra host copy / dtype cast."""
+        is taken from the current pinned staging buffers as they are (`self.h_in.array`, `self.h_lab.array`): a loader
+        that writes its batches straight into pinned memory skips the extra host copy / dtype cast.  Staging is
+        double-buffered: the set being filled is never the one an in-flight H2D copy is still reading, so
+        load() / run_device() can be called back to back without a sync."""
+        i = self._stage_i
+        h_in, h_lab, ev = self._stage[i]
+        if self._stage_used[i]:
+            lib.nt_event_synchronize(ev)          # the copy issued from this set two loads ago has finished
         if inputs is not None:
-            np.copyto(self.h_in.array, np.asarray(inputs).reshape(self.input_shape), casting="unsafe")
+            np.copyto(h_in.array, np.asarray(inputs).reshape(self.input_shape), casting="unsafe")
         if labels is not None:
-            np.copyto(self.h_lab.array, np.asarray(labels).reshape(-1), casting="unsafe")
-        lib.nt_h2d(self.d_in.ptr, self.h_in.ptr, self.h_in.nbytes)
-        lib.nt_h2d(self.d_lab.ptr, self.h_lab.ptr, self.h_lab.nbytes)
+            np.copyto(h_lab.array, np.asarray(labels).reshape(-1), casting="unsafe")
+        lib.nt_h2d(self.d_in.ptr, h_in.ptr, h_in.nbytes)
+        lib.nt_h2d(self.d_lab.ptr, h_lab.ptr, h_lab.nbytes)
+        lib.nt_event_record(ev)
+        self._stage_used[i] = True
+        if inputs is not None or labels is not None:
+            self._stage_i = 1 - i                 # a loader that fills h_in itself keeps addressing the same set
 
     def step(self, inputs=None, labels=None, lr=None, want_argmax=False):
         """End-to-end public call: host batch in (or already in the pinned staging buffers), host loss (and argmax) out."""
@@ -418,12 +417,11 @@ class TrainStep:
             self.set_lr(lr)
         self.load(inputs, labels)
         self.run_device()
-        nc = len(self.chains)
-        lib.nt_d2h_async(self.h_out.ptr, self.d_loss.ptr, 4 * nc)
+        lib.nt_d2h_async(self.h_out.ptr, self.d_loss.ptr, 4)
         if want_argmax:
             lib.nt_d2h_async(self.h_amax.ptr, self.d_amax.ptr, self.h_amax.nbytes)
         lib.nt_sync()
-        loss = float(self.h_out.array[:nc].sum())      # each chain's partial is already divided by the global N
+        loss = float(self.h_out.array[0])              # already divided by the global N
         return (loss, self.h_amax.array.copy()) if want_argmax else loss
 
     @property
@@ -465,6 +463,7 @@ class TrainStep:
             self.d_t.set(np.array([state["t"]], dtype=np.int32))
             self.sync_layer_counters()
         lib.nt_sync()
+        self.sync_replicas()
 
     def close(self):
         """Destroy the captured graphs (required before DataParallel.shutdown: they hold NCCL kernels)."""

@@ -151,25 +151,3 @@ def test_trainstep_uses_fused_stack(nt, use_graph):
     assert all(getattr(l, "_fused", False) for l in layers[2:5])
     if use_graph:
         assert ts.graph is not None and ts.graph_kernels < 40
-
-
-def test_trainstep_fused_ends_opt_in(nt, monkeypatch):
-    """NTB200_FUSED_ENDS=1: stem and head kernels (csrc/vit_ends.cu) turn the README layer list into nine launches;
-    same oracle parity as the default path (it is opt-in because it measured slower, see fused_vit.ends_supported)."""
-    from numpy_transformer_b200 import trainer
-    monkeypatch.setenv("NTB200_FUSED_ENDS", "1")
-    cfg = M.ViTConfig(batch=6, embed_dim=32, heads=2, blocks=3)
-    params = M.vit_init(cfg, 0)
-    images, labels, onehot = M.synthetic_vit_batch(cfg, 1)
-    layers = trainer.build_vit_layers(6, embed_dim=32, heads=2, blocks=3, seed=0)
-    ts = trainer.TrainStep(layers, "vit", images.shape, lr=0.02)
-    for step in range(4):
-        ref = M.vit_step(params, images, onehot, 0.02, cfg)
-        loss, amax = ts.step(images, labels, want_argmax=True)
-        assert abs(loss - ref["loss"]) < TOL * abs(ref["loss"]), step
-        assert np.array_equal(amax, ref["argmax"])
-        assert rel_err(np.asarray(ts.logits)[:, :10], ref["logits"]) < TOL
-        params = ref["params"]
-        for i, (a, b_) in enumerate(zip(M.tree_leaves(trainer.save_walk(layers)), M.tree_leaves(params))):
-            assert rel_err(a.reshape(-1), b_.reshape(-1)) < TOL, "step %d leaf %d" % (step, i)
-    assert ts.graph is not None and ts.graph_kernels == 9

@@ -33,14 +33,21 @@ def test_kv_cache_matches_full_window(nt, D, H):
                                   M.causal_mask(6))
     logits = gen.prefill(toks)
     assert rel_err(logits, np.asarray(ref_logits).reshape(B, 6, V)[:, -1]) < TOL
+    params = M.tree_unflatten(M.gpt_init(cfg, 0), M.tree_leaves(trainer.save_walk(layers)))
     seq = toks.copy()
     for _ in range(T - 6):
         nxt = np.argmax(logits, -1)
         seq = np.concatenate([seq, nxt[:, None]], 1)
         logits = gen.step(nxt)
+        # EVERY cached step against the oracle's forward over the whole window so far (the reference's procedure,
+        # gpt_predict_poetrythree.py:108-121), not against this repo's own full-window path
+        n = seq.shape[1]
+        ocfg = M.GPTConfig(batch=B, context=n, embed_dim=D, heads=H, blocks=2, vocab=V)
+        want = np.asarray(M.gpt_forward(params, seq, ocfg, M.causal_mask(n))[0]).reshape(B, n, V)[:, -1]
+        assert rel_err(logits, want) < TOL, seq.shape
+        assert np.array_equal(np.argmax(logits, -1), np.argmax(want, -1))
         full = gen.full_logits(seq)
         assert rel_err(logits, full) < TOL, seq.shape
-        assert np.array_equal(np.argmax(logits, -1), np.argmax(full, -1))
     assert gen.len == T
 
 

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 from conftest import rel_err
 from oracle import numpy_ref as R
+from oracle import models as M
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -144,3 +145,65 @@ def test_return_attention_mode(nt):
     from oracle import numpy_ref as RR
     _, _, S = RR.attention_fwd(c["qkv"], 2, None)
     assert rel_err(np.array(att), S) < TOL
+
+
+def test_progressive_block_growth_restore(nt):
+    """gpt/gpt_train_potry3000.py:212-231: a checkpoint of an N-block model restored into an (N+1)-block model.  The
+    reference's loop relies on restore_model RAISING when the new block is handed the final LayerNorm's [gamma, beta]
+    (its restore indexes models[0..5]), then seeds the block from the previous entry.  Run that loop verbatim on the
+    drop-in objects, and the same through trainer.restore_walk(grow=True)."""
+    import pickle
+    from numpy_transformer_b200 import trainer
+    small = trainer.build_gpt_layers(2, 8, 32, 2, 2, 11, adam=True, seed=0)
+    x = np.random.RandomState(0).randint(0, 11, (2, 8))
+    for l in small:                                     # one forward: LayerNorm checkpoints take their rank-expanded shape
+        x = l.forward(x, "causal") if type(l).__name__ == "attdecoderblock_layer" else l.forward(x)
+    tree = trainer.save_walk(small)
+    tree.append(1234)                                   # the trainer's step counter (:370)
+    models = pickle.loads(pickle.dumps(tree))
+
+    def grown_layers():
+        return trainer.build_gpt_layers(2, 8, 32, 2, 3, 11, adam=True, seed=7)
+
+    # (1) the reference's own loop, verbatim
+    layers = grown_layers()
+    jk, cnt, num_attention = models[-1], 0, 0
+    for l in layers:
+        k = dir(l)
+        nam = l.__module__
+        if 'attdecoderblock' in nam:
+            num_attention += 1
+        if 'restore_model' in k and 'save_model' in k:
+            try:
+                l.restore_model(models[cnt])
+            except:                                     # noqa: E722  (as in the reference)
+                jk = 0
+                l.restore_model(models[cnt - 1])
+                continue
+            cnt += 1
+    assert num_attention == 3 and jk == 0 and cnt == 5
+    got = trainer.save_walk(layers)
+    want = [tree[0], tree[1], tree[2], tree[2], tree[3], tree[4]]      # the new block is a copy of the block before it
+    for a, b in zip(M.tree_leaves(got), M.tree_leaves(want)):
+        assert np.array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1))
+    # (2) a failed restore leaves the layer untouched (validated before anything is overwritten)
+    probe = grown_layers()
+    before = [np.asarray(a).copy() for a in M.tree_leaves(probe[3].save_model())]
+    with pytest.raises((IndexError, ValueError)):
+        probe[3].restore_model(models[3])               # the final LayerNorm's [gamma, beta]
+    for a, b in zip(M.tree_leaves(probe[3].save_model()), before):
+        assert np.array_equal(np.asarray(a), b)
+    with pytest.raises((IndexError, ValueError)):
+        probe[3].restore_model(models[2][:4])           # a block tree cut short
+    # (3) the library's walk does the same and reports it
+    layers2 = grown_layers()
+    step, grown = trainer.restore_walk(layers2, models, grow=True)
+    assert grown == 1 and step is None
+    for a, b in zip(M.tree_leaves(trainer.save_walk(layers2)), M.tree_leaves(want)):
+        assert np.array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1))
+    step, grown = trainer.restore_walk(trainer.build_gpt_layers(2, 8, 32, 2, 2, 11, adam=True, seed=9), models, grow=True)
+    assert (step, grown) == (1234, 0)
+    # the grown model trains
+    ts = trainer.TrainStep(layers2, "gpt", (2, 8), lr=1e-3, adam=True)
+    assert np.isfinite(ts.step(np.random.RandomState(1).randint(0, 11, (2, 8)), np.random.RandomState(2).randint(0, 11, (2, 8))))
+    ts.close()

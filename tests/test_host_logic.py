@@ -32,9 +32,58 @@ def test_header_parses_and_library_exports_every_symbol(nt):
 
 
 def test_library_is_sm100a_only_and_carries_tcgen05_tma(nt):
-    sass = subprocess.run(["cuobjdump", "-lelf", nt.LIBPATH], capture_output=True, text=True).stdout
-    assert "sm_100a" in sass
-    assert "sm_90" not in sass and "sm_80" not in sass
+    elf = subprocess.run(["cuobjdump", "-lelf", nt.LIBPATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    assert "sm_90" not in elf and "sm_80" not in elf
+    # the Blackwell-native instructions themselves, per kernel (SASS mnemonics: tcgen05.mma -> UTC*MMA, tcgen05.ld ->
+    # LDTM, TMA tensor loads -> UTMALDG, bulk copies -> UBLKCP; /opt/skills/guides/B200_PROFILING.md)
+    sass = subprocess.run(["cuobjdump", "-sass", nt.LIBPATH], capture_output=True, text=True).stdout
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        line = line.strip()
+        if line.startswith("Function :"):
+            cur = per_kernel.setdefault(line.split(":", 1)[1].strip(), {"UTCHMMA": 0, "LDTM": 0, "UTMALDG": 0, "UBLKCP": 0, "HMMA": 0})
+        elif cur is not None:
+            for op in cur:
+                if " " + op in line or line.startswith(op):
+                    if op == "HMMA" and "UTCHMMA" in line:
+                        continue
+                    cur[op] += 1
+
+    def total(pattern, op):
+        return sum(v[op] for k, v in per_kernel.items() if pattern in k)
+    assert total("gemm_tc_kernel", "UTCHMMA") > 0 and total("gemm_tc_kernel", "LDTM") > 0 and total("gemm_tc_kernel", "UTMALDG") > 0
+    # the fused ViT stack (the headline kernel) and the dh=64 attention kernels run their contractions on tcgen05
+    for k in ("vit_tc_fwd", "vit_tc_bwd"):
+        if any(k in name for name in per_kernel):
+            assert total(k, "UTCHMMA") > 0 and total(k, "LDTM") > 0 and total(k, "HMMA") == 0, k
+
+
+def test_reference_tree_is_the_unmodified_reference():
+    """oracle/_ref/tree (what the GPU tests execute and bench.py --impl reference times) is byte-identical to the
+    reference: every file's sha256 equals tests/golden/ref_scripts/MANIFEST.json, which was written from /root/reference."""
+    import json
+    from oracle import ref_tree
+    want = json.load(open(ref_tree.MANIFEST))
+    assert "transformer_of_image.py" in want and "gpt/gpt_train_potry3000.py" in want and "net/activation.py" in want
+    if os.path.isdir(ref_tree.REFERENCE):
+        for rel, sha in want.items():
+            assert ref_tree._sha(os.path.join(ref_tree.REFERENCE, rel)) == sha, rel
+    if not ref_tree.available():
+        pytest.skip("oracle/_ref/tree has not been built here (python -c 'import __graft_entry__ as g; g.build()')")
+    assert ref_tree.tree_manifest() == want
+
+
+def test_golden_trainer_logs_parse():
+    from oracle import ref_tree
+    gold = os.path.dirname(ref_tree.MANIFEST)
+    rows, extra = ref_tree.parse_log(open(os.path.join(gold, "vit.log"), encoding="utf-8").read())
+    assert len(rows) == 22 and rows[0]["epoch"] == 25 and rows[-1]["epoch"] == 35
+    assert sum("testset precision" in l for l in extra) == 11
+    rows, _ = ref_tree.parse_log(open(os.path.join(gold, "gpt_char.log"), encoding="utf-8").read())
+    assert len(rows) == 101 and rows[0]["lr"] == 0.0 and rows[-1]["loss"] < 0.5 * rows[0]["loss"]
+    rows, _ = ref_tree.parse_log(open(os.path.join(gold, "gpt_poetry.log"), encoding="utf-8").read())
+    assert [r["iters"] for r in rows] == ["6599_6600", "6600_6600", "6601_6600"] and rows[1]["valpre"] is not None
 
 
 def test_no_cpu_fallback(nt):
