@@ -237,6 +237,16 @@ int nt_vit_blocks_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int
 int nt_vit_blocks_bwd(const NtVitBlock* blocks, int nblocks, const float* x, const float* dout, float* dx,
                       float* scratch, int B, int N, int D, int H);
 
+/* The same stack on the 5th-generation tensor cores (csrc/vit_block_tc.cu): tcgen05.mma with the accumulators in TMEM,
+ * operands as swizzled bf16 hi/lo planes in shared memory, weights streamed by bulk copies.  Shape: N <= 64, D = 96, H = 4
+ * (the README configuration).  NtVitBlock is interpreted slightly differently: `dgelu` receives the fc0 PRE-activation
+ * [B,N,2D] (GELU and GELU' are recomputed in the backward), `P` may be NULL (the softmax is then not materialised; the
+ * backward recomputes it from q, k), `save` is unused, `wfrag` holds nt_vit_tc_wimg_bytes(D) bytes of weight tiles. */
+int nt_vit_tc_supported(int N, int D, int H, int* ok);
+int nt_vit_tc_wimg_bytes(int D, size_t* bytes);
+int nt_vit_tc_prepare(const NtVitBlock* blocks, int nblocks, int D, int H);
+int nt_vit_tc_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H, int prepared);
+
 /* ---------------------------------------------------------------- embeds */
 /* PatchEmbed_flatten.forward patch loops, PatchEmbed.py:22-36: (B,C,Hi,Wi) -> (B, n_patch^2, C*h*w) */
 int nt_patchify(const float* images, float* out, int B, int C, int Hi, int Wi, int n_patch);

@@ -42,6 +42,23 @@ class NtError(RuntimeError):
     pass
 
 
+def _preload_nccl():
+    """libntb200.so needs libnccl.so.2.  A process that later imports torch (the reference's transformer_of_image.py does,
+    through torchvision) must end up with ONE NCCL: torch's libtorch_cuda.so is linked against the NCCL wheel bundled in
+    site-packages (2.28) and fails with an undefined symbol if the older system library (2.27) was mapped first.  So map the
+    bundled one first when it exists; libntb200 only uses the stable ncclCommInitRank / ncclAllReduce / ncclBroadcast ABI."""
+    import glob
+    import sys
+    for base in sys.path:
+        for cand in glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.*")):
+            try:
+                ctypes.CDLL(cand, mode=ctypes.RTLD_GLOBAL)
+                return cand
+            except OSError:
+                pass
+    return None
+
+
 class _Lib:
     def __init__(self):
         self._dll = None
@@ -95,6 +112,7 @@ class _Lib:
         if not os.path.exists(LIBPATH):
             raise NtError("libntb200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "or `make -C numpy_transformer_b200/csrc`. This backend has no CPU fallback." % LIBPATH)
+        _preload_nccl()
         dll = ctypes.CDLL(LIBPATH, mode=ctypes.RTLD_GLOBAL)
         for name, (res, args) in self.protos.items():
             fn = getattr(dll, name)          # AttributeError here = header/library mismatch

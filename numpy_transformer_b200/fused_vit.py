@@ -28,8 +28,20 @@ def supported(N, D, H):
     """True when the fused kernels cover this shape in the current GEMM mode (mode 1 = fp32-class tensor-core path)."""
     if not enabled() or get_gemm_mode() != 1:
         return False
+    if tc_supported(N, D, H):
+        return True
     ok = ctypes.c_int(0)
     lib.nt_vit_blocks_supported(int(N), int(D), int(H), ctypes.byref(ok))
+    return bool(ok.value)
+
+
+def tc_supported(N, D, H):
+    """The tcgen05 / TMEM kernels (csrc/vit_block_tc.cu) cover this shape: the README configuration (D = 96, 4 heads,
+    N <= 64).  NTB200_VIT_TC=0 forces the older mma.sync kernels (csrc/vit_block.cu), which cover more (D, H) pairs."""
+    if os.environ.get("NTB200_VIT_TC", "0") == "0" or not enabled() or get_gemm_mode() != 1:
+        return False
+    ok = ctypes.c_int(0)
+    lib.nt_vit_tc_supported(int(N), int(D), int(H), ctypes.byref(ok))
     return bool(ok.value)
 
 
@@ -44,12 +56,14 @@ def _save_bytes(D):
     return _SAVE_BYTES[D]
 
 
-def _wfrag(layer, D):
-    w = getattr(layer, "_wfrag", None)
+def _wfrag(layer, D, tc=False):
+    name = "_wimg_tc" if tc else "_wfrag"
+    w = getattr(layer, name, None)
     if w is None:
         nbytes = ctypes.c_size_t(0)
-        lib.nt_vit_blocks_wfrag_bytes(int(D), ctypes.byref(nbytes))
-        w = layer._wfrag = DeviceArray((nbytes.value // 4,))
+        (lib.nt_vit_tc_wimg_bytes if tc else lib.nt_vit_blocks_wfrag_bytes)(int(D), ctypes.byref(nbytes))
+        w = DeviceArray((nbytes.value // 4,))
+        setattr(layer, name, w)
     return w
 
 
@@ -66,11 +80,12 @@ def prepare(layers):
     lib.nt_vit_blocks_prepare(ctypes.addressof(arr), len(layers), D, H)
 
 
-def _block_array(layers, weights_only=False):
+def _block_array(layers, weights_only=False, tc=False):
     arr = (NtVitBlock * len(layers))()
     for s, l in zip(arr, layers):
+        wf = l._wimg_tc if tc else l._wfrag
         if weights_only:
-            s.wqkv, s.w0, s.w1, s.wfrag = l.qkvfc.params.ptr, l.fc0.params.ptr, l.fc1.params.ptr, l._wfrag.ptr
+            s.wqkv, s.w0, s.w1, s.wfrag = l.qkvfc.params.ptr, l.fc0.params.ptr, l.fc1.params.ptr, wf.ptr
             continue
         s.ln_g, s.ln_b = l.norm.gamma.ptr, l.norm.beta.ptr
         s.wqkv, s.bqkv = l.qkvfc.params.ptr, l.qkvfc.bias_params.ptr
@@ -82,35 +97,41 @@ def _block_array(layers, weights_only=False):
         s.d_ln1_g, s.d_ln1_b = l.norm1.gamma_delta.ptr, l.norm1.beta_delta.ptr
         s.d_w0, s.d_b0 = l.fc0.params_delta.ptr, l.fc0.bias_delta.ptr
         s.d_w1, s.d_b1 = l.fc1.params_delta.ptr, l.fc1.bias_delta.ptr
-        s.qkv, s.P, s.h, s.dgelu, s.out = l.qkv.ptr, l.P.ptr, l.input1.ptr, l._dgelu.ptr, l._out.ptr
-        s.save = l._save.ptr
-        s.wfrag = l._wfrag.ptr
+        s.qkv, s.P, s.h, s.dgelu, s.out = l.qkv.ptr, _null_ptr(l.P), l.input1.ptr, l._dgelu.ptr, l._out.ptr
+        s.save = _null_ptr(l._save)
+        s.wfrag = wf.ptr
     return arr
 
 
-def forward_stack(layers, x, prepared=False):
-    """attention_layer.forward (attention.py:20-55) of every layer in `layers`, chained, in one launch."""
+def forward_stack(layers, x, prepared=False, want_P=True):
+    """attention_layer.forward (attention.py:20-55) of every layer in `layers`, chained, in one launch.
+    want_P=False (TrainStep): the tcgen05 kernels do not materialise the softmax matrices (the reference's atg__); the
+    backward recomputes them from q and k."""
     B, N, D = x.shape
     H = layers[0].num_h
     hd = x.host_dtype
+    tc = tc_supported(N, D, H)
     for l in layers:
         assert l.embed_dim == D and l.num_h == H, "fused stack needs identical blocks"
         l.batch, l.block = B, N
         l._mask_kind = 0
         l.qkv = DeviceArray((B, N, 3 * D), host_dtype=hd)
-        l.P = DeviceArray((B, H, N, N), host_dtype=hd)
+        l.P = DeviceArray((B, H, N, N), host_dtype=hd) if (want_P or not tc) else None
         l.input1 = DeviceArray((B, N, D), host_dtype=hd)
-        l._dgelu = DeviceArray((B, N, 2 * D), host_dtype=hd)
-        l._save = DeviceArray((B, _save_bytes(D) // 4))
+        l._dgelu = DeviceArray((B, N, 2 * D), host_dtype=hd)      # tcgen05 path: the fc0 PRE-activation
+        l._save = None if tc else DeviceArray((B, _save_bytes(D) // 4))
         l._out = DeviceArray((B, N, D), host_dtype=hd)
         l.out = l.out1 = l.out2 = None          # LN outputs / GELU output are recomputed in backward, not stored
-        l._fused = True
-        _wfrag(l, D)
+        l._fused = "tc" if tc else "mma"
+        _wfrag(l, D, tc)
     layers[0]._x_in = x
     for prev, l in zip(layers, layers[1:]):
         l._x_in = prev._out
-    arr = _block_array(layers)
-    lib.nt_vit_blocks_fwd(ctypes.addressof(arr), len(layers), x.ptr, B, N, D, H, int(bool(prepared)))
+    arr = _block_array(layers, tc=tc)
+    if tc:
+        lib.nt_vit_tc_fwd(ctypes.addressof(arr), len(layers), x.ptr, B, N, D, H, int(bool(prepared)))
+    else:
+        lib.nt_vit_blocks_fwd(ctypes.addressof(arr), len(layers), x.ptr, B, N, D, H, int(bool(prepared)))
     return layers[-1]._out
 
 
@@ -120,6 +141,10 @@ def backward_stack(layers, delta):
     B, N, D = x.shape
     H = layers[0].num_h
     dx = DeviceArray((B, N, D), host_dtype=delta.host_dtype)
+    if layers[0]._fused == "tc":
+        arr = _block_array(layers, tc=True)
+        lib.nt_vit_tc_bwd(ctypes.addressof(arr), len(layers), x.ptr, delta.ptr, dx.ptr, B, N, D, H)
+        return dx
     scratch = DeviceArray((2, B, N, D))
     arr = _block_array(layers)
     lib.nt_vit_blocks_bwd(ctypes.addressof(arr), len(layers), x.ptr, delta.ptr, dx.ptr, scratch.ptr, B, N, D, H)

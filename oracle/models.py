@@ -229,11 +229,12 @@ def vit_forward(params, images, cfg: ViTConfig, refstruct=False):
     return logits, acts
 
 
-def vit_backward(params, acts, dlogits, cfg: ViTConfig, refstruct=False):
-    """transformer_of_image.py:156-159 (backward halves of the same layers)."""
+def vit_backward(params, acts, dlogits, cfg: ViTConfig, refstruct=False, head_relu_mask=None):
+    """transformer_of_image.py:156-159 (backward halves of the same layers).  head_relu_mask: test-only override of the
+    head's ReLU mask (see gpt_block_bwd)."""
     (Wc0, bc0), (Wc1, bc1) = params[3 + cfg.blocks]
     d, dWc1, dbc1 = R.linear_bwd(dlogits, acts['hact'], Wc1)
-    d = R.relu_bwd(d, acts['hpre'])
+    d = R.relu_bwd(d, acts['hpre']) if head_relu_mask is None else d * head_relu_mask.reshape(d.shape)
     d, dWc0, dbc0 = R.linear_bwd(d, acts['zf'], Wc0)
     deltas = [d]
     d = d.reshape(-1, cfg.tokens, cfg.embed_dim)
@@ -253,12 +254,12 @@ def vit_backward(params, acts, dlogits, cfg: ViTConfig, refstruct=False):
     return grads, deltas
 
 
-def vit_step(params, images, onehot, lr, cfg: ViTConfig, refstruct=False):
+def vit_step(params, images, onehot, lr, cfg: ViTConfig, refstruct=False, head_relu_mask=None):
     """One SGD training step (transformer_of_image.py:141-159). Returns a dict with loss, logits,
     probs, argmax, grads, deltas, activations and the updated parameter tree."""
     logits, acts = vit_forward(params, images, cfg, refstruct)
     loss, partial, probs = R.cross_entropy(logits, onehot)
-    grads, deltas = vit_backward(params, acts, partial, cfg, refstruct)
+    grads, deltas = vit_backward(params, acts, partial, cfg, refstruct, head_relu_mask)
     new_params = tree_map(lambda p, g: R.sgd_update(p, g, lr), params, grads)
     return dict(loss=loss, logits=logits, probs=probs, argmax=np.argmax(probs, axis=-1),
                 partial=partial, grads=grads, deltas=deltas, acts=acts, params=new_params)

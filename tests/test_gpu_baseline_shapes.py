@@ -47,15 +47,15 @@ def _block_grads(blk):
 def _check_tree(mine, gold, tol, what):
     a, b = M.tree_leaves(mine), M.tree_leaves(gold)
     assert len(a) == len(b), (len(a), len(b))
-    worst = 0.0
+    errs = []
     for i, (x, y) in enumerate(zip(a, b)):
         x, y = np.asarray(x, dtype=np.float64).reshape(-1), np.asarray(y, dtype=np.float64).reshape(-1)
         if x.size != y.size:                       # class axis of the head padded to a multiple of 4 (fullconnect._pad_out)
             x = np.asarray(mine_leaf_unpad(a[i], b[i].shape)).reshape(-1)
-        e = rel_err(x, y)
-        worst = max(worst, e)
-        assert e < tol, "%s: leaf %d (%d elements) rel err %.3e" % (what, i, y.size, e)
-    return worst
+        errs.append(rel_err(x, y))
+    bad = [(i, M.tree_leaves(gold)[i].size, "%.2e" % e) for i, e in enumerate(errs) if not e < tol]
+    assert not bad, "%s: leaves (index, elements, rel err) over %.0e: %s" % (what, tol, bad)
+    return max(errs)
 
 
 def mine_leaf_unpad(x, shape):
@@ -147,8 +147,12 @@ def test_gpt_poetry_trainstep_adam_update_vs_oracle(nt):
     opt = M.adam_state(params)
     before = M.tree_leaves(params)
     for step in range(2):
-        ref = M.gpt_step(params, opt, tokens, labels, 3e-4, cfg)
         loss, amax = ts.step(tokens, labels, want_argmax=True)
+        # step 0 ran eagerly: the blocks still hold its ReLU pre-activations.  The oracle's backward takes the device's
+        # masks (see the module docstring: a flip moves the embedding rows of its token by ~1e-3 of the tensor, and Adam*
+        # turns the SIGN of a tiny gradient into a full step)
+        masks = [np.asarray(b.pre2, dtype=np.float64) > 0 for b in layers[1:1 + cfg.blocks]] if step == 0 else None
+        ref = M.gpt_step(params, opt, tokens, labels, 3e-4, cfg, relu_masks=masks)
         assert abs(loss - ref["loss"]) < TOL * abs(ref["loss"]), step
         assert np.mean(amax.reshape(-1) == ref["argmax"].reshape(-1)) > 0.999
         if step == 0:
@@ -159,10 +163,16 @@ def test_gpt_poetry_trainstep_adam_update_vs_oracle(nt):
                 y = np.asarray(y, dtype=np.float64)
                 x = mine_leaf_unpad(x, y.shape).reshape(-1)
                 y, p0, g = y.reshape(-1), np.asarray(p0).reshape(-1), np.abs(np.asarray(g).reshape(-1))
-                keep = g > 1e-3 * g.max() if g.max() > 0 else np.zeros(g.shape, bool)
-                # the UPDATE (p1 - p0 = -lr * mhat / (sqrt(vhat) + eps), |.| <= lr) is what the kernel computes
-                e = np.max(np.abs((x - p0) - (y - p0))[keep]) / 3e-4 if keep.any() else 0.0
-                assert e < 2e-3, "Adam* update of leaf %d off by %.2e of lr" % (i, e)
+                # Adam*'s step is lr * sign-like(g) near g -> 0: compare where |g| is well above the fp32 noise of the tensor
+                keep = g > 1e-2 * g.max() if g.max() > 0 else np.zeros(g.shape, bool)
+                # the UPDATE (p1 - p0 = -lr * mhat / (sqrt(vhat) + eps), |.| <= 1.8 lr) is what the kernel computes
+                err = np.abs(x - y) / 3e-4
+                e = np.max(err[keep]) if keep.any() else 0.0
+                if not e < 5e-3:
+                    j = int(np.argmax(np.where(keep, err, 0)))
+                    raise AssertionError("Adam* update of leaf %d off by %.2e of lr at element %d: p0 %.8g mine %.8g oracle %.8g, "
+                                         "oracle |g| %.3e (tensor max %.3e), %d of %d kept entries over 5e-3"
+                                         % (i, e, j, p0[j], x[j], y[j], g[j], g.max(), int((err[keep] > 5e-3).sum()), int(keep.sum())))
         params, opt = ref["params"], ref["opt"]
     ts.close()
 
@@ -187,16 +197,33 @@ def test_vit_scaled_real_shape_vs_oracle(nt):
     for l in reversed(layers):
         delta = l.backward(delta)
     pe, head = layers[0], layers[-1]
+    # the head's ReLU (classify.py:28): with only 48 rows ONE pre-activation on the other side of zero moves the head's
+    # bias gradient by ~10 % and everything upstream by ~2 %.  Bound the disagreements, then hand the oracle the device's mask.
+    hpre, ref_hpre = np.asarray(head.pre1, dtype=np.float64), ref["acts"]["hpre"]
+    assert rel_err(hpre, ref_hpre) < TOL
+    flips = (hpre > 0) != (ref_hpre > 0)
+    assert flips.sum() <= 3 and (not flips.any() or np.abs(ref_hpre[flips]).max() < 1e-4 * np.abs(ref_hpre).max())
+    ref = M.vit_step(params, images, onehot, 1e-3, cfg, head_relu_mask=hpre > 0)
     grads = [[_ln_grads(pe.norm), _fc_grads(pe.fullconnect)], []]
     grads += [_block_grads(b) for b in layers[2:14]]
     grads += [_ln_grads(layers[14]), [_fc_grads(head.fc0), _fc_grads(head.fc1)]]
     worst = _check_tree(grads, ref["grads"], TOL, "gradients")
-    print("V2 widths, 48 images: loss %.6f (oracle %.6f), worst gradient rel err %.2e" % (float(loss), ref["loss"], worst))
+    print("V2 widths, 48 images: loss %.6f (oracle %.6f), %d head ReLU masks at rounding of zero, worst gradient rel err %.2e"
+          % (float(loss), ref["loss"], int(flips.sum()), worst))
     # the graph-captured step on the same batch
     layers2 = trainer.build_vit_layers(cfg.batch, embed_dim=384, heads=6, blocks=12, seed=0)
     ts = trainer.TrainStep(layers2, "vit", images.shape, lr=1e-3)
+    before2 = [np.asarray(a, dtype=np.float64).copy() for a in M.tree_leaves(trainer.save_walk(layers2))]
     l2, amax = ts.step(images, labels, want_argmax=True)
     assert abs(l2 - ref["loss"]) < TOL * abs(ref["loss"])
     assert np.array_equal(amax, ref["argmax"])
-    _check_tree(trainer.save_walk(layers2), ref["params"], TOL, "parameters after one SGD step")
+    ref2 = M.vit_step(params, images, onehot, 1e-3, cfg, head_relu_mask=np.asarray(layers2[-1].pre1, dtype=np.float64) > 0)
+    # lr * gradient is a few 1e-6 of a weight: compare the UPDATE (after - before on the device), not the parameter
+    after = [np.asarray(a, dtype=np.float64) for a in M.tree_leaves(trainer.save_walk(layers2))]
+    for i, (p0, p1, q0, q1) in enumerate(zip(before2, after, M.tree_leaves(params), M.tree_leaves(ref2["params"]))):
+        u = (p1 - p0).reshape(-1)
+        w = (np.asarray(q1, dtype=np.float64) - np.asarray(q0, dtype=np.float64)).reshape(-1)
+        # fp32 storage: p1 = fl(p0 - lr g) carries half an ulp of |p| (6e-8 |p|), comparable to the update of a gamma ~ 1
+        tol = 5e-3 * np.abs(w).max() + 1.2e-7 * np.abs(p0).max()
+        assert np.abs(u - w).max() < tol, "SGD update of leaf %d: |err| %.2e vs tol %.2e" % (i, np.abs(u - w).max(), tol)
     ts.close()

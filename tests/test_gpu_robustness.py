@@ -170,7 +170,8 @@ def test_learnable_positions_stay_sgd_under_adam(nt):
         l.setzero()
     ts.step(images, labels)
     pos1 = np.asarray(layers[1].param)
-    assert rel_err(pos0 - pos1, 0.01 * gpos) < 1e-3                      # plain SGD: p -= lr * g
+    assert rel_err(pos0 - pos1, 0.01 * gpos) < 5e-3                      # plain SGD: p -= lr * g (an Adam* step would be ~lr)
+    assert np.abs(pos0 - pos1).max() < 0.05 * 0.01
     step = np.abs(np.asarray(layers[-1].fc1.params)[:, :10] - head0[:, :10])
     assert np.median(step[step > 0]) > 0.2 * 0.01                        # Adam*: |step| ~ lr regardless of |g|
     ts.close()
