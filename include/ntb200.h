@@ -244,8 +244,12 @@ int nt_vit_blocks_bwd(const NtVitBlock* blocks, int nblocks, const float* x, con
  * backward recomputes it from q, k), `save` is unused, `wfrag` holds nt_vit_tc_wimg_bytes(D) bytes of weight tiles. */
 int nt_vit_tc_supported(int N, int D, int H, int* ok);
 int nt_vit_tc_wimg_bytes(int D, size_t* bytes);
+int nt_vit_tc_debug(long long* stamps);   /* development aid: [2][16][16] clock64 phase stamps of CTA 0, NULL = off */
 int nt_vit_tc_prepare(const NtVitBlock* blocks, int nblocks, int D, int H);
 int nt_vit_tc_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H, int prepared);
+/* backward of the same stack (needs the forward's qkv / h / pre-activation / block outputs and the weight tiles of the
+ * same step); dx [B,N,D] doubles as scratch during the call */
+int nt_vit_tc_bwd(const NtVitBlock* blocks, int nblocks, const float* x, const float* dout, float* dx, int B, int N, int D, int H);
 
 /* ---------------------------------------------------------------- embeds */
 /* PatchEmbed_flatten.forward patch loops, PatchEmbed.py:22-36: (B,C,Hi,Wi) -> (B, n_patch^2, C*h*w) */

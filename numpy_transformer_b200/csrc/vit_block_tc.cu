@@ -31,7 +31,11 @@ struct Args {
   const float* x;       // [B,N,D] input of block 0
   const float* dout;    // [B,N,D] gradient w.r.t. the last block's output      (backward)
   float* dx;            // [B,N,D] gradient w.r.t. x                              (backward)
+  long long* dbg;       // optional: phase time stamps (clock64) of CTA 0, [role][block][event]
 };
+__device__ __forceinline__ void stamp(const Args& a, int role, int bi, int ev) {
+  if (a.dbg && blockIdx.x == 0) a.dbg[(role * MAXB + bi) * 16 + ev] = clock64();
+}
 
 constexpr int D = 96, H = 4, DH = 24, DHP = 32, HD = 192;
 constexpr int ROWS = 64;                       // token rows of a plane chunk
@@ -183,6 +187,21 @@ __device__ __forceinline__ void store24_global(float* p, const float (&v)[24]) {
 #pragma unroll
   for (int j = 0; j < 6; j++) *reinterpret_cast<float4*>(p + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
+// "Tiled" fp32 saves: a per-image [N][W] tensor is kept as [W/4][N][4] (16-byte unit u of every row r contiguous over r),
+// so that the 32 lanes of a warp — 32 consecutive rows — store / load 512 contiguous bytes per instruction instead of 32
+// separate sectors.  Only this kernel pair reads them; the host side un-tiles on demand (fused_vit.untile).
+__device__ __forceinline__ void store24_tiled(float* img_base, int N, int r, int u0, const float (&v)[24]) {
+#pragma unroll
+  for (int j = 0; j < 6; j++)
+    *reinterpret_cast<float4*>(img_base + ((size_t)(u0 + j) * N + r) * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void load24_tiled(const float* img_base, int N, int r, int u0, float (&v)[24]) {
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const float4 t = *reinterpret_cast<const float4*>(img_base + ((size_t)(u0 + j) * N + r) * 4);
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
 __device__ __forceinline__ void load24_global(const float* p, float (&v)[24]) {
 #pragma unroll
   for (int j = 0; j < 6; j++) {
@@ -269,8 +288,10 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
       for (int bi = 0; bi < a.nblocks; bi++) {
         const uint32_t ph = bi & 1;
         // ---- qkv = LN(x) Wqkv                                          attention.py:23-24
+        stamp(a, 1, bi, 0);
         mbar_wait(&bar[FB_U], ph);
         tc_fence_after();
+        stamp(a, 1, bi, 1);
         for (int nt = 0; nt < 3; nt++) {
           for (int kc = 0; kc < 2; kc++) {
             const uint32_t st = stage_wait();
@@ -280,8 +301,10 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
           mma_commit(&bar[FB_QKVACC + nt]);
         }
         // ---- S_h = Q_h K_h^T                                           attention.py:35-36
+        stamp(a, 1, bi, 2);
         mbar_wait(&bar[FB_QKVRDY], ph);
         tc_fence_after();
+        stamp(a, 1, bi, 3);
         for (int h = 0; h < H; h++) {
           const uint32_t off = (h >> 1) * CH + (h & 1) * 64;
 #pragma unroll
@@ -311,8 +334,10 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
           mma_commit(&bar[FB_O + h]);
         }
         // ---- pre = LN1(h) W0                                           attention.py:49
+        stamp(a, 1, bi, 4);
         mbar_wait(&bar[FB_U1], ph);
         tc_fence_after();
+        stamp(a, 1, bi, 5);
         for (int nt = 0; nt < 2; nt++) {
           for (int kc = 0; kc < 2; kc++) {
             const uint32_t st = stage_wait();
@@ -322,14 +347,17 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
           mma_commit(&bar[FB_F0 + nt]);
         }
         // ---- y = GELU(pre) W1                                          attention.py:51
+        stamp(a, 1, bi, 6);
         mbar_wait(&bar[FB_G], ph);
         tc_fence_after();
+        stamp(a, 1, bi, 7);
         for (int kc = 0; kc < 3; kc++) {
           const uint32_t st = stage_wait();
           mma_stage(aB + kc * CH, aB + 3 * CH + kc * CH, st, 4, tbase + 416, id_lin, kc == 0);
           stage_done();
         }
         mma_commit(&bar[FB_F1]);
+        stamp(a, 1, bi, 8);
       }
     }
     __syncwarp();
@@ -354,6 +382,8 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
       const NtVitBlock& P = a.blk[bi];
       const uint32_t ph = bi & 1;
       float v[24];
+      const bool t0 = tid == 0;
+      if (t0) stamp(a, 0, bi, 0);
       // ---- u = LN(x) -> A planes                                       attention.py:22
       {
         float mean, rstd;
@@ -363,15 +393,17 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
           v[c] = live ? (x[c] - mean) * rstd * __ldg(P.ln_g + 24 * g + c) + __ldg(P.ln_b + 24 * g + c) : 0.f;
         store24_split(sA, sA + 2 * CH, r, 24 * g, v);
         arrive(FB_U);
+        if (t0) stamp(a, 0, bi, 1);
       }
       // ---- q | k | v = acc + bias -> head-padded planes (+ fp32 copy for the backward / the layer API)
       for (int nt = 0; nt < 3; nt++) {
         mbar_wait(&bar[FB_QKVACC + nt], ph);
         tc_fence_after();
+        if (t0) stamp(a, 0, bi, 2 + nt);
         ld24(lane_addr + NT * nt + 24 * g, v);
 #pragma unroll
         for (int c = 0; c < 24; c++) v[c] = live ? v[c] + __ldg(P.bqkv + NT * nt + 24 * g + c) : 0.f;
-        if (live) store24_global(P.qkv + ((size_t)img * N + r) * 3 * D + NT * nt + 24 * g, v);
+        if (live) store24_tiled(P.qkv + (size_t)img * N * 3 * D, N, r, 24 * nt + 6 * g, v);
         store24_split(sB + nt * 4 * CH, sB + nt * 4 * CH + 2 * CH, r, DHP * g, v);
         // the 8 padding columns of the head: P (heads 2, 3) and G were parked over these planes, so re-zero them every block
         const uint32_t zoff = plane_off(r, DHP * g + DH, CH);
@@ -379,11 +411,13 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
         *reinterpret_cast<uint4*>(sB + nt * 4 * CH + 2 * CH + zoff) = make_uint4(0, 0, 0, 0);
       }
       arrive(FB_QKVRDY);
+      if (t0) stamp(a, 0, bi, 5);
       // ---- P = softmax(S / sqrt(dh)) for head g                         attention.py:37-41
       {
         mbar_wait(&bar[FB_S + g], ph);
         if (g >= 2) mbar_wait(&bar[FB_S + 3], ph);          // heads 2, 3 park P in the q planes: every S product must be done
         tc_fence_after();
+        if (t0) stamp(a, 0, bi, 6);
         uint32_t s0[32], s1[32];
         tmem_ld32(lane_addr + 64 * g, s0);
         tmem_ld32(lane_addr + 64 * g + 32, s1);
@@ -407,7 +441,7 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
         }
         const float inv = live ? __fdividef(1.0f, sum) : 0.f;
         uint8_t* ph_ = (g < 2 ? sA : sB) + (g & 1) * 2 * CH;
-        float* pg = P.P ? P.P + (((size_t)img * H + g) * N + r) * N : nullptr;
+        float* pg = P.P ? P.P + ((size_t)img * H + g) * (size_t)((N + 3) / 4) * N * 4 : nullptr;   // tiled [ceil(N/4)][N][4]
 #pragma unroll
         for (int j8 = 0; j8 < 8; j8++) {
           float w[8];
@@ -417,22 +451,23 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
             w[i] = live ? __uint_as_float(j < 32 ? s0[j & 31] : s1[j & 31]) * inv : 0.f;
           }
           store8_split(ph_, ph_ + CH, r, 8 * j8, CH, w);
-          if (pg && live) {
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-              if (8 * j8 + i < N) pg[8 * j8 + i] = w[i];                 // the reference's atg__ (attention.py:41)
+          if (pg && live) {                                             // the reference's atg__ (attention.py:41)
+            if (8 * j8 < N) *reinterpret_cast<float4*>(pg + ((size_t)(2 * j8) * N + r) * 4) = make_float4(w[0], w[1], w[2], w[3]);
+            if (8 * j8 + 4 < N) *reinterpret_cast<float4*>(pg + ((size_t)(2 * j8 + 1) * N + r) * 4) = make_float4(w[4], w[5], w[6], w[7]);
           }
         }
         arrive(FB_P + g);
+        if (t0) stamp(a, 0, bi, 7);
       }
       // ---- h = x + O_g ; u1 = LN1(h)                                   attention.py:46-48
       {
         mbar_wait(&bar[FB_O + g], ph);
         tc_fence_after();
+        if (t0) stamp(a, 0, bi, 8);
         ld24(lane_addr + 288 + DHP * g, v);
 #pragma unroll
         for (int c = 0; c < 24; c++) x[c] = live ? x[c] + v[c] : 0.f;
-        if (live) store24_global(P.h + ((size_t)img * N + r) * D + 24 * g, x);
+        if (live) store24_tiled(P.h + (size_t)img * N * D, N, r, 6 * g, x);
         float mean, rstd;
         row_stats(x, stat, r, g, mean, rstd);
 #pragma unroll
@@ -440,15 +475,17 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
           v[c] = live ? (x[c] - mean) * rstd * __ldg(P.ln1_g + 24 * g + c) + __ldg(P.ln1_b + 24 * g + c) : 0.f;
         store24_split(sA, sA + 2 * CH, r, 24 * g, v);
         arrive(FB_U1);
+        if (t0) stamp(a, 0, bi, 9);
       }
       // ---- pre = acc + b0 ; G = GELU(pre) -> planes (aliasing q | k)    attention.py:49-50
       for (int nt = 0; nt < 2; nt++) {
         mbar_wait(&bar[FB_F0 + nt], ph);
         tc_fence_after();
+        if (t0) stamp(a, 0, bi, 10 + nt);
         ld24(lane_addr + NT * nt + 24 * g, v);
 #pragma unroll
         for (int c = 0; c < 24; c++) v[c] = live ? v[c] + __ldg(P.b0 + NT * nt + 24 * g + c) : 0.f;
-        if (live) store24_global(P.dgelu + ((size_t)img * N + r) * HD + NT * nt + 24 * g, v);   // pre-activation, kept for backward
+        if (live) store24_tiled(P.dgelu + (size_t)img * N * HD, N, r, 24 * nt + 6 * g, v);   // pre-activation, kept for backward
 #pragma unroll
         for (int c = 0; c < 24; c++) {
           float y, dy;
@@ -458,14 +495,21 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
         store24_split(sB, sB + 3 * CH, r, NT * nt + 24 * g, v);
       }
       arrive(FB_G);
+      if (t0) stamp(a, 0, bi, 12);
       // ---- out = h + acc + b1                                           attention.py:51-53
       {
         mbar_wait(&bar[FB_F1], ph);
         tc_fence_after();
+        if (t0) stamp(a, 0, bi, 13);
         ld24(lane_addr + 416 + 24 * g, v);
 #pragma unroll
         for (int c = 0; c < 24; c++) x[c] = live ? x[c] + v[c] + __ldg(P.b1 + 24 * g + c) : 0.f;
-        if (live) store24_global(P.out + ((size_t)img * N + r) * D + 24 * g, x);
+        if (live) {
+          // the stack's output in the caller's row-major layout; block outputs in between are only read by the backward
+          if (bi == a.nblocks - 1) store24_global(P.out + ((size_t)img * N + r) * D + 24 * g, x);
+          else store24_tiled(P.out + (size_t)img * N * D, N, r, 6 * g, x);
+        }
+        if (t0) stamp(a, 0, bi, 14);
       }
     }
     tc_fence_before();
@@ -477,7 +521,595 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
   }
 }
 
+// ================================================================================================ backward
+// Warp roles (16 warps): token warps {0,1,4,5,8,9,12,13} (one token row per thread, column group g = head g), loader 2,
+// critical-path MMA issuer 3, weight-gradient ("flush") warps {6,7,10,11} on TMEM lanes 64..127, flush MMA issuer 14.
+//
+// Weight gradients dW = X^T dY are contracted over the image's tokens with the activation planes as MN-major operands
+// (no transposes).  Their M index is the input FEATURE; the A descriptor starts one 64-feature chunk early so that the
+// wanted 64 features land in accumulator rows 64..127 = the TMEM lanes of warps that are NOT on the critical path, which
+// add them to the gradient arena with red.global.add.v4 (the reference's `+=` into *_delta, fullconnect.py:118-122).  A
+// constant 1 in the first padding column of U / U1 makes row 96 of dWqkv / dW0 the bias gradient.
+constexpr int BTHREADS = 512;
+constexpr int BNSTAGE = 2;
+constexpr uint32_t BOFF_D = 0;                              // 4 chunks
+constexpr uint32_t BOFF_X = 4 * CH;                         // 16 chunks
+constexpr uint32_t BOFF_RING = 20 * CH;
+constexpr uint32_t BOFF_STAT = BOFF_RING + BNSTAGE * STAGE; // [2][64][4] floats
+constexpr uint32_t BOFF_BAR = BOFF_STAT + 2 * 64 * 4 * 4;
+constexpr int BNBAR = 2 * BNSTAGE + 48;
+constexpr uint32_t BSMEM_BYTES = BOFF_BAR + BNBAR * 8 + 16;
+static_assert(BSMEM_BYTES <= 232448, "shared memory budget (backward)");
+// chunk indices inside the operand area (chunk c lives at smem + c * CH)
+constexpr int C_DH = 0, C_DL = 2;                           // d / dO: hi chunks 0,1  lo chunks 2,3
+constexpr int C_GH = 4, C_GL = 7, C_PH = 10, C_PL = 13, C_U1H = 16, C_U1L = 18;     // MLP phase: G, dpre, LN1(h)
+constexpr int C_QH = 4, C_QL = 10;                          // attention phase: [q c0 c1 | k c0 c1 | v c0 c1] hi, then lo
+constexpr int C_PS = 16;                                    // PS[b]: hi chunk 16 + 2b, lo chunk 17 + 2b
+constexpr int C_UH = 16, C_UL = 18;                         // LN(x) for dWqkv (after the attention phase)
+enum { BB_D = 0, BB_DGACC = 1 /*2*/, BB_GDP = 3, BB_DU1ACC = 4, BB_ATT = 5, BB_SACC = 6 /*4*/, BB_SCONS = 10 /*4*/, BB_DPACC = 14 /*4*/,
+       BB_P = 18 /*4*/, BB_DVACC = 22 /*4*/, BB_DS = 26 /*4*/, BB_DQKACC = 30 /*4*/, BB_DQKV = 34, BB_U = 35, BB_DUACC = 36,
+       BB_DW1_DONE = 37, BB_DW0_DONE = 38, BB_DWQKV_DONE = 39, BB_FFULL = 40 /*2*/, BB_FFREE = 42 /*2*/, BB_COUNT = 44 };
+constexpr int PIECES = 24;                                  // weight-gradient pieces per block: dW1 6, dW0 6, dWqkv 12
+
+// column sums over the 32 rows of a warp of 24 per-thread values: reduce-scatter (the lanes trade halves of their columns),
+// then two full butterfly steps.  Afterwards every lane holds the sums of columns c0, c0+1, c0+2 with
+// c0 = 12*bit4(lane) + 6*bit3(lane) + 3*bit2(lane); the lanes with (lane & 3) == 0 cover all 24 columns once.
+__device__ __forceinline__ void colsum24(const float (&v)[24], int lane, float (&out)[3], int& c0) {
+  float a[12], b[6];
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    const float send = u16 ? v[i] : v[12 + i], keep = u16 ? v[12 + i] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const float send = u8 ? a[i] : a[6 + i], keep = u8 ? a[6 + i] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float send = u4 ? b[i] : b[3 + i], keep = u4 ? b[3 + i] : b[i];
+    float t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    out[i] = t;
+  }
+  c0 = (u16 ? 12 : 0) + (u8 ? 6 : 0) + (u4 ? 3 : 0);
+}
+// dst[24*g + c] += sum over the warp's rows of v[c]
+__device__ __forceinline__ void colsum24_atomic(const float (&v)[24], int lane, float* dst) {
+  float o[3];
+  int c0;
+  colsum24(v, lane, o, c0);
+  if ((lane & 3) == 0) {
+    atomicAdd(dst + c0, o[0]);
+    atomicAdd(dst + c0 + 1, o[1]);
+    atomicAdd(dst + c0 + 2, o[2]);
+  }
+}
+__device__ __forceinline__ void red4(float* p, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// row-wise sums of two per-thread partials over the 4 column groups (LayerNorm backward)
+__device__ __forceinline__ void row_sum2(float p1, float p2, float* stat, int r, int g, float& s1, float& s2) {
+  stat[r * 4 + g] = p1;
+  stat[256 + r * 4 + g] = p2;
+  named_bar_sync(1, EPI_THREADS);
+  const float4 t = *reinterpret_cast<const float4*>(stat + r * 4), u = *reinterpret_cast<const float4*>(stat + 256 + r * 4);
+  s1 = t.x + t.y + t.z + t.w;
+  s2 = u.x + u.y + u.z + u.w;
+  named_bar_sync(1, EPI_THREADS);            // the buffer may be rewritten right away
+}
+// a 16-byte unit [1, 0, .., 0] (bf16) at column c0 of row r: the "ones" feature that turns a weight-gradient row into the bias gradient
+__device__ __forceinline__ void store_ones_unit(uint8_t* hi, uint8_t* lo, int r, int c0, bool one) {
+  const uint32_t off = plane_off(r, c0, CH);
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(one ? 0x00003F80u : 0u, 0, 0, 0);
+  *reinterpret_cast<uint4*>(lo + off) = make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem_raw) & 1023u) __trap();
+  float* stat = reinterpret_cast<float*>(smem + BOFF_STAT);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + BOFF_BAR);
+  uint64_t* empty = full + BNSTAGE;
+  uint64_t* bar = empty + BNSTAGE;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 48);
+  auto chunk = [&](int c) -> uint8_t* { return smem + (uint32_t)c * CH; };
+
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.N, img = blockIdx.x, L = a.nblocks;
+  const bool is_tok = (warp & 3) < 2;
+  const int q = warp & 3, g = warp >> 2, r = 32 * q + lane;
+
+  if (tid == 0) {
+    for (int s = 0; s < BNSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < BB_COUNT; i++) mbar_init(&bar[i], 1);
+    const int eights[] = {BB_D, BB_GDP, BB_ATT, BB_DQKV, BB_U};
+    for (int i = 0; i < 5; i++) mbar_init(&bar[eights[i]], 8);
+    for (int i = 0; i < 4; i++) { mbar_init(&bar[BB_SCONS + i], 2); mbar_init(&bar[BB_P + i], 2); mbar_init(&bar[BB_DS + i], 2); }
+    mbar_init(&bar[BB_FFREE], 4); mbar_init(&bar[BB_FFREE + 1], 4);
+    mbar_fence_init();
+  }
+  for (uint32_t i = tid * 16; i < 20 * CH; i += BTHREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  if (warp == 3) tmem_alloc<512>(tslot);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tslot;
+  const uint32_t sm0 = smem_u32(smem);
+  auto caddr = [&](int c) -> uint32_t { return sm0 + (uint32_t)c * CH; };
+  pdl_wait();
+
+  if (warp == 2) {
+    // ===================== loader =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int bi = L - 1; bi >= 0; bi--) {
+        const uint8_t* wimg = reinterpret_cast<const uint8_t*>(a.blk[bi].wfrag) + (size_t)FWD_STAGES * STAGE;
+        for (int i = 0; i < BWD_STAGES; i++, it++) {
+          const int s = it % BNSTAGE;
+          if (it >= BNSTAGE) mbar_wait(&empty[s], ((it / BNSTAGE) - 1) & 1);
+          mbar_expect_tx(&full[s], STAGE);
+          bulk_g2s(smem + BOFF_RING + s * STAGE, wimg + (size_t)i * STAGE, STAGE, &full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ===================== critical-path MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t id_lin = idesc_bf16(128, NT, 0, 0), id_s = idesc_bf16(128, 64, 0, 0);
+      const uint32_t id_dv = idesc_bf16(128, DHP, 1, 1), id_dq = idesc_bf16(128, DHP, 0, 1);
+      uint32_t it = 0;
+      auto stage_wait = [&]() -> uint32_t {
+        const int s = it % BNSTAGE;
+        mbar_wait(&full[s], (it / BNSTAGE) & 1);
+        tc_fence_after();
+        return sm0 + BOFF_RING + s * STAGE;
+      };
+      auto stage_done = [&]() { mma_commit(&empty[it % BNSTAGE]); it++; };
+      auto wait = [&](int b, uint32_t ph) { mbar_wait(&bar[b], ph); tc_fence_after(); };
+      for (int n = 0; n < L; n++) {
+        const uint32_t ph = n & 1;
+        // ---- dG = d W1^T                                               attention.py:58
+        wait(BB_D, ph);
+        for (int nt = 0; nt < 2; nt++) {
+          for (int kc = 0; kc < 2; kc++) {
+            const uint32_t st = stage_wait();
+            mma_stage(caddr(C_DH + kc), caddr(C_DL + kc), st, kc ? 2 : 4, tbase + NT * nt, id_lin, kc == 0);
+            stage_done();
+          }
+          mma_commit(&bar[BB_DGACC + nt]);
+        }
+        // ---- dU1 = dpre W0^T                                           attention.py:60
+        wait(BB_GDP, ph);
+        for (int kc = 0; kc < 3; kc++) {
+          const uint32_t st = stage_wait();
+          mma_stage(caddr(C_PH + kc), caddr(C_PL + kc), st, 4, tbase + 192, id_lin, kc == 0);
+          stage_done();
+        }
+        mma_commit(&bar[BB_DU1ACC]);
+        // ---- attention backward                                        attention.py:63-84
+        wait(BB_ATT, ph);
+        auto hoff = [&](int h) -> uint32_t { return (uint32_t)(h >> 1) * CH + (uint32_t)(h & 1) * 64u; };
+        const uint32_t Qh = caddr(C_QH), Ql = caddr(C_QL), Kh = caddr(C_QH + 2), Kl = caddr(C_QL + 2), Vh = caddr(C_QH + 4), Vl = caddr(C_QL + 4);
+        const uint32_t Oh = caddr(C_DH), Ol = caddr(C_DL);
+        for (int h = 0; h < H; h++) {                         // S_h = Q_h K_h^T (recomputed)
+          const uint32_t off = hoff(h);
+#pragma unroll
+          for (int ks = 0; ks < 2; ks++) {
+            const uint32_t o = off + ks * KMAJ_STEP;
+            mma_bf16(tbase + 64 * h, desc_kmajor(Ql + o), desc_kmajor(Kh + o), id_s, ks ? 1u : 0u);
+            mma_bf16(tbase + 64 * h, desc_kmajor(Qh + o), desc_kmajor(Kl + o), id_s, 1u);
+            mma_bf16(tbase + 64 * h, desc_kmajor(Qh + o), desc_kmajor(Kh + o), id_s, 1u);
+          }
+          mma_commit(&bar[BB_SACC + h]);
+        }
+        auto dP_dV = [&](int h) {
+          const uint32_t off = hoff(h);
+          wait(BB_SCONS + h, ph);                             // the softmax threads hold S_h in registers: its columns are free
+#pragma unroll
+          for (int ks = 0; ks < 2; ks++) {                    // dP_h = dO_h V_h^T  (attention.py:74)
+            const uint32_t o = off + ks * KMAJ_STEP;
+            mma_bf16(tbase + 64 * h, desc_kmajor(Ol + o), desc_kmajor(Vh + o), id_s, ks ? 1u : 0u);
+            mma_bf16(tbase + 64 * h, desc_kmajor(Oh + o), desc_kmajor(Vl + o), id_s, 1u);
+            mma_bf16(tbase + 64 * h, desc_kmajor(Oh + o), desc_kmajor(Vh + o), id_s, 1u);
+          }
+          mma_commit(&bar[BB_DPACC + h]);
+          wait(BB_P + h, ph);
+          const uint32_t Ph = caddr(C_PS + 2 * (h & 1)), Pl = Ph + CH;
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {                    // dV_h = P_h^T dO_h  (attention.py:76): both operands MN-major
+            const uint32_t pa = ks * MNMAJ_STEP, ob = off + ks * MNMAJ_STEP;
+            mma_bf16(tbase + 256 + DHP * h, desc_mnmajor(Pl + pa, CH), desc_mnmajor(Oh + ob, CH), id_dv, ks ? 1u : 0u);
+            mma_bf16(tbase + 256 + DHP * h, desc_mnmajor(Ph + pa, CH), desc_mnmajor(Ol + ob, CH), id_dv, 1u);
+            mma_bf16(tbase + 256 + DHP * h, desc_mnmajor(Ph + pa, CH), desc_mnmajor(Oh + ob, CH), id_dv, 1u);
+          }
+          mma_commit(&bar[BB_DVACC + h]);
+        };
+        auto dQ_dK = [&](int h) {
+          const uint32_t off = hoff(h);
+          wait(BB_DS + h, ph);
+          const uint32_t Sh = caddr(C_PS + 2 * (h & 1)), Sl = Sh + CH;
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {                    // dQ_h = dS_h K_h  (attention.py:78), dS already carries 1/sqrt(dh)
+            const uint32_t kb = off + ks * MNMAJ_STEP;
+            mma_bf16(tbase + 64 * h, desc_kmajor(Sl + ks * KMAJ_STEP), desc_mnmajor(Kh + kb, CH), id_dq, ks ? 1u : 0u);
+            mma_bf16(tbase + 64 * h, desc_kmajor(Sh + ks * KMAJ_STEP), desc_mnmajor(Kl + kb, CH), id_dq, 1u);
+            mma_bf16(tbase + 64 * h, desc_kmajor(Sh + ks * KMAJ_STEP), desc_mnmajor(Kh + kb, CH), id_dq, 1u);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {                    // dK_h = dS_h^T Q_h  (attention.py:79)
+            const uint32_t sa = ks * MNMAJ_STEP, qb = off + ks * MNMAJ_STEP;
+            mma_bf16(tbase + 64 * h + 32, desc_mnmajor(Sl + sa, CH), desc_mnmajor(Qh + qb, CH), id_dv, ks ? 1u : 0u);
+            mma_bf16(tbase + 64 * h + 32, desc_mnmajor(Sh + sa, CH), desc_mnmajor(Ql + qb, CH), id_dv, 1u);
+            mma_bf16(tbase + 64 * h + 32, desc_mnmajor(Sh + sa, CH), desc_mnmajor(Qh + qb, CH), id_dv, 1u);
+          }
+          mma_commit(&bar[BB_DQKACC + h]);
+        };
+        dP_dV(0); dP_dV(1); dQ_dK(0); dQ_dK(1); dP_dV(2); dP_dV(3); dQ_dK(2); dQ_dK(3);
+        // ---- dU = dqkv Wqkv^T                                          attention.py:85
+        wait(BB_DQKV, ph);
+        for (int kc = 0; kc < 6; kc++) {
+          const uint32_t st = stage_wait();
+          mma_stage(caddr(C_QH + kc), caddr(C_QL + kc), st, 4, tbase, id_lin, kc == 0);
+          stage_done();
+        }
+        mma_commit(&bar[BB_DUACC]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 14) {
+    // ===================== weight-gradient MMA issuer =====================
+    if (lane == 0) {
+      uint32_t piece = 0;
+      auto wait = [&](int b, uint32_t ph) { mbar_wait(&bar[b], ph); tc_fence_after(); };
+      // one piece: accumulator rows 64..127 <- features [64 f, 64 f + 64) of the A plane, N columns of the B plane chunk
+      auto issue = [&](uint32_t a_hi, uint32_t a_lo, int f, uint32_t b_hi, uint32_t b_lo, int ncols) {
+        const int buf = piece & 1;
+        if (piece >= 2) wait(BB_FFREE + buf, ((piece >> 1) - 1) & 1);
+        const uint32_t idesc = idesc_bf16(128, ncols, 1, 1), tacc = tbase + 384 + 64 * buf;
+        const uint32_t ah = a_hi + (uint32_t)(f - 1) * CH, al = a_lo + (uint32_t)(f - 1) * CH;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+          const uint32_t o = ks * MNMAJ_STEP;
+          mma_bf16(tacc, desc_mnmajor(al + o, CH), desc_mnmajor(b_hi + o, CH), idesc, ks ? 1u : 0u);
+          mma_bf16(tacc, desc_mnmajor(ah + o, CH), desc_mnmajor(b_lo + o, CH), idesc, 1u);
+          mma_bf16(tacc, desc_mnmajor(ah + o, CH), desc_mnmajor(b_hi + o, CH), idesc, 1u);
+        }
+        mma_commit(&bar[BB_FFULL + buf]);
+        piece++;
+      };
+      for (int n = 0; n < L; n++) {
+        const uint32_t ph = n & 1;
+        wait(BB_GDP, ph);                                     // G, dpre, LN1(h) (and d) are in place
+        for (int f = 0; f < 3; f++)                           // dW1 += G^T d            fullconnect.py:118-121
+          for (int j = 0; j < 2; j++) issue(caddr(C_GH), caddr(C_GL), f, caddr(C_DH + j), caddr(C_DL + j), j ? 32 : 64);
+        mma_commit(&bar[BB_DW1_DONE]);
+        for (int f = 0; f < 2; f++)                           // dW0 (+ db0) += [LN1(h) | 1]^T dpre
+          for (int j = 0; j < 3; j++) issue(caddr(C_U1H), caddr(C_U1L), f, caddr(C_PH + j), caddr(C_PL + j), 64);
+        mma_commit(&bar[BB_DW0_DONE]);
+        wait(BB_DQKV, ph);
+        wait(BB_U, ph);
+        for (int f = 0; f < 2; f++)                           // dWqkv (+ dbqkv) += [LN(x) | 1]^T dqkv
+          for (int j = 0; j < 6; j++) issue(caddr(C_UH), caddr(C_UL), f, caddr(C_QH + j), caddr(C_QL + j), 64);
+        mma_commit(&bar[BB_DWQKV_DONE]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 6 || warp == 7 || warp == 10 || warp == 11) {
+    // ===================== weight-gradient flush: TMEM lanes 64..127 -> red.global.add =====================
+    const int fq = warp & 3, fc = (warp >> 2) - 1, fl = 32 * (fq - 2) + lane;       // feature within the 64-feature half
+    uint32_t piece = 0;
+    for (int n = 0; n < L; n++) {
+      const NtVitBlock& P = a.blk[L - 1 - n];
+      for (int p = 0; p < PIECES; p++, piece++) {
+        const int buf = piece & 1;
+        mbar_wait(&bar[BB_FFULL + buf], (piece >> 1) & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tbase + ((uint32_t)(32 * fq) << 16) + 384 + 64 * buf + 32 * fc, v);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[BB_FFREE + buf]);
+        float* dst = nullptr;
+        int ncol = 32;
+        if (p < 6) {
+          const int f = p >> 1, j = p & 1, F = 64 * f + fl;
+          if (!(j == 1 && fc == 1)) dst = P.d_w1 + (size_t)F * D + 64 * j + 32 * fc;           // F < 192 always
+        } else if (p < 12) {
+          const int f = (p - 6) / 3, j = (p - 6) % 3, F = 64 * f + fl;
+          if (F < D) dst = P.d_w0 + (size_t)F * HD + 64 * j + 32 * fc;
+          else if (F == D) dst = P.d_b0 + 64 * j + 32 * fc;
+        } else {
+          const int f = (p - 12) / 6, j = (p - 12) % 6, F = 64 * f + fl;
+          const int col = (j >> 1) * D + DH * (2 * (j & 1) + fc);       // [q|k|v][head][24] <- padded [part][head][32]
+          if (F < D) dst = P.d_wqkv + (size_t)F * 3 * D + col;
+          else if (F == D) dst = P.d_bqkv + col;
+          ncol = DH;
+        }
+        if (dst) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            if (c < ncol)
+              red4(dst + c, __uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+        }
+      }
+    }
+  } else if (is_tok) {
+    // ===================== token warps: the backward chain of one token row =====================
+    const bool live = r < N;
+    const float scale = rsqrtf((float)DH);
+    const uint32_t lane_addr = tbase + ((uint32_t)(32 * q) << 16);
+    auto arrive = [&](int b) {
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[b]);
+    };
+    auto wait = [&](int b, uint32_t ph) { mbar_wait(&bar[b], ph); tc_fence_after(); };
+    float d[24];                                             // gradient w.r.t. the current block's output
+    if (live) load24_global(a.dout + ((size_t)img * N + r) * D + 24 * g, d);
+    else {
+#pragma unroll
+      for (int c = 0; c < 24; c++) d[c] = 0.f;
+    }
+    float* dh_scratch = a.dx + (size_t)img * N * D;           // dh parked here (tiled) during the attention phase
+    for (int n = 0; n < L; n++) {
+      const int bi = L - 1 - n;
+      const NtVitBlock& P = a.blk[bi];
+      const uint32_t ph = n & 1;
+      float v[24], w[24];
+      // ---- d -> operand planes; db1 += colsum(d)                         fullconnect.py:122
+      colsum24_atomic(d, lane, P.d_b1 + 24 * g);
+      if (n > 0) wait(BB_DW1_DONE, (n - 1) & 1);               // the previous block's dW1 products read the d planes
+      store24_split(chunk(C_DH), chunk(C_DL), r, 24 * g, d);
+      arrive(BB_D);
+      // ---- u1 = LN1(h) (recomputed), xhat1 kept for the LayerNorm backward
+      float xh[24], rstd1;
+      {
+        if (live) load24_tiled(P.h + (size_t)img * N * D, N, r, 6 * g, v);
+        else {
+#pragma unroll
+          for (int c = 0; c < 24; c++) v[c] = 0.f;
+        }
+        float mean;
+        row_stats(v, stat, r, g, mean, rstd1);
+#pragma unroll
+        for (int c = 0; c < 24; c++) {
+          xh[c] = live ? (v[c] - mean) * rstd1 : 0.f;
+          w[c] = live ? xh[c] * __ldg(P.ln1_g + 24 * g + c) + __ldg(P.ln1_b + 24 * g + c) : 0.f;
+        }
+        if (n > 0) wait(BB_DWQKV_DONE, (n - 1) & 1);           // the previous block's dWqkv products read this area (LN(x), dqkv)
+        store24_split(chunk(C_U1H), chunk(C_U1L), r, 24 * g, w);
+        if (g == 0) store_ones_unit(chunk(C_U1H), chunk(C_U1L), r, D, live);
+      }
+      // ---- dG -> G = GELU(pre), dpre = dG * GELU'(pre)                   attention.py:58-59
+      for (int nt = 0; nt < 2; nt++) {
+        wait(BB_DGACC + nt, ph);
+        ld24(lane_addr + NT * nt + 24 * g, v);
+        if (live) load24_tiled(P.dgelu + (size_t)img * N * HD, N, r, 24 * nt + 6 * g, w);
+        else {
+#pragma unroll
+          for (int c = 0; c < 24; c++) w[c] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 24; c++) {
+          float y, dy;
+          gelu_both(w[c], y, dy);
+          w[c] = live ? y : 0.f;
+          v[c] = live ? v[c] * dy : 0.f;
+        }
+        store24_split(chunk(C_GH), chunk(C_GL), r, NT * nt + 24 * g, w);
+        store24_split(chunk(C_PH), chunk(C_PL), r, NT * nt + 24 * g, v);
+      }
+      arrive(BB_GDP);
+      // ---- dh = d + LN1-backward(dU1); dgamma1, dbeta1                    attention.py:61-62, layernorm.py:116-135
+      {
+        wait(BB_DU1ACC, ph);
+        ld24(lane_addr + 192 + 24 * g, v);
+        float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 24; c++) {
+          if (!live) v[c] = 0.f;
+          w[c] = v[c] * xh[c];                                 // dgamma contribution
+          const float gd = v[c] * __ldg(P.ln1_g + 24 * g + c);
+          p1 += gd;
+          p2 += gd * xh[c];
+        }
+        colsum24_atomic(w, lane, P.d_ln1_g + 24 * g);
+        colsum24_atomic(v, lane, P.d_ln1_b + 24 * g);
+        float s1, s2;
+        row_sum2(p1, p2, stat, r, g, s1, s2);
+        s1 *= (1.0f / D); s2 *= (1.0f / D);
+#pragma unroll
+        for (int c = 0; c < 24; c++) {
+          const float gd = v[c] * __ldg(P.ln1_g + 24 * g + c);
+          d[c] = live ? d[c] + rstd1 * (gd - s1 - xh[c] * s2) : 0.f;
+        }
+        if (live) store24_tiled(dh_scratch, N, r, 6 * g, d);
+      }
+      // ---- dO (= dh) and q, k, v -> head-padded planes
+      {
+        wait(BB_DW0_DONE, ph);                                 // dW1 / dW0 products have read d, G, dpre, LN1(h)
+        store24_split(chunk(C_DH), chunk(C_DL), r, DHP * g, d);
+        {
+          const uint32_t zoff = plane_off(r, DHP * g + DH, CH);
+          *reinterpret_cast<uint4*>(chunk(C_DH) + zoff) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(chunk(C_DL) + zoff) = make_uint4(0, 0, 0, 0);
+        }
+        for (int part = 0; part < 3; part++) {
+          if (live) load24_tiled(P.qkv + (size_t)img * N * 3 * D, N, r, 24 * part + 6 * g, v);
+          else {
+#pragma unroll
+            for (int c = 0; c < 24; c++) v[c] = 0.f;
+          }
+          store24_split(chunk(C_QH + 2 * part), chunk(C_QL + 2 * part), r, DHP * g, v);
+          const uint32_t zoff = plane_off(r, DHP * g + DH, CH);
+          *reinterpret_cast<uint4*>(chunk(C_QH + 2 * part) + zoff) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(chunk(C_QL + 2 * part) + zoff) = make_uint4(0, 0, 0, 0);
+        }
+        arrive(BB_ATT);
+      }
+      // ---- head g: P (recomputed), dS = P o (dP - rowsum(dP o P)) / sqrt(dh)        attention.py:74-75
+      {
+        uint32_t s0[32], s1[32];
+        wait(BB_SACC + g, ph);
+        tmem_ld32(lane_addr + 64 * g, s0);
+        tmem_ld32(lane_addr + 64 * g + 32, s1);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[BB_SCONS + g]);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const float t0 = j < N ? __uint_as_float(s0[j]) * scale : -INFINITY;
+          const float t1 = 32 + j < N ? __uint_as_float(s1[j]) * scale : -INFINITY;
+          s0[j] = __float_as_uint(t0);
+          s1[j] = __float_as_uint(t1);
+          mx = fmaxf(mx, fmaxf(t0, t1));
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const float e0 = __expf(__uint_as_float(s0[j]) - mx), e1 = __expf(__uint_as_float(s1[j]) - mx);
+          s0[j] = __float_as_uint(e0);
+          s1[j] = __float_as_uint(e1);
+          sum += e0 + e1;
+        }
+        const float inv = live ? __fdividef(1.0f, sum) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          s0[j] = __float_as_uint(__uint_as_float(s0[j]) * inv);
+          s1[j] = __float_as_uint(__uint_as_float(s1[j]) * inv);
+        }
+        uint8_t* ps_hi = chunk(C_PS + 2 * (g & 1));
+        uint8_t* ps_lo = ps_hi + CH;
+        if (g >= 2) wait(BB_DQKACC + g - 2, ph);               // the buffer is shared with head g - 2
+#pragma unroll
+        for (int j8 = 0; j8 < 8; j8++) {
+          float t[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) t[i] = __uint_as_float(8 * j8 + i < 32 ? s0[(8 * j8 + i) & 31] : s1[(8 * j8 + i) & 31]);
+          store8_split(ps_hi, ps_lo, r, 8 * j8, CH, t);
+        }
+        arrive(BB_P + g);
+        // row sum of dP o P (dP is read from TMEM twice; P stays in registers)
+        wait(BB_DPACC + g, ph);
+        float tsum = 0.f;
+        {
+          uint32_t dp[32];
+          tmem_ld32(lane_addr + 64 * g, dp);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; j++) tsum += __uint_as_float(dp[j]) * __uint_as_float(s0[j]);
+          tmem_ld32(lane_addr + 64 * g + 32, dp);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; j++) tsum += __uint_as_float(dp[j]) * __uint_as_float(s1[j]);
+          tmem_ld32(lane_addr + 64 * g, dp);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; j++) s0[j] = __float_as_uint(__uint_as_float(s0[j]) * (__uint_as_float(dp[j]) - tsum) * scale);
+          tmem_ld32(lane_addr + 64 * g + 32, dp);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; j++) s1[j] = __float_as_uint(__uint_as_float(s1[j]) * (__uint_as_float(dp[j]) - tsum) * scale);
+        }
+        wait(BB_DVACC + g, ph);                                // dV_h has read P: the buffer takes dS
+#pragma unroll
+        for (int j8 = 0; j8 < 8; j8++) {
+          float t[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) t[i] = live ? __uint_as_float(8 * j8 + i < 32 ? s0[(8 * j8 + i) & 31] : s1[(8 * j8 + i) & 31]) : 0.f;
+          store8_split(ps_hi, ps_lo, r, 8 * j8, CH, t);
+        }
+        arrive(BB_DS + g);
+      }
+      // ---- dq, dk, dv of head g -> the planes q, k, v occupied (attention.py:81-83)
+      {
+        wait(BB_DQKACC + g, ph);
+        for (int part = 0; part < 3; part++) {
+          const uint32_t col = part == 0 ? 64 * g : (part == 1 ? 64 * g + 32 : 256 + DHP * g);
+          ld24(lane_addr + col, v);
+          if (!live) {
+#pragma unroll
+            for (int c = 0; c < 24; c++) v[c] = 0.f;
+          }
+          store24_split(chunk(C_QH + 2 * part), chunk(C_QL + 2 * part), r, DHP * g, v);
+        }
+        arrive(BB_DQKV);
+      }
+      // ---- u = LN(x) (recomputed) for dWqkv; xhat kept for the LayerNorm backward
+      float rstd0;
+      {
+        const float* xin = bi ? a.blk[bi - 1].out : a.x;
+        if (live) {
+          if (bi) load24_tiled(xin + (size_t)img * N * D, N, r, 6 * g, v);
+          else load24_global(xin + ((size_t)img * N + r) * D + 24 * g, v);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 24; c++) v[c] = 0.f;
+        }
+        float mean;
+        row_stats(v, stat, r, g, mean, rstd0);
+#pragma unroll
+        for (int c = 0; c < 24; c++) {
+          xh[c] = live ? (v[c] - mean) * rstd0 : 0.f;
+          w[c] = live ? xh[c] * __ldg(P.ln_g + 24 * g + c) + __ldg(P.ln_b + 24 * g + c) : 0.f;
+        }
+        wait(BB_DQKACC + 3, ph);                               // every product that read the P / dS buffers is done
+        store24_split(chunk(C_UH), chunk(C_UL), r, 24 * g, w);
+        if (g == 0) store_ones_unit(chunk(C_UH), chunk(C_UL), r, D, live);
+        arrive(BB_U);
+      }
+      // ---- dx = dh + LN-backward(dU); dgamma, dbeta                       attention.py:87-88
+      {
+        wait(BB_DUACC, ph);
+        ld24(lane_addr + 24 * g, v);
+        float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 24; c++) {
+          if (!live) v[c] = 0.f;
+          w[c] = v[c] * xh[c];
+          const float gd = v[c] * __ldg(P.ln_g + 24 * g + c);
+          p1 += gd;
+          p2 += gd * xh[c];
+        }
+        colsum24_atomic(w, lane, P.d_ln_g + 24 * g);
+        colsum24_atomic(v, lane, P.d_ln_b + 24 * g);
+        // dh back from its parking place BEFORE the row-sum barriers: after the last block the same buffer receives dx in
+        // row-major order, and no thread may write that while another still has to read its parked dh
+        if (live) load24_tiled(dh_scratch, N, r, 6 * g, d);
+        float s1, s2;
+        row_sum2(p1, p2, stat, r, g, s1, s2);
+        s1 *= (1.0f / D); s2 *= (1.0f / D);
+#pragma unroll
+        for (int c = 0; c < 24; c++) {
+          const float gd = v[c] * __ldg(P.ln_g + 24 * g + c);
+          d[c] = live ? d[c] + rstd0 * (gd - s1 - xh[c] * s2) : 0.f;
+        }
+      }
+    }
+    if (live) store24_global(a.dx + ((size_t)img * N + r) * D + 24 * g, d);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after();
+    tmem_dealloc<512>(tbase);
+  }
+}
+
 static bool supported(int N, int D_, int H_) { return N >= 1 && N <= ROWS && D_ == D && H_ == H; }
+static long long* g_dbg = nullptr;
 
 }  // namespace vtc
 }  // namespace nt
@@ -487,6 +1119,12 @@ extern "C" {
 
 int nt_vit_tc_supported(int N, int D, int H, int* ok) {
   *ok = vtc::supported(N, D, H) ? 1 : 0;
+  return 0;
+}
+
+/* development aid: phase time stamps of CTA 0 ([2 roles][16 blocks][16 events] clock64 values); NULL switches them off */
+int nt_vit_tc_debug(long long* stamps) {
+  vtc::g_dbg = stamps;
   return 0;
 }
 
@@ -514,12 +1152,29 @@ int nt_vit_tc_prepare(const NtVitBlock* blocks, int nblocks, int D, int H) {
   return 0;
 }
 
+int nt_vit_tc_bwd(const NtVitBlock* blocks, int nblocks, const float* x, const float* dout, float* dx, int B, int N, int D, int H) {
+  NT_ENTRY();
+  vtc::Args a{};
+  if (int rc = vtc_fill(a, blocks, nblocks, "nt_vit_tc_bwd", N, D, H)) return rc;
+  if (B == 0) return 0;
+  a.x = x; a.dout = dout; a.dx = dx;
+  static bool attr = false;
+  if (!attr) {
+    NT_CHECK(cudaFuncSetAttribute(vtc::vit_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtc::BSMEM_BYTES));
+    attr = true;
+  }
+  NT_CHECK(launch_k(vtc::vit_tc_bwd_kernel, dim3(B), dim3(vtc::BTHREADS), vtc::BSMEM_BYTES, a));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
 int nt_vit_tc_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H, int prepared) {
   NT_ENTRY();
   vtc::Args a{};
   if (int rc = vtc_fill(a, blocks, nblocks, "nt_vit_tc_fwd", N, D, H)) return rc;
   if (B == 0) return 0;
   a.x = x;
+  a.dbg = vtc::g_dbg;
   if (!prepared) {
     NT_CHECK(launch_k(vtc::vit_tc_wprep_kernel, dim3(ceil_div(vtc::ALL_STAGES * vtc::NT * 8, 256), nblocks), dim3(256), 0, a));
     NT_LAUNCH_OK();

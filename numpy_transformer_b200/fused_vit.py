@@ -7,6 +7,8 @@ launch granularity changes.  Shapes the kernels do not cover fall back to the pe
 import ctypes
 import os
 
+import numpy as np
+
 from ._lib import lib
 from .device import DeviceArray, get_gemm_mode
 
@@ -38,7 +40,7 @@ def supported(N, D, H):
 def tc_supported(N, D, H):
     """The tcgen05 / TMEM kernels (csrc/vit_block_tc.cu) cover this shape: the README configuration (D = 96, 4 heads,
     N <= 64).  NTB200_VIT_TC=0 forces the older mma.sync kernels (csrc/vit_block.cu), which cover more (D, H) pairs."""
-    if os.environ.get("NTB200_VIT_TC", "0") == "0" or not enabled() or get_gemm_mode() != 1:
+    if os.environ.get("NTB200_VIT_TC", "1") == "0" or not enabled() or get_gemm_mode() != 1:
         return False
     ok = ctypes.c_int(0)
     lib.nt_vit_tc_supported(int(N), int(D), int(H), ctypes.byref(ok))
@@ -69,6 +71,37 @@ def _wfrag(layer, D, tc=False):
 
 def _null_ptr(x):
     return None if x is None else x.ptr
+
+
+def untile(a, lead, N, W):
+    """Host view of a tensor the tcgen05 kernels keep TILED: per leading index [ceil(W/4)][N][4] (the 16-byte unit u of every
+    row contiguous over the rows, so a warp's 32 rows store 512 contiguous bytes) -> row-major lead + (N, W)."""
+    U = (W + 3) // 4
+    a = np.asarray(a).reshape(tuple(lead) + (U, N, 4))
+    nd = len(lead)
+    a = np.moveaxis(a, nd, nd + 1).reshape(tuple(lead) + (N, U * 4))
+    return a[..., :W]
+
+
+class Tiled:
+    """A device tensor in the tiled layout that answers NumPy like its row-major equivalent (np.asarray, shape, ptr).
+    Only host code that inspects the layers' saved activations (tests, atg__) ever converts it."""
+
+    def __init__(self, dev, lead, N, W, host_dtype):
+        self.dev, self.lead, self.N, self.W, self.host_dtype = dev, tuple(lead), N, W, host_dtype
+        self.shape = self.lead + (N, W)
+
+    @property
+    def ptr(self):
+        return self.dev.ptr
+
+    def __array__(self, dtype=None, copy=None):
+        a = untile(self.dev.numpy(), self.lead, self.N, self.W).astype(self.host_dtype, copy=False)
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+
+def _tiled(lead, N, W, hd):
+    return Tiled(DeviceArray(tuple(lead) + ((W + 3) // 4, N, 4), host_dtype=hd), lead, N, W, hd)
 
 
 def prepare(layers):
@@ -115,12 +148,21 @@ def forward_stack(layers, x, prepared=False, want_P=True):
         assert l.embed_dim == D and l.num_h == H, "fused stack needs identical blocks"
         l.batch, l.block = B, N
         l._mask_kind = 0
-        l.qkv = DeviceArray((B, N, 3 * D), host_dtype=hd)
-        l.P = DeviceArray((B, H, N, N), host_dtype=hd) if (want_P or not tc) else None
-        l.input1 = DeviceArray((B, N, D), host_dtype=hd)
-        l._dgelu = DeviceArray((B, N, 2 * D), host_dtype=hd)      # tcgen05 path: the fc0 PRE-activation
-        l._save = None if tc else DeviceArray((B, _save_bytes(D) // 4))
-        l._out = DeviceArray((B, N, D), host_dtype=hd)
+        last = l is layers[-1]
+        if tc:          # saved activations in the kernels' tiled layout (see Tiled); the stack's output stays row-major
+            l.qkv = _tiled((B,), N, 3 * D, hd)
+            l.P = _tiled((B, H), N, N, hd) if want_P else None
+            l.input1 = _tiled((B,), N, D, hd)
+            l._dgelu = _tiled((B,), N, 2 * D, hd)                     # the fc0 PRE-activation
+            l._save = None
+            l._out = DeviceArray((B, N, D), host_dtype=hd) if last else _tiled((B,), N, D, hd)
+        else:
+            l.qkv = DeviceArray((B, N, 3 * D), host_dtype=hd)
+            l.P = DeviceArray((B, H, N, N), host_dtype=hd)
+            l.input1 = DeviceArray((B, N, D), host_dtype=hd)
+            l._dgelu = DeviceArray((B, N, 2 * D), host_dtype=hd)
+            l._save = DeviceArray((B, _save_bytes(D) // 4))
+            l._out = DeviceArray((B, N, D), host_dtype=hd)
         l.out = l.out1 = l.out2 = None          # LN outputs / GELU output are recomputed in backward, not stored
         l._fused = "tc" if tc else "mma"
         _wfrag(l, D, tc)

@@ -55,3 +55,34 @@ def test_tc_forward_vs_oracle(nt, monkeypatch, B, N, L):
     # the softmax is optional: same outputs without materialising it
     out2 = fused_vit.forward_stack(layers, nt.as_device(x), want_P=False)
     assert layers[0].P is None and np.array_equal(np.asarray(out2), np.asarray(out))
+
+
+@pytest.mark.parametrize("B,N,L", [(3, 49, 2), (4, 64, 1), (2, 17, 3), (100, 49, 6)])
+def test_tc_backward_vs_oracle(nt, monkeypatch, B, N, L):
+    """dx and every parameter gradient of the stack (accumulated over two backward calls: the reference's `+=` until
+    setzero) against the oracle's hand-derived adjoint (attention.py:57-89)."""
+    from numpy_transformer_b200 import fused_vit
+    monkeypatch.setenv("NTB200_VIT_TC", "1")
+    layers, blks, x = _stack(nt, B, N, L, seed=7 * B + N)
+    rs = np.random.RandomState(5)
+    dout = rs.randn(B, N, 96) / np.sqrt(96)
+    for want_P in (True, False):
+        out = fused_vit.forward_stack(layers, nt.as_device(x), want_P=want_P)
+        dx = fused_vit.backward_stack(layers, nt.as_device(dout))
+    # oracle
+    ref, caches = x, []
+    for blk in blks:
+        ref, c = M.vit_block_fwd(ref, blk, 4)
+        caches.append(c)
+    d, grads = dout, []
+    for blk, c in zip(reversed(blks), reversed(caches)):
+        d, gr, _ = M.vit_block_bwd(d, blk, c, 4)
+        grads.insert(0, gr)
+    assert rel_err(dx, d) < TOL
+    for li, (l, gr) in enumerate(zip(layers, grads)):
+        mine = [[c.gamma_delta, c.beta_delta] if hasattr(c, "gamma") else [c.params_delta, c.bias_delta] for c in l._children()]
+        for i, (a_, b_) in enumerate(zip(M.tree_leaves(mine), M.tree_leaves(gr))):
+            e = rel_err(np.asarray(a_).reshape(-1), 2.0 * np.asarray(b_).reshape(-1))      # two accumulated passes
+            assert e < TOL, "block %d leaf %d rel err %.2e" % (li, i, e)
+        for c in l._children():
+            c.setzero()

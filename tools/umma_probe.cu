@@ -23,6 +23,7 @@ struct Case {
   uint32_t a_stride, b_stride;            // MN-major chunk strides
   uint32_t a_bytes, b_bytes;              // image sizes
   int split_commit;                       // commit after the first half of the steps, wait, then issue the rest
+  int M;                                  // 0 -> 128
 };
 
 __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* __restrict__ aimg, const uint8_t* __restrict__ bimg, Case c,
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* __restrict__ 
   tc_fence_after();
   const uint32_t tbase = tslot;
   if (tid == 0) {
-    const uint32_t idesc = idesc_bf16(128, c.N, c.a_mn, c.b_mn);
+    const uint32_t idesc = idesc_bf16(c.M ? c.M : 128, c.N, c.a_mn, c.b_mn);
     uint32_t parity = 0;
     for (int s = 0; s < c.steps; s++) {
       const uint32_t aa = smem_u32(sa) + c.a_start[s], bb = smem_u32(sb) + c.b_start[s];
@@ -183,6 +184,38 @@ int main() {
     for (int s = 0; s < 6; s++) { c.a_start[s] = (s / 4) * 8192 + (s % 4) * 32; c.b_start[s] = (s / 4) * 192 * 128 + (s % 4) * 32; }
     fails += run_case("6 N=192 @col 288, 2 commits", c, A, B, 64, 192, [](const Plane& A, const Plane& B, int i, int j) {
       float s = 0; for (int k = 0; k < 96; k++) s += A.at(i, k) * B.at(j, k); return s; });
+  }
+  {  // 7: where do the rows of an M = 64 instruction land in TMEM?  (accumulator pre-filled by an M=128 product of zeros)
+    Plane A(64, 64, 8192, 8192, 21), B(64, 64, 8192, 8192, 22);
+    Case c{}; c.N = 64; c.steps = 4; c.M = 64; c.a_bytes = 2 * 8192; c.b_bytes = 8192;
+    A.img.resize(c.a_bytes, 0);
+    for (int s = 0; s < 4; s++) c.a_start[s] = c.b_start[s] = s * 32;
+    uint8_t *da, *db; float* dout;
+    cudaMalloc(&da, c.a_bytes); cudaMalloc(&db, c.b_bytes); cudaMalloc(&dout, 128 * c.N * 4);
+    cudaMemcpy(da, A.img.data(), c.a_bytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, B.img.data(), c.b_bytes, cudaMemcpyHostToDevice);
+    const size_t smem = 2 * 8192 + 8192 + 2048;
+    probe_kernel<<<1, 128, smem>>>(da, db, c, dout);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) printf("case 7: CUDA error %s\n", cudaGetErrorString(e));
+    else {
+      std::vector<float> out(128 * 64);
+      cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost);
+      printf("case 7 M=64: TMEM lane <- A row (by matching the whole row of D): ");
+      for (int lane = 0; lane < 128; lane++) {
+        int found = -1;
+        for (int i = 0; i < 64 && found < 0; i++) {
+          bool ok = true;
+          for (int j = 0; j < 64 && ok; j++) {
+            float s = 0; for (int k = 0; k < 64; k++) s += A.at(i, k) * B.at(j, k);
+            ok = fabsf(s - out[lane * 64 + j]) <= 1e-3f * (1.0f + fabsf(s));
+          }
+          if (ok) found = i;
+        }
+        if (found >= 0) printf("%d<-%d ", lane, found);
+      }
+      printf("\n");
+    }
   }
   printf(fails ? "PROBE FAILED (%d)\n" : "PROBE OK\n", fails);
   return fails;

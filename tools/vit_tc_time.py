@@ -43,3 +43,22 @@ for tc in ("1", "0"):
         if bwd:
             f()
             print("VIT_TC=%s backward: %.1f us" % (tc, timeit(lambda: fused_vit.backward_stack(layers, dout))))
+
+# phase timeline of CTA 0 (tcgen05 forward)
+os.environ["NTB200_VIT_TC"] = "1"
+dbg = nt.DeviceArray.zeros((2 * 16 * 16 * 2,), dtype=np.int32)
+lib.nt_vit_tc_debug(dbg.ptr)
+fused_vit.forward_stack(layers, x, want_P=False)
+lib.nt_sync()
+st = dbg.numpy().view(np.int64).reshape(2, 16, 16)
+lib.nt_vit_tc_debug(None)
+t0 = st[0, 0, 0]
+names_e = ["start", "U ready", "qacc", "kacc", "vacc", "qkv rdy", "S ready", "P written", "O ready", "U1 ready", "f0acc0", "f0acc1",
+           "G ready", "f1acc", "out stored"]
+for bi in (0, 1, 5):
+    print("block %d epilogue thread 0 (cycles since kernel's first stamp; delta):" % bi)
+    prev = st[0, bi, 0]
+    for k, nme in enumerate(names_e):
+        print("   %-12s %8d  +%d" % (nme, st[0, bi, k] - t0, st[0, bi, k] - prev))
+        prev = st[0, bi, k]
+    print("  MMA thread:", [int(v - t0) for v in st[1, bi, :9]])
