@@ -536,7 +536,8 @@ constexpr uint32_t BOFF_D = 0;                              // 4 chunks
 constexpr uint32_t BOFF_X = 4 * CH;                         // 16 chunks
 constexpr uint32_t BOFF_RING = 20 * CH;
 constexpr uint32_t BOFF_STAT = BOFF_RING + BNSTAGE * STAGE; // [2][64][4] floats
-constexpr uint32_t BOFF_BAR = BOFF_STAT + 2 * 64 * 4 * 4;
+constexpr uint32_t BOFF_ACC = BOFF_STAT + 2 * 64 * 4 * 4;       // [2 buffers][5 quantities][96] floats: column sums (bias / LayerNorm gradients)
+constexpr uint32_t BOFF_BAR = BOFF_ACC + 2 * 5 * 96 * 4;
 constexpr int BNBAR = 2 * BNSTAGE + 48;
 constexpr uint32_t BSMEM_BYTES = BOFF_BAR + BNBAR * 8 + 16;
 static_assert(BSMEM_BYTES <= 232448, "shared memory budget (backward)");
@@ -544,11 +545,14 @@ static_assert(BSMEM_BYTES <= 232448, "shared memory budget (backward)");
 constexpr int C_DH = 0, C_DL = 2;                           // d / dO: hi chunks 0,1  lo chunks 2,3
 constexpr int C_GH = 4, C_GL = 7, C_PH = 10, C_PL = 13, C_U1H = 16, C_U1L = 18;     // MLP phase: G, dpre, LN1(h)
 constexpr int C_QH = 4, C_QL = 10;                          // attention phase: [q c0 c1 | k c0 c1 | v c0 c1] hi, then lo
-constexpr int C_PS = 16;                                    // PS[b]: hi chunk 16 + 2b, lo chunk 17 + 2b
+// P / dS of head h: hi chunk ps_chunk(h), lo the next one.  Heads 2, 3 borrow the weight ring, which is idle between the
+// dU1 and the dU products (the loader holds the dU tiles back until the attention phase is over).
+__host__ __device__ constexpr int ps_chunk(int h) { return h < 2 ? 16 + 2 * h : 20 + 2 * (h - 2); }
 constexpr int C_UH = 16, C_UL = 18;                         // LN(x) for dWqkv (after the attention phase)
 enum { BB_D = 0, BB_DGACC = 1 /*2*/, BB_GDP = 3, BB_DU1ACC = 4, BB_ATT = 5, BB_SACC = 6 /*4*/, BB_SCONS = 10 /*4*/, BB_DPACC = 14 /*4*/,
        BB_P = 18 /*4*/, BB_DVACC = 22 /*4*/, BB_DS = 26 /*4*/, BB_DQKACC = 30 /*4*/, BB_DQKV = 34, BB_U = 35, BB_DUACC = 36,
-       BB_DW1_DONE = 37, BB_DW0_DONE = 38, BB_DWQKV_DONE = 39, BB_FFULL = 40 /*2*/, BB_FFREE = 42 /*2*/, BB_COUNT = 44 };
+       BB_DW1_DONE = 37, BB_DW0_DONE = 38, BB_DWQKV_DONE = 39, BB_FFULL = 40 /*2*/, BB_FFREE = 42 /*2*/, BB_ACCRDY = 44,
+       BB_ACCFREE = 45 /*2*/, BB_COUNT = 47 };
 constexpr int PIECES = 24;                                  // weight-gradient pieces per block: dW1 6, dW0 6, dWqkv 12
 
 // column sums over the 32 rows of a warp of 24 per-thread values: reduce-scatter (the lanes trade halves of their columns),
@@ -577,7 +581,8 @@ __device__ __forceinline__ void colsum24(const float (&v)[24], int lane, float (
   }
   c0 = (u16 ? 12 : 0) + (u8 ? 6 : 0) + (u4 ? 3 : 0);
 }
-// dst[24*g + c] += sum over the warp's rows of v[c]
+// dst[c] += sum over the warp's rows of v[c]; dst is a SHARED-memory accumulator (the global reds are issued later by a
+// warp that is not on the critical path: 100 CTAs adding to the same 96 addresses made the token warps wait)
 __device__ __forceinline__ void colsum24_atomic(const float (&v)[24], int lane, float* dst) {
   float o[3];
   int c0;
@@ -628,13 +633,15 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
   if (tid == 0) {
     for (int s = 0; s < BNSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < BB_COUNT; i++) mbar_init(&bar[i], 1);
-    const int eights[] = {BB_D, BB_GDP, BB_ATT, BB_DQKV, BB_U};
-    for (int i = 0; i < 5; i++) mbar_init(&bar[eights[i]], 8);
+    const int eights[] = {BB_D, BB_GDP, BB_ATT, BB_DQKV, BB_U, BB_ACCRDY};
+    for (int i = 0; i < 6; i++) mbar_init(&bar[eights[i]], 8);
     for (int i = 0; i < 4; i++) { mbar_init(&bar[BB_SCONS + i], 2); mbar_init(&bar[BB_P + i], 2); mbar_init(&bar[BB_DS + i], 2); }
     mbar_init(&bar[BB_FFREE], 4); mbar_init(&bar[BB_FFREE + 1], 4);
     mbar_fence_init();
   }
   for (uint32_t i = tid * 16; i < 20 * CH; i += BTHREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  float* accs = reinterpret_cast<float*>(smem + BOFF_ACC);
+  for (int i = tid; i < 2 * 5 * 96; i += BTHREADS) accs[i] = 0.f;
   if (warp == 3) tmem_alloc<512>(tslot);
   fence_async_smem();
   tc_fence_before();
@@ -654,6 +661,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
         for (int i = 0; i < BWD_STAGES; i++, it++) {
           const int s = it % BNSTAGE;
           if (it >= BNSTAGE) mbar_wait(&empty[s], ((it / BNSTAGE) - 1) & 1);
+          if (i == 7) mbar_wait(&bar[BB_DQKV], (L - 1 - bi) & 1);     // heads 2, 3 keep P / dS in the ring until here
           mbar_expect_tx(&full[s], STAGE);
           bulk_g2s(smem + BOFF_RING + s * STAGE, wimg + (size_t)i * STAGE, STAGE, &full[s]);
         }
@@ -710,7 +718,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           }
           mma_commit(&bar[BB_SACC + h]);
         }
-        auto dP_dV = [&](int h) {
+        auto dP = [&](int h) {
           const uint32_t off = hoff(h);
           wait(BB_SCONS + h, ph);                             // the softmax threads hold S_h in registers: its columns are free
 #pragma unroll
@@ -721,8 +729,11 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
             mma_bf16(tbase + 64 * h, desc_kmajor(Oh + o), desc_kmajor(Vh + o), id_s, 1u);
           }
           mma_commit(&bar[BB_DPACC + h]);
+        };
+        auto dV = [&](int h) {
+          const uint32_t off = hoff(h);
           wait(BB_P + h, ph);
-          const uint32_t Ph = caddr(C_PS + 2 * (h & 1)), Pl = Ph + CH;
+          const uint32_t Ph = caddr(ps_chunk(h)), Pl = Ph + CH;
 #pragma unroll
           for (int ks = 0; ks < 4; ks++) {                    // dV_h = P_h^T dO_h  (attention.py:76): both operands MN-major
             const uint32_t pa = ks * MNMAJ_STEP, ob = off + ks * MNMAJ_STEP;
@@ -735,7 +746,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
         auto dQ_dK = [&](int h) {
           const uint32_t off = hoff(h);
           wait(BB_DS + h, ph);
-          const uint32_t Sh = caddr(C_PS + 2 * (h & 1)), Sl = Sh + CH;
+          const uint32_t Sh = caddr(ps_chunk(h)), Sl = Sh + CH;
 #pragma unroll
           for (int ks = 0; ks < 4; ks++) {                    // dQ_h = dS_h K_h  (attention.py:78), dS already carries 1/sqrt(dh)
             const uint32_t kb = off + ks * MNMAJ_STEP;
@@ -752,7 +763,9 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           }
           mma_commit(&bar[BB_DQKACC + h]);
         };
-        dP_dV(0); dP_dV(1); dQ_dK(0); dQ_dK(1); dP_dV(2); dP_dV(3); dQ_dK(2); dQ_dK(3);
+        for (int h = 0; h < H; h++) dP(h);
+        for (int h = 0; h < H; h++) dV(h);
+        for (int h = 0; h < H; h++) dQ_dK(h);
         // ---- dU = dqkv Wqkv^T                                          attention.py:85
         wait(BB_DQKV, ph);
         for (int kc = 0; kc < 6; kc++) {
@@ -802,6 +815,22 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
       }
     }
     __syncwarp();
+  } else if (warp == 15) {
+    // ===================== column sums (bias / LayerNorm gradients): shared accumulators -> red.global.add =====================
+    for (int n = 0; n < L; n++) {
+      const NtVitBlock& P = a.blk[L - 1 - n];
+      mbar_wait(&bar[BB_ACCRDY], n & 1);
+      float* acc = accs + (n & 1) * 480;
+      float* dsts[5] = {P.d_b1, P.d_ln1_g, P.d_ln1_b, P.d_ln_g, P.d_ln_b};
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+        for (int c = lane; c < D; c += 32) {
+          atomicAdd(dsts[k] + c, acc[96 * k + c]);
+          acc[96 * k + c] = 0.f;
+        }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[BB_ACCFREE + (n & 1)]);
+    }
   } else if (warp == 6 || warp == 7 || warp == 10 || warp == 11) {
     // ===================== weight-gradient flush: TMEM lanes 64..127 -> red.global.add =====================
     const int fq = warp & 3, fc = (warp >> 2) - 1, fl = 32 * (fq - 2) + lane;       // feature within the 64-feature half
@@ -866,11 +895,16 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
       const NtVitBlock& P = a.blk[bi];
       const uint32_t ph = n & 1;
       float v[24], w[24];
+      const bool t0 = tid == 0;
+      if (t0) stamp(a, 0, n, 0);
+      float* acc = accs + (n & 1) * 480 + 24 * g;             // [quantity][96]: db1, dgamma1, dbeta1, dgamma, dbeta of this block
+      if (n >= 2) wait(BB_ACCFREE + (n & 1), ((n >> 1) - 1) & 1);
       // ---- d -> operand planes; db1 += colsum(d)                         fullconnect.py:122
-      colsum24_atomic(d, lane, P.d_b1 + 24 * g);
+      colsum24_atomic(d, lane, acc);
       if (n > 0) wait(BB_DW1_DONE, (n - 1) & 1);               // the previous block's dW1 products read the d planes
       store24_split(chunk(C_DH), chunk(C_DL), r, 24 * g, d);
       arrive(BB_D);
+      if (t0) stamp(a, 0, n, 1);
       // ---- u1 = LN1(h) (recomputed), xhat1 kept for the LayerNorm backward
       float xh[24], rstd1;
       {
@@ -891,8 +925,10 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
         if (g == 0) store_ones_unit(chunk(C_U1H), chunk(C_U1L), r, D, live);
       }
       // ---- dG -> G = GELU(pre), dpre = dG * GELU'(pre)                   attention.py:58-59
+      if (t0) stamp(a, 0, n, 2);
       for (int nt = 0; nt < 2; nt++) {
         wait(BB_DGACC + nt, ph);
+        if (t0) stamp(a, 0, n, 3 + nt);
         ld24(lane_addr + NT * nt + 24 * g, v);
         if (live) load24_tiled(P.dgelu + (size_t)img * N * HD, N, r, 24 * nt + 6 * g, w);
         else {
@@ -910,10 +946,13 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
         store24_split(chunk(C_PH), chunk(C_PL), r, NT * nt + 24 * g, v);
       }
       arrive(BB_GDP);
+      if (t0) stamp(a, 0, n, 5);
       // ---- dh = d + LN1-backward(dU1); dgamma1, dbeta1                    attention.py:61-62, layernorm.py:116-135
       {
         wait(BB_DU1ACC, ph);
+        if (t0) stamp(a, 0, n, 6);
         ld24(lane_addr + 192 + 24 * g, v);
+        if (t0) stamp(a, 1, n, 0);
         float p1 = 0.f, p2 = 0.f;
 #pragma unroll
         for (int c = 0; c < 24; c++) {
@@ -923,21 +962,28 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           p1 += gd;
           p2 += gd * xh[c];
         }
-        colsum24_atomic(w, lane, P.d_ln1_g + 24 * g);
-        colsum24_atomic(v, lane, P.d_ln1_b + 24 * g);
+        if (t0) stamp(a, 1, n, 1);
+        colsum24_atomic(w, lane, acc + 96);
+        colsum24_atomic(v, lane, acc + 192);
+        if (t0) stamp(a, 1, n, 2);
         float s1, s2;
         row_sum2(p1, p2, stat, r, g, s1, s2);
+        if (t0) stamp(a, 1, n, 3);
         s1 *= (1.0f / D); s2 *= (1.0f / D);
 #pragma unroll
         for (int c = 0; c < 24; c++) {
           const float gd = v[c] * __ldg(P.ln1_g + 24 * g + c);
           d[c] = live ? d[c] + rstd1 * (gd - s1 - xh[c] * s2) : 0.f;
         }
+        if (t0) stamp(a, 1, n, 4);
         if (live) store24_tiled(dh_scratch, N, r, 6 * g, d);
+        if (t0) stamp(a, 1, n, 5);
       }
       // ---- dO (= dh) and q, k, v -> head-padded planes
       {
+        if (t0) stamp(a, 0, n, 7);
         wait(BB_DW0_DONE, ph);                                 // dW1 / dW0 products have read d, G, dpre, LN1(h)
+        if (t0) stamp(a, 0, n, 8);
         store24_split(chunk(C_DH), chunk(C_DL), r, DHP * g, d);
         {
           const uint32_t zoff = plane_off(r, DHP * g + DH, CH);
@@ -956,11 +1002,13 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           *reinterpret_cast<uint4*>(chunk(C_QL + 2 * part) + zoff) = make_uint4(0, 0, 0, 0);
         }
         arrive(BB_ATT);
+        if (t0) stamp(a, 0, n, 9);
       }
       // ---- head g: P (recomputed), dS = P o (dP - rowsum(dP o P)) / sqrt(dh)        attention.py:74-75
       {
         uint32_t s0[32], s1[32];
         wait(BB_SACC + g, ph);
+        if (t0) stamp(a, 0, n, 10);
         tmem_ld32(lane_addr + 64 * g, s0);
         tmem_ld32(lane_addr + 64 * g + 32, s1);
         tmem_wait_ld();
@@ -990,9 +1038,8 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           s0[j] = __float_as_uint(__uint_as_float(s0[j]) * inv);
           s1[j] = __float_as_uint(__uint_as_float(s1[j]) * inv);
         }
-        uint8_t* ps_hi = chunk(C_PS + 2 * (g & 1));
+        uint8_t* ps_hi = chunk(ps_chunk(g));
         uint8_t* ps_lo = ps_hi + CH;
-        if (g >= 2) wait(BB_DQKACC + g - 2, ph);               // the buffer is shared with head g - 2
 #pragma unroll
         for (int j8 = 0; j8 < 8; j8++) {
           float t[8];
@@ -1001,6 +1048,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           store8_split(ps_hi, ps_lo, r, 8 * j8, CH, t);
         }
         arrive(BB_P + g);
+        if (t0) stamp(a, 0, n, 11);
         // row sum of dP o P (dP is read from TMEM twice; P stays in registers)
         wait(BB_DPACC + g, ph);
         float tsum = 0.f;
@@ -1032,10 +1080,12 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           store8_split(ps_hi, ps_lo, r, 8 * j8, CH, t);
         }
         arrive(BB_DS + g);
+        if (t0) stamp(a, 0, n, 12);
       }
       // ---- dq, dk, dv of head g -> the planes q, k, v occupied (attention.py:81-83)
       {
         wait(BB_DQKACC + g, ph);
+        if (t0) stamp(a, 0, n, 13);
         for (int part = 0; part < 3; part++) {
           const uint32_t col = part == 0 ? 64 * g : (part == 1 ? 64 * g + 32 : 256 + DHP * g);
           ld24(lane_addr + col, v);
@@ -1065,14 +1115,16 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           xh[c] = live ? (v[c] - mean) * rstd0 : 0.f;
           w[c] = live ? xh[c] * __ldg(P.ln_g + 24 * g + c) + __ldg(P.ln_b + 24 * g + c) : 0.f;
         }
-        wait(BB_DQKACC + 3, ph);                               // every product that read the P / dS buffers is done
+        wait(BB_DQKACC + 1, ph);                               // heads 0, 1 kept P / dS here; their products are done
         store24_split(chunk(C_UH), chunk(C_UL), r, 24 * g, w);
         if (g == 0) store_ones_unit(chunk(C_UH), chunk(C_UL), r, D, live);
         arrive(BB_U);
+        if (t0) stamp(a, 0, n, 14);
       }
       // ---- dx = dh + LN-backward(dU); dgamma, dbeta                       attention.py:87-88
       {
         wait(BB_DUACC, ph);
+        if (t0) stamp(a, 0, n, 15);
         ld24(lane_addr + 24 * g, v);
         float p1 = 0.f, p2 = 0.f;
 #pragma unroll
@@ -1083,8 +1135,10 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           p1 += gd;
           p2 += gd * xh[c];
         }
-        colsum24_atomic(w, lane, P.d_ln_g + 24 * g);
-        colsum24_atomic(v, lane, P.d_ln_b + 24 * g);
+        colsum24_atomic(w, lane, acc + 288);
+        colsum24_atomic(v, lane, acc + 384);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[BB_ACCRDY]);           // (mbarrier arrive has release semantics for the shared atomics)
         // dh back from its parking place BEFORE the row-sum barriers: after the last block the same buffer receives dx in
         // row-major order, and no thread may write that while another still has to read its parked dh
         if (live) load24_tiled(dh_scratch, N, r, 6 * g, d);
@@ -1158,6 +1212,7 @@ int nt_vit_tc_bwd(const NtVitBlock* blocks, int nblocks, const float* x, const f
   if (int rc = vtc_fill(a, blocks, nblocks, "nt_vit_tc_bwd", N, D, H)) return rc;
   if (B == 0) return 0;
   a.x = x; a.dout = dout; a.dx = dx;
+  a.dbg = vtc::g_dbg;
   static bool attr = false;
   if (!attr) {
     NT_CHECK(cudaFuncSetAttribute(vtc::vit_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtc::BSMEM_BYTES));

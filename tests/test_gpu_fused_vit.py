@@ -120,7 +120,7 @@ def test_fused_and_unfused_paths_agree(nt):
             np.random.seed(1)
             at = attention_layer(96, 4)
             y = np.asarray(at.forward(x))
-            assert at._fused == (fused == "1")
+            assert bool(at._fused) == (fused == "1")
             dx = np.asarray(at.backward(gin))
             outs.append([y, dx] + [np.asarray(a) for a in _grads(at)])
         finally:

@@ -62,3 +62,23 @@ for bi in (0, 1, 5):
         print("   %-12s %8d  +%d" % (nme, st[0, bi, k] - t0, st[0, bi, k] - prev))
         prev = st[0, bi, k]
     print("  MMA thread:", [int(v - t0) for v in st[1, bi, :9]])
+
+if bwd:
+    lib.nt_vit_tc_debug(dbg.ptr)
+    fused_vit.forward_stack(layers, x, want_P=False)
+    dbg.fill_zero()
+    fused_vit.backward_stack(layers, dout)
+    lib.nt_sync()
+    st = dbg.numpy().view(np.int64).reshape(2, 16, 16)
+    lib.nt_vit_tc_debug(None)
+    t0 = st[0, 0, 0]
+    names_b = ["start", "D stored", "U1 stored", "dGacc0", "dGacc1", "G,dpre rdy", "dU1acc", "LN1bwd done", "dW0 done", "att planes",
+               "S ready", "P written", "dS written", "dQK ready", "U stored", "dU ready"]
+    for n in (0, 1, 5):
+        print("backward iteration %d, token thread 0 (cycles; delta):" % n)
+        prev = st[0, n, 0]
+        for k, nme in enumerate(names_b):
+            print("   %-12s %8d  +%d" % (nme, st[0, n, k] - t0, st[0, n, k] - prev))
+            prev = st[0, n, k]
+    print("LN1-backward sub-phases (iteration 1): after ld24, products, colsums, row sums, final, scratch store:",
+          [int(st[1, 1, k] - st[0, 1, 6]) for k in range(6)])
