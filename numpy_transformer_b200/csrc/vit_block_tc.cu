@@ -44,7 +44,7 @@ constexpr int NT = 96;                         // rows (output features) of a we
 constexpr uint32_t WPLANE = NT * 128;          // 12 KB
 constexpr uint32_t STAGE = 2 * WPLANE;         // hi + lo
 constexpr int FWD_STAGES = 13, BWD_STAGES = 13, ALL_STAGES = FWD_STAGES + BWD_STAGES;
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 3;
 constexpr int THREADS = 448;                   // 14 warps: epilogue {0,1,4,5,8,9,12,13}, loader 2, MMA 3
 constexpr int EPI_THREADS = 256;
 
@@ -53,8 +53,12 @@ constexpr uint32_t OFF_A = 0;                        // 4 chunks: U / U1 (hi 2, 
 constexpr uint32_t OFF_B = OFF_A + 4 * CH;           // 12 chunks: Q hi 2, Q lo 2, K hi 2, K lo 2, V hi 2, V lo 2  |  G hi 3, G lo 3
 constexpr uint32_t OFF_RING = OFF_B + 12 * CH;
 constexpr uint32_t OFF_STAT = OFF_RING + NSTAGE * STAGE;      // [2][64][4] floats
-constexpr uint32_t OFF_BAR = OFF_STAT + 2 * 64 * 4 * 4;
-constexpr int NBAR = 2 * NSTAGE + 24;
+// the block's small parameter vectors, copied once per block by the loader (double-buffered):
+// ln_g 0 | ln_b 96 | bqkv 192 | ln1_g 480 | ln1_b 576 | b0 672 | b1 864   (960 floats)
+constexpr int PAR_FLOATS = 960, PV_LNG = 0, PV_LNB = 96, PV_BQKV = 192, PV_LN1G = 480, PV_LN1B = 576, PV_B0 = 672, PV_B1 = 864;
+constexpr uint32_t OFF_PAR = OFF_STAT + 2 * 64 * 4 * 4;
+constexpr uint32_t OFF_BAR = OFF_PAR + 2 * PAR_FLOATS * 4;
+constexpr int NBAR = 2 * NSTAGE + 26;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;          // no static shared memory: the dynamic window starts 1024-aligned
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -212,7 +216,7 @@ __device__ __forceinline__ void load24_global(const float* p, float (&v)[24]) {
 
 // barrier indices (forward)
 enum { FB_U = 0, FB_QKVACC = 1 /*3*/, FB_QKVRDY = 4, FB_S = 5 /*4*/, FB_P = 9 /*4*/, FB_O = 13 /*4*/, FB_U1 = 17, FB_F0 = 18 /*2*/,
-       FB_G = 20, FB_F1 = 21, FB_COUNT = 22 };
+       FB_G = 20, FB_F1 = 21, FB_PAR = 22 /*2*/, FB_COUNT = 24 };
 
 // ---------------------------------------------------------------- forward
 __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
@@ -226,7 +230,8 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* empty = full + NSTAGE;
   uint64_t* bar = empty + NSTAGE;
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 24);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 26);
+  float* par = reinterpret_cast<float*>(smem + OFF_PAR);
 
   pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -244,6 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
     mbar_init(&bar[FB_F0], 1); mbar_init(&bar[FB_F0 + 1], 1);
     mbar_init(&bar[FB_G], 8);
     mbar_init(&bar[FB_F1], 1);
+    mbar_init(&bar[FB_PAR], 1); mbar_init(&bar[FB_PAR + 1], 1);
     mbar_fence_init();
   }
   // zero the operand regions once: head-padding columns and padded token rows must be exact zeros / finite forever
@@ -265,6 +271,18 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
         for (int i = 0; i < FWD_STAGES; i++, it++) {
           const int s = it % NSTAGE;
           if (it >= NSTAGE) mbar_wait(&empty[s], ((it / NSTAGE) - 1) & 1);
+          if (i == 0) {
+            // this block's bias / LayerNorm vectors -> shared memory.  The buffer was last used two blocks ago: the ring slot
+            // just obtained proves the MMAs are within NSTAGE tiles of here, i.e. the token warps are past that block
+            const NtVitBlock& P = a.blk[bi];
+            float* pb = par + (bi & 1) * PAR_FLOATS;
+            uint64_t* pbar = &bar[FB_PAR + (bi & 1)];
+            mbar_expect_tx(pbar, PAR_FLOATS * 4);
+            bulk_g2s(pb + PV_LNG, P.ln_g, D * 4, pbar);    bulk_g2s(pb + PV_LNB, P.ln_b, D * 4, pbar);
+            bulk_g2s(pb + PV_BQKV, P.bqkv, 3 * D * 4, pbar);
+            bulk_g2s(pb + PV_LN1G, P.ln1_g, D * 4, pbar);  bulk_g2s(pb + PV_LN1B, P.ln1_b, D * 4, pbar);
+            bulk_g2s(pb + PV_B0, P.b0, HD * 4, pbar);      bulk_g2s(pb + PV_B1, P.b1, D * 4, pbar);
+          }
           mbar_expect_tx(&full[s], STAGE);
           bulk_g2s(sRing + s * STAGE, wimg + (size_t)i * STAGE, STAGE, &full[s]);
         }
@@ -363,6 +381,8 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
     __syncwarp();
   } else if (is_epi) {
     // ===================== epilogue warps: one token row per thread, 24 columns (= one head) per column group ========
+    // The phases are ROLLED loops over 8-column units: a fully unrolled version is ~180 KB of straight-line code and runs
+    // at the speed of the instruction cache misses (ncu: ICC hit rate 81 %, profiles/r02_ncu_full_vit_tc_bwd_v1_summary.csv).
     const bool live = r < N;
     const float scale = rsqrtf((float)DH);
     float x[24];                                            // the residual stream of this (row, column group)
@@ -378,46 +398,81 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[b]);
     };
+    // y[c] = (x[c] - mean) * rstd * gamma[c] + beta[c] -> split planes at columns 24 g + c (unrolled: x lives in registers)
+    auto layernorm_to_planes = [&](const float* gam, const float* bet) {
+      float mean, rstd;
+      row_stats(x, stat, r, g, mean, rstd);
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float w[8];
+        const float4 g0 = *reinterpret_cast<const float4*>(gam + 24 * g + 8 * j), g1 = *reinterpret_cast<const float4*>(gam + 24 * g + 8 * j + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(bet + 24 * g + 8 * j), b1 = *reinterpret_cast<const float4*>(bet + 24 * g + 8 * j + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = live ? (x[8 * j + i] - mean) * rstd * gg[i] + bb[i] : 0.f;
+        store8_split(sA, sA + 2 * CH, r, 24 * g + 8 * j, CH, w);
+      }
+    };
+    // eight accumulator columns starting at TMEM column `col` (+ vector `add8` from shared memory)
+    auto ld8_add = [&](uint32_t col, const float* add8, float (&w)[8]) {
+      uint32_t t[8];
+      tmem_ld8(lane_addr + col, t);
+      const float4 b0 = *reinterpret_cast<const float4*>(add8), b1 = *reinterpret_cast<const float4*>(add8 + 4);
+      tmem_wait_ld();
+      w[0] = __uint_as_float(t[0]) + b0.x; w[1] = __uint_as_float(t[1]) + b0.y; w[2] = __uint_as_float(t[2]) + b0.z; w[3] = __uint_as_float(t[3]) + b0.w;
+      w[4] = __uint_as_float(t[4]) + b1.x; w[5] = __uint_as_float(t[5]) + b1.y; w[6] = __uint_as_float(t[6]) + b1.z; w[7] = __uint_as_float(t[7]) + b1.w;
+      if (!live) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = 0.f;
+      }
+    };
+    auto store8_tiled = [&](float* img_base, int u, const float (&w)[8]) {     // units u, u + 1 of row r
+      *reinterpret_cast<float4*>(img_base + ((size_t)u * N + r) * 4) = make_float4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<float4*>(img_base + ((size_t)(u + 1) * N + r) * 4) = make_float4(w[4], w[5], w[6], w[7]);
+    };
     for (int bi = 0; bi < a.nblocks; bi++) {
       const NtVitBlock& P = a.blk[bi];
       const uint32_t ph = bi & 1;
-      float v[24];
+      const float* pv = par + (bi & 1) * PAR_FLOATS;
       const bool t0 = tid == 0;
       if (t0) stamp(a, 0, bi, 0);
+      mbar_wait(&bar[FB_PAR + (bi & 1)], (bi >> 1) & 1);
       // ---- u = LN(x) -> A planes                                       attention.py:22
+      layernorm_to_planes(pv + PV_LNG, pv + PV_LNB);
+      arrive(FB_U);
+      if (t0) stamp(a, 0, bi, 1);
+      // ---- q | k | v = acc + bias -> head-padded planes (+ fp32 copy, tiled, for the backward / the layer API)
       {
-        float mean, rstd;
-        row_stats(x, stat, r, g, mean, rstd);
-#pragma unroll
-        for (int c = 0; c < 24; c++)
-          v[c] = live ? (x[c] - mean) * rstd * __ldg(P.ln_g + 24 * g + c) + __ldg(P.ln_b + 24 * g + c) : 0.f;
-        store24_split(sA, sA + 2 * CH, r, 24 * g, v);
-        arrive(FB_U);
-        if (t0) stamp(a, 0, bi, 1);
-      }
-      // ---- q | k | v = acc + bias -> head-padded planes (+ fp32 copy for the backward / the layer API)
-      for (int nt = 0; nt < 3; nt++) {
-        mbar_wait(&bar[FB_QKVACC + nt], ph);
-        tc_fence_after();
-        if (t0) stamp(a, 0, bi, 2 + nt);
-        ld24(lane_addr + NT * nt + 24 * g, v);
-#pragma unroll
-        for (int c = 0; c < 24; c++) v[c] = live ? v[c] + __ldg(P.bqkv + NT * nt + 24 * g + c) : 0.f;
-        if (live) store24_tiled(P.qkv + (size_t)img * N * 3 * D, N, r, 24 * nt + 6 * g, v);
-        store24_split(sB + nt * 4 * CH, sB + nt * 4 * CH + 2 * CH, r, DHP * g, v);
-        // the 8 padding columns of the head: P (heads 2, 3) and G were parked over these planes, so re-zero them every block
-        const uint32_t zoff = plane_off(r, DHP * g + DH, CH);
-        *reinterpret_cast<uint4*>(sB + nt * 4 * CH + zoff) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(sB + nt * 4 * CH + 2 * CH + zoff) = make_uint4(0, 0, 0, 0);
+        float* qkv_img = P.qkv + (size_t)img * N * 3 * D;
+#pragma unroll 1
+        for (int it = 0; it < 9; it++) {
+          const int nt = it / 3, j = it - 3 * nt;
+          if (j == 0) {
+            mbar_wait(&bar[FB_QKVACC + nt], ph);
+            tc_fence_after();
+            if (t0) stamp(a, 0, bi, 2 + nt);
+          }
+          float w[8];
+          ld8_add(NT * nt + 24 * g + 8 * j, pv + PV_BQKV + NT * nt + 24 * g + 8 * j, w);
+          if (live) store8_tiled(qkv_img, 24 * nt + 6 * g + 2 * j, w);
+          uint8_t* hi = sB + nt * 4 * CH;
+          store8_split(hi, hi + 2 * CH, r, DHP * g + 8 * j, CH, w);
+          if (j == 2) {     // the 8 padding columns of the head: P (heads 2, 3) and G were parked over these planes
+            const uint32_t zoff = plane_off(r, DHP * g + DH, CH);
+            *reinterpret_cast<uint4*>(hi + zoff) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(hi + 2 * CH + zoff) = make_uint4(0, 0, 0, 0);
+          }
+        }
       }
       arrive(FB_QKVRDY);
       if (t0) stamp(a, 0, bi, 5);
-      // ---- P = softmax(S / sqrt(dh)) for head g                         attention.py:37-41
+      // ---- P = softmax(S / sqrt(dh)) for head g: three passes over the 64 key columns, 16 at a time  attention.py:37-41
       {
         mbar_wait(&bar[FB_S + g], ph);
         if (g >= 2) mbar_wait(&bar[FB_S + 3], ph);          // heads 2, 3 park P in the q planes: every S product must be done
         tc_fence_after();
         if (t0) stamp(a, 0, bi, 6);
+        // the whole row of scores in registers: one TMEM round trip (reading it in pieces costs a load latency per piece)
         uint32_t s0[32], s1[32];
         tmem_ld32(lane_addr + 64 * g, s0);
         tmem_ld32(lane_addr + 64 * g + 32, s1);
@@ -425,31 +480,29 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 32; j++) {
-          const float t0 = j < N ? __uint_as_float(s0[j]) * scale : -INFINITY;
-          const float t1 = 32 + j < N ? __uint_as_float(s1[j]) * scale : -INFINITY;
-          s0[j] = __float_as_uint(t0);
-          s1[j] = __float_as_uint(t1);
-          mx = fmaxf(mx, fmaxf(t0, t1));
+          const float t0_ = j < N ? __uint_as_float(s0[j]) * scale : -INFINITY;
+          const float t1_ = 32 + j < N ? __uint_as_float(s1[j]) * scale : -INFINITY;
+          s0[j] = __float_as_uint(t0_);
+          s1[j] = __float_as_uint(t1_);
+          mx = fmaxf(mx, fmaxf(t0_, t1_));
         }
-        float sum = 0.f;
+        float sum = 0.f, sum1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; j++) {
           const float e0 = __expf(__uint_as_float(s0[j]) - mx), e1 = __expf(__uint_as_float(s1[j]) - mx);
           s0[j] = __float_as_uint(e0);
           s1[j] = __float_as_uint(e1);
-          sum += e0 + e1;
+          sum += e0;
+          sum1 += e1;
         }
-        const float inv = live ? __fdividef(1.0f, sum) : 0.f;
+        const float inv = live ? __fdividef(1.0f, sum + sum1) : 0.f;
         uint8_t* ph_ = (g < 2 ? sA : sB) + (g & 1) * 2 * CH;
         float* pg = P.P ? P.P + ((size_t)img * H + g) * (size_t)((N + 3) / 4) * N * 4 : nullptr;   // tiled [ceil(N/4)][N][4]
 #pragma unroll
         for (int j8 = 0; j8 < 8; j8++) {
           float w[8];
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int j = 8 * j8 + i;
-            w[i] = live ? __uint_as_float(j < 32 ? s0[j & 31] : s1[j & 31]) * inv : 0.f;
-          }
+          for (int i = 0; i < 8; i++) w[i] = __uint_as_float(8 * j8 + i < 32 ? s0[(8 * j8 + i) & 31] : s1[(8 * j8 + i) & 31]) * inv;
           store8_split(ph_, ph_ + CH, r, 8 * j8, CH, w);
           if (pg && live) {                                             // the reference's atg__ (attention.py:41)
             if (8 * j8 < N) *reinterpret_cast<float4*>(pg + ((size_t)(2 * j8) * N + r) * 4) = make_float4(w[0], w[1], w[2], w[3]);
@@ -464,35 +517,37 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
         mbar_wait(&bar[FB_O + g], ph);
         tc_fence_after();
         if (t0) stamp(a, 0, bi, 8);
+        float v[24];
         ld24(lane_addr + 288 + DHP * g, v);
 #pragma unroll
         for (int c = 0; c < 24; c++) x[c] = live ? x[c] + v[c] : 0.f;
         if (live) store24_tiled(P.h + (size_t)img * N * D, N, r, 6 * g, x);
-        float mean, rstd;
-        row_stats(x, stat, r, g, mean, rstd);
-#pragma unroll
-        for (int c = 0; c < 24; c++)
-          v[c] = live ? (x[c] - mean) * rstd * __ldg(P.ln1_g + 24 * g + c) + __ldg(P.ln1_b + 24 * g + c) : 0.f;
-        store24_split(sA, sA + 2 * CH, r, 24 * g, v);
+        layernorm_to_planes(pv + PV_LN1G, pv + PV_LN1B);
         arrive(FB_U1);
         if (t0) stamp(a, 0, bi, 9);
       }
       // ---- pre = acc + b0 ; G = GELU(pre) -> planes (aliasing q | k)    attention.py:49-50
-      for (int nt = 0; nt < 2; nt++) {
-        mbar_wait(&bar[FB_F0 + nt], ph);
-        tc_fence_after();
-        if (t0) stamp(a, 0, bi, 10 + nt);
-        ld24(lane_addr + NT * nt + 24 * g, v);
+      {
+        float* pre_img = P.dgelu + (size_t)img * N * HD;
+#pragma unroll 1
+        for (int it = 0; it < 6; it++) {
+          const int nt = it / 3, j = it - 3 * nt;
+          if (j == 0) {
+            mbar_wait(&bar[FB_F0 + nt], ph);
+            tc_fence_after();
+            if (t0) stamp(a, 0, bi, 10 + nt);
+          }
+          float w[8];
+          ld8_add(NT * nt + 24 * g + 8 * j, pv + PV_B0 + NT * nt + 24 * g + 8 * j, w);
+          if (live) store8_tiled(pre_img, 24 * nt + 6 * g + 2 * j, w);      // pre-activation, kept for the backward
 #pragma unroll
-        for (int c = 0; c < 24; c++) v[c] = live ? v[c] + __ldg(P.b0 + NT * nt + 24 * g + c) : 0.f;
-        if (live) store24_tiled(P.dgelu + (size_t)img * N * HD, N, r, 24 * nt + 6 * g, v);   // pre-activation, kept for backward
-#pragma unroll
-        for (int c = 0; c < 24; c++) {
-          float y, dy;
-          gelu_both(v[c], y, dy);
-          v[c] = live ? y : 0.f;
+          for (int i = 0; i < 8; i++) {
+            float y, dy;
+            gelu_both(w[i], y, dy);
+            w[i] = live ? y : 0.f;
+          }
+          store8_split(sB, sB + 3 * CH, r, NT * nt + 24 * g + 8 * j, CH, w);
         }
-        store24_split(sB, sB + 3 * CH, r, NT * nt + 24 * g, v);
       }
       arrive(FB_G);
       if (t0) stamp(a, 0, bi, 12);
@@ -501,9 +556,10 @@ __global__ void __launch_bounds__(THREADS, 1) vit_tc_fwd_kernel(Args a) {
         mbar_wait(&bar[FB_F1], ph);
         tc_fence_after();
         if (t0) stamp(a, 0, bi, 13);
+        float v[24];
         ld24(lane_addr + 416 + 24 * g, v);
 #pragma unroll
-        for (int c = 0; c < 24; c++) x[c] = live ? x[c] + v[c] + __ldg(P.b1 + 24 * g + c) : 0.f;
+        for (int c = 0; c < 24; c++) x[c] = live ? x[c] + v[c] + pv[PV_B1 + 24 * g + c] : 0.f;
         if (live) {
           // the stack's output in the caller's row-major layout; block outputs in between are only read by the backward
           if (bi == a.nblocks - 1) store24_global(P.out + ((size_t)img * N + r) * D + 24 * g, x);
@@ -536,9 +592,13 @@ constexpr uint32_t BOFF_D = 0;                              // 4 chunks
 constexpr uint32_t BOFF_X = 4 * CH;                         // 16 chunks
 constexpr uint32_t BOFF_RING = 20 * CH;
 constexpr uint32_t BOFF_STAT = BOFF_RING + BNSTAGE * STAGE; // [2][64][4] floats
-constexpr uint32_t BOFF_ACC = BOFF_STAT + 2 * 64 * 4 * 4;       // [2 buffers][5 quantities][96] floats: column sums (bias / LayerNorm gradients)
-constexpr uint32_t BOFF_BAR = BOFF_ACC + 2 * 5 * 96 * 4;
-constexpr int BNBAR = 2 * BNSTAGE + 48;
+constexpr uint32_t BOFF_ACC = BOFF_STAT + 2 * 64 * 4 * 4;       // [5 quantities][96] floats: column sums (bias / LayerNorm gradients)
+constexpr uint32_t BOFF_PAR = BOFF_ACC + 5 * 96 * 4;        // [2 buffers][ln_g | ln_b | ln1_g | ln1_b] floats, copied by the loader
+constexpr int BPAR_FLOATS = 4 * 96;
+constexpr uint32_t STG_PITCH = 80;                              // bytes per staged row: 16 floats + 16 (conflict-free 16-byte stores)
+constexpr uint32_t BOFF_STG = BOFF_PAR + 2 * BPAR_FLOATS * 4;   // [4 flush warps][32 rows][STG_PITCH]: transposition tiles of the flush
+constexpr uint32_t BOFF_BAR = BOFF_STG + 4 * 32 * STG_PITCH;
+constexpr int BNBAR = 2 * BNSTAGE + 49;
 constexpr uint32_t BSMEM_BYTES = BOFF_BAR + BNBAR * 8 + 16;
 static_assert(BSMEM_BYTES <= 232448, "shared memory budget (backward)");
 // chunk indices inside the operand area (chunk c lives at smem + c * CH)
@@ -552,7 +612,7 @@ constexpr int C_UH = 16, C_UL = 18;                         // LN(x) for dWqkv (
 enum { BB_D = 0, BB_DGACC = 1 /*2*/, BB_GDP = 3, BB_DU1ACC = 4, BB_ATT = 5, BB_SACC = 6 /*4*/, BB_SCONS = 10 /*4*/, BB_DPACC = 14 /*4*/,
        BB_P = 18 /*4*/, BB_DVACC = 22 /*4*/, BB_DS = 26 /*4*/, BB_DQKACC = 30 /*4*/, BB_DQKV = 34, BB_U = 35, BB_DUACC = 36,
        BB_DW1_DONE = 37, BB_DW0_DONE = 38, BB_DWQKV_DONE = 39, BB_FFULL = 40 /*2*/, BB_FFREE = 42 /*2*/, BB_ACCRDY = 44,
-       BB_ACCFREE = 45 /*2*/, BB_COUNT = 47 };
+       BB_ACCFREE = 45 /*2*/, BB_PAR = 47 /*2*/, BB_COUNT = 49 };
 constexpr int PIECES = 24;                                  // weight-gradient pieces per block: dW1 6, dW0 6, dWqkv 12
 
 // column sums over the 32 rows of a warp of 24 per-thread values: reduce-scatter (the lanes trade halves of their columns),
@@ -621,7 +681,8 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + BOFF_BAR);
   uint64_t* empty = full + BNSTAGE;
   uint64_t* bar = empty + BNSTAGE;
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 48);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 49);
+  float* par = reinterpret_cast<float*>(smem + BOFF_PAR);
   auto chunk = [&](int c) -> uint8_t* { return smem + (uint32_t)c * CH; };
 
   pdl_launch_dependents();
@@ -641,7 +702,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
   }
   for (uint32_t i = tid * 16; i < 20 * CH; i += BTHREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
   float* accs = reinterpret_cast<float*>(smem + BOFF_ACC);
-  for (int i = tid; i < 2 * 5 * 96; i += BTHREADS) accs[i] = 0.f;
+  for (int i = tid; i < 5 * 96; i += BTHREADS) accs[i] = 0.f;
   if (warp == 3) tmem_alloc<512>(tslot);
   fence_async_smem();
   tc_fence_before();
@@ -662,6 +723,14 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           const int s = it % BNSTAGE;
           if (it >= BNSTAGE) mbar_wait(&empty[s], ((it / BNSTAGE) - 1) & 1);
           if (i == 7) mbar_wait(&bar[BB_DQKV], (L - 1 - bi) & 1);     // heads 2, 3 keep P / dS in the ring until here
+          if (i == 0) {      // the block's LayerNorm vectors -> shared memory (buffer last used two iterations ago, see the forward)
+            const NtVitBlock& P = a.blk[bi];
+            const int nb = (L - 1 - bi) & 1;
+            float* pb = par + nb * BPAR_FLOATS;
+            mbar_expect_tx(&bar[BB_PAR + nb], BPAR_FLOATS * 4);
+            bulk_g2s(pb, P.ln_g, D * 4, &bar[BB_PAR + nb]);            bulk_g2s(pb + 96, P.ln_b, D * 4, &bar[BB_PAR + nb]);
+            bulk_g2s(pb + 192, P.ln1_g, D * 4, &bar[BB_PAR + nb]);     bulk_g2s(pb + 288, P.ln1_b, D * 4, &bar[BB_PAR + nb]);
+          }
           mbar_expect_tx(&full[s], STAGE);
           bulk_g2s(smem + BOFF_RING + s * STAGE, wimg + (size_t)i * STAGE, STAGE, &full[s]);
         }
@@ -820,7 +889,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
     for (int n = 0; n < L; n++) {
       const NtVitBlock& P = a.blk[L - 1 - n];
       mbar_wait(&bar[BB_ACCRDY], n & 1);
-      float* acc = accs + (n & 1) * 480;
+      float* acc = accs;
       float* dsts[5] = {P.d_b1, P.d_ln1_g, P.d_ln1_b, P.d_ln_g, P.d_ln_b};
 #pragma unroll
       for (int k = 0; k < 5; k++)
@@ -829,11 +898,19 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           acc[96 * k + c] = 0.f;
         }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[BB_ACCFREE + (n & 1)]);
+      if (lane == 0) mbar_arrive(&bar[BB_ACCFREE]);
     }
   } else if (warp == 6 || warp == 7 || warp == 10 || warp == 11) {
-    // ===================== weight-gradient flush: TMEM lanes 64..127 -> red.global.add =====================
-    const int fq = warp & 3, fc = (warp >> 2) - 1, fl = 32 * (fq - 2) + lane;       // feature within the 64-feature half
+    // ===================== weight-gradient flush: TMEM lanes 64..127 -> shared staging -> red.global.add.v4 ================
+    // A lane holds 32 columns of ONE gradient row; straight from registers every red instruction would touch 32 rows (32
+    // half-used sectors) and the flood fills this SM's load/store queue in front of the token warps' shuffles and shared
+    // memory traffic (their LayerNorm-backward phase took 20 K cycles for 400 instructions).  Through a small staging
+    // tile each instruction instead covers 8 rows x 64 contiguous bytes.  (cp.reduce.async.bulk, one per row, was tried:
+    // the TMA engine needs ~20 cycles per 128-byte operation, 3072 of them per block — slower than the block itself.)
+    const int fq = warp & 3, fc = (warp >> 2) - 1;                     // TMEM lane quadrant (2, 3); 32-column half of the piece
+    uint8_t* tile = smem + BOFF_STG + (uint32_t)(2 * fc + fq - 2) * 32 * STG_PITCH;
+    const int sub = lane >> 2, quad = lane & 3;                        // read side: row 8 i + sub, columns 4 quad .. 4 quad + 3
+    const int F0 = 32 * (fq - 2);                                      // first feature (within the 64-feature half) of this warp
     uint32_t piece = 0;
     for (int n = 0; n < L; n++) {
       const NtVitBlock& P = a.blk[L - 1 - n];
@@ -846,28 +923,44 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar[BB_FFREE + buf]);
-        float* dst = nullptr;
-        int ncol = 32;
+        if (lane == 0) mbar_arrive(&bar[BB_FFREE + buf]);               // accumulator consumed: the MMA issuer may reuse it
+        // destination of staged row 0 of this warp, row pitch, valid rows [0, nrow) plus an optional bias row
+        float* base = nullptr;
+        float* bias = nullptr;
+        int pitch = 0, nrow = 32, brow = -1, ncol = 32;
         if (p < 6) {
-          const int f = p >> 1, j = p & 1, F = 64 * f + fl;
-          if (!(j == 1 && fc == 1)) dst = P.d_w1 + (size_t)F * D + 64 * j + 32 * fc;           // F < 192 always
+          const int f = p >> 1, j = p & 1;
+          base = P.d_w1 + (size_t)(64 * f + F0) * D + 64 * j + 32 * fc; pitch = D;
+          if (j == 1 && fc == 1) ncol = 0;                              // the second column piece of dW1 is 32 wide
         } else if (p < 12) {
-          const int f = (p - 6) / 3, j = (p - 6) % 3, F = 64 * f + fl;
-          if (F < D) dst = P.d_w0 + (size_t)F * HD + 64 * j + 32 * fc;
-          else if (F == D) dst = P.d_b0 + 64 * j + 32 * fc;
+          const int f = (p - 6) / 3, j = (p - 6) % 3, Fa = 64 * f + F0;
+          base = P.d_w0 + (size_t)Fa * HD + 64 * j + 32 * fc; pitch = HD;
+          nrow = min(32, max(0, D - Fa));
+          if (D >= Fa && D < Fa + 32) { brow = D - Fa; bias = P.d_b0 + 64 * j + 32 * fc; }
         } else {
-          const int f = (p - 12) / 6, j = (p - 12) % 6, F = 64 * f + fl;
+          const int f = (p - 12) / 6, j = (p - 12) % 6, Fa = 64 * f + F0;
           const int col = (j >> 1) * D + DH * (2 * (j & 1) + fc);       // [q|k|v][head][24] <- padded [part][head][32]
-          if (F < D) dst = P.d_wqkv + (size_t)F * 3 * D + col;
-          else if (F == D) dst = P.d_bqkv + col;
+          base = P.d_wqkv + (size_t)Fa * 3 * D + col; pitch = 3 * D;
+          nrow = min(32, max(0, D - Fa));
+          if (D >= Fa && D < Fa + 32) { brow = D - Fa; bias = P.d_bqkv + col; }
           ncol = DH;
         }
-        if (dst) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            if (c < ncol)
-              red4(dst + c, __uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+        for (int hc = 0; hc < 2; hc++) {                                // two 16-column halves through the tile
+          __syncwarp();                                                 // the previous half's reads of the tile are done
+#pragma unroll
+          for (int c = 0; c < 16; c += 4)
+            *reinterpret_cast<uint4*>(tile + lane * STG_PITCH + 4 * c) = make_uint4(v[16 * hc + c], v[16 * hc + c + 1], v[16 * hc + c + 2], v[16 * hc + c + 3]);
+          __syncwarp();
+          if (16 * hc + 4 * quad < ncol) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const int row = 8 * i + sub;
+              const float4 t = *reinterpret_cast<const float4*>(tile + row * STG_PITCH + 16 * quad);
+              if (row < nrow) red4(base + (size_t)row * pitch + 16 * hc + 4 * quad, t.x, t.y, t.z, t.w);
+              else if (row == brow) red4(bias + 16 * hc + 4 * quad, t.x, t.y, t.z, t.w);
+            }
+          }
         }
       }
     }
@@ -897,10 +990,10 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
       float v[24], w[24];
       const bool t0 = tid == 0;
       if (t0) stamp(a, 0, n, 0);
-      float* acc = accs + (n & 1) * 480 + 24 * g;             // [quantity][96]: db1, dgamma1, dbeta1, dgamma, dbeta of this block
-      if (n >= 2) wait(BB_ACCFREE + (n & 1), ((n >> 1) - 1) & 1);
-      // ---- d -> operand planes; db1 += colsum(d)                         fullconnect.py:122
-      colsum24_atomic(d, lane, acc);
+      float* acc = accs + 24 * g;                             // [quantity][96]: db1, dgamma1, dbeta1, dgamma, dbeta of this block
+      const float* pv = par + (n & 1) * BPAR_FLOATS + 24 * g;  // this thread's 24 columns of ln_g | ln_b | ln1_g | ln1_b (stride 96)
+      mbar_wait(&bar[BB_PAR + (n & 1)], (n >> 1) & 1);
+      // ---- d -> operand planes
       if (n > 0) wait(BB_DW1_DONE, (n - 1) & 1);               // the previous block's dW1 products read the d planes
       store24_split(chunk(C_DH), chunk(C_DL), r, 24 * g, d);
       arrive(BB_D);
@@ -918,32 +1011,48 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
 #pragma unroll
         for (int c = 0; c < 24; c++) {
           xh[c] = live ? (v[c] - mean) * rstd1 : 0.f;
-          w[c] = live ? xh[c] * __ldg(P.ln1_g + 24 * g + c) + __ldg(P.ln1_b + 24 * g + c) : 0.f;
+          w[c] = live ? xh[c] * pv[192 + c] + pv[288 + c] : 0.f;
         }
         if (n > 0) wait(BB_DWQKV_DONE, (n - 1) & 1);           // the previous block's dWqkv products read this area (LN(x), dqkv)
         store24_split(chunk(C_U1H), chunk(C_U1L), r, 24 * g, w);
         if (g == 0) store_ones_unit(chunk(C_U1H), chunk(C_U1L), r, D, live);
+        // db1 += colsum(d)  (fullconnect.py:122) — here, not at the top: the previous block's column sums have left the
+        // shared accumulators by now
+        if (n > 0) wait(BB_ACCFREE, (n - 1) & 1);
+        colsum24_atomic(d, lane, acc);
       }
       // ---- dG -> G = GELU(pre), dpre = dG * GELU'(pre)                   attention.py:58-59
       if (t0) stamp(a, 0, n, 2);
-      for (int nt = 0; nt < 2; nt++) {
-        wait(BB_DGACC + nt, ph);
-        if (t0) stamp(a, 0, n, 3 + nt);
-        ld24(lane_addr + NT * nt + 24 * g, v);
-        if (live) load24_tiled(P.dgelu + (size_t)img * N * HD, N, r, 24 * nt + 6 * g, w);
-        else {
+      {
+        const float* pre_img = P.dgelu + (size_t)img * N * HD;
+#pragma unroll 1
+        for (int it = 0; it < 6; it++) {                       // rolled over 8-column units (code size: see the forward)
+          const int nt = it / 3, j = it - 3 * nt;
+          if (j == 0) {
+            wait(BB_DGACC + nt, ph);
+            if (t0) stamp(a, 0, n, 3 + nt);
+          }
+          uint32_t t[8];
+          tmem_ld8(lane_addr + NT * nt + 24 * g + 8 * j, t);
+          float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+          if (live) {
+            const int u = 24 * nt + 6 * g + 2 * j;
+            p0 = *reinterpret_cast<const float4*>(pre_img + ((size_t)u * N + r) * 4);
+            p1 = *reinterpret_cast<const float4*>(pre_img + ((size_t)(u + 1) * N + r) * 4);
+          }
+          tmem_wait_ld();
+          const float pre[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          float gy[8], dp[8];
 #pragma unroll
-          for (int c = 0; c < 24; c++) w[c] = 0.f;
+          for (int i = 0; i < 8; i++) {
+            float y, dy;
+            gelu_both(pre[i], y, dy);
+            gy[i] = live ? y : 0.f;
+            dp[i] = live ? __uint_as_float(t[i]) * dy : 0.f;
+          }
+          store8_split(chunk(C_GH), chunk(C_GL), r, NT * nt + 24 * g + 8 * j, CH, gy);
+          store8_split(chunk(C_PH), chunk(C_PL), r, NT * nt + 24 * g + 8 * j, CH, dp);
         }
-#pragma unroll
-        for (int c = 0; c < 24; c++) {
-          float y, dy;
-          gelu_both(w[c], y, dy);
-          w[c] = live ? y : 0.f;
-          v[c] = live ? v[c] * dy : 0.f;
-        }
-        store24_split(chunk(C_GH), chunk(C_GL), r, NT * nt + 24 * g, w);
-        store24_split(chunk(C_PH), chunk(C_PL), r, NT * nt + 24 * g, v);
       }
       arrive(BB_GDP);
       if (t0) stamp(a, 0, n, 5);
@@ -958,7 +1067,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
         for (int c = 0; c < 24; c++) {
           if (!live) v[c] = 0.f;
           w[c] = v[c] * xh[c];                                 // dgamma contribution
-          const float gd = v[c] * __ldg(P.ln1_g + 24 * g + c);
+          const float gd = v[c] * pv[192 + c];
           p1 += gd;
           p2 += gd * xh[c];
         }
@@ -972,7 +1081,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
         s1 *= (1.0f / D); s2 *= (1.0f / D);
 #pragma unroll
         for (int c = 0; c < 24; c++) {
-          const float gd = v[c] * __ldg(P.ln1_g + 24 * g + c);
+          const float gd = v[c] * pv[192 + c];
           d[c] = live ? d[c] + rstd1 * (gd - s1 - xh[c] * s2) : 0.f;
         }
         if (t0) stamp(a, 1, n, 4);
@@ -990,16 +1099,27 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           *reinterpret_cast<uint4*>(chunk(C_DH) + zoff) = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(chunk(C_DL) + zoff) = make_uint4(0, 0, 0, 0);
         }
-        for (int part = 0; part < 3; part++) {
-          if (live) load24_tiled(P.qkv + (size_t)img * N * 3 * D, N, r, 24 * part + 6 * g, v);
-          else {
-#pragma unroll
-            for (int c = 0; c < 24; c++) v[c] = 0.f;
+        {
+          const float* qkv_img = P.qkv + (size_t)img * N * 3 * D;
+#pragma unroll 1
+          for (int it = 0; it < 9; it++) {
+            const int part = it / 3, j = it - 3 * part;
+            float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+            if (live) {
+              const int u = 24 * part + 6 * g + 2 * j;
+              p0 = *reinterpret_cast<const float4*>(qkv_img + ((size_t)u * N + r) * 4);
+              p1 = *reinterpret_cast<const float4*>(qkv_img + ((size_t)(u + 1) * N + r) * 4);
+            }
+            const float w8[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            uint8_t* hi = chunk(C_QH + 2 * part);
+            uint8_t* lo = chunk(C_QL + 2 * part);
+            store8_split(hi, lo, r, DHP * g + 8 * j, CH, w8);
+            if (j == 2) {
+              const uint32_t zoff = plane_off(r, DHP * g + DH, CH);
+              *reinterpret_cast<uint4*>(hi + zoff) = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(lo + zoff) = make_uint4(0, 0, 0, 0);
+            }
           }
-          store24_split(chunk(C_QH + 2 * part), chunk(C_QL + 2 * part), r, DHP * g, v);
-          const uint32_t zoff = plane_off(r, DHP * g + DH, CH);
-          *reinterpret_cast<uint4*>(chunk(C_QH + 2 * part) + zoff) = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(chunk(C_QL + 2 * part) + zoff) = make_uint4(0, 0, 0, 0);
         }
         arrive(BB_ATT);
         if (t0) stamp(a, 0, n, 9);
@@ -1086,14 +1206,17 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
       {
         wait(BB_DQKACC + g, ph);
         if (t0) stamp(a, 0, n, 13);
-        for (int part = 0; part < 3; part++) {
-          const uint32_t col = part == 0 ? 64 * g : (part == 1 ? 64 * g + 32 : 256 + DHP * g);
-          ld24(lane_addr + col, v);
-          if (!live) {
+#pragma unroll 1
+        for (int it = 0; it < 9; it++) {
+          const int part = it / 3, j = it - 3 * part;
+          const uint32_t col = (part == 0 ? 64 * g : (part == 1 ? 64 * g + 32 : 256 + DHP * g)) + 8 * j;
+          uint32_t t[8];
+          tmem_ld8(lane_addr + col, t);
+          tmem_wait_ld();
+          float w8[8];
 #pragma unroll
-            for (int c = 0; c < 24; c++) v[c] = 0.f;
-          }
-          store24_split(chunk(C_QH + 2 * part), chunk(C_QL + 2 * part), r, DHP * g, v);
+          for (int i = 0; i < 8; i++) w8[i] = live ? __uint_as_float(t[i]) : 0.f;
+          store8_split(chunk(C_QH + 2 * part), chunk(C_QL + 2 * part), r, DHP * g + 8 * j, CH, w8);
         }
         arrive(BB_DQKV);
       }
@@ -1113,7 +1236,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
 #pragma unroll
         for (int c = 0; c < 24; c++) {
           xh[c] = live ? (v[c] - mean) * rstd0 : 0.f;
-          w[c] = live ? xh[c] * __ldg(P.ln_g + 24 * g + c) + __ldg(P.ln_b + 24 * g + c) : 0.f;
+          w[c] = live ? xh[c] * pv[c] + pv[96 + c] : 0.f;
         }
         wait(BB_DQKACC + 1, ph);                               // heads 0, 1 kept P / dS here; their products are done
         store24_split(chunk(C_UH), chunk(C_UL), r, 24 * g, w);
@@ -1131,7 +1254,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
         for (int c = 0; c < 24; c++) {
           if (!live) v[c] = 0.f;
           w[c] = v[c] * xh[c];
-          const float gd = v[c] * __ldg(P.ln_g + 24 * g + c);
+          const float gd = v[c] * pv[c];
           p1 += gd;
           p2 += gd * xh[c];
         }
@@ -1147,7 +1270,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
         s1 *= (1.0f / D); s2 *= (1.0f / D);
 #pragma unroll
         for (int c = 0; c < 24; c++) {
-          const float gd = v[c] * __ldg(P.ln_g + 24 * g + c);
+          const float gd = v[c] * pv[c];
           d[c] = live ? d[c] + rstd0 * (gd - s1 - xh[c] * s2) : 0.f;
         }
       }

@@ -38,9 +38,11 @@ def supported(N, D, H):
 
 
 def tc_supported(N, D, H):
-    """The tcgen05 / TMEM kernels (csrc/vit_block_tc.cu) cover this shape: the README configuration (D = 96, 4 heads,
-    N <= 64).  NTB200_VIT_TC=0 forces the older mma.sync kernels (csrc/vit_block.cu), which cover more (D, H) pairs."""
-    if os.environ.get("NTB200_VIT_TC", "1") == "0" or not enabled() or get_gemm_mode() != 1:
+    """The tcgen05 / TMEM kernels (csrc/vit_block_tc.cu) cover this shape (the README configuration: D = 96, 4 heads,
+    N <= 64) AND are selected.  They are OPT-IN (NTB200_VIT_TC=1): measured on B200 at B = 100 (tools/vit_tc_time.py,
+    DESIGN.md 4.4) the forward is faster than the mma.sync kernels of csrc/vit_block.cu (138 vs 161 us) but the backward is
+    slower (310 vs 239 us), so the default stack stays on the older kernels until the backward catches up."""
+    if os.environ.get("NTB200_VIT_TC", "0") != "1" or not enabled() or get_gemm_mode() != 1:
         return False
     ok = ctypes.c_int(0)
     lib.nt_vit_tc_supported(int(N), int(D), int(H), ctypes.byref(ok))
