@@ -321,6 +321,15 @@ int nt_dp_join(void);                            /* compute stream waits for out
 /* replicas must start identical: rank `root`'s buffer (n 4-byte words) overwrites every other rank's, on the compute stream */
 int nt_dp_broadcast(void* buf, size_t n, int root);
 int nt_dp_shutdown(void);
+/* Small-message all-reduce over NVLink peer memory (csrc/dp_nccl.cu): every rank maps every peer's gradient arena through
+ * CUDA IPC and ONE kernel per rank sums in place (two-shot: rank r reduces slice r of all arenas and stores it back into
+ * all of them), bracketed by flag barriers in peer memory.  Used instead of the NCCL call when the range is small enough to
+ * be latency-bound (the README ViT: 3.4 MB).  handles are 64-byte cudaIpcMemHandle_t, world of them, rank-ordered. */
+int nt_p2p_flags_alloc(void** dptr);
+int nt_p2p_ipc_handle(void* dptr, void* handle64);
+int nt_p2p_setup(int rank, int world, float* my_grads, const void* grad_handles, void* my_flags, const void* flag_handles);
+int nt_p2p_allreduce_sum(size_t off, size_t n, int channel);
+int nt_p2p_shutdown(void);
 
 #ifdef __cplusplus
 }

@@ -65,10 +65,55 @@ class DataParallel:
         lib.nt_dp_init(ctypes.create_string_buffer(uid, 128), self.rank, self.world)
         self.nccl_ready = True
 
-    def allreduce_buckets(self, flat, buckets=1):
+    def init_p2p(self, grads):
+        """Map every rank's gradient arena into this process (CUDA IPC over NVLink) for the small-message all-reduce
+        (nt_p2p_allreduce_sum).  `grads` must be a whole device allocation (the flat arena is).  Collective."""
+        import ctypes
+        import os
         from ._lib import lib
+        max_floats = int(float(os.environ.get("NTB200_P2P_MAX_MB", "16")) * (1 << 20) / 4)
+        if (self.world == 1 or self.world > 8 or os.environ.get("NTB200_P2P", "1") == "0" or getattr(self, "p2p_ready", False)
+                or grads.size > 4 * max_floats):
+            return False
+        flags = ctypes.c_void_p()
+        lib.nt_p2p_flags_alloc(ctypes.byref(flags))
+        hg, hf = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
+        lib.nt_p2p_ipc_handle(grads.ptr, hg)
+        lib.nt_p2p_ipc_handle(flags, hf)
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, (self.rank, hg.raw, hf.raw, grads.size))
+        gathered.sort(key=lambda t: t[0])
+        assert all(t[3] == grads.size for t in gathered), "gradient arenas differ in size across ranks"
+        allg = ctypes.create_string_buffer(b"".join(t[1] for t in gathered), 64 * self.world)
+        allf = ctypes.create_string_buffer(b"".join(t[2] for t in gathered), 64 * self.world)
+        lib.nt_p2p_setup(self.rank, self.world, grads.ptr, allg, flags, allf)
+        self.p2p_ready, self.p2p_base, self.p2p_size = True, grads.ptr, grads.size
+        self.p2p_max_floats = int(float(os.environ.get("NTB200_P2P_MAX_MB", "16")) * (1 << 20) / 4)
+        self.barrier()
+        return True
+
+    def close_p2p(self):
+        from ._lib import lib
+        if getattr(self, "p2p_ready", False):
+            self.barrier()
+            lib.nt_p2p_shutdown()
+            self.p2p_ready = False
+            self.barrier()
+
+    def allreduce_range(self, flat, lo, hi, side=False):
+        """Sum grads[lo:hi) over the ranks, in place.  Small ranges of the IPC-mapped arena go through the one-kernel NVLink
+        reduction, everything else through NCCL.  side=True: on the comm stream, to be joined later (nt_dp_join)."""
+        from ._lib import lib
+        if (getattr(self, "p2p_ready", False) and flat.ptr == self.p2p_base and hi - lo <= self.p2p_max_floats
+                and lo % 4 == 0 and (hi - lo) % 4 == 0):
+            lib.nt_p2p_allreduce_sum(lo, hi - lo, 1 if side else 0)
+            return "p2p"
+        lib.nt_dp_allreduce_sum(flat.ptr + 4 * lo, hi - lo)
+        return "nccl"
+
+    def allreduce_buckets(self, flat, buckets=1):
         for lo, hi in bucket_bounds(flat.size, buckets):
-            lib.nt_dp_allreduce_sum(flat.ptr + 4 * lo, hi - lo)
+            self.allreduce_range(flat, lo, hi, side=True)
 
     def barrier(self):
         if self.world > 1:
@@ -94,6 +139,9 @@ class DataParallel:
 
     def shutdown(self):
         from ._lib import lib
+        if getattr(self, "p2p_ready", False):
+            lib.nt_p2p_shutdown()
+            self.p2p_ready = False
         if self.nccl_ready:
             lib.nt_dp_shutdown()
             self.nccl_ready = False

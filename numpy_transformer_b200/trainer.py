@@ -21,6 +21,7 @@ from ._lib import lib
 from .device import DeviceArray, PinnedBuffer, as_device, init, keep_allocations, rehome_generation, bump_rehome
 from . import ops
 from . import fused_vit
+from .parallel import bucket_bounds
 
 
 def _import_layers():
@@ -230,6 +231,8 @@ class TrainStep:
         self._vit_block_t = L["attention_layer"]
         self._layer_types = L
         self._opt_runs = self.arena.optimizer_runs(adam)
+        if dp is not None and dp.world > 1 and dp.nccl_ready:
+            dp.init_p2p(self.arena.grads)           # small arenas: one-kernel NVLink all-reduce instead of an NCCL call
         self._gen = rehome_generation()
         self.sync_replicas()
 
@@ -302,7 +305,7 @@ class TrainStep:
                     if offs:
                         lib.nt_side_join()
                         lo = min(offs)
-                        lib.nt_dp_allreduce_sum(self.arena.grads.ptr + 4 * lo, self.arena.n - lo)
+                        self.dp.allreduce_range(self.arena.grads, lo, self.arena.n, side=True)
                         self._early_from = lo
                 delta = fused_vit.backward_stack(runs[ends[i]], delta)
                 i = ends[i] - 1
@@ -321,10 +324,14 @@ class TrainStep:
         a = self.arena
         lib.nt_side_join()                       # weight-gradient branch must land before all-reduce / update
         if self.dp is not None and self.dp.world > 1:
-            if self._early_from is None:
-                self.dp.allreduce_buckets(a.grads, self.grad_buckets)
-            elif self._early_from > 0:
-                self.dp.allreduce_buckets(a.grads.view(0, (self._early_from,)), self.grad_buckets)
+            hi = a.n if self._early_from is None else self._early_from
+            if hi > 0:
+                if getattr(self.dp, "p2p_ready", False) and hi <= self.dp.p2p_max_floats:
+                    # launch-bound shapes: ONE NVLink peer-memory kernel on the compute stream right behind the backward
+                    self.dp.allreduce_range(a.grads, 0, hi, side=False)
+                else:
+                    for lo_, hi_ in bucket_bounds(hi, self.grad_buckets):
+                        self.dp.allreduce_range(a.grads, lo_, hi_, side=True)
             lib.nt_dp_join()
         # one launch per run of slots that share an optimizer: Adam* where the layer has moments and adam=True, plain SGD
         # elsewhere (Position_learnable.param has no moments in the reference: Position_add.py:26-28 is always SGD)
@@ -472,6 +479,8 @@ class TrainStep:
             lib.nt_graph_destroy(self.graph)
             self.graph = None
         self._graph_buffers = None
+        if self.dp is not None and getattr(self.dp, "p2p_ready", False) and self.dp.p2p_base == self.arena.grads.ptr:
+            self.dp.close_p2p()                     # the peers' mappings of this arena end with it (collective)
 
     def __del__(self):
         try:

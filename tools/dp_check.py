@@ -32,8 +32,11 @@ def run(dp, world, rank, dim):
     params = M.vit_init(cfg, 0)
     images, labels, onehot = M.synthetic_vit_batch(cfg, 1)
     lo, hi = shard_range(cfg.batch, rank, world)
-    layers = trainer.build_vit_layers(per, embed_dim=dim, heads=4, blocks=2, seed=0)
+    # every rank seeds differently: TrainStep must broadcast rank 0's parameters (seed 0 = the oracle's) before training
+    layers = trainer.build_vit_layers(per, embed_dim=dim, heads=4, blocks=2, seed=17 * rank)
     ts = trainer.TrainStep(layers, "vit", (per,) + images.shape[1:], lr=0.02, dp=dp, grad_buckets=3)
+    if rank == 0:
+        print("gradient all-reduce path:", "NVLink peer-memory kernel" if getattr(dp, "p2p_ready", False) else "NCCL", flush=True)
     worst = 0.0
     for step in range(4):
         ref = M.vit_step(params, images, onehot, 0.02, cfg)
