@@ -27,6 +27,9 @@ import time
 
 import numpy as np
 
+# NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment; stdout carries exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -218,6 +221,7 @@ def measure(workload, dp, K, W, full, local, buckets=1, min_region_s=0.6):
     for r in range(rounds):
         for i in range(K):
             lib.nt_flush_l2()
+            ts.device_barrier()          # N > 1: ranks leave the flush together (its duration differs by tens of us per GPU)
             lib.nt_event_record(ev[2 * i])
             ts.run_device()
             lib.nt_event_record(ev[2 * i + 1])
@@ -298,7 +302,7 @@ def profile_ops(ts, dp, kind, c, workload, prof_steps=5):
         cl["flops"] += fl * n
         cl["bytes"] += by * n
     # the dominant KERNEL: waits on the collective (nt_dp_*) stay in the op table but are not a kernel of this repo
-    tname, tc = max(((k, v) for k, v in classes.items() if not k.startswith("nt_dp_")), key=lambda kv: kv[1]["ms"])
+    tname, tc = max(((k, v) for k, v in classes.items() if not k.startswith(("nt_dp_", "nt_p2p_"))), key=lambda kv: kv[1]["ms"])
     if tc["flops"] > 0:
         ach = tc["flops"] / (tc["ms"] / 1e3) / 1e12
         roof = dict(bound="tensor", kernel=tname, achieved=ach, peak=pk["tf_burst"], unit="TFLOP/s", frac=ach / pk["tf_burst"],
@@ -406,7 +410,8 @@ def run_ours(args):
                        **{k: v for k, v in c.items() if k != "batch"}, "parallelism": "dp%d" % world,
                        "gemm_mode": m["gemm_mode"], "timed_rounds_of_K_steps": m["rounds"],
                        "ms_per_step_round_min_max": [m["ms_per_step_round_min"], m["ms_per_step_round_max"]],
-                       "l2": "256 MB memset between timed steps (working set is L2-resident)",
+                       "l2": "256 MB memset between timed steps (working set is L2-resident)" + (
+                           "; then a 16-byte device-side all-reduce so that the ranks start each timed step together" if world > 1 else ""),
                        "graph_kernels_per_step": m["graph_kernels"], "params": m["params"]},
             "clocks": m["clocks"], "e2e": m["e2e"], "gpu_launches": m["launches"],
             "roofline": m["roofline"], "step_roofline": m["step_roofline"],

@@ -71,7 +71,7 @@ class _Lib:
     _PROFILED = ("nt_linear_", "nt_layernorm_", "nt_attention_", "nt_cross_entropy", "nt_sgd", "nt_adam_star",
                  "nt_patchify", "nt_add", "nt_embedding_", "nt_gelu_", "nt_relu_", "nt_softmax_", "nt_dp_", "nt_vit_blocks_fwd",
                  "nt_vit_blocks_bwd", "nt_split_bf16", "nt_kv_append", "nt_decode_embed",
-                 "nt_argmax_next", "nt_increment")
+                 "nt_argmax_next", "nt_increment", "nt_p2p_allreduce", "nt_vit_tc_fwd", "nt_vit_tc_bwd")
 
     def profile_begin(self, external=False):
         """external=True records with cudaEventRecordExternal so the pairs survive stream capture as graph

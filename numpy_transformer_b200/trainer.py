@@ -14,6 +14,7 @@ The update is applied after the whole backward instead of layer by layer; a laye
 reads another layer's parameters, so the result is identical to the reference's interleaving.
 """
 import ctypes
+import os
 import numpy as np
 
 from . import install
@@ -297,7 +298,7 @@ class TrainStep:
         while i >= 0:
             l = layers[i]
             if i in ends:
-                if self.dp is not None and self.dp.world > 1 and self._early_from is None:
+                if self.dp is not None and self.dp.world > 1 and self._early_from is None and os.environ.get("NTB200_DP_SKIP") != "1":
                     # data parallel: the gradients of everything AFTER the fused stack (final LayerNorm + head, more than
                     # half of the V1 arena) are complete -> all-reduce them now, under the fused backward launch
                     offs = [self.arena.first_offset(l) for l in layers[i + 1:]]
@@ -323,7 +324,9 @@ class TrainStep:
         self.loss, self.argmax = self.d_loss, self.d_amax
         a = self.arena
         lib.nt_side_join()                       # weight-gradient branch must land before all-reduce / update
-        if self.dp is not None and self.dp.world > 1:
+        if self.dp is not None and self.dp.world > 1 and os.environ.get("NTB200_DP_SKIP") == "1":
+            pass            # measurement aid: replicas run unsynchronised (what the step costs without any exchange)
+        elif self.dp is not None and self.dp.world > 1:
             hi = a.n if self._early_from is None else self._early_from
             if hi > 0:
                 if getattr(self.dp, "p2p_ready", False) and hi <= self.dp.p2p_max_floats:
@@ -343,6 +346,14 @@ class TrainStep:
                 lib.nt_sgd(a.params.ptr + 4 * lo, a.grads.ptr + 4 * lo, n, 0.0, self.d_lr.ptr, 1)
         if self.adam:
             lib.nt_increment(self.d_t.ptr)
+
+    def device_barrier(self):
+        """Data parallel: the ranks' compute streams meet here — a 16-byte all-reduce of gradient words that are zero
+        between steps.  bench.py puts it between the L2 flush and the timed step so that one rank's slower flush is not
+        charged to the others' step (they would wait for it inside the gradient exchange)."""
+        if self.dp is not None and self.dp.world > 1:
+            self.dp.allreduce_range(self.arena.grads, 0, 4, side=False)
+            lib.nt_dp_join()
 
     def set_lr(self, lr):
         if float(lr) != self._lr:
