@@ -54,7 +54,7 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void spin_until(const unsigned* p, unsigned epoch) {
   for (unsigned it = 0; it < (1u << 27); ++it) {
     if ((int)(ld_acquire_sys(p) - epoch) >= 0) return;
-    __nanosleep(64);
+    if (it > 64) __nanosleep(32);
   }
   __trap();
 }
@@ -85,15 +85,21 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(P2PArgs a, int chan,
     for (int p = 0; p < P2P_MAX; p++)
       if (p < a.world) reinterpret_cast<float4*>(a.buf[p] + off)[i] = acc;
   }
-  __threadfence_system();
+  __threadfence_system();                          // this thread's peer stores are out
+  __shared__ unsigned s_last;
   __syncthreads();
-  if (tid == 0) {
-    const unsigned t = atomicAdd(&mine->done, 1u);
-    if (t == gridDim.x - 1) {                      // last CTA of this rank: every store of the rank is out
-      mine->done = 0;
+  if (tid == 0) s_last = (atomicAdd(&mine->done, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {                                    // last CTA of this rank to finish: every store of the rank is out
+    // one thread per peer: signal and wait in parallel (a loop of release stores by one thread costs a fence round trip each)
+    if (tid < a.world) {
       __threadfence_system();
-      for (int p = 0; p < a.world; p++) st_release_sys(&(a.flags[p] + chan)->end[a.rank], epoch);
-      for (int p = 0; p < a.world; p++) spin_until(&mine->end[p], epoch);      // all the slices of MY arena have landed
+      st_release_sys(&(a.flags[tid] + chan)->end[a.rank], epoch);
+      spin_until(&mine->end[tid], epoch);          // rank `tid` has stored its slice into MY arena
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mine->done = 0;
       mine->epoch = epoch;
       __threadfence();
     }

@@ -309,6 +309,14 @@ class TrainStep:
                         self.dp.allreduce_range(self.arena.grads, lo, self.arena.n, side=True)
                         self._early_from = lo
                 delta = fused_vit.backward_stack(runs[ends[i]], delta)
+                if (self.dp is not None and self.dp.world > 1 and self._early_from is not None
+                        and os.environ.get("NTB200_DP_SKIP") != "1"):
+                    # the block gradients are complete: reduce them NOW on the comm stream, under the stem's backward
+                    # kernels; only the (tiny) range in front of the blocks is left for the end of the step
+                    lo = self.arena.first_offset(layers[ends[i]])
+                    if lo is not None and lo < self._early_from:
+                        self.dp.allreduce_range(self.arena.grads, lo, self._early_from, side=True)
+                        self._early_from = lo
                 i = ends[i] - 1
                 continue
             if l is first and (hasattr(l, "fullconnect") or hasattr(l, "convolution")):
