@@ -7,6 +7,11 @@
 
 namespace nt {
 bool attention_bf16_ok(int N, int H, int dh);
+// attention_tc.cu: tcgen05 / TMEM kernels for dh == 64, 16 <= N <= 64 (no dense mask, no score output)
+bool attention_tc_ok(int N, int H, int dh, int mask_kind, bool want_scores);
+int attention_fwd_tc(const float* qkv, int mask_kind, float* out, float* P, int B, int N, int H, const float* residual, void* o_hi,
+                     void* o_lo);
+int attention_bwd_tc(const float* dout, const float* qkv, float* dqkv, int B, int N, int H, int causal, void* g_hi, void* g_lo);
 int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S, int B, int N, int H,
                        const float* residual, void* o_hi, void* o_lo);
 int attention_bwd_bf16(const float* dout, const float* qkv, const float* P, float* dqkv, float* tsum, int B, int N, int H,
@@ -1175,6 +1180,7 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
   NT_REQUIRE(mask_kind != NT_MASK_DENSE || mask, "nt_attention_fwd: dense mask_kind needs a mask");
   if (B == 0) return 0;
   const int D = H * dh;
+  if (nt::attention_tc_ok(N, H, dh, mask_kind, S != nullptr)) return nt::attention_fwd_tc(qkv, mask_kind, out, P, B, N, H, residual, nullptr, nullptr);
   if (nt::attention_bf16_ok(N, H, dh)) return nt::attention_fwd_bf16(qkv, mask, mask_kind, out, P, S, B, N, H, residual, nullptr, nullptr);
   if (const char* e = getenv("NTB200_ATT_MMA")) g_att_mma = (e[0] != '0');
   if (mma_ok(N, dh)) {
@@ -1254,6 +1260,8 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
   if (B == 0) return 0;
   const int D = H * dh;
   // BF16x3 kernels (attention_bf16.cu): `scratch` only carries the B*H*N softmax-backward row sums
+  if (nt::attention_tc_ok(N, H, dh, mask_kind, false))
+    return nt::attention_bwd_tc(dout, qkv, dqkv, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0, nullptr, nullptr);
   if ((scratch || N <= 64) && nt::attention_bf16_ok(N, H, dh))
     return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0, nullptr, nullptr, nullptr);
   if (mma_ok(N, dh)) {
@@ -1357,6 +1365,7 @@ int nt_attention_fwd_split(const float* qkv, const float* mask, int mask_kind, f
   NT_REQUIRE(nt::attention_bf16_ok(N, H, dh), "nt_attention_fwd_split: only the BF16x3 kernels (dh == 64, GEMM mode 1) emit split outputs");
   NT_REQUIRE((out_hi != nullptr) == (out_lo != nullptr), "nt_attention_fwd_split: pass both split planes or neither");
   if (B == 0) return 0;
+  if (nt::attention_tc_ok(N, H, dh, mask_kind, S != nullptr)) return nt::attention_fwd_tc(qkv, mask_kind, out, P, B, N, H, residual, out_hi, out_lo);
   return nt::attention_fwd_bf16(qkv, mask, mask_kind, out, P, S, B, N, H, residual, out_hi, out_lo);
 }
 
@@ -1368,6 +1377,8 @@ int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, 
              "nt_attention_bwd_split: only the BF16x3 kernels (dh == 64, GEMM mode 1, scratch of B*H*N floats) emit split outputs");
   NT_REQUIRE((dqkv_hi != nullptr) == (dqkv_lo != nullptr), "nt_attention_bwd_split: pass both split planes or neither");
   if (B == 0) return 0;
+  if (nt::attention_tc_ok(N, H, dh, mask_kind, false))
+    return nt::attention_bwd_tc(dout, qkv, dqkv, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0, dqkv_hi, dqkv_lo);
   return nt::attention_bwd_bf16(dout, qkv, P, dqkv, scratch, B, N, H, mask_kind == NT_MASK_CAUSAL ? 1 : 0, dqkv_hi, dqkv_lo, att_out);
 }
 

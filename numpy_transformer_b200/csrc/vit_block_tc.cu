@@ -18,6 +18,7 @@
 //   * The fp32 residual stream of the image stays in REGISTERS (24 values per thread) across the whole stack.
 #include "common.cuh"
 #include "umma.cuh"
+#include <cstdlib>
 
 namespace nt {
 namespace vtc {
@@ -32,6 +33,7 @@ struct Args {
   const float* dout;    // [B,N,D] gradient w.r.t. the last block's output      (backward)
   float* dx;            // [B,N,D] gradient w.r.t. x                              (backward)
   long long* dbg;       // optional: phase time stamps (clock64) of CTA 0, [role][block][event]
+  int dbg_flags;        // experiments (results become WRONG): 1 = token warps do not wait for the weight-gradient flush
 };
 __device__ __forceinline__ void stamp(const Args& a, int role, int bi, int ev) {
   if (a.dbg && blockIdx.x == 0) a.dbg[(role * MAXB + bi) * 16 + ev] = clock64();
@@ -994,7 +996,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
       const float* pv = par + (n & 1) * BPAR_FLOATS + 24 * g;  // this thread's 24 columns of ln_g | ln_b | ln1_g | ln1_b (stride 96)
       mbar_wait(&bar[BB_PAR + (n & 1)], (n >> 1) & 1);
       // ---- d -> operand planes
-      if (n > 0) wait(BB_DW1_DONE, (n - 1) & 1);               // the previous block's dW1 products read the d planes
+      if (n > 0 && !(a.dbg_flags & 1)) wait(BB_DW1_DONE, (n - 1) & 1);     // the previous block's dW1 products read the d planes
       store24_split(chunk(C_DH), chunk(C_DL), r, 24 * g, d);
       arrive(BB_D);
       if (t0) stamp(a, 0, n, 1);
@@ -1013,7 +1015,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
           xh[c] = live ? (v[c] - mean) * rstd1 : 0.f;
           w[c] = live ? xh[c] * pv[192 + c] + pv[288 + c] : 0.f;
         }
-        if (n > 0) wait(BB_DWQKV_DONE, (n - 1) & 1);           // the previous block's dWqkv products read this area (LN(x), dqkv)
+        if (n > 0 && !(a.dbg_flags & 1)) wait(BB_DWQKV_DONE, (n - 1) & 1);   // the previous block's dWqkv products read this area (LN(x), dqkv)
         store24_split(chunk(C_U1H), chunk(C_U1L), r, 24 * g, w);
         if (g == 0) store_ones_unit(chunk(C_U1H), chunk(C_U1L), r, D, live);
         // db1 += colsum(d)  (fullconnect.py:122) — here, not at the top: the previous block's column sums have left the
@@ -1091,7 +1093,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) vit_tc_bwd_kernel(Args a) {
       // ---- dO (= dh) and q, k, v -> head-padded planes
       {
         if (t0) stamp(a, 0, n, 7);
-        wait(BB_DW0_DONE, ph);                                 // dW1 / dW0 products have read d, G, dpre, LN1(h)
+        if (!(a.dbg_flags & 1)) wait(BB_DW0_DONE, ph);         // dW1 / dW0 products have read d, G, dpre, LN1(h)
         if (t0) stamp(a, 0, n, 8);
         store24_split(chunk(C_DH), chunk(C_DL), r, DHP * g, d);
         {
@@ -1336,6 +1338,7 @@ int nt_vit_tc_bwd(const NtVitBlock* blocks, int nblocks, const float* x, const f
   if (B == 0) return 0;
   a.x = x; a.dout = dout; a.dx = dx;
   a.dbg = vtc::g_dbg;
+  if (const char* e = getenv("NTB200_VTC_DBG")) a.dbg_flags = atoi(e);
   static bool attr = false;
   if (!attr) {
     NT_CHECK(cudaFuncSetAttribute(vtc::vit_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtc::BSMEM_BYTES));

@@ -27,8 +27,11 @@ def enabled():
 
 
 def supported(N, D, H):
-    """True when the fused kernels cover this shape in the current GEMM mode (mode 1 = fp32-class tensor-core path)."""
-    if not enabled() or get_gemm_mode() != 1:
+    """True when the fused kernels cover this shape in the current GEMM mode.  Mode 1 (fp32-class tensor-core path) and
+    mode 2 (single-pass, bar 1e-2): the fused kernels' 3-pass products are MORE accurate than mode 2 asks for and, at these
+    launch-bound shapes, faster than the per-op single-pass path (0.63 vs 0.49 ms per README step), so mode 2 keeps them.
+    Mode 0 (exact fp32 SIMT) does not."""
+    if not enabled() or get_gemm_mode() not in (1, 2):
         return False
     if tc_supported(N, D, H):
         return True
@@ -42,7 +45,7 @@ def tc_supported(N, D, H):
     N <= 64) AND are selected.  They are OPT-IN (NTB200_VIT_TC=1): measured on B200 at B = 100 (tools/vit_tc_time.py,
     DESIGN.md 4.4) the forward is faster than the mma.sync kernels of csrc/vit_block.cu (138 vs 161 us) but the backward is
     slower (310 vs 239 us), so the default stack stays on the older kernels until the backward catches up."""
-    if os.environ.get("NTB200_VIT_TC", "0") != "1" or not enabled() or get_gemm_mode() != 1:
+    if os.environ.get("NTB200_VIT_TC", "0") != "1" or not enabled() or get_gemm_mode() not in (1, 2):
         return False
     ok = ctypes.c_int(0)
     lib.nt_vit_tc_supported(int(N), int(D), int(H), ctypes.byref(ok))
