@@ -437,6 +437,25 @@ def run_ours(args):
                 others[wl] = {"error": "%s: %s" % (type(e).__name__, e)}
         if rank == 0:
             out["other_configs"] = others
+        # throughput per precision mode: mode 1 = error-compensated 3-pass products (fp32-class, bar 1e-4, the
+        # default and what every number above is); mode 2 = single-pass TF32 tcgen05 GEMMs (bar 1e-2).  The fused ViT stack and
+        # the BF16x3 attention kernels stay on in mode 2 (more accurate than it asks for, and faster than the alternatives).
+        if args.gemm_mode is None:
+            per_mode = {}
+            base = {"vit_readme": m["ms_per_step"], **{wl: o.get("ms_per_step") for wl, o in others.items()}}
+            nt.set_gemm_mode(2)
+            for wl in ("vit_readme", "vit_scaled", "gpt_scaled", "gpt_poetry"):
+                try:
+                    r = measure(wl, dp, max(2, min(K, 5)), 3, False, local, args.buckets, min_region_s=0.3)
+                    per_mode[wl] = {"mode1_ms_per_step": base.get(wl), "mode2_ms_per_step": r["ms_per_step"],
+                                    "mode2_value": r["value"], "unit": r["unit"], "mode2_loss": r["loss"],
+                                    "mode2_achieved_tflops": r["step_roofline"]["achieved_tflops"]}
+                except Exception as e:
+                    per_mode[wl] = {"error": "%s: %s" % (type(e).__name__, e)}
+            nt.set_gemm_mode(1)
+            if rank == 0:
+                out["precision_modes"] = {"mode1": "3-pass hi/lo products on tcgen05 / mma.sync, rel <= 1e-4 (default)",
+                                          "mode2": "single-pass TF32 tcgen05 GEMMs, rel <= 1e-2", **per_mode}
     if world == 1 and rank == 0:
         if args.workload == "vit_readme" and not args.no_extra:
             out["e2e_layer_api"] = layer_api_e2e()

@@ -548,7 +548,8 @@ bool attention_bf16_ok(int N, int H, int dh) {
   if (on < 0) { const char* e = getenv("NTB200_ATT_BF16"); on = (e && e[0] == '0') ? 0 : 1; }
   const char* f = getenv("NTB200_ATT_BF16_MIN_N");
   const int min_n = f ? atoi(f) : 16;         // below ~16 tokens the TF32x3 single-block kernels are faster (G0, T = 5: -7 us/step)
-  return on && dh == 64 && N >= min_n && g_gemm_mode == 1;
+  // mode 2 (bar 1e-2) keeps these kernels: their 3-pass products are more accurate than it asks for and faster than TF32x3
+  return on && dh == 64 && N >= min_n && g_gemm_mode >= 1;
 }
 
 int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S, int B, int N, int H,

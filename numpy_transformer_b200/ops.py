@@ -164,7 +164,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, addend=None, want_dx=
 
 def _att_bf16(N, dh):
     import os
-    return (dh == 64 and N >= int(os.environ.get("NTB200_ATT_BF16_MIN_N", "16")) and get_gemm_mode() == 1
+    return (dh == 64 and N >= int(os.environ.get("NTB200_ATT_BF16_MIN_N", "16")) and get_gemm_mode() in (1, 2)
             and os.environ.get("NTB200_ATT_BF16", "1") != "0")
 
 

@@ -308,9 +308,25 @@ class TrainStep:
                         lo = min(offs)
                         self.dp.allreduce_range(self.arena.grads, lo, self.arena.n, side=True)
                         self._early_from = lo
-                delta = fused_vit.backward_stack(runs[ends[i]], delta)
-                if (self.dp is not None and self.dp.world > 1 and self._early_from is not None
-                        and os.environ.get("NTB200_DP_SKIP") != "1"):
+                run = runs[ends[i]]
+                dp_on = (self.dp is not None and self.dp.world > 1 and self._early_from is not None
+                         and os.environ.get("NTB200_DP_SKIP") != "1")
+                kb = int(os.environ.get("NTB200_DP_BWD_SPLIT", "2")) if dp_on and len(run) >= 4 else 0
+                if 0 < kb < len(run):
+                    # data parallel: the stack's backward runs as TWO launches.  The gradients of the later blocks are
+                    # reduced on the comm stream under the launch of the first `kb` blocks (an exchange costs >= 20 us at 8
+                    # GPUs whatever its size — tools/p2p_latency.py — so it has to hide under a launch that long); the
+                    # first blocks' gradients join the stem's in the single exchange that ends the step
+                    delta = fused_vit.backward_stack(run[kb:], delta)
+                    lo = self.arena.first_offset(run[kb])
+                    if lo is not None and lo < self._early_from:
+                        self.dp.allreduce_range(self.arena.grads, lo, self._early_from, side=True)
+                        self._early_from = lo
+                    delta = fused_vit.backward_stack(run[:kb], delta)
+                    i = ends[i] - 1
+                    continue
+                delta = fused_vit.backward_stack(run, delta)
+                if dp_on:
                     # the block gradients are complete: reduce them NOW on the comm stream, under the stem's backward
                     # kernels; only the (tiny) range in front of the blocks is left for the end of the step
                     lo = self.arena.first_offset(layers[ends[i]])
