@@ -688,9 +688,17 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU time the reference arm aims for")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record: anything a library prints to fd 1 meanwhile (NCCL's version banner
+    # ignores NCCL_DEBUG_FILE) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
