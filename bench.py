@@ -132,7 +132,7 @@ def op_cost(name, a, kind, c):
         fwd = L * B * (2.0 * N * 7 * D * D + 4.0 * N * N * D)
         act = 4.0 * L * B * N * (3 * D + H * N + D + 2 * D + D)      # qkv, P, h, dgelu, out
         return (fwd, act) if "fwd" in name else (2.0 * fwd, act)
-    if name in ("nt_attention_fwd", "nt_attention_fwd_split"):
+    if name in ("nt_attention_fwd", "nt_attention_fwd_split", "nt_attention_fwd_planes"):
         # ints: (mask_kind, B, N, H, dh)
         B, N, H, dh = a[1:5]
         return 4.0 * B * H * N * N * dh, 4.0 * (4 * B * N * H * dh + B * H * N * N)

@@ -175,6 +175,12 @@ int nt_attention_fwd_split(const float* qkv, const float* mask, int mask_kind, f
                            int B, int N, int H, int dh, const float* residual, void* out_hi, void* out_lo);
 int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch,
                            int B, int N, int H, int dh, int mask_kind, void* dqkv_hi, void* dqkv_lo, const float* att_out);
+/* attention.py:31-46 / gpt/attdecoderblock.py:52-69 on the tcgen05 kernel (dh == 64, 64 < N <= 256, no dense mask) with
+ * qkv ALSO given as row-major bf16 hi / lo planes [B*N][3*H*dh] (what nt_linear_fwd_bf16x3 writes for the QKV Linear):
+ * q, k, v tiles reach shared memory by TMA in tensor-core operand layout.  *taken = 0 and nothing done if the shape is
+ * not covered (call nt_attention_fwd_split instead). */
+int nt_attention_fwd_planes(const float* qkv, const void* qkv_hi, const void* qkv_lo, int mask_kind, float* out, float* P,
+                            int B, int N, int H, int dh, const float* residual, void* out_hi, void* out_lo, int* taken);
 
 /* KV-cache decode.  The reference generates by re-running the whole window for every new token
  * (gpt/gpt_predict_poetrythree.py:108-121, gpt/gpt_train_potry3000.py:300-342); while the window is still growing the
@@ -244,6 +250,7 @@ int nt_vit_blocks_bwd(const NtVitBlock* blocks, int nblocks, const float* x, con
  * backward recomputes it from q, k), `save` is unused, `wfrag` holds nt_vit_tc_wimg_bytes(D) bytes of weight tiles. */
 int nt_vit_tc_supported(int N, int D, int H, int* ok);
 int nt_vit_tc_wimg_bytes(int D, size_t* bytes);
+int nt_attention_tcl_debug(long long* stamps);   /* development aid: [8][2][16] clock64 phase stamps of CTA 0 of the tcgen05 attention forward (64 < N <= 256), NULL = off */
 int nt_vit_tc_debug(long long* stamps);   /* development aid: [2][16][16] clock64 phase stamps of CTA 0, NULL = off */
 int nt_vit_tc_prepare(const NtVitBlock* blocks, int nblocks, int D, int H);
 int nt_vit_tc_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H, int prepared);

@@ -552,18 +552,25 @@ bool attention_bf16_ok(int N, int H, int dh) {
   return on && dh == 64 && N >= min_n && g_gemm_mode >= 1;
 }
 
+// opt-in to > 48 KB of dynamic shared memory, once (the backward may run without this library's forward having run: the
+// tcgen05 forward of attention_tcl.cu feeds it)
+static int configure() {
+  using namespace ab;
+  static bool cfg = false;
+  if (cfg) return 0;
+  NT_CHECK(cudaFuncSetAttribute(attn_fwd_bf16_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
+  NT_CHECK(cudaFuncSetAttribute(attn_bwd_bf16_q_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwdq_smem<64>()));
+  NT_CHECK(cudaFuncSetAttribute(attn_bwd_bf16_k_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwdk_smem<64>()));
+  NT_CHECK(cudaFuncSetAttribute(attn_fwd_bf16_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
+  NT_CHECK(cudaFuncSetAttribute(attn_bwd_bf16_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwds_smem<64>()));
+  cfg = true;
+  return 0;
+}
+
 int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S, int B, int N, int H,
                        const float* residual, void* o_hi, void* o_lo) {
   using namespace ab;
-  static bool cfg = false;
-  if (!cfg) {
-    NT_CHECK(cudaFuncSetAttribute(attn_fwd_bf16_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
-    NT_CHECK(cudaFuncSetAttribute(attn_bwd_bf16_q_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwdq_smem<64>()));
-    NT_CHECK(cudaFuncSetAttribute(attn_bwd_bf16_k_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwdk_smem<64>()));
-    NT_CHECK(cudaFuncSetAttribute(attn_fwd_bf16_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
-    NT_CHECK(cudaFuncSetAttribute(attn_bwd_bf16_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwds_smem<64>()));
-    cfg = true;
-  }
+  if (configure()) return 1;
   if (N <= LQ) {
     NT_CHECK(launch_k(attn_fwd_bf16_small_kernel<64>, dim3(B * H), dim3(128), fwd_smem<64>(), qkv, mask, mask_kind, out, P, S, N, H,
                       residual, (uint32_t*)o_hi, (uint32_t*)o_lo));
@@ -579,6 +586,7 @@ int attention_fwd_bf16(const float* qkv, const float* mask, int mask_kind, float
 int attention_bwd_bf16(const float* dout, const float* qkv, const float* P, float* dqkv, float* tsum, int B, int N, int H,
                        int causal, void* g_hi, void* g_lo, const float* att_out) {
   using namespace ab;
+  if (configure()) return 1;
   if (N <= LQ) {
     NT_CHECK(launch_k(attn_bwd_bf16_small_kernel<64>, dim3(B * H), dim3(128), bwds_smem<64>(), dout, qkv, P, dqkv, N, H, (uint32_t*)g_hi, (uint32_t*)g_lo));
     NT_LAUNCH_OK();

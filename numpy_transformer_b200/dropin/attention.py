@@ -38,7 +38,8 @@ class attention_layer(LayerArenaMixin):
             return fused_vit.forward_stack([self], x)             # whole block in one launch (csrc/vit_block.cu)
         # split_out: producers whose output feeds a Linear also emit its bf16 hi/lo planes (BF16x3 engine, large shapes)
         self.out = self.norm._forward(x, split_out=True)
-        self.qkv = self.qkvfc._forward(self.out)                       # (B,N,3D): [q,k,v][head][dh]
+        self.qkv = self.qkvfc._forward(self.out, split_out=ops.attention_wants_planes(       # (B,N,3D): [q,k,v][head][dh]
+            self.block, self.embed_dim // self.num_h, self._mask_kind))
         input1, self.P, _ = ops.attention_fwd(self.qkv, self.num_h, dmask, kind, residual=x)
         self.out1 = self.norm1._forward(input1, split_out=True)
         self.out2, self.pre2 = self.fc0._forward(self.out1, ops.ACT_GELU, want_pre=True, split_out=True)

@@ -41,7 +41,9 @@ class attdecoderblock_layer(LayerArenaMixin):
         self.out2, self.pre2 = self.fc0._forward(self.out0, ops.ACT_RELU, want_pre=True, split_out=True)
         self.out6 = self.fc1._forward(self.out2, residual=x)
         self.outnorm = self.norm1._forward(self.out6, split_out=True)
-        self.qkv = self.qkvfc._forward(self.outnorm)
+        # qkv also as bf16 planes when the tcgen05 attention forward will take its operands by TMA
+        self.qkv = self.qkvfc._forward(self.outnorm, split_out=ops.attention_wants_planes(
+            self.block, self.embed_dim // self.num_h, kind, self.return_attention))
         self.rkk, self.P, self.S = ops.attention_fwd(self.qkv, self.num_h, dmask, kind,
                                                      want_scores=self.return_attention, split_out=True)
         input1 = self.fc_out._forward(self.rkk, residual=self.out6)

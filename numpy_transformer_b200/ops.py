@@ -1,5 +1,7 @@
 """Thin functional wrappers: DeviceArray in, DeviceArray out, one C-ABI call each (see include/ntb200.h).
 Nothing here touches the host copy of a tensor, so every function is graph-capturable."""
+import ctypes
+
 import numpy as np
 from ._lib import lib
 from .device import DeviceArray, as_device, ptr_or_null, _prod, get_gemm_mode
@@ -168,12 +170,35 @@ def _att_bf16(N, dh):
             and os.environ.get("NTB200_ATT_BF16", "1") != "0")
 
 
+def attention_wants_planes(N, dh, mask_kind, want_scores=False):
+    """True when attention_fwd would take qkv as bf16 hi / lo planes (the tcgen05 forward for 64 < N <= 256, dh = 64,
+    csrc/attention_tcl.cu): the QKV Linear should then be run with split_out=True.  NTB200_ATT_TCL=0 / NTB200_ATT_PLANES=0
+    switch the kernel / the TMA operand path off."""
+    import os
+    return (dh == 64 and 64 < N <= 256 and mask_kind != MASK_DENSE and not want_scores and get_gemm_mode() in (1, 2)
+            and os.environ.get("NTB200_ATT_TCL", "1") != "0" and os.environ.get("NTB200_ATT_PLANES", "1") != "0")
+
+
 def attention_fwd(qkv, H, mask=None, mask_kind=MASK_NONE, residual=None, want_scores=False, split_out=False):
     B, N, three_d = qkv.shape
     D = three_d // 3
     out = DeviceArray((B, N, D), host_dtype=qkv.host_dtype)
     P = DeviceArray((B, H, N, N), host_dtype=qkv.host_dtype)
     S = P.empty_like() if want_scores else None
+    sp = getattr(qkv, "_split", None)
+    if sp is not None and attention_wants_planes(N, D // H, mask_kind, want_scores):
+        # qkv came with its bf16 planes (QKV Linear with split_out=True): the tcgen05 kernel takes its operands by TMA
+        oh = ol = None
+        if split_out and want_split(B * N, D):
+            oh, ol = new_planes(B * N * D)
+        taken = ctypes.c_int(0)
+        lib.nt_attention_fwd_planes(qkv.ptr, sp[0].ptr, sp[1].ptr, mask_kind, out.ptr, P.ptr, B, N, H, D // H, ptr_or_null(residual),
+                                    ptr_or_null(oh), ptr_or_null(ol), ctypes.byref(taken))
+        if taken.value:
+            qkv._split = None                       # nothing else reads the planes: give the memory back
+            if oh is not None:
+                out._split = (oh, ol)
+            return out, P, S
     if split_out and _att_bf16(N, D // H) and want_split(B * N, D):
         oh, ol = new_planes(B * N * D)
         out._split = (oh, ol)

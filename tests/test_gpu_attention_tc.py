@@ -52,3 +52,51 @@ def test_attention_tc_kernels_vs_oracle():
     assert cp.returncode == 0 and "ATT_TC_OK" in cp.stdout, (cp.stdout + cp.stderr)[-3000:]
     # the kernels really ran: the library reports the engine through its SASS (checked on the CPU side) and the switch
     assert "worst" in cp.stdout
+
+
+def test_attention_tcl_forward_vs_oracle():
+    """The tcgen05 forward for 64 < N <= 256 (csrc/attention_tcl.cu, the default for the GPT shapes): output (+ residual),
+    the probabilities P incl. exact zeros above the causal diagonal, and the bf16 hi / lo planes, against the oracle; ragged
+    N (not a multiple of 128 / 64 / 4), more items than CTAs, and the backward of attention_bf16.cu fed with its P."""
+    import numpy_transformer_b200 as nt
+    from numpy_transformer_b200 import ops
+    from oracle import numpy_ref as R
+    from oracle import models as M
+    from conftest import rel_err
+    nt.init(0)
+    nt.set_gemm_mode(1)
+    assert os.environ.get("NTB200_ATT_TCL", "1") != "0"
+    worst = 0.0
+    for B, N, H, causal in [(2, 256, 2, True), (1, 200, 3, True), (2, 128, 1, False), (3, 192, 2, False), (1, 100, 2, True),
+                            (2, 250, 1, False), (1, 65, 1, True), (40, 256, 6, True)]:
+        rs = np.random.RandomState(B + N)
+        qkv = rs.randn(B, N, 3 * H * 64)
+        res = rs.randn(B, N, H * 64)
+        dout = rs.randn(B, N, H * 64)
+        mask = M.causal_mask(N) if causal else None
+        O, P, _ = R.attention_fwd(qkv, H, mask)
+        kind = ops.MASK_CAUSAL if causal else ops.MASK_NONE
+        qd = nt.as_device(qkv)
+        out, Pd, _ = ops.attention_fwd(qd, H, None, kind, residual=nt.as_device(res), split_out=True)
+        Ph = np.asarray(Pd)
+        e = [rel_err(out, O + res), rel_err(Ph, P)]
+        if causal:
+            assert not np.triu(Ph, 1).any(), "probabilities above the causal diagonal must be exact zeros"
+        sp = getattr(out, "_split", None)
+        if sp is not None:
+            bf = lambda a: (a.numpy().view(np.uint16).astype(np.uint32) << 16).view(np.float32).reshape(-1)[:B * N * H * 64]
+            e.append(rel_err((bf(sp[0]) + bf(sp[1])).reshape(B, N, H * 64), O + res))
+        out2, P2, _ = ops.attention_fwd(qd, H, None, kind)
+        g = ops.attention_bwd(nt.as_device(dout), qd, P2, H, kind, att_out=out2)
+        e.append(rel_err(g, R.attention_bwd(dout, qkv, P, H)))
+        # the TMA operand path: qkv also given as the bf16 planes the QKV Linear's epilogue writes
+        hi, lo, _ = ops.split_bf16(qd, B * N, 3 * H * 64)
+        qd._split = (hi, lo)
+        out3, P3, _ = ops.attention_fwd(qd, H, None, kind, residual=nt.as_device(res), split_out=True)
+        assert qd._split is None, "the planes path was not taken"
+        e += [rel_err(out3, O + res), rel_err(P3, P)]
+        if causal:
+            assert not np.triu(np.asarray(P3), 1).any()
+        worst = max(worst, max(e))
+        assert max(e) < 1e-4, (B, N, H, causal, e)
+    print("attention_tcl worst rel err %.2e" % worst)

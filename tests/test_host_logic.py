@@ -54,9 +54,11 @@ def test_library_is_sm100a_only_and_carries_tcgen05_tma(nt):
         return sum(v[op] for k, v in per_kernel.items() if pattern in k)
     assert total("gemm_tc_kernel", "UTCHMMA") > 0 and total("gemm_tc_kernel", "LDTM") > 0 and total("gemm_tc_kernel", "UTMALDG") > 0
     # the fused ViT stack (the headline kernel) and the dh=64 attention kernels run their contractions on tcgen05
-    for k in ("vit_tc_fwd", "vit_tc_bwd"):
+    for k in ("vit_tc_fwd", "vit_tc_bwd", "attn_tc_kernel", "attn_tcl_fwd_kernel"):
         if any(k in name for name in per_kernel):
             assert total(k, "UTCHMMA") > 0 and total(k, "LDTM") > 0 and total(k, "HMMA") == 0, k
+    # the default attention forward of the GPT shapes takes its operands by TMA
+    assert total("attn_tcl_fwd_kernel", "UTMALDG") > 0
 
 
 def test_reference_tree_is_the_unmodified_reference():
