@@ -39,6 +39,9 @@ struct TcParams {
   int dbg_mma;            // experiment: MMAs issued per k-block (default 4)
   int a_3d, b_3d;         // MN-major operand described by a 3-D map {32, k, chunk}: one TMA per k-block
   int bf16;               // 1: operands are pre-split bf16 hi/lo K-major copies (4 tensor maps), kind::f16, 64 k per stage
+  int wide;               // bf16 only: two MMAs per K = 16 step instead of three — A.hi x [B.hi ; B.lo] as ONE instruction of
+                          // N = 2 BN (the lo tile sits right behind the hi tile, so the pair is one operand) and A.lo x B.hi;
+                          // the accumulator has 2 BN columns, summed by the epilogue
   long long ldc;
   float* C;
   Epilogue ep;
@@ -112,6 +115,12 @@ __device__ __forceinline__ void tc_split2(float a, float b, uint32_t& hi, uint32
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -159,6 +168,10 @@ template <int ACT, int DACT, bool PRE_OUT, bool ATOMIC, bool ADDEND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
+  // the two-MMA product (TcParams::wide) is only compiled into the weight-gradient instance: it needs 2 BN TMEM columns,
+  // which would cut the forward / dX configuration from three co-resident CTAs to two (measured: dW -18 %, forward +15 %),
+  // and its epilogue code pushes the other instances over the 68 registers three CTAs per SM allow
+  const bool wide = ATOMIC && p.wide;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages] x { A hi | B hi | (A lo | B lo) }, then barriers
   // offset arithmetic on the __shared__ array (not on a generic uintptr_t) keeps the address space known,
@@ -185,7 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_end = min(total_kb, kb_begin + p.kblocks_per_split);
   const int nkb = kb_end - kb_begin;       // >= 1 by construction of the grid
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.BN) tmem_cols <<= 1;
+  while ((int)tmem_cols < (wide ? 2 * p.BN : p.BN)) tmem_cols <<= 1;
 
   const uint32_t a_bytes_ = BM * BK * 4;
   // one stage's TMA traffic (lambda so the pre-sync prologue and the steady-state loop share it)
@@ -197,7 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.bf16) {
       // pre-split operands: hi and lo tiles of A and B arrive by TMA (no in-kernel conversion)
       mbar_expect_tx(&full[s], 2 * (a_bytes_ + b_bytes));
-      const uint32_t sal_ = sb + b_bytes, sbl_ = sal_ + a_bytes_;
+      const uint32_t sbl_ = sb + b_bytes, sal_ = sbl_ + b_bytes;          // A.hi | B.hi | B.lo | A.lo
       if (!p.a_mn) {
         tma_load_2d(sa, &tmA, &full[s], k0, m0);                            // box {64 k, 128 m} bf16
         tma_load_2d(sal_, &tmAl, &full[s], k0, m0);
@@ -310,6 +323,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t b_lbo = p.b_mn ? mn_lbo : 16, b_sbo = p.b_mn ? mn_sbo : 1024;
       const uint32_t a_lay = p.a_mn ? mn_lay : LAYOUT_SW128;
       const uint32_t b_lay = p.b_mn ? mn_lay : LAYOUT_SW128;
+      const uint32_t idesc_w = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                               ((uint32_t)((2 * p.BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t accum = 0;
       for (int i = 0; i < nkb; i++) {
         const int s = i % p.stages;
@@ -317,7 +332,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait((p.passes == 3 && !p.bf16) ? &conv[s] : &full[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
-        const uint32_t sal = sb + b_bytes, sbl = sal + a_bytes;
+        // lo tiles: fp32 3-pass keeps A.lo | B.lo behind the hi pair; bf16 puts B.lo right behind B.hi (see TcParams::wide)
+        const uint32_t sbl = p.bf16 ? sb + b_bytes : sb + b_bytes + a_bytes;
+        const uint32_t sal = p.bf16 ? sbl + b_bytes : sb + b_bytes;
 #pragma unroll
         for (int k = 0; k < BK / 8; k++) {
           if (k >= p.dbg_mma && p.dbg_mma < 4) break;
@@ -327,9 +344,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // 16 bf16 per MMA = the same 32-byte advance as 8 fp32: descriptors are identical to the K-major fp32 case
             const uint64_t al = make_smem_desc(sal + k * a_adv, a_lbo, a_sbo, a_lay);
             const uint64_t bl = make_smem_desc(sbl + k * b_adv, b_lbo, b_sbo, b_lay);
-            umma_f16(tmem_base, al, bh, idesc, accum);       // small terms first
-            umma_f16(tmem_base, ah, bl, idesc, 1);
-            umma_f16(tmem_base, ah, bh, idesc, 1);
+            if (wide) {
+              // an M = 128 MMA costs ~130 cycles for its A strip whatever N is (measured in attention_tcl.cu): fewer, wider
+              umma_f16(tmem_base, ah, bh, idesc_w, accum);   // [hi*hi | hi*lo] -> columns [0, BN) and [BN, 2 BN)
+              umma_f16(tmem_base, al, bh, idesc, 1);         // lo*hi -> columns [0, BN)
+            } else {
+              umma_f16(tmem_base, al, bh, idesc, accum);       // small terms first
+              umma_f16(tmem_base, ah, bl, idesc, 1);
+              umma_f16(tmem_base, ah, bh, idesc, 1);
+            }
           } else if (p.passes == 3) {
             const uint64_t al = make_smem_desc(sal + k * a_adv, a_lbo, a_sbo, a_lay);
             const uint64_t bl = make_smem_desc(sbl + k * b_adv, b_lbo, b_sbo, b_lay);
@@ -476,6 +499,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) =
               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                           __uint_as_float(r[4 * j + 3]));
+        if (wide) {
+          // + the hi*lo half of the accumulator, added in the staging tile (same registers: three CTAs share an SM only
+          // below 68 registers per thread)
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + c0), r);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float4 t = *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j);
+            t.x += __uint_as_float(r[4 * j]); t.y += __uint_as_float(r[4 * j + 1]);
+            t.z += __uint_as_float(r[4 * j + 2]); t.w += __uint_as_float(r[4 * j + 3]);
+            *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) = t;
+          }
+        }
       }
       __syncwarp();
       if (vec_ok) {
@@ -703,6 +738,7 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   p.a_mn = a_mn; p.b_mn = b_mn;
   p.passes = passes;
   p.bf16 = bf ? 1 : 0;
+  p.wide = 0;
   if (bf && b_mn && (p.BN % 64)) p.BN = d.N > 64 ? 128 : 64;       // MN-major bf16 tiles come in 64-wide chunks
   p.ldc = d.ldc;
   p.C = d.C;
@@ -710,6 +746,8 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   { const char* e = getenv("NTB200_DBG_MMA"); p.dbg_mma = e ? atoi(e) : 4; }
   { const char* e = getenv("NTB200_DBG_SKIP_A"); p.dbg_skip_a = (e && e[0] == '1') ? 1 : 0; }
   if (const char* e = getenv("NTB200_BN")) { int v = atoi(e); if (v == 32 || v == 64 || v == 96 || v == 128 || (bf && v == 256 && d.N >= 256)) p.BN = v; }
+  { static int w = -1; if (w < 0) { const char* e = getenv("NTB200_GEMM_WIDE"); w = (e && e[0] == '0') ? 0 : 1; }
+    p.wide = (bf && w && d.ep.atomic && 2 * p.BN <= 256) ? 1 : 0; }
   const int total_kb = ceil_div(d.K, bf ? 2 * BK : BK);
   int splits = 1;
   if (d.splitk > 1) {
