@@ -136,7 +136,7 @@ def op_cost(name, a, kind, c):
         # ints: (mask_kind, B, N, H, dh)
         B, N, H, dh = a[1:5]
         return 4.0 * B * H * N * N * dh, 4.0 * (4 * B * N * H * dh + B * H * N * N)
-    if name in ("nt_attention_bwd", "nt_attention_bwd_split"):
+    if name in ("nt_attention_bwd", "nt_attention_bwd_split", "nt_attention_bwd_planes"):
         # ints: (B, N, H, dh, mask_kind)
         B, N, H, dh = a[0:4]
         return 8.0 * B * H * N * N * dh, 4.0 * (7 * B * N * H * dh + B * H * N * N)

@@ -177,10 +177,18 @@ int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, 
                            int B, int N, int H, int dh, int mask_kind, void* dqkv_hi, void* dqkv_lo, const float* att_out);
 /* attention.py:31-46 / gpt/attdecoderblock.py:52-69 on the tcgen05 kernel (dh == 64, 64 < N <= 256, no dense mask) with
  * qkv ALSO given as row-major bf16 hi / lo planes [B*N][3*H*dh] (what nt_linear_fwd_bf16x3 writes for the QKV Linear):
- * q, k, v tiles reach shared memory by TMA in tensor-core operand layout.  *taken = 0 and nothing done if the shape is
- * not covered (call nt_attention_fwd_split instead). */
+ * q, k, v tiles reach shared memory by TMA in tensor-core operand layout.  lse (may be NULL): [B,H,N] row log-sum-exp
+ * in the log2 domain, for nt_attention_bwd_planes.  *taken = 0 and nothing done if the shape is not covered (call
+ * nt_attention_fwd_split instead). */
 int nt_attention_fwd_planes(const float* qkv, const void* qkv_hi, const void* qkv_lo, int mask_kind, float* out, float* P,
-                            int B, int N, int H, int dh, const float* residual, void* out_hi, void* out_lo, int* taken);
+                            int B, int N, int H, int dh, const float* residual, void* out_hi, void* out_lo, float* lse, int* taken);
+/* attention.py:63-84 / gpt/attdecoderblock.py:79-99 on tcgen05 for the same shapes: dout and qkv as bf16 hi / lo planes
+ * (TMA operands), att_out = the forward's output WITHOUT a residual (row sums of dP o P = dout . att_out), lse [B,H,N] =
+ * the row log-sum-exp the forward wrote (the probabilities are recomputed from q and k, P is not read).  Writes dqkv (+ its
+ * planes when given).  *taken = 0 and nothing done if the shape is not covered. */
+int nt_attention_bwd_planes(const float* dout, const void* dout_hi, const void* dout_lo, const void* qkv_hi, const void* qkv_lo,
+                            const float* att_out, const float* lse, float* dqkv, void* dqkv_hi, void* dqkv_lo,
+                            int B, int N, int H, int dh, int mask_kind, int* taken);
 
 /* KV-cache decode.  The reference generates by re-running the whole window for every new token
  * (gpt/gpt_predict_poetrythree.py:108-121, gpt/gpt_train_potry3000.py:300-342); while the window is still growing the

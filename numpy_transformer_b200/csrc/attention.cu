@@ -11,7 +11,10 @@ bool attention_bf16_ok(int N, int H, int dh);
 bool attention_tc_ok(int N, int H, int dh, int mask_kind, bool want_scores);
 bool attention_tcl_ok(int N, int H, int dh, int mask_kind, bool want_scores);
 int attention_fwd_tcl(const float* qkv, const void* qkv_hi, const void* qkv_lo, int mask_kind, float* out, float* P, int B, int N,
-                      int H, const float* residual, void* o_hi, void* o_lo);
+                      int H, const float* residual, void* o_hi, void* o_lo, float* lse);
+bool attention_bwd_tcl_ok(int N, int H, int dh, int mask_kind);
+int attention_bwd_tcl(const float* dout, const void* dout_hi, const void* dout_lo, const void* qkv_hi, const void* qkv_lo,
+                      const float* att_out, const float* lse, float* dqkv, void* g_hi, void* g_lo, int B, int N, int H, int causal);
 int attention_fwd_tc(const float* qkv, int mask_kind, float* out, float* P, int B, int N, int H, const float* residual, void* o_hi,
                      void* o_lo);
 int attention_bwd_tc(const float* dout, const float* qkv, float* dqkv, int B, int N, int H, int causal, void* g_hi, void* g_lo);
@@ -1184,7 +1187,7 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
   if (B == 0) return 0;
   const int D = H * dh;
   if (nt::attention_tc_ok(N, H, dh, mask_kind, S != nullptr)) return nt::attention_fwd_tc(qkv, mask_kind, out, P, B, N, H, residual, nullptr, nullptr);
-  if (nt::attention_tcl_ok(N, H, dh, mask_kind, S != nullptr)) return nt::attention_fwd_tcl(qkv, nullptr, nullptr, mask_kind, out, P, B, N, H, residual, nullptr, nullptr);
+  if (nt::attention_tcl_ok(N, H, dh, mask_kind, S != nullptr)) return nt::attention_fwd_tcl(qkv, nullptr, nullptr, mask_kind, out, P, B, N, H, residual, nullptr, nullptr, nullptr);
   if (nt::attention_bf16_ok(N, H, dh)) return nt::attention_fwd_bf16(qkv, mask, mask_kind, out, P, S, B, N, H, residual, nullptr, nullptr);
   if (const char* e = getenv("NTB200_ATT_MMA")) g_att_mma = (e[0] != '0');
   if (mma_ok(N, dh)) {
@@ -1370,12 +1373,12 @@ int nt_attention_fwd_split(const float* qkv, const float* mask, int mask_kind, f
   NT_REQUIRE((out_hi != nullptr) == (out_lo != nullptr), "nt_attention_fwd_split: pass both split planes or neither");
   if (B == 0) return 0;
   if (nt::attention_tc_ok(N, H, dh, mask_kind, S != nullptr)) return nt::attention_fwd_tc(qkv, mask_kind, out, P, B, N, H, residual, out_hi, out_lo);
-  if (nt::attention_tcl_ok(N, H, dh, mask_kind, S != nullptr)) return nt::attention_fwd_tcl(qkv, nullptr, nullptr, mask_kind, out, P, B, N, H, residual, out_hi, out_lo);
+  if (nt::attention_tcl_ok(N, H, dh, mask_kind, S != nullptr)) return nt::attention_fwd_tcl(qkv, nullptr, nullptr, mask_kind, out, P, B, N, H, residual, out_hi, out_lo, nullptr);
   return nt::attention_fwd_bf16(qkv, mask, mask_kind, out, P, S, B, N, H, residual, out_hi, out_lo);
 }
 
 int nt_attention_fwd_planes(const float* qkv, const void* qkv_hi, const void* qkv_lo, int mask_kind, float* out, float* P, int B,
-                            int N, int H, int dh, const float* residual, void* out_hi, void* out_lo, int* taken) {
+                            int N, int H, int dh, const float* residual, void* out_hi, void* out_lo, float* lse, int* taken) {
   NT_ENTRY();
   NT_REQUIRE(B >= 0 && N > 0 && H > 0 && dh > 0 && taken, "nt_attention_fwd_planes: bad shape");
   NT_REQUIRE(qkv_hi && qkv_lo, "nt_attention_fwd_planes: needs both planes of qkv");
@@ -1384,7 +1387,22 @@ int nt_attention_fwd_planes(const float* qkv, const void* qkv_hi, const void* qk
   if (!nt::attention_tcl_ok(N, H, dh, mask_kind, false)) return 0;
   *taken = 1;
   if (B == 0) return 0;
-  return nt::attention_fwd_tcl(qkv, qkv_hi, qkv_lo, mask_kind, out, P, B, N, H, residual, out_hi, out_lo);
+  return nt::attention_fwd_tcl(qkv, qkv_hi, qkv_lo, mask_kind, out, P, B, N, H, residual, out_hi, out_lo, lse);
+}
+
+int nt_attention_bwd_planes(const float* dout, const void* dout_hi, const void* dout_lo, const void* qkv_hi, const void* qkv_lo,
+                            const float* att_out, const float* lse, float* dqkv, void* dqkv_hi, void* dqkv_lo, int B, int N, int H,
+                            int dh, int mask_kind, int* taken) {
+  NT_ENTRY();
+  NT_REQUIRE(B >= 0 && N > 0 && H > 0 && dh > 0 && taken, "nt_attention_bwd_planes: bad shape");
+  NT_REQUIRE(dout && dout_hi && dout_lo && qkv_hi && qkv_lo && att_out && lse && dqkv, "nt_attention_bwd_planes: missing operand");
+  NT_REQUIRE((dqkv_hi != nullptr) == (dqkv_lo != nullptr), "nt_attention_bwd_planes: pass both split planes or neither");
+  *taken = 0;
+  if (!nt::attention_bwd_tcl_ok(N, H, dh, mask_kind)) return 0;
+  *taken = 1;
+  if (B == 0) return 0;
+  return nt::attention_bwd_tcl(dout, dout_hi, dout_lo, qkv_hi, qkv_lo, att_out, lse, dqkv, dqkv_hi, dqkv_lo, B, N, H,
+                               mask_kind == NT_MASK_CAUSAL ? 1 : 0);
 }
 
 int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch, int B, int N,

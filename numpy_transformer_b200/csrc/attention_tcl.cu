@@ -49,6 +49,8 @@ struct Args {
   const float* residual; // [B,N,H*64] or null
   uint32_t* o_hi;        // bf16 pairs of `out` (row-major) or null
   uint32_t* o_lo;
+  float* lse;            // [B,H,N] or null: log2-domain log-sum-exp of every score row, max * c + log2(sum), c = log2(e) / sqrt(dh)
+                         // (what the tcgen05 backward needs to recompute P: P_ij = 2^(s_ij c - lse_i))
   int B, N, H, causal;
   int planes;            // q, k, v arrive by TMA from the bf16 planes of qkv (tensor maps in the kernel parameters)
   long long* dbg;        // optional phase time stamps of CTA 0: [item < 8][warp 0 / warp 15][16 events]
@@ -293,6 +295,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tcl_fwd_kernel(Args a, const 
       named_bar_sync(1 + q, 128);
       sum = (xr[0].y + xr[1].y) + (xr[2].y + xr[3].y);
       const float inv = (live && sum > 0.f) ? __fdividef(1.0f, sum) : 0.f;
+      if (a.lse && cg == 0 && live) a.lse[(long long)bh * N + grow] = mc + log2f(sum);
       stamp(a, n, 6);
 #pragma unroll
       for (int j8 = 0; j8 < 8; j8++)
@@ -411,6 +414,278 @@ static bool enabled() {
 }
 }  // namespace atl
 
+
+// ================================================================================================ backward
+// attention.py:63-84 / gpt/attdecoderblock.py:79-99 for the same shapes.  One work item = (sample, head); the CTA walks
+// the (key block kb, query tile qt) pairs of 128 x 128, key blocks from the last to the first, and per pair
+//     S  = Q_t K_b^T,  dP = dO_t V_b^T                        (K-major operands, N = 128)
+//     P  = 2^(S c - lse)  (recomputed: the forward's row log-sum-exp instead of the B*H*T*T matrix),  dS = P o (dP - delta) / sqrt(dh)
+//     dV_b += P^T dO_t                                         (P and dO as MN-major operands: nothing is transposed)
+//     dQ_t += dS K_b,  dK_b += dS^T Q_t                        (dS takes P's planes once dV has consumed them)
+// with delta_i = dO_i . O_i (the softmax-backward row sum, attention.py:75).  q, k, v and dO arrive by TMA from bf16 hi / lo
+// planes; all accumulators live in TMEM: S 128 + dP 128 + dK 64 + dV 64 + dQ 2 x 64 = 512 columns.
+namespace atb {
+using namespace um;
+using atl::tma_load_3d;
+using atl::ex2;
+
+constexpr int DH = 64, BM = 128;
+constexpr uint32_t PCH = BM * 128;
+constexpr int TOK_WARPS = 16, THREADS = 32 * TOK_WARPS;
+constexpr uint32_t OFF_Q_HI = 0, OFF_Q_LO = PCH, OFF_D_HI = 2 * PCH, OFF_D_LO = 3 * PCH, OFF_K_HI = 4 * PCH, OFF_K_LO = 5 * PCH,
+                   OFF_V_HI = 6 * PCH, OFF_V_LO = 7 * PCH;
+constexpr uint32_t OFF_PS_HI = 8 * PCH, OFF_PS_LO = 10 * PCH;      // P, then dS: [128 q][128 keys] = two chunks per plane
+constexpr uint32_t OFF_STG = OFF_PS_HI;                            // fp32 [128][64] staging tile of the output epilogues
+constexpr uint32_t OFF_DELTA = 12 * PCH, OFF_LSE = OFF_DELTA + BM * 4, OFF_BAR = OFF_LSE + BM * 4;
+enum { B_QD = 0, B_KV, B_SDP, B_P, B_DV, B_DS, B_DQK, B_COUNT };
+constexpr uint32_t SMEM = OFF_BAR + B_COUNT * 8 + 16;
+static_assert(SMEM <= 232448, "shared memory budget");
+constexpr uint32_t T_S = 0, T_DP = 128, T_DK = 256, T_DV = 320, T_DQ = 384;
+
+struct Args {
+  const float* dout;     // [B,N,H*64]
+  const float* att_out;  // [B,N,H*64]  forward output without a residual
+  const float* lse;      // [B,H,N]
+  float* dqkv;           // [B,N,3*H*64]
+  uint32_t* g_hi;        // bf16 pairs of dqkv or null
+  uint32_t* g_lo;
+  int B, N, H, causal;
+};
+
+// D (+)= A B in three passes; operands given as descriptors of the first K = 16 step and the per-step advance in 16-byte units
+__device__ __forceinline__ void mma3x(uint32_t tacc, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t a_step, uint32_t b_step,
+                                      int ksteps, uint32_t idesc, bool fresh) {
+#pragma unroll 4
+  for (int ks = 0; ks < ksteps; ks++) {
+    const uint64_t ao = (uint64_t)(ks * a_step), bo = (uint64_t)(ks * b_step);
+    mma_bf16(tacc, al + ao, bh + bo, idesc, (fresh && ks == 0) ? 0u : 1u);
+    mma_bf16(tacc, ah + ao, bl + bo, idesc, 1u);
+    mma_bf16(tacc, ah + ao, bh + bo, idesc, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) attn_tcl_bwd_kernel(Args a, const __grid_constant__ CUtensorMap tq_hi,
+                                                                  const __grid_constant__ CUtensorMap tq_lo,
+                                                                  const __grid_constant__ CUtensorMap td_hi,
+                                                                  const __grid_constant__ CUtensorMap td_lo) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023u) __trap();
+  float* delta_s = reinterpret_cast<float*>(smem + OFF_DELTA);
+  float* lse_s = reinterpret_cast<float*>(smem + OFF_LSE);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
+
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.N, H = a.H, D = H * DH;
+  const int QT = (N + BM - 1) / BM, KT = QT, BH = a.B * H;
+  if (tid == 0) {
+    for (int i = 0; i < B_COUNT; i++) mbar_init(&bar[i], 1);
+    mbar_init(&bar[B_P], TOK_WARPS);
+    mbar_init(&bar[B_DS], TOK_WARPS);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tslot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tslot;
+  pdl_wait();
+
+  const uint32_t sb = smem_u32(smem);
+  const int q = warp & 3, cg = warp >> 2, r = 32 * q + lane;          // thread = (row of the tile = TMEM lane, column group)
+  const uint32_t lane_addr = tbase + ((uint32_t)(32 * q) << 16);
+  const float scale = rsqrtf((float)DH), c = scale * 1.4426950408889634f;
+  auto arrive = [&](int b) {
+    tc_fence_before();
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar[b]);
+  };
+  // [128][64] accumulator at TMEM column tcol -> dqkv rows row0.., part 0 (dq) / 1 (dk) / 2 (dv) of head h (+ bf16 planes).
+  // Accumulator layout (row per thread) -> swizzled fp32 staging tile -> 256-byte row segments, 16 lanes per row.
+  auto store_tile = [&](uint32_t tcol, int part, int row0, int b, int h) {
+    uint32_t o[16];
+    tmem_ld16(lane_addr + tcol + 16 * cg, o);
+    tmem_wait_ld();
+    uint8_t* stg = smem + OFF_STG;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      *reinterpret_cast<uint4*>(stg + r * 256 + (((4 * cg + j) ^ (r & 15)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    named_bar_sync(1 + q, 128);
+    const int gt = cg * 32 + lane, unit = gt & 15;
+#pragma unroll 1
+    for (int ps = 0; ps < 4; ps++) {
+      const int rl = 32 * q + (gt >> 4) + 8 * ps, g = row0 + rl;
+      if (g < N) {
+        const float4 w = *reinterpret_cast<const float4*>(stg + rl * 256 + ((unit ^ (rl & 15)) << 4));
+        const long long oi = ((long long)b * N + g) * 3 * D + part * D + h * DH + 4 * unit;
+        *reinterpret_cast<float4*>(a.dqkv + oi) = w;
+        if (a.g_hi) {
+          uint2 hh, ll;
+          split2(w.x, w.y, hh.x, ll.x);
+          split2(w.z, w.w, hh.y, ll.y);
+          *reinterpret_cast<uint2*>(a.g_hi + (oi >> 1)) = hh;
+          *reinterpret_cast<uint2*>(a.g_lo + (oi >> 1)) = ll;
+        }
+      }
+    }
+    named_bar_sync(1 + q, 128);                     // the tile is rewritten by the next store_tile / the next pair's planes
+  };
+
+  uint32_t ph_qd = 0, ph_kv = 0, pp = 0;            // barrier phases (every thread keeps the same counters)
+  for (int item = blockIdx.x; item < BH; item += gridDim.x) {
+    const int b = item / H, h = item % H;
+    int cur_qt = -1;
+    for (int kb = KT - 1; kb >= 0; kb--) {
+      if (tid == 0) {                               // k, v of this key block (everything that read the old ones has retired)
+        fence_async_smem();
+        mbar_expect_tx(&bar[B_KV], 4u * PCH);
+        tma_load_3d(sb + OFF_K_HI, &tq_hi, &bar[B_KV], D + h * DH, kb * BM, b);
+        tma_load_3d(sb + OFF_K_LO, &tq_lo, &bar[B_KV], D + h * DH, kb * BM, b);
+        tma_load_3d(sb + OFF_V_HI, &tq_hi, &bar[B_KV], 2 * D + h * DH, kb * BM, b);
+        tma_load_3d(sb + OFF_V_LO, &tq_lo, &bar[B_KV], 2 * D + h * DH, kb * BM, b);
+      }
+      const int qt_lo = a.causal ? kb : 0;
+      for (int qt = QT - 1; qt >= qt_lo; qt--) {
+        const bool first_k = (qt == QT - 1);                         // first pair of this key block: dK, dV start from zero
+        const bool first_q = (kb == (a.causal ? qt : KT - 1));       // first pair of this query tile: dQ starts from zero
+        const bool new_q = (qt != cur_qt);
+        if (new_q) {
+          cur_qt = qt;
+          if (tid == 0) {
+            fence_async_smem();
+            mbar_expect_tx(&bar[B_QD], 4u * PCH);
+            tma_load_3d(sb + OFF_Q_HI, &tq_hi, &bar[B_QD], h * DH, qt * BM, b);
+            tma_load_3d(sb + OFF_Q_LO, &tq_lo, &bar[B_QD], h * DH, qt * BM, b);
+            tma_load_3d(sb + OFF_D_HI, &td_hi, &bar[B_QD], h * DH, qt * BM, b);
+            tma_load_3d(sb + OFF_D_LO, &td_lo, &bar[B_QD], h * DH, qt * BM, b);
+          }
+          // delta_i = dO_i . O_i and the row log-sum-exp of the tile: 4 lanes per row, 256 contiguous bytes
+          {
+            const int row = tid >> 2, qq = tid & 3, g = qt * BM + row;
+            float acc = 0.f;
+            if (g < N) {
+              const long long oi = ((long long)b * N + g) * D + h * DH + 16 * qq;
+              const float4* pd = reinterpret_cast<const float4*>(a.dout + oi);
+              const float4* po = reinterpret_cast<const float4*>(a.att_out + oi);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const float4 x = __ldg(pd + j), y = __ldg(po + j);
+                acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+              }
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (qq == 0) delta_s[row] = acc;
+            if (tid < BM) lse_s[tid] = (qt * BM + tid < N) ? __ldg(a.lse + (long long)item * N + qt * BM + tid) : 0.f;
+            named_bar_sync(5, THREADS);
+          }
+        }
+        // ---- S = Q K^T, dP = dO V^T
+        if (tid == 0) {
+          if (new_q) { mbar_wait(&bar[B_QD], ph_qd); }
+          if (first_k) { mbar_wait(&bar[B_KV], ph_kv); }
+          tc_fence_after();
+          const uint32_t id = idesc_bf16(128, 128, 0, 0);
+          mma3x(tbase + T_S, desc_kmajor(sb + OFF_Q_HI), desc_kmajor(sb + OFF_Q_LO), desc_kmajor(sb + OFF_K_HI), desc_kmajor(sb + OFF_K_LO),
+                KMAJ_STEP >> 4, KMAJ_STEP >> 4, 4, id, true);
+          mma3x(tbase + T_DP, desc_kmajor(sb + OFF_D_HI), desc_kmajor(sb + OFF_D_LO), desc_kmajor(sb + OFF_V_HI), desc_kmajor(sb + OFF_V_LO),
+                KMAJ_STEP >> 4, KMAJ_STEP >> 4, 4, id, true);
+          mma_commit(&bar[B_SDP]);
+        }
+        __syncwarp();
+        if (new_q) ph_qd ^= 1;
+        if (first_k) ph_kv ^= 1;
+        // ---- P and dS of this thread's 32 key columns
+        uint32_t pv[32], dv[32];
+        mbar_wait(&bar[B_SDP], pp);
+        tc_fence_after();
+        tmem_ld32(lane_addr + T_S + 32 * cg, pv);
+        tmem_ld32(lane_addr + T_DP + 32 * cg, dv);
+        tmem_wait_ld();
+        {
+          const int g = qt * BM + r, cb = kb * BM + 32 * cg;
+          const bool live = g < N;
+          const float ls = lse_s[r], dl = delta_s[r];
+          const bool edge = (cb + 31 >= N) || (a.causal && cb + 31 > qt * BM + 32 * q);
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            bool ok = live;
+            if (edge) ok = ok && (cb + j < N) && !(a.causal && cb + j > g);
+            const float p = ok ? ex2(fmaf(__uint_as_float(pv[j]), c, -ls)) : 0.f;
+            pv[j] = __float_as_uint(p);
+            dv[j] = __float_as_uint(p * (__uint_as_float(dv[j]) - dl) * scale);
+          }
+        }
+#pragma unroll
+        for (int j8 = 0; j8 < 4; j8++) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] = __uint_as_float(pv[8 * j8 + i]);
+          store8_split(smem + OFF_PS_HI, smem + OFF_PS_LO, r, 32 * cg + 8 * j8, PCH, v);
+        }
+        arrive(B_P);
+        // ---- dV += P^T dO
+        if (tid == 0) {
+          mbar_wait(&bar[B_P], pp);
+          tc_fence_after();
+          mma3x(tbase + T_DV, desc_mnmajor(sb + OFF_PS_HI, PCH), desc_mnmajor(sb + OFF_PS_LO, PCH), desc_mnmajor(sb + OFF_D_HI, 8192),
+                desc_mnmajor(sb + OFF_D_LO, 8192), MNMAJ_STEP >> 4, MNMAJ_STEP >> 4, 8, idesc_bf16(128, 64, 1, 1), first_k);
+          mma_commit(&bar[B_DV]);
+        }
+        __syncwarp();
+        mbar_wait(&bar[B_DV], pp);                   // the tensor core has consumed P: its planes take dS
+        tc_fence_after();
+#pragma unroll
+        for (int j8 = 0; j8 < 4; j8++) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] = __uint_as_float(dv[8 * j8 + i]);
+          store8_split(smem + OFF_PS_HI, smem + OFF_PS_LO, r, 32 * cg + 8 * j8, PCH, v);
+        }
+        arrive(B_DS);
+        // ---- dQ += dS K, dK += dS^T Q
+        if (tid == 0) {
+          mbar_wait(&bar[B_DS], pp);
+          tc_fence_after();
+          // dS as a K-major A operand: K = 16 step ks lives in chunk ks / 4 at 32 (ks % 4) bytes
+          const uint64_t ah0 = desc_kmajor(sb + OFF_PS_HI), al0 = desc_kmajor(sb + OFF_PS_LO);
+          const uint64_t bh0 = desc_mnmajor(sb + OFF_K_HI, 8192), bl0 = desc_mnmajor(sb + OFF_K_LO, 8192);
+          const uint32_t idq = idesc_bf16(128, 64, 0, 1);
+#pragma unroll 4
+          for (int ks = 0; ks < 8; ks++) {
+            const uint64_t pa = (uint64_t)((ks >> 2) * (PCH >> 4) + (ks & 3) * (KMAJ_STEP >> 4)), pb = (uint64_t)(ks * (MNMAJ_STEP >> 4));
+            mma_bf16(tbase + T_DQ + 64 * qt, al0 + pa, bh0 + pb, idq, (first_q && ks == 0) ? 0u : 1u);
+            mma_bf16(tbase + T_DQ + 64 * qt, ah0 + pa, bl0 + pb, idq, 1u);
+            mma_bf16(tbase + T_DQ + 64 * qt, ah0 + pa, bh0 + pb, idq, 1u);
+          }
+          mma3x(tbase + T_DK, desc_mnmajor(sb + OFF_PS_HI, PCH), desc_mnmajor(sb + OFF_PS_LO, PCH), desc_mnmajor(sb + OFF_Q_HI, 8192),
+                desc_mnmajor(sb + OFF_Q_LO, 8192), MNMAJ_STEP >> 4, MNMAJ_STEP >> 4, 8, idesc_bf16(128, 64, 1, 1), first_k);
+          mma_commit(&bar[B_DQK]);
+        }
+        __syncwarp();
+        mbar_wait(&bar[B_DQK], pp);
+        tc_fence_after();
+        pp ^= 1;
+      }
+      // ---- dK, dV of this key block are complete
+      store_tile(T_DK, 1, kb * BM, b, h);
+      store_tile(T_DV, 2, kb * BM, b, h);
+      named_bar_sync(5, THREADS);                    // staging tile = P / dS planes of the next pair
+    }
+    for (int qt = 0; qt < QT; qt++) store_tile(T_DQ + 64 * qt, 0, qt * BM, b, h);
+    named_bar_sync(5, THREADS);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tbase);
+  }
+}
+}  // namespace atb
+
 bool attention_tcl_ok(int N, int H, int dh, int mask_kind, bool want_scores) {
   return atl::enabled() && dh == 64 && N > 64 && N <= atl::MAXK && H >= 1 && mask_kind != NT_MASK_DENSE && !want_scores &&
          g_gemm_mode >= 1;
@@ -442,7 +717,7 @@ static int plane_map(CUtensorMap* tm, const void* base, int B, int N, int D3) {
 }
 
 int attention_fwd_tcl(const float* qkv, const void* qkv_hi, const void* qkv_lo, int mask_kind, float* out, float* P, int B, int N,
-                      int H, const float* residual, void* o_hi, void* o_lo) {
+                      int H, const float* residual, void* o_hi, void* o_lo, float* lse) {
   static bool cfg = false;
   if (!cfg) {
     NT_CHECK(cudaFuncSetAttribute(atl::attn_tcl_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atl::SMEM));
@@ -453,6 +728,7 @@ int attention_fwd_tcl(const float* qkv, const void* qkv_hi, const void* qkv_lo, 
   a.qkv = qkv; a.out = out; a.P = P; a.residual = residual; a.o_hi = (uint32_t*)o_hi; a.o_lo = (uint32_t*)o_lo;
   a.B = B; a.N = N; a.H = H; a.causal = mask_kind == NT_MASK_CAUSAL ? 1 : 0;
   a.dbg = atl::g_dbg;
+  a.lse = lse;
   CUtensorMap tm_hi, tm_lo;
   memset(&tm_hi, 0, sizeof(tm_hi));
   memset(&tm_lo, 0, sizeof(tm_lo));
@@ -462,6 +738,37 @@ int attention_fwd_tcl(const float* qkv, const void* qkv_hi, const void* qkv_lo, 
   const int grid = items < g_sm_count ? items : g_sm_count;
   if (a.planes) NT_CHECK(launch_k(atl::attn_tcl_fwd_kernel<true>, dim3(grid), dim3(atl::THREADS), atl::SMEM, a, tm_hi, tm_lo));
   else NT_CHECK(launch_k(atl::attn_tcl_fwd_kernel<false>, dim3(grid), dim3(atl::THREADS), atl::SMEM, a, tm_hi, tm_lo));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
+
+// NTB200_ATT_TCL_BWD=0 keeps the mma.sync backward.
+bool attention_bwd_tcl_ok(int N, int H, int dh, int mask_kind) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("NTB200_ATT_TCL_BWD"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on && atl::enabled() && dh == 64 && N > 64 && N <= atl::MAXK && H >= 1 && mask_kind != NT_MASK_DENSE && g_gemm_mode >= 1;
+}
+
+int attention_bwd_tcl(const float* dout, const void* dout_hi, const void* dout_lo, const void* qkv_hi, const void* qkv_lo,
+                      const float* att_out, const float* lse, float* dqkv, void* g_hi, void* g_lo, int B, int N, int H, int causal) {
+  static bool cfg = false;
+  if (!cfg) {
+    NT_CHECK(cudaFuncSetAttribute(atb::attn_tcl_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atb::SMEM));
+    cfg = true;
+  }
+  NT_REQUIRE(!((uintptr_t)dout_hi & 15) && !((uintptr_t)dout_lo & 15) && !((uintptr_t)qkv_hi & 15) && !((uintptr_t)qkv_lo & 15),
+             "attention_bwd_tcl: planes must be 16-byte aligned");
+  atb::Args a{};
+  a.dout = dout; a.att_out = att_out; a.lse = lse; a.dqkv = dqkv; a.g_hi = (uint32_t*)g_hi; a.g_lo = (uint32_t*)g_lo;
+  a.B = B; a.N = N; a.H = H; a.causal = causal;
+  CUtensorMap tq_hi, tq_lo, td_hi, td_lo;
+  if (plane_map(&tq_hi, qkv_hi, B, N, 3 * H * atb::DH) || plane_map(&tq_lo, qkv_lo, B, N, 3 * H * atb::DH) ||
+      plane_map(&td_hi, dout_hi, B, N, H * atb::DH) || plane_map(&td_lo, dout_lo, B, N, H * atb::DH))
+    return 1;
+  const int items = B * H;
+  const int grid = items < g_sm_count ? items : g_sm_count;
+  NT_CHECK(launch_k(atb::attn_tcl_bwd_kernel, dim3(grid), dim3(atb::THREADS), atb::SMEM, a, tq_hi, tq_lo, td_hi, td_lo));
   NT_LAUNCH_OK();
   return 0;
 }

@@ -53,7 +53,8 @@ class attdecoderblock_layer(LayerArenaMixin):
 
     def backward(self, delta):
         delta = as_device(delta, self.norm.host_dtype)
-        delta0 = self.fc_out._backward(delta, self.rkk)
+        # the gradient of the attention output also as bf16 planes when the tcgen05 attention backward will take it by TMA
+        delta0 = self.fc_out._backward(delta, self.rkk, split_out=getattr(self.P, "_lse", None) is not None)
         self.delta_qkv = ops.attention_bwd(delta0, self.qkv, self.P, self.num_h, self._mask_kind, split_out=True,
                                            att_out=self.rkk)
         d = self.qkvfc._backward(self.delta_qkv, self.outnorm)

@@ -9,6 +9,7 @@ from .device import DeviceArray, as_device, ptr_or_null, _prod, get_gemm_mode
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 MASK_NONE, MASK_CAUSAL, MASK_DENSE = 0, 1, 2
 LN_EPS = 1e-5        # net/layernorm.py:86
+_last = {}           # which engine the last call of an op took (tests assert on it)
 
 
 def bf16x3_ok(M, K, N):
@@ -192,10 +193,13 @@ def attention_fwd(qkv, H, mask=None, mask_kind=MASK_NONE, residual=None, want_sc
         if split_out and want_split(B * N, D):
             oh, ol = new_planes(B * N * D)
         taken = ctypes.c_int(0)
+        lse = DeviceArray((B * H * N,))
         lib.nt_attention_fwd_planes(qkv.ptr, sp[0].ptr, sp[1].ptr, mask_kind, out.ptr, P.ptr, B, N, H, D // H, ptr_or_null(residual),
-                                    ptr_or_null(oh), ptr_or_null(ol), ctypes.byref(taken))
+                                    ptr_or_null(oh), ptr_or_null(ol), lse.ptr, ctypes.byref(taken))
         if taken.value:
-            qkv._split = None                       # nothing else reads the planes: give the memory back
+            qkv._split = None
+            # what the tcgen05 backward takes instead of P: the planes of qkv and the row log-sum-exp (attention_bwd)
+            P._lse, P._qkv_planes = lse, sp
             if oh is not None:
                 out._split = (oh, ol)
             return out, P, S
@@ -217,6 +221,23 @@ def attention_bwd(dout, qkv, P, H, mask_kind=MASK_NONE, split_out=False, att_out
     D = three_d // 3
     dh = D // H
     dqkv = qkv.empty_like()
+    dsp = getattr(dout, "_split", None)
+    if (getattr(P, "_lse", None) is not None and dsp is not None and att_out is not None
+            and attention_wants_planes(N, dh, mask_kind)):
+        # tcgen05 backward (csrc/attention_tcl.cu): dout and qkv as bf16 planes by TMA, P recomputed from the row log-sum-exp
+        gh = gl = None
+        if split_out and want_split(B * N, 3 * D):
+            gh, gl = new_planes(B * N * 3 * D)
+        taken = ctypes.c_int(0)
+        lib.nt_attention_bwd_planes(dout.ptr, dsp[0].ptr, dsp[1].ptr, P._qkv_planes[0].ptr, P._qkv_planes[1].ptr, att_out.ptr,
+                                    P._lse.ptr, dqkv.ptr, ptr_or_null(gh), ptr_or_null(gl), B, N, H, dh, int(mask_kind),
+                                    ctypes.byref(taken))
+        if taken.value:
+            _last["attention_bwd"] = "tcgen05-planes"
+            if gh is not None:
+                dqkv._split = (gh, gl)
+            return dqkv
+    _last["attention_bwd"] = "mma.sync"
     if _att_bf16(N, dh):
         scratch = DeviceArray((B * H * N,))             # BF16x3 kernels: row sums of dP o P only
         gh = gl = None

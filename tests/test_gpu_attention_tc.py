@@ -83,9 +83,9 @@ def test_attention_tcl_forward_vs_oracle():
         if causal:
             assert not np.triu(Ph, 1).any(), "probabilities above the causal diagonal must be exact zeros"
         sp = getattr(out, "_split", None)
+        bf = lambda a: (a.numpy().view(np.uint16).astype(np.uint32) << 16).view(np.float32).reshape(-1)
         if sp is not None:
-            bf = lambda a: (a.numpy().view(np.uint16).astype(np.uint32) << 16).view(np.float32).reshape(-1)[:B * N * H * 64]
-            e.append(rel_err((bf(sp[0]) + bf(sp[1])).reshape(B, N, H * 64), O + res))
+            e.append(rel_err((bf(sp[0]) + bf(sp[1]))[:B * N * H * 64].reshape(B, N, H * 64), O + res))
         out2, P2, _ = ops.attention_fwd(qd, H, None, kind)
         g = ops.attention_bwd(nt.as_device(dout), qd, P2, H, kind, att_out=out2)
         e.append(rel_err(g, R.attention_bwd(dout, qkv, P, H)))
@@ -97,6 +97,17 @@ def test_attention_tcl_forward_vs_oracle():
         e += [rel_err(out3, O + res), rel_err(P3, P)]
         if causal:
             assert not np.triu(np.asarray(P3), 1).any()
+        # the tcgen05 backward: dout and qkv as planes, P recomputed from the forward's row log-sum-exp
+        qd._split = (hi, lo)
+        out4, P4, _ = ops.attention_fwd(qd, H, None, kind)                     # no residual: att_out for the row sums
+        dd = nt.as_device(dout)
+        dd._split = ops.split_bf16(dd, B * N, H * 64)[:2]
+        g2 = ops.attention_bwd(dd, qd, P4, H, kind, split_out=True, att_out=out4)
+        assert ops._last["attention_bwd"] == "tcgen05-planes"
+        e.append(rel_err(g2, R.attention_bwd(dout, qkv, P, H)))
+        sp = getattr(g2, "_split", None)
+        if sp is not None:
+            e.append(rel_err((bf(sp[0]) + bf(sp[1]))[:B * N * 3 * H * 64].reshape(B, N, 3 * H * 64), R.attention_bwd(dout, qkv, P, H)))
         worst = max(worst, max(e))
         assert max(e) < 1e-4, (B, N, H, causal, e)
     print("attention_tcl worst rel err %.2e" % worst)

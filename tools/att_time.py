@@ -38,6 +38,8 @@ def fwd():
     if PLANES:
         qkv._split = planes
     res["o"] = ops.attention_fwd(qkv, H, None, KIND, split_out=True)
+if PLANES:
+    dout._split = ops.split_bf16(dout, B * N, H * dh)[:2]
 def bwd():
     o, P, _ = res["o"]
     ops.attention_bwd(dout, qkv, P, H, KIND, split_out=True, att_out=o)
