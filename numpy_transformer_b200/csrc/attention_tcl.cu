@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tcl_fwd_kernel(Args a, const 
   };
   // O = P V.  Per K = 16 step two MMAs instead of three: P.hi x [V.hi | V.lo] (the two planes are one MN-major operand
   // of N = 128, chunk stride = the distance between the planes) lands hi*hi in accumulator columns 0..63 and hi*lo in
-  // 64..127, P.lo x V.hi adds to 0..63; the epilogue sums the halves.  (An M = 128 MMA pays ~130 cycles for its K-major A
-  // strip whatever N is, so fewer, wider MMAs are cheaper.)
+  // 64..127, P.lo x V.hi adds to 0..63; the epilogue sums the halves.  (An M = 128, K = 16 MMA has a floor of ~51 cycles
+  // however narrow it is — tools/umma_rate.cu: N = 64 51, N = 128 66 — so fewer, wider MMAs are cheaper.)
   auto issue_o = [&](int nk, uint32_t ph) {
     const uint32_t id_o = idesc_bf16(128, 64, 0, 1), id_o2 = idesc_bf16(128, 128, 0, 1);
     const uint64_t ah0 = desc_kmajor(sb + OFF_P_HI), al0 = desc_kmajor(sb + OFF_P_LO);

@@ -345,7 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t al = make_smem_desc(sal + k * a_adv, a_lbo, a_sbo, a_lay);
             const uint64_t bl = make_smem_desc(sbl + k * b_adv, b_lbo, b_sbo, b_lay);
             if (wide) {
-              // an M = 128 MMA costs ~130 cycles for its A strip whatever N is (measured in attention_tcl.cu): fewer, wider
+              // two instructions of N = 2 BN and BN instead of three of BN (tools/umma_rate.cu: N = 128 66, N = 256 124 cycles)
               umma_f16(tmem_base, ah, bh, idesc_w, accum);   // [hi*hi | hi*lo] -> columns [0, BN) and [BN, 2 BN)
               umma_f16(tmem_base, al, bh, idesc, 1);         // lo*hi -> columns [0, BN)
             } else {
