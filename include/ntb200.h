@@ -259,6 +259,7 @@ int nt_vit_blocks_bwd(const NtVitBlock* blocks, int nblocks, const float* x, con
 int nt_vit_tc_supported(int N, int D, int H, int* ok);
 int nt_vit_tc_wimg_bytes(int D, size_t* bytes);
 int nt_attention_tcl_debug(long long* stamps);   /* development aid: [8][2][16] clock64 phase stamps of CTA 0 of the tcgen05 attention forward (64 < N <= 256), NULL = off */
+int nt_attention_tcl_bwd_debug(long long* stamps);   /* the same for the backward: [8 pairs][2][16] */
 int nt_vit_tc_debug(long long* stamps);   /* development aid: [2][16][16] clock64 phase stamps of CTA 0, NULL = off */
 int nt_vit_tc_prepare(const NtVitBlock* blocks, int nblocks, int D, int H);
 int nt_vit_tc_fwd(const NtVitBlock* blocks, int nblocks, const float* x, int B, int N, int D, int H, int prepared);

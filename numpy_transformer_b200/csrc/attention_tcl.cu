@@ -56,6 +56,7 @@ struct Args {
   long long* dbg;        // optional phase time stamps of CTA 0: [item < 8][warp 0 / warp 15][16 events]
 };
 static long long* g_dbg = nullptr;
+static long long* g_dbg_bwd = nullptr;
 __device__ __forceinline__ void stamp(const Args& a, int n, int ev) {
   if (a.dbg && blockIdx.x == 0 && n < 8 && (threadIdx.x == 0 || threadIdx.x == 480)) a.dbg[(n * 2 + (threadIdx.x ? 1 : 0)) * 16 + ev] = clock64();
 }
@@ -90,6 +91,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -239,7 +244,24 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tcl_fwd_kernel(Args a, const 
         stamp(a, n, 2);
         arrive(B_V);
       } else {
-        if (tid == 0) issue_s(nk, ph);
+        if (tid == 0) {
+          if (it + (int)gridDim.x < items) {
+            // the next item's tiles towards L2 now: a tile is 128-byte rows 3D * 2 bytes apart, slow when it has to come from
+            // DRAM at the moment it is needed
+            int bh2, qt2, nk2;
+            decode(it + gridDim.x, bh2, qt2, nk2);
+            const int b2 = bh2 / H, c2 = (bh2 % H) * DH;
+            tma_prefetch_3d(&tm_hi, c2, qt2 * BM, b2);
+            tma_prefetch_3d(&tm_lo, c2, qt2 * BM, b2);
+            for (int j = 0; j < ((nk2 + 127) >> 7); j++) {
+              tma_prefetch_3d(&tm_hi, D + c2, j * 128, b2);
+              tma_prefetch_3d(&tm_lo, D + c2, j * 128, b2);
+              tma_prefetch_3d(&tm_hi, 2 * D + c2, j * 128, b2);
+              tma_prefetch_3d(&tm_lo, 2 * D + c2, j * 128, b2);
+            }
+          }
+          issue_s(nk, ph);
+        }
         __syncwarp();
       }
       stamp(a, n, 3);
@@ -427,6 +449,7 @@ static bool enabled() {
 namespace atb {
 using namespace um;
 using atl::tma_load_3d;
+using atl::tma_prefetch_3d;
 using atl::ex2;
 
 constexpr int DH = 64, BM = 128;
@@ -436,8 +459,8 @@ constexpr uint32_t OFF_Q_HI = 0, OFF_Q_LO = PCH, OFF_D_HI = 2 * PCH, OFF_D_LO = 
                    OFF_V_HI = 6 * PCH, OFF_V_LO = 7 * PCH;
 constexpr uint32_t OFF_PS_HI = 8 * PCH, OFF_PS_LO = 10 * PCH;      // P, then dS: [128 q][128 keys] = two chunks per plane
 constexpr uint32_t OFF_STG = OFF_PS_HI;                            // fp32 [128][64] staging tile of the output epilogues
-constexpr uint32_t OFF_DELTA = 12 * PCH, OFF_LSE = OFF_DELTA + BM * 4, OFF_BAR = OFF_LSE + BM * 4;
-enum { B_QD = 0, B_KV, B_SDP, B_P, B_DV, B_DS, B_DQK, B_COUNT };
+constexpr uint32_t OFF_DELTA = 12 * PCH, OFF_LSE = OFF_DELTA + 2 * BM * 4, OFF_BAR = OFF_LSE + 2 * BM * 4;   // [2][128] each
+enum { B_TQ = 0, B_TD, B_TK, B_TV, B_SDP, B_P, B_DV, B_DS, B_DQK, B_COUNT };   // B_T*: q, dO, k, v landed (TMA)
 constexpr uint32_t SMEM = OFF_BAR + B_COUNT * 8 + 16;
 static_assert(SMEM <= 232448, "shared memory budget");
 constexpr uint32_t T_S = 0, T_DP = 128, T_DK = 256, T_DV = 320, T_DQ = 384;
@@ -450,7 +473,11 @@ struct Args {
   uint32_t* g_hi;        // bf16 pairs of dqkv or null
   uint32_t* g_lo;
   int B, N, H, causal;
+  long long* dbg;        // optional phase time stamps of CTA 0: [pair < 8][thread 0 / thread 480][16 events]
 };
+__device__ __forceinline__ void stamp(const Args& a, int n, int ev) {
+  if (a.dbg && blockIdx.x == 0 && n < 8 && (threadIdx.x == 0 || threadIdx.x == 480)) a.dbg[(n * 2 + (threadIdx.x ? 1 : 0)) * 16 + ev] = clock64();
+}
 
 // D (+)= A B in three passes; operands given as descriptors of the first K = 16 step and the per-step advance in 16-byte units
 __device__ __forceinline__ void mma3x(uint32_t tacc, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t a_step, uint32_t b_step,
@@ -533,151 +560,220 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tcl_bwd_kernel(Args a, const 
     named_bar_sync(1 + q, 128);                     // the tile is rewritten by the next store_tile / the next pair's planes
   };
 
-  uint32_t ph_qd = 0, ph_kv = 0, pp = 0;            // barrier phases (every thread keeps the same counters)
-  for (int item = blockIdx.x; item < BH; item += gridDim.x) {
+  // ---- operand loads run ahead of the pairs: a tensor is re-requested as soon as the last MMA that reads the old tile has
+  // retired (v after S / dP, dO after dV, q and k after dQ / dK), i.e. during the current pair, also across items.
+  // Every thread keeps the same bookkeeping; thread 0 issues the copies and waits for them before the MMAs.
+  enum { T_Q = 0, T_D, T_K, T_V };
+  int have_item[4] = {-1, -1, -1, -1}, have_idx[4] = {-1, -1, -1, -1};
+  uint32_t tph[4] = {0, 0, 0, 0};
+  bool pend[4] = {false, false, false, false};
+  auto request = [&](int which, int item, int idx) {
+    if (have_item[which] == item && have_idx[which] == idx) return;
+    have_item[which] = item; have_idx[which] = idx; pend[which] = true;
+    if (tid == 0) {
+      const int b = item / H, h = item % H;
+      const uint32_t dst = sb + (which == T_Q ? OFF_Q_HI : which == T_D ? OFF_D_HI : which == T_K ? OFF_K_HI : OFF_V_HI);
+      const int col = (which == T_Q ? 0 : which == T_D ? 0 : which == T_K ? D : 2 * D) + h * DH;
+      fence_async_smem();
+      mbar_expect_tx(&bar[B_TQ + which], 2u * PCH);
+      tma_load_3d(dst, which == T_D ? &td_hi : &tq_hi, &bar[B_TQ + which], col, idx * BM, b);
+      tma_load_3d(dst + PCH, which == T_D ? &td_lo : &tq_lo, &bar[B_TQ + which], col, idx * BM, b);
+    }
+  };
+  auto await = [&](int which) {                      // thread 0 blocks; everybody flips the phase
+    if (!pend[which]) return;
+    if (tid == 0) mbar_wait(&bar[B_TQ + which], tph[which]);
+    tph[which] ^= 1;
+    pend[which] = false;
+  };
+  auto advance = [&](int& item, int& kb, int& qt) {   // next (item, key block, query tile); item >= BH: none
+    qt--;
+    if (qt < (a.causal ? kb : 0)) { kb--; qt = QT - 1; }
+    if (kb < 0) { item += gridDim.x; kb = KT - 1; qt = QT - 1; }
+  };
+
+  // delta_i = dO_i . O_i (attention.py:75) and the row log-sum-exp of query tile (item, qt) -> buffer `buf`:
+  // 4 lanes per row, 256 contiguous bytes
+  auto compute_delta = [&](int item_, int qt_, int buf) {
+    const int row = tid >> 2, qq = tid & 3, g = qt_ * BM + row;
+    const int b_ = item_ / H, h_ = item_ % H;
+    float acc = 0.f;
+    if (g < N) {
+      const long long oi = ((long long)b_ * N + g) * D + h_ * DH + 16 * qq;
+      const float4* pd = reinterpret_cast<const float4*>(a.dout + oi);
+      const float4* po = reinterpret_cast<const float4*>(a.att_out + oi);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float4 x = __ldg(pd + j), y = __ldg(po + j);
+        acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (qq == 0) delta_s[buf * BM + row] = acc;
+    if (tid < BM) lse_s[buf * BM + tid] = (qt_ * BM + tid < N) ? __ldg(a.lse + (long long)item_ * N + qt_ * BM + tid) : 0.f;
+  };
+  int dbuf = 0;
+  bool dnext = false;
+  uint32_t pp = 0;                                  // phase of the per-pair barriers
+  int np = 0;                                       // pairs done by this CTA (time stamps)
+  int item = blockIdx.x, kb = KT - 1, qt = QT - 1;
+  int d_item = -1, d_qt = -1;                       // query tile whose delta / lse sit in shared memory
+  if (item < BH) { request(T_Q, item, qt); request(T_K, item, kb); request(T_D, item, qt); request(T_V, item, kb); }
+  while (item < BH) {
     const int b = item / H, h = item % H;
-    int cur_qt = -1;
-    for (int kb = KT - 1; kb >= 0; kb--) {
-      if (tid == 0) {                               // k, v of this key block (everything that read the old ones has retired)
-        fence_async_smem();
-        mbar_expect_tx(&bar[B_KV], 4u * PCH);
-        tma_load_3d(sb + OFF_K_HI, &tq_hi, &bar[B_KV], D + h * DH, kb * BM, b);
-        tma_load_3d(sb + OFF_K_LO, &tq_lo, &bar[B_KV], D + h * DH, kb * BM, b);
-        tma_load_3d(sb + OFF_V_HI, &tq_hi, &bar[B_KV], 2 * D + h * DH, kb * BM, b);
-        tma_load_3d(sb + OFF_V_LO, &tq_lo, &bar[B_KV], 2 * D + h * DH, kb * BM, b);
+    int n_item = item, n_kb = kb, n_qt = qt;
+    advance(n_item, n_kb, n_qt);
+    const bool has_next = n_item < BH;
+    const bool first_k = (qt == QT - 1);                         // first pair of this key block: dK, dV start from zero
+    const bool first_q = (kb == (a.causal ? qt : KT - 1));       // first pair of this query tile: dQ starts from zero
+    const bool last_k = (qt == (a.causal ? kb : 0));             // last pair of this key block: dK, dV are complete
+    const bool last_item = last_k && kb == 0;
+    stamp(a, np, 0);
+    if (tid == 0 && has_next) {
+      // the tiles the next pair will ask for, towards L2 now (a [128][64] tile of a plane is 128 rows of 128 bytes, 3D * 2
+      // bytes apart: 4.4 K cycles when it comes from DRAM at the moment it is needed)
+      const int nb = n_item / H, nc = (n_item % H) * DH;
+      if (n_item != item || n_qt != qt) {
+        tma_prefetch_3d(&tq_hi, nc, n_qt * BM, nb); tma_prefetch_3d(&tq_lo, nc, n_qt * BM, nb);
+        tma_prefetch_3d(&td_hi, nc, n_qt * BM, nb); tma_prefetch_3d(&td_lo, nc, n_qt * BM, nb);
       }
-      const int qt_lo = a.causal ? kb : 0;
-      for (int qt = QT - 1; qt >= qt_lo; qt--) {
-        const bool first_k = (qt == QT - 1);                         // first pair of this key block: dK, dV start from zero
-        const bool first_q = (kb == (a.causal ? qt : KT - 1));       // first pair of this query tile: dQ starts from zero
-        const bool new_q = (qt != cur_qt);
-        if (new_q) {
-          cur_qt = qt;
-          if (tid == 0) {
-            fence_async_smem();
-            mbar_expect_tx(&bar[B_QD], 4u * PCH);
-            tma_load_3d(sb + OFF_Q_HI, &tq_hi, &bar[B_QD], h * DH, qt * BM, b);
-            tma_load_3d(sb + OFF_Q_LO, &tq_lo, &bar[B_QD], h * DH, qt * BM, b);
-            tma_load_3d(sb + OFF_D_HI, &td_hi, &bar[B_QD], h * DH, qt * BM, b);
-            tma_load_3d(sb + OFF_D_LO, &td_lo, &bar[B_QD], h * DH, qt * BM, b);
-          }
-          // delta_i = dO_i . O_i and the row log-sum-exp of the tile: 4 lanes per row, 256 contiguous bytes
-          {
-            const int row = tid >> 2, qq = tid & 3, g = qt * BM + row;
-            float acc = 0.f;
-            if (g < N) {
-              const long long oi = ((long long)b * N + g) * D + h * DH + 16 * qq;
-              const float4* pd = reinterpret_cast<const float4*>(a.dout + oi);
-              const float4* po = reinterpret_cast<const float4*>(a.att_out + oi);
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                const float4 x = __ldg(pd + j), y = __ldg(po + j);
-                acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
-              }
-            }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            if (qq == 0) delta_s[row] = acc;
-            if (tid < BM) lse_s[tid] = (qt * BM + tid < N) ? __ldg(a.lse + (long long)item * N + qt * BM + tid) : 0.f;
-            named_bar_sync(5, THREADS);
-          }
-        }
-        // ---- S = Q K^T, dP = dO V^T
-        if (tid == 0) {
-          if (new_q) { mbar_wait(&bar[B_QD], ph_qd); }
-          if (first_k) { mbar_wait(&bar[B_KV], ph_kv); }
-          tc_fence_after();
-          const uint32_t id = idesc_bf16(128, 128, 0, 0);
-          mma3x(tbase + T_S, desc_kmajor(sb + OFF_Q_HI), desc_kmajor(sb + OFF_Q_LO), desc_kmajor(sb + OFF_K_HI), desc_kmajor(sb + OFF_K_LO),
-                KMAJ_STEP >> 4, KMAJ_STEP >> 4, 4, id, true);
-          mma3x(tbase + T_DP, desc_kmajor(sb + OFF_D_HI), desc_kmajor(sb + OFF_D_LO), desc_kmajor(sb + OFF_V_HI), desc_kmajor(sb + OFF_V_LO),
-                KMAJ_STEP >> 4, KMAJ_STEP >> 4, 4, id, true);
-          mma_commit(&bar[B_SDP]);
-        }
-        __syncwarp();
-        if (new_q) ph_qd ^= 1;
-        if (first_k) ph_kv ^= 1;
-        // ---- P and dS of this thread's 32 key columns
-        uint32_t pv[32], dv[32];
-        mbar_wait(&bar[B_SDP], pp);
+      if (n_item != item || n_kb != kb) {
+        tma_prefetch_3d(&tq_hi, D + nc, n_kb * BM, nb); tma_prefetch_3d(&tq_lo, D + nc, n_kb * BM, nb);
+        tma_prefetch_3d(&tq_hi, 2 * D + nc, n_kb * BM, nb); tma_prefetch_3d(&tq_lo, 2 * D + nc, n_kb * BM, nb);
+      }
+    }
+    // ---- S = Q K^T, dP = dO V^T
+    {
+      const uint32_t id = idesc_bf16(128, 128, 0, 0);
+      await(T_Q);
+      await(T_K);
+      if (tid == 0) {
         tc_fence_after();
-        tmem_ld32(lane_addr + T_S + 32 * cg, pv);
-        tmem_ld32(lane_addr + T_DP + 32 * cg, dv);
-        tmem_wait_ld();
-        {
-          const int g = qt * BM + r, cb = kb * BM + 32 * cg;
-          const bool live = g < N;
-          const float ls = lse_s[r], dl = delta_s[r];
-          const bool edge = (cb + 31 >= N) || (a.causal && cb + 31 > qt * BM + 32 * q);
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            bool ok = live;
-            if (edge) ok = ok && (cb + j < N) && !(a.causal && cb + j > g);
-            const float p = ok ? ex2(fmaf(__uint_as_float(pv[j]), c, -ls)) : 0.f;
-            pv[j] = __float_as_uint(p);
-            dv[j] = __float_as_uint(p * (__uint_as_float(dv[j]) - dl) * scale);
-          }
-        }
-#pragma unroll
-        for (int j8 = 0; j8 < 4; j8++) {
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; i++) v[i] = __uint_as_float(pv[8 * j8 + i]);
-          store8_split(smem + OFF_PS_HI, smem + OFF_PS_LO, r, 32 * cg + 8 * j8, PCH, v);
-        }
-        arrive(B_P);
-        // ---- dV += P^T dO
-        if (tid == 0) {
-          mbar_wait(&bar[B_P], pp);
-          tc_fence_after();
-          mma3x(tbase + T_DV, desc_mnmajor(sb + OFF_PS_HI, PCH), desc_mnmajor(sb + OFF_PS_LO, PCH), desc_mnmajor(sb + OFF_D_HI, 8192),
-                desc_mnmajor(sb + OFF_D_LO, 8192), MNMAJ_STEP >> 4, MNMAJ_STEP >> 4, 8, idesc_bf16(128, 64, 1, 1), first_k);
-          mma_commit(&bar[B_DV]);
-        }
-        __syncwarp();
-        mbar_wait(&bar[B_DV], pp);                   // the tensor core has consumed P: its planes take dS
+        mma3x(tbase + T_S, desc_kmajor(sb + OFF_Q_HI), desc_kmajor(sb + OFF_Q_LO), desc_kmajor(sb + OFF_K_HI), desc_kmajor(sb + OFF_K_LO),
+              KMAJ_STEP >> 4, KMAJ_STEP >> 4, 4, id, true);
+      }
+      await(T_D);
+      await(T_V);
+      if (tid == 0) {
         tc_fence_after();
+        mma3x(tbase + T_DP, desc_kmajor(sb + OFF_D_HI), desc_kmajor(sb + OFF_D_LO), desc_kmajor(sb + OFF_V_HI), desc_kmajor(sb + OFF_V_LO),
+              KMAJ_STEP >> 4, KMAJ_STEP >> 4, 4, id, true);
+        mma_commit(&bar[B_SDP]);
+      }
+      __syncwarp();
+    }
+    stamp(a, np, 1);
+    // ---- delta / lse of this query tile: normally computed one pair ahead (below); only the first pair computes here
+    if (d_item != item || d_qt != qt) {
+      dbuf ^= 1;
+      compute_delta(item, qt, dbuf);
+      d_item = item; d_qt = qt;
+      named_bar_sync(5, THREADS);
+    }
+    stamp(a, np, 2);
+    // ---- P and dS of this thread's 32 key columns
+    uint32_t pv[32], dv[32];
+    mbar_wait(&bar[B_SDP], pp);
+    tc_fence_after();
+    if (has_next) request(T_V, n_item, n_kb);        // dP has retired: v may go
+    tmem_ld32(lane_addr + T_S + 32 * cg, pv);
+    tmem_ld32(lane_addr + T_DP + 32 * cg, dv);
+    tmem_wait_ld();
+    stamp(a, np, 3);
+    {
+      const int g = qt * BM + r, cb = kb * BM + 32 * cg;
+      const bool live = g < N;
+      const float ls = lse_s[dbuf * BM + r], dl = delta_s[dbuf * BM + r];
+      const bool edge = (cb + 31 >= N) || (a.causal && cb + 31 > qt * BM + 32 * q);
 #pragma unroll
-        for (int j8 = 0; j8 < 4; j8++) {
-          float v[8];
+      for (int j = 0; j < 32; j++) {
+        bool ok = live;
+        if (edge) ok = ok && (cb + j < N) && !(a.causal && cb + j > g);
+        const float p = ok ? ex2(fmaf(__uint_as_float(pv[j]), c, -ls)) : 0.f;
+        pv[j] = __float_as_uint(p);
+        dv[j] = __float_as_uint(p * (__uint_as_float(dv[j]) - dl) * scale);
+      }
+    }
 #pragma unroll
-          for (int i = 0; i < 8; i++) v[i] = __uint_as_float(dv[8 * j8 + i]);
-          store8_split(smem + OFF_PS_HI, smem + OFF_PS_LO, r, 32 * cg + 8 * j8, PCH, v);
-        }
-        arrive(B_DS);
-        // ---- dQ += dS K, dK += dS^T Q
-        if (tid == 0) {
-          mbar_wait(&bar[B_DS], pp);
-          tc_fence_after();
-          // dS as a K-major A operand: K = 16 step ks lives in chunk ks / 4 at 32 (ks % 4) bytes
-          const uint64_t ah0 = desc_kmajor(sb + OFF_PS_HI), al0 = desc_kmajor(sb + OFF_PS_LO);
-          const uint64_t bh0 = desc_mnmajor(sb + OFF_K_HI, 8192), bl0 = desc_mnmajor(sb + OFF_K_LO, 8192);
-          const uint32_t idq = idesc_bf16(128, 64, 0, 1);
+    for (int j8 = 0; j8 < 4; j8++) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = __uint_as_float(pv[8 * j8 + i]);
+      store8_split(smem + OFF_PS_HI, smem + OFF_PS_LO, r, 32 * cg + 8 * j8, PCH, v);
+    }
+    stamp(a, np, 4);
+    arrive(B_P);
+    // ---- dV += P^T dO
+    if (tid == 0) {
+      mbar_wait(&bar[B_P], pp);
+      tc_fence_after();
+      mma3x(tbase + T_DV, desc_mnmajor(sb + OFF_PS_HI, PCH), desc_mnmajor(sb + OFF_PS_LO, PCH), desc_mnmajor(sb + OFF_D_HI, 8192),
+            desc_mnmajor(sb + OFF_D_LO, 8192), MNMAJ_STEP >> 4, MNMAJ_STEP >> 4, 8, idesc_bf16(128, 64, 1, 1), first_k);
+      mma_commit(&bar[B_DV]);
+    }
+    __syncwarp();
+    mbar_wait(&bar[B_DV], pp);                       // the tensor core has consumed P: its planes take dS
+    tc_fence_after();
+    if (has_next) request(T_D, n_item, n_qt);        // dP and dV have retired: dO may go
+    stamp(a, np, 5);
+#pragma unroll
+    for (int j8 = 0; j8 < 4; j8++) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = __uint_as_float(dv[8 * j8 + i]);
+      store8_split(smem + OFF_PS_HI, smem + OFF_PS_LO, r, 32 * cg + 8 * j8, PCH, v);
+    }
+    stamp(a, np, 6);
+    arrive(B_DS);
+    // ---- dQ += dS K, dK += dS^T Q
+    if (tid == 0) {
+      mbar_wait(&bar[B_DS], pp);
+      tc_fence_after();
+      // dS as a K-major A operand: K = 16 step ks lives in chunk ks / 4 at 32 (ks % 4) bytes
+      const uint64_t ah0 = desc_kmajor(sb + OFF_PS_HI), al0 = desc_kmajor(sb + OFF_PS_LO);
+      const uint64_t bh0 = desc_mnmajor(sb + OFF_K_HI, 8192), bl0 = desc_mnmajor(sb + OFF_K_LO, 8192);
+      const uint32_t idq = idesc_bf16(128, 64, 0, 1);
 #pragma unroll 4
-          for (int ks = 0; ks < 8; ks++) {
-            const uint64_t pa = (uint64_t)((ks >> 2) * (PCH >> 4) + (ks & 3) * (KMAJ_STEP >> 4)), pb = (uint64_t)(ks * (MNMAJ_STEP >> 4));
-            mma_bf16(tbase + T_DQ + 64 * qt, al0 + pa, bh0 + pb, idq, (first_q && ks == 0) ? 0u : 1u);
-            mma_bf16(tbase + T_DQ + 64 * qt, ah0 + pa, bl0 + pb, idq, 1u);
-            mma_bf16(tbase + T_DQ + 64 * qt, ah0 + pa, bh0 + pb, idq, 1u);
-          }
-          mma3x(tbase + T_DK, desc_mnmajor(sb + OFF_PS_HI, PCH), desc_mnmajor(sb + OFF_PS_LO, PCH), desc_mnmajor(sb + OFF_Q_HI, 8192),
-                desc_mnmajor(sb + OFF_Q_LO, 8192), MNMAJ_STEP >> 4, MNMAJ_STEP >> 4, 8, idesc_bf16(128, 64, 1, 1), first_k);
-          mma_commit(&bar[B_DQK]);
-        }
-        __syncwarp();
-        mbar_wait(&bar[B_DQK], pp);
-        tc_fence_after();
-        pp ^= 1;
+      for (int ks = 0; ks < 8; ks++) {
+        const uint64_t pa = (uint64_t)((ks >> 2) * (PCH >> 4) + (ks & 3) * (KMAJ_STEP >> 4)), pb = (uint64_t)(ks * (MNMAJ_STEP >> 4));
+        mma_bf16(tbase + T_DQ + 64 * qt, al0 + pa, bh0 + pb, idq, (first_q && ks == 0) ? 0u : 1u);
+        mma_bf16(tbase + T_DQ + 64 * qt, ah0 + pa, bl0 + pb, idq, 1u);
+        mma_bf16(tbase + T_DQ + 64 * qt, ah0 + pa, bh0 + pb, idq, 1u);
       }
-      // ---- dK, dV of this key block are complete
+      mma3x(tbase + T_DK, desc_mnmajor(sb + OFF_PS_HI, PCH), desc_mnmajor(sb + OFF_PS_LO, PCH), desc_mnmajor(sb + OFF_Q_HI, 8192),
+            desc_mnmajor(sb + OFF_Q_LO, 8192), MNMAJ_STEP >> 4, MNMAJ_STEP >> 4, 8, idesc_bf16(128, 64, 1, 1), first_k);
+      mma_commit(&bar[B_DQK]);
+    }
+    __syncwarp();
+    if (has_next && (n_item != item || n_qt != qt)) {
+      // the next pair works on another query tile: its delta / lse into the other buffer while dQ and dK are being multiplied
+      // (everybody is past its reads of the buffers: B_DS was complete before the MMAs were issued ... for the OTHER buffer the
+      // last readers finished a whole pair ago)
+      compute_delta(n_item, n_qt, dbuf ^ 1);
+      d_item = n_item; d_qt = n_qt;
+      dnext = true;
+    }
+    mbar_wait(&bar[B_DQK], pp);
+    tc_fence_after();
+    if (has_next) { request(T_K, n_item, n_kb); request(T_Q, n_item, n_qt); }     // everything has retired
+    stamp(a, np, 7);
+    pp ^= 1;
+    if (last_k) {                                    // dK, dV of this key block are complete
       store_tile(T_DK, 1, kb * BM, b, h);
       store_tile(T_DV, 2, kb * BM, b, h);
-      named_bar_sync(5, THREADS);                    // staging tile = P / dS planes of the next pair
+      stamp(a, np, 8);
     }
-    for (int qt = 0; qt < QT; qt++) store_tile(T_DQ + 64 * qt, 0, qt * BM, b, h);
-    named_bar_sync(5, THREADS);
-    tc_fence_before();
+    if (last_item) {
+      for (int t = 0; t < QT; t++) store_tile(T_DQ + 64 * t, 0, t * BM, b, h);
+      stamp(a, np, 9);
+    }
+    if (last_k || dnext) named_bar_sync(5, THREADS); // the staging tile is the P / dS planes of the next pair; delta is published
+    if (dnext) { dbuf ^= 1; dnext = false; }
+    np++;
+    item = n_item; kb = n_kb; qt = n_qt;
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
@@ -762,6 +858,7 @@ int attention_bwd_tcl(const float* dout, const void* dout_hi, const void* dout_l
   atb::Args a{};
   a.dout = dout; a.att_out = att_out; a.lse = lse; a.dqkv = dqkv; a.g_hi = (uint32_t*)g_hi; a.g_lo = (uint32_t*)g_lo;
   a.B = B; a.N = N; a.H = H; a.causal = causal;
+  a.dbg = atl::g_dbg_bwd;
   CUtensorMap tq_hi, tq_lo, td_hi, td_lo;
   if (plane_map(&tq_hi, qkv_hi, B, N, 3 * H * atb::DH) || plane_map(&tq_lo, qkv_lo, B, N, 3 * H * atb::DH) ||
       plane_map(&td_hi, dout_hi, B, N, H * atb::DH) || plane_map(&td_lo, dout_lo, B, N, H * atb::DH))
@@ -778,5 +875,9 @@ int attention_bwd_tcl(const float* dout, const void* dout_hi, const void* dout_l
 /* development aid: phase time stamps of CTA 0 ([8 items][2 threads][16 events] clock64 values); NULL switches them off */
 extern "C" int nt_attention_tcl_debug(long long* stamps) {
   nt::atl::g_dbg = stamps;
+  return 0;
+}
+extern "C" int nt_attention_tcl_bwd_debug(long long* stamps) {
+  nt::atl::g_dbg_bwd = stamps;
   return 0;
 }

@@ -66,3 +66,21 @@ if N > 64 and os.environ.get("NTB200_ATT_TCL", "1") != "0":
             prev = st[n, th, 0]
             print("   " + "  ".join("%s %d(+%d)" % (nm, st[n, th, k] - t0, st[n, th, k] - (st[n, th, k - 1] if k else prev))
                                     for k, nm in enumerate(names)))
+
+    if PLANES and os.environ.get("NTB200_ATT_TCL_BWD", "1") != "0":
+        dbg.fill_zero()
+        lib.nt_attention_tcl_bwd_debug(dbg.ptr)
+        bwd()
+        lib.nt_sync()
+        st = dbg.numpy().view(np.int64).reshape(8, 2, 16)
+        lib.nt_attention_tcl_bwd_debug(None)
+        names = ["pair start", "loads issued, delta", "S dP issued", "S dP in regs", "P stored", "dV done", "dS stored", "dQ dK done",
+                 "dK dV stored", "dQ stored"]
+        t0 = st[0, 0, 0]
+        for n in range(int(os.environ.get("ITEMS", 3)) * 2):
+            for th in (0, 1):
+                if st[n, th, 0] == 0:
+                    continue
+                print("backward pair %d of CTA 0, thread %s:" % (n, "0" if th == 0 else "480"))
+                print("   " + "  ".join("%s %d(+%d)" % (nm, st[n, th, k] - t0, st[n, th, k] - st[n, th, k - 1] if k else 0)
+                                        for k, nm in enumerate(names) if st[n, th, k]))
