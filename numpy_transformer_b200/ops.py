@@ -187,6 +187,10 @@ def attention_fwd(qkv, H, mask=None, mask_kind=MASK_NONE, residual=None, want_sc
     P = DeviceArray((B, H, N, N), host_dtype=qkv.host_dtype)
     S = P.empty_like() if want_scores else None
     sp = getattr(qkv, "_split", None)
+    if sp is None and B * N >= 2048 and attention_wants_planes(N, D // H, mask_kind, want_scores):
+        # the producer did not emit the planes (mode 2: the QKV Linear is a single-pass TF32 GEMM): one split pass over qkv is
+        # cheaper than what the TMA-fed kernels save (G1: ~30 us against ~150 us per layer, forward + backward)
+        sp = split_bf16(qkv, B * N, 3 * D)[:2]
     if sp is not None and attention_wants_planes(N, D // H, mask_kind, want_scores):
         # qkv came with its bf16 planes (QKV Linear with split_out=True): the tcgen05 kernel takes its operands by TMA
         oh = ol = None
@@ -222,6 +226,9 @@ def attention_bwd(dout, qkv, P, H, mask_kind=MASK_NONE, split_out=False, att_out
     dh = D // H
     dqkv = qkv.empty_like()
     dsp = getattr(dout, "_split", None)
+    if (dsp is None and getattr(P, "_lse", None) is not None and att_out is not None and B * N >= 2048
+            and attention_wants_planes(N, dh, mask_kind)):
+        dsp = split_bf16(dout, B * N, D)[:2]          # see attention_fwd
     if (getattr(P, "_lse", None) is not None and dsp is not None and att_out is not None
             and attention_wants_planes(N, dh, mask_kind)):
         # tcgen05 backward (csrc/attention_tcl.cu): dout and qkv as bf16 planes by TMA, P recomputed from the row log-sum-exp
