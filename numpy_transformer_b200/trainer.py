@@ -326,7 +326,12 @@ class TrainStep:
                     i = ends[i] - 1
                     continue
                 delta = fused_vit.backward_stack(run, delta)
-                if dp_on:
+                # With the one-kernel NVLink exchange available (small arenas) the block gradients wait for the stem's and
+                # go in ONE exchange at the end of the step: an exchange costs >= 20 us at 8 GPUs whatever its size, and the
+                # stem's backward (~10 us) hides less of a separate block exchange than the second latency floor costs
+                # (8 GPUs: 0.5359 vs 0.5430 ms/step).  NTB200_DP_MERGE=0 restores the early block exchange.
+                merge = getattr(self.dp, "p2p_ready", False) and os.environ.get("NTB200_DP_MERGE", "1") != "0"
+                if dp_on and not merge:
                     # the block gradients are complete: reduce them NOW on the comm stream, under the stem's backward
                     # kernels; only the (tiny) range in front of the blocks is left for the end of the step
                     lo = self.arena.first_offset(layers[ends[i]])
