@@ -178,7 +178,8 @@ int nt_attention_bwd_split(const float* dout, const float* qkv, const float* P, 
 /* attention.py:31-46 / gpt/attdecoderblock.py:52-69 on the tcgen05 kernel (dh == 64, 64 < N <= 256, no dense mask) with
  * qkv ALSO given as row-major bf16 hi / lo planes [B*N][3*H*dh] (what nt_linear_fwd_bf16x3 writes for the QKV Linear):
  * q, k, v tiles reach shared memory by TMA in tensor-core operand layout.  lse (may be NULL): [B,H,N] row log-sum-exp
- * in the log2 domain, for nt_attention_bwd_planes.  *taken = 0 and nothing done if the shape is not covered (call
+ * in the log2 domain, for nt_attention_bwd_planes.  P may be NULL when lse is given (the probabilities are then not
+ * materialised: 100 MB per call at the poetry3000 shape that only the layer API's atg__ needs).  *taken = 0 and nothing done if the shape is not covered (call
  * nt_attention_fwd_split instead). */
 int nt_attention_fwd_planes(const float* qkv, const void* qkv_hi, const void* qkv_lo, int mask_kind, float* out, float* P,
                             int B, int N, int H, int dh, const float* residual, void* out_hi, void* out_lo, float* lse, int* taken);

@@ -45,7 +45,7 @@ constexpr uint32_t T_S = 0, T_O = 256;          // TMEM columns
 struct Args {
   const float* qkv;      // [B,N,3*H*64]
   float* out;            // [B,N,H*64]
-  float* P;              // [B,H,N,N]
+  float* P;              // [B,H,N,N], or null: not materialised (the tcgen05 backward recomputes it from lse)
   const float* residual; // [B,N,H*64] or null
   uint32_t* o_hi;        // bf16 pairs of `out` (row-major) or null
   uint32_t* o_lo;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tcl_fwd_kernel(Args a, const 
       // 2^-17) while the tensor core multiplies them with V.  A warp writes 512 contiguous bytes of one row per instruction
       // (row-per-thread stores of the accumulator layout cost 32 LSU wavefronts per instruction: 11 K of 48 K cycles per tile).
       mbar_wait(&bar[B_P], ph);                      // the planes of ALL warps are complete (rows are re-dealt below)
-      if (warp) {                                    // warp 0 issued the MMAs meanwhile: the other 15 share the rows
+      if (warp && a.P) {                             // warp 0 issued the MMAs meanwhile: the other 15 share the rows
         const bool vec = (N & 3) == 0;
         for (int rr = warp - 1; rr < BM; rr += TOK_WARPS - 1) {
           const int g2 = qt * BM + rr;

@@ -180,11 +180,59 @@ def attention_wants_planes(N, dh, mask_kind, want_scores=False):
             and os.environ.get("NTB200_ATT_TCL", "1") != "0" and os.environ.get("NTB200_ATT_PLANES", "1") != "0")
 
 
+_lean = [False]
+
+
+class lean_attention:
+    """Context: attention_fwd may skip materialising P where the backward does not need it (TrainStep; the layer API keeps
+    P because the reference exposes it as atg__ / att)."""
+
+    def __enter__(self):
+        self.prev, _lean[0] = _lean[0], True
+
+    def __exit__(self, *exc):
+        _lean[0] = self.prev
+
+
+class LazyP:
+    """Stand-in for the probabilities [B,H,N,N] when the forward did not write them: carries what the tcgen05 backward takes
+    instead (row log-sum-exp, planes of qkv) and recomputes P on the device the first time anybody asks (np.asarray, .ptr)."""
+
+    def __init__(self, qkv, H, mask_kind, lse, planes, host_dtype):
+        B, N, _ = qkv.shape
+        self.shape, self.host_dtype = (B, H, N, N), host_dtype
+        self._qkv, self._H, self._mask_kind = qkv, H, mask_kind
+        self._lse, self._qkv_planes, self._dense = lse, planes, None
+
+    def _materialise(self):
+        if self._dense is None:
+            prev, _lean[0] = _lean[0], False
+            try:
+                self._dense = attention_fwd(self._qkv, self._H, None, self._mask_kind)[1]
+            finally:
+                _lean[0] = prev
+        return self._dense
+
+    @property
+    def ptr(self):
+        return self._materialise().ptr
+
+    def numpy(self):
+        return self._materialise().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = np.asarray(self._materialise())
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+
 def attention_fwd(qkv, H, mask=None, mask_kind=MASK_NONE, residual=None, want_scores=False, split_out=False):
     B, N, three_d = qkv.shape
     D = three_d // 3
     out = DeviceArray((B, N, D), host_dtype=qkv.host_dtype)
-    P = DeviceArray((B, H, N, N), host_dtype=qkv.host_dtype)
+    import os
+    lean = (_lean[0] and not want_scores and os.environ.get("NTB200_ATT_TCL_BWD", "1") != "0" and B * N >= 2048
+            and attention_wants_planes(N, D // H, mask_kind, want_scores))
+    P = None if lean else DeviceArray((B, H, N, N), host_dtype=qkv.host_dtype)
     S = P.empty_like() if want_scores else None
     sp = getattr(qkv, "_split", None)
     if sp is None and B * N >= 2048 and attention_wants_planes(N, D // H, mask_kind, want_scores):
@@ -198,15 +246,20 @@ def attention_fwd(qkv, H, mask=None, mask_kind=MASK_NONE, residual=None, want_sc
             oh, ol = new_planes(B * N * D)
         taken = ctypes.c_int(0)
         lse = DeviceArray((B * H * N,))
-        lib.nt_attention_fwd_planes(qkv.ptr, sp[0].ptr, sp[1].ptr, mask_kind, out.ptr, P.ptr, B, N, H, D // H, ptr_or_null(residual),
-                                    ptr_or_null(oh), ptr_or_null(ol), lse.ptr, ctypes.byref(taken))
+        lib.nt_attention_fwd_planes(qkv.ptr, sp[0].ptr, sp[1].ptr, mask_kind, out.ptr, ptr_or_null(P), B, N, H, D // H,
+                                    ptr_or_null(residual), ptr_or_null(oh), ptr_or_null(ol), lse.ptr, ctypes.byref(taken))
         if taken.value:
             qkv._split = None
             # what the tcgen05 backward takes instead of P: the planes of qkv and the row log-sum-exp (attention_bwd)
-            P._lse, P._qkv_planes = lse, sp
+            if P is None:
+                P = LazyP(qkv, H, mask_kind, lse, sp, qkv.host_dtype)
+            else:
+                P._lse, P._qkv_planes = lse, sp
             if oh is not None:
                 out._split = (oh, ol)
             return out, P, S
+    if P is None:
+        P = DeviceArray((B, H, N, N), host_dtype=qkv.host_dtype)
     if split_out and _att_bf16(N, D // H) and want_split(B * N, D):
         oh, ol = new_planes(B * N * D)
         out._split = (oh, ol)

@@ -349,7 +349,8 @@ class TrainStep:
 
     def _enqueue(self):
         self._early_from = None          # arena offset from which the gradients were all-reduced early (DP only)
-        self.logits, self.probs = self._enqueue_body()
+        with ops.lean_attention():           # nobody reads the attention probabilities of a TrainStep (they are recomputed on demand)
+            self.logits, self.probs = self._enqueue_body()
         self.loss, self.argmax = self.d_loss, self.d_amax
         a = self.arena
         lib.nt_side_join()                       # weight-gradient branch must land before all-reduce / update
