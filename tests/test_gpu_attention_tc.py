@@ -111,3 +111,40 @@ def test_attention_tcl_forward_vs_oracle():
         worst = max(worst, max(e))
         assert max(e) < 1e-4, (B, N, H, causal, e)
     print("attention_tcl worst rel err %.2e" % worst)
+
+
+def test_attention_tcl_shape_sweep_vs_oracle():
+    """Forward (TMA operand path) + backward of csrc/attention_tcl.cu over ragged sequence lengths, head counts and batch
+    sizes that change the work-item walk (one / two query tiles, one / two key blocks, 1 ... 3 items per CTA, odd pair counts),
+    causal and not, against the oracle.  Two consecutive calls per shape: the second one reuses barriers / TMEM of a warm CTA
+    state only through fresh launches, but catches anything left behind in global scratch."""
+    import numpy_transformer_b200 as nt
+    from numpy_transformer_b200 import ops
+    from oracle import numpy_ref as R
+    from oracle import models as M
+    from conftest import rel_err
+    nt.init(0)
+    nt.set_gemm_mode(1)
+    rs = np.random.RandomState(7)
+    shapes = [(1, 96, 1), (3, 127, 2), (2, 129, 3), (5, 160, 1), (1, 255, 4), (7, 256, 1), (150, 72, 1), (37, 256, 4),
+              (75, 130, 2), (2, 68, 6)]
+    worst = 0.0
+    for B, N, H in shapes:
+        for causal in (True, False):
+            qkv = rs.randn(B, N, 3 * H * 64) * rs.choice([0.3, 1.0, 2.0])
+            dout = rs.randn(B, N, H * 64)
+            mask = M.causal_mask(N) if causal else None
+            O, P, _ = R.attention_fwd(qkv, H, mask)
+            ref_g = R.attention_bwd(dout, qkv, P, H)
+            kind = ops.MASK_CAUSAL if causal else ops.MASK_NONE
+            for rep in range(2):
+                qd, dd = nt.as_device(qkv), nt.as_device(dout)
+                qd._split = ops.split_bf16(qd, B * N, 3 * H * 64)[:2]
+                dd._split = ops.split_bf16(dd, B * N, H * 64)[:2]
+                out, Pd, _ = ops.attention_fwd(qd, H, None, kind)
+                g = ops.attention_bwd(dd, qd, Pd, H, kind, att_out=out)
+                assert ops._last["attention_bwd"] == "tcgen05-planes"
+                e = [rel_err(out, O), rel_err(Pd, P), rel_err(g, ref_g)]
+                worst = max(worst, max(e))
+                assert max(e) < 1e-4, (B, N, H, causal, rep, e)
+    print("attention_tcl sweep worst rel err %.2e" % worst)
