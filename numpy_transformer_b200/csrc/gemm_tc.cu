@@ -165,7 +165,9 @@ __device__ unsigned long long g_tc_times[16384 * 8];
 // Epilogue flags are template parameters: a runtime-configured epilogue costs ~8 uniform branches per
 // 4-row store group, which measured ~250 cycles per group on a path that runs once per CTA.
 template <int ACT, int DACT, bool PRE_OUT, bool ATOMIC, bool ADDEND>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// The GELU-derivative epilogue would take 68-71 registers: with 320 threads that is one CTA too many for the three co-resident
+// single-stage CTAs the forward / dX configuration runs with (65536 / (3 x 320) = 68), so those instances are capped at 64.
+__global__ void __launch_bounds__(TC_THREADS, (DACT == NT_ACT_GELU && !ATOMIC) ? 3 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
   // the two-MMA product (TcParams::wide) is only compiled into the weight-gradient instance: it needs 2 BN TMEM columns,
