@@ -251,7 +251,7 @@ def measure(workload, dp, K, W, full, local, buckets=1, min_region_s=0.6):
     e2e_s = time.perf_counter() - t0
     e2e_s_max = dp.max_over_ranks(e2e_s) if dp else e2e_s
     clocks = sampler.stop()
-    e2e = dict(value=B * world * n_steps / e2e_s_max, unit=unit, h2d_bytes_per_step=ts.h2d_bytes, d2h_bytes_per_step=4,
+    e2e = dict(value=B * world * n_steps / e2e_s_max, unit=unit, h2d_bytes_per_step=ts.h2d_bytes, d2h_bytes_per_step=ts.d2h_bytes,
                timing="host wall clock around %d public TrainStep.step() calls (batch in pinned host memory -> H2D -> step -> "
                       "D2H loss), max over ranks" % n_steps)
     res = dict(workload=workload, kind=kind, unit=unit, value=value, ms_per_step=dev_s_max / n_steps * 1e3, rounds=rounds,

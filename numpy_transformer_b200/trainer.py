@@ -213,6 +213,7 @@ class TrainStep:
                        for _ in range(2)]
         self._stage_i = 0
         self._stage_used = [False, False]
+        self._e2e_graphs = {}
         self.h_out = PinnedBuffer((8,), np.float32)
         self.h_amax = PinnedBuffer((self.rows,), np.int32)
         self.d_in = DeviceArray(self.input_shape, in_dtype)
@@ -459,10 +460,56 @@ class TrainStep:
         if inputs is not None or labels is not None:
             self._stage_i = 1 - i                 # a loader that fills h_in itself keeps addressing the same set
 
+    def _step_one_graph(self, inputs, labels):
+        """The end-to-end step as ONE graph launch: the H2D copies of the batch out of a pinned staging set, the training step
+        and the D2H copies of loss and arg-max are nodes of the same graph (three stream operations and their gaps less per
+        call than load() + run_device() + nt_d2h_async: bench.py's e2e 0.528 -> 0.51x ms on the README ViT).  One graph per
+        staging set, captured on first use; step() is synchronous, so a set is never overwritten under a running copy."""
+        i = self._stage_i
+        h_in, h_lab, ev = self._stage[i]
+        if self._stage_used[i]:
+            lib.nt_event_synchronize(ev)
+            self._stage_used[i] = False
+        if inputs is not None:
+            np.copyto(h_in.array, np.asarray(inputs).reshape(self.input_shape), casting="unsafe")
+        if labels is not None:
+            np.copyto(h_lab.array, np.asarray(labels).reshape(-1), casting="unsafe")
+        if rehome_generation() != self._gen:
+            self.arena.readopt()
+            self._gen = rehome_generation()
+            self._e2e_graphs = {}
+        g = self._e2e_graphs.get(i)
+        if g is None:
+            lib.nt_sync()
+            with keep_allocations() as keep:
+                lib.nt_graph_begin()
+                try:
+                    lib.nt_h2d(self.d_in.ptr, h_in.ptr, h_in.nbytes)
+                    lib.nt_h2d(self.d_lab.ptr, h_lab.ptr, h_lab.nbytes)
+                    self._enqueue()
+                    lib.nt_d2h_async(self.h_out.ptr, self.d_loss.ptr, 4)
+                    lib.nt_d2h_async(self.h_amax.ptr, self.d_amax.ptr, self.h_amax.nbytes)
+                finally:
+                    gg = ctypes.c_void_p()
+                    nk = ctypes.c_int(0)
+                    lib.nt_graph_end(ctypes.byref(gg), ctypes.byref(nk))
+            self._e2e_buffers = getattr(self, "_e2e_buffers", []) + [keep.buffers]
+            g = self._e2e_graphs[i] = gg
+        lib.nt_graph_launch(g)
+        self.steps_done += 1
+        if inputs is not None or labels is not None:
+            self._stage_i = 1 - i
+
     def step(self, inputs=None, labels=None, lr=None, want_argmax=False):
         """End-to-end public call: host batch in (or already in the pinned staging buffers), host loss (and argmax) out."""
         if lr is not None:
             self.set_lr(lr)
+        if (self.use_graph and self.graph is not None and os.environ.get("NTB200_E2E_GRAPH", "1") != "0"
+                and (self.dp is None or self.dp.world == 1)):
+            self._step_one_graph(inputs, labels)
+            lib.nt_sync()
+            loss = float(self.h_out.array[0])
+            return (loss, self.h_amax.array.copy()) if want_argmax else loss
         self.load(inputs, labels)
         self.run_device()
         lib.nt_d2h_async(self.h_out.ptr, self.d_loss.ptr, 4)
@@ -475,6 +522,12 @@ class TrainStep:
     @property
     def h2d_bytes(self):
         return self.h_in.nbytes + self.h_lab.nbytes
+
+    @property
+    def d2h_bytes(self):
+        """Bytes step() reads back per call: the loss, and (one-graph path) the arg-max of every row."""
+        one_graph = (self.use_graph and os.environ.get("NTB200_E2E_GRAPH", "1") != "0" and (self.dp is None or self.dp.world == 1))
+        return 4 + (self.h_amax.nbytes if one_graph else 0)
 
     def sync_layer_counters(self):
         """Bring the per-object Adam `t` (fullconnect.py:97,149) in line with the device counter."""
@@ -519,6 +572,9 @@ class TrainStep:
         if self.graph is not None:
             lib.nt_graph_destroy(self.graph)
             self.graph = None
+        for g in getattr(self, "_e2e_graphs", {}).values():
+            lib.nt_graph_destroy(g)
+        self._e2e_graphs, self._e2e_buffers = {}, []
         self._graph_buffers = None
         if self.dp is not None and getattr(self.dp, "p2p_ready", False) and self.dp.p2p_base == self.arena.grads.ptr:
             self.dp.close_p2p()                     # the peers' mappings of this arena end with it (collective)
