@@ -734,6 +734,11 @@ int gemm_tc(const GemmDesc& d, int passes, bool* handled) {
   if (d.splitk > 1) {
     // split-K fills the machine; take the widest tile without padded columns so A is re-read least
     p.BN = d.N % 128 == 0 ? 128 : (d.N % 96 == 0 ? 96 : (d.N % 64 == 0 ? 64 : (d.N >= 96 ? 128 : (d.N > 32 ? 64 : 32))));
+    // pre-split bf16 operands, one CTA per SM with a ring: 128 x 256 tiles move 25 % fewer operand bytes per FLOP, and operand
+    // delivery (not the tensor core, tools/umma_rate.cu) is what bounds these kernels — G2 weight-gradient GEMMs 9.50 -> 7.78 ms
+    { static int w256 = -1; if (w256 < 0) { const char* e = getenv("NTB200_DW_BN256"); w256 = (e && e[0] == '0') ? 0 : 1; }
+      // (a ragged last tile is accepted while it wastes < 15 %: N = 1152 -> 5 tiles instead of 9)
+      if (bf && w256 && d.N >= 256 && (long long)ceil_div(d.N, 256) * 256 * 100 <= 115LL * d.N) p.BN = 256; }
   } else {
     p.BN = pick_bn(d.M, d.N, 1);
   }
