@@ -312,20 +312,6 @@ class TrainStep:
                 run = runs[ends[i]]
                 dp_on = (self.dp is not None and self.dp.world > 1 and self._early_from is not None
                          and os.environ.get("NTB200_DP_SKIP") != "1")
-                kb = int(os.environ.get("NTB200_DP_BWD_SPLIT", "0")) if dp_on and len(run) >= 4 else 0
-                if 0 < kb < len(run):
-                    # experiment (off by default): the stack's backward as TWO launches, the later blocks' gradients
-                    # reduced on the comm stream under the launch of the first `kb` blocks.  Measured at 2 GPUs: 0.5345 ms
-                    # against 0.5222 ms for the single launch — the second launch's prologue and the extra max-over-CTAs in
-                    # the middle cost 12 us, more than the part of a 20-30 us exchange it can hide
-                    delta = fused_vit.backward_stack(run[kb:], delta)
-                    lo = self.arena.first_offset(run[kb])
-                    if lo is not None and lo < self._early_from:
-                        self.dp.allreduce_range(self.arena.grads, lo, self._early_from, side=True)
-                        self._early_from = lo
-                    delta = fused_vit.backward_stack(run[:kb], delta)
-                    i = ends[i] - 1
-                    continue
                 delta = fused_vit.backward_stack(run, delta)
                 # With the one-kernel NVLink exchange available (small arenas) the block gradients wait for the stem's and
                 # go in ONE exchange at the end of the step: an exchange costs >= 20 us at 8 GPUs whatever its size, and the
