@@ -136,6 +136,134 @@ static int linear_skinny_launch(const float* x, const float* w, const float* b, 
   return linear_skinny_launch_cl<MR, 8>(x, w, b, y, M, K, N, act, pre, residual, ln_g, ln_b);
 }
 
+// ---- backward of the same <= 16-row Linears (the gpt_character configuration: 10 token rows).  Through the tensor-core
+// tile these cost 18 us (dX) and 10 us (dW) per layer, almost all of it the fixed latency of a 128-row tile pipeline.
+// dX[M][K] = dY[M][N] W[K][N]^T (x act'(pre), + addend): one warp per weight row k — the row is read once, coalesced, and
+// dotted with the <= 16 rows of dY that sit in shared memory; exact fp32.
+template <int MR>
+__global__ void __launch_bounds__(256) linear_skinny_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                      float* __restrict__ dx, int M, int K, int N, int act,
+                                                                      const float* __restrict__ pre, const float* __restrict__ addend) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float sdy[];           // [MR][N]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < MR * N; e += 256) sdy[e] = e < M * N ? dy[e] : 0.f;
+  __syncthreads();
+  const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
+  for (int k = blockIdx.x * 8 + warp; k < K; k += gridDim.x * 8) {
+    const float* wr = w + (long long)k * N;
+    float acc[MR];
+#pragma unroll
+    for (int r = 0; r < MR; r++) acc[r] = 0.f;
+    if (vec) {
+      for (int n = 4 * lane; n < N; n += 128) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(wr + n));
+#pragma unroll
+        for (int r = 0; r < MR; r++) {
+          const float4 d = *reinterpret_cast<const float4*>(sdy + r * N + n);
+          acc[r] = fmaf(t.x, d.x, fmaf(t.y, d.y, fmaf(t.z, d.z, fmaf(t.w, d.w, acc[r]))));
+        }
+      }
+    } else {
+      for (int n = lane; n < N; n += 32) {
+        const float t = __ldg(wr + n);
+#pragma unroll
+        for (int r = 0; r < MR; r++) acc[r] = fmaf(t, sdy[r * N + n], acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < MR; r++) acc[r] = warp_sum(acc[r]);
+#pragma unroll
+    for (int r = 0; r < MR; r++)
+      if (lane == r && r < M) {
+        const long long o = (long long)r * K + k;
+        float v = acc[r];
+        if (act == NT_ACT_RELU) v = pre[o] > 0.f ? v : 0.f;
+        else if (act == NT_ACT_GELU) v *= gelu_grad_f(pre[o]);
+        if (addend) v += addend[o];
+        dx[o] = v;
+      }
+  }
+}
+
+// dW[K][N] += x[M][K]^T dY[M][N], db[N] += colsum(dY): a thread owns four columns of a strip of weight rows; dY lives in its
+// registers, x in shared memory; plain read-modify-write (every element has one owner), which keeps the reference's
+// accumulate-until-setzero semantics (fullconnect.py:118-122).
+template <int MR>
+__global__ void __launch_bounds__(128) linear_skinny_bwd_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                       float* __restrict__ dw, float* __restrict__ db, int M, int K,
+                                                                       int N, int krows) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float sx[];            // [MR][krows]
+  const int k0 = blockIdx.y * krows, kn = min(krows, K - k0);
+  for (int e = threadIdx.x; e < MR * krows; e += 128) {
+    const int r = e / krows, kk = e % krows;
+    sx[e] = (r < M && kk < kn) ? x[(long long)r * K + k0 + kk] : 0.f;
+  }
+  __syncthreads();
+  const int n = 4 * (blockIdx.x * 128 + threadIdx.x);
+  if (n >= N) return;
+  const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+  float d[MR][4];
+#pragma unroll
+  for (int r = 0; r < MR; r++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) d[r][c] = (r < M && n + c < N) ? dy[(long long)r * N + n + c] : 0.f;
+  }
+  if (db && blockIdx.y == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+      if (n + c < N) {
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < MR; r++) sum += d[r][c];
+        db[n + c] += sum;
+      }
+  }
+  for (int kk = 0; kk < kn; kk++) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int r = 0; r < MR; r++) {
+      const float xv = sx[r * krows + kk];
+      a0 = fmaf(xv, d[r][0], a0); a1 = fmaf(xv, d[r][1], a1); a2 = fmaf(xv, d[r][2], a2); a3 = fmaf(xv, d[r][3], a3);
+    }
+    float* o = dw + (long long)(k0 + kk) * N + n;
+    if (vec) {
+      float4 t = *reinterpret_cast<float4*>(o);
+      t.x += a0; t.y += a1; t.z += a2; t.w += a3;
+      *reinterpret_cast<float4*>(o) = t;
+    } else {
+      if (n < N) o[0] += a0;
+      if (n + 1 < N) o[1] += a1;
+      if (n + 2 < N) o[2] += a2;
+      if (n + 3 < N) o[3] += a3;
+    }
+  }
+}
+
+template <int MR>
+static int linear_skinny_bwd_input_launch(const float* dy, const float* w, float* dx, int M, int K, int N, int act, const float* pre,
+                                          const float* addend) {
+  const size_t smem = sizeof(float) * (size_t)MR * N;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    NT_CHECK(cudaFuncSetAttribute(linear_skinny_bwd_input_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int grid = ceil_div(K, 8) < 2 * g_sm_count ? ceil_div(K, 8) : 2 * g_sm_count;
+  NT_CHECK(launch_k(linear_skinny_bwd_input_kernel<MR>, dim3(grid), dim3(256), smem, dy, w, dx, M, K, N, act, pre, addend));
+  NT_LAUNCH_OK();
+  return 0;
+}
+template <int MR>
+static int linear_skinny_bwd_params_launch(const float* x, const float* dy, float* dw, float* db, int M, int K, int N) {
+  const int krows = 4;                 // K / 4 x N / 512 CTAs: these launches are latency-bound, spread them over the SMs
+  NT_CHECK(launch_k(linear_skinny_bwd_params_kernel<MR>, dim3(ceil_div(N, 512), ceil_div(K, krows)), dim3(128),
+                    sizeof(float) * (size_t)MR * krows, x, dy, dw, db, M, K, N, krows));
+  NT_LAUNCH_OK();
+  return 0;
+}
+
 // M <= 16 (a decode step, the heads of tiny batches, the 10-row Linears of the gpt_character config) and the row panel
 // fits shared memory
 static bool linear_skinny_ok(int M, int K) {
@@ -220,6 +348,11 @@ int nt_linear_bwd_input(const float* dy, const float* w, float* dx, int M, int K
   NT_ENTRY();
   NT_REQUIRE(M >= 0 && K > 0 && N > 0, "nt_linear_bwd_input: bad shape M=%d K=%d N=%d", M, K, N);
   NT_REQUIRE(act == 0 || pre != nullptr, "nt_linear_bwd_input: act' needs the saved pre-activation");
+  if (M >= 1 && linear_skinny_ok(M, N)) {
+    if (M <= 4) return linear_skinny_bwd_input_launch<4>(dy, w, dx, M, K, N, act, pre, addend);
+    if (M <= 8) return linear_skinny_bwd_input_launch<8>(dy, w, dx, M, K, N, act, pre, addend);
+    return linear_skinny_bwd_input_launch<16>(dy, w, dx, M, K, N, act, pre, addend);
+  }
   GemmDesc d{};
   // dx[M,K] = dy[M,N] . w[K,N]^T : contraction over N
   d.A = dy; d.B = w; d.C = dx;
@@ -233,6 +366,11 @@ int nt_linear_bwd_params(const float* x, const float* dy, float* dw, float* db, 
   NT_ENTRY();
   NT_REQUIRE(M >= 0 && K > 0 && N > 0, "nt_linear_bwd_params: bad shape M=%d K=%d N=%d", M, K, N);
   if (M == 0) return 0;
+  if (linear_skinny_ok(M, K)) {
+    if (M <= 4) return linear_skinny_bwd_params_launch<4>(x, dy, dw, db, M, K, N);
+    if (M <= 8) return linear_skinny_bwd_params_launch<8>(x, dy, dw, db, M, K, N);
+    return linear_skinny_bwd_params_launch<16>(x, dy, dw, db, M, K, N);
+  }
   GemmDesc d{};
   // dw[K,N] += x[M,K]^T . dy[M,N] : contraction over M (long), split across CTAs, atomic accumulate
   d.A = x; d.B = dy; d.C = dw;

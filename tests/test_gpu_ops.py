@@ -300,3 +300,28 @@ def test_skinny_linear_forward_and_layernorm_fusion(nt, M_, K, N):
     lib.nt_linear_ln_skinny(dx.ptr, dg.ptr, dbe.ptr, dW.ptr, db.ptr, out.ptr, M_, K, N, ops.ACT_RELU, dres.ptr)
     u = R.layernorm_fwd(x, g, be)[0]
     assert rel_err(out, np.maximum(R.linear_fwd(u, W, b), 0) + res) < 1e-5
+
+
+@pytest.mark.parametrize("M_,K,N", [(1, 192, 576), (5, 384, 26), (10, 768, 192), (16, 100, 30), (10, 192, 768), (3, 2352, 384)])
+def test_skinny_linear_backward(nt, M_, K, N):
+    """<= 16-row Linear backward (linear_skinny_bwd_input_kernel / linear_skinny_bwd_params_kernel: the 10-row layers of the
+    gpt_character configuration): dX with the fused act'(pre) and addend, dW / db accumulating over two calls
+    (fullconnect.py:118-127), vector and scalar paths, one launch each, vs the oracle."""
+    from numpy_transformer_b200 import ops, DeviceArray
+    rs = np.random.RandomState(M_ * 7 + K + N)
+    x, W, dy = rs.randn(M_, K), rs.randn(K, N) / np.sqrt(K), rs.randn(M_, N)
+    pre, add = rs.randn(M_, K), rs.randn(M_, K)
+    dW_, ddy, dpre, dadd, dx_ = (DeviceArray.from_host(a) for a in (W, dy, pre, add, x))
+    before = nt.launch_count()
+    g = ops.linear_bwd_input(ddy, dW_, ops.ACT_RELU, dpre, dadd)
+    assert nt.launch_count() - before == 1
+    ref = dy @ W.T
+    assert rel_err(g, ref * (pre > 0) + add) < 1e-5
+    assert rel_err(ops.linear_bwd_input(ddy, dW_), ref) < 1e-5
+    assert rel_err(ops.linear_bwd_input(ddy, dW_, ops.ACT_GELU, dpre), R.gelu_bwd(ref, pre)) < 1e-5
+    gw, gb = DeviceArray.zeros((K, N)), DeviceArray.zeros((N,))
+    before = nt.launch_count()
+    ops.linear_bwd_params(dx_, ddy, gw, gb)
+    assert nt.launch_count() - before == 1
+    ops.linear_bwd_params(dx_, ddy, gw, gb)
+    assert rel_err(gw, 2 * (x.T @ dy)) < 1e-5 and rel_err(gb, 2 * dy.sum(0)) < 1e-5
