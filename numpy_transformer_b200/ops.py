@@ -230,7 +230,9 @@ def attention_fwd(qkv, H, mask=None, mask_kind=MASK_NONE, residual=None, want_sc
     D = three_d // 3
     out = DeviceArray((B, N, D), host_dtype=qkv.host_dtype)
     import os
-    lean = (_lean[0] and not want_scores and os.environ.get("NTB200_ATT_TCL_BWD", "1") != "0" and B * N >= 2048
+    # (residual is None: the GPT block, whose backward hands attention_bwd the residual-free output the tcgen05 backward needs;
+    # a caller that fuses a residual here would fall back to the kernels that read P)
+    lean = (_lean[0] and not want_scores and residual is None and os.environ.get("NTB200_ATT_TCL_BWD", "1") != "0" and B * N >= 2048
             and attention_wants_planes(N, D // H, mask_kind, want_scores))
     P = None if lean else DeviceArray((B, H, N, N), host_dtype=qkv.host_dtype)
     S = P.empty_like() if want_scores else None
