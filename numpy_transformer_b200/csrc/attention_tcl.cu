@@ -418,6 +418,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tcl_fwd_kernel(Args a, const 
         }
       }
       stamp(a, n, 10);
+      // PLANES: nothing but TMA and the tensor core stands between this item and the next one's P planes, whose tail IS the
+      // staging tile — a warp that is still storing its rows must not be overtaken by another row group's softmax.  (Without
+      // planes every warp delivers q / k first, which orders the two.)
+      if constexpr (PLANES) named_bar_sync(5, TOK_THREADS);
     }
     tc_fence_before();
   }
