@@ -329,6 +329,22 @@ int nt_adam_star(float* p, float* g, float* m, float* v, size_t n, float lr, con
                  int t, const int32_t* t_dev, int zero_grad);
 int nt_increment(int32_t* counter);      /* t += 1 on device (fullconnect.py:149) */
 
+/* ---------------------------------------------------------------- phase programs (launch-bound GPT shapes) */
+/* The fused decoder block of SURVEY.md 8(b) for the shapes where a step is a chain of <= 16-row ops (gpt_character:
+ * 10 token rows; one KV-cache decode step): gpt/attdecoderblock.py:31-111 forward and backward, the stem, head and
+ * loss around it (PatchEmbed.py:132-146, net/layernorm.py, gpt/classify_gpt.py:20-28, net/loss.py:46-51) as ONE kernel.
+ * Between nt_fuse_begin and nt_fuse_end the entry points nt_linear_fwd / _ln_skinny / _bwd_input / _bwd_params,
+ * nt_layernorm_fwd / _bwd, nt_attention_fwd / _bwd (N <= 32), nt_attention_decode_at, nt_cross_entropy,
+ * nt_embedding_fwd / _bwd, nt_decode_embed, nt_argmax_next and nt_increment do not launch: each call appends one phase
+ * to a host-side program.  nt_fuse_end — or any call the program cannot express, which then runs as usual — launches
+ * the program as a single thread-block cluster that walks the phases in order, every CTA on a slice of each phase, with
+ * a cluster barrier only where a phase touches what an earlier one wrote.  Results are those of the per-op kernels to
+ * fp32 rounding (exact fp32 FMAs).  Regions nest; capturable like every other call. */
+int nt_fuse_begin(void);
+int nt_fuse_end(void);
+/* totals since start-up: program launches, phases in them, cluster barriers in them; CTAs per cluster (0 = none yet) */
+int nt_fuse_stats(long long* launches, long long* phases, long long* barriers, int* cluster_size);
+
 /* ---------------------------------------------------------------- data parallel */
 /* One NCCL communicator per process (one process per GPU).  uid is the 128-byte ncclUniqueId. */
 int nt_dp_unique_id(void* uid128);

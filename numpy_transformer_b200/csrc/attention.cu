@@ -1185,6 +1185,7 @@ int nt_attention_fwd(const float* qkv, const float* mask, int mask_kind, float* 
   NT_REQUIRE(B >= 0 && N > 0 && H > 0 && dh > 0, "nt_attention_fwd: bad shape");
   NT_REQUIRE(mask_kind != NT_MASK_DENSE || mask, "nt_attention_fwd: dense mask_kind needs a mask");
   if (B == 0) return 0;
+  NT_FUSE_TRY(nt::fuse_attn_fwd(qkv, mask_kind == NT_MASK_DENSE ? mask : nullptr, mask_kind, out, P, S, B, N, H, dh, residual));
   const int D = H * dh;
   if (nt::attention_tc_ok(N, H, dh, mask_kind, S != nullptr)) return nt::attention_fwd_tc(qkv, mask_kind, out, P, B, N, H, residual, nullptr, nullptr);
   if (nt::attention_tcl_ok(N, H, dh, mask_kind, S != nullptr)) return nt::attention_fwd_tcl(qkv, nullptr, nullptr, mask_kind, out, P, B, N, H, residual, nullptr, nullptr, nullptr);
@@ -1265,6 +1266,7 @@ int nt_attention_bwd(const float* dout, const float* qkv, const float* P, float*
   NT_ENTRY();
   NT_REQUIRE(B >= 0 && N > 0 && H > 0 && dh > 0, "nt_attention_bwd: bad shape");
   if (B == 0) return 0;
+  NT_FUSE_TRY(nt::fuse_attn_bwd(dout, qkv, P, dqkv, B, N, H, dh));
   const int D = H * dh;
   // BF16x3 kernels (attention_bf16.cu): `scratch` only carries the B*H*N softmax-backward row sums
   if (nt::attention_tc_ok(N, H, dh, mask_kind, false))
@@ -1458,6 +1460,7 @@ int nt_attention_decode_at(const float* qkv_new, float* kcache, float* vcache, f
   NT_ENTRY();
   NT_REQUIRE(B >= 0 && Tmax >= 1 && H > 0 && dh > 0 && d_pos, "nt_attention_decode_at: bad arguments");
   if (B == 0) return 0;
+  NT_FUSE_TRY(nt::fuse_attn_decode(qkv_new, kcache, vcache, out, B, Tmax, H, dh, d_pos, append));
   const size_t smem = sizeof(float) * (5 * (size_t)dh + 8 + Tmax);
   NT_REQUIRE(smem <= 48 * 1024, "nt_attention_decode_at: context %d too long", Tmax);
   NT_CHECK(nt::launch_k(attn_decode_kernel, dim3(B * H), dim3(DEC_THREADS), smem, qkv_new, kcache, vcache, out, Tmax, 0, H, dh, d_pos,

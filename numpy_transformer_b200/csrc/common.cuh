@@ -21,6 +21,36 @@ enum { NT_DEVERR_TOKEN = 1, NT_DEVERR_LABEL = 2 };
 void set_error(const char* fmt, ...);
 bool ensure_init();
 
+// Phase programs (phase_prog.cu): while g_fusing, the entry points of the ops a program can express hand their arguments
+// to the matching fuse_* hook.  0 = recorded (nothing launched), NT_FUSE_PASS = not expressible: whatever was pending has
+// been launched and the caller runs its own kernel, anything else = an error.  Every other kernel launch (launch_k) and
+// stream operation first launches what is pending, so program order is stream order.
+extern bool g_fusing;
+enum { NT_FUSE_PASS = -1 };
+int fuse_flush();
+int fuse_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int K, int N, int act, float* pre,
+                    const float* residual, const float* ln_g, const float* ln_b);
+int fuse_linear_bwd_input(const float* dy, const float* w, float* dx, int M, int K, int N, int act, const float* pre,
+                          const float* addend);
+int fuse_linear_bwd_params(const float* x, const float* dy, float* dw, float* db, int M, int K, int N);
+int fuse_ln_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int M, int D, float eps,
+                const float* post_add);
+int fuse_ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, float* dx, float* dgamma,
+                float* dbeta, int M, int D, const float* addend);
+int fuse_attn_fwd(const float* qkv, const float* mask, int mask_kind, float* out, float* P, float* S, int B, int N, int H, int dh,
+                  const float* residual);
+int fuse_attn_bwd(const float* dout, const float* qkv, const float* P, float* dqkv, int B, int N, int H, int dh);
+int fuse_cross_entropy(const float* logits, const int32_t* labels, const float* onehot, float n_norm, float* loss, float* row_loss,
+                       float* grad, float* prob, int32_t* argmax, int rows, int cols);
+int fuse_embed_fwd(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int T, int D, int vocab);
+int fuse_embed_bwd(const int32_t* idx, const float* dy, float* detok, float* depos, int B, int T, int D, int vocab);
+int fuse_decode_embed(const int32_t* idx, const float* etok, const float* epos, float* out, int B, int D, int Tmax,
+                      const int32_t* d_pos, int vocab);
+int fuse_attn_decode(const float* qkv_new, float* kc, float* vc, float* out, int B, int Tmax, int H, int dh, const int32_t* d_pos,
+                     int append);
+int fuse_argmax_next(const float* logits, int ld, int cols, int B, int32_t* tok, int32_t* hist, int hist_ld, const int32_t* d_pos);
+int fuse_increment(int32_t* counter);
+
 #define NT_CHECK(expr)                                                              \
   do {                                                                              \
     cudaError_t _e = (expr);                                                        \
@@ -51,6 +81,23 @@ bool ensure_init();
 
 #define NT_ENTRY() do { if (!nt::ensure_init()) return 3; } while (0)
 
+// in an entry point a phase program can express:  NT_FUSE_TRY(nt::fuse_xxx(args));
+#define NT_FUSE_TRY(call)                          \
+  do {                                             \
+    if (nt::g_fusing) {                            \
+      const int _r = (call);                       \
+      if (_r != nt::NT_FUSE_PASS) return _r;       \
+    }                                              \
+  } while (0)
+// in an entry point that enqueues stream work of its own (copies, memsets, collectives)
+#define NT_FUSE_FLUSH()                            \
+  do {                                             \
+    if (nt::g_fusing) {                            \
+      const int _r = nt::fuse_flush();             \
+      if (_r) return _r;                           \
+    }                                              \
+  } while (0)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -78,6 +125,7 @@ __device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wa
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  if (g_fusing && fuse_flush() != 0) return cudaErrorLaunchFailure;     // pending phases go first (text in nt_last_error)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;

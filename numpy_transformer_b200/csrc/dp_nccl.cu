@@ -151,6 +151,7 @@ int nt_p2p_setup(int rank, int world, float* my_grads, const void* grad_handles,
 int nt_p2p_allreduce_sum(size_t off, size_t n, int channel) {
   NT_ENTRY();
   NT_REQUIRE(g_p2p_ready, "nt_p2p_allreduce_sum: nt_p2p_setup has not been called");
+  NT_FUSE_FLUSH();
   NT_REQUIRE(off % 4 == 0 && n % 4 == 0 && (channel == 0 || channel == 1), "nt_p2p_allreduce_sum: off / n must be multiples of 4");
   if (n == 0) return 0;
   const size_t per4 = (n / 4 + g_p2p.world - 1) / g_p2p.world;
@@ -212,6 +213,7 @@ int nt_dp_init(const void* uid128, int rank, int world) {
 int nt_dp_allreduce_sum(float* buf, size_t n) {
   NT_ENTRY();
   NT_REQUIRE(g_comm, "nt_dp_allreduce_sum: nt_dp_init has not been called");
+  NT_FUSE_FLUSH();
   // comm stream waits for everything enqueued on the compute stream so far (the bucket's grads)
   NT_CHECK(cudaEventRecord(g_ev_ready, g_stream));
   NT_CHECK(cudaStreamWaitEvent(g_comm_stream, g_ev_ready, 0));
@@ -223,6 +225,7 @@ int nt_dp_allreduce_sum(float* buf, size_t n) {
 int nt_dp_broadcast(void* buf, size_t n, int root) {
   NT_ENTRY();
   NT_REQUIRE(g_comm, "nt_dp_broadcast: nt_dp_init has not been called");
+  NT_FUSE_FLUSH();
   NT_NCCL(ncclBroadcast(buf, buf, n, ncclFloat, root, g_comm, g_stream));
   return 0;
 }

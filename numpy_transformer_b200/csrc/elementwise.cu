@@ -427,6 +427,7 @@ int nt_embedding_fwd(const int32_t* idx, const float* etok, const float* epos, f
   NT_ENTRY();
   NT_REQUIRE(vocab > 0, "nt_embedding_fwd: num_embeddings must be positive");
   if (B * T == 0) return 0;
+  NT_FUSE_TRY(nt::fuse_embed_fwd(idx, etok, epos, out, B, T, D, vocab));
   NT_CHECK(nt::launch_k(embedding_fwd_kernel, dim3(B * T), dim3(D >= 256 ? 256 : 128), 0, idx, etok, epos, out, B * T, T, D, vocab,
                         g_dev_error));
   NT_LAUNCH_OK();
@@ -436,6 +437,7 @@ int nt_embedding_fwd(const int32_t* idx, const float* etok, const float* epos, f
 int nt_embedding_bwd(const int32_t* idx, const float* dy, float* detok, float* depos, int B, int T, int D, int vocab) {
   NT_ENTRY();
   if (B * T == 0) return 0;
+  NT_FUSE_TRY(nt::fuse_embed_bwd(idx, dy, detok, depos, B, T, D, vocab));
   if (detok) {
     NT_REQUIRE(vocab > 0, "nt_embedding_bwd: num_embeddings must be positive");
     NT_CHECK(nt::launch_k(embedding_bwd_tok_kernel, dim3(B * T), dim3(D >= 256 ? 256 : 128), 0, idx, dy, detok, B * T, D, vocab,
@@ -471,6 +473,7 @@ int nt_decode_embed(const int32_t* idx, const float* etok, const float* epos, fl
   NT_ENTRY();
   NT_REQUIRE(idx && etok && epos && out && d_pos && D > 0 && Tmax > 0 && vocab > 0, "nt_decode_embed: bad arguments");
   if (B == 0) return 0;
+  NT_FUSE_TRY(nt::fuse_decode_embed(idx, etok, epos, out, B, D, Tmax, d_pos, vocab));
   NT_CHECK(nt::launch_k(decode_embed_kernel, dim3(B), dim3(D >= 256 ? 256 : 128), 0, idx, etok, epos, out, D, Tmax, d_pos, vocab,
                         g_dev_error));
   NT_LAUNCH_OK();
@@ -481,6 +484,7 @@ int nt_argmax_next(const float* logits, int ld, int cols, int B, int32_t* tok, i
   NT_ENTRY();
   NT_REQUIRE(logits && tok && d_pos && cols > 0 && ld >= cols, "nt_argmax_next: bad arguments");
   if (B == 0) return 0;
+  NT_FUSE_TRY(nt::fuse_argmax_next(logits, ld, cols, B, tok, hist, hist_ld, d_pos));
   NT_CHECK(nt::launch_k(argmax_next_kernel, dim3(B), dim3(256), 0, logits, ld, cols, tok, hist, hist_ld, d_pos));
   NT_LAUNCH_OK();
   return 0;
@@ -488,6 +492,7 @@ int nt_argmax_next(const float* logits, int ld, int cols, int B, int32_t* tok, i
 
 int nt_increment(int32_t* counter) {
   NT_ENTRY();
+  NT_FUSE_TRY(nt::fuse_increment(counter));
   NT_CHECK(nt::launch_k(increment_kernel, dim3(1), dim3(1), 0, counter));
   NT_LAUNCH_OK();
   return 0;

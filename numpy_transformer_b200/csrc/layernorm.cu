@@ -231,6 +231,8 @@ static int ln_fwd_impl(const float* x, const float* gamma, const float* beta, fl
 
 int nt_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
                      int M, int D, float eps, const float* post_add, int period) {
+  NT_ENTRY();
+  NT_FUSE_TRY(nt::fuse_ln_fwd(x, gamma, beta, y, mean, rstd, M, D, eps, post_add));
   return ln_fwd_impl(x, gamma, beta, y, mean, rstd, M, D, eps, post_add, period, nullptr, nullptr);
 }
 
@@ -244,6 +246,8 @@ static int ln_bwd_impl(const float* dy, const float* x, const float* mean, const
 
 int nt_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                      float* dx, float* dgamma, float* dbeta, int M, int D, const float* addend) {
+  NT_ENTRY();
+  NT_FUSE_TRY(nt::fuse_ln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend));
   return ln_bwd_impl(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, D, addend, nullptr, nullptr);
 }
 

@@ -292,6 +292,7 @@ int nt_linear_fwd(const float* x, const float* w, const float* b, float* y, int 
   NT_ENTRY();
   NT_REQUIRE(M >= 0 && K > 0 && N > 0, "nt_linear_fwd: bad shape M=%d K=%d N=%d", M, K, N);
   NT_REQUIRE(act >= 0 && act <= 2, "nt_linear_fwd: act %d", act);
+  NT_FUSE_TRY(nt::fuse_linear_fwd(x, w, b, y, M, K, N, act, pre, residual, nullptr, nullptr));
   if (linear_skinny_ok(M, K)) {
     if (M <= 1) return linear_skinny_launch<1>(x, w, b, y, M, K, N, act, pre, residual);
     if (M <= 2) return linear_skinny_launch<2>(x, w, b, y, M, K, N, act, pre, residual);
@@ -335,6 +336,7 @@ int nt_linear_ln_skinny(const float* x, const float* ln_g, const float* ln_b, co
   NT_ENTRY();
   NT_REQUIRE(M >= 1 && M <= 16 && K > 0 && N > 0 && ln_g && ln_b, "nt_linear_ln_skinny: needs 1..16 rows and the LayerNorm parameters (M=%d)", M);
   NT_REQUIRE(act >= 0 && act <= 2, "nt_linear_ln_skinny: act %d", act);
+  NT_FUSE_TRY(nt::fuse_linear_fwd(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b));
   NT_REQUIRE(linear_skinny_ok(M, K), "nt_linear_ln_skinny: K=%d does not fit the row panel", K);
   if (M <= 1) return linear_skinny_launch<1>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
   if (M <= 2) return linear_skinny_launch<2>(x, w, b, y, M, K, N, act, nullptr, residual, ln_g, ln_b);
@@ -348,6 +350,7 @@ int nt_linear_bwd_input(const float* dy, const float* w, float* dx, int M, int K
   NT_ENTRY();
   NT_REQUIRE(M >= 0 && K > 0 && N > 0, "nt_linear_bwd_input: bad shape M=%d K=%d N=%d", M, K, N);
   NT_REQUIRE(act == 0 || pre != nullptr, "nt_linear_bwd_input: act' needs the saved pre-activation");
+  NT_FUSE_TRY(nt::fuse_linear_bwd_input(dy, w, dx, M, K, N, act, pre, addend));
   if (M >= 1 && linear_skinny_ok(M, N)) {
     if (M <= 4) return linear_skinny_bwd_input_launch<4>(dy, w, dx, M, K, N, act, pre, addend);
     if (M <= 8) return linear_skinny_bwd_input_launch<8>(dy, w, dx, M, K, N, act, pre, addend);
@@ -366,6 +369,7 @@ int nt_linear_bwd_params(const float* x, const float* dy, float* dw, float* db, 
   NT_ENTRY();
   NT_REQUIRE(M >= 0 && K > 0 && N > 0, "nt_linear_bwd_params: bad shape M=%d K=%d N=%d", M, K, N);
   if (M == 0) return 0;
+  NT_FUSE_TRY(nt::fuse_linear_bwd_params(x, dy, dw, db, M, K, N));
   if (linear_skinny_ok(M, K)) {
     if (M <= 4) return linear_skinny_bwd_params_launch<4>(x, dy, dw, db, M, K, N);
     if (M <= 8) return linear_skinny_bwd_params_launch<8>(x, dy, dw, db, M, K, N);

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(256) elem_loss_kernel(const float* __restrict_
 
 template <int KIND>
 static int elem_loss(const float* pred, const float* label, float* loss, float* grad, float* prob, size_t n) {
+  NT_FUSE_FLUSH();
   NT_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), g_stream));
   if (n == 0) return 0;
   size_t blocks = (n + 256 * 8 - 1) / (256 * 8);
@@ -161,6 +162,7 @@ extern "C" int nt_cross_entropy(const float* logits, const int32_t* labels, cons
   NT_REQUIRE(rows > 0 && cols > 0, "nt_cross_entropy: bad shape rows=%d cols=%d", rows, cols);
   NT_REQUIRE((labels != nullptr) != (onehot != nullptr), "nt_cross_entropy: pass exactly one of labels / onehot");
   NT_REQUIRE(n_norm > 0.f && row_loss && loss, "nt_cross_entropy: n_norm, row_loss and loss are required");
+  NT_FUSE_TRY(nt::fuse_cross_entropy(logits, labels, onehot, n_norm, loss, row_loss, grad, prob, argmax, rows, cols));
   const float inv_n = 1.0f / n_norm;
   NT_CHECK(nt::launch_k(ce_row_kernel, dim3(rows), dim3(128), 0, logits, labels, onehot, inv_n, row_loss, grad, prob, argmax, cols,
                         g_dev_error));

@@ -160,31 +160,36 @@ int nt_host_free(void* hptr) { NT_CHECK(cudaFreeHost(hptr)); return 0; }
 
 int nt_h2d(void* dst, const void* src, size_t bytes) {
   NT_ENTRY();
+  NT_FUSE_FLUSH();
   NT_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
   return 0;
 }
 int nt_d2h_async(void* dst, const void* src, size_t bytes) {
   NT_ENTRY();
+  NT_FUSE_FLUSH();
   NT_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
   return 0;
 }
 int nt_d2h(void* dst, const void* src, size_t bytes) {
   NT_ENTRY();
+  NT_FUSE_FLUSH();
   NT_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
   NT_CHECK(cudaStreamSynchronize(g_stream));
   return check_dev_error("nt_d2h");
 }
 int nt_d2d(void* dst, const void* src, size_t bytes) {
   NT_ENTRY();
+  NT_FUSE_FLUSH();
   NT_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream));
   return 0;
 }
 int nt_memset(void* dst, int value, size_t bytes) {
   NT_ENTRY();
+  NT_FUSE_FLUSH();
   NT_CHECK(cudaMemsetAsync(dst, value, bytes, g_stream));
   return 0;
 }
-int nt_sync(void) { NT_ENTRY(); NT_CHECK(cudaStreamSynchronize(g_stream)); return check_dev_error("nt_sync"); }
+int nt_sync(void) { NT_ENTRY(); NT_FUSE_FLUSH(); NT_CHECK(cudaStreamSynchronize(g_stream)); return check_dev_error("nt_sync"); }
 int nt_stream_handle(void** s) { NT_ENTRY(); *s = (void*)g_stream; return 0; }
 
 int nt_event_create(void** ev) {
@@ -197,10 +202,11 @@ int nt_event_create(void** ev) {
 int nt_event_record_external(void* ev) {
   // inside stream capture this becomes an event-record NODE whose timestamp can be read after replay
   NT_ENTRY();
+  NT_FUSE_FLUSH();
   NT_CHECK(cudaEventRecordWithFlags((cudaEvent_t)ev, g_stream, cudaEventRecordExternal));
   return 0;
 }
-int nt_event_record(void* ev) { NT_ENTRY(); NT_CHECK(cudaEventRecord((cudaEvent_t)ev, g_stream)); return 0; }
+int nt_event_record(void* ev) { NT_ENTRY(); NT_FUSE_FLUSH(); NT_CHECK(cudaEventRecord((cudaEvent_t)ev, g_stream)); return 0; }
 int nt_event_elapsed_ms(void* e0, void* e1, float* ms) {
   NT_CHECK(cudaEventSynchronize((cudaEvent_t)e1));
   NT_CHECK(cudaEventElapsedTime(ms, (cudaEvent_t)e0, (cudaEvent_t)e1));
@@ -219,6 +225,7 @@ int nt_graph_begin(void) {
 int nt_graph_end(void** graph_exec, int* n_kernel_nodes) {
   NT_ENTRY();
   NT_REQUIRE(g_capturing, "nt_graph_end: not capturing");
+  if (nt::g_fusing) nt::fuse_flush();            // a capture that ends inside a fuse region still holds everything recorded
   // whatever happens below, the capture is over when this call returns: a failed join (or a kernel launch that
   // invalidated the capture) must not leave g_capturing set / the stream in capture mode, or every later
   // nt_graph_begin would fail
@@ -254,6 +261,7 @@ int nt_graph_end(void** graph_exec, int* n_kernel_nodes) {
 }
 int nt_graph_launch(void* graph_exec) {
   NT_ENTRY();
+  NT_FUSE_FLUSH();
   GraphRec* r = (GraphRec*)graph_exec;
   NT_CHECK(cudaGraphLaunch(r->exec, g_stream));
   g_launches += r->kernels;
@@ -276,6 +284,7 @@ int nt_graph_destroy(void* graph_exec) {
 int nt_set_side_branch(int enabled) { g_side_enabled = (enabled != 0); return 0; }
 int nt_side_begin(void) {
   NT_ENTRY();
+  if (nt::g_fusing) return 0;                     // a phase program keeps program order: no side stream while recording
   if (!g_capturing || !g_side_enabled || g_side_active) return 0;
   NT_CHECK(cudaEventRecord(g_ev_fork, g_main_stream));
   NT_CHECK(cudaStreamWaitEvent(g_side_stream, g_ev_fork, 0));
@@ -312,6 +321,7 @@ int nt_get_gemm_mode(int* mode) { *mode = g_gemm_mode; return 0; }
 
 int nt_flush_l2(void) {
   NT_ENTRY();
+  NT_FUSE_FLUSH();
   if (!g_flush_buf) NT_CHECK(cudaMalloc(&g_flush_buf, kFlushBytes));
   NT_CHECK(cudaMemsetAsync(g_flush_buf, 0, kFlushBytes, g_stream));
   return 0;

@@ -96,6 +96,18 @@ class KVGenerator:
         """One decode step on the device: consumes d_tok at position *d_pos, leaves the logits in self._logits, the
         greedy next token in d_tok / d_hist[:, *d_pos + 1], and advances d_pos."""
         B, D = self.d_tok.shape[0], self.D
+        # <= 16 sequences: the whole step (embedding, every block, head, greedy choice, position counter) is recorded as ONE
+        # phase program (csrc/phase_prog.cu) instead of ~30 launches.  NTB200_FUSE=0 keeps the per-op launches.
+        program = B <= 16 and os.environ.get("NTB200_FUSE", "1") != "0"
+        if program:
+            lib.nt_fuse_begin()
+        try:
+            self._enqueue_step_ops(B, D)
+        finally:
+            if program:
+                lib.nt_fuse_end()
+
+    def _enqueue_step_ops(self, B, D):
         x = DeviceArray((B, 1, D), host_dtype=self.embed.text_embedding.host_dtype)
         lib.nt_decode_embed(self.d_tok.ptr, self.embed.text_embedding.params.ptr, self.embed.pos_embedding.params.ptr, x.ptr,
                             B, D, self.context, self.d_pos.ptr,       # token row + position row (PatchEmbed.py:132-138)

@@ -233,6 +233,9 @@ class TrainStep:
         self._vit_block_t = L["attention_layer"]
         self._layer_types = L
         self._opt_runs = self.arena.optimizer_runs(adam)
+        # launch-bound GPT shapes (<= 16 token rows: the gpt_character configuration): forward, loss and backward are recorded
+        # as ONE phase program (csrc/phase_prog.cu) instead of ~30 launches.  NTB200_FUSE=0 keeps the per-op launches.
+        self._fuse = kind == "gpt" and self.rows <= 16 and os.environ.get("NTB200_FUSE", "1") != "0"
         if dp is not None and dp.world > 1 and dp.nccl_ready:
             dp.init_p2p(self.arena.grads)           # small arenas: one-kernel NVLink all-reduce instead of an NCCL call
         self._gen = rehome_generation()
@@ -336,8 +339,14 @@ class TrainStep:
 
     def _enqueue(self):
         self._early_from = None          # arena offset from which the gradients were all-reduced early (DP only)
-        with ops.lean_attention():           # nobody reads the attention probabilities of a TrainStep (they are recomputed on demand)
-            self.logits, self.probs = self._enqueue_body()
+        if self._fuse:
+            lib.nt_fuse_begin()
+        try:
+            with ops.lean_attention():       # nobody reads the attention probabilities of a TrainStep (they are recomputed on demand)
+                self.logits, self.probs = self._enqueue_body()
+        finally:
+            if self._fuse:
+                lib.nt_fuse_end()            # launches the recorded program
         self.loss, self.argmax = self.d_loss, self.d_amax
         a = self.arena
         lib.nt_side_join()                       # weight-gradient branch must land before all-reduce / update
@@ -411,6 +420,7 @@ class TrainStep:
         per-op device durations of that replay.  Every replay is a real training step."""
         lib.nt_sync()
         lib.nt_set_side_branch(0)               # serial capture: per-op times free of side-branch interference
+        fuse, self._fuse = self._fuse, False    # per-op times need per-op launches
         with keep_allocations() as keep:
             lib.profile_begin(external=True)
             lib.nt_graph_begin()
@@ -422,6 +432,7 @@ class TrainStep:
                 nk = ctypes.c_int(0)
                 lib.nt_graph_end(ctypes.byref(g), ctypes.byref(nk))
         lib.nt_set_side_branch(1)
+        self._fuse = fuse
         self._prof_buffers = keep.buffers
         return g, recs
 
