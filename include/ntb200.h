@@ -344,6 +344,10 @@ int nt_fuse_begin(void);
 int nt_fuse_end(void);
 /* totals since start-up: program launches, phases in them, cluster barriers in them; CTAs per cluster (0 = none yet) */
 int nt_fuse_stats(long long* launches, long long* phases, long long* barriers, int* cluster_size);
+/* development aid (tools/phase_stamps.py): programs launched after this call write the SM clock at the start of every
+ * phase, at the end of its body and behind its barrier into dev_int64_buf [phase][CTA][3] (device memory, >= 64 x 16 x 3
+ * int64; NULL switches it off again) */
+int nt_fuse_debug_stamps(void* dev_int64_buf);
 
 /* ---------------------------------------------------------------- data parallel */
 /* One NCCL communicator per process (one process per GPU).  uid is the 128-byte ncclUniqueId. */

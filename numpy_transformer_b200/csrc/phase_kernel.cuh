@@ -38,6 +38,9 @@ __device__ __forceinline__ void ph_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+__device__ __forceinline__ long long ph_clock() { return clock64(); }
+#else
+static inline long long ph_clock() { return 0; }
 #endif
 
 namespace ntph {
@@ -781,8 +784,10 @@ __device__ void argmax_next(const NtPhase& ph, float* sm, int rank, int C) {
 __device__ void run_program(const NtPhaseProgram& prog) {
   float* sm = ph_smem();
   const int rank = ph_rank(), C = ph_nrank();
+  long long* stamps = reinterpret_cast<long long*>(static_cast<uintptr_t>(prog.stamps));
   for (int i = 0; i < prog.n; i++) {
     const NtPhase& ph = prog.ph[i];
+    const long long t0 = stamps ? ph_clock() : 0;
     switch (ph.op) {
       case NT_PH_LINEAR_FWD: NTPH_ROWS_DISPATCH(linear_fwd, ph.i[0], ph, sm, rank, C); break;
       case NT_PH_LINEAR_BWD_INPUT: NTPH_ROWS_DISPATCH(linear_bwd_input, ph.i[0], ph, sm, rank, C); break;
@@ -803,8 +808,17 @@ __device__ void run_program(const NtPhaseProgram& prog) {
         break;
       default: break;
     }
+    long long t1 = 0;
+    if (stamps) {                        // debug timing: the CTA's body ends when its last thread is through
+      ph_syncthreads();
+      t1 = ph_clock();
+    }
     if (ph.flags & NT_PHF_SYNC_AFTER) ph_cluster_sync();
     else ph_syncthreads();               // the next phase reuses the shared-memory staging area
+    if (stamps && ph_tid() == 0) {
+      long long* s = stamps + ((long long)i * C + rank) * 3;
+      s[0] = t0; s[1] = t1; s[2] = ph_clock();
+    }
   }
 }
 

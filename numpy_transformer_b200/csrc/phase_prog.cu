@@ -15,6 +15,7 @@ static int g_fuse_depth = 0;
 static ntph::Recorder g_rec;
 static int g_cluster = 0;                     // CTAs per cluster (= grid size); 0 until configured
 static long long g_fuse_launches = 0, g_fuse_phases = 0, g_fuse_barriers = 0;
+static void* g_stamps = nullptr;              // debug: per-phase SM clock stamps of the launches that follow
 
 __global__ void __launch_bounds__(NT_PH_THREADS, 1) phase_program_kernel(const __grid_constant__ NtPhaseProgram prog) {
   ph_prologue();
@@ -70,6 +71,7 @@ int fuse_flush() {
     const size_t n = phases.size() - done < (size_t)NT_PH_MAX_PHASES ? phases.size() - done : (size_t)NT_PH_MAX_PHASES;
     memset(&prog, 0, sizeof(prog));
     prog.n = (int)n;
+    prog.stamps = (uint64_t)reinterpret_cast<uintptr_t>(g_stamps);
     for (size_t i = 0; i < n; i++) {
       prog.ph[i] = phases[done + i];
       if (prog.ph[i].flags & NT_PHF_SYNC_AFTER) g_fuse_barriers++;
@@ -182,6 +184,11 @@ int nt_fuse_end(void) {
   const int rc = fuse_flush();
   g_fusing = false;
   return rc;
+}
+
+int nt_fuse_debug_stamps(void* dev_int64_buf) {
+  g_stamps = dev_int64_buf;
+  return 0;
 }
 
 int nt_fuse_stats(long long* launches, long long* phases, long long* barriers, int* cluster_size) {

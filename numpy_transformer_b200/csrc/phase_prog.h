@@ -48,7 +48,8 @@ struct NtPhase {
 
 struct NtPhaseProgram {
   int32_t n;
-  int32_t pad[3];
+  int32_t pad;
+  uint64_t stamps;      // debug (nt_fuse_debug_stamps): device int64 [phase][CTA][3] = SM clock at phase start / body end / barrier end
   NtPhase ph[NT_PH_MAX_PHASES];
 };
 

@@ -96,9 +96,11 @@ class KVGenerator:
         """One decode step on the device: consumes d_tok at position *d_pos, leaves the logits in self._logits, the
         greedy next token in d_tok / d_hist[:, *d_pos + 1], and advances d_pos."""
         B, D = self.d_tok.shape[0], self.D
-        # <= 16 sequences: the whole step (embedding, every block, head, greedy choice, position counter) is recorded as ONE
-        # phase program (csrc/phase_prog.cu) instead of ~30 launches.  NTB200_FUSE=0 keeps the per-op launches.
-        program = B <= 16 and os.environ.get("NTB200_FUSE", "1") != "0"
+        # <= 16 sequences: the whole step (embedding, every block, head, greedy choice, position counter) can be recorded as
+        # ONE phase program (csrc/phase_prog.cu) instead of 30 launches.  OPT-IN (NTB200_FUSE=1): one cluster of 16 SMs
+        # streams the 39 MB of weights of a poetry3000-size step slower than the per-op GEMVs spread over 48-100 SMs
+        # (0.174 vs 0.143 ms per token on B200, DESIGN.md 4.7).
+        program = B <= 16 and os.environ.get("NTB200_FUSE", "0") == "1"
         if program:
             lib.nt_fuse_begin()
         try:

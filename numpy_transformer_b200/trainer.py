@@ -233,9 +233,12 @@ class TrainStep:
         self._vit_block_t = L["attention_layer"]
         self._layer_types = L
         self._opt_runs = self.arena.optimizer_runs(adam)
-        # launch-bound GPT shapes (<= 16 token rows: the gpt_character configuration): forward, loss and backward are recorded
-        # as ONE phase program (csrc/phase_prog.cu) instead of ~30 launches.  NTB200_FUSE=0 keeps the per-op launches.
-        self._fuse = kind == "gpt" and self.rows <= 16 and os.environ.get("NTB200_FUSE", "1") != "0"
+        # launch-bound GPT shapes (<= 16 token rows: the gpt_character configuration): forward, loss and backward can be
+        # recorded as ONE phase program (csrc/phase_prog.cu, 3 launches per step instead of 33).  OPT-IN (NTB200_FUSE=1):
+        # measured on B200 the program is slower than the graph of per-op launches it replaces (0.184 vs 0.123 ms per
+        # gpt_character step) — a dependent phase costs ~5.8 us through the cluster barrier against ~4 us
+        # per kernel under programmatic dependent launch.
+        self._fuse = kind == "gpt" and self.rows <= 16 and os.environ.get("NTB200_FUSE", "0") == "1"
         if dp is not None and dp.world > 1 and dp.nccl_ready:
             dp.init_p2p(self.arena.grads)           # small arenas: one-kernel NVLink all-reduce instead of an NCCL call
         self._gen = rehome_generation()

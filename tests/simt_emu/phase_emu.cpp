@@ -35,6 +35,7 @@ int emu_run(int nctas, int reverse, int all_barriers) {
     memset(&prog, 0, sizeof(prog));
     const size_t n = g_rec.phases.size() - done < NT_PH_MAX_PHASES ? g_rec.phases.size() - done : NT_PH_MAX_PHASES;
     prog.n = (int)n;
+    prog.stamps = 0;
     for (size_t i = 0; i < n; i++) {
       prog.ph[i] = g_rec.phases[done + i];
       if (all_barriers == 1) prog.ph[i].flags |= NT_PHF_SYNC_AFTER;

@@ -30,7 +30,7 @@ def fuse_stats():
 
 
 @pytest.mark.parametrize("shape", [(2, 5, 192, 3, 1, 26), (2, 8, 16, 2, 2, 11), (1, 16, 64, 2, 2, 50)])
-def test_fused_gpt_step_vs_per_op_kernels_and_oracle(nt, shape):
+def test_fused_gpt_step_vs_per_op_kernels_and_oracle(nt, shape, monkeypatch):
     """Four SGD steps (eager, captured, two replays) of a <= 16-row GPT: the program path against the per-op kernels it
     replaces (loss and every parameter, 1e-5) and against the oracle (1e-4); launch budget of the captured step."""
     from numpy_transformer_b200 import trainer
@@ -41,10 +41,10 @@ def test_fused_gpt_step_vs_per_op_kernels_and_oracle(nt, shape):
     lr = 0.05
     runs = {}
     for fused in (False, True):
+        monkeypatch.setenv("NTB200_FUSE", "1" if fused else "0")
         layers = trainer.build_gpt_layers(B, T, D, H, L, V, adam=False, seed=0)
         ts = trainer.TrainStep(layers, "gpt", (B, T), lr, adam=False)
-        assert ts._fuse                                        # <= 16 token rows: the program path is the default
-        ts._fuse = fused
+        assert ts._fuse == fused                               # <= 16 token rows: NTB200_FUSE=1 selects the program path
         before = fuse_stats()
         losses = [ts.step(toks, labs) for _ in range(4)]
         after = fuse_stats()
@@ -52,7 +52,7 @@ def test_fused_gpt_step_vs_per_op_kernels_and_oracle(nt, shape):
         runs[fused] = (losses, leaves, ts.graph_kernels, [y - x for x, y in zip(before[:3], after[:3])])
         ts.close()
     (l0, p0, k0, s0), (l1, p1, k1, s1) = runs[False], runs[True]
-    assert s0 == [0, 0, 0]                                     # NTB200_FUSE off: nothing recorded
+    assert s0 == [0, 0, 0]                                     # per-op path: nothing recorded
     launches, phases, barriers = s1
     assert launches >= 3 and phases >= 20 * launches and barriers < phases, s1
     assert k1 <= 6 < k0, (k1, k0)

@@ -22,7 +22,7 @@ def time_step(fused, n=300):
     B, T, D, H, L, V = 2, 5, 192, 3, 1, 26
     layers = trainer.build_gpt_layers(B, T, D, H, L, V, adam=True, seed=0)
     ts = trainer.TrainStep(layers, "gpt", (B, T), 3e-3, adam=True)
-    ts._fuse = fused
+    ts._fuse = bool(fused)
     rs = np.random.RandomState(0)
     ts.load(rs.randint(0, V, (B, T)), rs.randint(0, V, (B, T)))
     for _ in range(5):
@@ -48,7 +48,7 @@ for fused in (False, True):
     ms, k, loss = time_step(fused)
     print("gpt_char step  %-9s %.4f ms/step  %2d kernels per step  (loss after the run %.5f)" % ("program" if fused else "per-op", ms, k, loss), flush=True)
 
-for fused in ("0", "1"):
+for fused in (() if "--step-only" in sys.argv else ("0", "1")):
     os.environ["NTB200_FUSE"] = fused
     layers = trainer.build_gpt_layers(1, 256, 384, 6, 5, 2350, adam=False, seed=0)
     gen = KVGenerator(layers)
