@@ -185,7 +185,7 @@ class Recorder {
                    int append) {
     if (B < 1 || B > 64 || Tmax < 1 || H < 1 || dh < 1 || !d_pos) return false;
     const int NW = NT_PH_THREADS / 32;
-    if (sizeof(float) * ((size_t)dh + (size_t)NW * dh + 2 * NW + Tmax) > NT_PH_SMEM_BYTES) return false;
+    if (sizeof(float) * ((size_t)NW * dh + 2 * NW + Tmax + 4) > NT_PH_SMEM_BYTES) return false;
     NtPhase ph = blank(NT_PH_ATTN_DECODE);
     ph.i[0] = B; ph.i[1] = Tmax; ph.i[2] = H; ph.i[3] = dh; ph.i[4] = append ? 1 : 0;
     set(ph, 0, qkv_new); set(ph, 1, kc); set(ph, 2, vc); set(ph, 3, out); set(ph, 4, d_pos);

@@ -299,6 +299,36 @@ def test_decode_steps_vs_oracle(emu):
         nxt = d_tok.copy()
 
 
+@pytest.mark.parametrize("dh,append,pos", [(72, 1, 9), (72, 0, 9), (12, 1, 140), (64, 1, 0), (3, 0, 5)])
+def test_decode_attention_phase(emu, dh, append, pos):
+    """nt_attention_decode_at alone: head widths on both sides of the value prefetch (dh <= 64 / > 64, dh % 4 != 0), more cached
+    rows than the prefetch covers, the very first position, append folded in or done beforehand."""
+    E = emu
+    rs = np.random.RandomState(dh * 7 + pos)
+    B, H, Tmax = 2, 3, 150
+    D = H * dh
+    qkv = rs.randn(B, 3 * D)
+    kc, vc = rs.randn(B, Tmax, D), rs.randn(B, Tmax, D)
+    kc[:, pos + 1:], vc[:, pos + 1:] = 7e3, -7e3                   # beyond the window: must never be read
+    want_k, want_v = kc.copy(), vc.copy()
+    want_k[:, pos], want_v[:, pos] = qkv[:, D:2 * D], qkv[:, 2 * D:]
+    if not append:
+        kc, vc = want_k.copy(), want_v.copy()                          # nt_kv_append_at ran before
+    E.reset()
+    QKV, KC, VC, OUT, POS = E.a(qkv), E.a(kc), E.a(vc), E.a(shape=(B, D)), E.a([pos], dtype=I32)
+    E.op("attention_decode_at", QKV, KC, VC, OUT, B, Tmax, H, dh, POS, append)
+    E.run(4, pos % 2)
+    q = qkv[:, :D].reshape(B, H, dh)
+    k = want_k[:, :pos + 1].reshape(B, pos + 1, H, dh)
+    v = want_v[:, :pos + 1].reshape(B, pos + 1, H, dh)
+    s = np.einsum("bhd,bjhd->bhj", q, k) / np.sqrt(dh)
+    p = np.exp(s - s.max(-1, keepdims=True))
+    p /= p.sum(-1, keepdims=True)
+    want = np.einsum("bhj,bjhd->bhd", p, v).reshape(B, D)
+    assert rel(OUT, want) < 1e-5
+    assert rel(KC, want_k) < 1e-7 and rel(VC, want_v) < 1e-7
+
+
 # ------------------------------------------------------------------------------------------------ single ops, odd shapes
 @pytest.mark.parametrize("M,K,N,act", [(1, 48, 7, 0), (3, 33, 130, 2), (10, 64, 36, 1), (16, 40, 5, 2), (7, 24, 1030, 0)])
 def test_linear_phases_odd_shapes(emu, M, K, N, act):
