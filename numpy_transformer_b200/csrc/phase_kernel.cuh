@@ -125,7 +125,8 @@ __device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C) {
   const float* ln_g = arg<const float>(ph, 6);
   const float* ln_b = arg<const float>(ph, 7);
   float* xs = sm;                                                         // [K][XS]
-  const int xs_floats = (K * XS + 3) & ~3;
+  float* sg = sm + ((K * XS + 3) & ~3);                                   // [K] gamma | [K] beta (only with ln_g)
+  const int xs_floats = ((K * XS + 3) & ~3) + (ln_g ? ((2 * K + 3) & ~3) : 0);
   float4* red = reinterpret_cast<float4*>(sm + xs_floats);                // [NG or 1][NW][RC][QP]
   const int NQ = (N + 3) >> 2, per = (NQ + C - 1) / C;
   const int q_begin = rank * per, q_end = imin(NQ, q_begin + per);
@@ -145,6 +146,7 @@ __device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C) {
     // ---- requests that do not depend on x: first weight batch, bias / residual of the outputs this thread finishes
     float wa[U][4], wb[U][4];
     load_w_batch<MT, U>(wa, w, kg, KG, K, N, n0, vec, active);
+    load_w_batch<MT, U>(wb, w, kg + KG * U, KG, K, N, n0, vec, active);
     const int er = tid / nqc, eq = tid - er * nqc;          // epilogue role: row er of each group, quad eq
     const bool fin = tid < RC * nqc;
     float eb[4] = {0.f, 0.f, 0.f, 0.f}, eres[NG][4];
@@ -172,6 +174,9 @@ __device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C) {
         const int m = e / K, k = e - m * K;
         xs[k * XS + m] = m < M ? x[e] : 0.f;
       }
+      if (ln_g) {                  // gamma / beta travel with the rows: no second round trip inside the normalisation
+        for (int k = tid; k < K; k += NT) { sg[k] = ln_g[k]; sg[K + k] = ln_b[k]; }
+      }
       ph_syncthreads();
       if (ln_g) {                  // net/layernorm.py:100-114 on the staged rows: biased variance, eps 1e-5
         for (int m = warp; m < M; m += NW) {
@@ -181,7 +186,7 @@ __device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C) {
           float q = 0.f;
           for (int k = lane; k < K; k += 32) { const float d = xs[k * XS + m] - mean; q += d * d; }
           const float rstd = 1.0f / sqrtf(warp_sum(q) / K + 1e-5f);
-          for (int k = lane; k < K; k += 32) xs[k * XS + m] = (xs[k * XS + m] - mean) * rstd * ln_g[k] + ln_b[k];
+          for (int k = lane; k < K; k += 32) xs[k * XS + m] = (xs[k * XS + m] - mean) * rstd * sg[k] + sg[K + k];
         }
         ph_syncthreads();
       }
@@ -189,8 +194,7 @@ __device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C) {
     float acc[MT][4];
 #pragma unroll
     for (int r = 0; r < MT; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
-    for (int k0 = kg; k0 < K; k0 += 2 * KG * U) {          // batch a under the loads of batch b and vice versa
-      load_w_batch<MT, U>(wb, w, k0 + KG * U, KG, K, N, n0, vec, active);
+    for (int k0 = kg; k0 < K; k0 += 2 * KG * U) {          // both batches are in flight; each is re-requested as it retires
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const int k = k0 + u * KG;
@@ -216,6 +220,7 @@ __device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C) {
           }
         }
       }
+      load_w_batch<MT, U>(wb, w, k0 + 3 * KG * U, KG, K, N, n0, vec, active);
     }
     for (int off = 16; off >= QP; off >>= 1) {
 #pragma unroll

@@ -33,7 +33,8 @@ class Recorder {
                   const float* residual, const float* ln_g, const float* ln_b) {
     if (M < 1 || M > NT_PH_MAX_ROWS || K < 1 || N < 1 || act < 0 || act > 2) return false;
     const int MT = row_tile(M), XS = MT >= 4 ? MT + 4 : MT, RC = MT < 4 ? MT : 4;
-    const size_t smem = sizeof(float) * ((((size_t)K * XS + 3) & ~(size_t)3) + (size_t)(NT_PH_THREADS / 32) * RC * 32 * 4);
+    const size_t smem = sizeof(float) * ((((size_t)K * XS + 3) & ~(size_t)3) + (ln_g ? (((size_t)2 * K + 3) & ~(size_t)3) : 0) +
+                                         (size_t)(NT_PH_THREADS / 32) * RC * 32 * 4);
     if (smem > NT_PH_SMEM_BYTES) return false;
     NtPhase ph = blank(NT_PH_LINEAR_FWD);
     ph.i[0] = M; ph.i[1] = K; ph.i[2] = N; ph.i[3] = act;

@@ -20,6 +20,9 @@ from .device import DeviceArray, keep_allocations, rehome_generation
 from . import ops
 
 
+DECODE_PROGRAM_DEFAULT = "0"        # NTB200_FUSE_DECODE / NTB200_FUSE: "1" = the decode step as one phase program
+
+
 class KVGenerator:
     """use_graph: the decode step reads its position from a device scalar, so after one eager step (sizes the pool,
     loads modules) it is captured once into a CUDA graph and every later token is one graph launch; greedy
@@ -100,7 +103,7 @@ class KVGenerator:
         # ONE phase program (csrc/phase_prog.cu) instead of 30 launches.  OPT-IN (NTB200_FUSE=1): one cluster of 16 SMs
         # streams the 39 MB of weights of a poetry3000-size step slower than the per-op GEMVs spread over 48-100 SMs
         # (0.174 vs 0.143 ms per token on B200).
-        program = B <= 16 and os.environ.get("NTB200_FUSE", "0") == "1"
+        program = B <= 16 and os.environ.get("NTB200_FUSE_DECODE", os.environ.get("NTB200_FUSE", DECODE_PROGRAM_DEFAULT)) == "1"
         if program:
             lib.nt_fuse_begin()
         try:
