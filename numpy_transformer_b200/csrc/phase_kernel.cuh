@@ -30,6 +30,9 @@ __device__ __forceinline__ void ph_syncthreads() { __syncthreads(); }
 __device__ __forceinline__ void ph_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// the two halves on their own: between them a thread may only touch what no phase of the program writes (weights, biases)
+__device__ __forceinline__ void ph_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ph_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 extern __shared__ __align__(16) float ph_smem_[];
 __device__ __forceinline__ float* ph_smem() { return ph_smem_; }
 __device__ __forceinline__ float ph_shfl_xor(float v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
@@ -109,7 +112,7 @@ __device__ __forceinline__ void load_w_batch(float (&wv)[U][4], const float* __r
 }
 
 template <int MT>
-__device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C) {
+__device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C, bool pending) {
   constexpr int XS = MT >= 4 ? MT + 4 : MT;             // row pitch of the transposed panel (bank spread for float4 reads)
   constexpr int RC = MT < 4 ? MT : 4;                   // rows per group of the cross-warp reduction
   constexpr int NG = MT / RC;                           // row groups
@@ -152,12 +155,24 @@ __device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C) {
     float eb[4] = {0.f, 0.f, 0.f, 0.f}, eres[NG][4];
 #pragma unroll
     for (int g = 0; g < NG; g++) eres[g][0] = eres[g][1] = eres[g][2] = eres[g][3] = 0.f;
+    if (fin && b) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int n = (qb + eq) * 4 + c;
+        if (n < N) eb[c] = b[n];
+      }
+    }
+    // the barrier behind the previous phase is only awaited here: weights and biases are written by no phase, so their
+    // requests are already in flight while the other CTAs arrive; everything below may depend on the previous phase
+    if (pending) {
+      ph_cluster_wait();
+      pending = false;
+    }
     if (fin) {
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         const int n = (qb + eq) * 4 + c;
         if (n < N) {
-          if (b) eb[c] = b[n];
           if (res) {
 #pragma unroll
             for (int g = 0; g < NG; g++) {
@@ -268,6 +283,7 @@ __device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C) {
       }
     }
   }
+  if (pending) ph_cluster_wait();        // a CTA that owns no columns of this phase
 }
 
 // dx[M][K] = (dy[M][N] w[K][N]^T) o act'(pre) + addend: one warp per weight row (read once, coalesced), dy in shared memory
@@ -858,6 +874,7 @@ __device__ void argmax_next(const NtPhase& ph, float* sm, int rank, int C) {
   const int32_t* d_pos = arg<const int32_t>(ph, 3);
   float* sv = sm;                                  // [NW]
   int* si = reinterpret_cast<int*>(sm + NW);       // [NW]
+  const int p = *d_pos + 1;                        // requested with the logits, not behind the reduction
   for (int row = rank; row < B; row += C) {
     float v = -kInf;
     int idx = 0x7fffffff;
@@ -872,7 +889,6 @@ __device__ void argmax_next(const NtPhase& ph, float* sm, int rank, int C) {
       for (int wp = 1; wp < NW; wp++)
         if (sv[wp] > v || (sv[wp] == v && si[wp] < idx)) { v = sv[wp]; idx = si[wp]; }
       tok[row] = idx;
-      const int p = *d_pos + 1;
       if (hist && p < hist_ld) hist[(long long)row * hist_ld + p] = idx;
     }
     ph_syncthreads();
@@ -893,11 +909,18 @@ __device__ void run_program(const NtPhaseProgram& prog) {
   float* sm = ph_smem();
   const int rank = ph_rank(), C = ph_nrank();
   long long* stamps = reinterpret_cast<long long*>(static_cast<uintptr_t>(prog.stamps));
+  bool pending = false;                  // arrived at the cluster barrier behind the previous phase, not yet waited for it
+  int op = prog.n > 0 ? prog.ph[0].op : NT_PH_NOP;
   for (int i = 0; i < prog.n; i++) {
     const NtPhase& ph = prog.ph[i];
+    const int next_op = i + 1 < prog.n ? prog.ph[i + 1].op : NT_PH_NOP;      // also warms the next descriptor's constant line
     const long long t0 = stamps ? ph_clock() : 0;
-    switch (ph.op) {
-      case NT_PH_LINEAR_FWD: NTPH_ROWS_DISPATCH(linear_fwd, ph.i[0], ph, sm, rank, C); break;
+    if (pending && op != NT_PH_LINEAR_FWD) {       // only the Linear forward has barrier-independent requests to make first
+      ph_cluster_wait();
+      pending = false;
+    }
+    switch (op) {
+      case NT_PH_LINEAR_FWD: NTPH_ROWS_DISPATCH(linear_fwd, ph.i[0], ph, sm, rank, C, pending); pending = false; break;
       case NT_PH_LINEAR_BWD_INPUT: NTPH_ROWS_DISPATCH(linear_bwd_input, ph.i[0], ph, sm, rank, C); break;
       case NT_PH_LINEAR_BWD_PARAMS: NTPH_ROWS_DISPATCH(linear_bwd_params, ph.i[0], ph, sm, rank, C); break;
       case NT_PH_LN_FWD: ln_fwd(ph, rank, C); break;
@@ -921,12 +944,21 @@ __device__ void run_program(const NtPhaseProgram& prog) {
       ph_syncthreads();
       t1 = ph_clock();
     }
-    if (ph.flags & NT_PHF_SYNC_AFTER) ph_cluster_sync();
-    else ph_syncthreads();               // the next phase reuses the shared-memory staging area
+    if (ph.flags & NT_PHF_SYNC_AFTER) {
+      if (next_op == NT_PH_LINEAR_FWD && !stamps) {
+        ph_cluster_arrive();             // the next phase waits once its weight / bias requests are out
+        pending = true;
+      } else {
+        ph_cluster_sync();
+      }
+    } else {
+      ph_syncthreads();                  // the next phase reuses the shared-memory staging area
+    }
     if (stamps && ph_tid() == 0) {
       long long* s = stamps + ((long long)i * C + rank) * 3;
       s[0] = t0; s[1] = t1; s[2] = ph_clock();
     }
+    op = next_op;
   }
 }
 
