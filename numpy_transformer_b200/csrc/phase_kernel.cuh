@@ -30,9 +30,6 @@ __device__ __forceinline__ void ph_syncthreads() { __syncthreads(); }
 __device__ __forceinline__ void ph_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// the two halves on their own: between them a thread may only touch what no phase of the program writes (weights, biases)
-__device__ __forceinline__ void ph_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void ph_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 extern __shared__ __align__(16) float ph_smem_[];
 __device__ __forceinline__ float* ph_smem() { return ph_smem_; }
 __device__ __forceinline__ float ph_shfl_xor(float v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
@@ -83,40 +80,13 @@ __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
 // ---------------------------------------------------------------------------------------------------------------- Linear
 // y[M][N] = act(LN?(x)[M][K] w[K][N] + b) + residual.  The CTA owns a contiguous run of column quads; x (transposed, zero
 // padded to MT rows) sits in shared memory; a lane is (column quad, k-group): QP = next power of two of the quads in
-// flight, 32 / QP k-groups per warp, NW warps -> the weight panel of the slice is streamed once with float4 loads;
-// k-groups fold by shuffles inside the warp, across warps through shared memory.
-//
-// A phase is latency-bound (measured: ~0.9 K cycles per DEPENDENT global round trip right behind the cluster barrier, which
-// invalidated the L1), so everything that does not depend on x is requested before x is even staged: the first batch of
-// weights, the bias and the residual of the outputs this thread will finish.  The weight batches are double-buffered
-// (batch i + 1 in flight under the FMAs of batch i) and, shared memory permitting, all row groups of the cross-warp
-// reduction go through ONE barrier pair.
-template <int MT, int U>
-__device__ __forceinline__ void load_w_batch(float (&wv)[U][4], const float* __restrict__ w, int k0, int KG, int K, int N, int n0,
-                                             bool vec, bool active) {
-#pragma unroll
-  for (int u = 0; u < U; u++) {
-    const int k = k0 + u * KG;
-    wv[u][0] = wv[u][1] = wv[u][2] = wv[u][3] = 0.f;
-    if (active && k < K) {
-      const float* wr = w + (long long)k * N + n0;
-      if (vec) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(wr));
-        wv[u][0] = t.x; wv[u][1] = t.y; wv[u][2] = t.z; wv[u][3] = t.w;
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; c++) if (n0 + c < N) wv[u][c] = __ldg(wr + c);
-      }
-    }
-  }
-}
-
+// flight, 32 / QP k-groups per warp, NW warps -> the weight panel of the slice is streamed once with float4 loads, U of
+// them in flight per thread; k-groups fold by shuffles inside the warp, across warps through shared memory.
 template <int MT>
-__device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C, bool pending) {
+__device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C) {
   constexpr int XS = MT >= 4 ? MT + 4 : MT;             // row pitch of the transposed panel (bank spread for float4 reads)
-  constexpr int RC = MT < 4 ? MT : 4;                   // rows per group of the cross-warp reduction
-  constexpr int NG = MT / RC;                           // row groups
-  constexpr int U = MT <= 2 ? 8 : (MT <= 8 ? 4 : 1);    // weight loads per batch and thread (two batches in flight)
+  constexpr int RC = MT < 4 ? MT : 4;                   // rows per cross-warp reduction round
+  constexpr int U = MT <= 2 ? 8 : (MT <= 8 ? 4 : 2);    // weight loads in flight per thread
   const int tid = ph_tid(), warp = tid >> 5, lane = tid & 31;
   const int M = ph.i[0], K = ph.i[1], N = ph.i[2], act = ph.i[3];
   const float* x = arg<const float>(ph, 0);
@@ -128,14 +98,27 @@ __device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C, bool p
   const float* ln_g = arg<const float>(ph, 6);
   const float* ln_b = arg<const float>(ph, 7);
   float* xs = sm;                                                         // [K][XS]
-  float* sg = sm + ((K * XS + 3) & ~3);                                   // [K] gamma | [K] beta (only with ln_g)
-  const int xs_floats = ((K * XS + 3) & ~3) + (ln_g ? ((2 * K + 3) & ~3) : 0);
-  float4* red = reinterpret_cast<float4*>(sm + xs_floats);                // [NG or 1][NW][RC][QP]
+  float4* red = reinterpret_cast<float4*>(sm + ((K * XS + 3) & ~3));      // [NW][RC][32]
+  for (int e = tid; e < MT * K; e += NT) {
+    const int m = e / K, k = e - m * K;
+    xs[k * XS + m] = m < M ? x[e] : 0.f;
+  }
+  ph_syncthreads();
+  if (ln_g) {                      // net/layernorm.py:100-114 on the staged rows: biased variance, eps 1e-5
+    for (int m = warp; m < M; m += NW) {
+      float s = 0.f;
+      for (int k = lane; k < K; k += 32) s += xs[k * XS + m];
+      const float mean = warp_sum(s) / K;
+      float q = 0.f;
+      for (int k = lane; k < K; k += 32) { const float d = xs[k * XS + m] - mean; q += d * d; }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / K + 1e-5f);
+      for (int k = lane; k < K; k += 32) xs[k * XS + m] = (xs[k * XS + m] - mean) * rstd * ln_g[k] + ln_b[k];
+    }
+    ph_syncthreads();
+  }
   const int NQ = (N + 3) >> 2, per = (NQ + C - 1) / C;
   const int q_begin = rank * per, q_end = imin(NQ, q_begin + per);
   const bool vec = ((N & 3) == 0) && aligned16(w);
-  bool staged = false;
-  // a CTA without columns still has to take part in nothing but the barriers of the interpreter: the loop is empty for it
   for (int qb = q_begin; qb < q_end; qb += 32) {
     const int nqc = imin(32, q_end - qb);
     int QP = 1;
@@ -143,99 +126,40 @@ __device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C, bool p
     const int ql = lane & (QP - 1), kgl = lane / QP, KGW = 32 / QP, kg = warp * KGW + kgl, KG = NW * KGW;
     const bool active = ql < nqc;
     const int n0 = (qb + ql) * 4;
-    // all row groups through one barrier pair when their partials fit next to the panel
-    const bool one_round = (size_t)(xs_floats + NG * NW * RC * QP * 4) * sizeof(float) <= (size_t)NT_PH_SMEM_BYTES;
-    const int group_stride = one_round ? NW * RC * QP : 0;
-    // ---- requests that do not depend on x: first weight batch, bias / residual of the outputs this thread finishes
-    float wa[U][4], wb[U][4];
-    load_w_batch<MT, U>(wa, w, kg, KG, K, N, n0, vec, active);
-    load_w_batch<MT, U>(wb, w, kg + KG * U, KG, K, N, n0, vec, active);
-    const int er = tid / nqc, eq = tid - er * nqc;          // epilogue role: row er of each group, quad eq
-    const bool fin = tid < RC * nqc;
-    float eb[4] = {0.f, 0.f, 0.f, 0.f}, eres[NG][4];
+    float acc[MT][4];
 #pragma unroll
-    for (int g = 0; g < NG; g++) eres[g][0] = eres[g][1] = eres[g][2] = eres[g][3] = 0.f;
-    if (fin && b) {
+    for (int r = 0; r < MT; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+    if (active) {
+      for (int k0 = kg; k0 < K; k0 += KG * U) {
+        float wv[U][4];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int n = (qb + eq) * 4 + c;
-        if (n < N) eb[c] = b[n];
-      }
-    }
-    // the barrier behind the previous phase is only awaited here: weights and biases are written by no phase, so their
-    // requests are already in flight while the other CTAs arrive; everything below may depend on the previous phase
-    if (pending) {
-      ph_cluster_wait();
-      pending = false;
-    }
-    if (fin) {
+        for (int u = 0; u < U; u++) {
+          const int k = k0 + u * KG;
+          wv[u][0] = wv[u][1] = wv[u][2] = wv[u][3] = 0.f;
+          if (k < K) {
+            const float* wr = w + (long long)k * N + n0;
+            if (vec) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(wr));
+              wv[u][0] = t.x; wv[u][1] = t.y; wv[u][2] = t.z; wv[u][3] = t.w;
+            } else {
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int n = (qb + eq) * 4 + c;
-        if (n < N) {
-          if (res) {
+              for (int c = 0; c < 4; c++) if (n0 + c < N) wv[u][c] = __ldg(wr + c);
+            }
+          }
+        }
 #pragma unroll
-            for (int g = 0; g < NG; g++) {
-              const int m = g * RC + er;
-              if (m < M) eres[g][c] = res[(long long)m * N + n];
+        for (int u = 0; u < U; u++) {
+          const int k = k0 + u * KG;
+          if (k < K) {
+#pragma unroll
+            for (int r = 0; r < MT; r++) {
+              const float xv = xs[k * XS + r];
+#pragma unroll
+              for (int c = 0; c < 4; c++) acc[r][c] = fmaf(xv, wv[u][c], acc[r][c]);
             }
           }
         }
       }
-    }
-    if (!staged) {                 // first column chunk: stage (and normalise) the rows while those loads are in flight
-      staged = true;
-      for (int e = tid; e < MT * K; e += NT) {
-        const int m = e / K, k = e - m * K;
-        xs[k * XS + m] = m < M ? x[e] : 0.f;
-      }
-      if (ln_g) {                  // gamma / beta travel with the rows: no second round trip inside the normalisation
-        for (int k = tid; k < K; k += NT) { sg[k] = ln_g[k]; sg[K + k] = ln_b[k]; }
-      }
-      ph_syncthreads();
-      if (ln_g) {                  // net/layernorm.py:100-114 on the staged rows: biased variance, eps 1e-5
-        for (int m = warp; m < M; m += NW) {
-          float s = 0.f;
-          for (int k = lane; k < K; k += 32) s += xs[k * XS + m];
-          const float mean = warp_sum(s) / K;
-          float q = 0.f;
-          for (int k = lane; k < K; k += 32) { const float d = xs[k * XS + m] - mean; q += d * d; }
-          const float rstd = 1.0f / sqrtf(warp_sum(q) / K + 1e-5f);
-          for (int k = lane; k < K; k += 32) xs[k * XS + m] = (xs[k * XS + m] - mean) * rstd * sg[k] + sg[K + k];
-        }
-        ph_syncthreads();
-      }
-    }
-    float acc[MT][4];
-#pragma unroll
-    for (int r = 0; r < MT; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
-    for (int k0 = kg; k0 < K; k0 += 2 * KG * U) {          // both batches are in flight; each is re-requested as it retires
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int k = k0 + u * KG;
-        if (active && k < K) {
-#pragma unroll
-          for (int r = 0; r < MT; r++) {
-            const float xv = xs[k * XS + r];
-#pragma unroll
-            for (int c = 0; c < 4; c++) acc[r][c] = fmaf(xv, wa[u][c], acc[r][c]);
-          }
-        }
-      }
-      load_w_batch<MT, U>(wa, w, k0 + 2 * KG * U, KG, K, N, n0, vec, active);
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int k = k0 + KG * U + u * KG;
-        if (active && k < K) {
-#pragma unroll
-          for (int r = 0; r < MT; r++) {
-            const float xv = xs[k * XS + r];
-#pragma unroll
-            for (int c = 0; c < 4; c++) acc[r][c] = fmaf(xv, wb[u][c], acc[r][c]);
-          }
-        }
-      }
-      load_w_batch<MT, U>(wb, w, k0 + 3 * KG * U, KG, K, N, n0, vec, active);
     }
     for (int off = 16; off >= QP; off >>= 1) {
 #pragma unroll
@@ -244,46 +168,40 @@ __device__ void linear_fwd(const NtPhase& ph, float* sm, int rank, int C, bool p
         for (int c = 0; c < 4; c++) acc[r][c] += ph_shfl_xor(acc[r][c], off);
     }
 #pragma unroll
-    for (int g = 0; g < NG; g++) {
-      float4* rg = red + g * group_stride;
+    for (int mc = 0; mc < MT; mc += RC) {
       if (kgl == 0 && active) {
 #pragma unroll
         for (int r = 0; r < RC; r++)
-          rg[(warp * RC + r) * QP + ql] = make_float4(acc[g * RC + r][0], acc[g * RC + r][1], acc[g * RC + r][2], acc[g * RC + r][3]);
+          red[(warp * RC + r) * 32 + ql] = make_float4(acc[mc + r][0], acc[mc + r][1], acc[mc + r][2], acc[mc + r][3]);
       }
-      if (!one_round || g == NG - 1) ph_syncthreads();
-      if (!one_round || g == NG - 1) {
+      ph_syncthreads();
+      for (int e = tid; e < RC * nqc; e += NT) {
+        const int r = e / nqc, q = e - r * nqc, m = mc + r;
+        if (m < M) {
+          float s[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int wp = 0; wp < NW; wp++) {
+            const float4 t = red[(wp * RC + r) * 32 + q];
+            s[0] += t.x; s[1] += t.y; s[2] += t.z; s[3] += t.w;
+          }
 #pragma unroll
-        for (int h = 0; h < NG; h++) {
-          if (one_round || h == g) {
-            const int m = h * RC + er;
-            if (fin && m < M) {
-              const float4* rh = red + h * group_stride;
-              float sv[4] = {0.f, 0.f, 0.f, 0.f};
-              for (int wp = 0; wp < NW; wp++) {
-                const float4 t = rh[(wp * RC + er) * QP + eq];
-                sv[0] += t.x; sv[1] += t.y; sv[2] += t.z; sv[3] += t.w;
-              }
-#pragma unroll
-              for (int c = 0; c < 4; c++) {
-                const int n = (qb + eq) * 4 + c;
-                if (n < N) {
-                  float v = sv[c] + eb[c];
-                  const long long o = (long long)m * N + n;
-                  if (pre) pre[o] = v;
-                  if (act == 1) v = fmaxf(v, 0.f);
-                  else if (act == 2) v = gelu(v);
-                  y[o] = v + eres[h][c];
-                }
-              }
+          for (int c = 0; c < 4; c++) {
+            const int n = (qb + q) * 4 + c;
+            if (n < N) {
+              float v = s[c];
+              if (b) v += b[n];
+              const long long o = (long long)m * N + n;
+              if (pre) pre[o] = v;
+              if (act == 1) v = fmaxf(v, 0.f);
+              else if (act == 2) v = gelu(v);
+              if (res) v += res[o];
+              y[o] = v;
             }
           }
         }
-        ph_syncthreads();
       }
+      ph_syncthreads();
     }
   }
-  if (pending) ph_cluster_wait();        // a CTA that owns no columns of this phase
 }
 
 // dx[M][K] = (dy[M][N] w[K][N]^T) o act'(pre) + addend: one warp per weight row (read once, coalesced), dy in shared memory
@@ -617,12 +535,9 @@ __device__ void attn_bwd(const NtPhase& ph, float* sm, int rank, int C) {
   }
 }
 
-// one new query per (sample, head) over the cached keys / values.  `append`: the item's k / v slice is also stored into
-// cache row len-1; inside this phase that row is taken from qkv_new itself, so the stores need no ordering against the
-// reads.  Latency first (see linear_fwd): the query is read straight from global memory by every thread, and the first
-// VP value rows of every warp are requested before the scores are computed, so keys, values and query are one round trip.
+// one new query per (sample, head) over the cached keys / values; `append`: the item's k / v slice is stored into cache
+// row len-1 first (the rows are re-read by the same CTA after the barrier)
 __device__ void attn_decode(const NtPhase& ph, float* sm, int rank, int C) {
-  constexpr int VP = 8;
   const int tid = ph_tid(), warp = tid >> 5, lane = tid & 31;
   const int B = ph.i[0], Tmax = ph.i[1], H = ph.i[2], dh = ph.i[3], append = ph.i[4];
   const float* qkv_new = arg<const float>(ph, 0);
@@ -632,56 +547,41 @@ __device__ void attn_decode(const NtPhase& ph, float* sm, int rank, int C) {
   const int32_t* d_pos = arg<const int32_t>(ph, 4);
   const int len = imin(*d_pos + 1, Tmax);
   const int D = H * dh;
-  float* sr = sm;                      // [2 NW]
+  float* sq = sm;                      // [dh]
+  float* so = sq + dh;                 // [NW][dh]
+  float* sr = so + NW * dh;            // [2 NW]
   float* sp = sr + 2 * NW;             // [Tmax]
-  float* so = sp + ((Tmax + 3) & ~3);  // [NW][dh]
   const float scale = 1.0f / sqrtf((float)dh);
-  const bool vec = ((dh & 3) == 0) && ((D & 3) == 0) && aligned16(kc) && aligned16(qkv_new);
-  const bool pref = dh <= 64;
+  const bool vec = ((dh & 3) == 0) && ((D & 3) == 0) && aligned16(kc);
   for (int item = rank; item < B * H; item += C) {
     const int b = item / H, h = item - b * H;
-    const float* qn = qkv_new + (long long)b * 3 * D + h * dh;     // q | + D: k | + 2 D: v of the new token
+    for (int d = tid; d < dh; d += NT) {
+      const long long qo = (long long)b * 3 * D + h * dh + d;
+      sq[d] = qkv_new[qo];
+      if (append) {
+        const long long co = ((long long)b * Tmax + (len - 1)) * D + h * dh + d;
+        kc[co] = qkv_new[qo + D];
+        vc[co] = qkv_new[qo + 2 * D];
+      }
+    }
+    ph_syncthreads();
     const float* kb = kc + (long long)b * Tmax * D + h * dh;
     const float* vb = vc + (long long)b * Tmax * D + h * dh;
-    const int jn = append ? len - 1 : -1;                            // the row that is taken from qkv_new
-    float vreg[VP][2];
-    if (pref) {
-#pragma unroll
-      for (int i = 0; i < VP; i++) {
-        const int j = warp + NW * i;
-#pragma unroll
-        for (int dd = 0; dd < 2; dd++) {
-          const int d = lane + 32 * dd;
-          float v = 0.f;
-          if (j < len && d < dh) v = (j == jn) ? qn[2 * D + d] : vb[(long long)j * D + d];
-          vreg[i][dd] = v;
-        }
-      }
-    }
     float mx = -kInf;
     for (int j = tid; j < len; j += NT) {
-      const float* kr = (j == jn) ? qn + D : kb + (long long)j * D;
+      const float* kr = kb + (long long)j * D;
       float s = 0.f;
       if (vec) {
-#pragma unroll 4
         for (int d = 0; d < dh; d += 4) {
           const float4 k4 = *reinterpret_cast<const float4*>(kr + d);
-          const float4 q4 = *reinterpret_cast<const float4*>(qn + d);
-          s = fmaf(q4.x, k4.x, s); s = fmaf(q4.y, k4.y, s); s = fmaf(q4.z, k4.z, s); s = fmaf(q4.w, k4.w, s);
+          s = fmaf(sq[d], k4.x, s); s = fmaf(sq[d + 1], k4.y, s); s = fmaf(sq[d + 2], k4.z, s); s = fmaf(sq[d + 3], k4.w, s);
         }
       } else {
-        for (int d = 0; d < dh; d++) s = fmaf(qn[d], kr[d], s);
+        for (int d = 0; d < dh; d++) s = fmaf(sq[d], kr[d], s);
       }
-      s *= scale;                                       // attdecoderblock.py:57; the new token sees every cached key
+      s *= scale;
       sp[j] = s;
       mx = fmaxf(mx, s);
-    }
-    if (append) {
-      for (int d = tid; d < dh; d += NT) {
-        const long long co = ((long long)b * Tmax + (len - 1)) * D + h * dh + d;
-        kc[co] = qn[D + d];
-        vc[co] = qn[2 * D + d];
-      }
     }
     mx = warp_max(mx);
     if (lane == 0) sr[warp] = mx;
@@ -696,34 +596,10 @@ __device__ void attn_decode(const NtPhase& ph, float* sm, int rank, int C) {
     float tot = 0.f;
     for (int wp = 0; wp < NW; wp++) tot += sr[NW + wp];
     const float inv = 1.0f / tot;
-    if (pref) {
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < VP; i++) {
-        const int j = warp + NW * i;
-        if (j < len) {
-          const float pv = sp[j];
-          a0 = fmaf(pv, vreg[i][0], a0);
-          a1 = fmaf(pv, vreg[i][1], a1);
-        }
-      }
-      for (int j = warp + NW * VP; j < len; j += NW) {
-        const float pv = sp[j];
-        const float* vr = (j == jn) ? qn + 2 * D : vb + (long long)j * D;
-        if (lane < dh) a0 = fmaf(pv, vr[lane], a0);
-        if (lane + 32 < dh) a1 = fmaf(pv, vr[lane + 32], a1);
-      }
-      if (lane < dh) so[warp * dh + lane] = a0;
-      if (lane + 32 < dh) so[warp * dh + lane + 32] = a1;
-    } else {
-      for (int d = lane; d < dh; d += 32) {
-        float acc = 0.f;
-        for (int j = warp; j < len; j += NW) {
-          const float* vr = (j == jn) ? qn + 2 * D : vb + (long long)j * D;
-          acc = fmaf(sp[j], vr[d], acc);
-        }
-        so[warp * dh + d] = acc;
-      }
+    for (int d = lane; d < dh; d += 32) {
+      float acc = 0.f;
+      for (int j = warp; j < len; j += NW) acc = fmaf(sp[j], vb[(long long)j * D + d], acc);
+      so[warp * dh + d] = acc;
     }
     ph_syncthreads();
     for (int d = tid; d < dh; d += NT) {
@@ -874,7 +750,6 @@ __device__ void argmax_next(const NtPhase& ph, float* sm, int rank, int C) {
   const int32_t* d_pos = arg<const int32_t>(ph, 3);
   float* sv = sm;                                  // [NW]
   int* si = reinterpret_cast<int*>(sm + NW);       // [NW]
-  const int p = *d_pos + 1;                        // requested with the logits, not behind the reduction
   for (int row = rank; row < B; row += C) {
     float v = -kInf;
     int idx = 0x7fffffff;
@@ -889,6 +764,7 @@ __device__ void argmax_next(const NtPhase& ph, float* sm, int rank, int C) {
       for (int wp = 1; wp < NW; wp++)
         if (sv[wp] > v || (sv[wp] == v && si[wp] < idx)) { v = sv[wp]; idx = si[wp]; }
       tok[row] = idx;
+      const int p = *d_pos + 1;
       if (hist && p < hist_ld) hist[(long long)row * hist_ld + p] = idx;
     }
     ph_syncthreads();
@@ -909,18 +785,11 @@ __device__ void run_program(const NtPhaseProgram& prog) {
   float* sm = ph_smem();
   const int rank = ph_rank(), C = ph_nrank();
   long long* stamps = reinterpret_cast<long long*>(static_cast<uintptr_t>(prog.stamps));
-  bool pending = false;                  // arrived at the cluster barrier behind the previous phase, not yet waited for it
-  int op = prog.n > 0 ? prog.ph[0].op : NT_PH_NOP;
   for (int i = 0; i < prog.n; i++) {
     const NtPhase& ph = prog.ph[i];
-    const int next_op = i + 1 < prog.n ? prog.ph[i + 1].op : NT_PH_NOP;      // also warms the next descriptor's constant line
     const long long t0 = stamps ? ph_clock() : 0;
-    if (pending && op != NT_PH_LINEAR_FWD) {       // only the Linear forward has barrier-independent requests to make first
-      ph_cluster_wait();
-      pending = false;
-    }
-    switch (op) {
-      case NT_PH_LINEAR_FWD: NTPH_ROWS_DISPATCH(linear_fwd, ph.i[0], ph, sm, rank, C, pending); pending = false; break;
+    switch (ph.op) {
+      case NT_PH_LINEAR_FWD: NTPH_ROWS_DISPATCH(linear_fwd, ph.i[0], ph, sm, rank, C); break;
       case NT_PH_LINEAR_BWD_INPUT: NTPH_ROWS_DISPATCH(linear_bwd_input, ph.i[0], ph, sm, rank, C); break;
       case NT_PH_LINEAR_BWD_PARAMS: NTPH_ROWS_DISPATCH(linear_bwd_params, ph.i[0], ph, sm, rank, C); break;
       case NT_PH_LN_FWD: ln_fwd(ph, rank, C); break;
@@ -944,21 +813,12 @@ __device__ void run_program(const NtPhaseProgram& prog) {
       ph_syncthreads();
       t1 = ph_clock();
     }
-    if (ph.flags & NT_PHF_SYNC_AFTER) {
-      if (next_op == NT_PH_LINEAR_FWD && !stamps) {
-        ph_cluster_arrive();             // the next phase waits once its weight / bias requests are out
-        pending = true;
-      } else {
-        ph_cluster_sync();
-      }
-    } else {
-      ph_syncthreads();                  // the next phase reuses the shared-memory staging area
-    }
+    if (ph.flags & NT_PHF_SYNC_AFTER) ph_cluster_sync();
+    else ph_syncthreads();               // the next phase reuses the shared-memory staging area
     if (stamps && ph_tid() == 0) {
       long long* s = stamps + ((long long)i * C + rank) * 3;
       s[0] = t0; s[1] = t1; s[2] = ph_clock();
     }
-    op = next_op;
   }
 }
 

@@ -33,8 +33,7 @@ class Recorder {
                   const float* residual, const float* ln_g, const float* ln_b) {
     if (M < 1 || M > NT_PH_MAX_ROWS || K < 1 || N < 1 || act < 0 || act > 2) return false;
     const int MT = row_tile(M), XS = MT >= 4 ? MT + 4 : MT, RC = MT < 4 ? MT : 4;
-    const size_t smem = sizeof(float) * ((((size_t)K * XS + 3) & ~(size_t)3) + (ln_g ? (((size_t)2 * K + 3) & ~(size_t)3) : 0) +
-                                         (size_t)(NT_PH_THREADS / 32) * RC * 32 * 4);
+    const size_t smem = sizeof(float) * ((((size_t)K * XS + 3) & ~(size_t)3) + (size_t)(NT_PH_THREADS / 32) * RC * 32 * 4);
     if (smem > NT_PH_SMEM_BYTES) return false;
     NtPhase ph = blank(NT_PH_LINEAR_FWD);
     ph.i[0] = M; ph.i[1] = K; ph.i[2] = N; ph.i[3] = act;
@@ -186,7 +185,7 @@ class Recorder {
                    int append) {
     if (B < 1 || B > 64 || Tmax < 1 || H < 1 || dh < 1 || !d_pos) return false;
     const int NW = NT_PH_THREADS / 32;
-    if (sizeof(float) * ((size_t)NW * dh + 2 * NW + Tmax + 4) > NT_PH_SMEM_BYTES) return false;
+    if (sizeof(float) * ((size_t)dh + (size_t)NW * dh + 2 * NW + Tmax) > NT_PH_SMEM_BYTES) return false;
     NtPhase ph = blank(NT_PH_ATTN_DECODE);
     ph.i[0] = B; ph.i[1] = Tmax; ph.i[2] = H; ph.i[3] = dh; ph.i[4] = append ? 1 : 0;
     set(ph, 0, qkv_new); set(ph, 1, kc); set(ph, 2, vc); set(ph, 3, out); set(ph, 4, d_pos);

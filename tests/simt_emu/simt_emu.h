@@ -43,7 +43,6 @@ struct Fiber {
   bool done = false;
   Barrier* wait_bar = nullptr;
   uint64_t wait_gen = 0;
-  uint64_t cluster_arrive_gen = 0;     // generation of the cluster barrier this fibre has arrived at (split arrive / wait)
 };
 
 struct Cta {
@@ -159,25 +158,6 @@ static inline int ph_rank() { return emu::self()->cta; }
 static inline int ph_nrank() { return emu::g_launch->nctas; }
 static inline void ph_syncthreads() { emu::barrier_wait(emu::g_launch->ctas[emu::self()->cta].bar); }
 static inline void ph_cluster_sync() { emu::barrier_wait(emu::g_launch->cluster_bar); }
-// split barrier: arriving counts the fibre in and returns at once — it runs on while other CTAs are still inside the
-// previous phase, so anything it reads before the wait that a phase writes shows up as stale data in the tests
-static inline void ph_cluster_arrive() {
-  emu::Barrier& b = emu::g_launch->cluster_bar;
-  emu::self()->cluster_arrive_gen = b.gen;
-  if (++b.count == b.expected) {
-    b.count = 0;
-    b.gen++;
-  }
-}
-static inline void ph_cluster_wait() {
-  emu::Barrier& b = emu::g_launch->cluster_bar;
-  emu::Fiber* f = emu::self();
-  if (b.gen == f->cluster_arrive_gen) {
-    f->wait_bar = &b;
-    f->wait_gen = f->cluster_arrive_gen;
-    emu::yield_to_scheduler();
-  }
-}
 static inline float* ph_smem() {
   unsigned char* p = emu::g_launch->ctas[emu::self()->cta].smem.data();
   return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
