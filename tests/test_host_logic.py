@@ -42,7 +42,8 @@ def test_library_is_sm100a_only_and_carries_tcgen05_tma(nt):
     for line in sass.splitlines():
         line = line.strip()
         if line.startswith("Function :"):
-            cur = per_kernel.setdefault(line.split(":", 1)[1].strip(), {"UTCHMMA": 0, "LDTM": 0, "UTMALDG": 0, "UBLKCP": 0, "HMMA": 0})
+            cur = per_kernel.setdefault(line.split(":", 1)[1].strip(), {"UTCHMMA": 0, "LDTM": 0, "UTMALDG": 0, "UBLKCP": 0, "HMMA": 0,
+                                                                        "UCGABAR_ARV": 0, "UCGABAR_WAIT": 0})
         elif cur is not None:
             for op in cur:
                 if " " + op in line or line.startswith(op):
@@ -59,6 +60,8 @@ def test_library_is_sm100a_only_and_carries_tcgen05_tma(nt):
             assert total(k, "UTCHMMA") > 0 and total(k, "LDTM") > 0 and total(k, "HMMA") == 0, k
     # the default attention forward of the GPT shapes takes its operands by TMA
     assert total("attn_tcl_fwd_kernel", "UTMALDG") > 0
+    # the phase-program kernel synchronises its CTAs with the hardware cluster barrier (barrier.cluster.arrive / wait)
+    assert total("phase_program_kernel", "UCGABAR_ARV") > 0 and total("phase_program_kernel", "UCGABAR_WAIT") > 0
 
 
 def test_reference_tree_is_the_unmodified_reference():
