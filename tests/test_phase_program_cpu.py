@@ -217,9 +217,12 @@ def test_emulator_notices_missing_cluster_barriers(emu):
     assert wrong >= 1
 
 
-def test_gpt_character_shape(emu):
-    """BASELINE.json configs[2] at its real shape: 2 x 5 tokens, D = 192, 3 heads (dh = 64), one block, 26 characters."""
-    check_gpt_step(emu, OM.GPT_CHAR, 4, 1)
+@pytest.mark.parametrize("nctas", [4, 16])
+def test_gpt_character_shape(emu, nctas):
+    """BASELINE.json configs[2] at its real shape: 2 x 5 tokens, D = 192, 3 heads (dh = 64), one block, 26 characters — on 4
+    CTAs and on the 16-CTA cluster the B200 launch uses (8192 fibres)."""
+    out, phases, barriers = check_gpt_step(emu, OM.GPT_CHAR, nctas, 1)
+    assert (phases, barriers) == (30, 22)
 
 
 def test_sixteen_rows_wide_vocabulary(emu):
