@@ -342,6 +342,35 @@ int nt_increment(int32_t* counter);      /* t += 1 on device (fullconnect.py:149
  * fp32 rounding (exact fp32 FMAs).  Regions nest; capturable like every other call. */
 int nt_fuse_begin(void);
 int nt_fuse_end(void);
+/* attdecoderblock_layer.forward / backward (gpt/attdecoderblock.py:31-75, 77-111) as ONE call each: the block's op sequence
+ * — LN, FC0 + ReLU, FC1 + x, LN1, QKV, masked attention, FCout + h, and its reverse — issued inside a fuse region.  With
+ * B*T <= 16 rows and T <= 32 that is one phase-program launch each way; any other shape runs the per-op kernels of the
+ * entry points above in the same order.  All members are DEVICE pointers; the struct itself is HOST memory.
+ * FFN width is 4 D (attdecoderblock.py:23-24), qkv columns are [q,k,v][head][dh] (:52-55). */
+typedef struct NtGptBlock {
+  const float *ln_g, *ln_b;        /* norm:   gamma, beta [D]                          attdecoderblock.py:19 */
+  const float *w0, *b0;            /* fc0:    [D,4D], [4D]                             :23 */
+  const float *w1, *b1;            /* fc1:    [4D,D], [D]                              :24 */
+  const float *ln1_g, *ln1_b;      /* norm1                                            :20 */
+  const float *wqkv, *bqkv;        /* qkvfc:  [D,3D], [3D]                             :21 */
+  const float *wo, *bo;            /* fc_out: [D,D], [D]                               :25 */
+  float *d_ln_g, *d_ln_b, *d_w0, *d_b0, *d_w1, *d_b1, *d_ln1_g, *d_ln1_b, *d_wqkv, *d_bqkv, *d_wo, *d_bo;   /* accumulate (+=) */
+  /* written by forward, read by backward */
+  float *out0, *mean0, *rstd0;     /* LN(x) [M,D] and its statistics [M]               :37 */
+  float *pre2, *out2;              /* fc0 pre-activation and ReLU output [M,4D]        :38-41 */
+  float *out6;                     /* h = x + fc1(...) [M,D]                           :45 */
+  float *outnorm, *mean1, *rstd1;  /* LN1(h)                                           :47 */
+  float *qkv;                      /* [B,T,3D]                                         :52 */
+  float *P;                        /* [B,H,T,T] softmax, the reference's atg__         :64 */
+  float *rkk;                      /* attention output before fc_out [M,D]             :68 */
+} NtGptBlock;
+/* y [B,T,D] = block(x [B,T,D]); mask (may be NULL) is the dense additive [T,T] matrix for mask_kind NT_MASK_DENSE */
+int nt_gpt_block_fwd(const NtGptBlock* blk, const float* x, float* y, int B, int T, int D, int H, const float* mask, int mask_kind);
+/* dx [B,T,D] from dy [B,T,D]; parameter gradients accumulate into the d_* members; workspace holds
+ * nt_gpt_block_bwd_workspace(B,T,D,H) floats of device memory and must differ from every other argument */
+int nt_gpt_block_bwd_workspace(int B, int T, int D, int H, size_t* floats);
+int nt_gpt_block_bwd(const NtGptBlock* blk, const float* x, const float* dy, float* dx, float* workspace, int B, int T, int D,
+                     int H, int mask_kind);
 /* totals since start-up: program launches, phases in them, cluster barriers in them; CTAs per cluster (0 = none yet) */
 int nt_fuse_stats(long long* launches, long long* phases, long long* barriers, int* cluster_size);
 /* development aid (tools/phase_stamps.py): programs launched after this call write the SM clock at the start of every

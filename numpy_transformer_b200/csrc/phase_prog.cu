@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "phase_kernel.cuh"
 #include "phase_record.h"
+#include "gpt_block.h"
 #include <cstdlib>
 
 namespace nt {
@@ -163,10 +164,70 @@ int fuse_argmax_next(const float* logits, int ld, int cols, int B, int32_t* tok,
 }
 int fuse_increment(int32_t* counter) { return recorded_or_pass(g_rec.increment(counter)); }
 
+// the decoder block's op sequence (gpt_block.h) over the library's own entry points
+struct LibOps {
+  static int ln_fwd(const float* x, const float* g, const float* b, float* y, float* mean, float* rstd, int M, int D) {
+    return nt_layernorm_fwd(x, g, b, y, mean, rstd, M, D, 1e-5f, nullptr, 0);          // net/layernorm.py:86
+  }
+  static int ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* g, float* dx, float* dg,
+                    float* db, int M, int D, const float* addend) {
+    return nt_layernorm_bwd(dy, x, mean, rstd, g, dx, dg, db, M, D, addend);
+  }
+  static int linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int K, int N, int act, float* pre,
+                        const float* residual) {
+    return nt_linear_fwd(x, w, b, y, M, K, N, act, pre, residual);
+  }
+  static int linear_bwd_input(const float* dy, const float* w, float* dx, int M, int K, int N, int act, const float* pre,
+                              const float* addend) {
+    return nt_linear_bwd_input(dy, w, dx, M, K, N, act, pre, addend);
+  }
+  static int linear_bwd_params(const float* x, const float* dy, float* dw, float* db, int M, int K, int N) {
+    return nt_linear_bwd_params(x, dy, dw, db, M, K, N);
+  }
+  static int attn_fwd(const float* qkv, const float* mask, int mask_kind, float* out, float* P, int B, int N, int H, int dh) {
+    return nt_attention_fwd(qkv, mask, mask_kind, out, P, nullptr, B, N, H, dh, nullptr);
+  }
+  static int attn_bwd(const float* dout, const float* qkv, const float* P, float* dqkv, float* scratch, int B, int N, int H, int dh,
+                      int mask_kind) {
+    return nt_attention_bwd(dout, qkv, P, dqkv, scratch, B, N, H, dh, mask_kind);
+  }
+};
+
 }  // namespace nt
 using namespace nt;
 
 extern "C" {
+
+int nt_gpt_block_fwd(const NtGptBlock* blk, const float* x, float* y, int B, int T, int D, int H, const float* mask, int mask_kind) {
+  NT_ENTRY();
+  NT_REQUIRE(blk && x && y && B >= 0 && T > 0 && D > 0 && H > 0 && D % H == 0, "nt_gpt_block_fwd: bad arguments (D %d, heads %d)", D, H);
+  NT_REQUIRE(mask_kind != NT_MASK_DENSE || mask, "nt_gpt_block_fwd: dense mask_kind needs a mask");
+  if (B == 0) return 0;
+  int rc = nt_fuse_begin();
+  if (rc) return rc;
+  rc = ntgpt::block_fwd<LibOps>(*blk, x, y, B, T, D, H, mask_kind == NT_MASK_DENSE ? mask : nullptr, mask_kind);
+  const int rc_end = nt_fuse_end();
+  return rc ? rc : rc_end;
+}
+
+int nt_gpt_block_bwd_workspace(int B, int T, int D, int H, size_t* floats) {
+  NT_REQUIRE(floats && B >= 0 && T > 0 && D > 0 && H > 0, "nt_gpt_block_bwd_workspace: bad arguments");
+  *floats = ntgpt::bwd_workspace_floats(B, T, D, H);
+  return 0;
+}
+
+int nt_gpt_block_bwd(const NtGptBlock* blk, const float* x, const float* dy, float* dx, float* workspace, int B, int T, int D,
+                     int H, int mask_kind) {
+  NT_ENTRY();
+  NT_REQUIRE(blk && x && dy && dx && workspace && B >= 0 && T > 0 && D > 0 && H > 0 && D % H == 0,
+             "nt_gpt_block_bwd: bad arguments (D %d, heads %d)", D, H);
+  if (B == 0) return 0;
+  int rc = nt_fuse_begin();
+  if (rc) return rc;
+  rc = ntgpt::block_bwd<LibOps>(*blk, x, dy, dx, workspace, B, T, D, H, mask_kind);
+  const int rc_end = nt_fuse_end();
+  return rc ? rc : rc_end;
+}
 
 int nt_fuse_begin(void) {
   NT_ENTRY();

@@ -4,6 +4,7 @@
 #include "simt_emu.h"
 #include "../../numpy_transformer_b200/csrc/phase_kernel.cuh"
 #include "../../numpy_transformer_b200/csrc/phase_record.h"
+#include "../../numpy_transformer_b200/csrc/gpt_block.h"
 
 namespace emu { Launch* g_launch = nullptr; }
 
@@ -100,5 +101,41 @@ int emu_argmax_next(const float* logits, int ld, int cols, int B, int32_t* tok, 
   return g_rec.argmax_next(logits, ld, cols, B, tok, hist, hist_ld, d_pos) ? 0 : -1;
 }
 int emu_increment(int32_t* counter) { return g_rec.increment(counter) ? 0 : -1; }
+
+// gpt_block.h (what nt_gpt_block_fwd / nt_gpt_block_bwd issue) over the recorder
+struct EmuOps {
+  static int ln_fwd(const float* x, const float* g, const float* b, float* y, float* mean, float* rstd, int M, int D) {
+    return g_rec.ln_fwd(x, g, b, y, mean, rstd, M, D, 1e-5f, nullptr) ? 0 : -1;
+  }
+  static int ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* g, float* dx, float* dg,
+                    float* db, int M, int D, const float* addend) {
+    return g_rec.ln_bwd(dy, x, mean, rstd, g, dx, dg, db, M, D, addend) ? 0 : -1;
+  }
+  static int linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int K, int N, int act, float* pre,
+                        const float* residual) {
+    return g_rec.linear_fwd(x, w, b, y, M, K, N, act, pre, residual, nullptr, nullptr) ? 0 : -1;
+  }
+  static int linear_bwd_input(const float* dy, const float* w, float* dx, int M, int K, int N, int act, const float* pre,
+                              const float* addend) {
+    return g_rec.linear_bwd_input(dy, w, dx, M, K, N, act, pre, addend) ? 0 : -1;
+  }
+  static int linear_bwd_params(const float* x, const float* dy, float* dw, float* db, int M, int K, int N) {
+    return g_rec.linear_bwd_params(x, dy, dw, db, M, K, N) ? 0 : -1;
+  }
+  static int attn_fwd(const float* qkv, const float* mask, int mask_kind, float* out, float* P, int B, int N, int H, int dh) {
+    return g_rec.attn_fwd(qkv, mask, mask_kind, out, P, nullptr, B, N, H, dh, nullptr) ? 0 : -1;
+  }
+  static int attn_bwd(const float* dout, const float* qkv, const float* P, float* dqkv, float*, int B, int N, int H, int dh, int) {
+    return g_rec.attn_bwd(dout, qkv, P, dqkv, B, N, H, dh) ? 0 : -1;
+  }
+};
+int emu_gpt_block_fwd(const NtGptBlock* blk, const float* x, float* y, int B, int T, int D, int H, int mask_kind) {
+  return ntgpt::block_fwd<EmuOps>(*blk, x, y, B, T, D, H, nullptr, mask_kind);
+}
+size_t emu_gpt_block_bwd_workspace(int B, int T, int D, int H) { return ntgpt::bwd_workspace_floats(B, T, D, H); }
+int emu_gpt_block_bwd(const NtGptBlock* blk, const float* x, const float* dy, float* dx, float* ws, int B, int T, int D, int H,
+                      int mask_kind) {
+  return ntgpt::block_bwd<EmuOps>(*blk, x, dy, dx, ws, B, T, D, H, mask_kind);
+}
 
 }  // extern "C"

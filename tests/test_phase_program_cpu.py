@@ -417,3 +417,75 @@ def test_label_out_of_range_sets_the_error_flag(emu):
     E.op("cross_entropy", logits, lab, None, 3.0, loss, row_loss, grad, prob, amax, 3, 6)
     E.run(2, 0)
     assert E.dll.emu_err_flag() == 2 and row_loss[1] == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ nt_gpt_block_fwd / _bwd
+_BLOCK_FIELDS = ["ln_g", "ln_b", "w0", "b0", "w1", "b1", "ln1_g", "ln1_b", "wqkv", "bqkv", "wo", "bo",
+                 "d_ln_g", "d_ln_b", "d_w0", "d_b0", "d_w1", "d_b1", "d_ln1_g", "d_ln1_b", "d_wqkv", "d_bqkv", "d_wo", "d_bo",
+                 "out0", "mean0", "rstd0", "pre2", "out2", "out6", "outnorm", "mean1", "rstd1", "qkv", "P", "rkk"]
+
+
+class NtGptBlock(ctypes.Structure):
+    """Mirror of `struct NtGptBlock` (include/ntb200.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in _BLOCK_FIELDS]
+
+
+def test_header_struct_matches_the_mirror():
+    import re
+    src = open(os.path.join(os.path.dirname(HERE), "include", "ntb200.h")).read()
+    body = re.search(r"typedef struct NtGptBlock \{(.*?)\} NtGptBlock;", src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\*\s*(\w+)", body)
+    assert names == _BLOCK_FIELDS
+
+
+@pytest.mark.parametrize("B,T,D,H,mask_kind", [(2, 5, 32, 2, 1), (1, 16, 48, 3, 0)])
+def test_gpt_block_entry_points_vs_oracle(emu, B, T, D, H, mask_kind):
+    """The op sequence behind nt_gpt_block_fwd / nt_gpt_block_bwd (csrc/gpt_block.h, shared by the library and the emulator build)
+    against oracle.models.gpt_block_fwd / gpt_block_bwd: output, saved activations, input gradient and all twelve parameter
+    gradients, accumulated on top of what the buffers held."""
+    E = emu
+    rs = np.random.RandomState(B * 100 + T)
+    M, F = B * T, 4 * D
+
+    def fc(i, o):
+        return [rs.randn(i, o) / np.sqrt(i), rs.randn(o) * 0.1]
+    blk = [[1 + 0.1 * rs.randn(D), 0.1 * rs.randn(D)], fc(D, 3 * D), [1 + 0.1 * rs.randn(D), 0.1 * rs.randn(D)], fc(D, F), fc(F, D), fc(D, D)]
+    (g0, b0), (Wqkv, bqkv), (g1, b1), (W0, bb0), (W1, bb1), (Wo, bo) = blk
+    x, dy = rs.randn(B, T, D), rs.randn(B, T, D)
+    mask = OM.causal_mask(T) if mask_kind == 1 else None
+    want_y, c = OM.gpt_block_fwd(x, blk, H, mask)
+    want_dx, want_g = OM.gpt_block_bwd(dy, blk, c, H)
+    E.reset()
+    k = NtGptBlock()
+    params = dict(ln_g=g0, ln_b=b0, w0=W0, b0=bb0, w1=W1, b1=bb1, ln1_g=g1, ln1_b=b1, wqkv=Wqkv, bqkv=bqkv, wo=Wo, bo=bo)
+    held = {}
+    for n, v in params.items():
+        held[n] = E.a(v)
+        held["d_" + n] = E.a(rs.randn(*np.shape(v)))                     # gradients accumulate on top of this
+    start = {n: held["d_" + n].copy() for n in params}
+    shapes = dict(out0=(M, D), mean0=(M,), rstd0=(M,), pre2=(M, F), out2=(M, F), out6=(M, D), outnorm=(M, D), mean1=(M,), rstd1=(M,),
+                  qkv=(M, 3 * D), P=(B, H, T, T), rkk=(M, D))
+    for n, shp in shapes.items():
+        held[n] = E.a(shape=shp)
+    for n in _BLOCK_FIELDS:
+        setattr(k, n, held[n].ctypes.data)
+    X, DY, Y, DX = E.a(x), E.a(dy), E.a(shape=(M, D)), E.a(shape=(M, D))
+    E.dll.emu_gpt_block_bwd_workspace.restype = ctypes.c_size_t
+    ws = E.a(shape=(E.dll.emu_gpt_block_bwd_workspace(B, T, D, H),))
+    assert ws.size == 11 * M * D
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    assert E.dll.emu_gpt_block_fwd(ctypes.byref(k), p(X), p(Y), B, T, D, H, mask_kind) == 0
+    assert E.counts()[0] == 7
+    E.run(4, 0)
+    assert rel(Y, want_y.reshape(M, D)) < 1e-5
+    assert rel(held["qkv"], c["qkv"].reshape(M, 3 * D)) < 1e-5 and rel(held["P"], np.asarray(c["P"]).reshape(B, H, T, T)) < 1e-5
+    assert rel(held["out6"], c["h"].reshape(M, D)) < 1e-5 and rel(held["pre2"], c["pre"].reshape(M, F)) < 1e-5
+    assert E.dll.emu_gpt_block_bwd(ctypes.byref(k), p(X), p(DY), p(DX), p(ws), B, T, D, H, mask_kind) == 0
+    assert E.counts()[0] == 11
+    E.run(3, 1)
+    assert rel(DX, want_dx.reshape(M, D)) < 1e-5
+    order = [("ln_g", "ln_b"), ("wqkv", "bqkv"), ("ln1_g", "ln1_b"), ("w0", "b0"), ("w1", "b1"), ("wo", "bo")]
+    for (wn, bn), (gw, gb) in zip(order, want_g):
+        assert rel(held["d_" + wn] - start[wn], np.asarray(gw).reshape(start[wn].shape)) < 2e-5, wn
+        assert rel(held["d_" + bn] - start[bn], np.asarray(gb).reshape(start[bn].shape)) < 2e-5, bn
